@@ -1,0 +1,69 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE ONLY.
+#
+# Builds, from the reference sources WHERE THEY LIE under /root/reference
+# (nothing is copied into this repository), two artefacts into oracle/_ref/
+# (git-ignored, but shipped to the GPU box by gpurun):
+#
+#   oracle/_ref/libgraspa_ref_host.so   host harness around the reference's own
+#                                       PBC / VDW / CoulombReal / Ewald_Total /
+#                                       tail-correction routines (ref_harness.cu
+#                                       #includes the reference headers)
+#   oracle/_ref/graspa_ref_cuda.x       the reference's own CUDA program, built
+#                                       for sm_100 (the "reference CUDA build on
+#                                       the same B200" baseline of BASELINE.md 2a)
+#   oracle/_ref/examples/<name>/        the example input decks the baseline
+#                                       binary is run on (input data, not code)
+#
+# The reference's own build system (nvc++ scripts) is NOT used: only nvcc on
+# its five translation units, as BASELINE.md 2a records.  The full-binary
+# build needs one narrowing cast (mc_swap_moves.h:268), applied to a scratch
+# copy under /tmp, never to /root/reference.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${GRASPA_REFERENCE:-/root/reference}"
+OUT="$HERE/_ref"
+WHAT="${1:-all}"
+if [ ! -d "$REF/src_clean" ]; then
+  echo "build_ref.sh: $REF/src_clean not present; keeping prebuilt oracle/_ref as is"
+  exit 0
+fi
+mkdir -p "$OUT"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+
+if [ "$WHAT" = "all" ] || [ "$WHAT" = "host" ]; then
+  echo "[build_ref] host harness"
+  "$NVCC" -O2 -std=c++20 -arch=sm_100 --expt-relaxed-constexpr -w \
+      -Xcompiler -fopenmp -Xcompiler -fPIC -shared -x cu \
+      -I"$REF/src_clean" "$HERE/ref_harness.cu" -o "$OUT/libgraspa_ref_host.so"
+fi
+
+if [ "$WHAT" = "all" ] || [ "$WHAT" = "examples" ]; then
+  echo "[build_ref] example decks"
+  for ex in Henrys_coefficient CO2-MFI CO2_NaX_Zeolite XeKr-Mixture; do
+    mkdir -p "$OUT/examples/$ex"
+    # inputs only: no committed outputs, no restart dumps
+    find "$REF/Examples/$ex" -maxdepth 1 -type f \
+        \( -name '*.def' -o -name '*.cif' -o -name 'simulation.input' \) \
+        -exec cp {} "$OUT/examples/$ex/" \;
+  done
+fi
+
+if [ "$WHAT" = "all" ] || [ "$WHAT" = "cuda" ]; then
+  echo "[build_ref] reference CUDA program (sm_100)"
+  SCR="$(mktemp -d /tmp/graspa_ref_build.XXXXXX)"
+  cp -r "$REF/src_clean/." "$SCR/"
+  chmod -R u+w "$SCR"
+  # the one accommodation nvcc needs: size_t -> int narrowing in a braced init
+  sed -i '268s/{OLDComponent, OLDMolInComponent}/{(int) OLDComponent, (int) OLDMolInComponent}/' "$SCR/mc_swap_moves.h"
+  FLAGS="-O3 -std=c++20 -arch=sm_100 --expt-relaxed-constexpr -w -Xcompiler -fopenmp -rdc=true -x cu"
+  ( cd "$SCR"
+    for f in axpy.cu main.cpp read_data.cpp data_struct.cpp VDW_Coulomb.cu; do
+      "$NVCC" $FLAGS -c "$f" -o "${f%.*}.o" &
+    done
+    wait
+    "$NVCC" -arch=sm_100 -rdc=true -Xcompiler -fopenmp main.o read_data.o axpy.o data_struct.o VDW_Coulomb.o -o "$OUT/graspa_ref_cuda.x"
+  )
+  rm -rf "$SCR"
+fi
+echo "[build_ref] done: $(ls "$OUT")"
