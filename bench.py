@@ -1,0 +1,243 @@
+#!/usr/bin/env python
+"""bench.py -- Widom insertions/s of the B200-native gRASPA energy engine (BASELINE.json north_star).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the CPU arm: oracle port on the host cores)
+
+Workload (config.workload): BASELINE.json configs[4] -- synthetic 4x4x4 Mg-MOF-74 supercell (3456 framework atoms,
+triclinic, Ewald 5800 k-vectors), CO2 Widom insertions with 10 trial positions + 10 trial orientations, FP64.
+One "step" = one batch of --batch ghost insertions per GPU through Insertion_Body's whole path (first bead, chain,
+Rosenbluth selection, Ewald Fourier delta, tail, block sums).  Insertions are independent, so ranks take disjoint
+index ranges (weak scaling: fixed per-GPU batch) and only the block sums are all-reduced over NCCL.
+
+value : inputs (random pool, uniforms) already resident in HBM; sums read back.
+e2e   : the same step through the C ABI with HOST (pinned) buffers: H2D of the randoms and D2H of the sums inside
+        the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests.conftest import load_config  # noqa: E402  (fixture loader only: committed .npz, no oracle)
+
+METRIC = "widom_insertions_per_s"
+UNIT = "insertions/s"
+WORKLOAD = "synthetic 4x4x4 Mg-MOF-74 supercell (3456 atoms, 5800 k), CO2 Widom, 10 positions + 10 orientations, FP64"
+
+
+def flops_per_insertion(counts, n, triclinic=True, natoms_mol=3):
+    """SURVEY section 8(d) nominal flop count: F_pair = Npairs*(44|20) + Nvdw*17 + Ncoul*9 + 2*Nin;
+    Fourier: (17*n_atoms + 55) per active k."""
+    pairs, nvdw, ncoul, nin, act_atoms = [float(c) / n for c in counts]
+    f_pair = pairs * (44.0 if triclinic else 20.0) + nvdw * 17.0 + ncoul * 9.0 + 2.0 * nin
+    nact = act_atoms / natoms_mol
+    f_k = nact * (17.0 * natoms_mol + 55.0)
+    return f_pair, f_k
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index; self.stop_flag = False; self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def oracle_setup(box, ff, s, z, comp):
+    from oracle import oracle as orc
+    orc.build()
+    return orc, orc.WidomSetup(box, ff, s, comp, float(z["beta"]), 10, 10, z["sf_ads"], z["sf_fw"])
+
+
+def cpu_sample(box, ff, s, z, comp, target_s=12.0, seed=7):
+    """oracle Widom batch on the host cores, bounded to ~target_s seconds; also yields the per-insertion pair counts"""
+    orc, ws = oracle_setup(box, ff, s, z, comp)
+    rng = np.random.default_rng(seed)
+    n0 = 64 * max(1, orc.max_threads() // 8)
+    t0 = time.perf_counter(); orc.widom_batch(ws, rng.random((n0, 20, 3)), rng.random((n0, 2))); dt = time.perf_counter() - t0
+    n = int(max(n0, min(200000, n0 * target_s / max(dt, 1e-3))))
+    rnd = rng.random((n, 20, 3)); uni = rng.random((n, 2))
+    t0 = time.perf_counter(); out, stage, counts = orc.widom_batch(ws, rnd, uni); dt = time.perf_counter() - t0
+    return dict(value=n / dt, n=n, seconds=dt, cores=orc.max_threads(), counts=[int(c) for c in counts], mean_W=float(out[:, 0].mean()))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    box, ff, s, z = load_config("E")
+    comp = int(z["comp"])
+    orc, ws = oracle_setup(box, ff, s, z, comp)
+    rng = np.random.default_rng(17)
+    # bounded sample per step: sized from a probe so that warmup+steps stay within a few minutes
+    n0 = 64
+    t0 = time.perf_counter(); orc.widom_batch(ws, rng.random((n0, 20, 3)), rng.random((n0, 2))); rate = n0 / (time.perf_counter() - t0)
+    per_step = int(max(64, min(100000, rate * 60.0 / max(1, args.steps + args.warmup))))
+    rnd = rng.random((per_step, 20, 3)); uni = rng.random((per_step, 2))
+    for _ in range(args.warmup):
+        orc.widom_batch(ws, rnd, uni)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.widom_batch(ws, rnd, uni)
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "insertions_per_step": per_step},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.max_threads(), "kind": "port",
+                             "sample": f"{per_step} insertions/step x {args.steps} steps of the same workload, OpenMP over insertions"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=400000, help="Widom insertions per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from graspa_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: graspa_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    box, ff, s, z = load_config("E")
+    comp = int(z["comp"]); B = args.batch
+    eng = engine.Engine(local).setup(box, ff, s, float(z["beta"]), 10, 10)
+    eng.total_ewald(store=True)                                  # structure factors built on the GPU
+    eng.set_exclusion_constants(comp, float(z["excl"][0]), float(z["excl"][1]))
+    fp64_peak = eng.measure_fp64_peak()
+
+    # ---- synthetic inputs: this rank's contiguous index range of the job
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1234 + rank)
+    d_pool = torch.rand((B * 20, 3), dtype=torch.float64, device="cuda", generator=gen)
+    d_uni = torch.rand((B, 2), dtype=torch.float64, device="cuda", generator=gen)
+    h_pool = torch.empty((B * 20, 3), dtype=torch.float64).pin_memory(); h_pool.copy_(d_pool)
+    h_uni = torch.empty((B, 2), dtype=torch.float64).pin_memory(); h_uni.copy_(d_uni)
+    d_sums = torch.zeros((5, 12), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+
+    def step_device():
+        sums = eng.widom_batch_device(comp, B, d_pool.data_ptr(), B * 20, d_uni.data_ptr())
+        if world > 1:
+            d_sums.copy_(torch.from_numpy(sums)); dist.all_reduce(d_sums); return d_sums.cpu().numpy()
+        return sums
+
+    def step_e2e():
+        _, _, sums = eng.widom_batch(comp, h_pool.numpy(), h_uni.numpy(), want_outputs=False)
+        if world > 1:
+            d_sums.copy_(torch.from_numpy(sums)); dist.all_reduce(d_sums); return d_sums.cpu().numpy()
+        return sums
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier(); t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn()
+        barrier(); dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        return dt, out
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local); sampler.start()
+    eng.timing_enable(True); eng.timing_read(2, reset=True); eng.launch_count(reset=True)
+    dt, sums = timed(step_device, args.steps)
+    launches = eng.launch_count()
+    ms_pair, n_pair = eng.timing_read(0); ms_ew, n_ew = eng.timing_read(1)
+    eng.timing_enable(False)
+    for _ in range(2):
+        step_e2e()
+    dt_e2e, sums_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True; sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = B * world * args.steps / dt
+    e2e_value = B * world * args.steps / dt_e2e
+    total_count = float(sums[:, 2].sum())
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "insertions_per_gpu_per_step": B, "global_insertions_per_step": B * world,
+                       "parallelism": f"widom-shard x{world}", "cache": "inputs per step (random pool %.0f MB) exceed the 126 MB L2" % (B * 20 * 24 / 1e6),
+                       "mean_W": float(sums[:, 0].sum() / max(total_count, 1.0)), "failed_fraction": float(sums[:, 10].sum() / max(total_count, 1.0))},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * 20 * 24 + B * 16), "d2h_bytes_per_step": int(5 * 12 * 8)},
+            "gpu_launches": int(launches), "clocks": sampler.summary()}
+    # ---- CPU baseline + algorithmic flop count on a bounded sample of the same workload
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_sample(box, ff, s, z, comp)
+        line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
+                                "sample": f"{cpu['n']} insertions of the same workload in {cpu['seconds']:.1f} s, OpenMP over insertions"}
+        f_pair, f_k = flops_per_insertion(cpu["counts"], cpu["n"])
+        t_pair = ms_pair / max(n_pair, 1) * 1e-3
+        achieved = f_pair * B / t_pair / 1e12
+        line["roofline"] = {"bound": "fp64", "kernel": "k_widom_pair", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": achieved / fp64_peak, "traffic": None,
+                            "peak_source": "DFMA microbenchmark run in this process (gb_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                            "flop_per_insertion": f_pair, "launch_ms": t_pair * 1e3, "share_of_step": ms_pair / max(ms_pair + ms_ew, 1e-9),
+                            "ewald_kernel": {"achieved": f_k * B / (ms_ew / max(n_ew / 2, 1) * 1e-3) / 1e12, "unit": "TFLOP/s", "launch_ms": ms_ew / max(n_ew / 2, 1)},
+                            "hbm": {"algorithmic_bytes_per_insertion": 20 * 24 + 16 + 8 * 8, "note": "framework and structure factors are shared-memory resident; HBM is not the binding roof"}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,980 @@
+// graspa_b200 -- host side of the C ABI (include/graspa_b200.h): device state, uploads, launches.
+// Product code.  There is no CPU fallback anywhere in this file: every energy comes from a kernel in kernels.cuh.
+#include "../../include/graspa_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(call)                                                                             \
+  do {                                                                                             \
+    cudaError_t err__ = (call);                                                                    \
+    if(err__ != cudaSuccess)                                                                       \
+      return fail(GB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));             \
+  } while(0)
+
+template <typename T>
+struct DevBuf
+{
+  T* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t n)
+  {
+    if(n <= cap) return cudaSuccess;
+    if(p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 4 + 16;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if(e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if(p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Comp
+{
+  int offset = 0, alloc = 0, molsize = 0, natoms = 0;
+  bool uploaded = false;
+  double excl_intra = 0.0, excl_atom = 0.0; int rigid = 1, has_charge = 0;
+};
+
+} // namespace
+
+struct gb_engine
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop{};
+  size_t smem_optin = 0;
+  DevParams P{};
+  bool have_ff = false, have_box = false;
+  int ntypes = 0;
+  DevBuf<double4> d_ffA; DevBuf<double> d_ffB;
+  std::vector<int> tail_use; std::vector<double> tail_e; bool has_tail = false;
+  DevBuf<int> d_tail_use; DevBuf<double> d_tail_e;
+
+  int ncomp = 0, nhost = 0;
+  std::vector<Comp> comps;
+  int nslots = 0;
+  // host staging of the slot arrays (authoritative until the first device-side commit)
+  std::vector<double> hx, hy, hz, hq, hscale, hscoul; std::vector<int> htype, hmolid;
+  DevBuf<double> dx, dy, dz, dfx, dfy, dfz, dq, dscale, dscoul; DevBuf<int> dtype, dmolid;
+  bool device_stale = true;
+  std::vector<long long> npseudo;          // Components::NumberOfPseudoAtoms
+
+  // framework pack
+  DevBuf<double> d_pack; int pack_n = 0, pack_npad = 0; bool pack_dirty = true;
+
+  // Ewald
+  long long nvec = 0;
+  std::vector<int> h_kpack, h_kslot; std::vector<double> h_ktemp;
+  DevBuf<int> d_kpack, d_kslot; DevBuf<double> d_ktemp;
+  int nact = 0, nact_pad = 0;
+  DevBuf<double> d_sf[3];                 // ads, fw, temp (full arrays)
+  int i_ads = 0, i_fw = 1, i_tmp = 2;     // pointer swap = index swap (Update_Vector_Ewald)
+  bool have_sf = false;
+  DevBuf<double> d_ktab; bool ktab_dirty = true;
+
+  // CBMC
+  int ntrials = 10, norient = 10; bool have_cbmc = false;
+  DevBuf<double> d_pool; long long n_pool = 0;
+
+  // scratch
+  DevBuf<double> d_rec, d_out8, d_partial, d_sums, d_uni, d_scratch, d_result;
+  DevBuf<int> d_stage, d_iscratch;
+  DevBuf<long long> d_idx0, d_idx1;
+  DevBuf<unsigned int> d_ticket;
+  double* h_pinned = nullptr;            // 4 KB pinned result slot
+
+  long long launches = 0;
+  bool timing = false;
+  double ms_pair = 0.0, ms_ewald = 0.0; long long n_pair = 0, n_ewald = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+SysView sys_view(gb_engine* e)
+{
+  SysView S; S.fx = e->dfx.p; S.fy = e->dfy.p; S.fz = e->dfz.p; S.q = e->dq.p; S.scale = e->dscale.p; S.scoul = e->dscoul.p;
+  S.type = e->dtype.p; S.molid = e->dmolid.p;
+  return S;
+}
+
+// live ranges; which = 0: all, 1: host only, 2: adsorbate only.  kind: host 1 (HG), adsorbate 2 (GG) -- trial-move convention.
+SegList seg_list(gb_engine* e, int which)
+{
+  SegList L; memset(&L, 0, sizeof(L));
+  for(int c = 0; c < e->ncomp && L.nseg < GBK_MAX_SEG; c++)
+  {
+    const bool host = c < e->nhost;
+    if((which == 1 && !host) || (which == 2 && host)) continue;
+    if(e->comps[c].natoms == 0) continue;
+    L.start[L.nseg] = e->comps[c].offset; L.count[L.nseg] = e->comps[c].natoms; L.comp[L.nseg] = c;
+    L.kind[L.nseg] = host ? 1 : 2; L.staged[L.nseg] = 0; L.nseg++;
+  }
+  return L;
+}
+
+int sync_slots_to_device(gb_engine* e)
+{
+  if(!e->device_stale) return GB_OK;
+  const size_t n = (size_t) e->nslots;
+  if(n == 0) return GB_OK;
+  CUDA_TRY(e->dx.reserve(n)); CUDA_TRY(e->dy.reserve(n)); CUDA_TRY(e->dz.reserve(n));
+  CUDA_TRY(e->dfx.reserve(n)); CUDA_TRY(e->dfy.reserve(n)); CUDA_TRY(e->dfz.reserve(n));
+  CUDA_TRY(e->dq.reserve(n)); CUDA_TRY(e->dscale.reserve(n)); CUDA_TRY(e->dscoul.reserve(n));
+  CUDA_TRY(e->dtype.reserve(n)); CUDA_TRY(e->dmolid.reserve(n));
+  const size_t b = n * sizeof(double);
+  CUDA_TRY(cudaMemcpyAsync(e->dx.p, e->hx.data(), b, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->dy.p, e->hy.data(), b, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->dz.p, e->hz.data(), b, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->dq.p, e->hq.data(), b, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->dscale.p, e->hscale.data(), b, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->dscoul.p, e->hscoul.data(), b, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->dtype.p, e->htype.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->dmolid.p, e->hmolid.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  if(e->have_box)
+  {
+    k_frac_update<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->P, e->dx.p, e->dy.p, e->dz.p, e->dfx.p, e->dfy.p, e->dfz.p, 0, (int) n);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->device_stale = false; e->pack_dirty = true;
+  bool unit = true;
+  for(int c = 0; c < e->ncomp; c++)
+    for(int i = 0; i < e->comps[c].alloc; i++)
+    {
+      const size_t g = (size_t) e->comps[c].offset + i;
+      if(e->hscale[g] != 1.0 || e->hscoul[g] != 1.0) unit = false;
+    }
+  e->P.all_unit_scale = unit ? 1 : 0;
+  return GB_OK;
+}
+
+int ready(gb_engine* e)
+{
+  if(!e) return fail(GB_ERR_ARG, "null engine");
+  if(!e->have_ff) return fail(GB_ERR_STATE, "gb_upload_forcefield has not been called");
+  if(!e->have_box) return fail(GB_ERR_STATE, "gb_upload_box has not been called");
+  if(e->ncomp == 0) return fail(GB_ERR_STATE, "gb_set_components has not been called");
+  for(int c = 0; c < e->ncomp; c++) if(!e->comps[c].uploaded) return fail(GB_ERR_STATE, "component " + std::to_string(c) + " has not been uploaded");
+  CUDA_TRY(cudaSetDevice(e->device));
+  return sync_slots_to_device(e);
+}
+
+// framework pack for TMA staging.  Only valid for moves whose exclusions do not touch host components.
+int ensure_pack(gb_engine* e, bool& usable, size_t extra_smem)
+{
+  usable = false;
+  SegList L = seg_list(e, 1);
+  int n = 0; for(int s = 0; s < L.nseg; s++) n += L.count[s];
+  if(n == 0 || !e->P.all_unit_scale) return GB_OK;
+  const int npad = (n + 31) / 32 * 32;
+  if((size_t) npad * 36 + 64 + extra_smem > e->smem_optin) return GB_OK;
+  if(e->pack_dirty || e->pack_n != n)
+  {
+    CUDA_TRY(e->d_pack.reserve((size_t) npad * 5));
+    k_build_pack<<<(npad + 255) / 256, 256, 0, e->stream>>>(e->dfx.p, e->dfy.p, e->dfz.p, e->dq.p, e->dscoul.p, e->dtype.p, L, npad, e->d_pack.p);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    e->pack_n = n; e->pack_npad = npad; e->pack_dirty = false;
+  }
+  usable = true;
+  return GB_OK;
+}
+
+// stored structure factors gathered at the active k, in the staged layout of k_widom_ewald
+__global__ void k_build_ktab(const double* __restrict__ temp, const int* __restrict__ kpack, const int* __restrict__ slot,
+                             const double* __restrict__ sa, const double* __restrict__ sf, int nact, int npad, double* ktab)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= npad) return;
+  int* kp = reinterpret_cast<int*>(ktab + 5 * (size_t) npad);
+  if(k < nact)
+  {
+    const int s = slot[k];
+    ktab[k] = temp[k];
+    ktab[npad + 2 * k] = sa[2 * s]; ktab[npad + 2 * k + 1] = sa[2 * s + 1];
+    ktab[3 * (size_t) npad + 2 * k] = sf[2 * s]; ktab[3 * (size_t) npad + 2 * k + 1] = sf[2 * s + 1];
+    kp[k] = kpack[k];
+  }
+  else
+  {
+    ktab[k] = 0.0; ktab[npad + 2 * k] = 0.0; ktab[npad + 2 * k + 1] = 0.0;
+    ktab[3 * (size_t) npad + 2 * k] = 0.0; ktab[3 * (size_t) npad + 2 * k + 1] = 0.0; kp[k] = (128 << 8) | 128;
+  }
+}
+
+int ensure_ktab(gb_engine* e)
+{
+  if(!e->ktab_dirty) return GB_OK;
+  if(e->nact == 0) { e->ktab_dirty = false; return GB_OK; }
+  CUDA_TRY(e->d_ktab.reserve((size_t) e->nact_pad * 6));
+  k_build_ktab<<<(e->nact_pad + 255) / 256, 256, 0, e->stream>>>(e->d_ktemp.p, e->d_kpack.p, e->d_kslot.p, e->d_sf[e->i_ads].p, e->d_sf[e->i_fw].p,
+                                                                   e->nact, e->nact_pad, e->d_ktab.p);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  e->ktab_dirty = false;
+  return GB_OK;
+}
+
+// tail corrections on the device (TailCorrection_Energy_Functions.h:3-113): tiny, one thread
+__global__ void k_tail(int n, const long long* __restrict__ np, const int* __restrict__ use, const double* __restrict__ te,
+                       const int* __restrict__ dcount /* null: total */, double volume, double* out)
+{
+  if(threadIdx.x != 0 || blockIdx.x != 0) return;
+  double T = 0.0;
+  for(int i = 0; i < n; i++)
+    for(int j = i; j < n; j++)
+      if(use[i * n + j])
+      {
+        double v;
+        if(dcount)
+        {
+          const int Ni = (int) np[i], Nj = (int) np[j], di = dcount[i], dj = dcount[j];
+          const int dN = Ni * dj + Nj * di + di * dj;
+          v = te[i * n + j] * (double) dN;
+        }
+        else v = te[i * n + j] * (double)((unsigned long long) np[i] * (unsigned long long) np[j]);
+        if(i != j) v *= 2.0;
+        T += v;
+      }
+  *out = T / volume;
+}
+
+int tail_device(gb_engine* e, const std::vector<int>* dcount, double* d_out)
+{
+  const int n = e->ntypes;
+  if(!e->has_tail) { CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(double), e->stream)); return GB_OK; }
+  CUDA_TRY(e->d_iscratch.reserve((size_t) n + 16));
+  CUDA_TRY(e->d_idx0.reserve((size_t) n + 16));
+  CUDA_TRY(cudaMemcpyAsync(e->d_idx0.p, e->npseudo.data(), n * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+  if(dcount) CUDA_TRY(cudaMemcpyAsync(e->d_iscratch.p, dcount->data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  k_tail<<<1, 32, 0, e->stream>>>(n, e->d_idx0.p, e->d_tail_use.p, e->d_tail_e.p, dcount ? e->d_iscratch.p : nullptr, e->P.volume, d_out);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return GB_OK;
+}
+
+std::vector<int> species_counts(gb_engine* e, int comp)
+{
+  std::vector<int> c(e->ntypes, 0);
+  const Comp& C = e->comps[comp];
+  for(int a = 0; a < C.molsize; a++) { const int t = e->htype[(size_t) C.offset + a]; if(t >= 0 && t < e->ntypes) c[t]++; }
+  return c;
+}
+
+struct Timer
+{
+  gb_engine* e; int fam; bool on;
+  Timer(gb_engine* e_, int fam_) : e(e_), fam(fam_), on(e_->timing) { if(on) cudaEventRecord(e->ev0, e->stream); }
+  void stop(long long launches)
+  {
+    if(!on) return;
+    cudaEventRecord(e->ev1, e->stream); cudaEventSynchronize(e->ev1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    if(fam == 0) { e->ms_pair += ms; e->n_pair += launches; } else { e->ms_ewald += ms; e->n_ewald += launches; }
+    on = false;
+  }
+};
+
+} // namespace
+
+extern "C" {
+
+int gb_abi_version(void) { return GB_ABI_VERSION; }
+const char* gb_last_error(void) { return g_err.c_str(); }
+
+int gb_engine_create(gb_engine** out, int device)
+{
+  if(!out) return fail(GB_ERR_ARG, "out is null");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if(err != cudaSuccess || ndev == 0)
+    return fail(GB_ERR_CUDA, std::string("no CUDA device: graspa_b200 has no CPU path (") + cudaGetErrorString(err) + ")");
+  if(device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if(device >= ndev) return fail(GB_ERR_ARG, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  gb_engine* e = new gb_engine();
+  e->device = device;
+  CUDA_TRY(cudaGetDeviceProperties(&e->prop, device));
+  int optin = 0; CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  e->smem_optin = (size_t) optin;
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&e->ev0)); CUDA_TRY(cudaEventCreate(&e->ev1));
+  CUDA_TRY(cudaMallocHost(&e->h_pinned, 4096));
+  CUDA_TRY(e->d_ticket.reserve(16)); CUDA_TRY(cudaMemset(e->d_ticket.p, 0, 16 * sizeof(unsigned int)));
+  CUDA_TRY(e->d_result.reserve(512));
+  CUDA_TRY(cudaFuncSetAttribute(k_widom_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_TRY(cudaFuncSetAttribute(k_widom_ewald, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_TRY(cudaFuncSetAttribute(k_ewald_delta, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  *out = e;
+  return GB_OK;
+}
+
+int gb_engine_destroy(gb_engine* e)
+{
+  if(!e) return GB_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  e->d_ffA.release(); e->d_ffB.release(); e->d_tail_use.release(); e->d_tail_e.release();
+  e->dx.release(); e->dy.release(); e->dz.release(); e->dfx.release(); e->dfy.release(); e->dfz.release();
+  e->dq.release(); e->dscale.release(); e->dscoul.release(); e->dtype.release(); e->dmolid.release();
+  e->d_pack.release(); e->d_kpack.release(); e->d_kslot.release(); e->d_ktemp.release();
+  for(int i = 0; i < 3; i++) e->d_sf[i].release();
+  e->d_ktab.release(); e->d_pool.release(); e->d_rec.release(); e->d_out8.release(); e->d_partial.release(); e->d_sums.release();
+  e->d_uni.release(); e->d_scratch.release(); e->d_result.release(); e->d_stage.release(); e->d_iscratch.release();
+  e->d_idx0.release(); e->d_idx1.release(); e->d_ticket.release();
+  if(e->h_pinned) cudaFreeHost(e->h_pinned);
+  cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return GB_OK;
+}
+
+int gb_device_info(gb_engine* e, int* sm_count, int* cc_major, int* cc_minor, int64_t* smem)
+{
+  if(!e) return fail(GB_ERR_ARG, "null engine");
+  if(sm_count) *sm_count = e->prop.multiProcessorCount;
+  if(cc_major) *cc_major = e->prop.major;
+  if(cc_minor) *cc_minor = e->prop.minor;
+  if(smem) *smem = (int64_t) e->smem_optin;
+  return GB_OK;
+}
+
+int gb_synchronize(gb_engine* e) { if(!e) return fail(GB_ERR_ARG, "null engine"); CUDA_TRY(cudaStreamSynchronize(e->stream)); return GB_OK; }
+void* gb_stream(gb_engine* e) { return e ? (void*) e->stream : nullptr; }
+
+int gb_upload_forcefield(gb_engine* e, const gb_forcefield* ff, const gb_tail_table* tail)
+{
+  if(!e || !ff) return fail(GB_ERR_ARG, "null argument");
+  if(ff->size <= 0 || ff->size > 1024) return fail(GB_ERR_ARG, "bad force-field size");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const int n = ff->size; const size_t n2 = (size_t) n * n;
+  std::vector<double4> A(n2); std::vector<double> B(n2);
+  for(size_t i = 0; i < n2; i++)
+  {
+    if(!ff->use1264) { const double s = ff->sigma[i]; A[i] = make_double4(4.0 * ff->epsilon[i], s * s, ff->shift[i], 1.0 / (s * s)); B[i] = 0.0; }
+    else { A[i] = make_double4(ff->epsilon[i], ff->sigma[i], ff->z[i], ff->shift[i]); B[i] = ff->c10 ? ff->c10[i] : 0.0; }
+  }
+  CUDA_TRY(e->d_ffA.reserve(n2)); CUDA_TRY(e->d_ffB.reserve(n2));
+  CUDA_TRY(cudaMemcpy(e->d_ffA.p, A.data(), n2 * sizeof(double4), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(e->d_ffB.p, B.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
+  e->ntypes = n;
+  e->P.ntypes = n; e->P.cut_vdw2 = ff->cutoff_vdw_sq; e->P.cut_coul2 = ff->cutoff_coul_sq; e->P.overlap = ff->overlap_criteria;
+  e->P.no_charges = ff->no_charges; e->P.vdw_real_bias = ff->vdw_real_bias; e->P.use1264 = ff->use1264;
+  e->P.ffA = e->d_ffA.p; e->P.ffB = e->d_ffB.p;
+  e->tail_use.assign(n2, 0); e->tail_e.assign(n2, 0.0); e->has_tail = false;
+  if(tail && tail->use_tail && tail->energy)
+  {
+    if(tail->size != n) return fail(GB_ERR_ARG, "tail table size differs from force-field size");
+    for(size_t i = 0; i < n2; i++) { e->tail_use[i] = tail->use_tail[i]; e->tail_e[i] = tail->energy[i]; if(tail->use_tail[i]) e->has_tail = true; }
+  }
+  CUDA_TRY(e->d_tail_use.reserve(n2)); CUDA_TRY(e->d_tail_e.reserve(n2));
+  CUDA_TRY(cudaMemcpy(e->d_tail_use.p, e->tail_use.data(), n2 * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(e->d_tail_e.p, e->tail_e.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
+  e->npseudo.assign(n, 0);
+  e->have_ff = true;
+  return GB_OK;
+}
+
+int gb_upload_box(gb_engine* e, const gb_box* box)
+{
+  if(!e || !box) return fail(GB_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  for(int i = 0; i < 9; i++) { e->P.cell[i] = box->cell[i]; e->P.inv[i] = box->inverse_cell[i]; }
+  e->P.volume = box->volume; e->P.alpha = box->alpha; e->P.prefactor = box->prefactor; e->P.recip_cutoff = box->reciprocal_cutoff;
+  e->P.cubic = box->cubic; e->P.use_lammps = box->use_lammps_ewald;
+  for(int i = 0; i < 3; i++) e->P.kmax[i] = box->kmax[i];
+  if(box->kmax[0] > 127 || box->kmax[1] > 127 || box->kmax[2] > 127 || box->kmax[0] < 0 || box->kmax[1] < 0 || box->kmax[2] < 0)
+    return fail(GB_ERR_ARG, "kmax out of range [0,127]");
+  // active k table: Ewald_Energy_Functions.h:299-334, 358-360
+  const int kxm = box->kmax[0], kym = box->kmax[1], kzm = box->kmax[2];
+  e->nvec = (long long)(kxm + 1) * (2 * kym + 1) * (2 * kzm + 1);
+  e->h_kpack.clear(); e->h_kslot.clear(); e->h_ktemp.clear();
+  const double* I = box->inverse_cell;
+  const double ax[3] = {I[0], I[3], I[6]}, ay[3] = {I[1], I[4], I[7]}, az[3] = {I[2], I[5], I[8]};
+  const double alpha_sq = box->alpha * box->alpha;
+  const double prefactor = box->prefactor * (2.0 * GBK_PI / box->volume);
+  if(box->alpha > 0.0)
+    for(long long kxyz = 0; kxyz < e->nvec; kxyz++)
+    {
+      const int kz = (int)(kxyz % (2 * kzm + 1)) - kzm;
+      const int kxy = (int)(kxyz / (2 * kzm + 1));
+      const int kx = kxy / (2 * kym + 1);
+      const int ky = kxy % (2 * kym + 1) - kym;
+      double ksqr = (double)(kx * kx + ky * ky + kz * kz);
+      if(box->use_lammps_ewald)
+      {
+        const double lx = box->cell[0], ly = box->cell[4], lz = box->cell[8], xy = box->cell[3], xz = box->cell[6], yz = box->cell[7];
+        const double ux = 2 * GBK_PI / lx, uy = 2 * GBK_PI * (-xy) / lx / ly, uz = 2 * GBK_PI * (xy * yz - ly * xz) / lx / ly / lz;
+        const double vy = 2 * GBK_PI / ly, vz = 2 * GBK_PI * (-yz) / ly / lz, wz = 2 * GBK_PI / lz;
+        const double kvx = kx * ux, kvy = kx * uy + ky * vy, kvz = kx * uz + ky * vz + kz * wz;
+        ksqr = kvx * kvx + kvy * kvy + kvz * kvz;
+      }
+      if(!((ksqr > 1e-10) && (ksqr < box->reciprocal_cutoff))) continue;
+      double kv[3];
+      for(int d = 0; d < 3; d++) kv[d] = ax[d] * 2.0 * GBK_PI * (double) kx + ay[d] * 2.0 * GBK_PI * (double) ky + az[d] * 2.0 * GBK_PI * (double) kz;
+      const double rksq = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2];
+      const double factor = (kx == 0) ? (1.0 * prefactor) : (2.0 * prefactor);
+      e->h_ktemp.push_back(factor * std::exp((-0.25 / alpha_sq) * rksq) / rksq);
+      e->h_kpack.push_back((kx << 16) | ((ky + 128) << 8) | (kz + 128));
+      e->h_kslot.push_back((int) kxyz);
+    }
+  e->nact = (int) e->h_kpack.size(); e->nact_pad = (e->nact + 31) / 32 * 32;
+  if(e->nact > 0)
+  {
+    CUDA_TRY(e->d_kpack.reserve(e->nact)); CUDA_TRY(e->d_kslot.reserve(e->nact)); CUDA_TRY(e->d_ktemp.reserve(e->nact));
+    CUDA_TRY(cudaMemcpy(e->d_kpack.p, e->h_kpack.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(e->d_kslot.p, e->h_kslot.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(e->d_ktemp.p, e->h_ktemp.data(), e->nact * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  for(int i = 0; i < 3; i++)
+  {
+    CUDA_TRY(e->d_sf[i].reserve((size_t) std::max<long long>(2 * e->nvec, 2)));
+    CUDA_TRY(cudaMemset(e->d_sf[i].p, 0, (size_t) std::max<long long>(2 * e->nvec, 2) * sizeof(double)));
+  }
+  e->i_ads = 0; e->i_fw = 1; e->i_tmp = 2; e->have_sf = false; e->ktab_dirty = true;
+  e->have_box = true; e->device_stale = true;
+  return GB_OK;
+}
+
+int gb_set_components(gb_engine* e, int32_t n_total, int32_t n_host)
+{
+  if(!e) return fail(GB_ERR_ARG, "null engine");
+  if(n_total <= 0 || n_total > GBK_MAX_SEG || n_host < 0 || n_host > n_total) return fail(GB_ERR_ARG, "bad component counts");
+  e->ncomp = n_total; e->nhost = n_host; e->comps.assign(n_total, Comp());
+  e->nslots = 0; e->hx.clear(); e->hy.clear(); e->hz.clear(); e->hq.clear(); e->hscale.clear(); e->hscoul.clear(); e->htype.clear(); e->hmolid.clear();
+  e->device_stale = true;
+  return GB_OK;
+}
+
+int gb_upload_atoms(gb_engine* e, int32_t c, const gb_atoms* a)
+{
+  if(!e || !a) return fail(GB_ERR_ARG, "null argument");
+  if(c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "component out of range");
+  if(a->n_live > a->n_upload || a->n_upload > a->n_alloc || a->molsize <= 0) return fail(GB_ERR_ARG, "inconsistent atom counts");
+  if(!e->have_ff) return fail(GB_ERR_STATE, "upload the force field before atoms");
+  Comp& C = e->comps[c];
+  if(C.uploaded && C.alloc != (int) a->n_alloc) return fail(GB_ERR_ARG, "component re-uploaded with a different n_alloc");
+  if(!C.uploaded)
+  {
+    for(int k = 0; k < c; k++) if(!e->comps[k].uploaded) return fail(GB_ERR_STATE, "upload components in order");
+    C.offset = e->nslots; C.alloc = (int) a->n_alloc; e->nslots += C.alloc;
+    const size_t n = (size_t) e->nslots;
+    e->hx.resize(n, 0.0); e->hy.resize(n, 0.0); e->hz.resize(n, 0.0); e->hq.resize(n, 0.0); e->hscale.resize(n, 1.0); e->hscoul.resize(n, 1.0);
+    e->htype.resize(n, 0); e->hmolid.resize(n, 0);
+  }
+  else
+  {
+    for(int i = 0; i < C.natoms; i++) { const int t = e->htype[(size_t) C.offset + i]; if(t >= 0 && t < e->ntypes) e->npseudo[t]--; }
+  }
+  C.molsize = (int) a->molsize; C.natoms = (int) a->n_live; C.uploaded = true;
+  for(int64_t i = 0; i < a->n_upload; i++)
+  {
+    const size_t g = (size_t) C.offset + i;
+    e->hx[g] = a->pos[3 * i]; e->hy[g] = a->pos[3 * i + 1]; e->hz[g] = a->pos[3 * i + 2];
+    e->hq[g] = a->charge ? a->charge[i] : 0.0; e->hscale[g] = a->scale ? a->scale[i] : 1.0; e->hscoul[g] = a->scale_coul ? a->scale_coul[i] : 1.0;
+    e->htype[g] = a->type ? (int) a->type[i] : 0; e->hmolid[g] = a->molid ? (int) a->molid[i] : 0;
+    if(e->htype[g] < 0 || e->htype[g] >= e->ntypes) return fail(GB_ERR_ARG, "atom type outside the force-field table");
+  }
+  for(int i = 0; i < C.natoms; i++) e->npseudo[e->htype[(size_t) C.offset + i]]++;
+  bool hc = false;
+  for(int i = 0; i < C.molsize && i < (int) a->n_upload; i++) if(std::fabs(e->hq[(size_t) C.offset + i]) > 1e-10) hc = true;
+  C.has_charge = hc ? 1 : 0;
+  e->device_stale = true; e->pack_dirty = true;
+  return GB_OK;
+}
+
+int gb_download_atoms(gb_engine* e, int32_t c, double* pos, double* scale, double* charge, double* scale_coul,
+                      uint64_t* type, uint64_t* molid, int64_t* n_live)
+{
+  int rc = ready(e); if(rc) return rc;
+  if(c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "component out of range");
+  const Comp& C = e->comps[c];
+  const size_t n = (size_t) C.alloc;
+  std::vector<double> t(n * 6); std::vector<int> ti(n * 2);
+  const size_t b = n * sizeof(double);
+  CUDA_TRY(cudaMemcpyAsync(t.data(), e->dx.p + C.offset, b, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(t.data() + n, e->dy.p + C.offset, b, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(t.data() + 2 * n, e->dz.p + C.offset, b, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(t.data() + 3 * n, e->dscale.p + C.offset, b, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(t.data() + 4 * n, e->dq.p + C.offset, b, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(t.data() + 5 * n, e->dscoul.p + C.offset, b, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(ti.data(), e->dtype.p + C.offset, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(ti.data() + n, e->dmolid.p + C.offset, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  for(size_t i = 0; i < n; i++)
+  {
+    if(pos) { pos[3 * i] = t[i]; pos[3 * i + 1] = t[n + i]; pos[3 * i + 2] = t[2 * n + i]; }
+    if(scale) scale[i] = t[3 * n + i];
+    if(charge) charge[i] = t[4 * n + i];
+    if(scale_coul) scale_coul[i] = t[5 * n + i];
+    if(type) type[i] = (uint64_t) ti[i];
+    if(molid) molid[i] = (uint64_t) ti[n + i];
+  }
+  if(n_live) *n_live = C.natoms;
+  return GB_OK;
+}
+
+int gb_upload_structure_factors(gb_engine* e, const double* ads, const double* fw)
+{
+  if(!e) return fail(GB_ERR_ARG, "null engine");
+  if(!e->have_box) return fail(GB_ERR_STATE, "upload the box first");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const size_t b = (size_t) e->nvec * 2 * sizeof(double);
+  if(ads) CUDA_TRY(cudaMemcpy(e->d_sf[e->i_ads].p, ads, b, cudaMemcpyHostToDevice));
+  if(fw)  CUDA_TRY(cudaMemcpy(e->d_sf[e->i_fw].p, fw, b, cudaMemcpyHostToDevice));
+  e->have_sf = true; e->ktab_dirty = true;
+  return GB_OK;
+}
+
+int gb_download_structure_factors(gb_engine* e, double* ads, double* fw, double* tmp)
+{
+  if(!e) return fail(GB_ERR_ARG, "null engine");
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  const size_t b = (size_t) e->nvec * 2 * sizeof(double);
+  if(ads) CUDA_TRY(cudaMemcpy(ads, e->d_sf[e->i_ads].p, b, cudaMemcpyDeviceToHost));
+  if(fw)  CUDA_TRY(cudaMemcpy(fw, e->d_sf[e->i_fw].p, b, cudaMemcpyDeviceToHost));
+  if(tmp) CUDA_TRY(cudaMemcpy(tmp, e->d_sf[e->i_tmp].p, b, cudaMemcpyDeviceToHost));
+  return GB_OK;
+}
+
+int gb_set_exclusion_constants(gb_engine* e, int32_t c, double intra, double atom, int32_t rigid, int32_t has_charge)
+{
+  if(!e || c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "bad component");
+  e->comps[c].excl_intra = intra; e->comps[c].excl_atom = atom; e->comps[c].rigid = rigid; e->comps[c].has_charge = has_charge;
+  return GB_OK;
+}
+
+int gb_upload_random_pool(gb_engine* e, const double* r3, int64_t n)
+{
+  if(!e || !r3 || n <= 0) return fail(GB_ERR_ARG, "bad pool");
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(e->d_pool.reserve((size_t) n * 3));
+  CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, r3, (size_t) n * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->n_pool = n;
+  return GB_OK;
+}
+
+int gb_set_cbmc(gb_engine* e, int32_t ntp, int32_t nto, double beta)
+{
+  if(!e) return fail(GB_ERR_ARG, "null engine");
+  if(ntp <= 0 || ntp > GBK_MAX_TRIALS || nto <= 0 || nto > GBK_MAX_TRIALS) return fail(GB_ERR_ARG, "trial counts must be in [1,32]");
+  e->ntrials = ntp; e->norient = nto; e->P.beta = beta; e->have_cbmc = true;
+  return GB_OK;
+}
+
+int gb_get_pseudo_atom_counts(gb_engine* e, int64_t* counts)
+{
+  if(!e || !counts) return fail(GB_ERR_ARG, "null argument");
+  for(int i = 0; i < e->ntypes; i++) counts[i] = e->npseudo[i];
+  return GB_OK;
+}
+
+int gb_number_of_molecules(gb_engine* e, int32_t c, int64_t* n)
+{
+  if(!e || !n || c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "bad argument");
+  *n = e->comps[c].molsize > 0 ? e->comps[c].natoms / e->comps[c].molsize : 0;
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- trial energies
+int gb_trial_energies(gb_engine* e, int32_t ntr, int32_t cs, const double* pos, const double* scale, const double* charge,
+                      const double* scale_coul, const uint64_t* type, int32_t new_comp, int64_t new_molid,
+                      int32_t excl_comp, int64_t excl_mol, double* out_energy, int32_t* out_flag)
+{
+  int rc = ready(e); if(rc) return rc;
+  if(ntr <= 0 || cs <= 0 || cs > GBK_MAX_CS || !pos || !type || !out_energy || !out_flag) return fail(GB_ERR_ARG, "bad trial arguments");
+  const size_t n = (size_t) ntr * cs;
+  std::vector<double> h(n * 5); std::vector<int> ht(n);
+  // fractional coordinates on the host is set-up arithmetic only (same product as to_frac)
+  for(size_t i = 0; i < n; i++)
+  {
+    const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+    h[i] = e->P.inv[0] * x + e->P.inv[3] * y + e->P.inv[6] * z;
+    h[n + i] = e->P.inv[1] * x + e->P.inv[4] * y + e->P.inv[7] * z;
+    h[2 * n + i] = e->P.inv[2] * x + e->P.inv[5] * y + e->P.inv[8] * z;
+    h[3 * n + i] = (charge ? charge[i] : 0.0) * (scale_coul ? scale_coul[i] : 1.0);
+    h[4 * n + i] = scale ? scale[i] : 1.0;
+    ht[i] = (int) type[i];
+    if(ht[i] < 0 || ht[i] >= e->ntypes) return fail(GB_ERR_ARG, "trial atom type outside the force-field table");
+  }
+  CUDA_TRY(e->d_scratch.reserve(n * 5 + (size_t) ntr * 6)); CUDA_TRY(e->d_iscratch.reserve(n + ntr));
+  CUDA_TRY(cudaMemcpyAsync(e->d_scratch.p, h.data(), n * 5 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->d_iscratch.p, ht.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  TrialBuf B; B.fx = e->d_scratch.p; B.fy = B.fx + n; B.fz = B.fy + n; B.q = B.fz + n; B.scale = B.q + n; B.type = e->d_iscratch.p;
+  double* d_out = e->d_scratch.p + n * 5; int* d_flag = e->d_iscratch.p + n;
+  SegList L = seg_list(e, 0);
+  Timer tm(e, 0);
+  k_trial_energies<<<ntr, 256, 0, e->stream>>>(e->P, sys_view(e), L, B, cs, new_comp, (int) new_molid, excl_comp, (int) excl_mol, d_out, d_flag);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  tm.stop(1);
+  std::vector<double> o((size_t) ntr * 6);
+  CUDA_TRY(cudaMemcpyAsync(o.data(), d_out, o.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(out_flag, d_flag, ntr * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  for(int t = 0; t < ntr; t++)
+  {
+    // HH contributions (a framework component inserted against other framework components) are reported with HG,
+    // as the reference's HG blocks cover every host component (VDW_Coulomb.cu:1232-1235)
+    out_energy[4 * t] = o[6 * t + 2] + o[6 * t]; out_energy[4 * t + 1] = o[6 * t + 3] + o[6 * t + 1];
+    out_energy[4 * t + 2] = o[6 * t + 4]; out_energy[4 * t + 3] = o[6 * t + 5];
+  }
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- Ewald delta
+static int ewald_delta_launch(gb_engine* e, bool framework_moved, int nold, int nnew, const double* d_pos3, const double* d_qeff, double out[2])
+{
+  const int n = nold + nnew;
+  if(n <= 0 || n > GBK_EW_MAX_ATOMS) return fail(GB_ERR_ARG, "Ewald delta supports 1..64 moved atoms");
+  if(e->nact == 0) { out[0] = 0.0; out[1] = 0.0; return GB_OK; }
+  EwaldDeltaArgs A;
+  A.pos3 = d_pos3; A.qeff = d_qeff; A.nold = nold; A.nnew = nnew;
+  A.K.kpack = e->d_kpack.p; A.K.temp = e->d_ktemp.p; A.K.slot = e->d_kslot.p; A.K.nact = e->nact;
+  A.same_sf = framework_moved ? e->d_sf[e->i_fw].p : e->d_sf[e->i_ads].p;
+  A.cross_sf = framework_moved ? e->d_sf[e->i_ads].p : e->d_sf[e->i_fw].p;
+  A.temp_sf = e->d_sf[e->i_tmp].p;
+  const int nblk = (e->nact + 127) / 128;
+  CUDA_TRY(e->d_partial.reserve((size_t) std::max(nblk * 2, 64)));
+  A.partial = e->d_partial.p; A.ticket = e->d_ticket.p; A.result = e->d_result.p;
+  const size_t smem = (size_t) n * (e->P.kmax[0] + e->P.kmax[1] + e->P.kmax[2] + 3) * sizeof(cplx) + (size_t) n * sizeof(double) + 16;
+  if(smem > e->smem_optin) return fail(GB_ERR_ARG, "eik tables exceed shared memory");
+  // inactive k of tempEik keep the same-type values (zeros from the total), they never contribute
+  CUDA_TRY(cudaMemcpyAsync(e->d_sf[e->i_tmp].p, A.same_sf, (size_t) e->nvec * 2 * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  Timer tm(e, 1);
+  k_ewald_delta<<<nblk, 128, smem, e->stream>>>(e->P, A);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  tm.stop(1);
+  CUDA_TRY(cudaMemcpyAsync(e->h_pinned, e->d_result.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  out[0] = e->h_pinned[0]; out[1] = e->h_pinned[1];
+  return GB_OK;
+}
+
+int gb_ewald_delta_explicit(gb_engine* e, int32_t fw_moved, int32_t nold, int32_t nnew, const double* pos, const double* charge,
+                            const double* scale_coul, double out[2])
+{
+  int rc = ready(e); if(rc) return rc;
+  if(!pos || !charge || !out) return fail(GB_ERR_ARG, "null argument");
+  const int n = nold + nnew;
+  if(n <= 0 || n > GBK_EW_MAX_ATOMS) return fail(GB_ERR_ARG, "Ewald delta supports 1..64 moved atoms");
+  std::vector<double> h((size_t) n * 4);
+  for(int i = 0; i < 3 * n; i++) h[i] = pos[i];
+  for(int i = 0; i < n; i++) h[3 * n + i] = (scale_coul ? scale_coul[i] : 1.0) * charge[i];
+  CUDA_TRY(e->d_scratch.reserve((size_t) n * 4));
+  CUDA_TRY(cudaMemcpyAsync(e->d_scratch.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  return ewald_delta_launch(e, fw_moved != 0, nold, nnew, e->d_scratch.p, e->d_scratch.p + 3 * n, out);
+}
+
+int gb_ewald_commit(gb_engine* e, int32_t c)
+{
+  if(!e || c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "bad component");
+  if(c < e->nhost) std::swap(e->i_fw, e->i_tmp); else std::swap(e->i_ads, e->i_tmp);   // Ewald_Energy_Functions.h:423-433
+  e->ktab_dirty = true;
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- tail
+int gb_tail_total(gb_engine* e, double* out)
+{
+  int rc = ready(e); if(rc) return rc;
+  rc = tail_device(e, nullptr, e->d_result.p + 8); if(rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 8, e->d_result.p + 8, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  *out = e->h_pinned[8];
+  return GB_OK;
+}
+
+int gb_tail_difference(gb_engine* e, int32_t c, int32_t move_type, double* out)
+{
+  int rc = ready(e); if(rc) return rc;
+  if(c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "bad component");
+  if(move_type == GB_CBCF_INSERTION || move_type == GB_CBCF_DELETION) return fail(GB_ERR_UNIMPLEMENTED, "tail corrections are not defined for CBCF moves (TailCorrection_Energy_Functions.h:48-55)");
+  std::vector<int> d = species_counts(e, c);
+  const int sign = (move_type == GB_DELETION) ? -1 : 1;     // every other type keeps sign = +1 (:40-61)
+  for(auto& v : d) v *= sign;
+  rc = tail_device(e, &d, e->d_result.p + 8); if(rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 8, e->d_result.p + 8, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  *out = e->h_pinned[8];
+  return GB_OK;
+}
+
+int gb_tail_identity_swap(gb_engine* e, int32_t newc, int32_t oldc, double* out)
+{
+  int rc = ready(e); if(rc) return rc;
+  if(newc < 0 || newc >= e->ncomp || oldc < 0 || oldc >= e->ncomp) return fail(GB_ERR_ARG, "bad component");
+  std::vector<int> dn = species_counts(e, newc), dold = species_counts(e, oldc);
+  for(int i = 0; i < e->ntypes; i++) dn[i] -= dold[i];
+  rc = tail_device(e, &dn, e->d_result.p + 8); if(rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 8, e->d_result.p + 8, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  *out = e->h_pinned[8];
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- totals
+int gb_total_vdw_real(gb_engine* e, gb_move_energy* out)
+{
+  int rc = ready(e); if(rc) return rc;
+  if(!out) return fail(GB_ERR_ARG, "null out");
+  memset(out, 0, sizeof(*out));
+  TotalArgs A; A.L = seg_list(e, 0); A.nhost = e->nhost; A.comp_of = nullptr;
+  int nlive = 0; for(int s = 0; s < A.L.nseg; s++) nlive += A.L.count[s];
+  if(nlive == 0) return GB_OK;
+  CUDA_TRY(e->d_scratch.reserve((size_t) nlive * 6 + 8));
+  A.out = e->d_scratch.p;
+  Timer tm(e, 0);
+  k_total_vdw_real<<<nlive, 128, 0, e->stream>>>(e->P, sys_view(e), A);
+  k_reduce_partials<<<1, 32, 0, e->stream>>>(e->d_scratch.p, nlive, 6, e->d_result.p + 16);
+  e->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  tm.stop(2);
+  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 16, e->d_result.p + 16, 6 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  const double* r = e->h_pinned + 16;
+  out->HHVDW = r[0]; out->HHReal = r[1]; out->HGVDW = r[2]; out->HGReal = r[3]; out->GGVDW = r[4]; out->GGReal = r[5];
+  return GB_OK;
+}
+
+int gb_total_ewald(gb_engine* e, int32_t store, gb_move_energy* out)
+{
+  int rc = ready(e); if(rc) return rc;
+  if(!out) return fail(GB_ERR_ARG, "null out");
+  memset(out, 0, sizeof(*out));
+  if(e->P.no_charges || e->nact == 0) return GB_OK;
+  EwaldTotalArgs A;
+  A.x = e->dx.p; A.y = e->dy.p; A.z = e->dz.p; A.q = e->dq.p; A.scoul = e->dscoul.p;
+  A.L = seg_list(e, 0);
+  A.K.kpack = e->d_kpack.p; A.K.temp = e->d_ktemp.p; A.K.slot = e->d_kslot.p; A.K.nact = e->nact;
+  int nhost_atoms = 0; for(int c = 0; c < e->nhost; c++) nhost_atoms += e->comps[c].natoms;
+  A.has_fw = (e->nhost > 0 && nhost_atoms > 0) ? 1 : 0;
+  if(store)
+  {
+    CUDA_TRY(cudaMemsetAsync(e->d_sf[e->i_ads].p, 0, (size_t) e->nvec * 2 * sizeof(double), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->d_sf[e->i_fw].p, 0, (size_t) e->nvec * 2 * sizeof(double), e->stream));
+    A.sf_ads = e->d_sf[e->i_ads].p; A.sf_fw = e->d_sf[e->i_fw].p;
+  }
+  else { A.sf_ads = nullptr; A.sf_fw = nullptr; }
+  // per-molecule exclusion records: count molecules
+  int nmol_total = 0; for(int c = 0; c < e->ncomp; c++) if(e->comps[c].molsize > 0) nmol_total += e->comps[c].natoms / e->comps[c].molsize;
+  CUDA_TRY(e->d_scratch.reserve((size_t) e->nact * 3 + (size_t) nmol_total * 2 + 64));
+  A.ek = e->d_scratch.p;
+  Timer tm(e, 1);
+  k_ewald_total<<<e->nact, 128, 0, e->stream>>>(e->P, A);
+  k_reduce_partials<<<1, 32, 0, e->stream>>>(A.ek, e->nact, 3, e->d_result.p + 32);
+  e->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  double* d_ex = e->d_scratch.p + (size_t) e->nact * 3;
+  int moff = 0;
+  std::vector<int> moffs(e->ncomp, 0), mcnt(e->ncomp, 0);
+  for(int c = 0; c < e->ncomp; c++)
+  {
+    const Comp& C = e->comps[c];
+    const int nm = C.molsize > 0 ? C.natoms / C.molsize : 0;
+    moffs[c] = moff; mcnt[c] = nm;
+    if(nm > 0)
+    {
+      ExclArgs X; X.x = e->dx.p; X.y = e->dy.p; X.z = e->dz.p; X.q = e->dq.p; X.scoul = e->dscoul.p; X.start = C.offset; X.nmol = nm; X.ms = C.molsize; X.out = d_ex + 2 * (size_t) moff;
+      k_ewald_exclusion<<<(nm + 127) / 128, 128, 0, e->stream>>>(e->P, X);
+      e->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+    moff += nm;
+  }
+  tm.stop(2 + e->ncomp);
+  std::vector<double> ex((size_t) nmol_total * 2 + 2);
+  if(nmol_total > 0) CUDA_TRY(cudaMemcpyAsync(ex.data(), d_ex, (size_t) nmol_total * 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 32, e->d_result.p + 32, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  double GG = e->h_pinned[32], HH = e->h_pinned[33], HG = e->h_pinned[34];
+  GG += HH;                                                            // ewald_preparation.h:174
+  for(int c = 0; c < e->ncomp; c++)
+    for(int m = 0; m < mcnt[c]; m++)
+    {
+      const double self = ex[2 * (size_t)(moffs[c] + m)], intra = ex[2 * (size_t)(moffs[c] + m) + 1];
+      GG -= self; GG -= intra;
+      if(c < e->nhost && A.has_fw) { HH -= self; HH -= intra; }
+    }
+  out->GGEwaldE = GG; out->HHEwaldE = HH; out->HGEwaldE = HG;
+  if(store) { e->have_sf = true; e->ktab_dirty = true; }
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- batched Widom
+int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs* in, double* out8, int32_t* stage,
+                   int32_t outputs_on_device, double* sums)
+{
+  int rc = ready(e); if(rc) return rc;
+  if(!in || n <= 0 || !in->pool3 || !in->uniforms) return fail(GB_ERR_ARG, "bad Widom inputs");
+  if(comp < e->nhost || comp >= e->ncomp) return fail(GB_ERR_ARG, "Widom component must be an adsorbate component");
+  if(!e->have_cbmc) return fail(GB_ERR_STATE, "gb_set_cbmc has not been called");
+  const Comp& C = e->comps[comp];
+  const int ms = C.molsize, cs = ms - 1;
+  if(cs > GBK_MAX_CS) return fail(GB_ERR_ARG, "molecule too large for the CBMC chain stage");
+  const bool do_ewald = !e->P.no_charges && C.has_charge && e->nact > 0;
+  if(do_ewald && !e->have_sf) return fail(GB_ERR_STATE, "structure factors have not been uploaded or computed (gb_total_ewald(store=1))");
+  if(ms > GBK_EW_MAX_ATOMS) return fail(GB_ERR_ARG, "molecule too large for the Ewald stage");
+  const int nbins = in->n_blocks > 0 ? in->n_blocks : 1;
+  const int per = e->ntrials + e->norient;
+
+  // ---- inputs on the device
+  const double* d_pool = in->pool3; const long long* d_fb = (const long long*) in->fb_index; const long long* d_or = (const long long*) in->or_index;
+  const double* d_uni = in->uniforms;
+  if(!in->inputs_on_device)
+  {
+    CUDA_TRY(e->d_pool.reserve((size_t) in->n_pool * 3));
+    CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, in->pool3, (size_t) in->n_pool * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    d_pool = e->d_pool.p;
+    CUDA_TRY(e->d_uni.reserve((size_t) n * 2));
+    CUDA_TRY(cudaMemcpyAsync(e->d_uni.p, in->uniforms, (size_t) n * 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    d_uni = e->d_uni.p;
+    if(in->fb_index)
+    {
+      CUDA_TRY(e->d_idx0.reserve((size_t) n)); CUDA_TRY(e->d_idx1.reserve((size_t) n));
+      CUDA_TRY(cudaMemcpyAsync(e->d_idx0.p, in->fb_index, (size_t) n * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(e->d_idx1.p, in->or_index, (size_t) n * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+      d_fb = e->d_idx0.p; d_or = e->d_idx1.p;
+    }
+  }
+  if(!in->fb_index && in->n_pool < n * per) return fail(GB_ERR_ARG, "random pool smaller than n*(trial positions+orientations)");
+
+  // ---- stage A
+  const int rec_stride = 5 + 3 * ms;
+  CUDA_TRY(e->d_rec.reserve((size_t) n * rec_stride)); CUDA_TRY(e->d_stage.reserve((size_t) n));
+  const int warpsA = 16;
+  const size_t per_warpA = (sizeof(TrialGroup) + sizeof(WarpQueue) + (size_t) e->norient * (cs > 0 ? cs : 1) * 6 * sizeof(double) + 15) / 16 * 16;
+  bool use_pack = false;
+  rc = ensure_pack(e, use_pack, warpsA * per_warpA + 64); if(rc) return rc;
+  WidomA A;
+  A.pool3 = d_pool; A.fb_index = d_fb; A.or_index = d_or; A.uni = d_uni; A.n = n;
+  A.ntrials = e->ntrials; A.norient = e->norient; A.ms = ms; A.comp = comp; A.new_molid = C.natoms / ms;
+  A.tx = e->dx.p + C.offset; A.ty = e->dy.p + C.offset; A.tz = e->dz.p + C.offset; A.tq = e->dq.p + C.offset;
+  A.tscoul = e->dscoul.p + C.offset; A.ttype = e->dtype.p + C.offset;
+  A.pack = e->d_pack.p; A.npad = e->pack_npad; A.use_pack = use_pack ? 1 : 0;
+  A.rec = e->d_rec.p; A.stage = e->d_stage.p;
+  SegList L = seg_list(e, 0);
+  if(use_pack)
+  {
+    int acc = 0;
+    for(int s = 0; s < L.nseg; s++) if(L.comp[s] < e->nhost) { L.staged[s] = 1; L.start[s] = acc; acc += L.count[s]; }
+  }
+  const size_t smemA = 16 + (use_pack ? ((size_t) e->pack_npad * 36 + 15) / 16 * 16 : 0) + warpsA * per_warpA;
+  if(smemA > e->smem_optin) return fail(GB_ERR_ARG, "Widom stage A shared memory exceeds the device limit");
+  const int gridA = (int) std::min<long long>((n + warpsA - 1) / warpsA, e->prop.multiProcessorCount);
+  {
+    Timer tm(e, 0);
+    k_widom_pair<<<gridA, warpsA * 32, smemA, e->stream>>>(e->P, sys_view(e), L, A);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    tm.stop(1);
+  }
+  // ---- tail (constant over the batch)
+  std::vector<int> dc = species_counts(e, comp);
+  rc = tail_device(e, &dc, e->d_result.p + 8); if(rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 8, e->d_result.p + 8, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  // ---- stage B
+  rc = ensure_ktab(e); if(rc) return rc;
+  const int warpsB = 8;
+  WidomB B;
+  B.rec = e->d_rec.p; B.stage = e->d_stage.p; B.n = n; B.ms = ms; B.tq = e->dq.p + C.offset; B.tscoul = e->dscoul.p + C.offset;
+  B.ktab = e->d_ktab.p; B.nact = e->nact; B.nact_pad = e->nact_pad; B.do_ewald = do_ewald ? 1 : 0;
+  B.excl_const = C.rigid ? (C.excl_intra + C.excl_atom) * 1.0 : 0.0;
+  B.tail = e->h_pinned[8]; B.nbins = nbins;
+  const size_t per_warpB = ((size_t) ms * (e->P.kmax[0] + e->P.kmax[1] + e->P.kmax[2] + 3) * sizeof(cplx) + (size_t) ms * 4 * sizeof(double) + 15) / 16 * 16;
+  const size_t fixedB = 16 + warpsB * per_warpB + (size_t) warpsB * nbins * 12 * sizeof(double) + 64;
+  const size_t ktab_bytes = ((size_t) e->nact_pad * 44 + 15) / 16 * 16;
+  B.stage_ktab = (do_ewald && fixedB + ktab_bytes <= e->smem_optin) ? 1 : 0;
+  const size_t smemB = fixedB + (B.stage_ktab ? ktab_bytes : 0);
+  if(smemB > e->smem_optin) return fail(GB_ERR_ARG, "Widom stage B shared memory exceeds the device limit");
+  const int gridB = (int) std::min<long long>((n + warpsB - 1) / warpsB, e->prop.multiProcessorCount);
+  if(out8 && !outputs_on_device) { CUDA_TRY(e->d_out8.reserve((size_t) n * 8)); B.out8 = e->d_out8.p; } else B.out8 = out8;
+  B.out_stage = nullptr;   // stage already lives in d_stage
+  CUDA_TRY(e->d_partial.reserve((size_t) gridB * nbins * 12)); CUDA_TRY(e->d_sums.reserve((size_t) nbins * 12));
+  B.partial = e->d_partial.p;
+  {
+    Timer tm(e, 1);
+    k_widom_ewald<<<gridB, warpsB * 32, smemB, e->stream>>>(e->P, B);
+    k_reduce_partials<<<(nbins * 12 + 63) / 64, 64, 0, e->stream>>>(e->d_partial.p, gridB, nbins * 12, e->d_sums.p);
+    e->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    tm.stop(2);
+  }
+  // ---- outputs
+  std::vector<double> hs((size_t) nbins * 12);
+  CUDA_TRY(cudaMemcpyAsync(hs.data(), e->d_sums.p, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if(out8 && !outputs_on_device) CUDA_TRY(cudaMemcpyAsync(out8, e->d_out8.p, (size_t) n * 8 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if(stage)
+  {
+    if(outputs_on_device) CUDA_TRY(cudaMemcpyAsync(stage, e->d_stage.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
+    else CUDA_TRY(cudaMemcpyAsync(stage, e->d_stage.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if(sums) for(size_t i = 0; i < hs.size(); i++) sums[i] = hs[i];
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- instrumentation
+int gb_launch_count(gb_engine* e, int64_t* n, int32_t reset)
+{
+  if(!e) return fail(GB_ERR_ARG, "null engine");
+  if(n) *n = e->launches;
+  if(reset) e->launches = 0;
+  return GB_OK;
+}
+
+int gb_timing_enable(gb_engine* e, int32_t on) { if(!e) return fail(GB_ERR_ARG, "null engine"); e->timing = on != 0; return GB_OK; }
+
+int gb_timing_read(gb_engine* e, int32_t family, double* ms, int64_t* launches, int32_t reset)
+{
+  if(!e) return fail(GB_ERR_ARG, "null engine");
+  double m = family == 0 ? e->ms_pair : (family == 1 ? e->ms_ewald : e->ms_pair + e->ms_ewald);
+  long long l = family == 0 ? e->n_pair : (family == 1 ? e->n_ewald : e->n_pair + e->n_ewald);
+  if(ms) *ms = m;
+  if(launches) *launches = l;
+  if(reset) { e->ms_pair = e->ms_ewald = 0.0; e->n_pair = e->n_ewald = 0; }
+  return GB_OK;
+}
+
+int gb_measure_fp64_peak(gb_engine* e, double* tflops)
+{
+  if(!e || !tflops) return fail(GB_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const int blocks = e->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  CUDA_TRY(e->d_scratch.reserve((size_t) blocks * threads));
+  float best = 1e30f;
+  for(int rep = 0; rep < 4; rep++)
+  {
+    cudaEventRecord(e->ev0, e->stream);
+    k_fp64_peak<<<blocks, threads, 0, e->stream>>>(e->d_scratch.p, iters, 1.0 + rep);
+    cudaEventRecord(e->ev1, e->stream);
+    CUDA_TRY(cudaEventSynchronize(e->ev1));
+    float ms = 0.f; cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    if(rep > 0 && ms < best) best = ms;
+    e->launches++;
+  }
+  const double flop = 2.0 * 64.0 * (double) iters * blocks * threads;
+  *tflops = flop / (best * 1e-3) / 1e12;
+  return GB_OK;
+}
+
+} // extern "C"
+#include "moves_stub.inc"

@@ -1,0 +1,664 @@
+// graspa_b200 -- kernels of the sm_100a energy engine (included by engine.cu).
+#pragma once
+#include "common.cuh"
+#include "pair.cuh"
+#include "ewald.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// small state kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_frac_update(DevParams P, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                              double* fx, double* fy, double* fz, int start, int count)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < count) to_frac(P, x[start + i], y[start + i], z[start + i], fx[start + i], fy[start + i], fz[start + i]);
+}
+
+// staged pack of the framework (all host components' live atoms): [fx | fy | fz | q | type], each npad long
+__global__ void k_build_pack(const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
+                             const double* __restrict__ q, const double* __restrict__ scoul, const int* __restrict__ type,
+                             SegList L, int npad, double* pack)
+{
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if(g >= npad) return;
+  int* ptype = reinterpret_cast<int*>(pack + 4 * (size_t) npad);
+  int src = -1, acc = 0;
+  for(int s = 0; s < L.nseg; s++) { if(g >= acc && g < acc + L.count[s]) src = L.start[s] + (g - acc); acc += L.count[s]; }
+  if(src >= 0)
+  {
+    pack[g] = fx[src]; pack[npad + g] = fy[src]; pack[2 * (size_t) npad + g] = fz[src];
+    pack[3 * (size_t) npad + g] = q[src] * scoul[src]; ptype[g] = type[src];
+  }
+  else { pack[g] = 0.0; pack[npad + g] = 0.0; pack[2 * (size_t) npad + g] = 0.0; pack[3 * (size_t) npad + g] = 0.0; ptype[g] = 0; }
+}
+
+// stage `bytes` of global memory into shared memory with TMA bulk copies (<= 32 KB each) on one mbarrier
+__device__ __forceinline__ void stage_bulk(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  if(threadIdx.x == 0)
+  {
+    mbar_init(bar, 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar, bytes);
+    uint32_t off = 0;
+    while(off < bytes)
+    {
+      uint32_t chunk = bytes - off; if(chunk > 32768u) chunk = 32768u;
+      tma_bulk_g2s(reinterpret_cast<char*>(dst) + off, reinterpret_cast<const char*>(src) + off, chunk, bar);
+      off += chunk;
+    }
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic trial-group energies: one CTA per trial group, warps split the atom ranges, fixed-order reduce.
+// Replaces Calculate_Multiple_Trial_Energy_VDWReal + Host_sum_Widom_HGGG_SEPARATE for caller-supplied trials
+// and is the energy step of the single-move CBMC stages.
+// ---------------------------------------------------------------------------------------------
+struct TrialBuf            // device arrays of trial atoms (Sims.New), group-major
+{
+  const double* __restrict__ fx; const double* __restrict__ fy; const double* __restrict__ fz;
+  const double* __restrict__ q;      // charge * scaleCoul
+  const double* __restrict__ scale;
+  const int*    __restrict__ type;
+};
+
+template <int CS>
+__device__ __forceinline__ void group_energy_cta(const DevParams& P, const SysView& S, const SegList& L, const TrialBuf& B,
+                                                 int group, int cs, int new_comp, int new_molid, int excl_comp, int excl_mol,
+                                                 TrialGroup* T, WarpQueue* Qall, double* red /* [nwarps][8] */, double* out6, int* out_flag)
+{
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = lane_id();
+  if(threadIdx.x < cs)
+  {
+    const int j = group * cs + threadIdx.x;
+    T->fx[threadIdx.x] = B.fx[j]; T->fy[threadIdx.x] = B.fy[j]; T->fz[threadIdx.x] = B.fz[j];
+    T->q[threadIdx.x] = B.q[j]; T->scale[threadIdx.x] = B.scale[j]; T->type[threadIdx.x] = B.type[j];
+  }
+  __syncthreads();
+  double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
+  pair_group<CS>(P, S, S, L, new_comp, new_molid, excl_comp, excl_mol, T, cs, Qall + warp, warp, nwarps, e6, flag);
+#pragma unroll
+  for(int k = 0; k < 6; k++) e6[k] = warp_sum(e6[k]);
+  flag = __any_sync(0xffffffffu, flag);
+  if(lane == 0) { for(int k = 0; k < 6; k++) red[warp * 8 + k] = e6[k]; red[warp * 8 + 6] = flag ? 1.0 : 0.0; }
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    double s[7] = {0, 0, 0, 0, 0, 0, 0};
+    for(int w = 0; w < nwarps; w++) for(int k = 0; k < 7; k++) s[k] += red[w * 8 + k];
+    for(int k = 0; k < 6; k++) out6[k] = s[k];
+    *out_flag = s[6] > 0.0 ? 1 : 0;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+k_trial_energies(DevParams P, SysView S, SegList L, TrialBuf B, int cs, int new_comp, int new_molid, int excl_comp, int excl_mol,
+                 double* out6 /* [ngroups][6] */, int* out_flag)
+{
+  __shared__ TrialGroup T;
+  __shared__ WarpQueue Q[8];
+  __shared__ double red[8 * 8];
+  const int g = blockIdx.x;
+  if(cs == 1)      group_energy_cta<1>(P, S, L, B, g, cs, new_comp, new_molid, excl_comp, excl_mol, &T, Q, red, out6 + 6 * g, out_flag + g);
+  else if(cs == 2) group_energy_cta<2>(P, S, L, B, g, cs, new_comp, new_molid, excl_comp, excl_mol, &T, Q, red, out6 + 6 * g, out_flag + g);
+  else             group_energy_cta<0>(P, S, L, B, g, cs, new_comp, new_molid, excl_comp, excl_mol, &T, Q, red, out6 + 6 * g, out_flag + g);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rosenbluth / Boltzmann stage inside one warp (mc_widom.h:14-39, 47-86, 305-383, 568-611).
+// Lane t holds trial t.  Sums run sequentially in trial order like the host code they replace.
+// ---------------------------------------------------------------------------------------------
+struct RosenResult { int success; int sel_lane; int nsurv; double R; double R_minus_sel; };
+
+__device__ __forceinline__ RosenResult rosenbluth_warp(double lb, bool surv, int ntr, double uniform, bool do_select)
+{
+  RosenResult r; r.success = 0; r.sel_lane = 0; r.nsurv = 0; r.R = 0.0; r.R_minus_sel = 0.0;
+  const int lane = lane_id();
+  const unsigned mask = __ballot_sync(0xffffffffu, surv && lane < ntr);
+  r.nsurv = __popc(mask);
+  if(mask == 0u) return r;
+  double largest = -INFINITY;
+  for(unsigned m = mask; m; m &= m - 1) { const int b = __ffs(m) - 1; largest = fmax(largest, __shfl_sync(0xffffffffu, lb, b)); }
+  int sel = __ffs(mask) - 1;
+  if(do_select)
+  {
+    double sum = 0.0;
+    for(unsigned m = mask; m; m &= m - 1) { const int b = __ffs(m) - 1; sum += exp(__shfl_sync(0xffffffffu, lb, b) - largest); }
+    const double ws = uniform * sum;
+    unsigned m = mask; int b = __ffs(m) - 1; m &= m - 1;
+    double cumw = exp(__shfl_sync(0xffffffffu, lb, b) - largest);
+    while(cumw < ws && m) { b = __ffs(m) - 1; m &= m - 1; cumw += exp(__shfl_sync(0xffffffffu, lb, b) - largest); }
+    sel = b;
+  }
+  double R = 0.0, Rsel = 0.0;
+  for(unsigned m = mask; m; m &= m - 1)
+  {
+    const int b = __ffs(m) - 1; const double w = exp(__shfl_sync(0xffffffffu, lb, b));
+    R += w; if(b == sel) Rsel = w;
+  }
+  r.sel_lane = sel; r.R = R; r.R_minus_sel = R - Rsel;
+  r.success = 1;
+  return r;
+}
+
+// quaternion rotation of one vector, mc_utilities.h:423-457
+__device__ __forceinline__ void rotate_quaternion(double& vx, double& vy, double& vz, double u, double v, double w)
+{
+  const double pi = 3.14159265358979323846;
+  double s1, c1, s2, c2;
+  sincos(2 * pi * v, &s1, &c1); sincos(2 * pi * w, &s2, &c2);
+  const double a = sqrt(1 - u), b = sqrt(u);
+  const double q0 = a * s1, q1 = a * c1, q2 = b * s2, q3 = b * c2;
+  const double a01 = q0 * q1, a02 = q0 * q2, a03 = q0 * q3, a11 = q1 * q1, a12 = q1 * q2, a13 = q1 * q3;
+  const double a22 = q2 * q2, a23 = q2 * q3, a33 = q3 * q3;
+  const double r0 = 1.0 - 2.0 * (a22 + a33), r1 = 2.0 * (a12 - a03), r2 = 2.0 * (a13 + a02);
+  const double r3 = 2.0 * (a12 + a03), r4 = 1.0 - 2.0 * (a11 + a33), r5 = 2.0 * (a23 - a01);
+  const double r6 = 2.0 * (a13 - a02), r7 = 2.0 * (a23 + a01), r8 = 1.0 - 2.0 * (a11 + a22);
+  const double x = vx * r0 + vy * r1 + vz * r2;
+  const double y = vx * r3 + vy * r4 + vz * r5;
+  const double z = vx * r6 + vy * r7 + vz * r8;
+  vx = x; vy = y; vz = z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched Widom, stage A: first bead + chain growth for n independent ghost insertions.
+// One warp = one insertion at a time (static stride over insertions -> deterministic results);
+// the framework pack is staged once per CTA by TMA bulk copies and stays resident in shared memory.
+// Follows Widom_Move_FirstBead_PARTIAL / Widom_Move_Chain_PARTIAL (mc_widom.h:385-614) with MoveType CBMC_INSERTION.
+// ---------------------------------------------------------------------------------------------
+struct WidomA
+{
+  const double* __restrict__ pool3;           // double3 pool
+  const long long* __restrict__ fb_index; const long long* __restrict__ or_index;
+  const double* __restrict__ uni;             // 2 per insertion
+  long long n;
+  int ntrials, norient, ms, comp, new_molid;
+  // template molecule = slot 0 of the component (mc_widom.h:256): Cartesian positions, charge*scaleCoul, type
+  const double* __restrict__ tx; const double* __restrict__ ty; const double* __restrict__ tz;
+  const double* __restrict__ tq; const double* __restrict__ tscoul; const int* __restrict__ ttype;
+  const double* __restrict__ pack; int npad; int use_pack;
+  double* rec;        // per insertion: [W12, HGv, HGr, GGv, GGr, x0,y0,z0, x1,...]  stride 5 + 3*ms
+  int* stage;         // 0 ok, 1 first bead failed, 2 chain failed
+};
+
+template <int CS>
+__device__ __forceinline__ void widom_chain_energy(const DevParams& P, const SysView& Sg, const SysView& Ss, const SegList& L,
+                                                   const WidomA& A, TrialGroup* T, WarpQueue* Q, const double* chain_f /* [norient][cs][3] frac */,
+                                                   int cs, double* my_e, int& my_flag)
+{
+  const int lane = lane_id();
+  for(int o = 0; o < A.norient; o++)
+  {
+    if(lane < cs)
+    {
+      const double* c = chain_f + (size_t)(o * cs + lane) * 3;
+      T->fx[lane] = c[0]; T->fy[lane] = c[1]; T->fz[lane] = c[2];
+      T->q[lane] = A.tq[1 + lane] * A.tscoul[1 + lane]; T->scale[lane] = 1.0; T->type[lane] = A.ttype[1 + lane];
+    }
+    __syncwarp();
+    double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
+    pair_group<CS>(P, Sg, Ss, L, A.comp, A.new_molid, -1, -1, T, cs, Q, 0, 1, e6, flag);
+#pragma unroll
+    for(int k = 2; k < 6; k++) e6[k] = warp_sum(e6[k]);
+    flag = __any_sync(0xffffffffu, flag);
+    if(lane == o) { my_e[0] = e6[2]; my_e[1] = e6[3]; my_e[2] = e6[4]; my_e[3] = e6[5]; my_flag = flag; }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(512, 1)
+k_widom_pair(DevParams P, SysView Sg, SegList L, WidomA A)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  double* pack = reinterpret_cast<double*>(smem + 16);
+  const size_t pack_bytes = A.use_pack ? ((size_t) A.npad * 36 + 15) / 16 * 16 : 0;
+  unsigned char* wbase = smem + 16 + pack_bytes;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = lane_id();
+  const int cs = A.ms - 1;
+  const size_t per_warp = (sizeof(TrialGroup) + sizeof(WarpQueue) + (size_t) A.norient * (cs > 0 ? cs : 1) * 6 * sizeof(double) + 15) / 16 * 16;
+  TrialGroup* T = reinterpret_cast<TrialGroup*>(wbase + warp * per_warp);
+  WarpQueue* Q = reinterpret_cast<WarpQueue*>(reinterpret_cast<unsigned char*>(T) + sizeof(TrialGroup));
+  double* chain_f = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(Q) + sizeof(WarpQueue));   // fractional [norient][cs][3]
+  double* chain_c = chain_f + (size_t) A.norient * (cs > 0 ? cs : 1) * 3;                                  // Cartesian
+
+  SysView Ss = Sg;
+  if(A.use_pack)
+  {
+    stage_bulk(pack, A.pack, (uint32_t) pack_bytes, bar);
+    Ss.fx = pack; Ss.fy = pack + A.npad; Ss.fz = pack + 2 * (size_t) A.npad; Ss.q = pack + 3 * (size_t) A.npad;
+    Ss.type = reinterpret_cast<const int*>(pack + 4 * (size_t) A.npad);
+    Ss.scale = nullptr; Ss.scoul = nullptr; Ss.molid = nullptr;
+  }
+  const long long gw = (long long) blockIdx.x * nwarps + warp, tw = (long long) gridDim.x * nwarps;
+  const int rec_stride = 5 + 3 * A.ms;
+  const double q0 = A.tq[0] * A.tscoul[0]; const int type0 = A.ttype[0];
+
+  for(long long ins = gw; ins < A.n; ins += tw)
+  {
+    const long long fb_off = A.fb_index ? A.fb_index[ins] : ins * (A.ntrials + A.norient);
+    const long long or_off = A.or_index ? A.or_index[ins] : fb_off + A.ntrials;
+    // ---------------- first bead: BoxLength o random, mc_widom.h:137-138
+    double px = 0, py = 0, pz = 0, fsx = 0, fsy = 0, fsz = 0;
+    if(lane < A.ntrials)
+    {
+      const double* r = A.pool3 + 3 * (fb_off + lane);
+      px = P.cell[0] * r[0]; py = P.cell[4] * r[1]; pz = P.cell[8] * r[2];
+      to_frac(P, px, py, pz, fsx, fsy, fsz);
+    }
+    double my_e[4] = {0, 0, 0, 0}; int my_flag = 0;
+    for(int t = 0; t < A.ntrials; t++)
+    {
+      const double bx = __shfl_sync(0xffffffffu, fsx, t), by = __shfl_sync(0xffffffffu, fsy, t), bz = __shfl_sync(0xffffffffu, fsz, t);
+      if(lane == 0) { T->fx[0] = bx; T->fy[0] = by; T->fz[0] = bz; T->q[0] = q0; T->scale[0] = 1.0; T->type[0] = type0; }
+      __syncwarp();
+      double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
+      pair_group<1>(P, Sg, Ss, L, A.comp, A.new_molid, -1, -1, T, 1, Q, 0, 1, e6, flag);
+#pragma unroll
+      for(int k = 2; k < 6; k++) e6[k] = warp_sum(e6[k]);
+      flag = __any_sync(0xffffffffu, flag);
+      if(lane == t) { my_e[0] = e6[2]; my_e[1] = e6[3]; my_e[2] = e6[4]; my_e[3] = e6[5]; my_flag = flag; }
+      __syncwarp();
+    }
+    double tot = my_e[0] + my_e[2]; if(P.vdw_real_bias) tot += my_e[1] + my_e[3];
+    RosenResult r1 = rosenbluth_warp(-P.beta * tot, !my_flag, A.ntrials, A.uni[2 * ins], true);
+    double W = 0.0; int ok = r1.success && !(r1.R < 1e-150);
+    const int sfb = r1.sel_lane;
+    double efb[4];
+#pragma unroll
+    for(int k = 0; k < 4; k++) efb[k] = __shfl_sync(0xffffffffu, my_e[k], sfb);
+    if(ok)
+    {
+      W = r1.R / (double) A.ntrials;
+      if(!P.vdw_real_bias) W *= exp(-P.beta * (efb[1] + efb[3]));
+      if(W <= 1e-150) ok = 0;
+    }
+    double* rec = A.rec + (size_t) ins * rec_stride;
+    if(!ok) { if(lane == 0) { A.stage[ins] = 1; rec[0] = 0.0; } continue; }
+    const double fbx = __shfl_sync(0xffffffffu, px, sfb), fby = __shfl_sync(0xffffffffu, py, sfb), fbz = __shfl_sync(0xffffffffu, pz, sfb);
+    double ech[4] = {0, 0, 0, 0}; int so = 0;
+    // ---------------- chain: mc_widom.h:509-614
+    if(cs > 0)
+    {
+      if(lane < A.norient)
+      {
+        const double* r = A.pool3 + 3 * (or_off + lane);
+        for(int a = 0; a < cs; a++)
+        {
+          double vx = A.tx[1 + a] - A.tx[0], vy = A.ty[1 + a] - A.ty[0], vz = A.tz[1 + a] - A.tz[0];
+          rotate_quaternion(vx, vy, vz, r[0], r[1], r[2]);
+          const double cx = fbx + vx, cy = fby + vy, cz = fbz + vz;
+          double* cc = chain_c + (size_t)(lane * cs + a) * 3; cc[0] = cx; cc[1] = cy; cc[2] = cz;
+          double* cf = chain_f + (size_t)(lane * cs + a) * 3; to_frac(P, cx, cy, cz, cf[0], cf[1], cf[2]);
+        }
+      }
+      __syncwarp();
+      my_e[0] = my_e[1] = my_e[2] = my_e[3] = 0.0; my_flag = 0;
+      if(cs == 1)      widom_chain_energy<1>(P, Sg, Ss, L, A, T, Q, chain_f, cs, my_e, my_flag);
+      else if(cs == 2) widom_chain_energy<2>(P, Sg, Ss, L, A, T, Q, chain_f, cs, my_e, my_flag);
+      else if(cs == 3) widom_chain_energy<3>(P, Sg, Ss, L, A, T, Q, chain_f, cs, my_e, my_flag);
+      else             widom_chain_energy<0>(P, Sg, Ss, L, A, T, Q, chain_f, cs, my_e, my_flag);
+      double tot2 = my_e[0] + my_e[2]; if(P.vdw_real_bias) tot2 += my_e[1] + my_e[3];
+      RosenResult r2 = rosenbluth_warp(-P.beta * tot2, !my_flag, A.norient, A.uni[2 * ins + 1], true);
+      int ok2 = r2.success && !(r2.R < 1e-150);
+      so = r2.sel_lane;
+#pragma unroll
+      for(int k = 0; k < 4; k++) ech[k] = __shfl_sync(0xffffffffu, my_e[k], so);
+      if(ok2)
+      {
+        double W2 = r2.R / (double) A.norient;
+        if(!P.vdw_real_bias) W2 *= exp(-P.beta * (ech[1] + ech[3]));
+        W *= W2;
+        if(W <= 1e-150) ok2 = 0;
+      }
+      if(!ok2) { if(lane == 0) { A.stage[ins] = 2; rec[0] = 0.0; } continue; }
+    }
+    if(lane == 0)
+    {
+      A.stage[ins] = 0;
+      rec[0] = W;
+      for(int k = 0; k < 4; k++) rec[1 + k] = efb[k] + ech[k];
+      rec[5] = fbx; rec[6] = fby; rec[7] = fbz;
+    }
+    if(lane < 3 * cs) rec[8 + lane] = chain_c[(size_t) so * cs * 3 + lane];
+    for(int k = 32 + lane; k < 3 * cs; k += 32) rec[8 + k] = chain_c[(size_t) so * cs * 3 + k];
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched Widom, stage B: Ewald Fourier delta of the grown molecule (GPU_EwaldDifference_General with INSERTION,
+// Ewald_Energy_Functions.h:438-580), exclusion constant, tail correction, final Rosenbluth weight
+// (mc_swap_utilities.h:96-108) and the block-average sums (RecordRosen data_struct.h:627-652, axpy.cu:177-185).
+// One warp per insertion; the active-k table (k, temp, stored structure factors) is TMA-staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+struct WidomB
+{
+  const double* rec; const int* stage; long long n; int ms;
+  const double* __restrict__ tq; const double* __restrict__ tscoul;   // template charges
+  // staged k table: [temp (nact) | sa (2 nact) | sf (2 nact) | kpack (nact int)]
+  const double* __restrict__ ktab; int nact; int nact_pad; int stage_ktab;
+  int do_ewald;
+  double excl_const;       // (ExclusionIntra + ExclusionAtom) * scale^2, Ewald_Energy_Functions.h:553-556
+  double tail;             // TailCorrectionDifference for this component (same for every ghost insertion)
+  int nbins;
+  double* out8; int* out_stage;      // may be null
+  double* partial;                   // [gridDim.x][nbins][12]
+};
+
+__global__ void __launch_bounds__(256, 1)
+k_widom_ewald(DevParams P, WidomB B)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  double* ktab = reinterpret_cast<double*>(smem + 16);
+  const size_t ktab_bytes = (B.do_ewald && B.stage_ktab) ? (size_t) B.nact_pad * 44 : 0;
+  unsigned char* wbase = smem + 16 + (ktab_bytes + 15) / 16 * 16;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = lane_id();
+  const int n = B.ms;
+  const int kx1 = P.kmax[0] + 1, ky1 = P.kmax[1] + 1, kz1 = P.kmax[2] + 1;
+  const size_t per_warp = ((size_t) n * (kx1 + ky1 + kz1) * sizeof(cplx) + (size_t) n * 4 * sizeof(double) + 15) / 16 * 16;
+  cplx* ex = reinterpret_cast<cplx*>(wbase + warp * per_warp);
+  cplx* ey = ex + (size_t) n * kx1; cplx* ez = ey + (size_t) n * ky1;
+  double* qeff = reinterpret_cast<double*>(ez + (size_t) n * kz1);
+  double* mpos = qeff + n;
+  double* bins = reinterpret_cast<double*>(wbase + nwarps * per_warp);   // [nwarps][nbins][12]
+
+  const double* g_temp = B.ktab; const double* g_sa = B.ktab + B.nact_pad; const double* g_sf = B.ktab + 3 * (size_t) B.nact_pad;
+  const int* g_kp = reinterpret_cast<const int*>(B.ktab + 5 * (size_t) B.nact_pad);
+  if(B.do_ewald && B.stage_ktab)
+  {
+    stage_bulk(ktab, B.ktab, (uint32_t) ktab_bytes, bar);
+    g_temp = ktab; g_sa = ktab + B.nact_pad; g_sf = ktab + 3 * (size_t) B.nact_pad;
+    g_kp = reinterpret_cast<const int*>(ktab + 5 * (size_t) B.nact_pad);
+  }
+  for(int k = lane; k < B.nbins * 12; k += 32) bins[(size_t) warp * B.nbins * 12 + k] = 0.0;
+  __syncwarp();
+  const long long gw = (long long) blockIdx.x * nwarps + warp, tw = (long long) gridDim.x * nwarps;
+  const int rec_stride = 5 + 3 * B.ms;
+  for(long long ins = gw; ins < B.n; ins += tw)
+  {
+    const int st = B.stage[ins];
+    const int bin = (int)((ins * B.nbins) / B.n);
+    double* mybin = bins + ((size_t) warp * B.nbins + bin) * 12;
+    double o8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if(st == 0)
+    {
+      const double* rec = B.rec + (size_t) ins * rec_stride;
+      double W = rec[0];
+      double same = 0.0, cross = 0.0;
+      if(B.do_ewald)
+      {
+        for(int k = lane; k < 3 * n; k += 32) mpos[k] = rec[5 + k];
+        for(int k = lane; k < n; k += 32) qeff[k] = B.tscoul[k] * B.tq[k];
+        __syncwarp();
+        build_eik(P, mpos, n, ex, ey, ez, lane, 32);
+        __syncwarp();
+        for(int kk = lane; kk < B.nact; kk += 32)
+        {
+          int kx, ky, kz; unpack_k(g_kp[kk], kx, ky, kz);
+          const cplx d = ck_sum(ex, ey, ez, qeff, n, 0, n, kx, ky, kz);
+          const double temp = g_temp[kk];
+          const double ore = g_sa[2 * kk], oim = g_sa[2 * kk + 1];
+          const double nre = ore + d.re, nim = oim + d.im;
+          same += temp * (nre * nre + nim * nim);
+          same -= temp * (ore * ore + oim * oim);
+          cross += temp * (g_sf[2 * kk] * d.re + g_sf[2 * kk + 1] * d.im);
+        }
+        same = warp_sum(same); cross = warp_sum(cross);
+        same -= B.excl_const; cross *= 2.0;
+        W *= exp(-P.beta * (same + cross));
+        __syncwarp();
+      }
+      W *= exp(-P.beta * B.tail);
+      o8[0] = W; o8[1] = rec[1]; o8[2] = rec[2]; o8[3] = rec[3]; o8[4] = rec[4]; o8[5] = same; o8[6] = cross; o8[7] = B.tail;
+    }
+    if(lane == 0)
+    {
+      if(B.out8) for(int k = 0; k < 8; k++) B.out8[(size_t) ins * 8 + k] = o8[k];
+      if(B.out_stage) B.out_stage[ins] = st;
+      mybin[0] += o8[0]; mybin[1] += o8[0] * o8[0]; mybin[2] += 1.0;
+      for(int k = 0; k < 7; k++) mybin[3 + k] += o8[0] * o8[1 + k];
+      if(st != 0) mybin[10] += 1.0;
+    }
+  }
+  __syncthreads();
+  // fixed-order CTA reduction of the per-warp bins
+  for(int k = threadIdx.x; k < B.nbins * 12; k += blockDim.x)
+  {
+    double s = 0.0;
+    for(int w = 0; w < nwarps; w++) s += bins[(size_t) w * B.nbins * 12 + k];
+    B.partial[(size_t) blockIdx.x * B.nbins * 12 + k] = s;
+  }
+}
+
+__global__ void k_reduce_partials(const double* __restrict__ partial, int nparts, int width, double* out)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= width) return;
+  double s = 0.0;
+  for(int p = 0; p < nparts; p++) s += partial[(size_t) p * width + k];
+  out[k] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-move Ewald delta: eik tables + per-k delta in one launch (replaces Initialize_WaveVector_General +
+// Fourier_Ewald_Diff + the host block sum).  Threads run over ACTIVE k; writes tempEik; last CTA sums the
+// CTA partials in fixed order and stores {same, 2*cross}.
+// ---------------------------------------------------------------------------------------------
+struct EwaldDeltaArgs
+{
+  const double* __restrict__ pos3;      // (nold + nnew) xyz
+  const double* __restrict__ qeff;      // charge * scaleCoul
+  int nold, nnew;
+  KTable K;
+  const double* __restrict__ same_sf;   // full arrays (nvec complex)
+  const double* __restrict__ cross_sf;
+  double* temp_sf;
+  double* partial;                      // [gridDim.x][2]
+  unsigned int* ticket;
+  double* result;                       // {same, 2*cross}
+};
+
+__global__ void __launch_bounds__(128)
+k_ewald_delta(DevParams P, EwaldDeltaArgs A)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int n = A.nold + A.nnew;
+  const int kx1 = P.kmax[0] + 1, ky1 = P.kmax[1] + 1, kz1 = P.kmax[2] + 1;
+  cplx* ex = reinterpret_cast<cplx*>(smem);
+  cplx* ey = ex + (size_t) n * kx1; cplx* ez = ey + (size_t) n * ky1;
+  double* qeff = reinterpret_cast<double*>(ez + (size_t) n * kz1);
+  __shared__ double red[2][4];
+  __shared__ bool last;
+  for(int k = threadIdx.x; k < n; k += blockDim.x) qeff[k] = A.qeff[k];
+  build_eik(P, A.pos3, n, ex, ey, ez, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+  double same = 0.0, cross = 0.0;
+  if(kk < A.K.nact)
+  {
+    int kx, ky, kz; unpack_k(A.K.kpack[kk], kx, ky, kz);
+    const cplx co = ck_sum(ex, ey, ez, qeff, n, 0, A.nold, kx, ky, kz);
+    const cplx cn = ck_sum(ex, ey, ez, qeff, n, A.nold, n, kx, ky, kz);
+    const double temp = A.K.temp[kk];
+    const int slot = A.K.slot[kk];
+    const double ore = A.same_sf[2 * slot], oim = A.same_sf[2 * slot + 1];
+    const double nre = ore + cn.re - co.re, nim = oim + cn.im - co.im;
+    same += temp * (nre * nre + nim * nim);
+    same -= temp * (ore * ore + oim * oim);
+    A.temp_sf[2 * slot] = nre; A.temp_sf[2 * slot + 1] = nim;
+    cross += temp * (A.cross_sf[2 * slot] * (cn.re - co.re) + A.cross_sf[2 * slot + 1] * (cn.im - co.im));
+  }
+  same = warp_sum(same); cross = warp_sum(cross);
+  if(lane_id() == 0) { red[0][threadIdx.x >> 5] = same; red[1][threadIdx.x >> 5] = cross; }
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    double s = 0.0, c = 0.0;
+    for(int w = 0; w < (int)(blockDim.x >> 5); w++) { s += red[0][w]; c += red[1][w]; }
+    A.partial[2 * blockIdx.x] = s; A.partial[2 * blockIdx.x + 1] = c;
+    __threadfence();
+    const unsigned int t = atomicAdd(A.ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if(last && threadIdx.x == 0)
+  {
+    __threadfence();
+    double s = 0.0, c = 0.0;
+    const volatile double* p = A.partial;
+    for(unsigned int b = 0; b < gridDim.x; b++) { s += p[2 * b]; c += p[2 * b + 1]; }
+    A.result[0] = s; A.result[1] = 2.0 * c;
+    *A.ticket = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Totals
+// ---------------------------------------------------------------------------------------------
+// total structure factors + Fourier energies (Ewald_Total ewald_preparation.h:84-171 / TotalFourierEwald
+// Ewald_Energy_Functions.h:834-1147): one CTA per active k, threads stride over atoms.
+struct EwaldTotalArgs
+{
+  const double* __restrict__ x; const double* __restrict__ y; const double* __restrict__ z;
+  const double* __restrict__ q; const double* __restrict__ scoul;
+  SegList L;                 // all live ranges; kind 0/1 = framework (comp < nhost), 2 = adsorbate
+  KTable K;
+  double* sf_ads; double* sf_fw;   // full arrays, written at active slots (others must be pre-zeroed)
+  double* ek;                       // [nact][3] per-k GG, HH, HG contributions
+  int has_fw;
+};
+
+__global__ void __launch_bounds__(128)
+k_ewald_total(DevParams P, EwaldTotalArgs A)
+{
+  const int kk = blockIdx.x;
+  int kx, ky, kz; unpack_k(A.K.kpack[kk], kx, ky, kz);
+  double are = 0, aim = 0, fre = 0, fim = 0;
+  for(int s = 0; s < A.L.nseg; s++)
+  {
+    const bool fw = A.L.kind[s] != 2;
+    for(int i = A.L.start[s] + threadIdx.x; i < A.L.start[s] + A.L.count[s]; i += blockDim.x)
+    {
+      double sx, sy, sz; to_frac(P, A.x[i], A.y[i], A.z[i], sx, sy, sz);
+      // phase of exp(i k.r) = 2 pi (kx sx + ky sy + kz sz); evaluated directly (no recurrence) with exact integer k
+      const double ph = 2 * GBK_PI * ((double) kx * sx + (double) ky * sy + (double) kz * sz);
+      double sn, cs; sincos(ph, &sn, &cs);
+      const double w = A.scoul[i] * A.q[i];
+      if(fw) { fre += w * cs; fim += w * sn; } else { are += w * cs; aim += w * sn; }
+    }
+  }
+  __shared__ double red[4][4];
+  are = warp_sum(are); aim = warp_sum(aim); fre = warp_sum(fre); fim = warp_sum(fim);
+  const int w = threadIdx.x >> 5;
+  if(lane_id() == 0) { red[w][0] = are; red[w][1] = aim; red[w][2] = fre; red[w][3] = fim; }
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    double v[4] = {0, 0, 0, 0};
+    for(int i = 0; i < (int)(blockDim.x >> 5); i++) for(int k = 0; k < 4; k++) v[k] += red[i][k];
+    if(!A.has_fw) { v[0] += v[2]; v[1] += v[3]; v[2] = 0.0; v[3] = 0.0; }   // no framework: everything is "adsorbate" (ewald_preparation.h:141-150)
+    const double temp = A.K.temp[kk];
+    const int slot = A.K.slot[kk];
+    if(A.sf_ads) { A.sf_ads[2 * slot] = v[0]; A.sf_ads[2 * slot + 1] = v[1]; A.sf_fw[2 * slot] = v[2]; A.sf_fw[2 * slot + 1] = v[3]; }
+    A.ek[3 * kk]     = temp * (v[0] * v[0] + v[1] * v[1]);
+    A.ek[3 * kk + 1] = temp * (v[2] * v[2] + v[3] * v[3]);
+    A.ek[3 * kk + 2] = temp * (v[2] * v[0] + v[3] * v[1]) * 2.0;
+  }
+}
+
+// self + intra-molecular exclusion (ewald_preparation.h:176-227): one thread per molecule
+struct ExclArgs
+{
+  const double* __restrict__ x; const double* __restrict__ y; const double* __restrict__ z;
+  const double* __restrict__ q; const double* __restrict__ scoul;
+  int start, nmol, ms;
+  double* out;      // [nmol][2] self, intra
+};
+__global__ void k_ewald_exclusion(DevParams P, ExclArgs A)
+{
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if(m >= A.nmol) return;
+  const int a0 = A.start + m * A.ms;
+  const double pself = P.prefactor * P.alpha / sqrt(GBK_PI);
+  double self = 0.0, intra = 0.0;
+  for(int i = a0; i < a0 + A.ms; i++) { const double f = A.scoul[i] * A.q[i]; self += pself * f * f; }
+  for(int i = a0; i < a0 + A.ms - 1; i++)
+  {
+    const double fa = A.scoul[i] * A.q[i];
+    double si, sj, sk; to_frac(P, A.x[i], A.y[i], A.z[i], si, sj, sk);
+    for(int j = i + 1; j < a0 + A.ms; j++)
+    {
+      const double fb = A.scoul[j] * A.q[j];
+      double ti, tj, tk; to_frac(P, A.x[j], A.y[j], A.z[j], ti, tj, tk);
+      const double r = sqrt(min_image_r2(P, si - ti, sj - tj, sk - tk));
+      intra += P.prefactor * fa * fb * erf(P.alpha * r) / r;
+    }
+  }
+  A.out[2 * m] = self; A.out[2 * m + 1] = intra;
+}
+
+// total VDW + real: every live atom is a one-atom "trial group" against all live atoms with the own-molecule
+// exclusion; 0.5 x the double-counted sum, exactly the reference's CPU loop structure (VDW_Coulomb.cu:94-206).
+struct TotalArgs { SegList L; int nhost; double* out; /* [natoms_live][6] */ const int* __restrict__ comp_of; };
+
+__global__ void __launch_bounds__(128)
+k_total_vdw_real(DevParams P, SysView S, TotalArgs A)
+{
+  __shared__ TrialGroup T;
+  __shared__ WarpQueue Q[4];
+  __shared__ double red[4 * 8];
+  // which live atom is this CTA's "trial"
+  int g = blockIdx.x, seg = 0;
+  while(seg < A.L.nseg && g >= A.L.count[seg]) { g -= A.L.count[seg]; seg++; }
+  const int i = A.L.start[seg] + g;
+  const int mycomp = A.L.comp[seg];
+  const bool mine_host = mycomp < A.nhost;
+  if(threadIdx.x == 0)
+  {
+    T.fx[0] = S.fx[i]; T.fy[0] = S.fy[i]; T.fz[0] = S.fz[i];
+    T.q[0] = S.q[i] * S.scoul[i]; T.scale[0] = S.scale[i]; T.type[0] = S.type[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
+  // kinds relative to the trial atom: host-host 0, mixed 1, guest-guest 2
+  SegList L = A.L;
+  for(int s = 0; s < L.nseg; s++) { const bool oh = L.comp[s] < A.nhost; L.kind[s] = (mine_host && oh) ? 0 : ((!mine_host && !oh) ? 2 : 1); L.staged[s] = 0; }
+  pair_group<1>(P, S, S, L, mycomp, S.molid[i], -1, -1, &T, 1, Q + warp, warp, nwarps, e6, flag);
+#pragma unroll
+  for(int k = 0; k < 6; k++) e6[k] = warp_sum(e6[k]);
+  if(lane_id() == 0) for(int k = 0; k < 6; k++) red[warp * 8 + k] = e6[k];
+  __syncthreads();
+  if(threadIdx.x < 6)
+  {
+    double s = 0.0;
+    for(int w = 0; w < nwarps; w++) s += red[w * 8 + threadIdx.x];
+    A.out[(size_t) blockIdx.x * 6 + threadIdx.x] = 0.5 * s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 FMA peak microbenchmark (the roofline denominator bench.py reports for the pair kernel)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fp64_peak(double* out, int iters, double seed)
+{
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.9999999, c = 1e-7;
+  for(int i = 0; i < iters; i++)
+  {
+#pragma unroll
+    for(int u = 0; u < 8; u++)
+    {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}

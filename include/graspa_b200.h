@@ -1,0 +1,276 @@
+/* graspa_b200 -- C ABI of the B200-native Monte Carlo energy engine.
+ *
+ * This is the drop-in boundary for gRASPA's data-parallel hot path.
+ * The reference has no FFI; its seam is the set of free functions / kernels that the kept
+ * move drivers (mc_widom.h, mc_swap_utilities.h, mc_swap_moves.h, mc_single_particle.h)
+ * call.  Every entry point below names the reference interface it replaces
+ * (file:line relative to /root/reference/src_clean).  INTEGRATION.md shows the binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all structs are POD; no C++/torch types.
+ *   - every call returns an int status (GB_OK == 0); gb_last_error() gives the text.
+ *     The reference printf+exit()s on CUDA errors (VDW_Coulomb.cuh:58-66); a binding keeps
+ *     that behaviour by checking the status.
+ *   - calls are blocking unless their name ends in _async; one CUDA stream per engine;
+ *     no global state; one engine per GPU (one process per GPU in multi-GPU runs).
+ *   - host pointers may be pageable or pinned; arguments named d_* are DEVICE pointers.
+ *   - there is NO CPU fallback: without a CUDA device gb_engine_create fails.
+ *   - energies are in the reference's internal units (10 J/mol), lengths in Angstrom.
+ *   - FP64 throughout.
+ */
+#ifndef GRASPA_B200_H
+#define GRASPA_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_ABI_VERSION 1
+
+enum {
+  GB_OK = 0,
+  GB_ERR_CUDA = 1,          /* a CUDA runtime call failed */
+  GB_ERR_ARG = 2,           /* bad argument */
+  GB_ERR_STATE = 3,         /* call made before the required upload */
+  GB_ERR_CAPACITY = 4,      /* component out of allocated space (mc_utilities.h:111-115 throws) */
+  GB_ERR_UNIMPLEMENTED = 5
+};
+
+/* MoveTypes, data_struct.h:20 */
+enum { GB_TRANSLATION = 0, GB_ROTATION, GB_SINGLE_INSERTION, GB_SINGLE_DELETION, GB_SPECIAL_ROTATION,
+       GB_INSERTION, GB_DELETION, GB_REINSERTION, GB_CBCF_LAMBDACHANGE, GB_CBCF_INSERTION,
+       GB_CBCF_DELETION, GB_IDENTITY_SWAP, GB_WIDOM };
+/* CBMC_Types, data_struct.h:22 */
+enum { GB_CBMC_INSERTION = 0, GB_CBMC_DELETION, GB_REINSERTION_INSERTION, GB_REINSERTION_RETRACE,
+       GB_IDENTITY_SWAP_NEW, GB_IDENTITY_SWAP_OLD };
+
+typedef struct gb_engine gb_engine;   /* opaque */
+
+/* Boxsize, data_struct.h:865-886 (scalar members; the device pointers of the reference struct are engine-owned) */
+typedef struct {
+  double cell[9];            /* rows = lattice vectors */
+  double inverse_cell[9];
+  double volume;
+  double alpha;
+  double prefactor;          /* 138935.483496 */
+  double reciprocal_cutoff;
+  int32_t kmax[3];
+  int32_t cubic;
+  int32_t use_lammps_ewald;
+  int32_t reserved;
+} gb_box;
+
+/* ForceField, data_struct.h:838-855.  Tables have size*size entries, row = typeA*size + typeB. */
+typedef struct {
+  const double* epsilon; const double* sigma; const double* z; const double* shift; const double* c10;
+  double cutoff_vdw_sq;      /* FF.CutOffVDW (already squared) */
+  double cutoff_coul_sq;
+  double overlap_criteria;
+  int32_t size;
+  int32_t no_charges;
+  int32_t vdw_real_bias;
+  int32_t use1264;
+} gb_forcefield;
+
+/* Tail table, Components::TailCorrection (data_struct.h:720-724, :1166), size*size */
+typedef struct { const int32_t* use_tail; const double* energy; int32_t size; int32_t reserved; } gb_tail_table;
+
+/* One component's Atoms, data_struct.h:788-799 (host side of Copy_Atom_data_to_device, fxn_main.h:46-96).
+ * The first n_live slots are live; slots up to n_alloc are uploaded as given (slot 0 of an adsorbate
+ * always holds the template molecule, read_data.cpp:2122-2147). */
+typedef struct {
+  const double* pos;         /* 3*n_upload, xyz interleaved (double3) */
+  const double* scale; const double* charge; const double* scale_coul;
+  const uint64_t* type; const uint64_t* molid;   /* size_t in the reference */
+  int64_t n_upload;          /* slots given in the arrays above (>= n_live) */
+  int64_t n_live;            /* Atoms.size */
+  int64_t n_alloc;           /* Atoms.Allocate_size */
+  int64_t molsize;           /* Atoms.Molsize */
+} gb_atoms;
+
+/* MoveEnergy, data_struct.h:416-431, same member order */
+typedef struct {
+  double storedHGVDW, storedHGReal, storedHGEwaldE;
+  double HHVDW, HGVDW, GGVDW;
+  double HHReal, HGReal, GGReal;
+  double HHEwaldE, HGEwaldE, GGEwaldE;
+  double TailE, DNN_E;
+} gb_move_energy;
+
+/* Result of one CBMC stage = what CBMC_FirstBead_Finish / the tail of Widom_Move_Chain_PARTIAL leave in
+ * CBMC_Variables (mc_widom.h:305-383, 568-611) */
+typedef struct {
+  double rosenbluth;         /* stage Rosenbluth weight (already / NumberOfTrials, with the VDWRealBias correction) */
+  double stored_r;           /* REINSERTION_INSERTION: Rosenbluth - Rosen[selected]  (mc_widom.h:365) */
+  double energy[4];          /* selected trial: HGVDW, HGReal, GGVDW, GGReal */
+  double selected_pos[3];    /* first-bead stage: position of the selected first bead */
+  int32_t success;           /* Goodconstruction */
+  int32_t selected;          /* REALselected: index among all trials (Trialindex[SelectedTrial]) */
+  int32_t n_survivors;       /* trials without overlap */
+  int32_t reserved;
+} gb_cbmc_result;
+
+/* ------------------------------------------------------------------------------------------------
+ * life cycle
+ * ------------------------------------------------------------------------------------------------ */
+int  gb_abi_version(void);
+const char* gb_last_error(void);
+/* device < 0: current device.  Fails (GB_ERR_CUDA) when no CUDA device is present -- there is no CPU path. */
+int  gb_engine_create(gb_engine** out, int device);
+int  gb_engine_destroy(gb_engine* e);
+int  gb_device_info(gb_engine* e, int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_per_block_optin);
+int  gb_synchronize(gb_engine* e);
+void* gb_stream(gb_engine* e);                       /* cudaStream_t, for callers that time on it */
+
+/* ------------------------------------------------------------------------------------------------
+ * set-up  (replaces fxn_main.h:12-280: Copy_ForceField_to_GPU, Copy_Atom_data_to_device,
+ *          Setup_Temporary_Atoms_Structure, Prepare_Widom, Allocate_Copy_Ewald_Vector; main.cpp:97-104, 243-300)
+ * ------------------------------------------------------------------------------------------------ */
+int  gb_upload_forcefield(gb_engine* e, const gb_forcefield* ff, const gb_tail_table* tail /* may be NULL */);
+int  gb_upload_box(gb_engine* e, const gb_box* box);
+/* declares the component table: n_total components, the first n_host of them framework components */
+int  gb_set_components(gb_engine* e, int32_t n_total, int32_t n_host);
+int  gb_upload_atoms(gb_engine* e, int32_t component, const gb_atoms* atoms);
+/* Atoms of one component back to the host (restart writers, write_data.h:109-263).  Arrays sized n_alloc. */
+int  gb_download_atoms(gb_engine* e, int32_t component, double* pos, double* scale, double* charge, double* scale_coul,
+                       uint64_t* type, uint64_t* molid, int64_t* n_live);
+/* stored structure factors, nvec complex (re,im); Allocate_Copy_Ewald_Vector fxn_main.h:235-280 */
+int  gb_upload_structure_factors(gb_engine* e, const double* adsorbate_eik, const double* framework_eik);
+int  gb_download_structure_factors(gb_engine* e, double* adsorbate_eik, double* framework_eik, double* temp_eik);
+/* rigid exclusion constants per component, Calculate_Exclusion_Energy_Rigid ewald_preparation.h:351-366 */
+int  gb_set_exclusion_constants(gb_engine* e, int32_t component, double exclusion_intra, double exclusion_atom, int32_t rigid, int32_t has_partial_charge);
+/* the device random pool, RandomNumber::DeviceRandom/ResetRandom data_struct.h:1300-1327: n double3 */
+int  gb_upload_random_pool(gb_engine* e, const double* random3, int64_t n);
+/* Widom/CBMC parameters, WidomStruct data_struct.h:1271-1278 and Components::Beta */
+int  gb_set_cbmc(gb_engine* e, int32_t n_trial_positions, int32_t n_trial_orientations, double beta);
+/* host mirror of Components::NumberOfPseudoAtoms (live atoms of each force-field type), kept by the engine
+ * and updated by the accept calls; this returns it (size = ff.size) */
+int  gb_get_pseudo_atom_counts(gb_engine* e, int64_t* counts);
+
+/* ------------------------------------------------------------------------------------------------
+ * CBMC stages  (replaces get_random_trial_position<<<>>> mc_widom.h:122-213,
+ *   get_random_trial_orientation<<<>>> :215-303, CBMC_PairwiseInteractions :89-119 with
+ *   Calculate_Multiple_Trial_Energy_VDWReal<<<>>> VDW_Coulomb.cu:1183-1352 and Host_sum_Widom_HGGG_SEPARATE
+ *   mc_widom.h:42-87, and the Boltzmann/selection/Rosenbluth host code :14-39, 305-383, 568-611).
+ *   One launch per stage, one small result read; trial coordinates stay on the device between stages.
+ * ------------------------------------------------------------------------------------------------ */
+/* first bead.  molecule = SelectedMolInComponent (ignored for CBMC_INSERTION / IDENTITY_SWAP_NEW);
+ * pool_offset = Random.offset; uniform = the Get_Uniform_Random() SelectTrialPosition would draw (consumed only
+ * for CBMC_INSERTION / REINSERTION_INSERTION with >=1 survivor -- *uniform_used reports it);
+ * scale = proposed_scale {vdw, coulomb}; stored_r = CBMC.StoredR (input for REINSERTION_RETRACE);
+ * exclude_{comp,mol} = Sims.ExcludeList[0] (-1 for none).
+ * For IDENTITY_SWAP_NEW the single trial position is preset_pos (copy_firstbead_to_new, mc_swap_moves.h:178-197). */
+int  gb_cbmc_first_bead(gb_engine* e, int32_t cbmc_type, int32_t component, int64_t molecule, int64_t pool_offset,
+                        double uniform, const double scale[2], double stored_r, int32_t exclude_comp, int64_t exclude_mol,
+                        const double* preset_pos, gb_cbmc_result* result, int32_t* uniform_used);
+/* chain growth from the first bead selected by the previous gb_cbmc_first_bead call (FirstBeadTrial) */
+int  gb_cbmc_chain(gb_engine* e, int32_t cbmc_type, int32_t component, int64_t molecule, int64_t pool_offset,
+                   double uniform, int32_t exclude_comp, int64_t exclude_mol, gb_cbmc_result* result, int32_t* uniform_used);
+/* positions of the molecule grown by the last first_bead(+chain) pair: 3*molsize doubles (block-pocket checks,
+ * mc_swap_utilities.h:46-80, read them) */
+int  gb_cbmc_grown_positions(gb_engine* e, int32_t component, double* pos);
+/* lower level: energies of caller-supplied trial atoms (n_trials groups of chainsize atoms), for drivers that
+ * generate trials themselves.  out_energy[t*4 + {HGVDW,HGReal,GGVDW,GGReal}], out_flag[t]. */
+int  gb_trial_energies(gb_engine* e, int32_t n_trials, int32_t chainsize, const double* pos, const double* scale,
+                       const double* charge, const double* scale_coul, const uint64_t* type,
+                       int32_t new_comp, int64_t new_molid, int32_t exclude_comp, int64_t exclude_mol,
+                       double* out_energy, int32_t* out_flag);
+
+/* ------------------------------------------------------------------------------------------------
+ * translation / rotation  (replaces get_new_position<<<>>> mc_utilities.h:485-606 and
+ *   Calculate_Single_Body_Energy_VDWReal<<<>>> VDW_Coulomb.cu:626-841 + the host sum mc_single_particle.h:183-200)
+ * ------------------------------------------------------------------------------------------------ */
+int  gb_single_body_propose(gb_engine* e, int32_t move_type, int32_t component, int64_t molecule,
+                            const double max_change[3], int64_t pool_offset, double* new_pos /* 3*molsize, may be NULL */);
+/* energy delta (new - old) of the proposal; overlap = flag[0] */
+int  gb_single_body_delta(gb_engine* e, int32_t component, int32_t do_new, int32_t do_old, gb_move_energy* delta, int32_t* overlap);
+/* caller-supplied old/new atoms instead of a stored proposal (n atoms each) */
+int  gb_single_body_delta_explicit(gb_engine* e, int32_t component, int64_t molid, int32_t n,
+                                   const double* old_pos, const double* new_pos, const double* scale, const double* charge,
+                                   const double* scale_coul, const uint64_t* type, int32_t do_new, int32_t do_old,
+                                   gb_move_energy* delta, int32_t* overlap);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ewald Fourier deltas  (replaces GPU_EwaldDifference_General Ewald_Energy_Functions.h:438-580 with
+ *   Initialize_WaveVector_General :162-185 and Fourier_Ewald_Diff :280-397 fused into one launch;
+ *   GPU_EwaldDifference_IdentitySwap :582-632; Update_Vector_Ewald :423-433)
+ * ------------------------------------------------------------------------------------------------ */
+/* returns {same-type, 2*cross-type} exactly like the reference's double2, exclusion constants applied.
+ * location = the reference's Location argument (selected trial for INSERTION, UpdateLocation for DELETION/REINSERTION). */
+int  gb_ewald_delta(gb_engine* e, int32_t component, int32_t move_type, int64_t location, const double scale[2], double out[2]);
+int  gb_ewald_delta_identity_swap(gb_engine* e, int32_t old_component, int32_t new_component, int64_t update_location, double out[2]);
+/* explicit atoms: n_old old atoms followed by n_new new atoms (Sims.Old layout) */
+int  gb_ewald_delta_explicit(gb_engine* e, int32_t component_is_framework, int32_t n_old, int32_t n_new, const double* pos,
+                             const double* charge, const double* scale_coul, double out[2]);
+int  gb_ewald_commit(gb_engine* e, int32_t component);                 /* Update_Vector_Ewald */
+
+/* ------------------------------------------------------------------------------------------------
+ * tail corrections  (replaces TailCorrection_Energy_Functions.h:3-113)
+ * ------------------------------------------------------------------------------------------------ */
+int  gb_tail_total(gb_engine* e, double* out);
+int  gb_tail_difference(gb_engine* e, int32_t component, int32_t move_type, double* out);
+int  gb_tail_identity_swap(gb_engine* e, int32_t new_component, int32_t old_component, double* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * state commit  (replaces AcceptTranslation/AcceptInsertion/AcceptDeletion mc_utilities.h:294-417 with
+ *   update_translation_position, Update_insertion_data_Parallel, Update_deletion_data_Parallel,
+ *   Update_NumberOfMolecules; reinsertion mc_swap_moves.h:27-49)
+ * ------------------------------------------------------------------------------------------------ */
+int  gb_accept_translation(gb_engine* e, int32_t component);          /* commits the stored single-body proposal (+ Ewald swap) */
+int  gb_accept_insertion(gb_engine* e, int32_t component);            /* commits the molecule grown by the last CBMC insertion (+ Ewald swap) */
+int  gb_accept_deletion(gb_engine* e, int32_t component, int64_t molecule);
+int  gb_accept_reinsertion(gb_engine* e, int32_t component, int64_t molecule);
+/* append a caller-supplied molecule (restart ingestion, CreateMolecule) */
+int  gb_append_molecule(gb_engine* e, int32_t component, const double* pos, const double* scale, const double* charge,
+                        const double* scale_coul, const uint64_t* type);
+int  gb_number_of_molecules(gb_engine* e, int32_t component, int64_t* n);
+
+/* ------------------------------------------------------------------------------------------------
+ * totals  (replaces Total_VDW_Coulomb_Energy VDW_Coulomb.cu:1580-1665, Ewald_TotalEnergy
+ *   Ewald_Energy_Functions.h:1272-1430 and the CPU Ewald_Total ewald_preparation.h:5-259 used at init)
+ * ------------------------------------------------------------------------------------------------ */
+int  gb_total_vdw_real(gb_engine* e, gb_move_energy* out);
+/* total Fourier energy incl. self and intra-molecular exclusion; store_structure_factors != 0 also (re)initialises
+ * AdsorbateEik / FrameworkEik from the current positions (what Ewald_Total + Allocate_Copy_Ewald_Vector do at init) */
+int  gb_total_ewald(gb_engine* e, int32_t store_structure_factors, gb_move_energy* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * batched Widom insertions  (the whole of Insertion_Body mc_swap_utilities.h:3-133 for n independent ghost
+ *   insertions of `component`, as axpy.cu:163-186 issues them one by one)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  /* randoms: a pool of double3 plus, per insertion, the pool index of its first-bead block (n_trial_positions
+   * entries) and of its orientation block (n_trial_orientations entries).  fb_index/or_index NULL = packed layout:
+   * insertion i uses pool[(i*(ntp+nto)) ...] then pool[(i*(ntp+nto)+ntp) ...].  uniforms: 2 per insertion
+   * (first-bead selection, orientation selection). */
+  const double* pool3;  int64_t n_pool;
+  const int64_t* fb_index; const int64_t* or_index;
+  const double* uniforms;
+  int32_t inputs_on_device;      /* 0: the four pointers above are host memory (copied inside the call) */
+  int32_t n_blocks;              /* block-average bins (Components::Nblock = 5); insertion i -> bin i*n_blocks/n */
+} gb_widom_inputs;
+
+/* per insertion outputs (any may be NULL): out8[i*8 + {W, HGVDW, HGReal, GGVDW, GGReal, GGEwaldE, HGEwaldE, TailE}],
+ * stage[i] (0 ok, 1 first bead failed, 2 chain failed).
+ * sums[(bin)*12 + {sumW, sumW2, count, sum(W*E) for the 7 energy terms, n_failed, reserved}] on the host, reduced on the device
+ * (RecordRosen data_struct.h:627-652 and widom_energy += E*W axpy.cu:177-185). */
+int  gb_widom_batch(gb_engine* e, int32_t component, int64_t n, const gb_widom_inputs* in,
+                    double* out8, int32_t* stage, int32_t outputs_on_device, double* sums);
+
+/* ------------------------------------------------------------------------------------------------
+ * instrumentation
+ * ------------------------------------------------------------------------------------------------ */
+/* kernels launched by this engine since creation / last reset (bench.py's gpu_launches) */
+int  gb_launch_count(gb_engine* e, int64_t* n, int32_t reset);
+/* elapsed device milliseconds of the engine's kernels of one family since last reset, measured with CUDA events
+ * on the engine stream: family 0 = pair kernels, 1 = Ewald kernels, 2 = all.  Timing must be enabled first. */
+int  gb_timing_enable(gb_engine* e, int32_t on);
+int  gb_timing_read(gb_engine* e, int32_t family, double* ms, int64_t* launches, int32_t reset);
+/* FP64 FMA peak microbenchmark on this device: returns TFLOP/s (2 flop per DFMA) */
+int  gb_measure_fp64_peak(gb_engine* e, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRASPA_B200_H */

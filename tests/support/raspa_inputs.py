@@ -131,6 +131,19 @@ def load_deck(folder, unitcells=None, extra_alloc=0):
     assert pnames == names, "pseudo_atoms.def must list the force-field names in order (read_data.cpp:1344)"
     cut_vdw = float(sim.get("CutOffVDW", [12.0])[0]); cut_coul = float(sim.get("CutOffCoulomb", [12.0])[0])
     e, s, sh, ut, te = orc.ff_mix(eps, sig, [shifted] * len(eps), [tail] * len(eps), cut_vdw)
+    # OverWriteTailCorrection, read_data.cpp:1132-1176 ("I J truncated yes" under "# rules to overwrite")
+    ffdef = os.path.join(folder, "force_field.def")
+    if os.path.exists(ffdef):
+        with open(ffdef) as f:
+            lines = f.read().splitlines()
+        nover = int(_terms(lines[1])[0])
+        n = len(names)
+        for ln in lines[3:3 + nover]:
+            t = _terms(ln)
+            if len(t) == 4 and t[3] == "yes":
+                i, j = names.index(t[0]), names.index(t[1])
+                _, _, _, _, te1 = orc.ff_mix(eps, sig, [shifted] * n, [True] * n, cut_vdw)
+                ut[i * n + j] = 1; ut[j * n + i] = 1; te[i * n + j] = te1[i * n + j]; te[j * n + i] = te1[i * n + j]
     charge_method = sim.get("ChargeMethod", ["None"])[0].lower()
     no_charges = charge_method != "ewald"
     ff = ForceField(e, s, sh, cut_vdw, cut_coul, overlap=float(sim.get("OverlapCriteria", [1e5])[0]), no_charges=no_charges,

@@ -1,0 +1,49 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol include/graspa_b200.h declares,
+fails loudly without a device, and the product never touches oracle/."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    with open(os.path.join(ROOT, "include", "graspa_b200.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from graspa_b200 import engine
+    engine.build()
+    lib = engine.load_library()
+    syms = header_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(engine.DECLARED_SYMBOLS) == syms
+    assert lib.gb_abi_version() == 1
+
+
+def test_engine_creation_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from graspa_b200 import engine
+    with pytest.raises(engine.EngineError, match="no CUDA device"):
+        engine.Engine()
+
+
+def test_product_does_not_reference_oracle():
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "graspa_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".inc", ".cpp", ".hpp")) or fn == "Makefile":
+                with open(os.path.join(base, fn), errors="ignore") as f:
+                    t = f.read()
+                if re.search(r"(import\s+oracle|from\s+oracle|liboracle|graspa_oracle|oracle/)", t):
+                    if not re.search(r"nothing .* oracle|never .* oracle|includes, links or calls oracle", t):
+                        bad.append(fn)
+    assert not bad, bad

@@ -1,0 +1,201 @@
+"""Parity of the CUDA engine (through the C ABI) against the oracle and the committed golden vectors.
+Tolerances are BASELINE.json's: energies 1e-10 relative, Widom <W> 1e-9 relative."""
+import numpy as np
+import pytest
+
+from graspa_b200.types import TrialAtoms, species_counts, pseudo_atom_counts, INSERTION, DELETION
+from tests.conftest import load_config, rel_err
+
+pytestmark = pytest.mark.gpu
+CONFIGS = ["A", "E", "B", "D"]
+ETOL = 1e-10
+
+
+def _scale(e):
+    return np.abs(e).sum(axis=1, keepdims=True) + 1e-3
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_trial_energies_vs_golden(gpu_engine_factory, name):
+    box, ff, s, z = load_config(name)
+    eng = gpu_engine_factory(box, ff, s)
+    comp = int(z["comp"]); ms = int(s.molsize[comp]); new_molid = int(s.natoms[comp]) // ms
+    t1 = TrialAtoms(z["tb1_pos"], z["tb1_charge"], z["tb1_type"])
+    e, f = eng.trial_energies(len(z["tb1_flag"]), 1, t1, comp, new_molid)
+    assert (f == z["tb1_flag"]).all()
+    assert np.max(np.abs(e - z["tb1_energy"]) / _scale(z["tb1_energy"])) < ETOL
+    if "tb2_pos" in z:
+        cs = int(z["tb2_cs"])
+        t2 = TrialAtoms(z["tb2_pos"], z["tb2_charge"], z["tb2_type"])
+        e, f = eng.trial_energies(len(z["tb2_flag"]), cs, t2, comp, new_molid)
+        assert (f == z["tb2_flag"]).all()
+        assert np.max(np.abs(e - z["tb2_energy"]) / _scale(z["tb2_energy"])) < ETOL
+    eng.close()
+
+
+def test_trial_energies_edge_cases(gpu_engine_factory, oracle):
+    """exclusion of a molecule (deletion/retrace), a trial on top of an atom (r^2 < 0.01 flag), ragged sizes"""
+    box, ff, s, z = load_config("B")
+    eng = gpu_engine_factory(box, ff, s)
+    comp = 1; o = int(s.offsets[comp]); ms = 3
+    # retrace of existing molecule 4: its own atoms must be excluded
+    mol = 4
+    tr = TrialAtoms(s.pos[o + ms * mol:o + ms * mol + 1], s.charge[o + ms * mol:o + ms * mol + 1], s.type[o + ms * mol:o + ms * mol + 1])
+    e_gpu, f_gpu = eng.trial_energies(1, 1, tr, comp, mol)
+    e_cpu, f_cpu, _ = oracle.trial_energies(box, ff, s, 1, 1, tr, comp, mol)
+    assert (f_gpu == f_cpu).all() and np.max(np.abs(e_gpu - e_cpu) / _scale(e_cpu)) < ETOL
+    # same position, nothing excluded: sits on top of itself -> overlap flag through r^2 < 0.01
+    e_gpu, f_gpu = eng.trial_energies(1, 1, tr, comp, 999)
+    e_cpu, f_cpu, _ = oracle.trial_energies(box, ff, s, 1, 1, tr, comp, 999)
+    assert f_gpu[0] == 1 and f_cpu[0] == 1
+    # ExcludeList[0] (identity swap): exclude molecule 7 of component 1
+    rng = np.random.default_rng(5)
+    pos = s.pos[o + ms * 7:o + ms * 7 + 1] + 0.3
+    tr = TrialAtoms(pos, [0.0], [int(s.type[o])])
+    e_gpu, f_gpu = eng.trial_energies(1, 1, tr, comp, 999, excl_comp=1, excl_mol=7)
+    e_cpu, f_cpu, _ = oracle.trial_energies(box, ff, s, 1, 1, tr, comp, 999, excl_comp=1, excl_mol=7)
+    assert (f_gpu == f_cpu).all() and np.max(np.abs(e_gpu - e_cpu) / _scale(e_cpu)) < ETOL
+    # ragged: 37 trials of a 5-atom group
+    n = 37 * 5
+    tr = TrialAtoms(rng.random((n, 3)) * 30.0, rng.normal(size=n) * 0.3, rng.integers(0, ff.ntypes, size=n))
+    e_gpu, f_gpu = eng.trial_energies(37, 5, tr, comp, 999)
+    e_cpu, f_cpu, _ = oracle.trial_energies(box, ff, s, 37, 5, tr, comp, 999)
+    assert (f_gpu == f_cpu).all() and np.max(np.abs(e_gpu - e_cpu) / _scale(e_cpu)) < ETOL
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["A", "E", "B"])
+def test_ewald_total_and_structure_factors(gpu_engine_factory, name):
+    box, ff, s, z = load_config(name)
+    eng = gpu_engine_factory(box, ff, s)
+    E = eng.total_ewald(store=True)
+    ref = z["ewald_E"]          # GG, HH, HG as the reference's Ewald_Total returns them
+    got = np.array([E["GGEwaldE"], E["HHEwaldE"], E["HGEwaldE"]])
+    assert rel_err(got, ref, floor=max(1.0, float(np.abs(ref).max()) * 1e-3)) < ETOL
+    sa, sf, _ = eng.download_structure_factors()
+    mag = max(1.0, float(np.abs(z["sf_fw"]).max()))
+    assert np.max(np.abs(sa - z["sf_ads"])) < 1e-10 * mag * 10 and np.max(np.abs(sf - z["sf_fw"])) < 1e-10 * mag * 10
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["A", "B"])
+def test_ewald_delta_vs_oracle(gpu_engine_factory, oracle, name):
+    box, ff, s, z = load_config(name)
+    eng = gpu_engine_factory(box, ff, s)
+    eng.upload_structure_factors(z["sf_ads"], z["sf_fw"])
+    rng = np.random.default_rng(11)
+    comp = int(z["comp"]); o = int(s.offsets[comp]); ms = int(s.molsize[comp])
+    q = s.charge[o:o + ms]
+    # insertion (0 old, ms new), deletion (ms old, 0 new), translation (ms old + ms new)
+    newp = rng.random((ms, 3)) * 20.0; oldp = rng.random((ms, 3)) * 20.0
+    for nold, nnew, pos, qq in [(0, ms, newp, q), (ms, 0, oldp, q), (ms, ms, np.concatenate([oldp, newp]), np.concatenate([q, q]))]:
+        got = eng.ewald_delta_explicit(False, nold, nnew, pos, qq, np.ones(len(qq)))
+        ref, temp, _ = oracle.ewald_delta(box, pos, qq, np.ones(len(qq)), nold, nnew, z["sf_ads"], z["sf_fw"])
+        mag = max(1.0, float(np.abs(ref).max()))
+        assert np.max(np.abs(got - ref)) / mag < ETOL
+        _, _, tgpu = eng.download_structure_factors()
+        assert np.max(np.abs(tgpu - temp)) < 1e-9
+    # commit = pointer swap: the adsorbate structure factors become the temp ones
+    eng.ewald_commit(comp)
+    sa, _, _ = eng.download_structure_factors()
+    assert np.max(np.abs(sa - temp)) < 1e-9
+    eng.close()
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_tail(gpu_engine_factory, name):
+    box, ff, s, z = load_config(name)
+    eng = gpu_engine_factory(box, ff, s)
+    assert (eng.pseudo_atom_counts() == z["npseudo"]).all()
+    assert abs(eng.tail_total() - float(z["tail_total"])) <= 1e-12 * max(1.0, abs(float(z["tail_total"])))
+    for k, c in enumerate(range(s.nhost, s.ncomp)):
+        assert abs(eng.tail_difference(c, INSERTION) - z["tail_ins"][k]) <= 1e-12 * max(1.0, abs(z["tail_ins"][k]))
+        assert abs(eng.tail_difference(c, DELETION) - z["tail_del"][k]) <= 1e-12 * max(1.0, abs(z["tail_del"][k]))
+    if "tail_swap" in z:
+        assert abs(eng.tail_identity_swap(s.nhost, s.nhost + 1) - float(z["tail_swap"])) <= 1e-12 * max(1.0, abs(float(z["tail_swap"])))
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["B", "D"])
+def test_total_vdw_real_vs_oracle(gpu_engine_factory, oracle, name):
+    box, ff, s, z = load_config(name)
+    eng = gpu_engine_factory(box, ff, s)
+    got = eng.total_vdw_real()
+    ref = oracle.total_vdw_real(box, ff, s)       # HHv, HHr, HGv, HGr, GGv, GGr
+    g = np.array([got["HHVDW"], got["HHReal"], got["HGVDW"], got["HGReal"], got["GGVDW"], got["GGReal"]])
+    assert rel_err(g, ref, floor=max(1.0, float(np.abs(ref).max()) * 1e-6)) < ETOL
+    eng.close()
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_widom_batch_vs_golden(gpu_engine_factory, name):
+    box, ff, s, z = load_config(name)
+    comp = int(z["comp"])
+    eng = gpu_engine_factory(box, ff, s, float(z["beta"]), int(z["ntrials"]), int(z["norient"]))
+    if "sf_ads" in z:
+        eng.upload_structure_factors(z["sf_ads"], z["sf_fw"])
+        eng.set_exclusion_constants(comp, float(z["excl"][0]), float(z["excl"][1]))
+    rnd = z["widom_rnd"].reshape(-1, 3)
+    out, stage, sums = eng.widom_batch(comp, rnd, z["widom_uni"], n_blocks=5)
+    ref = z["widom_out"]
+    assert (stage == z["widom_stage"]).all()
+    assert rel_err(out[:, 0], ref[:, 0], floor=1e-290) < 1e-9                   # W
+    esc = np.abs(ref[:, 1:]).sum(axis=1, keepdims=True) + 1e-3
+    assert np.max(np.abs(out[:, 1:] - ref[:, 1:]) / esc) < ETOL                 # energy terms
+    # block sums = RecordRosen + widom_energy accumulation
+    assert abs(sums[:, 0].sum() - ref[:, 0].sum()) <= 1e-9 * abs(ref[:, 0].sum())
+    assert abs(sums[:, 1].sum() - (ref[:, 0] ** 2).sum()) <= 1e-9 * (ref[:, 0] ** 2).sum()
+    assert sums[:, 2].sum() == len(ref)
+    assert np.allclose(sums[:, 3:10].sum(axis=0), (ref[:, :1] * ref[:, 1:]).sum(axis=0), rtol=1e-8, atol=1e-6)
+    eng.close()
+
+
+def test_widom_batch_vs_oracle_larger_with_failures(gpu_engine_factory, oracle):
+    """1024 insertions in config A with OverlapCriteria lowered so that first beads and chains fail:
+    identical stage codes, W within 1e-9, and explicit pool indices (the RNG-exact replay layout)."""
+    box, ff, s, z = load_config("A")
+    ff.overlap = 2.0e4
+    comp = 1; n = 1024
+    rng = np.random.default_rng(99)
+    rnd = rng.random((n, 20, 3)); uni = rng.random((n, 2))
+    ws = oracle.WidomSetup(box, ff, s, comp, float(z["beta"]), 10, 10, z["sf_ads"], z["sf_fw"])
+    ref, rstage, _ = oracle.widom_batch(ws, rnd, uni)
+    eng = gpu_engine_factory(box, ff, s, float(z["beta"]), 10, 10)
+    eng.upload_structure_factors(z["sf_ads"], z["sf_fw"]); eng.set_exclusion_constants(comp, *ws.excl)
+    out, stage, sums = eng.widom_batch(comp, rnd.reshape(-1, 3), uni)
+    assert (stage == rstage).all()
+    assert (rstage > 0).sum() > 0
+    assert rel_err(out[:, 0], ref[:, 0], floor=1e-290) < 1e-9
+    assert abs(sums[:, 0].sum() / n - ref[:, 0].mean()) <= 1e-9 * ref[:, 0].mean()
+    assert sums[:, 10].sum() == (rstage > 0).sum()
+    # shuffled pool with explicit indices gives the same answers
+    perm = rng.permutation(2 * n)
+    pool = np.zeros((2 * n * 10, 3))
+    blocks = rnd.reshape(2 * n, 10, 3)
+    for b in range(2 * n):
+        pool[perm[b] * 10:(perm[b] + 1) * 10] = blocks[b]
+    fb = perm[0::2] * 10; orr = perm[1::2] * 10
+    out2, stage2, _ = eng.widom_batch(comp, pool, uni, fb_index=fb, or_index=orr)
+    assert (stage2 == stage).all() and np.array_equal(out2, out)
+    eng.close()
+
+
+def test_widom_properties_full_size(gpu_engine_factory):
+    """size-independent properties at the benchmark shape (config E): determinism, batch-split additivity,
+    block sums consistent with per-insertion outputs, W >= 0 and stage/W consistency"""
+    box, ff, s, z = load_config("E")
+    comp = 1; n = 20000
+    rng = np.random.default_rng(3)
+    rnd = rng.random((n * 20, 3)); uni = rng.random((n, 2))
+    eng = gpu_engine_factory(box, ff, s, float(z["beta"]), 10, 10)
+    eng.upload_structure_factors(z["sf_ads"], z["sf_fw"]); eng.set_exclusion_constants(comp, float(z["excl"][0]), float(z["excl"][1]))
+    out, stage, sums = eng.widom_batch(comp, rnd, uni)
+    out_b, stage_b, sums_b = eng.widom_batch(comp, rnd, uni)
+    assert np.array_equal(out, out_b) and np.array_equal(sums, sums_b)            # bitwise deterministic
+    h = n // 2
+    o1, s1, _ = eng.widom_batch(comp, rnd[:h * 20], uni[:h]); o2, s2, _ = eng.widom_batch(comp, rnd[h * 20:], uni[h:])
+    assert np.array_equal(np.concatenate([o1, o2]), out)                          # insertions are independent
+    assert (out[:, 0] >= 0).all() and ((out[:, 0] == 0) == (stage > 0)).all()
+    assert abs(sums[:, 0].sum() - out[:, 0].sum()) <= 1e-11 * out[:, 0].sum()
+    assert sums[:, 2].sum() == n and (sums[:, 2] == n // 5).all()
+    eng.close()
