@@ -316,9 +316,17 @@ int gb_engine_create(gb_engine** out, int device)
   CUDA_TRY(cudaMallocHost(&e->h_pinned, 4096));
   CUDA_TRY(e->d_ticket.reserve(16)); CUDA_TRY(cudaMemset(e->d_ticket.p, 0, 16 * sizeof(unsigned int)));
   CUDA_TRY(e->d_result.reserve(512));
-  CUDA_TRY(cudaFuncSetAttribute(k_widom_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  CUDA_TRY(cudaFuncSetAttribute(k_widom_ewald, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  CUDA_TRY(cudaFuncSetAttribute(k_ewald_delta, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  {
+    // dynamic + static shared memory must stay within the opt-in limit
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_widom_pair));
+    CUDA_TRY(cudaFuncSetAttribute(k_widom_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_widom_ewald));
+    CUDA_TRY(cudaFuncSetAttribute(k_widom_ewald, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_ewald_delta));
+    CUDA_TRY(cudaFuncSetAttribute(k_ewald_delta, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
+    e->smem_optin -= 1024;   // head room for static shared memory of the kernels
+  }
   *out = e;
   return GB_OK;
 }
@@ -773,9 +781,9 @@ int gb_total_ewald(gb_engine* e, int32_t store, gb_move_energy* out)
     A.sf_ads = e->d_sf[e->i_ads].p; A.sf_fw = e->d_sf[e->i_fw].p;
   }
   else { A.sf_ads = nullptr; A.sf_fw = nullptr; }
-  // per-molecule exclusion records: count molecules
-  int nmol_total = 0; for(int c = 0; c < e->ncomp; c++) if(e->comps[c].molsize > 0) nmol_total += e->comps[c].natoms / e->comps[c].molsize;
-  CUDA_TRY(e->d_scratch.reserve((size_t) e->nact * 3 + (size_t) nmol_total * 2 + 64));
+  // exclusion records: one {self, intra} pair per live atom, then a fixed-order column sum per component
+  int nlive_total = 0; for(int c = 0; c < e->ncomp; c++) nlive_total += e->comps[c].natoms;
+  CUDA_TRY(e->d_scratch.reserve((size_t) e->nact * 3 + (size_t) nlive_total * 2 + 64));
   A.ek = e->d_scratch.p;
   Timer tm(e, 1);
   k_ewald_total<<<e->nact, 128, 0, e->stream>>>(e->P, A);
@@ -783,36 +791,33 @@ int gb_total_ewald(gb_engine* e, int32_t store, gb_move_energy* out)
   e->launches += 2;
   CUDA_TRY(cudaGetLastError());
   double* d_ex = e->d_scratch.p + (size_t) e->nact * 3;
-  int moff = 0;
-  std::vector<int> moffs(e->ncomp, 0), mcnt(e->ncomp, 0);
+  int aoff = 0;
   for(int c = 0; c < e->ncomp; c++)
   {
     const Comp& C = e->comps[c];
-    const int nm = C.molsize > 0 ? C.natoms / C.molsize : 0;
-    moffs[c] = moff; mcnt[c] = nm;
-    if(nm > 0)
+    if(C.natoms > 0)
     {
-      ExclArgs X; X.x = e->dx.p; X.y = e->dy.p; X.z = e->dz.p; X.q = e->dq.p; X.scoul = e->dscoul.p; X.start = C.offset; X.nmol = nm; X.ms = C.molsize; X.out = d_ex + 2 * (size_t) moff;
-      k_ewald_exclusion<<<(nm + 127) / 128, 128, 0, e->stream>>>(e->P, X);
-      e->launches++;
+      ExclArgs X; X.x = e->dx.p; X.y = e->dy.p; X.z = e->dz.p; X.q = e->dq.p; X.scoul = e->dscoul.p; X.start = C.offset; X.natoms = C.natoms; X.ms = C.molsize;
+      X.out = d_ex + 2 * (size_t) aoff;
+      k_ewald_exclusion<<<(C.natoms + 127) / 128, 128, 0, e->stream>>>(e->P, X);
+      k_reduce_partials<<<1, 32, 0, e->stream>>>(X.out, C.natoms, 2, e->d_result.p + 40 + 2 * c);
+      e->launches += 2;
       CUDA_TRY(cudaGetLastError());
     }
-    moff += nm;
+    else CUDA_TRY(cudaMemsetAsync(e->d_result.p + 40 + 2 * c, 0, 2 * sizeof(double), e->stream));
+    aoff += C.natoms;
   }
-  tm.stop(2 + e->ncomp);
-  std::vector<double> ex((size_t) nmol_total * 2 + 2);
-  if(nmol_total > 0) CUDA_TRY(cudaMemcpyAsync(ex.data(), d_ex, (size_t) nmol_total * 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 32, e->d_result.p + 32, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  tm.stop(2 + 2 * e->ncomp);
+  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 32, e->d_result.p + 32, (8 + 2 * GBK_MAX_SEG) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   double GG = e->h_pinned[32], HH = e->h_pinned[33], HG = e->h_pinned[34];
   GG += HH;                                                            // ewald_preparation.h:174
   for(int c = 0; c < e->ncomp; c++)
-    for(int m = 0; m < mcnt[c]; m++)
-    {
-      const double self = ex[2 * (size_t)(moffs[c] + m)], intra = ex[2 * (size_t)(moffs[c] + m) + 1];
-      GG -= self; GG -= intra;
-      if(c < e->nhost && A.has_fw) { HH -= self; HH -= intra; }
-    }
+  {
+    const double self = e->h_pinned[40 + 2 * c], intra = e->h_pinned[40 + 2 * c + 1];
+    GG -= self; GG -= intra;
+    if(c < e->nhost && A.has_fw) { HH -= self; HH -= intra; }
+  }
   out->GGEwaldE = GG; out->HHEwaldE = HH; out->HGEwaldE = HG;
   if(store) { e->have_sf = true; e->ktab_dirty = true; }
   return GB_OK;

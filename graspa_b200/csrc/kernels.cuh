@@ -572,35 +572,63 @@ k_ewald_total(DevParams P, EwaldTotalArgs A)
   }
 }
 
-// self + intra-molecular exclusion (ewald_preparation.h:176-227): one thread per molecule
+// self + intra-molecular exclusion (ewald_preparation.h:176-227): one thread per live atom i, pairs (i, j>i) of its
+// molecule.  Framework atoms of an even supercell sit at EXACT half-box separations, where the image the reference
+// picks is decided by its own rounding; this (cold) kernel therefore follows the reference's Cartesian arithmetic
+// operation by operation, unfused, with its truncating round (maths.cuh:437-448), instead of the hot path's
+// fractional-space formulation.
+__device__ __forceinline__ double ref_round_off(double s)
+{
+  return __dsub_rn(s, (double) static_cast<int>(__dadd_rn(s, (s >= 0.0) ? 0.5 : -0.5)));
+}
+__device__ __forceinline__ double dot3_unfused(double a0, double b0, double a1, double b1, double a2, double b2)
+{
+  return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+}
+__device__ __forceinline__ double min_image_r2_reference_order(const DevParams& P, double dx, double dy, double dz)
+{
+  if(P.cubic)
+  {
+    dx = __dsub_rn(dx, __dmul_rn((double) static_cast<int>(__dadd_rn(__dmul_rn(dx, P.inv[0]), (dx >= 0.0) ? 0.5 : -0.5)), P.cell[0]));
+    dy = __dsub_rn(dy, __dmul_rn((double) static_cast<int>(__dadd_rn(__dmul_rn(dy, P.inv[4]), (dy >= 0.0) ? 0.5 : -0.5)), P.cell[4]));
+    dz = __dsub_rn(dz, __dmul_rn((double) static_cast<int>(__dadd_rn(__dmul_rn(dz, P.inv[8]), (dz >= 0.0) ? 0.5 : -0.5)), P.cell[8]));
+    return dot3_unfused(dx, dx, dy, dy, dz, dz);
+  }
+  double sx = dot3_unfused(P.inv[0], dx, P.inv[3], dy, P.inv[6], dz);
+  double sy = dot3_unfused(P.inv[1], dx, P.inv[4], dy, P.inv[7], dz);
+  double sz = dot3_unfused(P.inv[2], dx, P.inv[5], dy, P.inv[8], dz);
+  sx = ref_round_off(sx); sy = ref_round_off(sy); sz = ref_round_off(sz);
+  const double px = dot3_unfused(P.cell[0], sx, P.cell[3], sy, P.cell[6], sz);
+  const double py = dot3_unfused(P.cell[1], sx, P.cell[4], sy, P.cell[7], sz);
+  const double pz = dot3_unfused(P.cell[2], sx, P.cell[5], sy, P.cell[8], sz);
+  return dot3_unfused(px, px, py, py, pz, pz);
+}
+
 struct ExclArgs
 {
   const double* __restrict__ x; const double* __restrict__ y; const double* __restrict__ z;
   const double* __restrict__ q; const double* __restrict__ scoul;
-  int start, nmol, ms;
-  double* out;      // [nmol][2] self, intra
+  int start, natoms, ms;
+  double* out;      // [natoms][2] self, intra (pairs i<j attributed to i)
 };
 __global__ void k_ewald_exclusion(DevParams P, ExclArgs A)
 {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if(m >= A.nmol) return;
-  const int a0 = A.start + m * A.ms;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if(t >= A.natoms) return;
+  const int i = A.start + t;
+  const int mol_end = A.start + (t / A.ms + 1) * A.ms;
   const double pself = P.prefactor * P.alpha / sqrt(GBK_PI);
-  double self = 0.0, intra = 0.0;
-  for(int i = a0; i < a0 + A.ms; i++) { const double f = A.scoul[i] * A.q[i]; self += pself * f * f; }
-  for(int i = a0; i < a0 + A.ms - 1; i++)
+  const double fa = A.scoul[i] * A.q[i];
+  const double self = pself * fa * fa;
+  double intra = 0.0;
+  const double xi = A.x[i], yi = A.y[i], zi = A.z[i];
+  for(int j = i + 1; j < mol_end; j++)
   {
-    const double fa = A.scoul[i] * A.q[i];
-    double si, sj, sk; to_frac(P, A.x[i], A.y[i], A.z[i], si, sj, sk);
-    for(int j = i + 1; j < a0 + A.ms; j++)
-    {
-      const double fb = A.scoul[j] * A.q[j];
-      double ti, tj, tk; to_frac(P, A.x[j], A.y[j], A.z[j], ti, tj, tk);
-      const double r = sqrt(min_image_r2(P, si - ti, sj - tj, sk - tk));
-      intra += P.prefactor * fa * fb * erf(P.alpha * r) / r;
-    }
+    const double fb = A.scoul[j] * A.q[j];
+    const double r = sqrt(min_image_r2_reference_order(P, __dsub_rn(xi, A.x[j]), __dsub_rn(yi, A.y[j]), __dsub_rn(zi, A.z[j])));
+    intra += P.prefactor * fa * fb * erf(P.alpha * r) / r;
   }
-  A.out[2 * m] = self; A.out[2 * m + 1] = intra;
+  A.out[2 * t] = self; A.out[2 * t + 1] = intra;
 }
 
 // total VDW + real: every live atom is a one-atom "trial group" against all live atoms with the own-molecule
