@@ -4,12 +4,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include "erfc_table.inc"
 
 #define GBK_PI 3.14159265358979323846
 #define GBK_MAX_SEG 16
 #define GBK_QCAP 64            // per-warp in-cutoff queue entries
 #define GBK_MAX_CS 32          // max atoms of one trial group handled by the warp pair loop
 #define GBK_MAX_TRIALS 32      // one lane per trial in the Rosenbluth stage
+#define GBK_ERFC_BYTES ((GBK_ERFC_DEG + 1) * GBK_ERFC_NINT * 8)
 
 // Kernel-side view of Boxsize + ForceField scalars (data_struct.h:838-886).  Passed by value.
 struct DevParams
@@ -21,8 +23,10 @@ struct DevParams
   int ntypes, cubic, no_charges, vdw_real_bias, use1264, use_lammps;
   int kmax[3];
   int all_unit_scale;                 // every system atom has scale == scaleCoul == 1
+  int cell_mode;                      // 0 general, 1 lower triangular (CIF cells, read_data.cpp:1545-1547), 2 orthorhombic
   const double4* __restrict__ ffA;    // LJ: {4*eps, sigma^2, shift, 1/sigma^2}; 12-6-4: {C12, C6, C4, shift}
   const double*  __restrict__ ffB;    // 12-6-4: C10
+  const double*  __restrict__ erfc_tab;   // device copy of h_erfc_table
 };
 
 // system atoms, SoA over slots (fractional coordinates are derived from the Cartesian ones)
@@ -60,6 +64,16 @@ __device__ __forceinline__ double warp_max(double v)
   return v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// explicit shared-memory loads (the pair loop reads either the TMA-staged pack or global memory;
+// keeping the state space in the instruction avoids generic LD and pointer selects in the hot loop)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+// address-space hints: pointers derived from the dynamic shared-memory block are declared shared so that loads
+// through them compile to LDS (not generic LD) after inlining
+#define GBK_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#define GBK_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
+
 // d - nearest_integer(d) without leaving the FP64 pipe (|d| < 2^51).  The reference truncates
 // static_cast<int>(s +- 0.5) (maths.cuh:442-444); both pick the same image except at exact half-integers.
 __device__ __forceinline__ double frac_wrap(double d)
@@ -70,7 +84,7 @@ __device__ __forceinline__ double frac_wrap(double d)
   return d - t;
 }
 
-// fractional coordinate of a Cartesian position: s = InverseCell^T-style product of maths.cuh:438-440
+// fractional coordinate of a Cartesian position: the product of maths.cuh:438-440
 __device__ __forceinline__ void to_frac(const DevParams& P, double x, double y, double z, double& sx, double& sy, double& sz)
 {
   sx = P.inv[0] * x + P.inv[3] * y + P.inv[6] * z;
@@ -78,23 +92,72 @@ __device__ __forceinline__ void to_frac(const DevParams& P, double x, double y, 
   sz = P.inv[2] * x + P.inv[5] * y + P.inv[8] * z;
 }
 
-// minimum-image squared distance from fractional differences (maths.cuh:442-448 + dot)
+// cell matrix held in registers by the pair loops; MODE 1 skips the structural zeros of a lower-triangular
+// cell (rows = lattice vectors: a = (c0,0,0), b = (c3,c4,0), c = (c6,c7,c8)), MODE 2 those of an orthorhombic one
+template <int MODE>
+struct CellRegs
+{
+  double c0, c1, c2, c3, c4, c5, c6, c7, c8;
+  __device__ __forceinline__ void load(const DevParams& P)
+  {
+    c0 = P.cell[0]; c1 = P.cell[1]; c2 = P.cell[2]; c3 = P.cell[3]; c4 = P.cell[4]; c5 = P.cell[5]; c6 = P.cell[6]; c7 = P.cell[7]; c8 = P.cell[8];
+  }
+  // minimum-image squared distance from fractional differences (maths.cuh:442-448 + dot)
+  __device__ __forceinline__ double r2(double dsx, double dsy, double dsz) const
+  {
+    dsx = frac_wrap(dsx); dsy = frac_wrap(dsy); dsz = frac_wrap(dsz);
+    double dx, dy, dz;
+    if(MODE == 2) { dx = c0 * dsx; dy = c4 * dsy; dz = c8 * dsz; }
+    else if(MODE == 1)
+    {
+      dx = c0 * dsx + c3 * dsy + c6 * dsz;
+      dy = c4 * dsy + c7 * dsz;
+      dz = c8 * dsz;
+    }
+    else
+    {
+      dx = c0 * dsx + c3 * dsy + c6 * dsz;
+      dy = c1 * dsx + c4 * dsy + c7 * dsz;
+      dz = c2 * dsx + c5 * dsy + c8 * dsz;
+    }
+    return dx * dx + dy * dy + dz * dz;
+  }
+};
+
 __device__ __forceinline__ double min_image_r2(const DevParams& P, double dsx, double dsy, double dsz)
 {
-  dsx = frac_wrap(dsx); dsy = frac_wrap(dsy); dsz = frac_wrap(dsz);
-  const double dx = P.cell[0] * dsx + P.cell[3] * dsy + P.cell[6] * dsz;
-  const double dy = P.cell[1] * dsx + P.cell[4] * dsy + P.cell[7] * dsz;
-  const double dz = P.cell[2] * dsx + P.cell[5] * dsy + P.cell[8] * dsz;
-  return dx * dx + dy * dy + dz * dz;
+  CellRegs<0> C; C.load(P);
+  return C.r2(dsx, dsy, dsz);
+}
+
+// erfc(x) for x in [0, GBK_ERFC_XMAX): degree-12 piecewise polynomials on intervals of width 1/8 centred at k/8
+// (tools/gen_erfc_table.py; worst relative error 5.6e-16 against 50-digit arithmetic).  Table in shared memory at
+// byte address tab (layout coef[j][k]).  13 FP64 instructions + 13 LDS instead of libdevice's ~60 DFMA with
+// immediate-constant moves.
+__device__ __forceinline__ double erfc_table_eval(const double* __restrict__ tab, double x)
+{
+  GBK_ASSUME_SHARED(tab);
+  const double M = 6755399441055744.0;
+  const double y = x * GBK_ERFC_SCALE;
+  double kd = __dadd_rn(y, M);
+  const int k = __double2loint(kd);
+  kd = __dsub_rn(kd, M);
+  const double t = y - kd;
+  const double* a = tab + k;
+  double acc = a[GBK_ERFC_NINT * GBK_ERFC_DEG];
+#pragma unroll
+  for(int j = GBK_ERFC_DEG - 1; j >= 0; j--) acc = fma(acc, t, a[GBK_ERFC_NINT * j]);
+  return acc;
 }
 
 // One in-cutoff pair: LJ 12-6 (+soft core, +shift) or 12-6-4 polynomial (maths.cuh:452-494) and the
 // real-space Ewald term (maths.cuh:496-500).  One rsqrt feeds both.
-__device__ __forceinline__ void pair_energy(const DevParams& P, double r2, int row, double scaling, double qq_scaled,
+__device__ __forceinline__ void pair_energy(const DevParams& P, const double* __restrict__ etab, double r2, int row, double scaling, double qq_scaled,
                                             double& e_vdw, double& e_real, int& flag)
 {
   const double rinv = rsqrt(r2);
   const double rinv2 = rinv * rinv;
+  e_vdw = 0.0; e_real = 0.0; flag = 0;
   if(r2 < P.cut_vdw2)
   {
     const double4 f = P.ffA[row];
@@ -113,24 +176,30 @@ __device__ __forceinline__ void pair_energy(const DevParams& P, double r2, int r
     else
     {
       const double ri4 = rinv2 * rinv2, ri6 = ri4 * rinv2, ri10 = ri4 * ri6, ri12 = ri6 * ri6;
-      e = scaling * (f.x * ri12 - f.y * ri6 + P.ffB[row] * ri10 + f.z * ri4 - f.w);
+      e = scaling * (f.x * ri12 - f.y * ri6 + __ldg(&P.ffB[row]) * ri10 + f.z * ri4 - f.w);
     }
     if(e > P.overlap) flag = 1;
     if(r2 < 0.01) flag = 1;
-    e_vdw += e;
+    e_vdw = e;
   }
   if(!P.no_charges && r2 < P.cut_coul2)
   {
     const double r = r2 * rinv;
-    e_real += P.prefactor * qq_scaled * erfc(P.alpha * r) * rinv;
+    const double x = P.alpha * r;
+    const double ec = (x < GBK_ERFC_XMAX) ? erfc_table_eval(etab, x) : erfc(x);
+    e_real = P.prefactor * qq_scaled * ec * rinv;
   }
+}
+
+// cooperative copy of the erfc table into shared memory (all threads of the CTA), returns its shared address
+__device__ __forceinline__ void stage_erfc_table(const DevParams& P, double* dst)
+{
+  for(int i = threadIdx.x; i < (GBK_ERFC_DEG + 1) * GBK_ERFC_NINT; i += blockDim.x) dst[i] = __ldg(&P.erfc_tab[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
 // TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
-
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));

@@ -1,7 +1,8 @@
 // graspa_b200 -- host side of the C ABI (include/graspa_b200.h): device state, uploads, launches.
-// Product code.  There is no CPU fallback anywhere in this file: every energy comes from a kernel in kernels.cuh.
+// Product code.  There is no CPU fallback anywhere in this file: every energy comes from a kernel in misc_kernels.cuh / pair_kernels.cuh.
 #include "../../include/graspa_b200.h"
-#include "kernels.cuh"
+#include "misc_kernels.cuh"
+#include "pair_kernels.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -57,7 +58,7 @@ struct gb_engine
   DevParams P{};
   bool have_ff = false, have_box = false;
   int ntypes = 0;
-  DevBuf<double4> d_ffA; DevBuf<double> d_ffB;
+  DevBuf<double4> d_ffA; DevBuf<double> d_ffB; DevBuf<double> d_erfc;
   std::vector<int> tail_use; std::vector<double> tail_e; bool has_tail = false;
   DevBuf<int> d_tail_use; DevBuf<double> d_tail_e;
 
@@ -319,14 +320,19 @@ int gb_engine_create(gb_engine** out, int device)
   {
     // dynamic + static shared memory must stay within the opt-in limit
     cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, k_widom_pair));
-    CUDA_TRY(cudaFuncSetAttribute(k_widom_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_widom_pair<0>));
+    CUDA_TRY(cudaFuncSetAttribute(k_widom_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_widom_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_widom_pair<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_widom_ewald));
     CUDA_TRY(cudaFuncSetAttribute(k_widom_ewald, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_ewald_delta));
     CUDA_TRY(cudaFuncSetAttribute(k_ewald_delta, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
     e->smem_optin -= 1024;   // head room for static shared memory of the kernels
   }
+  CUDA_TRY(e->d_erfc.reserve((GBK_ERFC_DEG + 1) * GBK_ERFC_NINT));
+  CUDA_TRY(cudaMemcpy(e->d_erfc.p, h_erfc_table, sizeof(h_erfc_table), cudaMemcpyHostToDevice));
+  e->P.erfc_tab = e->d_erfc.p;
   *out = e;
   return GB_OK;
 }
@@ -336,7 +342,7 @@ int gb_engine_destroy(gb_engine* e)
   if(!e) return GB_OK;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  e->d_ffA.release(); e->d_ffB.release(); e->d_tail_use.release(); e->d_tail_e.release();
+  e->d_ffA.release(); e->d_ffB.release(); e->d_erfc.release(); e->d_tail_use.release(); e->d_tail_e.release();
   e->dx.release(); e->dy.release(); e->dz.release(); e->dfx.release(); e->dfy.release(); e->dfz.release();
   e->dq.release(); e->dscale.release(); e->dscoul.release(); e->dtype.release(); e->dmolid.release();
   e->d_pack.release(); e->d_kpack.release(); e->d_kslot.release(); e->d_ktemp.release();
@@ -404,6 +410,12 @@ int gb_upload_box(gb_engine* e, const gb_box* box)
   for(int i = 0; i < 9; i++) { e->P.cell[i] = box->cell[i]; e->P.inv[i] = box->inverse_cell[i]; }
   e->P.volume = box->volume; e->P.alpha = box->alpha; e->P.prefactor = box->prefactor; e->P.recip_cutoff = box->reciprocal_cutoff;
   e->P.cubic = box->cubic; e->P.use_lammps = box->use_lammps_ewald;
+  {
+    const double* c = box->cell;
+    const bool upper_zero = c[1] == 0.0 && c[2] == 0.0 && c[5] == 0.0;
+    const bool lower_zero = c[3] == 0.0 && c[6] == 0.0 && c[7] == 0.0;
+    e->P.cell_mode = (upper_zero && lower_zero) ? 2 : (upper_zero ? 1 : 0);
+  }
   for(int i = 0; i < 3; i++) e->P.kmax[i] = box->kmax[i];
   if(box->kmax[0] > 127 || box->kmax[1] > 127 || box->kmax[2] > 127 || box->kmax[0] < 0 || box->kmax[1] < 0 || box->kmax[2] < 0)
     return fail(GB_ERR_ARG, "kmax out of range [0,127]");
@@ -744,7 +756,7 @@ int gb_total_vdw_real(gb_engine* e, gb_move_energy* out)
   int rc = ready(e); if(rc) return rc;
   if(!out) return fail(GB_ERR_ARG, "null out");
   memset(out, 0, sizeof(*out));
-  TotalArgs A; A.L = seg_list(e, 0); A.nhost = e->nhost; A.comp_of = nullptr;
+  TotalArgs A; A.L = seg_list(e, 0); A.nhost = e->nhost;
   int nlive = 0; for(int s = 0; s < A.L.nseg; s++) nlive += A.L.count[s];
   if(nlive == 0) return GB_OK;
   CUDA_TRY(e->d_scratch.reserve((size_t) nlive * 6 + 8));
@@ -867,7 +879,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   const int warpsA = 16;
   const size_t per_warpA = (sizeof(TrialGroup) + sizeof(WarpQueue) + (size_t) e->norient * (cs > 0 ? cs : 1) * 6 * sizeof(double) + 15) / 16 * 16;
   bool use_pack = false;
-  rc = ensure_pack(e, use_pack, warpsA * per_warpA + 64); if(rc) return rc;
+  rc = ensure_pack(e, use_pack, warpsA * per_warpA + GBK_ERFC_BYTES + sizeof(SegList) + 128); if(rc) return rc;
   WidomA A;
   A.pool3 = d_pool; A.fb_index = d_fb; A.or_index = d_or; A.uni = d_uni; A.n = n;
   A.ntrials = e->ntrials; A.norient = e->norient; A.ms = ms; A.comp = comp; A.new_molid = C.natoms / ms;
@@ -881,12 +893,15 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
     int acc = 0;
     for(int s = 0; s < L.nseg; s++) if(L.comp[s] < e->nhost) { L.staged[s] = 1; L.start[s] = acc; acc += L.count[s]; }
   }
-  const size_t smemA = 16 + (use_pack ? ((size_t) e->pack_npad * 36 + 15) / 16 * 16 : 0) + warpsA * per_warpA;
+  const size_t headA = (16 + GBK_ERFC_BYTES + sizeof(SegList) + 15) / 16 * 16;
+  const size_t smemA = headA + (use_pack ? ((size_t) e->pack_npad * 36 + 15) / 16 * 16 : 0) + warpsA * per_warpA;
   if(smemA > e->smem_optin) return fail(GB_ERR_ARG, "Widom stage A shared memory exceeds the device limit");
   const int gridA = (int) std::min<long long>((n + warpsA - 1) / warpsA, e->prop.multiProcessorCount);
   {
     Timer tm(e, 0);
-    k_widom_pair<<<gridA, warpsA * 32, smemA, e->stream>>>(e->P, sys_view(e), L, A);
+    if(e->P.cell_mode == 2)      k_widom_pair<2><<<gridA, warpsA * 32, smemA, e->stream>>>(e->P, sys_view(e), L, A);
+    else if(e->P.cell_mode == 1) k_widom_pair<1><<<gridA, warpsA * 32, smemA, e->stream>>>(e->P, sys_view(e), L, A);
+    else                         k_widom_pair<0><<<gridA, warpsA * 32, smemA, e->stream>>>(e->P, sys_view(e), L, A);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     tm.stop(1);
