@@ -8,10 +8,12 @@
 
 #define GBK_PI 3.14159265358979323846
 #define GBK_MAX_SEG 16
-#define GBK_QCAP 64            // per-warp in-cutoff queue entries
+#define GBK_QCAP 128           // per-warp in-cutoff queue entries (up to 31 left over + 3 x 32 pushed per iteration)
 #define GBK_MAX_CS 32          // max atoms of one trial group handled by the warp pair loop
 #define GBK_MAX_TRIALS 32      // one lane per trial in the Rosenbluth stage
 #define GBK_ERFC_BYTES ((GBK_ERFC_DEG + 1) * GBK_ERFC_NINT * 8)
+#define GBK_ERFC_BYTES_PAD ((GBK_ERFC_BYTES + 31) / 32 * 32)
+#define GBK_SMEM_TABLES_OFF 32   // dynamic smem: [0,16) mbarrier, tables from byte 32 (32-byte aligned for double4 loads)
 
 // Kernel-side view of Boxsize + ForceField scalars (data_struct.h:838-886).  Passed by value.
 struct DevParams
@@ -24,6 +26,7 @@ struct DevParams
   int kmax[3];
   int all_unit_scale;                 // every system atom has scale == scaleCoul == 1
   int cell_mode;                      // 0 general, 1 lower triangular (CIF cells, read_data.cpp:1545-1547), 2 orthorhombic
+  int erfc_table_ok;                  // alpha*sqrt(cut_coul2) < GBK_ERFC_XMAX: every in-cutoff pair is inside the erfc table
   const double4* __restrict__ ffA;    // LJ: {4*eps, sigma^2, shift, 1/sigma^2}; 12-6-4: {C12, C6, C4, shift}
   const double*  __restrict__ ffB;    // 12-6-4: C10
   const double*  __restrict__ erfc_tab;   // device copy of h_erfc_table
@@ -49,7 +52,8 @@ struct SegList
   int staged[GBK_MAX_SEG];   // 1: the segment lives in the shared-memory staged pack at offset start
 };
 
-__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+// %laneid through a volatile asm: evaluated once where it is called, never rematerialised as S2R+LOP3 inside hot loops
+__device__ __forceinline__ unsigned lane_id() { unsigned l; asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -152,7 +156,9 @@ __device__ __forceinline__ double erfc_table_eval(const double* __restrict__ tab
 
 // One in-cutoff pair: LJ 12-6 (+soft core, +shift) or 12-6-4 polynomial (maths.cuh:452-494) and the
 // real-space Ewald term (maths.cuh:496-500).  One rsqrt feeds both.
-__device__ __forceinline__ void pair_energy(const DevParams& P, const double* __restrict__ etab, double r2, int row, double scaling, double qq_scaled,
+// ffp: the LJ table (shared-memory copy or P.ffA); unit: warp-uniform "every scaling factor of this group is 1".
+__device__ __forceinline__ void pair_energy(const DevParams& P, const double* __restrict__ etab, const double4* __restrict__ ffp, bool unit,
+                                            double r2, int row, double scaling, double qq_scaled,
                                             double& e_vdw, double& e_real, int& flag)
 {
   const double rinv = rsqrt(r2);
@@ -160,18 +166,19 @@ __device__ __forceinline__ void pair_energy(const DevParams& P, const double* __
   e_vdw = 0.0; e_real = 0.0; flag = 0;
   if(r2 < P.cut_vdw2)
   {
-    const double4 f = P.ffA[row];
+    const double4 f = ffp[row];
     double e;
     if(!P.use1264)
     {
       double rri3;
-      if(scaling == 1.0) { const double x = f.y * rinv2; rri3 = x * x * x; }
+      if(unit) { const double x = f.y * rinv2; rri3 = x * x * x; e = f.x * (rri3 * (rri3 - 1.0)) - f.z; }
+      else if(scaling == 1.0) { const double x = f.y * rinv2; rri3 = x * x * x; e = scaling * (f.x * (rri3 * (rri3 - 1.0)) - f.z); }
       else
       {
         const double t = r2 * f.w; const double t3 = t * t * t; const double om = 1.0 - scaling;
         rri3 = 1.0 / (t3 + 0.5 * om * om);
+        e = scaling * (f.x * (rri3 * (rri3 - 1.0)) - f.z);
       }
-      e = scaling * (f.x * (rri3 * (rri3 - 1.0)) - f.z);
     }
     else
     {
@@ -186,7 +193,7 @@ __device__ __forceinline__ void pair_energy(const DevParams& P, const double* __
   {
     const double r = r2 * rinv;
     const double x = P.alpha * r;
-    const double ec = (x < GBK_ERFC_XMAX) ? erfc_table_eval(etab, x) : erfc(x);
+    const double ec = (P.erfc_table_ok || x < GBK_ERFC_XMAX) ? erfc_table_eval(etab, x) : erfc(x);
     e_real = P.prefactor * qq_scaled * ec * rinv;
   }
 }

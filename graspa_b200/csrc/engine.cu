@@ -170,6 +170,7 @@ int ready(gb_engine* e)
   if(e->ncomp == 0) return fail(GB_ERR_STATE, "gb_set_components has not been called");
   for(int c = 0; c < e->ncomp; c++) if(!e->comps[c].uploaded) return fail(GB_ERR_STATE, "component " + std::to_string(c) + " has not been uploaded");
   CUDA_TRY(cudaSetDevice(e->device));
+  e->P.erfc_table_ok = (e->P.alpha * std::sqrt(e->P.cut_coul2) < GBK_ERFC_XMAX) ? 1 : 0;
   return sync_slots_to_device(e);
 }
 
@@ -879,13 +880,15 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   const int warpsA = 16;
   const size_t per_warpA = (sizeof(TrialGroup) + sizeof(WarpQueue) + (size_t) e->norient * (cs > 0 ? cs : 1) * 6 * sizeof(double) + 15) / 16 * 16;
   bool use_pack = false;
-  rc = ensure_pack(e, use_pack, warpsA * per_warpA + GBK_ERFC_BYTES + sizeof(SegList) + 128); if(rc) return rc;
+  const bool stage_ff = e->ntypes <= 24;
+  const size_t ff_bytes = stage_ff ? (size_t) e->ntypes * e->ntypes * sizeof(double4) : 0;
+  rc = ensure_pack(e, use_pack, warpsA * per_warpA + GBK_ERFC_BYTES + ff_bytes + sizeof(SegList) + 128); if(rc) return rc;
   WidomA A;
   A.pool3 = d_pool; A.fb_index = d_fb; A.or_index = d_or; A.uni = d_uni; A.n = n;
   A.ntrials = e->ntrials; A.norient = e->norient; A.ms = ms; A.comp = comp; A.new_molid = C.natoms / ms;
   A.tx = e->dx.p + C.offset; A.ty = e->dy.p + C.offset; A.tz = e->dz.p + C.offset; A.tq = e->dq.p + C.offset;
   A.tscoul = e->dscoul.p + C.offset; A.ttype = e->dtype.p + C.offset;
-  A.pack = e->d_pack.p; A.npad = e->pack_npad; A.use_pack = use_pack ? 1 : 0;
+  A.pack = e->d_pack.p; A.npad = e->pack_npad; A.use_pack = use_pack ? 1 : 0; A.stage_ff = stage_ff ? 1 : 0;
   A.rec = e->d_rec.p; A.stage = e->d_stage.p;
   SegList L = seg_list(e, 0);
   if(use_pack)
@@ -893,7 +896,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
     int acc = 0;
     for(int s = 0; s < L.nseg; s++) if(L.comp[s] < e->nhost) { L.staged[s] = 1; L.start[s] = acc; acc += L.count[s]; }
   }
-  const size_t headA = (16 + GBK_ERFC_BYTES + sizeof(SegList) + 15) / 16 * 16;
+  const size_t headA = (GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD + ff_bytes + sizeof(SegList) + 15) / 16 * 16;
   const size_t smemA = headA + (use_pack ? ((size_t) e->pack_npad * 36 + 15) / 16 * 16 : 0) + warpsA * per_warpA;
   if(smemA > e->smem_optin) return fail(GB_ERR_ARG, "Widom stage A shared memory exceeds the device limit");
   const int gridA = (int) std::min<long long>((n + warpsA - 1) / warpsA, e->prop.multiProcessorCount);

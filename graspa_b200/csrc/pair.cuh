@@ -8,7 +8,8 @@
 //     atom of the group;
 //   - the distance test runs for every pair, but only pairs inside a cutoff are pushed (ballot + popc
 //     compaction) into a per-warp shared-memory queue; the expensive LJ / erfc body is executed on full
-//     32-entry batches, so the FP64 pipe does not idle on the ~85 % of lanes that fail the cutoff;
+//     32-entry batches taken from the queue tail, so the FP64 pipe does not idle on the ~85 % of lanes that
+//     fail the cutoff;
 //   - minimum image in fractional space with a magic-number round (3 DADD per axis, no F2I/I2F), cell matrix in
 //     registers with the structural zeros of lower-triangular / orthorhombic cells removed at compile time;
 //   - a group may feed NS (1 or 2) accumulator slots: the two atoms of a CO2 chain trial feed one slot, two
@@ -40,6 +41,10 @@ struct PairAcc
   __device__ __forceinline__ void clear() { for(int s = 0; s < NS; s++) { vdw[s] = 0.0; real[s] = 0.0; } flag = 0; }
 };
 
+// tables a pair loop needs besides the atoms: erfc polynomial table (shared memory), LJ table (shared copy or
+// P.ffA), and the warp-uniform "every scaling factor is 1" flag
+struct PairTables { const double* etab; const double4* ffp; bool unit; };
+
 // where the system atoms of a range live
 template <bool STAGED>
 struct SysAccess
@@ -61,22 +66,21 @@ __device__ __forceinline__ SysAccess<STAGED> make_access(const SysView& S)
   return A;
 }
 
-// the expensive body, executed by lanes [0, n)
+// the expensive body: lanes [0, n) take queue entries [off, off+n)
 template <int NS, bool STAGED>
-__device__ __forceinline__ void drain_queue(const DevParams& P, const double* __restrict__ etab, const SysAccess<STAGED>& S,
-                                            const TrialGroup* T, const WarpQueue* Q, int n, PairAcc<NS>& acc)
+__device__ __forceinline__ void drain_queue(const DevParams& P, const PairTables& W, const SysAccess<STAGED>& S,
+                                            const TrialGroup* T, const WarpQueue* Q, int lane, int off, int n, PairAcc<NS>& acc)
 {
-  const int lane = lane_id();
   if(lane < n)
   {
-    const double r2 = Q->r2[lane];
-    const int code = Q->code[lane];
+    const double r2 = Q->r2[off + lane];
+    const int code = Q->code[off + lane];
     const int i = code >> 6, a = code & 63;
     const int row = S.type[i] * P.ntypes + T->type[a];
     double scaling = T->scale[a], qq = S.q[i] * T->q[a];      // staged pack: q already holds charge*scaleCoul
     if(!STAGED && !P.all_unit_scale) { scaling *= S.scale[i]; qq *= S.scoul[i]; }
     double ev, er; int fl;
-    pair_energy(P, etab, r2, row, scaling, qq, ev, er, fl);
+    pair_energy(P, W.etab, W.ffp, W.unit, r2, row, scaling, qq, ev, er, fl);
     if(NS == 1) { acc.vdw[0] += ev; acc.real[0] += er; acc.flag |= fl; }
     else
     {
@@ -92,21 +96,22 @@ __device__ __forceinline__ void drain_queue(const DevParams& P, const double* __
 // excl_a / excl_b: molecule ids to skip in this range (-1: none) -- VDW_Coulomb.cu:1282-1283.
 // wslice/nslice: this warp handles iterations wslice, wslice+nslice, ... (nslice = 1: the whole range).
 template <int CS, int NS, int CELL, bool STAGED, bool EXCL>
-__device__ __forceinline__ void pair_range(const DevParams& P, const double* __restrict__ etab, const SysAccess<STAGED>& S,
+__device__ __forceinline__ void pair_range(const DevParams& P, const PairTables& W, const SysAccess<STAGED>& S,
                                            int start, int end, int excl_a, int excl_b, const TrialGroup* T, int cs_dyn,
                                            WarpQueue* Q, int wslice, int nslice, PairAcc<NS>& acc)
 {
   S.hint();
-  const int lane = lane_id();
+  const int lane = (int) lane_id();
   const unsigned lt_mask = (1u << lane) - 1u;
   const int cs = CS > 0 ? CS : cs_dyn;
   const double cut_max = P.no_charges ? P.cut_vdw2 : fmax(P.cut_vdw2, P.cut_coul2);
   CellRegs<CELL> C; C.load(P);
-  double tx[CS > 0 ? CS : 1], ty[CS > 0 ? CS : 1], tz[CS > 0 ? CS : 1];
-  if(CS > 0)
+  constexpr int NR = (CS > 0 && CS <= 3) ? CS : 1;
+  double tx[NR], ty[NR], tz[NR];
+  if(CS > 0 && CS <= 3)
   {
 #pragma unroll
-    for(int a = 0; a < CS; a++) { tx[a] = T->fx[a]; ty[a] = T->fy[a]; tz[a] = T->fz[a]; }
+    for(int a = 0; a < NR; a++) { tx[a] = T->fx[a]; ty[a] = T->fy[a]; tz[a] = T->fz[a]; }
   }
   int qn = 0;
   for(int base = start + 32 * wslice; base < end; base += 32 * nslice)
@@ -116,37 +121,58 @@ __device__ __forceinline__ void pair_range(const DevParams& P, const double* __r
     const int ii = STAGED ? i : (valid ? i : end - 1);        // the staged pack is padded: unconditional loads
     const double ax = S.fx[ii], ay = S.fy[ii], az = S.fz[ii];
     if(EXCL) { const int m = S.molid[ii]; valid = valid && (m != excl_a) && (m != excl_b); }
-#pragma unroll
-    for(int a = 0; a < cs; a++)
+    if(CS > 0 && CS <= 3)
     {
-      double bx, by, bz;
-      if(CS > 0) { bx = tx[a]; by = ty[a]; bz = tz[a]; } else { bx = T->fx[a]; by = T->fy[a]; bz = T->fz[a]; }
-      const double r2 = C.r2(ax - bx, ay - by, az - bz);
-      const bool hit = valid && (r2 < cut_max);
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if(hit) { const int p = qn + __popc(m & lt_mask); Q->r2[p] = r2; Q->code[p] = (i << 6) | a; }
-      qn += __popc(m);
+      // all distances of the group first (independent FP64 chains), then one compaction pass and one drain check
+      double r2v[NR]; unsigned mv[NR];
+#pragma unroll
+      for(int a = 0; a < NR; a++) r2v[a] = C.r2(ax - tx[a], ay - ty[a], az - tz[a]);
+#pragma unroll
+      for(int a = 0; a < NR; a++) mv[a] = __ballot_sync(0xffffffffu, valid && (r2v[a] < cut_max));
+#pragma unroll
+      for(int a = 0; a < NR; a++)
+      {
+        if((mv[a] >> lane) & 1u) { const int p = qn + __popc(mv[a] & lt_mask); Q->r2[p] = r2v[a]; Q->code[p] = (i << 6) | a; }
+        qn += __popc(mv[a]);
+      }
       if(qn >= 32)
       {
         __syncwarp();
-        drain_queue<NS, STAGED>(P, etab, S, T, Q, 32, acc);
-        const int rest = qn - 32;
-        double r2m = 0.0; int cm = 0;
-        if(lane < rest) { r2m = Q->r2[32 + lane]; cm = Q->code[32 + lane]; }
-        __syncwarp();
-        if(lane < rest) { Q->r2[lane] = r2m; Q->code[lane] = cm; }
-        qn = rest;
+        do { qn -= 32; drain_queue<NS, STAGED>(P, W, S, T, Q, lane, qn, 32, acc); } while(qn >= 32);
         __syncwarp();
       }
     }
+    else
+    {
+      for(int a = 0; a < cs; a++)
+      {
+        const double r2 = C.r2(ax - T->fx[a], ay - T->fy[a], az - T->fz[a]);
+        const bool hit = valid && (r2 < cut_max);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if(hit) { const int p = qn + __popc(m & lt_mask); Q->r2[p] = r2; Q->code[p] = (i << 6) | a; }
+        qn += __popc(m);
+        if(qn >= GBK_QCAP - 32)
+        {
+          __syncwarp();
+          do { qn -= 32; drain_queue<NS, STAGED>(P, W, S, T, Q, lane, qn, 32, acc); } while(qn >= 32);
+          __syncwarp();
+        }
+      }
+    }
   }
-  if(qn > 0) { __syncwarp(); drain_queue<NS, STAGED>(P, etab, S, T, Q, qn, acc); __syncwarp(); }
+  if(qn > 0)
+  {
+    __syncwarp();
+    while(qn >= 32) { qn -= 32; drain_queue<NS, STAGED>(P, W, S, T, Q, lane, qn, 32, acc); }
+    if(qn > 0) drain_queue<NS, STAGED>(P, W, S, T, Q, lane, 0, qn, acc);
+    __syncwarp();
+  }
 }
 
 // all segments for one trial group, generic (cold) flavour: global memory, general cell, exclusions checked.
 // e6 = lane-partial sums {HHv, HHr, HGv, HGr, GGv, GGr}; kinds come from L.kind[].
 template <int CS>
-__device__ __forceinline__ void pair_group_generic(const DevParams& P, const double* __restrict__ etab, const SysView& Sg, const SegList& L,
+__device__ __forceinline__ void pair_group_generic(const DevParams& P, const PairTables& W, const SysView& Sg, const SegList& L,
                                                    int new_comp, int new_molid, int excl_comp, int excl_mol,
                                                    const TrialGroup* T, int cs_dyn, WarpQueue* Q, int wslice, int nslice,
                                                    double* e6, int& flag)
@@ -157,7 +183,7 @@ __device__ __forceinline__ void pair_group_generic(const DevParams& P, const dou
     PairAcc<1> acc; acc.clear();
     const int ea = (L.comp[s] == excl_comp) ? excl_mol : -1;
     const int eb = (L.comp[s] == new_comp) ? new_molid : -1;
-    pair_range<CS, 1, 0, false, true>(P, etab, S, L.start[s], L.start[s] + L.count[s], ea, eb, T, cs_dyn, Q, wslice, nslice, acc);
+    pair_range<CS, 1, 0, false, true>(P, W, S, L.start[s], L.start[s] + L.count[s], ea, eb, T, cs_dyn, Q, wslice, nslice, acc);
     const int k = L.kind[s];
     e6[0] += (k == 0) ? acc.vdw[0] : 0.0; e6[1] += (k == 0) ? acc.real[0] : 0.0;
     e6[2] += (k == 1) ? acc.vdw[0] : 0.0; e6[3] += (k == 1) ? acc.real[0] : 0.0;

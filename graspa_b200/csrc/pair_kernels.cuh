@@ -17,7 +17,7 @@ struct TrialBuf            // device arrays of trial atoms (Sims.New), group-maj
 };
 
 template <int CS>
-__device__ __forceinline__ void group_energy_cta(const DevParams& P, const double* etab, const SysView& S, const SegList& L, const TrialBuf& B,
+__device__ __forceinline__ void group_energy_cta(const DevParams& P, const PairTables& W, const SysView& S, const SegList& L, const TrialBuf& B,
                                                  int group, int cs, int new_comp, int new_molid, int excl_comp, int excl_mol,
                                                  TrialGroup* T, WarpQueue* Qall, double* red /* [nwarps][8] */, double* out6, int* out_flag)
 {
@@ -30,7 +30,7 @@ __device__ __forceinline__ void group_energy_cta(const DevParams& P, const doubl
   }
   __syncthreads();
   double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
-  pair_group_generic<CS>(P, etab, S, L, new_comp, new_molid, excl_comp, excl_mol, T, cs, Qall + warp, warp, nwarps, e6, flag);
+  pair_group_generic<CS>(P, W, S, L, new_comp, new_molid, excl_comp, excl_mol, T, cs, Qall + warp, warp, nwarps, e6, flag);
 #pragma unroll
   for(int k = 0; k < 6; k++) e6[k] = warp_sum(e6[k]);
   flag = __any_sync(0xffffffffu, flag);
@@ -56,10 +56,11 @@ k_trial_energies(DevParams P, SysView S, SegList L, TrialBuf B, int cs, int new_
   __shared__ double etab[(GBK_ERFC_DEG + 1) * GBK_ERFC_NINT];
   stage_erfc_table(P, etab);
   __syncthreads();
+  PairTables W; W.etab = etab; W.ffp = P.ffA; W.unit = false;
   const int g = blockIdx.x;
-  if(cs == 1)      group_energy_cta<1>(P, etab, S, L, B, g, cs, new_comp, new_molid, excl_comp, excl_mol, &T, Q, red, out6 + 6 * g, out_flag + g);
-  else if(cs == 2) group_energy_cta<2>(P, etab, S, L, B, g, cs, new_comp, new_molid, excl_comp, excl_mol, &T, Q, red, out6 + 6 * g, out_flag + g);
-  else             group_energy_cta<0>(P, etab, S, L, B, g, cs, new_comp, new_molid, excl_comp, excl_mol, &T, Q, red, out6 + 6 * g, out_flag + g);
+  if(cs == 1)      group_energy_cta<1>(P, W, S, L, B, g, cs, new_comp, new_molid, excl_comp, excl_mol, &T, Q, red, out6 + 6 * g, out_flag + g);
+  else if(cs == 2) group_energy_cta<2>(P, W, S, L, B, g, cs, new_comp, new_molid, excl_comp, excl_mol, &T, Q, red, out6 + 6 * g, out_flag + g);
+  else             group_energy_cta<0>(P, W, S, L, B, g, cs, new_comp, new_molid, excl_comp, excl_mol, &T, Q, red, out6 + 6 * g, out_flag + g);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -93,7 +94,8 @@ k_total_vdw_real(DevParams P, SysView S, TotalArgs A)
   __syncthreads();
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
-  pair_group_generic<1>(P, etab, S, L, mycomp, S.molid[i], -1, -1, &T, 1, Q + warp, warp, nwarps, e6, flag);
+  PairTables W; W.etab = etab; W.ffp = P.ffA; W.unit = false;
+  pair_group_generic<1>(P, W, S, L, mycomp, S.molid[i], -1, -1, &T, 1, Q + warp, warp, nwarps, e6, flag);
 #pragma unroll
   for(int k = 0; k < 6; k++) e6[k] = warp_sum(e6[k]);
   if(lane_id() == 0) for(int k = 0; k < 6; k++) red[warp * 8 + k] = e6[k];
@@ -122,7 +124,7 @@ struct WidomA
   // template molecule = slot 0 of the component (mc_widom.h:256): Cartesian positions, charge, scaleCoul, type
   const double* __restrict__ tx; const double* __restrict__ ty; const double* __restrict__ tz;
   const double* __restrict__ tq; const double* __restrict__ tscoul; const int* __restrict__ ttype;
-  const double* __restrict__ pack; int npad; int use_pack;
+  const double* __restrict__ pack; int npad; int use_pack; int stage_ff;
   double* rec;        // per insertion: [W12, HGv, HGr, GGv, GGr, x0,y0,z0, x1,...]  stride 5 + 3*ms
   int* stage;         // 0 ok, 1 first bead failed, 2 chain failed
 };
@@ -130,7 +132,7 @@ struct WidomA
 // per-warp context of the Widom pair kernel
 struct WidomCtx
 {
-  const double* etab;
+  PairTables W;
   SysView Sg;        // global slot arrays
   SysView Ss;        // staged pack view (shared memory)
   const SegList* L;  // in shared memory
@@ -156,13 +158,13 @@ __device__ __forceinline__ void widom_group(const DevParams& P, const WidomCtx& 
     if(L.staged[g])
     {
       const SysAccess<true> S = make_access<true>(X.Ss);
-      pair_range<CS, NS, CELL, true, false>(P, X.etab, S, start, end, -1, -1, X.T, cs_dyn, X.Q, 0, 1, acc);
+      pair_range<CS, NS, CELL, true, false>(P, X.W, S, start, end, -1, -1, X.T, cs_dyn, X.Q, 0, 1, acc);
     }
     else
     {
       const SysAccess<false> S = make_access<false>(X.Sg);
       const int eb = (L.comp[g] == comp) ? new_molid : -1;
-      pair_range<CS, NS, CELL, false, true>(P, X.etab, S, start, end, -1, eb, X.T, cs_dyn, X.Q, 0, 1, acc);
+      pair_range<CS, NS, CELL, false, true>(P, X.W, S, start, end, -1, eb, X.T, cs_dyn, X.Q, 0, 1, acc);
     }
 #pragma unroll
     for(int s = 0; s < NS; s++)
@@ -186,11 +188,13 @@ __global__ void __launch_bounds__(512, 1)
 k_widom_pair(DevParams P, SysView Sg, SegList Lin, WidomA A)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  // layout: [mbarrier 16 B][erfc table][SegList][pack][per-warp: TrialGroup, WarpQueue, chain_f, chain_c]
+  // layout: [mbarrier 16 B][erfc table][LJ table (if it fits)][SegList][pack][per-warp: TrialGroup, WarpQueue, chain_f, chain_c]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  double* etab = reinterpret_cast<double*>(smem + 16);
-  SegList* L = reinterpret_cast<SegList*>(smem + 16 + GBK_ERFC_BYTES);
-  const size_t head = (16 + GBK_ERFC_BYTES + sizeof(SegList) + 15) / 16 * 16;
+  double* etab = reinterpret_cast<double*>(smem + GBK_SMEM_TABLES_OFF);
+  double4* fftab = reinterpret_cast<double4*>(smem + GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD);
+  const size_t ff_bytes = A.stage_ff ? (size_t) P.ntypes * P.ntypes * sizeof(double4) : 0;
+  SegList* L = reinterpret_cast<SegList*>(smem + GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD + ff_bytes);
+  const size_t head = (GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD + ff_bytes + sizeof(SegList) + 15) / 16 * 16;
   double* pack = reinterpret_cast<double*>(smem + head);
   const size_t pack_bytes = A.use_pack ? ((size_t) A.npad * 36 + 15) / 16 * 16 : 0;
   unsigned char* wbase = smem + head + pack_bytes;
@@ -203,8 +207,9 @@ k_widom_pair(DevParams P, SysView Sg, SegList Lin, WidomA A)
   double* chain_c = chain_f + (size_t) A.norient * (cs > 0 ? cs : 1) * 3;                                  // Cartesian
 
   stage_erfc_table(P, etab);
+  if(A.stage_ff) for(int i = threadIdx.x; i < P.ntypes * P.ntypes; i += blockDim.x) fftab[i] = P.ffA[i];
   if(threadIdx.x == 0) *L = Lin;
-  WidomCtx X; X.etab = etab; X.Sg = Sg; X.Ss = Sg; X.L = L; X.T = T; X.Q = Q;
+  WidomCtx X; X.W.etab = etab; X.W.ffp = A.stage_ff ? fftab : P.ffA; X.W.unit = P.all_unit_scale != 0; X.Sg = Sg; X.Ss = Sg; X.L = L; X.T = T; X.Q = Q;
   if(A.use_pack)
   {
     stage_bulk(pack, A.pack, (uint32_t) pack_bytes, bar);
