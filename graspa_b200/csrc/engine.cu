@@ -3,6 +3,7 @@
 #include "../../include/graspa_b200.h"
 #include "misc_kernels.cuh"
 #include "pair_kernels.cuh"
+#include "move_kernels.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -94,6 +95,12 @@ struct gb_engine
   DevBuf<long long> d_idx0, d_idx1;
   DevBuf<unsigned int> d_ticket;
   double* h_pinned = nullptr;            // 4 KB pinned result slot
+
+  // single-move path
+  DevBuf<double> d_mv, d_ewpos; DevBuf<int> d_mvi;
+  int last_fb_selected = 0, last_cbmc_comp = -1; long long last_cbmc_selected = 0;
+  int sb_comp = -1, sb_type = -1; long long sb_molecule = 0;
+  bool committed = false;                // device slots changed by accept calls: the device is authoritative
 
   long long launches = 0;
   bool timing = false;
@@ -350,7 +357,7 @@ int gb_engine_destroy(gb_engine* e)
   for(int i = 0; i < 3; i++) e->d_sf[i].release();
   e->d_ktab.release(); e->d_pool.release(); e->d_rec.release(); e->d_out8.release(); e->d_partial.release(); e->d_sums.release();
   e->d_uni.release(); e->d_scratch.release(); e->d_result.release(); e->d_stage.release(); e->d_iscratch.release();
-  e->d_idx0.release(); e->d_idx1.release(); e->d_ticket.release();
+  e->d_idx0.release(); e->d_idx1.release(); e->d_ticket.release(); e->d_mv.release(); e->d_mvi.release(); e->d_ewpos.release();
   if(e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
   cudaStreamDestroy(e->stream);
@@ -487,6 +494,18 @@ int gb_upload_atoms(gb_engine* e, int32_t c, const gb_atoms* a)
   if(c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "component out of range");
   if(a->n_live > a->n_upload || a->n_upload > a->n_alloc || a->molsize <= 0) return fail(GB_ERR_ARG, "inconsistent atom counts");
   if(!e->have_ff) return fail(GB_ERR_STATE, "upload the force field before atoms");
+  if(e->committed && !e->device_stale && e->nslots > 0)
+  {
+    // accept calls changed the device copy: bring the host staging arrays up to date before they are re-uploaded
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    const size_t n = (size_t) e->nslots, b = n * sizeof(double);
+    CUDA_TRY(cudaMemcpy(e->hx.data(), e->dx.p, b, cudaMemcpyDeviceToHost)); CUDA_TRY(cudaMemcpy(e->hy.data(), e->dy.p, b, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(e->hz.data(), e->dz.p, b, cudaMemcpyDeviceToHost)); CUDA_TRY(cudaMemcpy(e->hq.data(), e->dq.p, b, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(e->hscale.data(), e->dscale.p, b, cudaMemcpyDeviceToHost)); CUDA_TRY(cudaMemcpy(e->hscoul.data(), e->dscoul.p, b, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(e->htype.data(), e->dtype.p, n * sizeof(int), cudaMemcpyDeviceToHost)); CUDA_TRY(cudaMemcpy(e->hmolid.data(), e->dmolid.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    e->committed = false;
+  }
   Comp& C = e->comps[c];
   if(C.uploaded && C.alloc != (int) a->n_alloc) return fail(GB_ERR_ARG, "component re-uploaded with a different n_alloc");
   if(!C.uploaded)
@@ -1000,4 +1019,4 @@ int gb_measure_fp64_peak(gb_engine* e, double* tflops)
 }
 
 } // extern "C"
-#include "moves_stub.inc"
+#include "moves.inc"

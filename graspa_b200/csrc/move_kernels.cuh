@@ -1,0 +1,450 @@
+// graspa_b200 -- kernels of the single-move path (CBMC stages, translation/rotation, state commit).
+// One launch per CBMC stage: trial generation + pair energies + Boltzmann/selection/Rosenbluth (the last CTA to
+// finish runs the host code of mc_widom.h:305-383 / 568-611 on the device), one 128-byte result read.
+#pragma once
+#include "common.cuh"
+#include "pair.cuh"
+
+#define GBK_MV_MAXT 32
+#define GBK_MV_TRIAL_SLOTS 1024       // Setup_Temporary_Atoms_Structure allocates 1024 slots (fxn_main.h:99-113)
+#define GBK_MV_MOL_SLOTS 64
+enum { GBK_BUF_GROWN = 0, GBK_BUF_OLD = 1, GBK_BUF_NEW = 2, GBK_BUF_TEMP = 3 };
+
+// device scratch of the move path: trial atoms (Sims.New), and four molecule buffers:
+// grown (Sims.Old[0] + selected orientation), old / new (Sims.Old / Sims.New of single-body moves), temp (tempMolStorage)
+struct MoveBufs
+{
+  double* d; int* i;
+  __host__ __device__ double* tr(int arr) const { return d + (size_t) arr * GBK_MV_TRIAL_SLOTS; }           // 0..8: x y z fx fy fz q scale scoul
+  __host__ __device__ int* tr_type() const { return i; }
+  __host__ __device__ double* mol(int buf, int arr) const { return d + 9 * GBK_MV_TRIAL_SLOTS + ((size_t) buf * 9 + arr) * GBK_MV_MOL_SLOTS; }
+  __host__ __device__ int* mol_type(int buf) const { return i + GBK_MV_TRIAL_SLOTS + buf * GBK_MV_MOL_SLOTS; }
+  __host__ __device__ double* stage_e() const { return d + 9 * GBK_MV_TRIAL_SLOTS + 36 * GBK_MV_MOL_SLOTS; }   // [32][6]
+  __host__ __device__ int* stage_flag() const { return i + GBK_MV_TRIAL_SLOTS + 4 * GBK_MV_MOL_SLOTS; }      // [32]
+  __host__ __device__ double* result() const { return stage_e() + GBK_MV_MAXT * 6; }                          // 16 doubles
+  __host__ __device__ double* partial() const { return result() + 16; }                                       // [64][16]
+  static size_t doubles() { return 9 * GBK_MV_TRIAL_SLOTS + 36 * GBK_MV_MOL_SLOTS + GBK_MV_MAXT * 6 + 16 + 64 * 16; }
+  static size_t ints() { return GBK_MV_TRIAL_SLOTS + 4 * GBK_MV_MOL_SLOTS + GBK_MV_MAXT + 16; }
+};
+
+// component slot arrays (Cartesian + properties), for reading existing molecules / the template
+struct CompView
+{
+  const double* __restrict__ x; const double* __restrict__ y; const double* __restrict__ z;
+  const double* __restrict__ q; const double* __restrict__ scale; const double* __restrict__ scoul;
+  const int* __restrict__ type;
+};
+
+struct CbmcArgs
+{
+  int cbmc_type, comp, ms, ntrials, norm, new_molid, excl_comp, excl_mol, first_bead_trial;
+  long long molecule;          // SelectedMolInComponent
+  long long pool_off;
+  const double* __restrict__ pool3;
+  double uniform, scale, scale_coul, stored_r;
+  double preset[3]; int has_preset;
+  CompView C;                  // slots of the component (index 0 = slot 0 of the component)
+  MoveBufs B;
+  unsigned int* ticket;
+};
+
+// SelectTrialPosition, mc_widom.h:14-39
+__device__ __forceinline__ int select_trial_position(const double* lb, int n, double uniform)
+{
+  double largest = lb[0];
+  for(int i = 1; i < n; i++) largest = fmax(largest, lb[i]);
+  double sum = 0.0;
+  for(int i = 0; i < n; i++) sum += exp(lb[i] - largest);
+  int selected = 0; double cumw = exp(lb[0] - largest); const double ws = uniform * sum;
+  while(cumw < ws && selected + 1 < n) cumw += exp(lb[++selected] - largest);
+  return selected;
+}
+
+// device restatement of the tail of CBMC_FirstBead_Finish / Widom_Move_Chain_PARTIAL; result layout:
+// r[0] rosenbluth, r[1] stored_r, r[2..5] energy, r[6..8] selected pos, r[9] success, r[10] selected, r[11] nsurv, r[12] uniform used
+__device__ __forceinline__ void cbmc_finish(const DevParams& P, const CbmcArgs& A, bool is_chain, double* r)
+{
+  const double* E = A.B.stage_e(); const int* F = A.B.stage_flag();
+  double rosen[GBK_MV_MAXT]; int idx[GBK_MV_MAXT]; int ns = 0;
+  for(int t = 0; t < A.ntrials; t++)
+    if(!F[t])
+    {
+      // HH terms (a framework component grown against framework components) count with HG: VDW_Coulomb.cu:1232-1235
+      double tot = (E[6 * t] + E[6 * t + 2]) + E[6 * t + 4];
+      if(P.vdw_real_bias) tot += (E[6 * t + 1] + E[6 * t + 3]) + E[6 * t + 5];
+      rosen[ns] = -P.beta * tot; idx[ns] = t; ns++;
+    }
+  const int ty = A.cbmc_type;
+  const bool insertion_like = (ty == 0 /*CBMC_INSERTION*/ || ty == 2 /*REINSERTION_INSERTION*/ || (is_chain && ty == 4 /*IDENTITY_SWAP_NEW*/));
+  const bool needs_survivor = insertion_like || ty == 4;
+  int good = 0, sel = 0, used = 0; double R = 0.0, Rsel = 0.0;
+  for(int k = 0; k < 13; k++) r[k] = 0.0;
+  r[11] = ns;
+  if(!(needs_survivor && ns == 0))
+  {
+    if(insertion_like) { sel = select_trial_position(rosen, ns, A.uniform); used = 1; }
+    for(int a = 0; a < ns; a++) { const double w = exp(rosen[a]); R += w; if(a == sel) Rsel = w; }
+    good = needs_survivor ? !(R < 1e-150) : 1;
+  }
+  r[12] = used;
+  if(!good) return;
+  if(ns == 0) { r[9] = 1.0; return; }          // deletion types with every trial overlapping: Rosenbluth 0, Trialindex empty
+  const int real_sel = idx[sel];
+  double avg = R;
+  if(!is_chain)
+  {
+    if(ty == 2) r[1] = R - Rsel;                                        // StoredR, mc_widom.h:365
+    if(ty == 3) avg += A.stored_r;                                       // REINSERTION_RETRACE :366
+    if(ty != 4 && ty != 5) avg /= (double) A.norm;                       // :369-370
+  }
+  else avg = R / (double) A.norm;                                         // :601
+  const double hgr = E[6 * real_sel + 3] + E[6 * real_sel + 1], ggr = E[6 * real_sel + 5];
+  if(!P.vdw_real_bias) avg *= exp(-P.beta * (hgr + ggr));                 // :373-377, :603-607
+  r[0] = avg;
+  r[2] = E[6 * real_sel + 2] + E[6 * real_sel]; r[3] = hgr; r[4] = E[6 * real_sel + 4]; r[5] = ggr;
+  r[9] = 1.0; r[10] = real_sel;
+}
+
+template <int CS>
+__device__ __forceinline__ void cbmc_group_energy(const DevParams& P, const PairTables& W, const SysView& S, const SegList& L, const CbmcArgs& A,
+                                                  TrialGroup* T, WarpQueue* Q, double* red, int cs)
+{
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = (int) lane_id();
+  double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
+  pair_group_generic<CS>(P, W, S, L, A.comp, A.new_molid, A.excl_comp, A.excl_mol, T, cs, Q + warp, warp, nwarps, e6, flag);
+#pragma unroll
+  for(int k = 0; k < 6; k++) e6[k] = warp_sum(e6[k]);
+  flag = __any_sync(0xffffffffu, flag);
+  if(lane == 0) { for(int k = 0; k < 6; k++) red[warp * 8 + k] = e6[k]; red[warp * 8 + 6] = flag ? 1.0 : 0.0; }
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    double s[7] = {0, 0, 0, 0, 0, 0, 0};
+    for(int w = 0; w < nwarps; w++) for(int k = 0; k < 7; k++) s[k] += red[w * 8 + k];
+    for(int k = 0; k < 6; k++) A.B.stage_e()[6 * blockIdx.x + k] = s[k];
+    A.B.stage_flag()[blockIdx.x] = s[6] > 0.0 ? 1 : 0;
+  }
+}
+
+// first bead: get_random_trial_position (mc_widom.h:122-213) + energies + CBMC_FirstBead_Finish (:305-383)
+__global__ void __launch_bounds__(256)
+k_cbmc_first_bead(DevParams P, SysView S, SegList L, CbmcArgs A)
+{
+  __shared__ TrialGroup T;
+  __shared__ WarpQueue Q[8];
+  __shared__ double red[8 * 8];
+  __shared__ double etab[(GBK_ERFC_DEG + 1) * GBK_ERFC_NINT];
+  __shared__ bool last;
+  stage_erfc_table(P, etab);
+  const int t = blockIdx.x;
+  if(threadIdx.x == 0)
+  {
+    const int ty = A.cbmc_type;
+    const bool insertion_like = (ty == 0 || ty == 4);
+    const long long start = insertion_like ? 0 : A.molecule * A.ms;
+    double scale = A.scale, scoul = A.scale_coul;
+    if(!insertion_like) { scale = A.C.scale[start]; scoul = A.C.scoul[start]; }
+    double x, y, z;
+    const bool existing = (ty == 1 || ty == 3 || ty == 5) && t == 0;
+    if(existing) { x = A.C.x[start]; y = A.C.y[start]; z = A.C.z[start]; }
+    else if(ty == 4 && A.has_preset) { x = A.preset[0]; y = A.preset[1]; z = A.preset[2]; }
+    else { const double* r = A.pool3 + 3 * (A.pool_off + t); x = P.cell[0] * r[0]; y = P.cell[4] * r[1]; z = P.cell[8] * r[2]; }
+    double fx, fy, fz; to_frac(P, x, y, z, fx, fy, fz);
+    const double q = A.C.q[start]; const int type = A.C.type[start];
+    A.B.tr(0)[t] = x; A.B.tr(1)[t] = y; A.B.tr(2)[t] = z; A.B.tr(3)[t] = fx; A.B.tr(4)[t] = fy; A.B.tr(5)[t] = fz;
+    A.B.tr(6)[t] = q; A.B.tr(7)[t] = scale; A.B.tr(8)[t] = scoul; A.B.tr_type()[t] = type;
+    T.fx[0] = fx; T.fy[0] = fy; T.fz[0] = fz; T.q[0] = q * scoul; T.scale[0] = scale; T.type[0] = type; T.slot[0] = 0;
+  }
+  __syncthreads();
+  PairTables W; W.etab = etab; W.ffp = P.ffA; W.unit = false;
+  cbmc_group_energy<1>(P, W, S, L, A, &T, Q, red, 1);
+  if(threadIdx.x == 0) { __threadfence(); last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1); }
+  __syncthreads();
+  if(last && threadIdx.x == 0)
+  {
+    __threadfence();
+    double* r = A.B.result();
+    cbmc_finish(P, A, false, r);
+    if(r[9] != 0.0)
+    {
+      const int s = (int) r[10];
+      r[6] = A.B.tr(0)[s]; r[7] = A.B.tr(1)[s]; r[8] = A.B.tr(2)[s];
+      // Mol.pos[0] = NewMol.pos[FirstBeadTrial] etc., mc_widom.h:230-241
+      for(int k = 0; k < 9; k++) A.B.mol(GBK_BUF_GROWN, k)[0] = A.B.tr(k)[s];
+      A.B.mol_type(GBK_BUF_GROWN)[0] = A.B.tr_type()[s];
+    }
+    *A.ticket = 0u;
+  }
+}
+
+// chain: get_random_trial_orientation (mc_widom.h:215-303) + energies + the tail of Widom_Move_Chain_PARTIAL (:568-611)
+__global__ void __launch_bounds__(256)
+k_cbmc_chain(DevParams P, SysView S, SegList L, CbmcArgs A)
+{
+  __shared__ TrialGroup T;
+  __shared__ WarpQueue Q[8];
+  __shared__ double red[8 * 8];
+  __shared__ double etab[(GBK_ERFC_DEG + 1) * GBK_ERFC_NINT];
+  __shared__ bool last;
+  stage_erfc_table(P, etab);
+  const int o = blockIdx.x, cs = A.ms - 1;
+  if(threadIdx.x < cs)
+  {
+    const int a = threadIdx.x, ty = A.cbmc_type;
+    const bool insertion_like = (ty == 0 || ty == 4);
+    const long long start = (insertion_like ? 0 : A.molecule * A.ms) + 1;        // start_position, mc_widom.h:536-556
+    const double fbx = A.B.mol(GBK_BUF_GROWN, 0)[0], fby = A.B.mol(GBK_BUF_GROWN, 1)[0], fbz = A.B.mol(GBK_BUF_GROWN, 2)[0];
+    double vx = A.C.x[1 + a] - A.C.x[0], vy = A.C.y[1 + a] - A.C.y[0], vz = A.C.z[1 + a] - A.C.z[0];   // :256
+    double x, y, z;
+    if((ty == 1 || ty == 3 || ty == 5) && o == 0) { x = A.C.x[start + a]; y = A.C.y[start + a]; z = A.C.z[start + a]; }
+    else
+    {
+      const double* r = A.pool3 + 3 * (A.pool_off + o);
+      rotate_quaternion(vx, vy, vz, r[0], r[1], r[2]);
+      x = fbx + vx; y = fby + vy; z = fbz + vz;
+    }
+    double fx, fy, fz; to_frac(P, x, y, z, fx, fy, fz);
+    const double scale = A.B.mol(GBK_BUF_GROWN, 7)[0], scoul = A.B.mol(GBK_BUF_GROWN, 8)[0];             // Chosenscale(Coul)
+    const double q = A.C.q[start + a]; const int type = A.C.type[start + a];
+    const int j = o * cs + a;
+    A.B.tr(0)[j] = x; A.B.tr(1)[j] = y; A.B.tr(2)[j] = z; A.B.tr(3)[j] = fx; A.B.tr(4)[j] = fy; A.B.tr(5)[j] = fz;
+    A.B.tr(6)[j] = q; A.B.tr(7)[j] = scale; A.B.tr(8)[j] = scoul; A.B.tr_type()[j] = type;
+    T.fx[a] = fx; T.fy[a] = fy; T.fz[a] = fz; T.q[a] = q * scoul; T.scale[a] = scale; T.type[a] = type; T.slot[a] = 0;
+  }
+  __syncthreads();
+  PairTables W; W.etab = etab; W.ffp = P.ffA; W.unit = false;
+  if(cs == 1) cbmc_group_energy<1>(P, W, S, L, A, &T, Q, red, cs);
+  else if(cs == 2) cbmc_group_energy<2>(P, W, S, L, A, &T, Q, red, cs);
+  else cbmc_group_energy<0>(P, W, S, L, A, &T, Q, red, cs);
+  if(threadIdx.x == 0) { __threadfence(); last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1); }
+  __syncthreads();
+  if(last)
+  {
+    __shared__ int sel_s;
+    if(threadIdx.x == 0)
+    {
+      __threadfence();
+      double* r = A.B.result();
+      cbmc_finish(P, A, true, r);
+      sel_s = (r[9] != 0.0 && r[11] > 0.0) ? (int) r[10] : -1;
+      *A.ticket = 0u;
+    }
+    __syncthreads();
+    // selected orientation joins the first bead in the grown-molecule buffer
+    if(sel_s >= 0 && threadIdx.x < cs)
+    {
+      const int j = sel_s * cs + threadIdx.x;
+      for(int k = 0; k < 9; k++) A.B.mol(GBK_BUF_GROWN, k)[1 + threadIdx.x] = A.B.tr(k)[j];
+      A.B.mol_type(GBK_BUF_GROWN)[1 + threadIdx.x] = A.B.tr_type()[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// translation / rotation proposal, get_new_position mc_utilities.h:485-606 (+ RotationAroundAxis :459-483)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rotate_about_axis(double& px, double& py, double& pz, double theta, double ax, double ay, double az)
+{
+  double s, c; sincos(theta, &s, &c);
+  const double w = 1.0 - c;
+  const double r00 = ax * ax * w + c,      r01 = ax * ay * w + az * s, r02 = ax * az * w - ay * s;
+  const double r10 = ax * ay * w - az * s, r11 = ay * ay * w + c,      r12 = ay * az * w + ax * s;
+  const double r20 = ax * az * w + ay * s, r21 = ay * az * w - ax * s, r22 = az * az * w + c;
+  const double x = px * r00 + py * r01 + pz * r02;
+  const double y = px * r10 + py * r11 + pz * r12;
+  const double z = px * r20 + py * r21 + pz * r22;
+  px = x; py = y; pz = z;
+}
+
+struct ProposeArgs
+{
+  int move_type, ms; long long start; long long pool_index;
+  const double* __restrict__ pool3;
+  double maxc[3];
+  CompView C; MoveBufs B; int new_molid;
+};
+
+__global__ void k_single_propose(DevParams P, ProposeArgs A)
+{
+  const int i = threadIdx.x;
+  if(i >= A.ms) return;
+  const long long rp = A.start + i;
+  const double x = A.C.x[rp], y = A.C.y[rp], z = A.C.z[rp];
+  const double* R = A.pool3 + 3 * A.pool_index;
+  double nx = x, ny = y, nz = z;
+  const double x0 = A.C.x[A.start], y0 = A.C.y[A.start], z0 = A.C.z[A.start];
+  switch(A.move_type)
+  {
+    case 0: // TRANSLATION
+      nx = x + A.maxc[0] * 2.0 * (R[0] - 0.5); ny = y + A.maxc[1] * 2.0 * (R[1] - 0.5); nz = z + A.maxc[2] * 2.0 * (R[2] - 0.5);
+      break;
+    case 1: // ROTATION
+    {
+      nx = x - x0; ny = y - y0; nz = z - z0;
+      const double ax = A.maxc[0] * 2.0 * (R[0] - 0.5), ay = A.maxc[1] * 2.0 * (R[1] - 0.5), az = A.maxc[2] * 2.0 * (R[2] - 0.5);
+      rotate_about_axis(nx, ny, nz, ax, 1.0, 0.0, 0.0);
+      rotate_about_axis(nx, ny, nz, ay, 0.0, 1.0, 0.0);
+      rotate_about_axis(nx, ny, nz, az, 0.0, 0.0, 1.0);
+      nx += x0; ny += y0; nz += z0;
+      break;
+    }
+    case 2: // SINGLE_INSERTION
+    {
+      const double cx = P.cell[0] * R[0], cy = P.cell[4] * R[1], cz = P.cell[8] * R[2];
+      if(i == 0) { nx = cx; ny = cy; nz = cz; }
+      else { double vx = x - x0, vy = y - y0, vz = z - z0; rotate_quaternion(vx, vy, vz, R[3], R[4], R[5]); nx = vx + cx; ny = vy + cy; nz = vz + cz; }
+      break;
+    }
+    case 3: // SINGLE_DELETION: falls through to SPECIAL_ROTATION in the reference (mc_utilities.h:561-571)
+    case 4: // SPECIAL_ROTATION
+    {
+      nx = x - x0; ny = y - y0; nz = z - z0;
+      const double ang = A.maxc[0] * 2.0 * (R[0] - 0.5);
+      double ax = A.C.x[A.start + 1] - x0, ay = A.C.y[A.start + 1] - y0, az = A.C.z[A.start + 1] - z0;
+      const double inv = 1.0 / sqrt(ax * ax + ay * ay + az * az);
+      ax *= inv; ay *= inv; az *= inv;
+      if(i != 0 && i != 1) rotate_about_axis(nx, ny, nz, 3.0 * ang, ax, ay, az);
+      nx += x0; ny += y0; nz += z0;
+      break;
+    }
+  }
+  const double q = A.C.q[rp], sc = A.C.scale[rp], scc = A.C.scoul[rp]; const int ty = A.C.type[rp];
+  double fx, fy, fz;
+  to_frac(P, nx, ny, nz, fx, fy, fz);
+  double* const* dummy = nullptr; (void) dummy;
+  A.B.mol(GBK_BUF_NEW, 0)[i] = nx; A.B.mol(GBK_BUF_NEW, 1)[i] = ny; A.B.mol(GBK_BUF_NEW, 2)[i] = nz;
+  A.B.mol(GBK_BUF_NEW, 3)[i] = fx; A.B.mol(GBK_BUF_NEW, 4)[i] = fy; A.B.mol(GBK_BUF_NEW, 5)[i] = fz;
+  A.B.mol(GBK_BUF_NEW, 6)[i] = q; A.B.mol(GBK_BUF_NEW, 7)[i] = sc; A.B.mol(GBK_BUF_NEW, 8)[i] = scc; A.B.mol_type(GBK_BUF_NEW)[i] = ty;
+  to_frac(P, x, y, z, fx, fy, fz);
+  A.B.mol(GBK_BUF_OLD, 0)[i] = x; A.B.mol(GBK_BUF_OLD, 1)[i] = y; A.B.mol(GBK_BUF_OLD, 2)[i] = z;
+  A.B.mol(GBK_BUF_OLD, 3)[i] = fx; A.B.mol(GBK_BUF_OLD, 4)[i] = fy; A.B.mol(GBK_BUF_OLD, 5)[i] = fz;
+  A.B.mol(GBK_BUF_OLD, 6)[i] = q; A.B.mol(GBK_BUF_OLD, 7)[i] = sc; A.B.mol(GBK_BUF_OLD, 8)[i] = scc; A.B.mol_type(GBK_BUF_OLD)[i] = ty;
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-body delta: Calculate_Single_Body_Energy_VDWReal (VDW_Coulomb.cu:626-841) + host sum
+// (mc_single_particle.h:183-200).  CTAs slice the atom ranges; each evaluates the NEW and the OLD molecule;
+// the last CTA sums the CTA partials in fixed order: delta = sum(new) - sum(old).
+// ---------------------------------------------------------------------------------------------
+struct SingleBodyArgs { int comp, molid, ms, do_new, do_old; MoveBufs B; unsigned int* ticket; };
+
+__global__ void __launch_bounds__(256)
+k_single_body(DevParams P, SysView S, SegList L, SingleBodyArgs A)
+{
+  __shared__ TrialGroup T;
+  __shared__ WarpQueue Q[8];
+  __shared__ double red[8 * 16];
+  __shared__ double etab[(GBK_ERFC_DEG + 1) * GBK_ERFC_NINT];
+  __shared__ bool last;
+  stage_erfc_table(P, etab);
+  PairTables W; W.etab = etab; W.ffp = P.ffA; W.unit = false;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = (int) lane_id();
+  double tot[14];
+  for(int k = 0; k < 14; k++) tot[k] = 0.0;
+  for(int pass = 0; pass < 2; pass++)
+  {
+    const bool run = pass == 0 ? A.do_new != 0 : A.do_old != 0;
+    const int buf = pass == 0 ? GBK_BUF_NEW : GBK_BUF_OLD;
+    __syncthreads();
+    if(run && threadIdx.x < A.ms)
+    {
+      const int a = threadIdx.x;
+      T.fx[a] = A.B.mol(buf, 3)[a]; T.fy[a] = A.B.mol(buf, 4)[a]; T.fz[a] = A.B.mol(buf, 5)[a];
+      T.q[a] = A.B.mol(buf, 6)[a] * A.B.mol(buf, 8)[a]; T.scale[a] = A.B.mol(buf, 7)[a]; T.type[a] = A.B.mol_type(buf)[a]; T.slot[a] = 0;
+    }
+    __syncthreads();
+    if(!run) continue;
+    double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
+    pair_group_generic<0>(P, W, S, L, A.comp, A.molid, -1, -1, &T, A.ms, Q + warp, blockIdx.x * nwarps + warp, gridDim.x * nwarps, e6, flag);
+#pragma unroll
+    for(int k = 0; k < 6; k++) tot[pass * 7 + k] = warp_sum(e6[k]);
+    tot[pass * 7 + 6] = __any_sync(0xffffffffu, flag) ? 1.0 : 0.0;
+  }
+  if(lane == 0) for(int k = 0; k < 14; k++) red[warp * 16 + k] = tot[k];
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    double s[14];
+    for(int k = 0; k < 14; k++) { s[k] = 0.0; for(int w = 0; w < nwarps; w++) s[k] += red[w * 16 + k]; }
+    for(int k = 0; k < 14; k++) A.B.partial()[blockIdx.x * 16 + k] = s[k];
+    __threadfence();
+    last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if(last && threadIdx.x == 0)
+  {
+    __threadfence();
+    const volatile double* p = A.B.partial();
+    double* r = A.B.result();
+    for(int k = 0; k < 6; k++)
+    {
+      double n = 0.0, o = 0.0;
+      for(unsigned int b = 0; b < gridDim.x; b++) { n += p[b * 16 + k]; o += p[b * 16 + 7 + k]; }
+      r[k] = n - o;
+    }
+    double fl = 0.0;
+    for(unsigned int b = 0; b < gridDim.x; b++) fl += p[b * 16 + 6];     // overlap of the NEW configuration only (:768-769)
+    r[6] = fl > 0.0 ? 1.0 : 0.0;
+    *A.ticket = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// state commit: update_translation_position / Update_insertion_data_Parallel / Update_deletion_data_Parallel /
+// Update_Reinsertion_data (mc_utilities.h:118-292, mc_swap_moves.h:44-49)
+// ---------------------------------------------------------------------------------------------
+struct SlotArrays { double* x; double* y; double* z; double* fx; double* fy; double* fz; double* q; double* scale; double* scoul; int* type; int* molid; };
+
+// copy n atoms of a molecule buffer into slots [dst, dst+n); what: 0 = positions only, 1 = pos+scale+charge+scaleCoul,
+// 2 = everything incl. type and MolID (= molid)
+__global__ void k_commit_from_buffer(SlotArrays S, MoveBufs B, int buf, int dst, int n, int what, int molid)
+{
+  const int i = threadIdx.x;
+  if(i >= n) return;
+  S.x[dst + i] = B.mol(buf, 0)[i]; S.y[dst + i] = B.mol(buf, 1)[i]; S.z[dst + i] = B.mol(buf, 2)[i];
+  S.fx[dst + i] = B.mol(buf, 3)[i]; S.fy[dst + i] = B.mol(buf, 4)[i]; S.fz[dst + i] = B.mol(buf, 5)[i];
+  if(what >= 1) { S.q[dst + i] = B.mol(buf, 6)[i]; S.scale[dst + i] = B.mol(buf, 7)[i]; S.scoul[dst + i] = B.mol(buf, 8)[i]; }
+  if(what >= 2) { S.type[dst + i] = B.mol_type(buf)[i]; S.molid[dst + i] = molid; }
+}
+
+// deletion: the last molecule takes the place of the deleted one; MolID of the slot is kept (mc_utilities.h:163-189)
+__global__ void k_commit_delete(SlotArrays S, int dst, int src, int n)
+{
+  const int i = threadIdx.x;
+  if(i >= n || dst == src) return;
+  S.x[dst + i] = S.x[src + i]; S.y[dst + i] = S.y[src + i]; S.z[dst + i] = S.z[src + i];
+  S.fx[dst + i] = S.fx[src + i]; S.fy[dst + i] = S.fy[src + i]; S.fz[dst + i] = S.fz[src + i];
+  S.q[dst + i] = S.q[src + i]; S.scale[dst + i] = S.scale[src + i]; S.scoul[dst + i] = S.scoul[src + i]; S.type[dst + i] = S.type[src + i];
+}
+
+// buffer <- buffer / buffer <- slots copies (StoreNewLocation_Reinsertion mc_swap_moves.h:27-41 and Ewald gathers)
+__global__ void k_copy_buffer(MoveBufs B, int dst_buf, int src_buf, int n)
+{
+  const int i = threadIdx.x;
+  if(i >= n) return;
+  for(int k = 0; k < 9; k++) B.mol(dst_buf, k)[i] = B.mol(src_buf, k)[i];
+  B.mol_type(dst_buf)[i] = B.mol_type(src_buf)[i];
+}
+__global__ void k_load_buffer(DevParams P, MoveBufs B, int dst_buf, CompView C, long long start, int n, const double* pos3_override)
+{
+  const int i = threadIdx.x;
+  if(i >= n) return;
+  double x = C.x[start + i], y = C.y[start + i], z = C.z[start + i];
+  if(pos3_override) { x = pos3_override[3 * i]; y = pos3_override[3 * i + 1]; z = pos3_override[3 * i + 2]; }
+  double fx, fy, fz; to_frac(P, x, y, z, fx, fy, fz);
+  B.mol(dst_buf, 0)[i] = x; B.mol(dst_buf, 1)[i] = y; B.mol(dst_buf, 2)[i] = z; B.mol(dst_buf, 3)[i] = fx; B.mol(dst_buf, 4)[i] = fy; B.mol(dst_buf, 5)[i] = fz;
+  B.mol(dst_buf, 6)[i] = C.q[start + i]; B.mol(dst_buf, 7)[i] = C.scale[start + i]; B.mol(dst_buf, 8)[i] = C.scoul[start + i];
+  B.mol_type(dst_buf)[i] = C.type[start + i];
+}
+
+// Ewald gather: [old atoms | new atoms] -> pos3 / qeff in the layout k_ewald_delta reads (Initialize_Copy_Positions_Together,
+// Ewald_Energy_Functions.h:107-160).  Sources are molecule buffers (buf >= 0) .
+__global__ void k_ewald_gather(MoveBufs B, int old_buf, int nold, int new_buf, int nnew, double* pos3, double* qeff)
+{
+  const int i = threadIdx.x;
+  if(i >= nold + nnew) return;
+  const int buf = i < nold ? old_buf : new_buf;
+  const int j = i < nold ? i : i - nold;
+  pos3[3 * i] = B.mol(buf, 0)[j]; pos3[3 * i + 1] = B.mol(buf, 1)[j]; pos3[3 * i + 2] = B.mol(buf, 2)[j];
+  qeff[i] = B.mol(buf, 8)[j] * B.mol(buf, 6)[j];
+}

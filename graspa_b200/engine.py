@@ -27,7 +27,7 @@ DECLARED_SYMBOLS = [
     "gb_abi_version", "gb_last_error", "gb_engine_create", "gb_engine_destroy", "gb_device_info", "gb_synchronize", "gb_stream",
     "gb_upload_forcefield", "gb_upload_box", "gb_set_components", "gb_upload_atoms", "gb_download_atoms",
     "gb_upload_structure_factors", "gb_download_structure_factors", "gb_set_exclusion_constants", "gb_upload_random_pool",
-    "gb_set_cbmc", "gb_get_pseudo_atom_counts", "gb_cbmc_first_bead", "gb_cbmc_chain", "gb_cbmc_grown_positions",
+    "gb_set_cbmc", "gb_get_pseudo_atom_counts", "gb_cbmc_first_bead", "gb_cbmc_chain", "gb_cbmc_grown_positions", "gb_reinsertion_store",
     "gb_trial_energies", "gb_single_body_propose", "gb_single_body_delta", "gb_single_body_delta_explicit",
     "gb_ewald_delta", "gb_ewald_delta_identity_swap", "gb_ewald_delta_explicit", "gb_ewald_commit",
     "gb_tail_total", "gb_tail_difference", "gb_tail_identity_swap",
@@ -243,6 +243,89 @@ class Engine:
 
     def total_ewald(self, store=False):
         m = GbMoveEnergy(); self._chk(self.lib.gb_total_ewald(self.h, C.c_int32(int(store)), C.byref(m))); return m.as_dict()
+
+    # ------------------------------------------------------------ single-move path
+    def upload_random_pool(self, rnd3):
+        rnd3 = np.ascontiguousarray(rnd3, dtype=np.float64).reshape(-1, 3)
+        self._chk(self.lib.gb_upload_random_pool(self.h, _p(rnd3, f64p), C.c_int64(rnd3.shape[0])))
+
+    @staticmethod
+    def _cbmc_dict(r: GbCbmcResult, used):
+        return dict(rosenbluth=r.rosenbluth, stored_r=r.stored_r, energy=np.array(list(r.energy)), selected_pos=np.array(list(r.selected_pos)),
+                    success=bool(r.success), selected=int(r.selected), n_survivors=int(r.n_survivors), uniform_used=int(used))
+
+    def cbmc_first_bead(self, cbmc_type, comp, molecule, pool_offset, uniform, scale=(1.0, 1.0), stored_r=0.0,
+                        excl_comp=-1, excl_mol=-1, preset_pos=None):
+        sc = (C.c_double * 2)(*scale); r = GbCbmcResult(); used = C.c_int32()
+        pp = (C.c_double * 3)(*preset_pos) if preset_pos is not None else None
+        self._chk(self.lib.gb_cbmc_first_bead(self.h, C.c_int32(cbmc_type), C.c_int32(comp), C.c_int64(molecule), C.c_int64(pool_offset),
+                                              C.c_double(uniform), sc, C.c_double(stored_r), C.c_int32(excl_comp), C.c_int64(excl_mol),
+                                              pp, C.byref(r), C.byref(used)))
+        return self._cbmc_dict(r, used.value)
+
+    def cbmc_chain(self, cbmc_type, comp, molecule, pool_offset, uniform, excl_comp=-1, excl_mol=-1):
+        r = GbCbmcResult(); used = C.c_int32()
+        self._chk(self.lib.gb_cbmc_chain(self.h, C.c_int32(cbmc_type), C.c_int32(comp), C.c_int64(molecule), C.c_int64(pool_offset),
+                                         C.c_double(uniform), C.c_int32(excl_comp), C.c_int64(excl_mol), C.byref(r), C.byref(used)))
+        return self._cbmc_dict(r, used.value)
+
+    def cbmc_grown_positions(self, comp):
+        pos = np.zeros((int(self.system.molsize[comp]), 3))
+        self._chk(self.lib.gb_cbmc_grown_positions(self.h, C.c_int32(comp), _p(pos, f64p)))
+        return pos
+
+    def reinsertion_store(self, comp):
+        self._chk(self.lib.gb_reinsertion_store(self.h, C.c_int32(comp)))
+
+    def single_body_propose(self, move_type, comp, molecule, max_change, pool_offset, want_pos=True):
+        mc = (C.c_double * 3)(*max_change)
+        pos = np.zeros((int(self.system.molsize[comp]), 3)) if want_pos else None
+        self._chk(self.lib.gb_single_body_propose(self.h, C.c_int32(move_type), C.c_int32(comp), C.c_int64(molecule), mc, C.c_int64(pool_offset), _p(pos, f64p)))
+        return pos
+
+    def single_body_delta(self, comp, do_new=True, do_old=True):
+        m = GbMoveEnergy(); ov = C.c_int32()
+        self._chk(self.lib.gb_single_body_delta(self.h, C.c_int32(comp), C.c_int32(int(do_new)), C.c_int32(int(do_old)), C.byref(m), C.byref(ov)))
+        return m.as_dict(), int(ov.value)
+
+    def single_body_delta_explicit(self, comp, molid, old: TrialAtoms, new: TrialAtoms, do_new=True, do_old=True):
+        m = GbMoveEnergy(); ov = C.c_int32()
+        ref = new if new is not None else old
+        ty = np.ascontiguousarray(ref.type.astype(np.uint64))
+        self._chk(self.lib.gb_single_body_delta_explicit(self.h, C.c_int32(comp), C.c_int64(molid), C.c_int32(ref.n),
+                                                         _p(old.pos, f64p) if old is not None else None, _p(new.pos, f64p) if new is not None else None,
+                                                         _p(ref.scale, f64p), _p(ref.charge, f64p), _p(ref.scale_coul, f64p), _p(ty, u64p),
+                                                         C.c_int32(int(do_new)), C.c_int32(int(do_old)), C.byref(m), C.byref(ov)))
+        return m.as_dict(), int(ov.value)
+
+    def ewald_delta(self, comp, move_type, location=0, scale=(1.0, 1.0)):
+        sc = (C.c_double * 2)(*scale); out = np.zeros(2)
+        self._chk(self.lib.gb_ewald_delta(self.h, C.c_int32(comp), C.c_int32(move_type), C.c_int64(location), sc, _p(out, f64p)))
+        return out
+
+    def ewald_delta_identity_swap(self, old_comp, new_comp, update_location):
+        out = np.zeros(2)
+        self._chk(self.lib.gb_ewald_delta_identity_swap(self.h, C.c_int32(old_comp), C.c_int32(new_comp), C.c_int64(update_location), _p(out, f64p)))
+        return out
+
+    def accept_translation(self, comp):
+        self._chk(self.lib.gb_accept_translation(self.h, C.c_int32(comp)))
+
+    def accept_insertion(self, comp):
+        self._chk(self.lib.gb_accept_insertion(self.h, C.c_int32(comp)))
+
+    def accept_deletion(self, comp, molecule):
+        self._chk(self.lib.gb_accept_deletion(self.h, C.c_int32(comp), C.c_int64(molecule)))
+
+    def accept_reinsertion(self, comp, molecule):
+        self._chk(self.lib.gb_accept_reinsertion(self.h, C.c_int32(comp), C.c_int64(molecule)))
+
+    def append_molecule(self, comp, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        self._chk(self.lib.gb_append_molecule(self.h, C.c_int32(comp), _p(pos, f64p), None, None, None, None))
+
+    def number_of_molecules(self, comp):
+        n = C.c_int64(); self._chk(self.lib.gb_number_of_molecules(self.h, C.c_int32(comp), C.byref(n))); return n.value
 
     # ------------------------------------------------------------ batched Widom
     def widom_batch(self, comp, rnd, uni, fb_index=None, or_index=None, n_blocks=5, want_outputs=True):

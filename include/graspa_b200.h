@@ -170,6 +170,9 @@ int  gb_cbmc_chain(gb_engine* e, int32_t cbmc_type, int32_t component, int64_t m
 /* positions of the molecule grown by the last first_bead(+chain) pair: 3*molsize doubles (block-pocket checks,
  * mc_swap_utilities.h:46-80, read them) */
 int  gb_cbmc_grown_positions(gb_engine* e, int32_t component, double* pos);
+/* reinsertion: keep the molecule just grown (REINSERTION_INSERTION stages) aside while the old one is retraced
+ * (StoreNewLocation_Reinsertion<<<>>> into tempMolStorage, mc_swap_moves.h:27-41, move_struct.h:271) */
+int  gb_reinsertion_store(gb_engine* e, int32_t component);
 /* lower level: energies of caller-supplied trial atoms (n_trials groups of chainsize atoms), for drivers that
  * generate trials themselves.  out_energy[t*4 + {HGVDW,HGReal,GGVDW,GGReal}], out_flag[t]. */
 int  gb_trial_energies(gb_engine* e, int32_t n_trials, int32_t chainsize, const double* pos, const double* scale,

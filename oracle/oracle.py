@@ -170,6 +170,27 @@ def trial_energies(box, ff, sys_, ntrials, chainsize, trial: TrialAtoms, new_com
     return out, flag, counts
 
 
+def cbmc_finish(movetype, is_chain, energies, flags, beta, norm, uniform, vdw_real_bias=True, stored_in=0.0):
+    """Host_sum_Widom_HGGG_SEPARATE + CBMC_FirstBead_Finish / chain tail on per-trial energies (n,4) and flags (n,).
+    -> dict(success, selected (index among all trials), rosenbluth, stored_r, nsurv)"""
+    energies = np.asarray(energies, dtype=np.float64); flags = np.asarray(flags)
+    idx = [t for t in range(len(flags)) if not flags[t]]
+    tot = energies[idx, 0] + energies[idx, 2]
+    if vdw_real_bias:
+        tot = tot + energies[idx, 1] + energies[idx, 3]
+    rosen = np.ascontiguousarray(-beta * tot, dtype=np.float64)
+    if rosen.size == 0:
+        rosen = np.zeros(1)
+    sel = C.c_int(0); R = C.c_double(0.0); stored = C.c_double(0.0)
+    ok = lib().orc_cbmc_finish(C.c_int(movetype), C.c_int(int(is_chain)), _p(rosen, f64p), C.c_int(len(idx)), C.c_int(norm), C.c_double(uniform),
+                               C.c_double(stored_in), C.byref(stored), C.byref(sel), C.byref(R))
+    W = R.value
+    real_sel = idx[sel.value] if (ok and idx) else 0
+    if ok and idx and not vdw_real_bias:
+        W *= np.exp(-beta * (energies[real_sel, 1] + energies[real_sel, 3]))
+    return dict(success=bool(ok), selected=real_sel, rosenbluth=W, stored_r=stored.value, nsurv=len(idx))
+
+
 def ewald_delta(box, pos, charge, scale_coul, nold, nnew, same_sf, cross_sf, want_temp=True):
     pos = np.ascontiguousarray(pos, dtype=np.float64); charge = np.ascontiguousarray(charge, dtype=np.float64)
     scale_coul = np.ascontiguousarray(scale_coul, dtype=np.float64)

@@ -1,0 +1,256 @@
+"""Single-move path of the CUDA engine (CBMC stages, translation/rotation, Ewald deltas by move type, state commits)
+through the C ABI against the oracle, plus the reference's own self-check: running sum of accepted move deltas
+versus total energies recomputed from scratch (ENERGY DRIFT, fxn_main.h:467-468, test_examples.py:59-61)."""
+import numpy as np
+import pytest
+
+from graspa_b200.types import (TrialAtoms, CBMC_INSERTION, CBMC_DELETION, REINSERTION_INSERTION, REINSERTION_RETRACE,
+                               TRANSLATION, ROTATION, INSERTION, DELETION, REINSERTION)
+from tests.conftest import load_config
+
+pytestmark = pytest.mark.gpu
+ETOL = 1e-10
+
+
+def _grow(s, comp, nslots):
+    """same system with more allocated slots for one component (AdsorbateAllocateSpace)"""
+    from graspa_b200.types import System
+    alloc = s.alloc.copy(); alloc[comp] = nslots
+    off_o = s.offsets; off_n = np.concatenate([[0], np.cumsum(alloc)])
+    n = int(alloc.sum())
+    pos = np.zeros((n, 3)); q = np.zeros(n); ty = np.zeros(n, dtype=np.int64); mo = np.zeros(n, dtype=np.int64)
+    for c in range(s.ncomp):
+        k = int(s.alloc[c])
+        pos[off_n[c]:off_n[c] + k] = s.pos[off_o[c]:off_o[c] + k]; q[off_n[c]:off_n[c] + k] = s.charge[off_o[c]:off_o[c] + k]
+        ty[off_n[c]:off_n[c] + k] = s.type[off_o[c]:off_o[c] + k]; mo[off_n[c]:off_n[c] + k] = s.molid[off_o[c]:off_o[c] + k]
+    return System(s.nhost, s.natoms.copy(), s.molsize.copy(), pos, q, ty, mo, alloc=alloc)
+
+
+def _setup(gpu_engine_factory, name="B", grow=None):
+    box, ff, s, z = load_config(name)
+    if grow:
+        s = _grow(s, int(z["comp"]), grow)
+    eng = gpu_engine_factory(box, ff, s, float(z["beta"]), int(z["ntrials"]), int(z["norient"]))
+    if "sf_ads" in z:
+        eng.upload_structure_factors(z["sf_ads"], z["sf_fw"])
+        eng.set_exclusion_constants(int(z["comp"]), float(z["excl"][0]), float(z["excl"][1]))
+    return box, ff, s, z, eng
+
+
+def _close(a, b, scale=None, tol=ETOL):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    sc = scale if scale is not None else max(1e-3, float(np.abs(b).sum()))
+    return np.max(np.abs(a - b)) / sc < tol
+
+
+def test_cbmc_insertion_stages_vs_oracle(gpu_engine_factory, oracle):
+    box, ff, s, z, eng = _setup(gpu_engine_factory)
+    comp = 1; ms = 3; beta = float(z["beta"]); new_molid = int(s.natoms[comp]) // ms
+    rng = np.random.default_rng(21)
+    pool = rng.random((512, 3)); eng.upload_random_pool(pool)
+    for rep in range(6):
+        off = 40 * rep; u1, u2 = rng.random(2)
+        fb = eng.cbmc_first_bead(CBMC_INSERTION, comp, 0, off, u1)
+        tr = oracle.trial_positions(box, s, CBMC_INSERTION, comp, 0, 10, pool[off:off + 10])
+        e, f, _ = oracle.trial_energies(box, ff, s, 10, 1, tr, comp, new_molid)
+        ref = oracle.cbmc_finish(CBMC_INSERTION, False, e, f, beta, 10, u1)
+        assert fb["success"] == ref["success"] and fb["n_survivors"] == ref["nsurv"]
+        if not ref["success"]:
+            continue
+        assert fb["selected"] == ref["selected"] and fb["uniform_used"] == 1
+        assert abs(fb["rosenbluth"] - ref["rosenbluth"]) <= 1e-9 * ref["rosenbluth"]
+        assert _close(fb["energy"], e[ref["selected"]])
+        assert np.allclose(fb["selected_pos"], tr.pos[ref["selected"]], rtol=0, atol=1e-12)
+        ch = eng.cbmc_chain(CBMC_INSERTION, comp, 0, off + 10, u2)
+        t2 = oracle.trial_orientations(s, CBMC_INSERTION, comp, 1, ms - 1, 10, pool[off + 10:off + 20], tr.pos[ref["selected"]])
+        e2, f2, _ = oracle.trial_energies(box, ff, s, 10, ms - 1, t2, comp, new_molid)
+        ref2 = oracle.cbmc_finish(CBMC_INSERTION, True, e2, f2, beta, 10, u2)
+        assert ch["success"] == ref2["success"]
+        if not ref2["success"]:
+            continue
+        assert ch["selected"] == ref2["selected"]
+        assert abs(ch["rosenbluth"] - ref2["rosenbluth"]) <= 1e-9 * ref2["rosenbluth"]
+        assert _close(ch["energy"], e2[ref2["selected"]])
+        grown = eng.cbmc_grown_positions(comp)
+        so = ref2["selected"]
+        expect = np.concatenate([tr.pos[ref["selected"]][None, :], t2.pos[so * 2:so * 2 + 2]])
+        assert np.allclose(grown, expect, rtol=0, atol=1e-11)
+        # Ewald delta of the grown molecule (GPU_EwaldDifference_General, INSERTION)
+        o = int(s.offsets[comp]); q = s.charge[o:o + ms]
+        got = eng.ewald_delta(comp, INSERTION, location=ch["selected"])
+        ew, _, _ = oracle.ewald_delta(box, expect, q, np.ones(ms), 0, ms, z["sf_ads"], z["sf_fw"])
+        ew[0] -= float(z["excl"][0]) + float(z["excl"][1])
+        assert _close(got, ew, scale=max(1.0, float(np.abs(ew).max())))
+    eng.close()
+
+
+def test_cbmc_deletion_and_reinsertion_stages_vs_oracle(gpu_engine_factory, oracle):
+    box, ff, s, z, eng = _setup(gpu_engine_factory)
+    comp = 1; ms = 3; beta = float(z["beta"])
+    rng = np.random.default_rng(22)
+    pool = rng.random((512, 3)); eng.upload_random_pool(pool)
+    o = int(s.offsets[comp])
+    for mol in (0, 7, 19):
+        off = 30 * mol % 400
+        fb = eng.cbmc_first_bead(CBMC_DELETION, comp, mol, off, 0.5)
+        tr = oracle.trial_positions(box, s, CBMC_DELETION, comp, mol * ms, 10, pool[off:off + 10])
+        assert np.allclose(tr.pos[0], s.pos[o + mol * ms])
+        e, f, _ = oracle.trial_energies(box, ff, s, 10, 1, tr, comp, mol)
+        ref = oracle.cbmc_finish(CBMC_DELETION, False, e, f, beta, 10, 0.5)
+        assert fb["success"] and fb["selected"] == 0 and fb["uniform_used"] == 0
+        assert abs(fb["rosenbluth"] - ref["rosenbluth"]) <= 1e-9 * ref["rosenbluth"]
+        ch = eng.cbmc_chain(CBMC_DELETION, comp, mol, off + 10, 0.5)
+        t2 = oracle.trial_orientations(s, CBMC_DELETION, comp, mol * ms + 1, ms - 1, 10, pool[off + 10:off + 20], tr.pos[0])
+        assert np.allclose(t2.pos[:2], s.pos[o + mol * ms + 1:o + mol * ms + 3])
+        e2, f2, _ = oracle.trial_energies(box, ff, s, 10, ms - 1, t2, comp, mol)
+        ref2 = oracle.cbmc_finish(CBMC_DELETION, True, e2, f2, beta, 10, 0.5)
+        assert ch["selected"] == 0 and abs(ch["rosenbluth"] - ref2["rosenbluth"]) <= 1e-9 * ref2["rosenbluth"]
+        assert _close(ch["energy"], e2[0])
+        got = eng.ewald_delta(comp, DELETION, location=mol * ms)
+        q = s.charge[o:o + ms]
+        ew, _, _ = oracle.ewald_delta(box, s.pos[o + mol * ms:o + mol * ms + ms], q, np.ones(ms), ms, 0, z["sf_ads"], z["sf_fw"])
+        ew[0] -= (float(z["excl"][0]) + float(z["excl"][1])) * -1.0
+        assert _close(got, ew, scale=max(1.0, float(np.abs(ew).max())))
+    # reinsertion: insertion leg with StoredR, store, retrace leg with 1 trial + StoredR, Ewald(REINSERTION)
+    mol = 5; off = 200; u1, u2 = 0.37, 0.81
+    fb = eng.cbmc_first_bead(REINSERTION_INSERTION, comp, mol, off, u1)
+    tr = oracle.trial_positions(box, s, REINSERTION_INSERTION, comp, mol * ms, 10, pool[off:off + 10])
+    e, f, _ = oracle.trial_energies(box, ff, s, 10, 1, tr, comp, mol)
+    ref = oracle.cbmc_finish(REINSERTION_INSERTION, False, e, f, beta, 10, u1)
+    assert fb["success"] == ref["success"]
+    if ref["success"]:
+        assert fb["selected"] == ref["selected"]
+        assert abs(fb["stored_r"] - ref["stored_r"]) <= 1e-9 * max(abs(ref["stored_r"]), 1e-300)
+        ch = eng.cbmc_chain(REINSERTION_INSERTION, comp, mol, off + 10, u2)
+        if ch["success"]:
+            new_pos = eng.cbmc_grown_positions(comp)
+            eng.reinsertion_store(comp)
+            rb = eng.cbmc_first_bead(REINSERTION_RETRACE, comp, mol, off + 20, 0.5, stored_r=fb["stored_r"])
+            tr_r = oracle.trial_positions(box, s, REINSERTION_RETRACE, comp, mol * ms, 1, pool[off + 20:off + 21])
+            er, fr, _ = oracle.trial_energies(box, ff, s, 1, 1, tr_r, comp, mol)
+            ref_r = oracle.cbmc_finish(REINSERTION_RETRACE, False, er, fr, beta, 10, 0.5, stored_in=ref["stored_r"])
+            assert abs(rb["rosenbluth"] - ref_r["rosenbluth"]) <= 1e-9 * ref_r["rosenbluth"]
+            eng.cbmc_chain(REINSERTION_RETRACE, comp, mol, off + 21, 0.5)
+            got = eng.ewald_delta(comp, REINSERTION, location=mol * ms)
+            q = s.charge[o:o + ms]
+            pos = np.concatenate([s.pos[o + mol * ms:o + mol * ms + ms], new_pos])
+            ew, _, _ = oracle.ewald_delta(box, pos, np.concatenate([q, q]), np.ones(2 * ms), ms, ms, z["sf_ads"], z["sf_fw"])
+            assert _close(got, ew, scale=max(1.0, float(np.abs(ew).max())))
+    eng.close()
+
+
+def _rot(p, theta, axis):
+    c, s_ = np.cos(theta), np.sin(theta); w = 1.0 - c; ax, ay, az = axis
+    R = np.array([[ax * ax * w + c, ax * ay * w + az * s_, ax * az * w - ay * s_],
+                  [ax * ay * w - az * s_, ay * ay * w + c, ay * az * w + ax * s_],
+                  [ax * az * w + ay * s_, ay * az * w - ax * s_, az * az * w + c]])
+    return R @ p
+
+
+def test_single_body_translation_rotation_vs_oracle(gpu_engine_factory, oracle):
+    box, ff, s, z, eng = _setup(gpu_engine_factory)
+    comp = 1; ms = 3; o = int(s.offsets[comp])
+    rng = np.random.default_rng(23)
+    pool = rng.random((64, 3)); eng.upload_random_pool(pool)
+    for k, (mt, mol) in enumerate([(TRANSLATION, 3), (ROTATION, 11), (TRANSLATION, 19), (ROTATION, 0)]):
+        maxc = np.array([0.8, 0.6, 0.7]) if mt == TRANSLATION else np.array([0.5, 0.4, 0.3])
+        newp = eng.single_body_propose(mt, comp, mol, maxc, k)
+        oldp = s.pos[o + mol * ms:o + mol * ms + ms]
+        r = pool[k]
+        if mt == TRANSLATION:
+            expect = oldp + maxc * 2.0 * (r - 0.5)
+        else:
+            ang = maxc * 2.0 * (r - 0.5)
+            expect = np.array([_rot(_rot(_rot(p - oldp[0], ang[0], (1, 0, 0)), ang[1], (0, 1, 0)), ang[2], (0, 0, 1)) + oldp[0] for p in oldp])
+        assert np.allclose(newp, expect, rtol=0, atol=1e-11)
+        d, ov = eng.single_body_delta(comp)
+        q = s.charge[o:o + ms]; ty = s.type[o:o + ms]
+        ref, rov = oracle.single_body_delta(box, ff, s, comp, mol, TrialAtoms(oldp, q, ty), TrialAtoms(newp, q, ty))
+        got = np.array([d["HHVDW"], d["HHReal"], d["HGVDW"], d["HGReal"], d["GGVDW"], d["GGReal"]])
+        assert ov == rov
+        # tolerance against the magnitude of the summed terms (new and old each ~1e3-1e4 K), SURVEY section 7 "tolerance vs cancellation"
+        assert np.max(np.abs(got - ref)) < ETOL * 1e4
+        ew = eng.ewald_delta(comp, mt)
+        ewr, _, _ = oracle.ewald_delta(box, np.concatenate([oldp, newp]), np.concatenate([q, q]), np.ones(2 * ms), ms, ms, z["sf_ads"], z["sf_fw"])
+        assert _close(ew, ewr, scale=max(1.0, float(np.abs(ewr).max())))
+        # explicit-atoms entry point gives the same numbers
+        d2, _ = eng.single_body_delta_explicit(comp, mol, TrialAtoms(oldp, q, ty), TrialAtoms(newp, q, ty))
+        assert all(abs(d2[k2] - d[k2]) <= 1e-9 * max(1.0, abs(d[k2])) for k2 in d)
+    eng.close()
+
+
+def _total(eng):
+    v = eng.total_vdw_real(); w = eng.total_ewald(store=False)
+    return (v["HHVDW"] + v["HGVDW"] + v["GGVDW"] + v["HHReal"] + v["HGReal"] + v["GGReal"] + w["GGEwaldE"] + w["HGEwaldE"] + eng.tail_total())
+
+
+def test_energy_drift_over_a_short_gcmc_run(gpu_engine_factory):
+    """insert / delete / translate / rotate / reinsert with Metropolis acceptance on the engine's own deltas;
+    the running sum of accepted deltas must equal the from-scratch total-energy difference (drift < 1e-3 in the
+    reference's criterion; here 1e-7 relative to the energy scale)"""
+    box, ff, s, z, eng = _setup(gpu_engine_factory, grow=600)
+    comp = 1; ms = 3; beta = float(z["beta"])
+    rng = np.random.default_rng(24)
+    pool = rng.random((20000, 3)); eng.upload_random_pool(pool)
+    E0 = _total(eng)
+    run = 0.0; off = 0; acc = {k: 0 for k in ("ins", "del", "tr", "rot", "rei")}
+    for step in range(160):
+        nmol = eng.number_of_molecules(comp)
+        kind = rng.choice(["ins", "del", "tr", "rot", "rei"])
+        if kind in ("del", "tr", "rot", "rei") and nmol == 0:
+            continue
+        mol = int(rng.integers(0, max(nmol, 1)))
+        if kind == "ins":
+            fb = eng.cbmc_first_bead(CBMC_INSERTION, comp, 0, off, rng.random()); off += 10
+            if not fb["success"]:
+                continue
+            ch = eng.cbmc_chain(CBMC_INSERTION, comp, 0, off, rng.random()); off += 10
+            if not ch["success"]:
+                continue
+            ew = eng.ewald_delta(comp, INSERTION, location=ch["selected"])
+            dE = fb["energy"].sum() + ch["energy"].sum() + ew.sum() + eng.tail_difference(comp, INSERTION)
+            W = fb["rosenbluth"] * ch["rosenbluth"] * np.exp(-beta * ew.sum())
+            if rng.random() < min(1.0, 0.02 * W):
+                eng.accept_insertion(comp); run += dE; acc["ins"] += 1
+        elif kind == "del":
+            fb = eng.cbmc_first_bead(CBMC_DELETION, comp, mol, off, 0.5); off += 10
+            ch = eng.cbmc_chain(CBMC_DELETION, comp, mol, off, 0.5); off += 10
+            ew = eng.ewald_delta(comp, DELETION, location=mol * ms)
+            dE = -(fb["energy"].sum() + ch["energy"].sum()) + ew.sum() + eng.tail_difference(comp, DELETION)
+            if rng.random() < 0.3:
+                eng.accept_deletion(comp, mol); run += dE; acc["del"] += 1
+        elif kind in ("tr", "rot"):
+            mt = TRANSLATION if kind == "tr" else ROTATION
+            eng.single_body_propose(mt, comp, mol, (0.5, 0.5, 0.5), off, want_pos=False); off += 3
+            d, ov = eng.single_body_delta(comp)
+            if ov:
+                continue
+            ew = eng.ewald_delta(comp, mt)
+            dE = sum(d[k] for k in ("HHVDW", "HGVDW", "GGVDW", "HHReal", "HGReal", "GGReal")) + ew.sum()
+            if rng.random() < np.exp(min(0.0, -beta * dE)):
+                eng.accept_translation(comp); run += dE; acc[kind] += 1
+        else:
+            fb = eng.cbmc_first_bead(REINSERTION_INSERTION, comp, mol, off, rng.random()); off += 10
+            if not fb["success"]:
+                continue
+            ch = eng.cbmc_chain(REINSERTION_INSERTION, comp, mol, off, rng.random()); off += 10
+            if not ch["success"]:
+                continue
+            eng.reinsertion_store(comp)
+            rb = eng.cbmc_first_bead(REINSERTION_RETRACE, comp, mol, off, 0.5, stored_r=fb["stored_r"]); off += 1
+            rc = eng.cbmc_chain(REINSERTION_RETRACE, comp, mol, off, 0.5); off += 10
+            ew = eng.ewald_delta(comp, REINSERTION, location=mol * ms)
+            dE = (fb["energy"].sum() + ch["energy"].sum()) - (rb["energy"].sum() + rc["energy"].sum()) + ew.sum()
+            Wn = fb["rosenbluth"] * ch["rosenbluth"] * np.exp(-beta * ew.sum()); Wo = rb["rosenbluth"] * rc["rosenbluth"]
+            if Wo > 0 and rng.random() < min(1.0, Wn / Wo):
+                eng.accept_reinsertion(comp, mol); run += dE; acc["rei"] += 1
+    E1 = _total(eng)
+    assert sum(acc.values()) >= 20, acc
+    scale = max(1.0, abs(E0), abs(E1))
+    assert abs((E1 - E0) - run) < 1e-7 * scale, (E1 - E0, run, acc)
+    # the stored structure factors followed the accepted moves: recomputing them changes nothing
+    sa, _, _ = eng.download_structure_factors()
+    eng.total_ewald(store=True)
+    sb, _, _ = eng.download_structure_factors()
+    assert np.max(np.abs(sa - sb)) < 1e-8
+    eng.close()
