@@ -856,6 +856,66 @@ int gb_total_ewald(gb_engine* e, int32_t store, gb_move_energy* out)
 }
 
 // ---------------------------------------------------------------------------------------------- batched Widom
+// stage A launch shared by gb_widom_batch and gb_widom_first_bead_success
+static int widom_stage_a(gb_engine* e, int comp, long long n, const double* d_pool, const long long* d_fb, const long long* d_or, const double* d_uni,
+                         int first_bead_only)
+{
+  int rc;
+  const Comp& C = e->comps[comp];
+  const int ms = C.molsize, cs = ms - 1;
+  const int rec_stride = 5 + 3 * ms;
+  CUDA_TRY(e->d_rec.reserve((size_t) n * rec_stride)); CUDA_TRY(e->d_stage.reserve((size_t) n));
+  const int warpsA = 16;
+  const size_t per_warpA = (sizeof(TrialGroup) + sizeof(WarpQueue) + (size_t) e->norient * (cs > 0 ? cs : 1) * 6 * sizeof(double) + 15) / 16 * 16;
+  bool use_pack = false;
+  const bool stage_ff = e->ntypes <= 24;
+  const size_t ff_bytes = stage_ff ? (size_t) e->ntypes * e->ntypes * sizeof(double4) : 0;
+  rc = ensure_pack(e, use_pack, warpsA * per_warpA + GBK_ERFC_BYTES + ff_bytes + sizeof(SegList) + 128); if(rc) return rc;
+  WidomA A;
+  A.pool3 = d_pool; A.fb_index = d_fb; A.or_index = d_or; A.uni = d_uni; A.n = n;
+  A.ntrials = e->ntrials; A.norient = e->norient; A.ms = ms; A.comp = comp; A.new_molid = C.natoms / ms;
+  A.tx = e->dx.p + C.offset; A.ty = e->dy.p + C.offset; A.tz = e->dz.p + C.offset; A.tq = e->dq.p + C.offset;
+  A.tscoul = e->dscoul.p + C.offset; A.ttype = e->dtype.p + C.offset;
+  A.pack = e->d_pack.p; A.npad = e->pack_npad; A.use_pack = use_pack ? 1 : 0; A.stage_ff = stage_ff ? 1 : 0;
+  A.first_bead_only = first_bead_only;
+  A.rec = e->d_rec.p; A.stage = e->d_stage.p;
+  SegList L = seg_list(e, 0);
+  if(use_pack)
+  {
+    int acc = 0;
+    for(int s = 0; s < L.nseg; s++) if(L.comp[s] < e->nhost) { L.staged[s] = 1; L.start[s] = acc; acc += L.count[s]; }
+  }
+  const size_t headA = (GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD + ff_bytes + sizeof(SegList) + 15) / 16 * 16;
+  const size_t smemA = headA + (use_pack ? ((size_t) e->pack_npad * 36 + 15) / 16 * 16 : 0) + warpsA * per_warpA;
+  if(smemA > e->smem_optin) return fail(GB_ERR_ARG, "Widom stage A shared memory exceeds the device limit");
+  const int gridA = (int) std::min<long long>((n + warpsA - 1) / warpsA, e->prop.multiProcessorCount);
+  Timer tm(e, 0);
+  if(e->P.cell_mode == 2)      k_widom_pair<2><<<gridA, warpsA * 32, smemA, e->stream>>>(e->P, sys_view(e), L, A);
+  else if(e->P.cell_mode == 1) k_widom_pair<1><<<gridA, warpsA * 32, smemA, e->stream>>>(e->P, sys_view(e), L, A);
+  else                         k_widom_pair<0><<<gridA, warpsA * 32, smemA, e->stream>>>(e->P, sys_view(e), L, A);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  tm.stop(1);
+  return GB_OK;
+}
+
+int gb_widom_first_bead_success(gb_engine* e, int32_t comp, int64_t n, const double* pool3, int64_t n_pool, const int64_t* fb_index, int32_t* code)
+{
+  int rc = ready(e); if(rc) return rc;
+  if(n <= 0 || !pool3 || !fb_index || !code) return fail(GB_ERR_ARG, "bad arguments");
+  if(comp < e->nhost || comp >= e->ncomp) return fail(GB_ERR_ARG, "Widom component must be an adsorbate component");
+  if(!e->have_cbmc) return fail(GB_ERR_STATE, "gb_set_cbmc has not been called");
+  CUDA_TRY(e->d_pool.reserve((size_t) n_pool * 3));
+  CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, pool3, (size_t) n_pool * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  e->n_pool = n_pool;
+  CUDA_TRY(e->d_idx0.reserve((size_t) n));
+  CUDA_TRY(cudaMemcpyAsync(e->d_idx0.p, fb_index, (size_t) n * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+  rc = widom_stage_a(e, comp, n, e->d_pool.p, e->d_idx0.p, e->d_idx0.p, nullptr, 1); if(rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(code, e->d_stage.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return GB_OK;
+}
+
 int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs* in, double* out8, int32_t* stage,
                    int32_t outputs_on_device, double* sums)
 {
@@ -894,40 +954,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   if(!in->fb_index && in->n_pool < n * per) return fail(GB_ERR_ARG, "random pool smaller than n*(trial positions+orientations)");
 
   // ---- stage A
-  const int rec_stride = 5 + 3 * ms;
-  CUDA_TRY(e->d_rec.reserve((size_t) n * rec_stride)); CUDA_TRY(e->d_stage.reserve((size_t) n));
-  const int warpsA = 16;
-  const size_t per_warpA = (sizeof(TrialGroup) + sizeof(WarpQueue) + (size_t) e->norient * (cs > 0 ? cs : 1) * 6 * sizeof(double) + 15) / 16 * 16;
-  bool use_pack = false;
-  const bool stage_ff = e->ntypes <= 24;
-  const size_t ff_bytes = stage_ff ? (size_t) e->ntypes * e->ntypes * sizeof(double4) : 0;
-  rc = ensure_pack(e, use_pack, warpsA * per_warpA + GBK_ERFC_BYTES + ff_bytes + sizeof(SegList) + 128); if(rc) return rc;
-  WidomA A;
-  A.pool3 = d_pool; A.fb_index = d_fb; A.or_index = d_or; A.uni = d_uni; A.n = n;
-  A.ntrials = e->ntrials; A.norient = e->norient; A.ms = ms; A.comp = comp; A.new_molid = C.natoms / ms;
-  A.tx = e->dx.p + C.offset; A.ty = e->dy.p + C.offset; A.tz = e->dz.p + C.offset; A.tq = e->dq.p + C.offset;
-  A.tscoul = e->dscoul.p + C.offset; A.ttype = e->dtype.p + C.offset;
-  A.pack = e->d_pack.p; A.npad = e->pack_npad; A.use_pack = use_pack ? 1 : 0; A.stage_ff = stage_ff ? 1 : 0;
-  A.rec = e->d_rec.p; A.stage = e->d_stage.p;
-  SegList L = seg_list(e, 0);
-  if(use_pack)
-  {
-    int acc = 0;
-    for(int s = 0; s < L.nseg; s++) if(L.comp[s] < e->nhost) { L.staged[s] = 1; L.start[s] = acc; acc += L.count[s]; }
-  }
-  const size_t headA = (GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD + ff_bytes + sizeof(SegList) + 15) / 16 * 16;
-  const size_t smemA = headA + (use_pack ? ((size_t) e->pack_npad * 36 + 15) / 16 * 16 : 0) + warpsA * per_warpA;
-  if(smemA > e->smem_optin) return fail(GB_ERR_ARG, "Widom stage A shared memory exceeds the device limit");
-  const int gridA = (int) std::min<long long>((n + warpsA - 1) / warpsA, e->prop.multiProcessorCount);
-  {
-    Timer tm(e, 0);
-    if(e->P.cell_mode == 2)      k_widom_pair<2><<<gridA, warpsA * 32, smemA, e->stream>>>(e->P, sys_view(e), L, A);
-    else if(e->P.cell_mode == 1) k_widom_pair<1><<<gridA, warpsA * 32, smemA, e->stream>>>(e->P, sys_view(e), L, A);
-    else                         k_widom_pair<0><<<gridA, warpsA * 32, smemA, e->stream>>>(e->P, sys_view(e), L, A);
-    e->launches++;
-    CUDA_TRY(cudaGetLastError());
-    tm.stop(1);
-  }
+  rc = widom_stage_a(e, comp, n, d_pool, d_fb, d_or, d_uni, 0); if(rc) return rc;
   // ---- tail (constant over the batch)
   std::vector<int> dc = species_counts(e, comp);
   rc = tail_device(e, &dc, e->d_result.p + 8); if(rc) return rc;

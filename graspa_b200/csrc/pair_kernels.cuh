@@ -125,6 +125,7 @@ struct WidomA
   const double* __restrict__ tx; const double* __restrict__ ty; const double* __restrict__ tz;
   const double* __restrict__ tq; const double* __restrict__ tscoul; const int* __restrict__ ttype;
   const double* __restrict__ pack; int npad; int use_pack; int stage_ff;
+  int first_bead_only;                         // 1: write the first-bead success code into stage[] and stop there
   double* rec;        // per insertion: [W12, HGv, HGr, GGv, GGr, x0,y0,z0, x1,...]  stride 5 + 3*ms
   int* stage;         // 0 ok, 1 first bead failed, 2 chain failed
 };
@@ -264,7 +265,7 @@ k_widom_pair(DevParams P, SysView Sg, SegList Lin, WidomA A)
       __syncwarp();
     }
     double tot = my_e[0] + my_e[2]; if(P.vdw_real_bias) tot += my_e[1] + my_e[3];
-    RosenResult r1 = rosenbluth_warp(-P.beta * tot, !my_flag, A.ntrials, A.uni[2 * ins], true);
+    RosenResult r1 = rosenbluth_warp(-P.beta * tot, !my_flag, A.ntrials, A.uni ? A.uni[2 * ins] : 0.5, true);
     double W = 0.0; int ok = r1.success && !(r1.R < 1e-150);
     const int sfb = r1.sel_lane;
     double efb[4];
@@ -275,6 +276,12 @@ k_widom_pair(DevParams P, SysView Sg, SegList Lin, WidomA A)
       W = r1.R / (double) A.ntrials;
       if(!P.vdw_real_bias) W *= exp(-P.beta * (efb[1] + efb[3]));
       if(W <= 1e-150) ok = 0;
+    }
+    if(A.first_bead_only)
+    {
+      // code for the host's random-stream walk: 1 success, 0 failed with survivors, 2 no survivor
+      if(lane == 0) A.stage[ins] = ok ? 1 : (r1.nsurv > 0 ? 0 : 2);
+      continue;
     }
     double* rec = A.rec + (size_t) ins * rec_stride;
     if(!ok) { if(lane == 0) { A.stage[ins] = 1; rec[0] = 0.0; } continue; }
@@ -327,7 +334,7 @@ k_widom_pair(DevParams P, SysView Sg, SegList Lin, WidomA A)
         W *= W2;
         if(W <= 1e-150) ok2 = 0;
       }
-      if(!ok2) { if(lane == 0) { A.stage[ins] = 2; rec[0] = 0.0; } continue; }
+      if(!ok2) { if(lane == 0) { A.stage[ins] = (r2.nsurv > 0) ? 2 : 3; rec[0] = 0.0; } continue; }
     }
     if(lane == 0)
     {

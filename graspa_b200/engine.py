@@ -32,7 +32,7 @@ DECLARED_SYMBOLS = [
     "gb_ewald_delta", "gb_ewald_delta_identity_swap", "gb_ewald_delta_explicit", "gb_ewald_commit",
     "gb_tail_total", "gb_tail_difference", "gb_tail_identity_swap",
     "gb_accept_translation", "gb_accept_insertion", "gb_accept_deletion", "gb_accept_reinsertion", "gb_append_molecule",
-    "gb_number_of_molecules", "gb_total_vdw_real", "gb_total_ewald", "gb_widom_batch",
+    "gb_number_of_molecules", "gb_total_vdw_real", "gb_total_ewald", "gb_widom_batch", "gb_widom_first_bead_success",
     "gb_launch_count", "gb_timing_enable", "gb_timing_read", "gb_measure_fp64_peak",
 ]
 

@@ -1,0 +1,343 @@
+// graspa_b200 host layer -- reader of a gRASPA / RASPA-2 style input deck (the reference's input surface, kept as is):
+// simulation.input, force_field_mixing_rules.def, force_field.def, pseudo_atoms.def, <molecule>.def, <framework>.cif.
+// Each routine names the reference parser it mirrors (read_data.cpp); numbers that reach the engine are computed with
+// the reference's expressions so that energies agree to round-off.
+//
+// Supported subset (what SURVEY section 8's configs A, B, D, E need): one rigid framework component from a P1 CIF,
+// rigid adsorbates, Lennard-Jones + Lorentz-Berthelot mixing, shifted/truncated, tail corrections incl. the
+// "rules to overwrite" of force_field.def, Ewald with the RASPA-2 heuristic or the LAMMPS-style explicit set-up.
+// Not read (the engine has no use for them yet): separated framework components, block pockets, CBCF/TMMC keywords.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace deck {
+
+inline std::vector<std::string> terms(const std::string& line)      // Split_Tab_Space, read_data.cpp:85-94 (empty tokens dropped)
+{
+  std::vector<std::string> t; std::string cur;
+  for(char c : line)
+  {
+    if(c == ' ' || c == '\t' || c == '\r' || c == ',') { if(!cur.empty()) { t.push_back(cur); cur.clear(); } }
+    else cur.push_back(c);
+  }
+  if(!cur.empty()) t.push_back(cur);
+  return t;
+}
+inline bool ieq(const std::string& a, const std::string& b)
+{
+  if(a.size() != b.size()) return false;
+  for(size_t i = 0; i < a.size(); i++) if(std::tolower((unsigned char) a[i]) != std::tolower((unsigned char) b[i])) return false;
+  return true;
+}
+inline std::vector<std::string> read_lines(const std::string& path)
+{
+  std::ifstream f(path);
+  if(!f) throw std::runtime_error("cannot open " + path);
+  std::vector<std::string> L; std::string s;
+  while(std::getline(f, s)) L.push_back(s);
+  return L;
+}
+
+struct Component
+{
+  std::string name;
+  double ideal_rosenbluth = 1.0, fugacity_coeff = 1.0, mol_fraction = 1.0;
+  double p_translation = 0, p_rotation = 0, p_widom = 0, p_reinsertion = 0, p_identity = 0, p_swap = 0;   // raw inputs
+  int create_molecules = 0;
+  bool use_pr_eos = false;
+  // molecule definition
+  std::vector<double> pos;      // 3*ms
+  std::vector<int> type; std::vector<double> charge;
+  double tc = 0, pc = 0, acentric = 0, mass = 0;
+  int ms() const { return (int) type.size(); }
+};
+
+struct Deck
+{
+  // simulation.input
+  long init_cycles = 0, equil_cycles = 0, prod_cycles = 0;
+  bool use_max_step = false; long max_step_per_cycle = 1;
+  int random_seed = 0;
+  int n_trial_positions = 8, n_trial_orientations = 8;            // WidomStruct defaults, data_struct.h:1275-1276
+  long adsorbate_allocate = 10240;
+  std::string framework_name; int unitcells[3] = {1, 1, 1};
+  bool use_cif_charges = false, no_charges = true;
+  double temperature = 300.0, pressure_pa = 0.0;
+  double overlap = 1e5, cutoff_vdw = 12.0, cutoff_coul = 12.0, ewald_precision = 1e-6;
+  bool lammps_ewald = false; double lammps_alpha = 0.0; int lammps_kmax[3] = {0, 0, 0};
+  long movies_every = 5000, print_every = 5000;
+  std::vector<Component> comps;                                     // adsorbates, in input order
+  // force field
+  std::vector<std::string> names; std::vector<double> eps_in, sig_in, mass, pseudo_charge;
+  bool shifted = false, tail = false;
+  std::vector<double> eps, sigma, shift, tail_energy; std::vector<int> use_tail;   // n*n
+  // framework
+  double cell[9] = {0}, inv[9] = {0}, volume = 0;
+  std::vector<double> fpos; std::vector<int> ftype; std::vector<double> fcharge;  // supercell atoms
+  double framework_mass = 0.0;
+  // Ewald
+  double alpha = 0.0, prefactor = 138935.483496, recip_cutoff = 0.0; int kmax[3] = {0, 0, 0};
+  // derived
+  double beta = 0.0, pressure = 0.0;
+  int ntypes() const { return (int) names.size(); }
+};
+
+inline int type_of(const Deck& d, const std::string& name)
+{
+  for(size_t j = 0; j < d.names.size(); j++) if(d.names[j] == name) return (int) j;
+  throw std::runtime_error("Atom type not found in pseudo atoms definitions: " + name);
+}
+
+// VDW(), maths.cuh:477-492, for the shift value (Get_Shifted_Value)
+inline double lj_energy(double eps, double sig, double rr)
+{
+  const double arg1 = 4.0 * eps, arg2 = sig * sig;
+  const double temp = rr / arg2, temp3 = temp * temp * temp, rri3 = 1.0 / (temp3 + 0.0);
+  return arg1 * (rri3 * (rri3 - 1.0));
+}
+// GetTailCorrectionValue, read_data.cpp:833-846
+inline double tail_value(double eps, double sig, double cutsq)
+{
+  const double arg2 = sig * sig * sig, rr = std::sqrt(cutsq);
+  const double term1 = std::pow(arg2, 4) / (9.0 * std::pow(rr, 9)), term2 = std::pow(arg2, 2) / (3.0 * std::pow(rr, 3));
+  return 16.0 * 3.14159265358979323846 / 2.0 * eps * (term1 - term2);
+}
+
+inline void read_simulation_input(Deck& d, const std::string& dir)
+{
+  auto L = read_lines(dir + "/simulation.input");
+  Component* cur = nullptr;
+  for(auto& line : L)
+  {
+    auto t = terms(line);
+    if(t.empty() || t[0][0] == '#') continue;
+    auto has = [&](const char* k) { return line.find(k) != std::string::npos; };      // the reference matches by substring
+    if(t[0] == "Component" && t.size() >= 4) { d.comps.emplace_back(); cur = &d.comps.back(); cur->name = t[3]; continue; }
+    if(cur)
+    {
+      if(has("IdealGasRosenbluthWeight")) cur->ideal_rosenbluth = std::stod(t[1]);
+      else if(has("TranslationProbability")) cur->p_translation = std::stod(t[1]);
+      else if(has("RotationProbability")) cur->p_rotation = std::stod(t[1]);
+      else if(has("WidomProbability")) cur->p_widom = std::stod(t[1]);
+      else if(has("ReinsertionProbability")) cur->p_reinsertion = std::stod(t[1]);
+      else if(has("IdentityChangeProbability")) cur->p_identity = std::stod(t[1]);
+      else if(has("SwapProbability")) cur->p_swap = std::stod(t[1]);
+      else if(has("FugacityCoefficient")) { if(ieq(t[1], "PR-EOS")) { cur->use_pr_eos = true; cur->fugacity_coeff = -1.0; } else cur->fugacity_coeff = std::stod(t[1]); }
+      else if(has("MolFraction")) cur->mol_fraction = std::stod(t[1]);
+      else if(has("CreateNumberOfMolecules")) cur->create_molecules = std::stoi(t[1]);
+      continue;
+    }
+    if(has("NumberOfInitializationCycles")) d.init_cycles = std::stol(t[1]);
+    else if(has("NumberOfEquilibrationCycles")) d.equil_cycles = std::stol(t[1]);
+    else if(has("NumberOfProductionCycles")) d.prod_cycles = std::stol(t[1]);
+    else if(has("UseMaxStep")) d.use_max_step = ieq(t[1], "yes");
+    else if(has("MaxStepPerCycle")) d.max_step_per_cycle = std::stol(t[1]);
+    else if(has("RandomSeed")) d.random_seed = std::stoi(t[1]);
+    else if(has("NumberOfTrialPositions")) d.n_trial_positions = std::stoi(t[1]);
+    else if(has("NumberOfTrialOrientations")) d.n_trial_orientations = std::stoi(t[1]);
+    else if(has("AdsorbateAllocateSpace")) d.adsorbate_allocate = std::stol(t[1]);
+    else if(has("FrameworkName")) d.framework_name = t[1];
+    else if(has("UnitCells") && t.size() >= 5) { d.unitcells[0] = std::stoi(t[2]); d.unitcells[1] = std::stoi(t[3]); d.unitcells[2] = std::stoi(t[4]); }
+    else if(has("UseChargesFromCIFFile")) d.use_cif_charges = ieq(t[1], "yes");
+    else if(has("ChargeMethod")) d.no_charges = !ieq(t[1], "Ewald");
+    else if(has("Temperature")) d.temperature = std::stod(t[1]);
+    else if(has("Pressure")) d.pressure_pa = std::stod(t[1]);
+    else if(has("OverlapCriteria")) d.overlap = std::stod(t[1]);
+    else if(has("CutOffVDW")) d.cutoff_vdw = std::stod(t[1]);
+    else if(has("CutOffCoulomb")) d.cutoff_coul = std::stod(t[1]);
+    else if(has("EwaldPrecision")) d.ewald_precision = std::stod(t[1]);
+    else if(has("Ewald_UseLAMMPS_Setup")) d.lammps_ewald = ieq(t[1], "yes");
+    else if(has("Ewald_Alpha")) d.lammps_alpha = std::stod(t[1]);
+    else if(has("Ewald_kvectors") && t.size() >= 4) { for(int k = 0; k < 3; k++) d.lammps_kmax[k] = std::stoi(t[1 + k]); }
+  }
+}
+
+// ForceFieldParser :772-834, PseudoAtomParser, ForceField_Processing :1179-1247, OverWriteTailCorrection :1132-1176
+inline void read_force_field(Deck& d, const std::string& dir)
+{
+  auto L = read_lines(dir + "/force_field_mixing_rules.def");
+  d.shifted = terms(L.at(1)).at(0) == "shifted";
+  d.tail = terms(L.at(3)).at(0) == "yes";
+  const int n = std::stoi(terms(L.at(5)).at(0));
+  for(int i = 0; i < n; i++)
+  {
+    auto t = terms(L.at(7 + i));
+    d.names.push_back(t.at(0)); d.eps_in.push_back(std::stod(t.at(2))); d.sig_in.push_back(std::stod(t.at(3)));
+  }
+  auto P = read_lines(dir + "/pseudo_atoms.def");
+  const int np = std::stoi(terms(P.at(1)).at(0));
+  if(np != n) throw std::runtime_error("pseudo_atoms.def and force_field_mixing_rules.def list different numbers of atoms");
+  d.mass.resize(n); d.pseudo_charge.resize(n);
+  for(int i = 0; i < n; i++)
+  {
+    auto t = terms(P.at(3 + i));
+    if(t.at(0) != d.names[i]) throw std::runtime_error("pseudo_atoms.def must list the force-field names in the same order (read_data.cpp:1344)");
+    d.mass[i] = std::stod(t.at(5)); d.pseudo_charge[i] = std::stod(t.at(6));
+  }
+  const double cutsq = d.cutoff_vdw * d.cutoff_vdw;
+  d.eps.assign(n * n, 0); d.sigma.assign(n * n, 0); d.shift.assign(n * n, 0); d.tail_energy.assign(n * n, 0); d.use_tail.assign(n * n, 0);
+  for(int i = 0; i < n; i++)
+    for(int j = 0; j < n; j++)
+    {
+      const double e = std::sqrt(d.eps_in[i] * d.eps_in[j]) / 1.20272430057, s = 0.5 * (d.sig_in[i] + d.sig_in[j]);
+      d.eps[i * n + j] = e; d.sigma[i * n + j] = s;
+      d.shift[i * n + j] = d.shifted ? lj_energy(e, s, cutsq) : 0.0;
+      if(d.tail) { d.use_tail[i * n + j] = 1; d.tail_energy[i * n + j] = tail_value(e, s, cutsq); }
+    }
+  std::ifstream ffdef(dir + "/force_field.def");
+  if(ffdef)
+  {
+    auto F = read_lines(dir + "/force_field.def");
+    if(F.size() > 1)
+    {
+      const int nover = std::stoi(terms(F.at(1)).at(0));
+      for(int k = 0; k < nover && 3 + k < (int) F.size(); k++)
+      {
+        auto t = terms(F[3 + k]);
+        if(t.size() == 4 && t[3] == "yes")
+        {
+          const int i = type_of(d, t[0]), j = type_of(d, t[1]);
+          d.use_tail[i * n + j] = d.use_tail[j * n + i] = 1;
+          d.tail_energy[i * n + j] = d.tail_energy[j * n + i] = tail_value(d.eps[i * n + j], d.sigma[i * n + j], cutsq);
+        }
+      }
+    }
+  }
+}
+
+// MoleculeDefinitionParser, read_data.cpp:2044-2160 (rigid molecules)
+inline void read_molecule(Deck& d, Component& c, const std::string& dir)
+{
+  auto L = read_lines(dir + "/" + c.name + ".def");
+  c.tc = std::stod(terms(L.at(1)).at(0)); c.pc = std::stod(terms(L.at(2)).at(0)); c.acentric = std::stod(terms(L.at(3)).at(0));
+  const int ms = std::stoi(terms(L.at(5)).at(0));
+  if(!ieq(terms(L.at(9)).at(0), "rigid")) throw std::runtime_error("Currently Not allowing flexible molecule");
+  for(int a = 0; a < ms; a++)
+  {
+    auto t = terms(L.at(13 + a));
+    const int ty = type_of(d, t.at(1));
+    c.type.push_back(ty); c.charge.push_back(d.pseudo_charge[ty]); c.mass += d.mass[ty];
+    if(t.size() == 5) { c.pos.push_back(std::stod(t[2])); c.pos.push_back(std::stod(t[3])); c.pos.push_back(std::stod(t[4])); }
+    else if(t.size() == 2 && ms == 1) { c.pos.push_back(0.0); c.pos.push_back(0.0); c.pos.push_back(0.0); }
+    else throw std::runtime_error("Flexible molecules not implemented");
+  }
+}
+
+// inverse_matrix / matrix_determinant, maths.cuh:28-56
+inline void invert_cell(const double* x, double* r, double& det)
+{
+  const double m11 = x[0], m21 = x[3], m31 = x[6], m12 = x[1], m22 = x[4], m32 = x[7], m13 = x[2], m23 = x[5], m33 = x[8];
+  det = +m11 * (m22 * m33 - m23 * m32) - m12 * (m21 * m33 - m23 * m31) + m13 * (m21 * m32 - m22 * m31);
+  r[0] = +(m22 * m33 - m32 * m23) / det; r[3] = -(m21 * m33 - m31 * m23) / det; r[6] = +(m21 * m32 - m31 * m22) / det;
+  r[1] = -(m12 * m33 - m32 * m13) / det; r[4] = +(m11 * m33 - m31 * m13) / det; r[7] = -(m11 * m32 - m31 * m12) / det;
+  r[2] = +(m12 * m23 - m22 * m13) / det; r[5] = -(m11 * m23 - m21 * m13) / det; r[8] = +(m11 * m22 - m21 * m12) / det;
+}
+
+// ReadFramework (CIF, P1), read_data.cpp:1480-1760
+inline void read_framework(Deck& d, const std::string& dir)
+{
+  auto L = read_lines(dir + "/" + d.framework_name + ".cif");
+  double a = 0, b = 0, c = 0, al = 0, be = 0, ga = 0;
+  for(auto& s : L)
+  {
+    auto t = terms(s);
+    if(t.size() < 2) continue;
+    if(s.find("_cell_length_a") != std::string::npos) a = std::stod(t[1]);
+    if(s.find("_cell_length_b") != std::string::npos) b = std::stod(t[1]);
+    if(s.find("_cell_length_c") != std::string::npos) c = std::stod(t[1]);
+    if(s.find("_cell_angle_alpha") != std::string::npos) al = std::stod(t[1]) / (180.0 / 3.14159265358979323846);
+    if(s.find("_cell_angle_beta") != std::string::npos) be = std::stod(t[1]) / (180.0 / 3.14159265358979323846);
+    if(s.find("_cell_angle_gamma") != std::string::npos) ga = std::stod(t[1]) / (180.0 / 3.14159265358979323846);
+  }
+  const int nx = d.unitcells[0], ny = d.unitcells[1], nz = d.unitcells[2];
+  const double dy = b * std::sin(ga);
+  const double tempd = (std::cos(al) - std::cos(ga) * std::cos(be)) / std::sin(ga);
+  const double dz = c * std::sqrt(1 - std::pow(std::cos(be), 2) - std::pow(tempd, 2));
+  const double bx = b * std::cos(ga), cx = c * std::cos(be), cy = c * tempd;
+  d.cell[0] = nx * a;  d.cell[1] = 0.0;     d.cell[2] = 0.0;
+  d.cell[3] = ny * bx; d.cell[4] = ny * dy; d.cell[5] = 0.0;
+  d.cell[6] = nz * cx; d.cell[7] = nz * cy; d.cell[8] = nz * dz;
+  invert_cell(d.cell, d.inv, d.volume);
+  int col[5] = {-1, -1, -1, -1, -1}, count = 0, last = -1;
+  for(size_t i = 0; i < L.size(); i++)
+  {
+    if(L[i].find("_atom_site") != std::string::npos)
+    {
+      const char* keys[5] = {"_atom_site_label", "_atom_site_fract_x", "_atom_site_fract_y", "_atom_site_fract_z", "_atom_site_charge"};
+      for(int k = 0; k < 5; k++) if(L[i].find(keys[k]) != std::string::npos) col[k] = count;
+      count++; last = (int) i;
+    }
+    else if(last >= 0) break;
+  }
+  if(col[0] < 0 || col[1] < 0 || col[2] < 0 || col[3] < 0) throw std::runtime_error("Couldn't find required columns in the CIF file! Abort.");
+  std::vector<double> uf; std::vector<int> ut; std::vector<double> uq;
+  for(size_t i = last + 1; i < L.size(); i++)
+  {
+    auto t = terms(L[i]);
+    if(t.size() < 4) break;
+    std::string label = t[col[0]];
+    while(!label.empty() && std::isdigit((unsigned char) label.back())) label.pop_back();     // remove_number_at_the_end
+    const int ty = type_of(d, label);
+    uf.push_back(std::stod(t[col[1]])); uf.push_back(std::stod(t[col[2]])); uf.push_back(std::stod(t[col[3]]));
+    ut.push_back(ty);
+    uq.push_back((d.use_cif_charges && col[4] >= 0) ? std::stod(t[col[4]]) : d.pseudo_charge[ty]);
+    d.framework_mass += d.mass[ty];
+  }
+  const double sx = (double) 1 / nx, sy = (double) 1 / ny, sz = (double) 1 / nz;
+  for(int ix = 0; ix < nx; ix++) for(int jy = 0; jy < ny; jy++) for(int kz = 0; kz < nz; kz++)
+    for(size_t A = 0; A < ut.size(); A++)
+    {
+      const double fx = (uf[3 * A] + ix) * sx, fy = (uf[3 * A + 1] + jy) * sy, fz = (uf[3 * A + 2] + kz) * sz;
+      d.fpos.push_back(fx * d.cell[0] + fy * d.cell[3] + fz * d.cell[6]);
+      d.fpos.push_back(fx * d.cell[1] + fy * d.cell[4] + fz * d.cell[7]);
+      d.fpos.push_back(fx * d.cell[2] + fy * d.cell[5] + fz * d.cell[8]);
+      d.ftype.push_back(ut[A]); d.fcharge.push_back(uq[A]);
+    }
+}
+
+// read_Ewald_Parameters_from_input, read_data.cpp:609-702
+inline void setup_ewald(Deck& d)
+{
+  const double PI = 3.14159265358979323846;
+  if(d.lammps_ewald)
+  {
+    d.alpha = d.lammps_alpha; for(int k = 0; k < 3; k++) d.kmax[k] = d.lammps_kmax[k];
+    const double ux = 2 * PI / d.cell[0], vy = 2 * PI / d.cell[4], wz = 2 * PI / d.cell[8];
+    const double kx = d.kmax[0] * ux, ky = d.kmax[1] * vy, kz = d.kmax[2] * wz;
+    d.recip_cutoff = std::fmax(kx * kx, std::fmax(ky * ky, kz * kz)) * 1.00001;
+    return;
+  }
+  const double rc = d.cutoff_coul, p = d.ewald_precision;
+  const double tol = std::sqrt(std::fabs(std::log(p * rc)));
+  const double alpha = std::sqrt(std::fabs(std::log(p * rc * tol))) / rc;
+  const double tol1 = std::sqrt(-std::log(p * rc * std::pow(2.0 * tol * alpha, 2)));
+  d.alpha = alpha;
+  d.kmax[0] = (int) std::round(0.25 + d.cell[0] * alpha * tol1 / PI);
+  d.kmax[1] = (int) std::round(0.25 + d.cell[4] * alpha * tol1 / PI);
+  d.kmax[2] = (int) std::round(0.25 + d.cell[8] * alpha * tol1 / PI);
+  const int m = std::max(d.kmax[0], std::max(d.kmax[1], d.kmax[2]));
+  d.recip_cutoff = std::pow(1.05 * (double) m, 2);
+}
+
+inline Deck load(const std::string& dir)
+{
+  Deck d;
+  read_simulation_input(d, dir);
+  read_force_field(d, dir);
+  for(auto& c : d.comps) read_molecule(d, c, dir);
+  read_framework(d, dir);
+  if(!d.no_charges) setup_ewald(d);
+  // Setup_Box_Temperature_Pressure, fxn_main.h:115-127 with Units data_struct.h:58-68
+  const double kB = 1.380649e-23, mass_unit = 1.6605402e-27, length_unit = 1e-10, time_unit = 1e-12;
+  d.beta = 1.0 / (kB / (mass_unit * std::pow(length_unit, 2) / std::pow(time_unit, 2)) * d.temperature);
+  d.pressure = d.pressure_pa / (mass_unit / (length_unit * std::pow(time_unit, 2)));
+  return d;
+}
+
+} // namespace deck

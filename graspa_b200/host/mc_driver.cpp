@@ -1,0 +1,690 @@
+// graspa_b200 host layer -- Monte Carlo driver on top of the C ABI (include/graspa_b200.h).
+//
+// It keeps the reference's move drivers and simulation loop semantics, including the order in which every random
+// number is consumed, so that with the same RandomSeed it takes the same accept/reject decisions as the reference's
+// CUDA program:
+//   RunMoves / Select_Box_Component_Molecule            axpy.cu:74-298
+//   Determine_Number_Of_Steps, Run_Simulation_ForOneBox axpy.cu:580-641
+//   InsertionMove / DeletionMove / ReinsertionMove       move_struct.h:4-406
+//   Insertion_Body / Deletion_Body                       mc_swap_utilities.h:3-225
+//   SingleBodyMove                                       mc_single_particle.h:10-314
+//   RandomNumber (device pool of 333 334 double3)        data_struct.h:1287-1346
+//   GetPrefactor, Update_Max_Translation/Rotation        mc_utilities.h:315-351, 612-666
+//   Print_Widom_Statistics                               print_statistics.cuh:100-200
+// All energies come from the engine; this file only sequences calls, draws random numbers and keeps statistics.
+//
+// Two Widom paths: the reference's one-insertion-at-a-time sequence through the stage calls, and (for decks whose
+// only move is Widom insertion) an RNG-exact batched replay: per random pool the engine first evaluates the first-bead
+// success of every pool decade, a host walk then assigns pool blocks and uniforms to insertions exactly as the
+// sequential program would, and one gb_widom_batch call evaluates all insertions of the pool.
+#include "../../include/graspa_b200.h"
+#include "deck.hpp"
+#include "glibc_rand.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+[[noreturn]] void die(const std::string& what) { std::fprintf(stderr, "graspa_b200_mc: %s: %s\n", what.c_str(), gb_last_error()); std::exit(EXIT_FAILURE); }
+#define GB(call) do { if((call) != GB_OK) die(#call); } while(0)
+
+struct MoveCount { long total = 0, accepted = 0; };
+
+struct Energy   // MoveEnergy, data_struct.h:416-431 (terms this driver touches)
+{
+  double HHVDW = 0, HGVDW = 0, GGVDW = 0, HHReal = 0, HGReal = 0, GGReal = 0, HHEwald = 0, HGEwald = 0, GGEwald = 0, Tail = 0;
+  double total() const { return HHVDW + HGVDW + GGVDW + HHReal + HGReal + GGReal + HHEwald + HGEwald + GGEwald + Tail; }
+  void add(const Energy& o, double s = 1.0)
+  {
+    HHVDW += s * o.HHVDW; HGVDW += s * o.HGVDW; GGVDW += s * o.GGVDW; HHReal += s * o.HHReal; HGReal += s * o.HGReal; GGReal += s * o.GGReal;
+    HHEwald += s * o.HHEwald; HGEwald += s * o.HGEwald; GGEwald += s * o.GGEwald; Tail += s * o.Tail;
+  }
+};
+
+struct CompState
+{
+  // cumulative move probabilities, Move_Statistics::NormalizeProbabilities data_struct.h:569-608
+  double cTrans = 0, cRot = 0, cSpecial = 0, cWidom = 0, cReins = 0, cIdentity = 0, cCBCF = 0, cSwap = 0, total_prob = 0;
+  double max_trans[3] = {1, 1, 1}, max_rot[3] = {0, 0, 0};
+  MoveCount trans, rot, ins, del, reins, widom;
+  MoveCount trans_window, rot_window;           // TranslationTotal/Accepted are reset every 500 cycles
+  long nmol = 0;
+  bool has_charge = false;
+  // Rosenbluth statistics per block: sum W, sum W^2, count; W-weighted widom energies
+  std::vector<double> rw, rw2, rn; std::vector<Energy> wE;
+};
+
+struct Sim
+{
+  deck::Deck d;
+  gb_engine* e = nullptr;
+  GlibcRand rng;
+  std::vector<double> pool; size_t pool_size = 333334, pool_off = 0; long pool_rounds = 0;
+  int ncomp = 0;                                  // total components incl. framework (component 0)
+  std::vector<CompState> C;
+  long total_molecules = 1;                       // TotalNumberOfMolecules counts the framework as one
+  Energy running;                                 // SystemComponents.deltaE
+  int nblock = 5; long block_size = 1; bool production = false;
+  long moves_done = 0;
+  std::FILE* trace = nullptr;
+};
+
+void pool_reset(Sim& S)                           // RandomNumber::ResetRandom
+{
+  S.pool_off = 0;
+  for(size_t i = 0; i < S.pool_size; i++) { S.pool[3 * i] = S.rng.uniform(); S.pool[3 * i + 1] = S.rng.uniform(); S.pool[3 * i + 2] = S.rng.uniform(); }
+  for(size_t i = S.pool_size * 3; i < 1000000; i++) S.rng.uniform();
+  GB(gb_upload_random_pool(S.e, S.pool.data(), (int64_t) S.pool_size));
+  S.pool_rounds++;
+}
+inline void pool_check(Sim& S, size_t change) { if(S.pool_off + change >= S.pool_size) pool_reset(S); }
+inline void pool_update(Sim& S, size_t change) { S.pool_off += change; }
+
+void setup_engine(Sim& S)
+{
+  deck::Deck& d = S.d;
+  GB(gb_engine_create(&S.e, -1));
+  const int n = d.ntypes();
+  std::vector<double> zeros(n * n, 0.0);
+  gb_forcefield ff{d.eps.data(), d.sigma.data(), zeros.data(), d.shift.data(), zeros.data(), d.cutoff_vdw * d.cutoff_vdw, d.cutoff_coul * d.cutoff_coul,
+                   d.overlap, n, d.no_charges ? 1 : 0, 1 /* VDWRealBias stays true: SURVEY section 5 */, 0};
+  gb_tail_table tail{d.use_tail.data(), d.tail_energy.data(), n, 0};
+  GB(gb_upload_forcefield(S.e, &ff, &tail));
+  gb_box box; std::memset(&box, 0, sizeof(box));
+  for(int i = 0; i < 9; i++) { box.cell[i] = d.cell[i]; box.inverse_cell[i] = d.inv[i]; }
+  box.volume = d.volume; box.alpha = d.alpha; box.prefactor = d.prefactor; box.reciprocal_cutoff = d.recip_cutoff;
+  for(int k = 0; k < 3; k++) box.kmax[k] = d.kmax[k];
+  box.cubic = !((std::fabs(d.cell[3]) + std::fabs(d.cell[6]) + std::fabs(d.cell[7])) > 1e-10);
+  box.use_lammps_ewald = d.lammps_ewald ? 1 : 0;
+  GB(gb_upload_box(S.e, &box));
+  S.ncomp = 1 + (int) d.comps.size();
+  GB(gb_set_components(S.e, S.ncomp, 1));
+  {
+    const size_t nf = d.ftype.size();
+    std::vector<uint64_t> ty(nf), mol(nf, 0); std::vector<double> one(nf, 1.0);
+    for(size_t i = 0; i < nf; i++) ty[i] = (uint64_t) d.ftype[i];
+    gb_atoms a{d.fpos.data(), one.data(), d.fcharge.data(), one.data(), ty.data(), mol.data(), (int64_t) nf, (int64_t) nf, (int64_t) nf, (int64_t) nf};
+    GB(gb_upload_atoms(S.e, 0, &a));
+  }
+  for(size_t c = 0; c < d.comps.size(); c++)
+  {
+    const deck::Component& M = d.comps[c];
+    const int ms = M.ms();
+    std::vector<uint64_t> ty(ms), mol(ms, 0); std::vector<double> one(ms, 1.0);
+    for(int i = 0; i < ms; i++) ty[i] = (uint64_t) M.type[i];
+    // slot 0 holds the template molecule (read_data.cpp:2122-2147); Allocate_size = AdsorbateAllocateSpace (fxn_main.h:46-62)
+    gb_atoms a{M.pos.data(), one.data(), M.charge.data(), one.data(), ty.data(), mol.data(), ms, 0, (int64_t) std::max<long>(d.adsorbate_allocate, ms), ms};
+    GB(gb_upload_atoms(S.e, (int32_t) (c + 1), &a));
+  }
+  GB(gb_set_cbmc(S.e, d.n_trial_positions, d.n_trial_orientations, d.beta));
+  // rigid exclusion constants from the template molecule, Calculate_Exclusion_Energy_Rigid ewald_preparation.h:261-298, 351-366
+  for(size_t c = 0; c < d.comps.size(); c++)
+  {
+    const deck::Component& M = d.comps[c];
+    double intra = 0.0, self = 0.0; bool charged = false;
+    if(!d.no_charges)
+    {
+      for(int i = 0; i + 1 < M.ms(); i++)
+        for(int j = i + 1; j < M.ms(); j++)
+        {
+          double v[3] = {M.pos[3 * i] - M.pos[3 * j], M.pos[3 * i + 1] - M.pos[3 * j + 1], M.pos[3 * i + 2] - M.pos[3 * j + 2]};
+          // PBC(), maths.cuh:427-450
+          const double* I = d.inv; const double* Cc = d.cell;
+          if(box.cubic)
+          {
+            v[0] -= static_cast<int>(v[0] * I[0] + ((v[0] >= 0.0) ? 0.5 : -0.5)) * Cc[0];
+            v[1] -= static_cast<int>(v[1] * I[4] + ((v[1] >= 0.0) ? 0.5 : -0.5)) * Cc[4];
+            v[2] -= static_cast<int>(v[2] * I[8] + ((v[2] >= 0.0) ? 0.5 : -0.5)) * Cc[8];
+          }
+          else
+          {
+            double sx = I[0] * v[0] + I[3] * v[1] + I[6] * v[2], sy = I[1] * v[0] + I[4] * v[1] + I[7] * v[2], sz = I[2] * v[0] + I[5] * v[1] + I[8] * v[2];
+            sx -= static_cast<int>(sx + ((sx >= 0.0) ? 0.5 : -0.5)); sy -= static_cast<int>(sy + ((sy >= 0.0) ? 0.5 : -0.5)); sz -= static_cast<int>(sz + ((sz >= 0.0) ? 0.5 : -0.5));
+            v[0] = Cc[0] * sx + Cc[3] * sy + Cc[6] * sz; v[1] = Cc[1] * sx + Cc[4] * sy + Cc[7] * sz; v[2] = Cc[2] * sx + Cc[5] * sy + Cc[8] * sz;
+          }
+          const double r = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+          intra += d.prefactor * M.charge[i] * M.charge[j] * std::erf(d.alpha * r) / r;
+        }
+      const double ps = d.prefactor * d.alpha / std::sqrt(3.14159265358979323846);
+      for(int i = 0; i < M.ms(); i++) { self += ps * M.charge[i] * M.charge[i]; if(std::fabs(M.charge[i]) > 1e-10) charged = true; }
+    }
+    GB(gb_set_exclusion_constants(S.e, (int32_t) (c + 1), intra, self, 1, charged ? 1 : 0));
+    S.C[c + 1].has_charge = charged;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ probabilities
+void setup_probabilities(Sim& S)
+{
+  for(size_t c = 0; c < S.d.comps.size(); c++)
+  {
+    const deck::Component& M = S.d.comps[c]; CompState& X = S.C[c + 1];
+    double t = M.p_translation, r = M.p_rotation, sp = 0.0, w = M.p_widom, re = M.p_reinsertion, id = M.p_identity, sw = M.p_swap, cb = 0.0;
+    double tot = t + r + sp + w + re + id + sw + cb;
+    if(tot > 1e-10) { t /= tot; r /= tot; sp /= tot; w /= tot; sw /= tot; cb /= tot; re /= tot; id /= tot; tot = 1.0; }
+    X.total_prob = tot;
+    X.cTrans = t; X.cRot = r + X.cTrans; X.cSpecial = sp + X.cRot; X.cWidom = w + X.cSpecial; X.cReins = re + X.cWidom;
+    X.cIdentity = id + X.cReins; X.cCBCF = cb + X.cIdentity; X.cSwap = sw + X.cCBCF;
+    // InitializeMaxTranslationRotation fxn_main.h:151-160 then Prepare... :222-227 (0.1 x box lengths, 30 degrees)
+    X.max_trans[0] = S.d.cell[0] * 0.1; X.max_trans[1] = S.d.cell[4] * 0.1; X.max_trans[2] = S.d.cell[8] * 0.1;
+    for(int k = 0; k < 3; k++) X.max_rot[k] = 30.0 / (180 / 3.1415);
+    X.rw.assign(S.nblock, 0.0); X.rw2.assign(S.nblock, 0.0); X.rn.assign(S.nblock, 0.0); X.wE.assign(S.nblock, Energy());
+  }
+}
+
+double prefactor(const Sim& S, int comp, bool insertion)          // GetPrefactor, mc_utilities.h:315-351
+{
+  const deck::Component& M = S.d.comps[comp - 1];
+  const double N = (double) S.C[comp].nmol;
+  if(insertion) return S.d.beta * M.mol_fraction * S.d.pressure * M.fugacity_coeff * S.d.volume / (1.0 + N);
+  return N / (S.d.beta * M.mol_fraction * S.d.pressure * M.fugacity_coeff * S.d.volume);
+}
+
+// ------------------------------------------------------------------------------------------------ CBMC growth
+struct Growth { bool success = false; double W = 0.0; Energy E; int sel_fb = 0, sel_or = 0; double stored_r = 0.0; };
+
+// Insertion_Body (mc_swap_utilities.h:3-133) with MoveType INSERTION or WIDOM
+Growth insertion_body(Sim& S, int comp)
+{
+  Growth G;
+  const int ms = S.d.comps[comp - 1].ms();
+  const double scale[2] = {1.0, 1.0};
+  gb_cbmc_result r; int32_t used = 0;
+  pool_check(S, S.d.n_trial_positions);
+  GB(gb_cbmc_first_bead(S.e, GB_CBMC_INSERTION, comp, 0, (int64_t) S.pool_off, S.rng.peek(0), scale, 0.0, -1, -1, nullptr, &r, &used));
+  pool_update(S, S.d.n_trial_positions);
+  S.rng.advance(used);
+  double W = r.rosenbluth;
+  if(!r.success || W <= 1e-150) return G;
+  G.sel_fb = r.selected;
+  G.E.HGVDW = r.energy[0]; G.E.HGReal = r.energy[1]; G.E.GGVDW = r.energy[2]; G.E.GGReal = r.energy[3];
+  int sel = r.selected;
+  if(ms > 1)
+  {
+    pool_check(S, S.d.n_trial_orientations);
+    GB(gb_cbmc_chain(S.e, GB_CBMC_INSERTION, comp, 0, (int64_t) S.pool_off, S.rng.peek(0), -1, -1, &r, &used));
+    pool_update(S, S.d.n_trial_orientations);
+    S.rng.advance(used);
+    if(!r.success) return G;
+    W *= r.rosenbluth;
+    if(W <= 1e-150) return G;
+    G.sel_or = r.selected; sel = r.selected;
+    G.E.HGVDW += r.energy[0]; G.E.HGReal += r.energy[1]; G.E.GGVDW += r.energy[2]; G.E.GGReal += r.energy[3];
+  }
+  if(!S.d.no_charges && S.C[comp].has_charge)
+  {
+    double ew[2];
+    GB(gb_ewald_delta(S.e, comp, GB_INSERTION, sel, scale, ew));
+    G.E.GGEwald = ew[0]; G.E.HGEwald = ew[1];
+    W *= std::exp(-S.d.beta * (ew[0] + ew[1]));
+  }
+  double tail = 0.0;
+  GB(gb_tail_difference(S.e, comp, GB_INSERTION, &tail));
+  W *= std::exp(-S.d.beta * tail);
+  G.E.Tail = tail;
+  G.W = W; G.success = true;
+  return G;
+}
+
+void record_rosen(Sim& S, int comp, double W, const Energy& E, long cycle)      // axpy.cu:175-185, data_struct.h:627-652
+{
+  long b = cycle / S.block_size; if(b >= S.nblock) b--;
+  CompState& X = S.C[comp];
+  X.rw[b] += W; X.rw2[b] += W * W; X.rn[b] += 1.0;
+  X.wE[b].add(E, W);
+}
+
+void trace_move(Sim& S, const char* kind, int comp, long mol, int accepted, double dE)
+{
+  if(S.trace) std::fprintf(S.trace, "%ld %s %d %ld %d %.10e\n", S.moves_done, kind, comp, mol, accepted, dE);
+}
+
+// ------------------------------------------------------------------------------------------------ moves
+void move_widom(Sim& S, int comp, long cycle)
+{
+  S.C[comp].widom.total++;
+  Growth G = insertion_body(S, comp);
+  if(S.production) record_rosen(S, comp, G.success ? G.W : 0.0, G.success ? G.E : Energy(), cycle);
+  trace_move(S, "widom", comp, 0, G.success, G.W);
+}
+
+void move_insertion(Sim& S, int comp)              // InsertionMove::Run, move_struct.h:71-89
+{
+  CompState& X = S.C[comp];
+  X.ins.total++;
+  Growth G = insertion_body(S, comp);
+  if(!G.success) { trace_move(S, "insertion", comp, X.nmol, 0, 0.0); return; }
+  const double pacc = prefactor(S, comp, true) * G.W / S.d.comps[comp - 1].ideal_rosenbluth;
+  const double R = S.rng.uniform();
+  if(R < pacc)
+  {
+    GB(gb_accept_insertion(S.e, comp));
+    X.nmol++; S.total_molecules++; X.ins.accepted++;
+    S.running.add(G.E);
+    trace_move(S, "insertion", comp, X.nmol - 1, 1, G.E.total());
+  }
+  else trace_move(S, "insertion", comp, X.nmol, 0, 0.0);
+}
+
+void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run + Deletion_Body, move_struct.h:148-167, mc_swap_utilities.h:135-225
+{
+  CompState& X = S.C[comp];
+  X.del.total++;
+  const int ms = S.d.comps[comp - 1].ms();
+  const double scale[2] = {1.0, 1.0};
+  gb_cbmc_result r; int32_t used = 0;
+  pool_check(S, S.d.n_trial_positions);
+  GB(gb_cbmc_first_bead(S.e, GB_CBMC_DELETION, comp, mol, (int64_t) S.pool_off, 0.0, scale, 0.0, -1, -1, nullptr, &r, &used));
+  pool_update(S, S.d.n_trial_positions);
+  double W = r.rosenbluth;
+  if(!r.success || W <= 1e-150) { trace_move(S, "deletion", comp, mol, 0, 0.0); return; }
+  Energy E; E.HGVDW = r.energy[0]; E.HGReal = r.energy[1]; E.GGVDW = r.energy[2]; E.GGReal = r.energy[3];
+  if(ms > 1)
+  {
+    pool_check(S, S.d.n_trial_orientations);
+    GB(gb_cbmc_chain(S.e, GB_CBMC_DELETION, comp, mol, (int64_t) S.pool_off, 0.0, -1, -1, &r, &used));
+    pool_update(S, S.d.n_trial_orientations);
+    W *= r.rosenbluth;
+    E.HGVDW += r.energy[0]; E.HGReal += r.energy[1]; E.GGVDW += r.energy[2]; E.GGReal += r.energy[3];
+  }
+  if(W <= 1e-150) { trace_move(S, "deletion", comp, mol, 0, 0.0); return; }
+  const double pre = prefactor(S, comp, false);
+  if(!S.d.no_charges && X.has_charge)
+  {
+    double ew[2];
+    GB(gb_ewald_delta(S.e, comp, GB_DELETION, mol * ms, scale, ew));
+    W /= std::exp(-S.d.beta * (ew[0] + ew[1]));
+    E.GGEwald = -1.0 * ew[0]; E.HGEwald = -1.0 * ew[1];
+  }
+  double tail = 0.0;
+  GB(gb_tail_difference(S.e, comp, GB_DELETION, &tail));
+  W /= std::exp(-S.d.beta * tail);
+  E.Tail = -tail;
+  const double pacc = pre * S.d.comps[comp - 1].ideal_rosenbluth / W;
+  const double R = S.rng.uniform();
+  if(R < pacc)
+  {
+    GB(gb_accept_deletion(S.e, comp, mol));
+    X.nmol--; S.total_molecules--; X.del.accepted++;
+    S.running.add(E, -1.0);                                   // energy.take_negative()
+    trace_move(S, "deletion", comp, mol, 1, -E.total());
+  }
+  else trace_move(S, "deletion", comp, mol, 0, 0.0);
+}
+
+void move_reinsertion(Sim& S, int comp, long mol)  // ReinsertionMove::Run, move_struct.h:169-406
+{
+  CompState& X = S.C[comp];
+  X.reins.total++;
+  const int ms = S.d.comps[comp - 1].ms();
+  const double scale[2] = {1.0, 1.0};
+  gb_cbmc_result r; int32_t used = 0;
+  // insertion leg
+  pool_check(S, S.d.n_trial_positions);
+  GB(gb_cbmc_first_bead(S.e, GB_REINSERTION_INSERTION, comp, mol, (int64_t) S.pool_off, S.rng.peek(0), scale, 0.0, -1, -1, nullptr, &r, &used));
+  pool_update(S, S.d.n_trial_positions);
+  S.rng.advance(used);
+  double Wn = r.rosenbluth; const double stored_r = r.stored_r;
+  if(!r.success || Wn <= 1e-150) { trace_move(S, "reinsertion", comp, mol, 0, 0.0); return; }
+  Energy En; En.HGVDW = r.energy[0]; En.HGReal = r.energy[1]; En.GGVDW = r.energy[2]; En.GGReal = r.energy[3];
+  if(ms > 1)
+  {
+    pool_check(S, S.d.n_trial_orientations);
+    GB(gb_cbmc_chain(S.e, GB_REINSERTION_INSERTION, comp, mol, (int64_t) S.pool_off, S.rng.peek(0), -1, -1, &r, &used));
+    pool_update(S, S.d.n_trial_orientations);
+    S.rng.advance(used);
+    if(!r.success) { trace_move(S, "reinsertion", comp, mol, 0, 0.0); return; }
+    Wn *= r.rosenbluth;
+    if(Wn <= 1e-150) { trace_move(S, "reinsertion", comp, mol, 0, 0.0); return; }
+    En.HGVDW += r.energy[0]; En.HGReal += r.energy[1]; En.GGVDW += r.energy[2]; En.GGReal += r.energy[3];
+  }
+  GB(gb_reinsertion_store(S.e, comp));
+  // retrace leg: one first-bead trial + StoredR (mc_widom.h:365-366, 421-426)
+  pool_check(S, 1);
+  GB(gb_cbmc_first_bead(S.e, GB_REINSERTION_RETRACE, comp, mol, (int64_t) S.pool_off, 0.0, scale, stored_r, -1, -1, nullptr, &r, &used));
+  pool_update(S, 1);
+  double Wo = r.rosenbluth;
+  Energy Eo; Eo.HGVDW = r.energy[0]; Eo.HGReal = r.energy[1]; Eo.GGVDW = r.energy[2]; Eo.GGReal = r.energy[3];
+  if(ms > 1)
+  {
+    pool_check(S, S.d.n_trial_orientations);
+    GB(gb_cbmc_chain(S.e, GB_REINSERTION_RETRACE, comp, mol, (int64_t) S.pool_off, 0.0, -1, -1, &r, &used));
+    pool_update(S, S.d.n_trial_orientations);
+    Wo *= r.rosenbluth;
+    Eo.HGVDW += r.energy[0]; Eo.HGReal += r.energy[1]; Eo.GGVDW += r.energy[2]; Eo.GGReal += r.energy[3];
+  }
+  Energy E = En; E.add(Eo, -1.0);
+  if(!S.d.no_charges && X.has_charge)
+  {
+    double ew[2];
+    GB(gb_ewald_delta(S.e, comp, GB_REINSERTION, mol * ms, scale, ew));
+    E.GGEwald = ew[0]; E.HGEwald = ew[1];
+    Wn *= std::exp(-S.d.beta * (ew[0] + ew[1]));
+  }
+  const double R = S.rng.uniform();                          // drawn before the probability test (move_struct.h:350)
+  const double pacc = Wn / Wo;
+  if(!(R >= pacc))
+  {
+    GB(gb_accept_reinsertion(S.e, comp, mol));
+    X.reins.accepted++;
+    S.running.add(E);
+    trace_move(S, "reinsertion", comp, mol, 1, E.total());
+  }
+  else trace_move(S, "reinsertion", comp, mol, 0, 0.0);
+}
+
+void move_single_body(Sim& S, int comp, long mol, int move_type)   // SingleBodyMove, mc_single_particle.h:10-314
+{
+  CompState& X = S.C[comp];
+  MoveCount& cnt = move_type == GB_TRANSLATION ? X.trans : X.rot;
+  MoveCount& win = move_type == GB_TRANSLATION ? X.trans_window : X.rot_window;
+  cnt.total++; win.total++;
+  const int ms = S.d.comps[comp - 1].ms();
+  const double* maxc = move_type == GB_TRANSLATION ? X.max_trans : X.max_rot;
+  pool_check(S, ms);
+  GB(gb_single_body_propose(S.e, move_type, comp, mol, maxc, (int64_t) S.pool_off, nullptr));
+  pool_update(S, ms);
+  gb_move_energy d; int32_t overlap = 0;
+  GB(gb_single_body_delta(S.e, comp, 1, 1, &d, &overlap));
+  if(overlap) { trace_move(S, move_type == GB_TRANSLATION ? "translation" : "rotation", comp, mol, 0, 0.0); return; }
+  Energy E; E.HHVDW = d.HHVDW; E.HGVDW = d.HGVDW; E.GGVDW = d.GGVDW; E.HHReal = d.HHReal; E.HGReal = d.HGReal; E.GGReal = d.GGReal;
+  if(!S.d.no_charges && X.has_charge)
+  {
+    const double scale[2] = {1.0, 1.0}; double ew[2];
+    GB(gb_ewald_delta(S.e, comp, move_type, 0, scale, ew));
+    E.GGEwald = ew[0]; E.HGEwald = ew[1];
+  }
+  const double pacc = 1.0 * std::exp(-S.d.beta * E.total());
+  const double R = S.rng.uniform();
+  if(R < pacc)
+  {
+    GB(gb_accept_translation(S.e, comp));
+    cnt.accepted++; win.accepted++;
+    S.running.add(E);
+    trace_move(S, move_type == GB_TRANSLATION ? "translation" : "rotation", comp, mol, 1, E.total());
+  }
+  else trace_move(S, move_type == GB_TRANSLATION ? "translation" : "rotation", comp, mol, 0, 0.0);
+}
+
+// RunMoves, axpy.cu:102-298
+void run_move(Sim& S, long cycle)
+{
+  int comp = 0;
+  while(S.C[comp].total_prob < 1e-10) comp = (int) (size_t) (S.rng.uniform() * S.ncomp);
+  const long mol = (long) (size_t) (S.rng.uniform() * (double) S.C[comp].nmol);
+  const double R = S.rng.uniform();
+  const CompState& X = S.C[comp];
+  S.moves_done++;
+  if(R < X.cTrans) { if(X.nmol > 0) move_single_body(S, comp, mol, GB_TRANSLATION); }
+  else if(R < X.cRot) { if(X.nmol > 0) move_single_body(S, comp, mol, GB_ROTATION); }
+  else if(R < X.cSpecial) { }
+  else if(R < X.cWidom) move_widom(S, comp, cycle);
+  else if(R < X.cReins) { if(X.nmol > 0) move_reinsertion(S, comp, mol); }
+  else if(R < X.cIdentity) { std::fprintf(stderr, "identity swap is not driven by this host program yet\n"); std::exit(2); }
+  else if(R < X.cCBCF) { }
+  else if(R < X.cSwap)
+  {
+    if(S.rng.uniform() < 0.5) move_insertion(S, comp);
+    else if(X.nmol > 0) move_deletion(S, comp, mol);
+    else S.C[comp].del.total += 0;
+  }
+}
+
+void update_max(double* m, MoveCount& w, double cap)           // Update_Max_Translation / Update_Max_Rotation
+{
+  if(w.total == 0) return;
+  const double ratio = (double) w.accepted / (double) w.total;
+  for(int k = 0; k < 3; k++) { m[k] *= (ratio > 0.5) ? 1.05 : 0.95; if(m[k] < 0.01) m[k] = 0.01; if(m[k] > cap) m[k] = cap; }
+  w.total = 0; w.accepted = 0;
+}
+
+void run_phase(Sim& S, long cycles, bool production)
+{
+  S.production = production;
+  if(production) S.block_size = std::max<long>(1, cycles / S.nblock);
+  for(long i = 0; i < cycles; i++)
+  {
+    long steps = 20;
+    if(steps < S.total_molecules) steps = S.total_molecules;
+    if(S.d.use_max_step && steps > S.d.max_step_per_cycle) steps = S.d.max_step_per_cycle;
+    for(long j = 0; j < steps; j++) run_move(S, i);
+    if(i % 500 == 0)
+      for(int c = 1; c < S.ncomp; c++) { update_max(S.C[c].max_trans, S.C[c].trans_window, 5.0); update_max(S.C[c].max_rot, S.C[c].rot_window, 3.14); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RNG-exact batched Widom
+// Valid when Widom insertion of one component is the only move of the deck (Henrys_coefficient): pool offsets then
+// advance in decades.  Returns false (nothing consumed) when the deck does not qualify.
+bool widom_only(const Sim& S, int& comp)
+{
+  int found = -1;
+  for(int c = 1; c < S.ncomp; c++)
+  {
+    const CompState& X = S.C[c];
+    if(X.total_prob < 1e-10) continue;
+    if(found >= 0) return false;
+    if(std::fabs(X.cWidom - X.cSpecial - 1.0) > 1e-12) return false;
+    found = c;
+  }
+  comp = found;
+  return found >= 0 && S.d.n_trial_positions == S.d.n_trial_orientations && S.d.comps[found - 1].ms() > 1 && S.d.use_max_step && S.d.max_step_per_cycle == 1;
+}
+
+} // namespace
+
+// The batched walk in its final form: pools are generated ahead on the host (they only depend on the random stream),
+// so the walk never has to undo a draw.  The host keeps the previous pool alive until its queue is evaluated.
+namespace {
+
+struct Queue { std::vector<int64_t> fb, orr; std::vector<double> uni; std::vector<long> cyc; };
+
+void flush_queue(Sim& S, int comp, const std::vector<double>& pool, Queue& Q)
+{
+  const size_t n = Q.fb.size();
+  if(n == 0) return;
+  std::vector<double> out8(n * 8); std::vector<int32_t> stage(n); std::vector<double> sums(12);
+  gb_widom_inputs in; std::memset(&in, 0, sizeof(in));
+  in.pool3 = pool.data(); in.n_pool = (int64_t) (pool.size() / 3); in.fb_index = Q.fb.data(); in.or_index = Q.orr.data(); in.uniforms = Q.uni.data();
+  in.inputs_on_device = 0; in.n_blocks = 1;
+  GB(gb_widom_batch(S.e, comp, (int64_t) n, &in, out8.data(), stage.data(), 0, sums.data()));
+  for(size_t i = 0; i < n; i++)
+  {
+    Energy E; const double* o = &out8[8 * i];
+    E.HGVDW = o[1]; E.HGReal = o[2]; E.GGVDW = o[3]; E.GGReal = o[4]; E.GGEwald = o[5]; E.HGEwald = o[6]; E.Tail = o[7];
+    S.C[comp].widom.total++;
+    if(stage[i] == 3)
+    {
+      std::fprintf(stderr, "graspa_b200_mc: a chain stage lost every orientation to the overlap criterion; the batched replay cannot know that in advance. Re-run with --sequential-widom.\n");
+      std::exit(3);
+    }
+    record_rosen(S, comp, stage[i] == 0 ? o[0] : 0.0, stage[i] == 0 ? E : Energy(), Q.cyc[i]);
+  }
+  Q.fb.clear(); Q.orr.clear(); Q.uni.clear(); Q.cyc.clear();
+}
+
+void run_widom_batched_v2(Sim& S, int comp, long cycles)
+{
+  const size_t ntp = (size_t) S.d.n_trial_positions;
+  S.block_size = std::max<long>(1, cycles / S.nblock);
+  S.production = true;
+  std::vector<int32_t> ok;
+  auto classify = [&](const std::vector<double>& pool) {
+    const size_t ndec = S.pool_size / ntp;
+    ok.assign(ndec, 0);
+    std::vector<int64_t> idx(ndec);
+    for(size_t k = 0; k < ndec; k++) idx[k] = (int64_t) (k * ntp);
+    GB(gb_widom_first_bead_success(S.e, comp, (int64_t) ndec, pool.data(), (int64_t) S.pool_size, idx.data(), ok.data()));
+  };
+  classify(S.pool);
+  Queue Q;
+  for(long cycle = 0; cycle < cycles; cycle++)
+  {
+    // Select_Box_Component_Molecule
+    int c = 0;
+    while(S.C[c].total_prob < 1e-10) c = (int) (size_t) (S.rng.uniform() * S.ncomp);
+    S.rng.uniform(); S.rng.uniform();
+    S.moves_done++;
+    // first bead: Random.Check(ntp)
+    if(S.pool_off + ntp >= S.pool_size) { flush_queue(S, comp, S.pool, Q); pool_reset(S); classify(S.pool); }
+    const size_t dfb = S.pool_off / ntp;
+    S.pool_off += ntp;
+    const double u1 = (ok[dfb] != 2) ? S.rng.uniform() : 0.5;   // SelectTrialPosition draws only when a trial survived (mc_widom.h:334-335)
+    if(ok[dfb] != 1) { Q.fb.push_back((int64_t) (dfb * ntp)); Q.orr.push_back((int64_t) (dfb * ntp)); Q.uni.push_back(u1); Q.uni.push_back(0.5); Q.cyc.push_back(cycle); continue; }
+    // chain: Random.Check(nto)
+    if(S.pool_off + ntp >= S.pool_size)
+    {
+      // the orientation block lies in the NEXT pool: finish this insertion with the stage calls (once per pool)
+      flush_queue(S, comp, S.pool, Q);
+      gb_cbmc_result r; int32_t used = 0; const double scale[2] = {1.0, 1.0};
+      GB(gb_cbmc_first_bead(S.e, GB_CBMC_INSERTION, comp, 0, (int64_t) (dfb * ntp), u1, scale, 0.0, -1, -1, nullptr, &r, &used));
+      double W = r.rosenbluth; Energy E; E.HGVDW = r.energy[0]; E.HGReal = r.energy[1]; E.GGVDW = r.energy[2]; E.GGReal = r.energy[3];
+      pool_reset(S); classify(S.pool);
+      GB(gb_cbmc_chain(S.e, GB_CBMC_INSERTION, comp, 0, 0, S.rng.peek(0), -1, -1, &r, &used));
+      S.pool_off += ntp; S.rng.advance(used);
+      bool good = r.success != 0; W *= r.rosenbluth; if(W <= 1e-150) good = false;
+      E.HGVDW += r.energy[0]; E.HGReal += r.energy[1]; E.GGVDW += r.energy[2]; E.GGReal += r.energy[3];
+      if(good)
+      {
+        double ew[2] = {0, 0}, tail = 0.0;
+        if(!S.d.no_charges && S.C[comp].has_charge) GB(gb_ewald_delta(S.e, comp, GB_INSERTION, r.selected, scale, ew));
+        GB(gb_tail_difference(S.e, comp, GB_INSERTION, &tail));
+        E.GGEwald = ew[0]; E.HGEwald = ew[1]; E.Tail = tail;
+        W *= std::exp(-S.d.beta * (ew[0] + ew[1])); W *= std::exp(-S.d.beta * tail);
+      }
+      S.C[comp].widom.total++;
+      record_rosen(S, comp, good ? W : 0.0, good ? E : Energy(), cycle);
+      continue;
+    }
+    const size_t dor = S.pool_off / ntp;
+    S.pool_off += ntp;
+    const double u2 = S.rng.uniform();
+    Q.fb.push_back((int64_t) (dfb * ntp)); Q.orr.push_back((int64_t) (dor * ntp)); Q.uni.push_back(u1); Q.uni.push_back(u2); Q.cyc.push_back(cycle);
+  }
+  flush_queue(S, comp, S.pool, Q);
+}
+
+void print_widom(Sim& S, int comp)
+{
+  const CompState& X = S.C[comp];
+  const double R = 8.314462618, NA = 6.02214076e23;
+  const long ncell = (long) S.d.unitcells[0] * S.d.unitcells[1] * S.d.unitcells[2];
+  const double rho = S.d.framework_mass * ncell * 1.0e-3 / (NA * S.d.volume * 1.0e-30);
+  double tw = 0, tw2 = 0, th = 0, th2 = 0;
+  std::printf("=====================Rosenbluth Summary For Component [%d] (%s)=====================\n", comp, S.d.comps[comp - 1].name.c_str());
+  for(int b = 0; b < S.nblock; b++)
+  {
+    std::printf("=====BLOCK %d=====\nWidom Performed: %.1f\n", b, X.rn[b]);
+    if(X.rn[b] > 0)
+    {
+      const double w = X.rw[b] / X.rn[b], h = w / (R * S.d.temperature * rho);
+      std::printf("(Total) Averaged Rosenbluth Weight: %.10f\n", w);
+      std::printf("(Total) Averaged Excess Mu: %.10f\n", 1.2027242847 * -(1.0 / S.d.beta) * std::log(w));
+      std::printf("(Total) Averaged Henry Coefficient: %.10f\n", h);
+      const Energy& E = X.wE[b];
+      std::printf("AVG WIDOM %d HGVDW: %.5f, HGReal: %.5f, GGVDW: %.5f, GGReal: %.5f, HGEwaldE: %.5f, GGEwaldE: %.5f, TailE: %.5f\n", b,
+                  E.HGVDW / X.rn[b] / w, E.HGReal / X.rn[b] / w, E.GGVDW / X.rn[b] / w, E.GGReal / X.rn[b] / w, E.HGEwald / X.rn[b] / w, E.GGEwald / X.rn[b] / w, E.Tail / X.rn[b] / w);
+      tw += w; tw2 += w * w; th += h; th2 += h * h;
+    }
+  }
+  const double aw = tw / S.nblock, aw2 = tw2 / S.nblock, ah = th / S.nblock, ah2 = th2 / S.nblock;
+  std::printf("=========================AVERAGE========================\n");
+  std::printf("Averaged Rosenbluth Weight: %.10f +/- %.10f\n", aw, 2.0 * std::pow(std::fmax(aw2 - aw * aw, 0.0), 0.5));
+  std::printf("Averaged Henry Coefficient [mol/kg/Pa]: %.10g +/- %.10g\n", ah, 2.0 * std::pow(std::fmax(ah2 - ah * ah, 0.0), 0.5));
+}
+
+Energy total_energy(Sim& S)
+{
+  gb_move_energy v, w; double tail = 0.0;
+  GB(gb_total_vdw_real(S.e, &v)); GB(gb_total_ewald(S.e, 0, &w)); GB(gb_tail_total(S.e, &tail));
+  Energy E; E.HHVDW = v.HHVDW; E.HGVDW = v.HGVDW; E.GGVDW = v.GGVDW; E.HHReal = v.HHReal; E.HGReal = v.HGReal; E.GGReal = v.GGReal;
+  E.HHEwald = w.HHEwaldE; E.HGEwald = w.HGEwaldE; E.GGEwald = w.GGEwaldE; E.Tail = tail;
+  return E;
+}
+
+void print_energy(const char* tag, const Energy& E)
+{
+  std::printf("%s VDW [Host-Host]: %.5f, VDW [Host-Guest]: %.5f, VDW [Guest-Guest]: %.5f, Real [Host-Host]: %.5f, Real [Host-Guest]: %.5f, Real [Guest-Guest]: %.5f, "
+              "Ewald [Host-Host]: %.5f, Ewald [Host-Guest]: %.5f, Ewald [Guest-Guest]: %.5f, Tail: %.5f, Total: %.5f\n",
+              tag, E.HHVDW, E.HGVDW, E.GGVDW, E.HHReal, E.HGReal, E.GGReal, E.HHEwald, E.HGEwald, E.GGEwald, E.Tail, E.total());
+}
+
+} // namespace
+
+int main(int argc, char** argv)
+{
+  if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
+  const std::string dir = argv[1];
+  bool sequential_widom = false; const char* trace_path = nullptr;
+  long o_init = -1, o_equil = -1, o_prod = -1;
+  for(int i = 2; i < argc; i++)
+  {
+    const std::string a = argv[i];
+    if(a == "--sequential-widom") sequential_widom = true;
+    else if(a == "--trace" && i + 1 < argc) trace_path = argv[++i];
+    else if(a == "--init" && i + 1 < argc) o_init = std::atol(argv[++i]);
+    else if(a == "--equil" && i + 1 < argc) o_equil = std::atol(argv[++i]);
+    else if(a == "--prod" && i + 1 < argc) o_prod = std::atol(argv[++i]);
+  }
+  Sim S;
+  try { S.d = deck::load(dir); } catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
+  if(o_init >= 0) S.d.init_cycles = o_init;
+  if(o_equil >= 0) S.d.equil_cycles = o_equil;
+  if(o_prod >= 0) S.d.prod_cycles = o_prod;
+  S.C.assign(1 + S.d.comps.size(), CompState());
+  if(trace_path) S.trace = std::fopen(trace_path, "w");
+  setup_engine(S);
+  setup_probabilities(S);
+  std::printf("graspa_b200_mc: %s, %zu framework atoms, %zu adsorbate component(s), alpha %.6f, kmax %d %d %d, volume %.5f, beta %.8f\n",
+              dir.c_str(), S.d.ftype.size(), S.d.comps.size(), S.d.alpha, S.d.kmax[0], S.d.kmax[1], S.d.kmax[2], S.d.volume, S.d.beta);
+  // Random.Setup(333334): std::srand(RANDOMSEED) then the first pool (main.cpp:145, data_struct.h:1338-1346)
+  S.rng.reseed((unsigned) S.d.random_seed);
+  S.pool.assign(3 * S.pool_size, 0.0);
+  pool_reset(S); S.pool_rounds = 0;
+  // initial energies + structure factors (Check_Simulation_Energy(INITIAL), fxn_main.h:282-404)
+  { gb_move_energy w; GB(gb_total_ewald(S.e, 1, &w)); }
+  const Energy E0 = total_energy(S);
+  print_energy("INITIAL", E0);
+
+  const auto t0 = std::chrono::steady_clock::now();
+  int wcomp = -1;
+  const bool batched = !sequential_widom && widom_only(S, wcomp) && S.d.init_cycles == 0 && S.d.equil_cycles == 0;
+  if(batched) run_widom_batched_v2(S, wcomp, S.d.prod_cycles);
+  else
+  {
+    run_phase(S, S.d.init_cycles, false);
+    run_phase(S, S.d.equil_cycles, false);
+    run_phase(S, S.d.prod_cycles, true);
+  }
+  GB(gb_synchronize(S.e));
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+  const Energy E1 = total_energy(S);
+  print_energy("FINAL  ", E1);
+  Energy D = E1; D.add(E0, -1.0);
+  print_energy("RUNNING", S.running);
+  std::printf("ENERGY DRIFT (FINAL - INITIAL - RUNNING) Total Energy: %.6e\n", D.total() - S.running.total());
+  for(int c = 1; c < S.ncomp; c++)
+  {
+    const CompState& X = S.C[c];
+    std::printf("Component %d (%s): molecules %ld | translation %ld/%ld rotation %ld/%ld insertion %ld/%ld deletion %ld/%ld reinsertion %ld/%ld widom %ld\n",
+                c, S.d.comps[c - 1].name.c_str(), X.nmol, X.trans.accepted, X.trans.total, X.rot.accepted, X.rot.total, X.ins.accepted, X.ins.total,
+                X.del.accepted, X.del.total, X.reins.accepted, X.reins.total, X.widom.total);
+    if(X.widom.total > 0) print_widom(S, c);
+  }
+  const long cycles = S.d.init_cycles + S.d.equil_cycles + S.d.prod_cycles;
+  int64_t launches = 0; gb_launch_count(S.e, &launches, 0);
+  std::printf("Work took %.6f seconds\n", secs);
+  std::printf("{\"moves\": %ld, \"cycles\": %ld, \"seconds\": %.6f, \"moves_per_s\": %.3f, \"cycles_per_s\": %.3f, \"widom_path\": \"%s\", \"rng_draws\": %llu, \"pool_refills\": %ld, \"kernel_launches\": %lld}\n",
+              S.moves_done, cycles, secs, S.moves_done / secs, cycles / secs, batched ? "batched-exact" : "sequential",
+              (unsigned long long) S.rng.consumed(), S.pool_rounds, (long long) launches);
+  if(S.trace) std::fclose(S.trace);
+  gb_engine_destroy(S.e);
+  return 0;
+}

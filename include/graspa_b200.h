@@ -255,11 +255,19 @@ typedef struct {
 } gb_widom_inputs;
 
 /* per insertion outputs (any may be NULL): out8[i*8 + {W, HGVDW, HGReal, GGVDW, GGReal, GGEwaldE, HGEwaldE, TailE}],
- * stage[i] (0 ok, 1 first bead failed, 2 chain failed).
+ * stage[i] (0 ok, 1 first bead failed, 2 chain failed, 3 chain failed with no surviving orientation).
  * sums[(bin)*12 + {sumW, sumW2, count, sum(W*E) for the 7 energy terms, n_failed, reserved}] on the host, reduced on the device
  * (RecordRosen data_struct.h:627-652 and widom_energy += E*W axpy.cu:177-185). */
 int  gb_widom_batch(gb_engine* e, int32_t component, int64_t n, const gb_widom_inputs* in,
                     double* out8, int32_t* stage, int32_t outputs_on_device, double* sums);
+
+/* First-bead stage only, for n pool blocks: code[i] = 1 the first bead at pool3[fb_index[i] ...] succeeds
+ * (>= 1 trial without overlap, Rosenbluth >= 1e-150), 0 it fails although a trial survived, 2 no trial survived.
+ * This is what a host needs to replay the reference's random-number stream exactly for batched Widom insertions:
+ * whether an insertion consumes its orientation block and its second uniform depends only on these codes
+ * (mc_widom.h:332-341, mc_swap_utilities.h:19-27).  Host buffers. */
+int  gb_widom_first_bead_success(gb_engine* e, int32_t component, int64_t n, const double* pool3, int64_t n_pool,
+                                 const int64_t* fb_index, int32_t* code);
 
 /* ------------------------------------------------------------------------------------------------
  * instrumentation
