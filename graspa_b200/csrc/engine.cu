@@ -679,29 +679,35 @@ int gb_trial_energies(gb_engine* e, int32_t ntr, int32_t cs, const double* pos, 
 }
 
 // ---------------------------------------------------------------------------------------------- Ewald delta
-static int ewald_delta_launch(gb_engine* e, bool framework_moved, int nold, int nnew, const double* d_pos3, const double* d_qeff, double out[2])
+// enqueue the Ewald delta kernel (no synchronisation): result {same, 2*cross} goes to d_result2, skipped when *d_dep == 0
+static int ewald_delta_enqueue(gb_engine* e, bool framework_moved, int nold, int nnew, const double* d_pos3, const double* d_qeff,
+                               double* d_result2, const double* d_dep)
 {
   const int n = nold + nnew;
   if(n <= 0 || n > GBK_EW_MAX_ATOMS) return fail(GB_ERR_ARG, "Ewald delta supports 1..64 moved atoms");
-  if(e->nact == 0) { out[0] = 0.0; out[1] = 0.0; return GB_OK; }
   EwaldDeltaArgs A;
   A.pos3 = d_pos3; A.qeff = d_qeff; A.nold = nold; A.nnew = nnew;
   A.K.kpack = e->d_kpack.p; A.K.temp = e->d_ktemp.p; A.K.slot = e->d_kslot.p; A.K.nact = e->nact;
   A.same_sf = framework_moved ? e->d_sf[e->i_fw].p : e->d_sf[e->i_ads].p;
   A.cross_sf = framework_moved ? e->d_sf[e->i_ads].p : e->d_sf[e->i_fw].p;
-  A.temp_sf = e->d_sf[e->i_tmp].p;
+  A.temp_sf = e->d_sf[e->i_tmp].p;     // only active k are written; inactive entries of all three arrays stay zero
   const int nblk = (e->nact + 127) / 128;
   CUDA_TRY(e->d_partial.reserve((size_t) std::max(nblk * 2, 64)));
-  A.partial = e->d_partial.p; A.ticket = e->d_ticket.p; A.result = e->d_result.p;
+  A.partial = e->d_partial.p; A.ticket = e->d_ticket.p; A.result = d_result2; A.dep = d_dep;
   const size_t smem = (size_t) n * (e->P.kmax[0] + e->P.kmax[1] + e->P.kmax[2] + 3) * sizeof(cplx) + (size_t) n * sizeof(double) + 16;
   if(smem > e->smem_optin) return fail(GB_ERR_ARG, "eik tables exceed shared memory");
-  // inactive k of tempEik keep the same-type values (zeros from the total), they never contribute
-  CUDA_TRY(cudaMemcpyAsync(e->d_sf[e->i_tmp].p, A.same_sf, (size_t) e->nvec * 2 * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
   Timer tm(e, 1);
   k_ewald_delta<<<nblk, 128, smem, e->stream>>>(e->P, A);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   tm.stop(1);
+  return GB_OK;
+}
+
+static int ewald_delta_launch(gb_engine* e, bool framework_moved, int nold, int nnew, const double* d_pos3, const double* d_qeff, double out[2])
+{
+  if(e->nact == 0) { out[0] = 0.0; out[1] = 0.0; return GB_OK; }
+  int rc = ewald_delta_enqueue(e, framework_moved, nold, nnew, d_pos3, d_qeff, e->d_result.p, nullptr); if(rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(e->h_pinned, e->d_result.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   out[0] = e->h_pinned[0]; out[1] = e->h_pinned[1];
@@ -744,6 +750,7 @@ int gb_tail_total(gb_engine* e, double* out)
 
 int gb_tail_difference(gb_engine* e, int32_t c, int32_t move_type, double* out)
 {
+  if(e && e->have_ff && !e->has_tail && out) { *out = 0.0; return GB_OK; }     // HasTailCorrection == false (:39)
   int rc = ready(e); if(rc) return rc;
   if(c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "bad component");
   if(move_type == GB_CBCF_INSERTION || move_type == GB_CBCF_DELETION) return fail(GB_ERR_UNIMPLEMENTED, "tail corrections are not defined for CBCF moves (TailCorrection_Energy_Functions.h:48-55)");
@@ -1047,3 +1054,4 @@ int gb_measure_fp64_peak(gb_engine* e, double* tflops)
 
 } // extern "C"
 #include "moves.inc"
+#include "fused_moves.inc"

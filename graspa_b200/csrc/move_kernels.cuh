@@ -21,9 +21,11 @@ struct MoveBufs
   __host__ __device__ int* mol_type(int buf) const { return i + GBK_MV_TRIAL_SLOTS + buf * GBK_MV_MOL_SLOTS; }
   __host__ __device__ double* stage_e() const { return d + 9 * GBK_MV_TRIAL_SLOTS + 36 * GBK_MV_MOL_SLOTS; }   // [32][6]
   __host__ __device__ int* stage_flag() const { return i + GBK_MV_TRIAL_SLOTS + 4 * GBK_MV_MOL_SLOTS; }      // [32]
-  __host__ __device__ double* result() const { return stage_e() + GBK_MV_MAXT * 6; }                          // 16 doubles
-  __host__ __device__ double* partial() const { return result() + 16; }                                       // [64][16]
-  static size_t doubles() { return 9 * GBK_MV_TRIAL_SLOTS + 36 * GBK_MV_MOL_SLOTS + GBK_MV_MAXT * 6 + 16 + 64 * 16; }
+  // result slots of 16 doubles: 0 first bead (new), 1 chain (new), 2 first bead (old/retrace), 3 chain (old/retrace),
+  // 4 single-body delta, 5 Ewald {same, 2*cross}, 6-7 spare.  Fused move calls read all of them back in one copy.
+  __host__ __device__ double* result(int slot = 0) const { return stage_e() + GBK_MV_MAXT * 6 + 16 * slot; }
+  __host__ __device__ double* partial() const { return result(0) + 128; }                                     // [64][16]
+  static size_t doubles() { return 9 * GBK_MV_TRIAL_SLOTS + 36 * GBK_MV_MOL_SLOTS + GBK_MV_MAXT * 6 + 128 + 64 * 16; }
   static size_t ints() { return GBK_MV_TRIAL_SLOTS + 4 * GBK_MV_MOL_SLOTS + GBK_MV_MAXT + 16; }
 };
 
@@ -38,6 +40,9 @@ struct CompView
 struct CbmcArgs
 {
   int cbmc_type, comp, ms, ntrials, norm, new_molid, excl_comp, excl_mol, first_bead_trial;
+  // chaining of stages on the device (fused move calls): where this stage writes its result, which earlier stage must
+  // have succeeded for this one to run (-1: none), and from which result slot StoredR is taken (-1: the stored_r argument)
+  int rslot, dep_slot, stored_slot;
   long long molecule;          // SelectedMolInComponent
   long long pool_off;
   const double* __restrict__ pool3;
@@ -94,7 +99,7 @@ __device__ __forceinline__ void cbmc_finish(const DevParams& P, const CbmcArgs& 
   if(!is_chain)
   {
     if(ty == 2) r[1] = R - Rsel;                                        // StoredR, mc_widom.h:365
-    if(ty == 3) avg += A.stored_r;                                       // REINSERTION_RETRACE :366
+    if(ty == 3) avg += (A.stored_slot >= 0) ? A.B.result(A.stored_slot)[1] : A.stored_r;   // REINSERTION_RETRACE :366
     if(ty != 4 && ty != 5) avg /= (double) A.norm;                       // :369-370
   }
   else avg = R / (double) A.norm;                                         // :601
@@ -135,6 +140,12 @@ k_cbmc_first_bead(DevParams P, SysView S, SegList L, CbmcArgs A)
   __shared__ double red[8 * 8];
   __shared__ double etab[(GBK_ERFC_DEG + 1) * GBK_ERFC_NINT];
   __shared__ bool last;
+  if(A.dep_slot >= 0 && A.B.result(A.dep_slot)[13] == 0.0)
+  {
+    // the stage this one depends on failed (or left a Rosenbluth weight <= 1e-150): report failure, consume nothing
+    if(blockIdx.x == 0 && threadIdx.x < 16) A.B.result(A.rslot)[threadIdx.x] = 0.0;
+    return;
+  }
   stage_erfc_table(P, etab);
   const int t = blockIdx.x;
   if(threadIdx.x == 0)
@@ -163,9 +174,11 @@ k_cbmc_first_bead(DevParams P, SysView S, SegList L, CbmcArgs A)
   if(last && threadIdx.x == 0)
   {
     __threadfence();
-    double* r = A.B.result();
+    double* r = A.B.result(A.rslot);
     cbmc_finish(P, A, false, r);
-    if(r[9] != 0.0)
+    r[14] = r[0];                                                   // running Rosenbluth product of the growth
+    r[13] = (r[9] != 0.0 && r[0] > 1e-150) ? 1.0 : 0.0;             // "Rosenbluth <= 1e-150 -> SuccessConstruction = false", mc_swap_utilities.h:21
+    if(r[9] != 0.0 && r[11] > 0.0)
     {
       const int s = (int) r[10];
       r[6] = A.B.tr(0)[s]; r[7] = A.B.tr(1)[s]; r[8] = A.B.tr(2)[s];
@@ -186,6 +199,11 @@ k_cbmc_chain(DevParams P, SysView S, SegList L, CbmcArgs A)
   __shared__ double red[8 * 8];
   __shared__ double etab[(GBK_ERFC_DEG + 1) * GBK_ERFC_NINT];
   __shared__ bool last;
+  if(A.dep_slot >= 0 && A.B.result(A.dep_slot)[13] == 0.0)
+  {
+    if(blockIdx.x == 0 && threadIdx.x < 16) A.B.result(A.rslot)[threadIdx.x] = 0.0;
+    return;
+  }
   stage_erfc_table(P, etab);
   const int o = blockIdx.x, cs = A.ms - 1;
   if(threadIdx.x < cs)
@@ -224,8 +242,10 @@ k_cbmc_chain(DevParams P, SysView S, SegList L, CbmcArgs A)
     if(threadIdx.x == 0)
     {
       __threadfence();
-      double* r = A.B.result();
+      double* r = A.B.result(A.rslot);
       cbmc_finish(P, A, true, r);
+      r[14] = (A.dep_slot >= 0 ? A.B.result(A.dep_slot)[14] : 1.0) * r[0];   // CBMC.Rosenbluth *= averagedRosen, mc_widom.h:611
+      r[13] = (r[9] != 0.0 && r[14] > 1e-150) ? 1.0 : 0.0;                  // mc_swap_utilities.h:32
       sel_s = (r[9] != 0.0 && r[11] > 0.0) ? (int) r[10] : -1;
       *A.ticket = 0u;
     }
@@ -375,7 +395,7 @@ k_single_body(DevParams P, SysView S, SegList L, SingleBodyArgs A)
   {
     __threadfence();
     const volatile double* p = A.B.partial();
-    double* r = A.B.result();
+    double* r = A.B.result(4);
     for(int k = 0; k < 6; k++)
     {
       double n = 0.0, o = 0.0;
@@ -385,6 +405,7 @@ k_single_body(DevParams P, SysView S, SegList L, SingleBodyArgs A)
     double fl = 0.0;
     for(unsigned int b = 0; b < gridDim.x; b++) fl += p[b * 16 + 6];     // overlap of the NEW configuration only (:768-769)
     r[6] = fl > 0.0 ? 1.0 : 0.0;
+    r[7] = 1.0 - r[6];                                                   // "no overlap": dependency flag of the Ewald stage
     *A.ticket = 0u;
   }
 }

@@ -27,7 +27,7 @@ DECLARED_SYMBOLS = [
     "gb_abi_version", "gb_last_error", "gb_engine_create", "gb_engine_destroy", "gb_device_info", "gb_synchronize", "gb_stream",
     "gb_upload_forcefield", "gb_upload_box", "gb_set_components", "gb_upload_atoms", "gb_download_atoms",
     "gb_upload_structure_factors", "gb_download_structure_factors", "gb_set_exclusion_constants", "gb_upload_random_pool",
-    "gb_set_cbmc", "gb_get_pseudo_atom_counts", "gb_cbmc_first_bead", "gb_cbmc_chain", "gb_cbmc_grown_positions", "gb_reinsertion_store",
+    "gb_set_cbmc", "gb_get_pseudo_atom_counts", "gb_cbmc_first_bead", "gb_cbmc_chain", "gb_cbmc_grown_positions", "gb_reinsertion_store", "gb_move_insertion", "gb_move_deletion", "gb_move_reinsertion", "gb_move_single_body",
     "gb_trial_energies", "gb_single_body_propose", "gb_single_body_delta", "gb_single_body_delta_explicit",
     "gb_ewald_delta", "gb_ewald_delta_identity_swap", "gb_ewald_delta_explicit", "gb_ewald_commit",
     "gb_tail_total", "gb_tail_difference", "gb_tail_identity_swap",

@@ -72,6 +72,7 @@ struct Sim
   Energy running;                                 // SystemComponents.deltaE
   int nblock = 5; long block_size = 1; bool production = false;
   long moves_done = 0;
+  bool fused = true;                              // one host round trip per move (gb_move_*); false: the stage calls
   std::FILE* trace = nullptr;
 };
 
@@ -197,6 +198,27 @@ Growth insertion_body(Sim& S, int comp)
   const double scale[2] = {1.0, 1.0};
   gb_cbmc_result r; int32_t used = 0;
   pool_check(S, S.d.n_trial_positions);
+  if(S.fused && !(ms > 1 && S.pool_off + S.d.n_trial_positions + S.d.n_trial_orientations >= S.pool_size))
+  {
+    // one round trip for the whole Insertion_Body
+    const double u[2] = {S.rng.peek(0), S.rng.peek(1)};
+    gb_move_result m;
+    GB(gb_move_insertion(S.e, comp, (int64_t) S.pool_off, u, scale, &m));
+    S.rng.advance(m.uniforms_used); pool_update(S, m.pool_used);
+    if(!m.success) return G;
+    G.sel_fb = m.first_bead.selected; G.sel_or = m.chain.selected;
+    double W = m.first_bead.rosenbluth;
+    G.E.HGVDW = m.first_bead.energy[0]; G.E.HGReal = m.first_bead.energy[1]; G.E.GGVDW = m.first_bead.energy[2]; G.E.GGReal = m.first_bead.energy[3];
+    if(ms > 1)
+    {
+      W *= m.chain.rosenbluth;
+      G.E.HGVDW += m.chain.energy[0]; G.E.HGReal += m.chain.energy[1]; G.E.GGVDW += m.chain.energy[2]; G.E.GGReal += m.chain.energy[3];
+    }
+    if(!S.d.no_charges && S.C[comp].has_charge) { G.E.GGEwald = m.ewald[0]; G.E.HGEwald = m.ewald[1]; W *= std::exp(-S.d.beta * (m.ewald[0] + m.ewald[1])); }
+    W *= std::exp(-S.d.beta * m.tail);
+    G.E.Tail = m.tail; G.W = W; G.success = true;
+    return G;
+  }
   GB(gb_cbmc_first_bead(S.e, GB_CBMC_INSERTION, comp, 0, (int64_t) S.pool_off, S.rng.peek(0), scale, 0.0, -1, -1, nullptr, &r, &used));
   pool_update(S, S.d.n_trial_positions);
   S.rng.advance(used);
@@ -280,11 +302,26 @@ void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run + Deleti
   const double scale[2] = {1.0, 1.0};
   gb_cbmc_result r; int32_t used = 0;
   pool_check(S, S.d.n_trial_positions);
+  double W = 0.0; Energy E; double ew[2] = {0.0, 0.0}; double tail = 0.0;
+  const bool fused = S.fused && !(ms > 1 && S.pool_off + S.d.n_trial_positions + S.d.n_trial_orientations >= S.pool_size);
+  if(fused)
+  {
+    gb_move_result m;
+    GB(gb_move_deletion(S.e, comp, mol, (int64_t) S.pool_off, scale, &m));
+    pool_update(S, m.pool_used);
+    if(!m.success) { trace_move(S, "deletion", comp, mol, 0, 0.0); return; }
+    W = m.first_bead.rosenbluth;
+    E.HGVDW = m.first_bead.energy[0]; E.HGReal = m.first_bead.energy[1]; E.GGVDW = m.first_bead.energy[2]; E.GGReal = m.first_bead.energy[3];
+    if(ms > 1) { W *= m.chain.rosenbluth; E.HGVDW += m.chain.energy[0]; E.HGReal += m.chain.energy[1]; E.GGVDW += m.chain.energy[2]; E.GGReal += m.chain.energy[3]; }
+    ew[0] = m.ewald[0]; ew[1] = m.ewald[1]; tail = m.tail;
+  }
+  else
+  {
   GB(gb_cbmc_first_bead(S.e, GB_CBMC_DELETION, comp, mol, (int64_t) S.pool_off, 0.0, scale, 0.0, -1, -1, nullptr, &r, &used));
   pool_update(S, S.d.n_trial_positions);
-  double W = r.rosenbluth;
+  W = r.rosenbluth;
   if(!r.success || W <= 1e-150) { trace_move(S, "deletion", comp, mol, 0, 0.0); return; }
-  Energy E; E.HGVDW = r.energy[0]; E.HGReal = r.energy[1]; E.GGVDW = r.energy[2]; E.GGReal = r.energy[3];
+  E.HGVDW = r.energy[0]; E.HGReal = r.energy[1]; E.GGVDW = r.energy[2]; E.GGReal = r.energy[3];
   if(ms > 1)
   {
     pool_check(S, S.d.n_trial_orientations);
@@ -294,16 +331,15 @@ void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run + Deleti
     E.HGVDW += r.energy[0]; E.HGReal += r.energy[1]; E.GGVDW += r.energy[2]; E.GGReal += r.energy[3];
   }
   if(W <= 1e-150) { trace_move(S, "deletion", comp, mol, 0, 0.0); return; }
+  if(!S.d.no_charges && X.has_charge) GB(gb_ewald_delta(S.e, comp, GB_DELETION, mol * ms, scale, ew));
+  GB(gb_tail_difference(S.e, comp, GB_DELETION, &tail));
+  }
   const double pre = prefactor(S, comp, false);
   if(!S.d.no_charges && X.has_charge)
   {
-    double ew[2];
-    GB(gb_ewald_delta(S.e, comp, GB_DELETION, mol * ms, scale, ew));
     W /= std::exp(-S.d.beta * (ew[0] + ew[1]));
     E.GGEwald = -1.0 * ew[0]; E.HGEwald = -1.0 * ew[1];
   }
-  double tail = 0.0;
-  GB(gb_tail_difference(S.e, comp, GB_DELETION, &tail));
   W /= std::exp(-S.d.beta * tail);
   E.Tail = -tail;
   const double pacc = pre * S.d.comps[comp - 1].ideal_rosenbluth / W;
@@ -327,6 +363,35 @@ void move_reinsertion(Sim& S, int comp, long mol)  // ReinsertionMove::Run, move
   gb_cbmc_result r; int32_t used = 0;
   // insertion leg
   pool_check(S, S.d.n_trial_positions);
+  if(S.fused && !(S.pool_off + S.d.n_trial_positions + 1 + (ms > 1 ? 2 * S.d.n_trial_orientations : 0) >= S.pool_size))
+  {
+    const double u[2] = {S.rng.peek(0), S.rng.peek(1)};
+    gb_move_result m;
+    GB(gb_move_reinsertion(S.e, comp, mol, (int64_t) S.pool_off, u, &m));
+    S.rng.advance(m.uniforms_used); pool_update(S, m.pool_used);
+    if(!m.success) { trace_move(S, "reinsertion", comp, mol, 0, 0.0); return; }
+    double Wn = m.first_bead.rosenbluth, Wo = m.old_first_bead.rosenbluth;
+    Energy En, Eo;
+    En.HGVDW = m.first_bead.energy[0]; En.HGReal = m.first_bead.energy[1]; En.GGVDW = m.first_bead.energy[2]; En.GGReal = m.first_bead.energy[3];
+    Eo.HGVDW = m.old_first_bead.energy[0]; Eo.HGReal = m.old_first_bead.energy[1]; Eo.GGVDW = m.old_first_bead.energy[2]; Eo.GGReal = m.old_first_bead.energy[3];
+    if(ms > 1)
+    {
+      Wn *= m.chain.rosenbluth; Wo *= m.old_chain.rosenbluth;
+      En.HGVDW += m.chain.energy[0]; En.HGReal += m.chain.energy[1]; En.GGVDW += m.chain.energy[2]; En.GGReal += m.chain.energy[3];
+      Eo.HGVDW += m.old_chain.energy[0]; Eo.HGReal += m.old_chain.energy[1]; Eo.GGVDW += m.old_chain.energy[2]; Eo.GGReal += m.old_chain.energy[3];
+    }
+    Energy E = En; E.add(Eo, -1.0);
+    if(!S.d.no_charges && X.has_charge) { E.GGEwald = m.ewald[0]; E.HGEwald = m.ewald[1]; Wn *= std::exp(-S.d.beta * (m.ewald[0] + m.ewald[1])); }
+    const double R = S.rng.uniform();
+    if(!(R >= Wn / Wo))
+    {
+      GB(gb_accept_reinsertion(S.e, comp, mol));
+      X.reins.accepted++; S.running.add(E);
+      trace_move(S, "reinsertion", comp, mol, 1, E.total());
+    }
+    else trace_move(S, "reinsertion", comp, mol, 0, 0.0);
+    return;
+  }
   GB(gb_cbmc_first_bead(S.e, GB_REINSERTION_INSERTION, comp, mol, (int64_t) S.pool_off, S.rng.peek(0), scale, 0.0, -1, -1, nullptr, &r, &used));
   pool_update(S, S.d.n_trial_positions);
   S.rng.advance(used);
@@ -388,18 +453,24 @@ void move_single_body(Sim& S, int comp, long mol, int move_type)   // SingleBody
   const int ms = S.d.comps[comp - 1].ms();
   const double* maxc = move_type == GB_TRANSLATION ? X.max_trans : X.max_rot;
   pool_check(S, ms);
-  GB(gb_single_body_propose(S.e, move_type, comp, mol, maxc, (int64_t) S.pool_off, nullptr));
-  pool_update(S, ms);
-  gb_move_energy d; int32_t overlap = 0;
-  GB(gb_single_body_delta(S.e, comp, 1, 1, &d, &overlap));
+  gb_move_energy d; int32_t overlap = 0; double ew[2] = {0.0, 0.0};
+  if(S.fused)
+  {
+    gb_move_result m;
+    GB(gb_move_single_body(S.e, move_type, comp, mol, maxc, (int64_t) S.pool_off, &m));
+    pool_update(S, ms);
+    d = m.delta; overlap = m.overlap; ew[0] = m.ewald[0]; ew[1] = m.ewald[1];
+  }
+  else
+  {
+    GB(gb_single_body_propose(S.e, move_type, comp, mol, maxc, (int64_t) S.pool_off, nullptr));
+    pool_update(S, ms);
+    GB(gb_single_body_delta(S.e, comp, 1, 1, &d, &overlap));
+    if(!overlap && !S.d.no_charges && X.has_charge) { const double scale[2] = {1.0, 1.0}; GB(gb_ewald_delta(S.e, comp, move_type, 0, scale, ew)); }
+  }
   if(overlap) { trace_move(S, move_type == GB_TRANSLATION ? "translation" : "rotation", comp, mol, 0, 0.0); return; }
   Energy E; E.HHVDW = d.HHVDW; E.HGVDW = d.HGVDW; E.GGVDW = d.GGVDW; E.HHReal = d.HHReal; E.HGReal = d.HGReal; E.GGReal = d.GGReal;
-  if(!S.d.no_charges && X.has_charge)
-  {
-    const double scale[2] = {1.0, 1.0}; double ew[2];
-    GB(gb_ewald_delta(S.e, comp, move_type, 0, scale, ew));
-    E.GGEwald = ew[0]; E.HGEwald = ew[1];
-  }
+  if(!S.d.no_charges && X.has_charge) { E.GGEwald = ew[0]; E.HGEwald = ew[1]; }
   const double pacc = 1.0 * std::exp(-S.d.beta * E.total());
   const double R = S.rng.uniform();
   if(R < pacc)
@@ -619,14 +690,15 @@ void print_energy(const char* tag, const Energy& E)
 
 int main(int argc, char** argv)
 {
-  if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
+  if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
   const std::string dir = argv[1];
-  bool sequential_widom = false; const char* trace_path = nullptr;
+  bool sequential_widom = false, staged = false; const char* trace_path = nullptr;
   long o_init = -1, o_equil = -1, o_prod = -1;
   for(int i = 2; i < argc; i++)
   {
     const std::string a = argv[i];
     if(a == "--sequential-widom") sequential_widom = true;
+    else if(a == "--staged") staged = true;
     else if(a == "--trace" && i + 1 < argc) trace_path = argv[++i];
     else if(a == "--init" && i + 1 < argc) o_init = std::atol(argv[++i]);
     else if(a == "--equil" && i + 1 < argc) o_equil = std::atol(argv[++i]);
@@ -639,6 +711,7 @@ int main(int argc, char** argv)
   if(o_prod >= 0) S.d.prod_cycles = o_prod;
   S.C.assign(1 + S.d.comps.size(), CompState());
   if(trace_path) S.trace = std::fopen(trace_path, "w");
+  S.fused = !staged;
   setup_engine(S);
   setup_probabilities(S);
   std::printf("graspa_b200_mc: %s, %zu framework atoms, %zu adsorbate component(s), alpha %.6f, kmax %d %d %d, volume %.5f, beta %.8f\n",
@@ -647,6 +720,11 @@ int main(int argc, char** argv)
   S.rng.reseed((unsigned) S.d.random_seed);
   S.pool.assign(3 * S.pool_size, 0.0);
   pool_reset(S); S.pool_rounds = 0;
+  // RandomNumber::DeviceRandom runs the debug kernel Aaccess_device_random<<<1,1>>> after the first fill, which overwrites
+  // element 0 of the device pool with {2.3, 4.5, 6.7} and copies the pool back to the host (data_struct.h:1280-1285, 1322-1328):
+  // the very first trial position of a run comes from those three numbers.
+  S.pool[0] = 2.3; S.pool[1] = 4.5; S.pool[2] = 6.7;
+  GB(gb_upload_random_pool(S.e, S.pool.data(), (int64_t) S.pool_size));
   // initial energies + structure factors (Check_Simulation_Energy(INITIAL), fxn_main.h:282-404)
   { gb_move_energy w; GB(gb_total_ewald(S.e, 1, &w)); }
   const Energy E0 = total_energy(S);
@@ -681,8 +759,8 @@ int main(int argc, char** argv)
   const long cycles = S.d.init_cycles + S.d.equil_cycles + S.d.prod_cycles;
   int64_t launches = 0; gb_launch_count(S.e, &launches, 0);
   std::printf("Work took %.6f seconds\n", secs);
-  std::printf("{\"moves\": %ld, \"cycles\": %ld, \"seconds\": %.6f, \"moves_per_s\": %.3f, \"cycles_per_s\": %.3f, \"widom_path\": \"%s\", \"rng_draws\": %llu, \"pool_refills\": %ld, \"kernel_launches\": %lld}\n",
-              S.moves_done, cycles, secs, S.moves_done / secs, cycles / secs, batched ? "batched-exact" : "sequential",
+  std::printf("{\"moves\": %ld, \"cycles\": %ld, \"seconds\": %.6f, \"moves_per_s\": %.3f, \"cycles_per_s\": %.3f, \"widom_path\": \"%s\", \"move_calls\": \"%s\", \"rng_draws\": %llu, \"pool_refills\": %ld, \"kernel_launches\": %lld}\n",
+              S.moves_done, cycles, secs, S.moves_done / secs, cycles / secs, batched ? "batched-exact" : "sequential", S.fused ? "fused" : "staged",
               (unsigned long long) S.rng.consumed(), S.pool_rounds, (long long) launches);
   if(S.trace) std::fclose(S.trace);
   gb_engine_destroy(S.e);

@@ -181,6 +181,36 @@ int  gb_trial_energies(gb_engine* e, int32_t n_trials, int32_t chainsize, const 
                        double* out_energy, int32_t* out_flag);
 
 /* ------------------------------------------------------------------------------------------------
+ * fused moves: everything the kept drivers compute between choosing a move and drawing its acceptance random number,
+ * in ONE call with ONE host round trip (the reference needs 3-6 synchronisations per move).  Stages chain on the
+ * device; a failed stage turns the following ones into no-ops, exactly like the early returns of the drivers.
+ * The caller passes the uniforms the stages WOULD draw (peeked from its stream) and advances its stream by
+ * uniforms_used and its pool offset by pool_used afterwards.  A pool refill (RandomNumber::Check) must not fall
+ * inside the move: across a refill use the stage calls above.
+ *   gb_move_insertion     Insertion_Body            mc_swap_utilities.h:3-133   (swap insertion and Widom)
+ *   gb_move_deletion      Deletion_Body             mc_swap_utilities.h:135-225
+ *   gb_move_reinsertion   ReinsertionMove::Calculate_Insertion/_Deletion/_AdjustRosenbluth  move_struct.h:186-338
+ *   gb_move_single_body   SingleBody_Prepare + SingleBody_Calculation  mc_single_particle.h:10-241
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  gb_cbmc_result first_bead, chain;            /* insertion leg (or the only leg) */
+  gb_cbmc_result old_first_bead, old_chain;    /* retrace leg of a reinsertion */
+  double ewald[2];                             /* {same, 2*cross} with the exclusion term, as GPU_EwaldDifference_General returns */
+  double tail;                                 /* TailCorrectionDifference */
+  gb_move_energy delta;                        /* single body: new - old pair energies */
+  int32_t overlap;                             /* single body: flag[0] */
+  int32_t uniforms_used;                       /* how many of the uniforms passed in the reference would have drawn */
+  int32_t pool_used;                           /* pool entries the reference would have consumed (Random.Update) */
+  int32_t success;                             /* growth succeeded (Rosenbluth > 1e-150) / no overlap */
+} gb_move_result;
+
+int  gb_move_insertion(gb_engine* e, int32_t component, int64_t pool_offset, const double uniforms[2], const double scale[2], gb_move_result* out);
+int  gb_move_deletion(gb_engine* e, int32_t component, int64_t molecule, int64_t pool_offset, const double scale[2], gb_move_result* out);
+int  gb_move_reinsertion(gb_engine* e, int32_t component, int64_t molecule, int64_t pool_offset, const double uniforms[2], gb_move_result* out);
+int  gb_move_single_body(gb_engine* e, int32_t move_type, int32_t component, int64_t molecule, const double max_change[3],
+                         int64_t pool_offset, gb_move_result* out);
+
+/* ------------------------------------------------------------------------------------------------
  * translation / rotation  (replaces get_new_position<<<>>> mc_utilities.h:485-606 and
  *   Calculate_Single_Body_Energy_VDWReal<<<>>> VDW_Coulomb.cu:626-841 + the host sum mc_single_particle.h:183-200)
  * ------------------------------------------------------------------------------------------------ */

@@ -163,7 +163,8 @@ def test_widom_batch_vs_oracle_larger_with_failures(gpu_engine_factory, oracle):
     eng = gpu_engine_factory(box, ff, s, float(z["beta"]), 10, 10)
     eng.upload_structure_factors(z["sf_ads"], z["sf_fw"]); eng.set_exclusion_constants(comp, *ws.excl)
     out, stage, sums = eng.widom_batch(comp, rnd.reshape(-1, 3), uni)
-    assert (stage == rstage).all()
+    # the engine distinguishes "chain failed" (2) from "chain failed with no surviving orientation" (3); the oracle reports 2 for both
+    assert (np.where(stage == 3, 2, stage) == rstage).all()
     assert (rstage > 0).sum() > 0
     assert rel_err(out[:, 0], ref[:, 0], floor=1e-290) < 1e-9
     assert abs(sums[:, 0].sum() / n - ref[:, 0].mean()) <= 1e-9 * ref[:, 0].mean()
