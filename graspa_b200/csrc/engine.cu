@@ -4,6 +4,7 @@
 #include "misc_kernels.cuh"
 #include "pair_kernels.cuh"
 #include "move_kernels.cuh"
+#include "fused_kernel.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -334,6 +335,8 @@ int gb_engine_create(gb_engine** out, int device)
     CUDA_TRY(cudaFuncSetAttribute(k_widom_pair<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_widom_ewald));
     CUDA_TRY(cudaFuncSetAttribute(k_widom_ewald, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_move));
+    CUDA_TRY(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_ewald_delta));
     CUDA_TRY(cudaFuncSetAttribute(k_ewald_delta, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
     e->smem_optin -= 1024;   // head room for static shared memory of the kernels

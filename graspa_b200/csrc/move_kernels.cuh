@@ -24,8 +24,8 @@ struct MoveBufs
   // result slots of 16 doubles: 0 first bead (new), 1 chain (new), 2 first bead (old/retrace), 3 chain (old/retrace),
   // 4 single-body delta, 5 Ewald {same, 2*cross}, 6-7 spare.  Fused move calls read all of them back in one copy.
   __host__ __device__ double* result(int slot = 0) const { return stage_e() + GBK_MV_MAXT * 6 + 16 * slot; }
-  __host__ __device__ double* partial() const { return result(0) + 128; }                                     // [64][16]
-  static size_t doubles() { return 9 * GBK_MV_TRIAL_SLOTS + 36 * GBK_MV_MOL_SLOTS + GBK_MV_MAXT * 6 + 128 + 64 * 16; }
+  __host__ __device__ double* partial() const { return result(0) + 128; }                                     // 4096 doubles of CTA partials
+  static size_t doubles() { return 9 * GBK_MV_TRIAL_SLOTS + 36 * GBK_MV_MOL_SLOTS + GBK_MV_MAXT * 6 + 128 + 4096; }
   static size_t ints() { return GBK_MV_TRIAL_SLOTS + 4 * GBK_MV_MOL_SLOTS + GBK_MV_MAXT + 16; }
 };
 
@@ -53,87 +53,91 @@ struct CbmcArgs
   unsigned int* ticket;
 };
 
-// SelectTrialPosition, mc_widom.h:14-39
-__device__ __forceinline__ int select_trial_position(const double* lb, int n, double uniform)
+// Boltzmann factors, selection and Rosenbluth weight of one CBMC stage, run by ONE WARP (lane t = trial t) of the last CTA:
+// the tail of CBMC_FirstBead_Finish (mc_widom.h:305-383) / Widom_Move_Chain_PARTIAL (:568-611) with
+// Host_sum_Widom_HGGG_SEPARATE (:42-87) in front.  Sums run in trial order like the host code (rosenbluth_warp).
+// result layout: r[0] rosenbluth, r[1] stored_r, r[2..5] energy, r[6..8] selected pos, r[9] success, r[10] selected,
+// r[11] nsurv, r[12] uniform used, r[13] growth still alive (success and running product > 1e-150), r[14] running product
+__device__ __forceinline__ void cbmc_finish_warp(const DevParams& P, const CbmcArgs& A, bool is_chain, double* r)
 {
-  double largest = lb[0];
-  for(int i = 1; i < n; i++) largest = fmax(largest, lb[i]);
-  double sum = 0.0;
-  for(int i = 0; i < n; i++) sum += exp(lb[i] - largest);
-  int selected = 0; double cumw = exp(lb[0] - largest); const double ws = uniform * sum;
-  while(cumw < ws && selected + 1 < n) cumw += exp(lb[++selected] - largest);
-  return selected;
-}
-
-// device restatement of the tail of CBMC_FirstBead_Finish / Widom_Move_Chain_PARTIAL; result layout:
-// r[0] rosenbluth, r[1] stored_r, r[2..5] energy, r[6..8] selected pos, r[9] success, r[10] selected, r[11] nsurv, r[12] uniform used
-__device__ __forceinline__ void cbmc_finish(const DevParams& P, const CbmcArgs& A, bool is_chain, double* r)
-{
+  const int lane = (int) lane_id();
   const double* E = A.B.stage_e(); const int* F = A.B.stage_flag();
-  double rosen[GBK_MV_MAXT]; int idx[GBK_MV_MAXT]; int ns = 0;
-  for(int t = 0; t < A.ntrials; t++)
-    if(!F[t])
-    {
-      // HH terms (a framework component grown against framework components) count with HG: VDW_Coulomb.cu:1232-1235
-      double tot = (E[6 * t] + E[6 * t + 2]) + E[6 * t + 4];
-      if(P.vdw_real_bias) tot += (E[6 * t + 1] + E[6 * t + 3]) + E[6 * t + 5];
-      rosen[ns] = -P.beta * tot; idx[ns] = t; ns++;
-    }
+  double e[6] = {0, 0, 0, 0, 0, 0}; bool surv = false;
+  if(lane < A.ntrials)
+  {
+#pragma unroll
+    for(int k = 0; k < 6; k++) e[k] = E[6 * lane + k];
+    surv = F[lane] == 0;
+  }
+  // HH terms (a framework component grown against framework components) count with HG: VDW_Coulomb.cu:1232-1235
+  double tot = (e[0] + e[2]) + e[4];
+  if(P.vdw_real_bias) tot += (e[1] + e[3]) + e[5];
   const int ty = A.cbmc_type;
   const bool insertion_like = (ty == 0 /*CBMC_INSERTION*/ || ty == 2 /*REINSERTION_INSERTION*/ || (is_chain && ty == 4 /*IDENTITY_SWAP_NEW*/));
   const bool needs_survivor = insertion_like || ty == 4;
-  int good = 0, sel = 0, used = 0; double R = 0.0, Rsel = 0.0;
-  for(int k = 0; k < 13; k++) r[k] = 0.0;
-  r[11] = ns;
-  if(!(needs_survivor && ns == 0))
-  {
-    if(insertion_like) { sel = select_trial_position(rosen, ns, A.uniform); used = 1; }
-    for(int a = 0; a < ns; a++) { const double w = exp(rosen[a]); R += w; if(a == sel) Rsel = w; }
-    good = needs_survivor ? !(R < 1e-150) : 1;
-  }
-  r[12] = used;
+  const RosenResult rr = rosenbluth_warp(-P.beta * tot, surv, A.ntrials, A.uniform, insertion_like);
+  const int ns = rr.nsurv;
+  const bool good = needs_survivor ? (ns > 0 && !(rr.R < 1e-150)) : true;
+  const int sel = rr.sel_lane;
+  const double hgv = __shfl_sync(0xffffffffu, e[2] + e[0], sel), hgr = __shfl_sync(0xffffffffu, e[3] + e[1], sel);
+  const double ggv = __shfl_sync(0xffffffffu, e[4], sel), ggr = __shfl_sync(0xffffffffu, e[5], sel);
+  if(lane != 0) return;
+  for(int k = 0; k < 16; k++) r[k] = 0.0;
+  r[11] = ns; r[12] = (insertion_like && ns > 0) ? 1.0 : 0.0;
   if(!good) return;
   if(ns == 0) { r[9] = 1.0; return; }          // deletion types with every trial overlapping: Rosenbluth 0, Trialindex empty
-  const int real_sel = idx[sel];
-  double avg = R;
+  double avg = rr.R;
   if(!is_chain)
   {
-    if(ty == 2) r[1] = R - Rsel;                                        // StoredR, mc_widom.h:365
-    if(ty == 3) avg += (A.stored_slot >= 0) ? A.B.result(A.stored_slot)[1] : A.stored_r;   // REINSERTION_RETRACE :366
-    if(ty != 4 && ty != 5) avg /= (double) A.norm;                       // :369-370
+    if(ty == 2) r[1] = rr.R_minus_sel;                                                          // StoredR, mc_widom.h:365
+    if(ty == 3) avg += (A.stored_slot >= 0) ? A.B.result(A.stored_slot)[1] : A.stored_r;        // REINSERTION_RETRACE :366
+    if(ty != 4 && ty != 5) avg /= (double) A.norm;                                              // :369-370
   }
-  else avg = R / (double) A.norm;                                         // :601
-  const double hgr = E[6 * real_sel + 3] + E[6 * real_sel + 1], ggr = E[6 * real_sel + 5];
-  if(!P.vdw_real_bias) avg *= exp(-P.beta * (hgr + ggr));                 // :373-377, :603-607
-  r[0] = avg;
-  r[2] = E[6 * real_sel + 2] + E[6 * real_sel]; r[3] = hgr; r[4] = E[6 * real_sel + 4]; r[5] = ggr;
-  r[9] = 1.0; r[10] = real_sel;
+  else avg = rr.R / (double) A.norm;                                                            // :601
+  if(!P.vdw_real_bias) avg *= exp(-P.beta * (hgr + ggr));                                       // :373-377, :603-607
+  r[0] = avg; r[2] = hgv; r[3] = hgr; r[4] = ggv; r[5] = ggr; r[9] = 1.0; r[10] = sel;
 }
 
+// pair energies of the trial group in *T for this CTA's slice of the atom ranges; partial sums go to
+// partial[(group * nsplit + split) * 8 + {HHv,HHr,HGv,HGr,GGv,GGr,flag}]
 template <int CS>
 __device__ __forceinline__ void cbmc_group_energy(const DevParams& P, const PairTables& W, const SysView& S, const SegList& L, const CbmcArgs& A,
-                                                  TrialGroup* T, WarpQueue* Q, double* red, int cs)
+                                                  TrialGroup* T, WarpQueue* Q, double* red, int cs, int group, int split, int nsplit)
 {
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = (int) lane_id();
   double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
-  pair_group_generic<CS>(P, W, S, L, A.comp, A.new_molid, A.excl_comp, A.excl_mol, T, cs, Q + warp, warp, nwarps, e6, flag);
+  pair_group_generic<CS>(P, W, S, L, A.comp, A.new_molid, A.excl_comp, A.excl_mol, T, cs, Q + warp, split * nwarps + warp, nsplit * nwarps, e6, flag);
 #pragma unroll
   for(int k = 0; k < 6; k++) e6[k] = warp_sum(e6[k]);
   flag = __any_sync(0xffffffffu, flag);
   if(lane == 0) { for(int k = 0; k < 6; k++) red[warp * 8 + k] = e6[k]; red[warp * 8 + 6] = flag ? 1.0 : 0.0; }
   __syncthreads();
-  if(threadIdx.x == 0)
+  if(threadIdx.x < 7)
   {
-    double s[7] = {0, 0, 0, 0, 0, 0, 0};
-    for(int w = 0; w < nwarps; w++) for(int k = 0; k < 7; k++) s[k] += red[w * 8 + k];
-    for(int k = 0; k < 6; k++) A.B.stage_e()[6 * blockIdx.x + k] = s[k];
-    A.B.stage_flag()[blockIdx.x] = s[6] > 0.0 ? 1 : 0;
+    double s = 0.0;
+    for(int w = 0; w < nwarps; w++) s += red[w * 8 + threadIdx.x];
+    A.B.partial()[(size_t)(group * nsplit + split) * 8 + threadIdx.x] = s;
   }
 }
 
-// first bead: get_random_trial_position (mc_widom.h:122-213) + energies + CBMC_FirstBead_Finish (:305-383)
+// last CTA: fixed-order sum of the split partials into stage_e / stage_flag (one thread per trial)
+__device__ __forceinline__ void cbmc_collect(const CbmcArgs& A, int nsplit)
+{
+  if(threadIdx.x < A.ntrials)
+  {
+    const volatile double* p = A.B.partial() + (size_t) threadIdx.x * nsplit * 8;
+    double s[7] = {0, 0, 0, 0, 0, 0, 0};
+    for(int k = 0; k < nsplit; k++) for(int j = 0; j < 7; j++) s[j] += p[k * 8 + j];
+    for(int j = 0; j < 6; j++) A.B.stage_e()[6 * threadIdx.x + j] = s[j];
+    A.B.stage_flag()[threadIdx.x] = s[6] > 0.0 ? 1 : 0;
+  }
+  __syncthreads();
+}
+
+// first bead: get_random_trial_position (mc_widom.h:122-213) + energies + CBMC_FirstBead_Finish (:305-383).
+// grid = ntrials * nsplit CTAs: CTA (t, k) evaluates trial t against slice k of the system atoms.
 __global__ void __launch_bounds__(256)
-k_cbmc_first_bead(DevParams P, SysView S, SegList L, CbmcArgs A)
+k_cbmc_first_bead(DevParams P, SysView S, SegList L, CbmcArgs A, int nsplit)
 {
   __shared__ TrialGroup T;
   __shared__ WarpQueue Q[8];
@@ -147,7 +151,7 @@ k_cbmc_first_bead(DevParams P, SysView S, SegList L, CbmcArgs A)
     return;
   }
   stage_erfc_table(P, etab);
-  const int t = blockIdx.x;
+  const int t = blockIdx.x / nsplit, split = blockIdx.x % nsplit;
   if(threadIdx.x == 0)
   {
     const int ty = A.cbmc_type;
@@ -162,50 +166,60 @@ k_cbmc_first_bead(DevParams P, SysView S, SegList L, CbmcArgs A)
     else { const double* r = A.pool3 + 3 * (A.pool_off + t); x = P.cell[0] * r[0]; y = P.cell[4] * r[1]; z = P.cell[8] * r[2]; }
     double fx, fy, fz; to_frac(P, x, y, z, fx, fy, fz);
     const double q = A.C.q[start]; const int type = A.C.type[start];
-    A.B.tr(0)[t] = x; A.B.tr(1)[t] = y; A.B.tr(2)[t] = z; A.B.tr(3)[t] = fx; A.B.tr(4)[t] = fy; A.B.tr(5)[t] = fz;
-    A.B.tr(6)[t] = q; A.B.tr(7)[t] = scale; A.B.tr(8)[t] = scoul; A.B.tr_type()[t] = type;
+    if(split == 0)
+    {
+      A.B.tr(0)[t] = x; A.B.tr(1)[t] = y; A.B.tr(2)[t] = z; A.B.tr(3)[t] = fx; A.B.tr(4)[t] = fy; A.B.tr(5)[t] = fz;
+      A.B.tr(6)[t] = q; A.B.tr(7)[t] = scale; A.B.tr(8)[t] = scoul; A.B.tr_type()[t] = type;
+    }
     T.fx[0] = fx; T.fy[0] = fy; T.fz[0] = fz; T.q[0] = q * scoul; T.scale[0] = scale; T.type[0] = type; T.slot[0] = 0;
   }
   __syncthreads();
   PairTables W; W.etab = etab; W.ffp = P.ffA; W.unit = false;
-  cbmc_group_energy<1>(P, W, S, L, A, &T, Q, red, 1);
+  cbmc_group_energy<1>(P, W, S, L, A, &T, Q, red, 1, t, split, nsplit);
+  __syncthreads();
   if(threadIdx.x == 0) { __threadfence(); last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1); }
   __syncthreads();
-  if(last && threadIdx.x == 0)
+  if(!last) return;
+  __threadfence();
+  cbmc_collect(A, nsplit);
+  if(threadIdx.x < 32)
   {
-    __threadfence();
     double* r = A.B.result(A.rslot);
-    cbmc_finish(P, A, false, r);
-    r[14] = r[0];                                                   // running Rosenbluth product of the growth
-    r[13] = (r[9] != 0.0 && r[0] > 1e-150) ? 1.0 : 0.0;             // "Rosenbluth <= 1e-150 -> SuccessConstruction = false", mc_swap_utilities.h:21
-    if(r[9] != 0.0 && r[11] > 0.0)
+    cbmc_finish_warp(P, A, false, r);
+    if(threadIdx.x == 0)
     {
-      const int s = (int) r[10];
-      r[6] = A.B.tr(0)[s]; r[7] = A.B.tr(1)[s]; r[8] = A.B.tr(2)[s];
-      // Mol.pos[0] = NewMol.pos[FirstBeadTrial] etc., mc_widom.h:230-241
-      for(int k = 0; k < 9; k++) A.B.mol(GBK_BUF_GROWN, k)[0] = A.B.tr(k)[s];
-      A.B.mol_type(GBK_BUF_GROWN)[0] = A.B.tr_type()[s];
+      r[14] = r[0];                                                   // running Rosenbluth product of the growth
+      r[13] = (r[9] != 0.0 && r[0] > 1e-150) ? 1.0 : 0.0;             // "Rosenbluth <= 1e-150 -> SuccessConstruction = false", mc_swap_utilities.h:21
+      if(r[9] != 0.0 && r[11] > 0.0)
+      {
+        const int s = (int) r[10];
+        r[6] = A.B.tr(0)[s]; r[7] = A.B.tr(1)[s]; r[8] = A.B.tr(2)[s];
+        // Mol.pos[0] = NewMol.pos[FirstBeadTrial] etc., mc_widom.h:230-241
+        for(int k = 0; k < 9; k++) A.B.mol(GBK_BUF_GROWN, k)[0] = A.B.tr(k)[s];
+        A.B.mol_type(GBK_BUF_GROWN)[0] = A.B.tr_type()[s];
+      }
+      *A.ticket = 0u;
     }
-    *A.ticket = 0u;
   }
 }
 
 // chain: get_random_trial_orientation (mc_widom.h:215-303) + energies + the tail of Widom_Move_Chain_PARTIAL (:568-611)
 __global__ void __launch_bounds__(256)
-k_cbmc_chain(DevParams P, SysView S, SegList L, CbmcArgs A)
+k_cbmc_chain(DevParams P, SysView S, SegList L, CbmcArgs A, int nsplit)
 {
   __shared__ TrialGroup T;
   __shared__ WarpQueue Q[8];
   __shared__ double red[8 * 8];
   __shared__ double etab[(GBK_ERFC_DEG + 1) * GBK_ERFC_NINT];
   __shared__ bool last;
+  __shared__ int sel_s;
   if(A.dep_slot >= 0 && A.B.result(A.dep_slot)[13] == 0.0)
   {
     if(blockIdx.x == 0 && threadIdx.x < 16) A.B.result(A.rslot)[threadIdx.x] = 0.0;
     return;
   }
   stage_erfc_table(P, etab);
-  const int o = blockIdx.x, cs = A.ms - 1;
+  const int o = blockIdx.x / nsplit, split = blockIdx.x % nsplit, cs = A.ms - 1;
   if(threadIdx.x < cs)
   {
     const int a = threadIdx.x, ty = A.cbmc_type;
@@ -225,38 +239,43 @@ k_cbmc_chain(DevParams P, SysView S, SegList L, CbmcArgs A)
     const double scale = A.B.mol(GBK_BUF_GROWN, 7)[0], scoul = A.B.mol(GBK_BUF_GROWN, 8)[0];             // Chosenscale(Coul)
     const double q = A.C.q[start + a]; const int type = A.C.type[start + a];
     const int j = o * cs + a;
-    A.B.tr(0)[j] = x; A.B.tr(1)[j] = y; A.B.tr(2)[j] = z; A.B.tr(3)[j] = fx; A.B.tr(4)[j] = fy; A.B.tr(5)[j] = fz;
-    A.B.tr(6)[j] = q; A.B.tr(7)[j] = scale; A.B.tr(8)[j] = scoul; A.B.tr_type()[j] = type;
+    if(split == 0)
+    {
+      A.B.tr(0)[j] = x; A.B.tr(1)[j] = y; A.B.tr(2)[j] = z; A.B.tr(3)[j] = fx; A.B.tr(4)[j] = fy; A.B.tr(5)[j] = fz;
+      A.B.tr(6)[j] = q; A.B.tr(7)[j] = scale; A.B.tr(8)[j] = scoul; A.B.tr_type()[j] = type;
+    }
     T.fx[a] = fx; T.fy[a] = fy; T.fz[a] = fz; T.q[a] = q * scoul; T.scale[a] = scale; T.type[a] = type; T.slot[a] = 0;
   }
   __syncthreads();
   PairTables W; W.etab = etab; W.ffp = P.ffA; W.unit = false;
-  if(cs == 1) cbmc_group_energy<1>(P, W, S, L, A, &T, Q, red, cs);
-  else if(cs == 2) cbmc_group_energy<2>(P, W, S, L, A, &T, Q, red, cs);
-  else cbmc_group_energy<0>(P, W, S, L, A, &T, Q, red, cs);
+  if(cs == 1) cbmc_group_energy<1>(P, W, S, L, A, &T, Q, red, cs, o, split, nsplit);
+  else if(cs == 2) cbmc_group_energy<2>(P, W, S, L, A, &T, Q, red, cs, o, split, nsplit);
+  else cbmc_group_energy<0>(P, W, S, L, A, &T, Q, red, cs, o, split, nsplit);
+  __syncthreads();
   if(threadIdx.x == 0) { __threadfence(); last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1); }
   __syncthreads();
-  if(last)
+  if(!last) return;
+  __threadfence();
+  cbmc_collect(A, nsplit);
+  if(threadIdx.x < 32)
   {
-    __shared__ int sel_s;
+    double* r = A.B.result(A.rslot);
+    cbmc_finish_warp(P, A, true, r);
     if(threadIdx.x == 0)
     {
-      __threadfence();
-      double* r = A.B.result(A.rslot);
-      cbmc_finish(P, A, true, r);
       r[14] = (A.dep_slot >= 0 ? A.B.result(A.dep_slot)[14] : 1.0) * r[0];   // CBMC.Rosenbluth *= averagedRosen, mc_widom.h:611
       r[13] = (r[9] != 0.0 && r[14] > 1e-150) ? 1.0 : 0.0;                  // mc_swap_utilities.h:32
       sel_s = (r[9] != 0.0 && r[11] > 0.0) ? (int) r[10] : -1;
       *A.ticket = 0u;
     }
-    __syncthreads();
-    // selected orientation joins the first bead in the grown-molecule buffer
-    if(sel_s >= 0 && threadIdx.x < cs)
-    {
-      const int j = sel_s * cs + threadIdx.x;
-      for(int k = 0; k < 9; k++) A.B.mol(GBK_BUF_GROWN, k)[1 + threadIdx.x] = A.B.tr(k)[j];
-      A.B.mol_type(GBK_BUF_GROWN)[1 + threadIdx.x] = A.B.tr_type()[j];
-    }
+  }
+  __syncthreads();
+  // selected orientation joins the first bead in the grown-molecule buffer
+  if(sel_s >= 0 && threadIdx.x < cs)
+  {
+    const int j = sel_s * cs + threadIdx.x;
+    for(int k = 0; k < 9; k++) A.B.mol(GBK_BUF_GROWN, k)[1 + threadIdx.x] = A.B.tr(k)[j];
+    A.B.mol_type(GBK_BUF_GROWN)[1 + threadIdx.x] = A.B.tr_type()[j];
   }
 }
 
@@ -284,10 +303,8 @@ struct ProposeArgs
   CompView C; MoveBufs B; int new_molid;
 };
 
-__global__ void k_single_propose(DevParams P, ProposeArgs A)
+__device__ __forceinline__ void propose_atom(const DevParams& P, const ProposeArgs& A, int i)
 {
-  const int i = threadIdx.x;
-  if(i >= A.ms) return;
   const long long rp = A.start + i;
   const double x = A.C.x[rp], y = A.C.y[rp], z = A.C.z[rp];
   const double* R = A.pool3 + 3 * A.pool_index;
@@ -331,7 +348,6 @@ __global__ void k_single_propose(DevParams P, ProposeArgs A)
   const double q = A.C.q[rp], sc = A.C.scale[rp], scc = A.C.scoul[rp]; const int ty = A.C.type[rp];
   double fx, fy, fz;
   to_frac(P, nx, ny, nz, fx, fy, fz);
-  double* const* dummy = nullptr; (void) dummy;
   A.B.mol(GBK_BUF_NEW, 0)[i] = nx; A.B.mol(GBK_BUF_NEW, 1)[i] = ny; A.B.mol(GBK_BUF_NEW, 2)[i] = nz;
   A.B.mol(GBK_BUF_NEW, 3)[i] = fx; A.B.mol(GBK_BUF_NEW, 4)[i] = fy; A.B.mol(GBK_BUF_NEW, 5)[i] = fz;
   A.B.mol(GBK_BUF_NEW, 6)[i] = q; A.B.mol(GBK_BUF_NEW, 7)[i] = sc; A.B.mol(GBK_BUF_NEW, 8)[i] = scc; A.B.mol_type(GBK_BUF_NEW)[i] = ty;
@@ -339,6 +355,11 @@ __global__ void k_single_propose(DevParams P, ProposeArgs A)
   A.B.mol(GBK_BUF_OLD, 0)[i] = x; A.B.mol(GBK_BUF_OLD, 1)[i] = y; A.B.mol(GBK_BUF_OLD, 2)[i] = z;
   A.B.mol(GBK_BUF_OLD, 3)[i] = fx; A.B.mol(GBK_BUF_OLD, 4)[i] = fy; A.B.mol(GBK_BUF_OLD, 5)[i] = fz;
   A.B.mol(GBK_BUF_OLD, 6)[i] = q; A.B.mol(GBK_BUF_OLD, 7)[i] = sc; A.B.mol(GBK_BUF_OLD, 8)[i] = scc; A.B.mol_type(GBK_BUF_OLD)[i] = ty;
+}
+
+__global__ void k_single_propose(DevParams P, ProposeArgs A)
+{
+  if((int) threadIdx.x < A.ms) propose_atom(P, A, threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
