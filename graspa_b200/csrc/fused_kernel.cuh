@@ -3,9 +3,16 @@
 // A single GCMC move is a chain of small dependent stages (first bead -> selection -> chain growth -> selection ->
 // Ewald delta).  The reference runs each stage as its own launch followed by cudaDeviceSynchronize and a host-side sum
 // (3-6 host round trips per move); what bounds GCMC cycles/s is therefore latency, not arithmetic.  Here the whole move
-// is one launch of a small co-resident grid: the stages are separated by a device-wide barrier (all CTAs are resident,
-// grid <= number of SMs), selections run on the device (last stage's results stay in L2), and the host reads one 1 KB
-// result block.  Covers Insertion_Body / Deletion_Body (mc_swap_utilities.h:3-225), the reinsertion growth + retrace
+// is one launch of a small co-resident grid (grid <= number of SMs):
+//   * everything that does not depend on a selection runs in the FIRST stage: a deletion evaluates its first-bead
+//     trials, its orientations and its Ewald delta together; a reinsertion evaluates the retrace of the old molecule
+//     next to the first-bead trials of the new one; a translation/rotation evaluates new, old and Ewald at once;
+//   * stages are separated by a flag barrier (one store + one poll per CTA, no atomics);
+//   * after a barrier EVERY CTA reduces the stage's partial sums and runs the Boltzmann selection redundantly
+//     (bitwise identical arithmetic), so no CTA waits for another one to publish the selected trial;
+//   * CTA 0 stores the result block straight into pinned host memory and raises a sequence flag the host polls.
+// Barriers per move: translation/rotation 1, deletion 1, insertion 3 (2 for single-bead molecules), reinsertion 3.
+// Covers Insertion_Body / Deletion_Body (mc_swap_utilities.h:3-225), the reinsertion growth + retrace
 // (move_struct.h:186-338) and SingleBody_Prepare + SingleBody_Calculation (mc_single_particle.h:10-241).
 #pragma once
 #include "common.cuh"
@@ -14,6 +21,9 @@
 #include "move_kernels.cuh"
 
 enum { GBF_INSERTION = 0, GBF_DELETION = 1, GBF_REINSERTION = 2, GBF_SINGLE = 3 };
+#define GBF_MAX_GROUPS 96           // trial groups of one stage: ntrials + 1 + norient <= 65
+#define GBF_PART_HALF 2048          // doubles per parity half of MoveBufs::partial()
+#define GBF_PART_EWALD 1536         // Ewald CTA partials start here inside a half (pair partials: groups * nsplit * 8 <= 1536)
 
 struct FusedArgs
 {
@@ -22,27 +32,51 @@ struct FusedArgs
   double u0, u1, scale0, scale1, maxc[3];
   int ntrials, norient, nmol;             // nmol = NumberOfMolecule_for_Component (MolID of an inserted molecule)
   int do_ewald, check_overlap, framework_moved;
+  int natoms;                             // atoms in the live ranges of L
   const double* __restrict__ pool3;
   CompView C; MoveBufs B;
   SegList L;                              // live ranges with the kinds of THIS move
   KTable K; const double* same_sf; const double* cross_sf; double* temp_sf;
-  unsigned int* bar;                      // device-wide barrier counter, left at 0 by the kernel
+  unsigned long long* flags;              // one barrier flag per CTA, monotonic across launches
+  unsigned long long epoch;               // 8 * sequence number of this launch
+  double* host_result;                    // pinned host memory (UVA): the 8 result slots are stored there directly ...
+  unsigned long long* host_flag;          // ... followed by this move's sequence number, which the host polls
+  unsigned long long seq;
 };
 
-// all CTAs of the grid are co-resident (the host launches at most one CTA per SM)
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& phase)
+#ifdef GBK_PHASE_TIMING
+#include <cstdio>
+__device__ long long g_marks[64];
+__device__ int g_nmarks;
+#define GBK_MARK() do { if(blockIdx.x == 0 && threadIdx.x == 0) g_marks[g_nmarks++] = clock64(); } while(0)
+#else
+#define GBK_MARK() do { } while(0)
+#endif
+
+// all CTAs of the grid are co-resident (the host launches at most one CTA per SM, <= 256 CTAs): CTA b raises flag b,
+// thread t of every CTA waits for flag t
+__device__ __forceinline__ void grid_barrier(const FusedArgs& F, unsigned int& phase)
 {
+  phase++;
+  const unsigned long long want = F.epoch + phase;
   __syncthreads();
-  if(threadIdx.x == 0)
+  if(threadIdx.x == 0) { __threadfence(); *reinterpret_cast<volatile unsigned long long*>(F.flags + blockIdx.x) = want; }
+  if(threadIdx.x < gridDim.x)
   {
-    phase++;
-    __threadfence();
-    atomicAdd(counter, 1u);
-    const unsigned int target = phase * gridDim.x;
-    while(atomicAdd(counter, 0u) < target) { }
+    const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(F.flags + threadIdx.x);
+    while(*f < want) { }
     __threadfence();
   }
   __syncthreads();
+  GBK_MARK();
+}
+
+struct SmemMol { double a[9][GBK_MV_MOL_SLOTS]; int type[GBK_MV_MOL_SLOTS]; };   // x y z fx fy fz q scale scoul
+
+__device__ __forceinline__ void put_atom(SmemMol& M, int i, const AtomRec& r)
+{
+  M.a[0][i] = r.x; M.a[1][i] = r.y; M.a[2][i] = r.z; M.a[3][i] = r.fx; M.a[4][i] = r.fy; M.a[5][i] = r.fz;
+  M.a[6][i] = r.q; M.a[7][i] = r.scale; M.a[8][i] = r.scoul; M.type[i] = r.type;
 }
 
 struct FusedSmem
@@ -51,197 +85,267 @@ struct FusedSmem
   WarpQueue Q[8];
   double red[8 * 16];
   double etab[(GBK_ERFC_DEG + 1) * GBK_ERFC_NINT];
+  double E[GBF_MAX_GROUPS * 6]; int Fl[GBF_MAX_GROUPS];     // collected trial energies / overlap flags of the last stage
+  double Ekeep[33 * 6]; int Fkeep[33];                      // reinsertion: the retrace groups of stage 1, finished at the end
+  double res[8 * 16];                                       // the result slots (MoveBufs::result layout)
+  SmemMol mN, mO;                                           // molecule being grown / proposed, and its old image
 };
 
-__device__ __forceinline__ int fused_nsplit(const SegList& L, int ngroups)
+// one segment of a stage: n trial groups of one CBMC type
+struct StageSeg { int type, chain, n; long long pool_off; };
+
+__device__ __forceinline__ double* part_half(const FusedArgs& F, int par) { return F.B.partial() + (size_t) par * GBF_PART_HALF; }
+
+__device__ __forceinline__ int stage_nsplit(const FusedArgs& F, int ngroups)
 {
-  int natoms = 0; for(int s = 0; s < L.nseg; s++) natoms += L.count[s];
-  int ns = (natoms + 511) / 512;
-  const int cap = max(1, min(4096 / (8 * max(ngroups, 1)), (int) (2 * gridDim.x) / max(ngroups, 1)));
+  const int ns = (F.natoms + 255) / 256;                   // one 32-atom iteration per warp if the grid allows it
+  const int cap = max(1, min(GBF_PART_EWALD / (8 * max(ngroups, 1)), (int) gridDim.x / max(ngroups, 1)));
   return max(1, min(ns, cap));
 }
 
-// one CBMC stage (first bead or chain) of growth type `type`
-__device__ __forceinline__ void fused_cbmc_stage(const DevParams& P, const SysView& S, const FusedArgs& F, FusedSmem* sm, const PairTables& W,
-                                                 bool chain, int type, long long pool_off, double uniform, int rslot, int dep_slot, int stored_slot,
-                                                 unsigned int& phase)
+// get_random_trial_position, mc_widom.h:122-213
+__device__ __forceinline__ AtomRec first_bead_atom(const DevParams& P, const FusedArgs& F, int type, int g, long long pool_off)
 {
-  CbmcArgs A; memset(&A, 0, sizeof(A));
-  A.cbmc_type = type; A.comp = F.comp; A.ms = F.ms; A.molecule = F.molecule;
-  if(chain) { A.ntrials = F.norient; A.norm = F.norient; }
-  else { A.ntrials = (type == 3 || type == 4 || type == 5) ? 1 : F.ntrials; A.norm = F.ntrials; }
   const bool insertion_like = (type == 0 || type == 4);
-  A.new_molid = insertion_like ? F.nmol : (int) F.molecule;
-  A.excl_comp = -1; A.excl_mol = -1;
-  A.pool_off = pool_off; A.pool3 = F.pool3; A.uniform = uniform; A.scale = F.scale0; A.scale_coul = F.scale1;
-  A.C = F.C; A.B = F.B; A.rslot = rslot; A.dep_slot = dep_slot; A.stored_slot = stored_slot;
-  const bool run = dep_slot < 0 || F.B.result(dep_slot)[13] != 0.0;
-  const int cs = chain ? F.ms - 1 : 1;
-  const int nsplit = fused_nsplit(F.L, A.ntrials);
-  if(run)
-  {
-    for(int w = blockIdx.x; w < A.ntrials * nsplit; w += gridDim.x)
-    {
-      const int g = w / nsplit, split = w % nsplit;
-      __syncthreads();
-      if(!chain)
-      {
-        if(threadIdx.x == 0)
-        {
-          const long long start = insertion_like ? 0 : A.molecule * A.ms;
-          double scale = A.scale, scoul = A.scale_coul;
-          if(!insertion_like) { scale = A.C.scale[start]; scoul = A.C.scoul[start]; }
-          double x, y, z;
-          const bool existing = (type == 1 || type == 3 || type == 5) && g == 0;
-          if(existing) { x = A.C.x[start]; y = A.C.y[start]; z = A.C.z[start]; }
-          else { const double* r = A.pool3 + 3 * (A.pool_off + g); x = P.cell[0] * r[0]; y = P.cell[4] * r[1]; z = P.cell[8] * r[2]; }
-          double fx, fy, fz; to_frac(P, x, y, z, fx, fy, fz);
-          const double q = A.C.q[start]; const int ty = A.C.type[start];
-          if(split == 0)
-          {
-            A.B.tr(0)[g] = x; A.B.tr(1)[g] = y; A.B.tr(2)[g] = z; A.B.tr(3)[g] = fx; A.B.tr(4)[g] = fy; A.B.tr(5)[g] = fz;
-            A.B.tr(6)[g] = q; A.B.tr(7)[g] = scale; A.B.tr(8)[g] = scoul; A.B.tr_type()[g] = ty;
-          }
-          sm->T.fx[0] = fx; sm->T.fy[0] = fy; sm->T.fz[0] = fz; sm->T.q[0] = q * scoul; sm->T.scale[0] = scale; sm->T.type[0] = ty; sm->T.slot[0] = 0;
-        }
-      }
-      else if(threadIdx.x < cs)
-      {
-        const int a = threadIdx.x;
-        const long long start = (insertion_like ? 0 : A.molecule * A.ms) + 1;
-        const double fbx = A.B.mol(GBK_BUF_GROWN, 0)[0], fby = A.B.mol(GBK_BUF_GROWN, 1)[0], fbz = A.B.mol(GBK_BUF_GROWN, 2)[0];
-        double vx = A.C.x[1 + a] - A.C.x[0], vy = A.C.y[1 + a] - A.C.y[0], vz = A.C.z[1 + a] - A.C.z[0];
-        double x, y, z;
-        if((type == 1 || type == 3 || type == 5) && g == 0) { x = A.C.x[start + a]; y = A.C.y[start + a]; z = A.C.z[start + a]; }
-        else
-        {
-          const double* r = A.pool3 + 3 * (A.pool_off + g);
-          rotate_quaternion(vx, vy, vz, r[0], r[1], r[2]);
-          x = fbx + vx; y = fby + vy; z = fbz + vz;
-        }
-        double fx, fy, fz; to_frac(P, x, y, z, fx, fy, fz);
-        const double scale = A.B.mol(GBK_BUF_GROWN, 7)[0], scoul = A.B.mol(GBK_BUF_GROWN, 8)[0];
-        const double q = A.C.q[start + a]; const int ty = A.C.type[start + a];
-        const int j = g * cs + a;
-        if(split == 0)
-        {
-          A.B.tr(0)[j] = x; A.B.tr(1)[j] = y; A.B.tr(2)[j] = z; A.B.tr(3)[j] = fx; A.B.tr(4)[j] = fy; A.B.tr(5)[j] = fz;
-          A.B.tr(6)[j] = q; A.B.tr(7)[j] = scale; A.B.tr(8)[j] = scoul; A.B.tr_type()[j] = ty;
-        }
-        sm->T.fx[a] = fx; sm->T.fy[a] = fy; sm->T.fz[a] = fz; sm->T.q[a] = q * scoul; sm->T.scale[a] = scale; sm->T.type[a] = ty; sm->T.slot[a] = 0;
-      }
-      __syncthreads();
-      if(cs == 1)      cbmc_group_energy<1>(P, W, S, F.L, A, &sm->T, sm->Q, sm->red, cs, g, split, nsplit);
-      else if(cs == 2) cbmc_group_energy<2>(P, W, S, F.L, A, &sm->T, sm->Q, sm->red, cs, g, split, nsplit);
-      else             cbmc_group_energy<0>(P, W, S, F.L, A, &sm->T, sm->Q, sm->red, cs, g, split, nsplit);
-    }
-  }
-  grid_barrier(F.bar, phase);
-  if(blockIdx.x == 0)
-  {
-    double* r = A.B.result(rslot);
-    if(!run) { if(threadIdx.x < 16) r[threadIdx.x] = 0.0; }
-    else
-    {
-      cbmc_collect(A, nsplit);
-      __shared__ int sel_s;
-      if(threadIdx.x < 32)
-      {
-        cbmc_finish_warp(P, A, chain, r);
-        if(threadIdx.x == 0)
-        {
-          r[14] = ((chain && dep_slot >= 0) ? A.B.result(dep_slot)[14] : 1.0) * r[0];
-          r[13] = (r[9] != 0.0 && r[14] > 1e-150) ? 1.0 : 0.0;
-          sel_s = (r[9] != 0.0 && r[11] > 0.0) ? (int) r[10] : -1;
-          if(!chain && sel_s >= 0)
-          {
-            r[6] = A.B.tr(0)[sel_s]; r[7] = A.B.tr(1)[sel_s]; r[8] = A.B.tr(2)[sel_s];
-            for(int k = 0; k < 9; k++) A.B.mol(GBK_BUF_GROWN, k)[0] = A.B.tr(k)[sel_s];
-            A.B.mol_type(GBK_BUF_GROWN)[0] = A.B.tr_type()[sel_s];
-          }
-        }
-      }
-      __syncthreads();
-      if(chain && sel_s >= 0 && threadIdx.x < cs)
-      {
-        const int j = sel_s * cs + threadIdx.x;
-        for(int k = 0; k < 9; k++) A.B.mol(GBK_BUF_GROWN, k)[1 + threadIdx.x] = A.B.tr(k)[j];
-        A.B.mol_type(GBK_BUF_GROWN)[1 + threadIdx.x] = A.B.tr_type()[j];
-      }
-      // reinsertion: the grown molecule is kept in tempMolStorage while the old one is retraced (StoreNewLocation_Reinsertion)
-      __syncthreads();
-      if(type == 2 && (chain || F.ms == 1) && threadIdx.x < F.ms)
-      {
-        for(int k = 0; k < 9; k++) A.B.mol(GBK_BUF_TEMP, k)[threadIdx.x] = A.B.mol(GBK_BUF_GROWN, k)[threadIdx.x];
-        A.B.mol_type(GBK_BUF_TEMP)[threadIdx.x] = A.B.mol_type(GBK_BUF_GROWN)[threadIdx.x];
-      }
-    }
-  }
-  grid_barrier(F.bar, phase);
+  const long long start = insertion_like ? 0 : F.molecule * F.ms;
+  AtomRec r; r.scale = F.scale0; r.scoul = F.scale1;
+  if(!insertion_like) { r.scale = F.C.scale[start]; r.scoul = F.C.scoul[start]; }
+  const bool existing = (type == 1 || type == 3 || type == 5) && g == 0;
+  if(existing) { r.x = F.C.x[start]; r.y = F.C.y[start]; r.z = F.C.z[start]; }
+  else { const double* u = F.pool3 + 3 * (pool_off + g); r.x = P.cell[0] * u[0]; r.y = P.cell[4] * u[1]; r.z = P.cell[8] * u[2]; }
+  to_frac(P, r.x, r.y, r.z, r.fx, r.fy, r.fz);
+  r.q = F.C.q[start]; r.type = F.C.type[start];
+  return r;
 }
 
-// Ewald Fourier delta of [old atoms | new atoms] taken from molecule buffers / component slots; result slot 5
-__device__ __forceinline__ void fused_ewald_stage(const DevParams& P, const FusedArgs& F, unsigned char* dyn, double* red, int old_src, long long old_start,
-                                                  int nold, int new_buf, int nnew, const double* dep, unsigned int& phase)
+// get_random_trial_orientation, mc_widom.h:215-303: atom 1 + a of orientation g around the first bead (fbx, fby, fbz)
+__device__ __forceinline__ AtomRec chain_atom(const DevParams& P, const FusedArgs& F, int type, int g, int a, long long pool_off,
+                                              double fbx, double fby, double fbz, double scale, double scoul)
 {
-  double* res = F.B.result(5);
-  const bool run = (dep == nullptr || dep[0] != 0.0);
-  const int n = nold + nnew;
-  if(run)
+  const bool insertion_like = (type == 0 || type == 4);
+  const long long start = (insertion_like ? 0 : F.molecule * F.ms) + 1;        // start_position, mc_widom.h:536-556
+  double vx = F.C.x[1 + a] - F.C.x[0], vy = F.C.y[1 + a] - F.C.y[0], vz = F.C.z[1 + a] - F.C.z[0];   // :256
+  AtomRec r;
+  if((type == 1 || type == 3 || type == 5) && g == 0) { r.x = F.C.x[start + a]; r.y = F.C.y[start + a]; r.z = F.C.z[start + a]; }
+  else
   {
-    const int kx1 = P.kmax[0] + 1, ky1 = P.kmax[1] + 1, kz1 = P.kmax[2] + 1;
-    cplx* ex = reinterpret_cast<cplx*>(dyn);
-    cplx* ey = ex + (size_t) n * kx1; cplx* ez = ey + (size_t) n * ky1;
-    double* qeff = reinterpret_cast<double*>(ez + (size_t) n * kz1);
-    double* pos3 = qeff + n;
+    const double* u = F.pool3 + 3 * (pool_off + g);
+    rotate_quaternion(vx, vy, vz, u[0], u[1], u[2]);
+    r.x = fbx + vx; r.y = fby + vy; r.z = fbz + vz;
+  }
+  to_frac(P, r.x, r.y, r.z, r.fx, r.fy, r.fz);
+  r.scale = scale; r.scoul = scoul;
+  r.q = F.C.q[start + a]; r.type = F.C.type[start + a];
+  return r;
+}
+
+// first bead the orientations of `type` are grown around: the selected trial (growth) or the existing atom (deletion / retrace)
+__device__ __forceinline__ void chain_anchor(const FusedArgs& F, const FusedSmem* sm, int type, double& x, double& y, double& z, double& scale, double& scoul)
+{
+  if(type == 1 || type == 3 || type == 5)
+  {
+    const long long start = F.molecule * F.ms;
+    x = F.C.x[start]; y = F.C.y[start]; z = F.C.z[start]; scale = F.C.scale[start]; scoul = F.C.scoul[start];
+  }
+  else { x = sm->mN.a[0][0]; y = sm->mN.a[1][0]; z = sm->mN.a[2][0]; scale = sm->mN.a[7][0]; scoul = sm->mN.a[8][0]; }
+}
+
+__device__ __forceinline__ void set_trial(TrialGroup& T, int a, const AtomRec& r)
+{
+  T.fx[a] = r.fx; T.fy[a] = r.fy; T.fz[a] = r.fz; T.q[a] = r.q * r.scoul; T.scale[a] = r.scale; T.type[a] = r.type; T.slot[a] = 0;
+}
+
+// pair energies of the trial group in sm->T against slice `split` of the live ranges; 7 partial sums to out8
+template <int CS>
+__device__ __forceinline__ void group_energy(const DevParams& P, const PairTables& W, const SysView& S, const FusedArgs& F, FusedSmem* sm,
+                                             int new_molid, int cs, int split, int nsplit, double* out8)
+{
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = (int) lane_id();
+  double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
+  pair_group_generic<CS>(P, W, S, F.L, F.comp, new_molid, -1, -1, &sm->T, cs, sm->Q + warp, split * nwarps + warp, nsplit * nwarps, e6, flag);
+#pragma unroll
+  for(int k = 0; k < 6; k++) e6[k] = warp_sum(e6[k]);
+  flag = __any_sync(0xffffffffu, flag);
+  if(lane == 0) { for(int k = 0; k < 6; k++) sm->red[warp * 8 + k] = e6[k]; sm->red[warp * 8 + 6] = flag ? 1.0 : 0.0; }
+  __syncthreads();
+  if(threadIdx.x < 7)
+  {
+    double s = 0.0;
+    for(int w = 0; w < nwarps; w++) s += sm->red[w * 8 + threadIdx.x];
+    out8[threadIdx.x] = s;
+  }
+}
+
+// this CTA's share of the (group, split) items of a stage made of up to 3 segments
+__device__ __forceinline__ void run_stage(const DevParams& P, const SysView& S, const FusedArgs& F, FusedSmem* sm, const PairTables& W,
+                                          const StageSeg* segs, int nseg, int ngroups, int nsplit, int par)
+{
+  double* part = part_half(F, par);
+  for(int w = blockIdx.x; w < ngroups * nsplit; w += gridDim.x)
+  {
+    const int gg = w / nsplit, split = w % nsplit;
+    int g = gg, si = 0;
+    while(si + 1 < nseg && g >= segs[si].n) { g -= segs[si].n; si++; }
+    const int type = segs[si].type; const bool chain = segs[si].chain != 0; const long long off = segs[si].pool_off;
+    const int cs = chain ? F.ms - 1 : 1;
     __syncthreads();
-    for(int i = threadIdx.x; i < n; i += blockDim.x)
+    if(!chain) { if(threadIdx.x == 0) set_trial(sm->T, 0, first_bead_atom(P, F, type, g, off)); }
+    else if((int) threadIdx.x < cs)
     {
-      if(i < nold)
-      {
-        if(old_src < 0) { pos3[3 * i] = F.C.x[old_start + i]; pos3[3 * i + 1] = F.C.y[old_start + i]; pos3[3 * i + 2] = F.C.z[old_start + i]; qeff[i] = F.C.scoul[old_start + i] * F.C.q[old_start + i]; }
-        else { pos3[3 * i] = F.B.mol(old_src, 0)[i]; pos3[3 * i + 1] = F.B.mol(old_src, 1)[i]; pos3[3 * i + 2] = F.B.mol(old_src, 2)[i]; qeff[i] = F.B.mol(old_src, 8)[i] * F.B.mol(old_src, 6)[i]; }
-      }
-      else
-      {
-        const int j = i - nold;
-        pos3[3 * i] = F.B.mol(new_buf, 0)[j]; pos3[3 * i + 1] = F.B.mol(new_buf, 1)[j]; pos3[3 * i + 2] = F.B.mol(new_buf, 2)[j]; qeff[i] = F.B.mol(new_buf, 8)[j] * F.B.mol(new_buf, 6)[j];
-      }
+      double ax, ay, az, sc, scc; chain_anchor(F, sm, type, ax, ay, az, sc, scc);
+      set_trial(sm->T, threadIdx.x, chain_atom(P, F, type, g, threadIdx.x, off, ax, ay, az, sc, scc));
     }
     __syncthreads();
-    build_eik(P, pos3, n, ex, ey, ez, threadIdx.x, blockDim.x);
-    __syncthreads();
-    double same = 0.0, cross = 0.0;
-    for(int kk = blockIdx.x * blockDim.x + threadIdx.x; kk < F.K.nact; kk += gridDim.x * blockDim.x)
-    {
-      int kx, ky, kz; unpack_k(F.K.kpack[kk], kx, ky, kz);
-      const cplx co = ck_sum(ex, ey, ez, qeff, n, 0, nold, kx, ky, kz);
-      const cplx cn = ck_sum(ex, ey, ez, qeff, n, nold, n, kx, ky, kz);
-      const double temp = F.K.temp[kk];
-      const int slot = F.K.slot[kk];
-      const double ore = F.same_sf[2 * slot], oim = F.same_sf[2 * slot + 1];
-      const double nre = ore + cn.re - co.re, nim = oim + cn.im - co.im;
-      same += temp * (nre * nre + nim * nim);
-      same -= temp * (ore * ore + oim * oim);
-      F.temp_sf[2 * slot] = nre; F.temp_sf[2 * slot + 1] = nim;
-      cross += temp * (F.cross_sf[2 * slot] * (cn.re - co.re) + F.cross_sf[2 * slot + 1] * (cn.im - co.im));
-    }
-    same = warp_sum(same); cross = warp_sum(cross);
-    if(lane_id() == 0) { red[threadIdx.x >> 5] = same; red[8 + (threadIdx.x >> 5)] = cross; }
-    __syncthreads();
+    const int new_molid = (type == 0 || type == 4) ? F.nmol : (int) F.molecule;
+    double* out8 = part + (size_t) w * 8;
+    if(cs == 1)      group_energy<1>(P, W, S, F, sm, new_molid, cs, split, nsplit, out8);
+    else if(cs == 2) group_energy<2>(P, W, S, F, sm, new_molid, cs, split, nsplit, out8);
+    else             group_energy<0>(P, W, S, F, sm, new_molid, cs, split, nsplit, out8);
+  }
+}
+
+// fixed-order sum of the split partials of every group of the stage (one thread per group), by EVERY CTA
+__device__ __forceinline__ void collect_stage(const FusedArgs& F, FusedSmem* sm, int ngroups, int nsplit, int par)
+{
+  if((int) threadIdx.x < ngroups)
+  {
+    const double* p = part_half(F, par) + (size_t) threadIdx.x * nsplit * 8;
+    double s[7] = {0, 0, 0, 0, 0, 0, 0};
+    for(int k = 0; k < nsplit; k++)
+#pragma unroll
+      for(int j = 0; j < 7; j++) s[j] += __ldcg(p + k * 8 + j);
+#pragma unroll
+    for(int j = 0; j < 6; j++) sm->E[6 * threadIdx.x + j] = s[j];
+    sm->Fl[threadIdx.x] = s[6] > 0.0 ? 1 : 0;
+  }
+  __syncthreads();
+}
+
+// Boltzmann weights / selection / Rosenbluth factor of one segment into result slot `slot` (all threads call; warp 0 works)
+__device__ __forceinline__ void finish_segment(const DevParams& P, const FusedArgs& F, FusedSmem* sm, int type, bool chain, int n, double uniform,
+                                               double stored, const double* E, const int* Fl, int slot, double prev_product)
+{
+  double* r = sm->res + 16 * slot;
+  if(threadIdx.x < 32)
+  {
+    cbmc_finish_core(P, type, chain, n, chain ? F.norient : F.ntrials, uniform, stored, E, Fl, r);
     if(threadIdx.x == 0)
     {
-      double s = 0.0, c = 0.0;
-      for(int w = 0; w < (int)(blockDim.x >> 5); w++) { s += red[w]; c += red[8 + w]; }
-      F.B.partial()[2 * blockIdx.x] = s; F.B.partial()[2 * blockIdx.x + 1] = c;
+      r[14] = prev_product * r[0];                                       // CBMC.Rosenbluth *= averagedRosen, mc_widom.h:611
+      r[13] = (r[9] != 0.0 && r[14] > 1e-150) ? 1.0 : 0.0;               // mc_swap_utilities.h:21,32
     }
   }
-  grid_barrier(F.bar, phase);
-  if(blockIdx.x == 0 && threadIdx.x == 0)
+  __syncthreads();
+}
+
+// the selected trial joins the molecule being grown (Mol.pos[0] = NewMol.pos[FirstBeadTrial], mc_widom.h:230-241 / 590-599);
+// recomputed from the pool, which gives the same bits as the trial that was evaluated
+__device__ __forceinline__ void adopt_selection(const DevParams& P, const FusedArgs& F, FusedSmem* sm, int type, bool chain, long long pool_off, int slot)
+{
+  double* r = sm->res + 16 * slot;
+  const bool have = r[9] != 0.0 && r[11] > 0.0;
+  const int sel = (int) r[10];
+  __syncthreads();
+  if(have)
+  {
+    if(!chain)
+    {
+      if(threadIdx.x == 0)
+      {
+        const AtomRec a = first_bead_atom(P, F, type, sel, pool_off);
+        put_atom(sm->mN, 0, a);
+        r[6] = a.x; r[7] = a.y; r[8] = a.z;
+      }
+    }
+    else if((int) threadIdx.x < F.ms - 1)
+    {
+      double ax, ay, az, sc, scc; chain_anchor(F, sm, type, ax, ay, az, sc, scc);
+      put_atom(sm->mN, 1 + threadIdx.x, chain_atom(P, F, type, sel, threadIdx.x, pool_off, ax, ay, az, sc, scc));
+    }
+  }
+  __syncthreads();
+}
+
+// Ewald Fourier delta of [old atoms | new atoms]: the last `ne` CTAs of the grid each take 256 k-vectors; CTA partial
+// {same, cross} goes to out2[2 * slice].  old atoms: component slots (oldS == nullptr) or a shared-memory molecule.
+__device__ __forceinline__ int ewald_ctas(const FusedArgs& F) { return min((int) gridDim.x, (F.K.nact + 255) / 256); }
+
+__device__ __forceinline__ void ewald_slice(const DevParams& P, const FusedArgs& F, unsigned char* dyn, double* red, const SmemMol* oldS, long long old_start,
+                                            int nold, const SmemMol* newS, int nnew, double* out2)
+{
+  const int ne = ewald_ctas(F);
+  const int slice = (int) blockIdx.x - ((int) gridDim.x - ne);
+  if(slice < 0) return;
+  const int n = nold + nnew;
+  const int kx1 = P.kmax[0] + 1, ky1 = P.kmax[1] + 1, kz1 = P.kmax[2] + 1;
+  cplx* ex = reinterpret_cast<cplx*>(dyn);
+  cplx* ey = ex + (size_t) n * kx1; cplx* ez = ey + (size_t) n * ky1;
+  double* qeff = reinterpret_cast<double*>(ez + (size_t) n * kz1);
+  double* pos3 = qeff + n;
+  __syncthreads();
+  for(int i = threadIdx.x; i < n; i += blockDim.x)
+  {
+    if(i < nold)
+    {
+      if(oldS == nullptr) { pos3[3 * i] = F.C.x[old_start + i]; pos3[3 * i + 1] = F.C.y[old_start + i]; pos3[3 * i + 2] = F.C.z[old_start + i]; qeff[i] = F.C.scoul[old_start + i] * F.C.q[old_start + i]; }
+      else { pos3[3 * i] = oldS->a[0][i]; pos3[3 * i + 1] = oldS->a[1][i]; pos3[3 * i + 2] = oldS->a[2][i]; qeff[i] = oldS->a[8][i] * oldS->a[6][i]; }
+    }
+    else
+    {
+      const int j = i - nold;
+      pos3[3 * i] = newS->a[0][j]; pos3[3 * i + 1] = newS->a[1][j]; pos3[3 * i + 2] = newS->a[2][j]; qeff[i] = newS->a[8][j] * newS->a[6][j];
+    }
+  }
+  __syncthreads();
+  build_eik(P, pos3, n, ex, ey, ez, threadIdx.x, blockDim.x);
+  __syncthreads();
+  double same = 0.0, cross = 0.0;
+  for(int kk = slice * blockDim.x + threadIdx.x; kk < F.K.nact; kk += ne * blockDim.x)
+  {
+    int kx, ky, kz; unpack_k(F.K.kpack[kk], kx, ky, kz);
+    const cplx co = ck_sum(ex, ey, ez, qeff, n, 0, nold, kx, ky, kz);
+    const cplx cn = ck_sum(ex, ey, ez, qeff, n, nold, n, kx, ky, kz);
+    const double temp = F.K.temp[kk];
+    const int slot = F.K.slot[kk];
+    const double ore = F.same_sf[2 * slot], oim = F.same_sf[2 * slot + 1];
+    const double nre = ore + cn.re - co.re, nim = oim + cn.im - co.im;
+    same += temp * (nre * nre + nim * nim);
+    same -= temp * (ore * ore + oim * oim);
+    F.temp_sf[2 * slot] = nre; F.temp_sf[2 * slot + 1] = nim;
+    cross += temp * (F.cross_sf[2 * slot] * (cn.re - co.re) + F.cross_sf[2 * slot + 1] * (cn.im - co.im));
+  }
+  same = warp_sum(same); cross = warp_sum(cross);
+  __syncthreads();
+  if(lane_id() == 0) { red[threadIdx.x >> 5] = same; red[8 + (threadIdx.x >> 5)] = cross; }
+  __syncthreads();
+  if(threadIdx.x == 0)
   {
     double s = 0.0, c = 0.0;
-    if(run) { const volatile double* p = F.B.partial(); for(unsigned int b = 0; b < gridDim.x; b++) { s += p[2 * b]; c += p[2 * b + 1]; } }
-    res[0] = s; res[1] = 2.0 * c;
+    for(int w = 0; w < (int)(blockDim.x >> 5); w++) { s += red[w]; c += red[8 + w]; }
+    out2[2 * slice] = s; out2[2 * slice + 1] = c;
+  }
+}
+
+// CTA 0: result slot 5 = {same, 2 * cross} summed over the Ewald CTAs in fixed order
+__device__ __forceinline__ void ewald_total_slot(const FusedArgs& F, FusedSmem* sm, const double* in2, bool run)
+{
+  if(threadIdx.x == 0)
+  {
+    double s = 0.0, c = 0.0;
+    if(run) { const int ne = ewald_ctas(F); for(int b = 0; b < ne; b++) { s += __ldcg(in2 + 2 * b); c += __ldcg(in2 + 2 * b + 1); } }
+    sm->res[16 * 5] = s; sm->res[16 * 5 + 1] = 2.0 * c;
+  }
+  __syncthreads();
+}
+
+// CTA 0: copy a shared-memory molecule into one of the device molecule buffers (read by the accept calls)
+__device__ __forceinline__ void export_molecule(const FusedArgs& F, const SmemMol& M, int buf)
+{
+  if((int) threadIdx.x < F.ms)
+  {
+#pragma unroll
+    for(int k = 0; k < 9; k++) F.B.mol(buf, k)[threadIdx.x] = M.a[k][threadIdx.x];
+    F.B.mol_type(buf)[threadIdx.x] = M.type[threadIdx.x];
   }
 }
 
@@ -251,98 +355,216 @@ k_move(DevParams P, SysView S, FusedArgs F)
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ FusedSmem sm;
   unsigned int phase = 0;
+#ifdef GBK_PHASE_TIMING
+  if(blockIdx.x == 0 && threadIdx.x == 0) g_nmarks = 0;
+#endif
+  GBK_MARK();
   stage_erfc_table(P, sm.etab);
+  if(threadIdx.x < 128) sm.res[threadIdx.x] = 0.0;
   __syncthreads();
   PairTables W; W.etab = sm.etab; W.ffp = P.ffA; W.unit = false;
   const int ms = F.ms;
-  if(F.kind == GBF_INSERTION || F.kind == GBF_DELETION)
+  const int no = ms > 1 ? F.norient : 0;
+
+  if(F.kind == GBF_INSERTION)
   {
-    const int type = F.kind == GBF_INSERTION ? 0 : 1;
-    fused_cbmc_stage(P, S, F, &sm, W, false, type, F.pool_off, F.u0, 0, -1, -1, phase);
-    int last = 0;
-    if(ms > 1) { fused_cbmc_stage(P, S, F, &sm, W, true, type, F.pool_off + F.ntrials, F.u1, 1, 0, -1, phase); last = 1; }
+    StageSeg sg[1];
+    sg[0].type = 0; sg[0].chain = 0; sg[0].n = F.ntrials; sg[0].pool_off = F.pool_off;
+    int nsplit = stage_nsplit(F, F.ntrials);
+    run_stage(P, S, F, &sm, W, sg, 1, F.ntrials, nsplit, 0);
+    grid_barrier(F, phase);
+    collect_stage(F, &sm, F.ntrials, nsplit, 0);
+    finish_segment(P, F, &sm, 0, false, F.ntrials, F.u0, 0.0, sm.E, sm.Fl, 0, 1.0);
+    adopt_selection(P, F, &sm, 0, false, F.pool_off, 0);
+    bool alive = sm.res[13] != 0.0;
+    if(ms > 1)
+    {
+      sg[0].chain = 1; sg[0].n = no; sg[0].pool_off = F.pool_off + F.ntrials;
+      nsplit = stage_nsplit(F, no);
+      if(alive) run_stage(P, S, F, &sm, W, sg, 1, no, nsplit, 1);
+      grid_barrier(F, phase);
+      if(alive)
+      {
+        collect_stage(F, &sm, no, nsplit, 1);
+        finish_segment(P, F, &sm, 0, true, no, F.u1, 0.0, sm.E, sm.Fl, 1, sm.res[14]);
+        adopt_selection(P, F, &sm, 0, true, F.pool_off + F.ntrials, 1);
+        alive = sm.res[16 + 13] != 0.0;
+      }
+    }
+    double* ew = part_half(F, 0) + GBF_PART_EWALD;
     if(F.do_ewald)
     {
-      if(F.kind == GBF_INSERTION) fused_ewald_stage(P, F, dyn, sm.red, 0, 0, 0, GBK_BUF_GROWN, ms, F.B.result(last) + 13, phase);
-      else                        fused_ewald_stage(P, F, dyn, sm.red, -1, F.molecule * ms, ms, GBK_BUF_NEW, 0, F.B.result(last) + 13, phase);
+      if(alive) ewald_slice(P, F, dyn, sm.red, nullptr, 0, 0, &sm.mN, ms, ew);
+      grid_barrier(F, phase);
+    }
+    if(blockIdx.x == 0)
+    {
+      if(F.do_ewald) ewald_total_slot(F, &sm, ew, alive);
+      export_molecule(F, sm.mN, GBK_BUF_GROWN);
+    }
+  }
+  else if(F.kind == GBF_DELETION)
+  {
+    // nothing in a deletion depends on a selection: trial 0 of either stage is the existing molecule
+    StageSeg sg[2];
+    sg[0].type = 1; sg[0].chain = 0; sg[0].n = F.ntrials; sg[0].pool_off = F.pool_off;
+    sg[1].type = 1; sg[1].chain = 1; sg[1].n = no; sg[1].pool_off = F.pool_off + F.ntrials;
+    const int ngroups = F.ntrials + no;
+    const int nsplit = stage_nsplit(F, ngroups);
+    run_stage(P, S, F, &sm, W, sg, ms > 1 ? 2 : 1, ngroups, nsplit, 0);
+    double* ew = part_half(F, 0) + GBF_PART_EWALD;
+    if(F.do_ewald) ewald_slice(P, F, dyn, sm.red, nullptr, F.molecule * ms, ms, &sm.mN, 0, ew);
+    grid_barrier(F, phase);
+    if(blockIdx.x == 0)
+    {
+      collect_stage(F, &sm, ngroups, nsplit, 0);
+      finish_segment(P, F, &sm, 1, false, F.ntrials, 0.0, 0.0, sm.E, sm.Fl, 0, 1.0);
+      bool alive = sm.res[13] != 0.0;
+      if(ms > 1 && alive)
+      {
+        finish_segment(P, F, &sm, 1, true, no, 0.0, 0.0, sm.E + 6 * F.ntrials, sm.Fl + F.ntrials, 1, sm.res[14]);
+        alive = sm.res[16 + 13] != 0.0;
+      }
+      if(threadIdx.x == 0 && sm.res[9] != 0.0 && sm.res[11] > 0.0)
+      {
+        const long long start = F.molecule * ms;
+        sm.res[6] = F.C.x[start]; sm.res[7] = F.C.y[start]; sm.res[8] = F.C.z[start];
+      }
+      if(F.do_ewald) ewald_total_slot(F, &sm, ew, alive);
     }
   }
   else if(F.kind == GBF_REINSERTION)
   {
-    long long off = F.pool_off;
-    fused_cbmc_stage(P, S, F, &sm, W, false, 2, off, F.u0, 0, -1, -1, phase); off += F.ntrials;
+    // stage 1: first-bead trials of the new position + the whole retrace of the old molecule
+    StageSeg sg[3];
+    sg[0].type = 2; sg[0].chain = 0; sg[0].n = F.ntrials; sg[0].pool_off = F.pool_off;
+    sg[1].type = 3; sg[1].chain = 0; sg[1].n = 1;         sg[1].pool_off = F.pool_off + F.ntrials + no;
+    sg[2].type = 3; sg[2].chain = 1; sg[2].n = no;        sg[2].pool_off = F.pool_off + F.ntrials + no + 1;
+    const int ngroups = F.ntrials + 1 + no;
+    int nsplit = stage_nsplit(F, ngroups);
+    run_stage(P, S, F, &sm, W, sg, ms > 1 ? 3 : 2, ngroups, nsplit, 0);
+    grid_barrier(F, phase);
+    collect_stage(F, &sm, ngroups, nsplit, 0);
+    if(blockIdx.x == 0)
+    {
+      if((int) threadIdx.x < 6 * (1 + no)) sm.Ekeep[threadIdx.x] = sm.E[6 * F.ntrials + threadIdx.x];
+      if((int) threadIdx.x < 1 + no) sm.Fkeep[threadIdx.x] = sm.Fl[F.ntrials + threadIdx.x];
+      __syncthreads();
+    }
+    finish_segment(P, F, &sm, 2, false, F.ntrials, F.u0, 0.0, sm.E, sm.Fl, 0, 1.0);
+    adopt_selection(P, F, &sm, 2, false, F.pool_off, 0);
+    bool alive = sm.res[13] != 0.0;
     int nl = 0;
-    if(ms > 1) { fused_cbmc_stage(P, S, F, &sm, W, true, 2, off, F.u1, 1, 0, -1, phase); off += F.norient; nl = 1; }
-    fused_cbmc_stage(P, S, F, &sm, W, false, 3, off, 0.0, 2, nl, 0, phase); off += 1;
-    if(ms > 1) fused_cbmc_stage(P, S, F, &sm, W, true, 3, off, 0.0, 3, nl, -1, phase);
-    if(F.do_ewald) fused_ewald_stage(P, F, dyn, sm.red, -1, F.molecule * ms, ms, GBK_BUF_TEMP, ms, F.B.result(nl) + 13, phase);
+    if(ms > 1)
+    {
+      StageSeg sc[1];
+      sc[0].type = 2; sc[0].chain = 1; sc[0].n = no; sc[0].pool_off = F.pool_off + F.ntrials;
+      nsplit = stage_nsplit(F, no);
+      if(alive) run_stage(P, S, F, &sm, W, sc, 1, no, nsplit, 1);
+      grid_barrier(F, phase);
+      if(alive)
+      {
+        collect_stage(F, &sm, no, nsplit, 1);
+        finish_segment(P, F, &sm, 2, true, no, F.u1, 0.0, sm.E, sm.Fl, 1, sm.res[14]);
+        adopt_selection(P, F, &sm, 2, true, F.pool_off + F.ntrials, 1);
+        alive = sm.res[16 + 13] != 0.0;
+      }
+      nl = 1;
+    }
+    double* ew = part_half(F, 0) + GBF_PART_EWALD;
+    if(F.do_ewald)
+    {
+      if(alive) ewald_slice(P, F, dyn, sm.red, nullptr, F.molecule * ms, ms, &sm.mN, ms, ew);
+      grid_barrier(F, phase);
+    }
+    if(blockIdx.x == 0)
+    {
+      if(alive)
+      {
+        // retrace: Rosenbluth weight of the old configuration, with the stored weights of the insertion's other trials
+        finish_segment(P, F, &sm, 3, false, 1, 0.0, sm.res[1], sm.Ekeep, sm.Fkeep, 2, 1.0);
+        if(threadIdx.x == 0 && sm.res[32 + 9] != 0.0 && sm.res[32 + 11] > 0.0)
+        {
+          const long long start = F.molecule * ms;
+          sm.res[32 + 6] = F.C.x[start]; sm.res[32 + 7] = F.C.y[start]; sm.res[32 + 8] = F.C.z[start];
+        }
+        if(ms > 1) finish_segment(P, F, &sm, 3, true, no, 0.0, 0.0, sm.Ekeep + 6, sm.Fkeep + 1, 3, sm.res[16 * nl + 14]);
+      }
+      if(F.do_ewald) ewald_total_slot(F, &sm, ew, alive);
+      export_molecule(F, sm.mN, GBK_BUF_TEMP);            // tempMolStorage, StoreNewLocation_Reinsertion
+    }
   }
   else
   {
-    // ---- single body: proposal (every CTA computes it; CTA 0 publishes the buffers), new/old energies over CTA slices
-    const int i = threadIdx.x;
-    double* pn = reinterpret_cast<double*>(dyn);           // [ms][3] new Cartesian (kept for the Ewald stage through the buffers)
-    (void) pn;
-    if(i < ms)
+    // ---- translation / rotation: every CTA builds the proposal; items = (new | old) x atom slices; Ewald CTAs at the grid's end
+    if((int) threadIdx.x < ms)
     {
       ProposeArgs A; memset(&A, 0, sizeof(A));
       A.move_type = F.move_type; A.ms = ms; A.start = F.molecule * ms; A.pool_index = F.pool_off; A.pool3 = F.pool3;
       A.maxc[0] = F.maxc[0]; A.maxc[1] = F.maxc[1]; A.maxc[2] = F.maxc[2]; A.C = F.C; A.B = F.B;
-      if(blockIdx.x == 0) propose_atom(P, A, i);
+      AtomRec nw, od;
+      propose_atom(P, A, threadIdx.x, nw, od);
+      put_atom(sm.mN, threadIdx.x, nw); put_atom(sm.mO, threadIdx.x, od);
     }
-    grid_barrier(F.bar, phase);
-    double tot[14];
-    for(int k = 0; k < 14; k++) tot[k] = 0.0;
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = (int) lane_id();
-    for(int pass = 0; pass < 2; pass++)
-    {
-      const int buf = pass == 0 ? GBK_BUF_NEW : GBK_BUF_OLD;
-      __syncthreads();
-      if(threadIdx.x < ms)
-      {
-        const int a = threadIdx.x;
-        sm.T.fx[a] = F.B.mol(buf, 3)[a]; sm.T.fy[a] = F.B.mol(buf, 4)[a]; sm.T.fz[a] = F.B.mol(buf, 5)[a];
-        sm.T.q[a] = F.B.mol(buf, 6)[a] * F.B.mol(buf, 8)[a]; sm.T.scale[a] = F.B.mol(buf, 7)[a]; sm.T.type[a] = F.B.mol_type(buf)[a]; sm.T.slot[a] = 0;
-      }
-      __syncthreads();
-      double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
-      pair_group_generic<0>(P, W, S, F.L, F.comp, (int) F.molecule, -1, -1, &sm.T, ms, sm.Q + warp, blockIdx.x * nwarps + warp, gridDim.x * nwarps, e6, flag);
-#pragma unroll
-      for(int k = 0; k < 6; k++) tot[pass * 7 + k] = warp_sum(e6[k]);
-      tot[pass * 7 + 6] = __any_sync(0xffffffffu, flag) ? 1.0 : 0.0;
-    }
-    if(lane == 0) for(int k = 0; k < 14; k++) sm.red[warp * 16 + k] = tot[k];
     __syncthreads();
-    if(threadIdx.x < 14)
+    const int ne = F.do_ewald ? ewald_ctas(F) : 0;
+    const int npair = max(1, (int) gridDim.x - ne);          // CTAs that share the pair items
+    const int nslice = max(1, min((F.natoms + 255) / 256, GBF_PART_EWALD / 16));
+    double* part = part_half(F, 0);
+    if((int) blockIdx.x < npair)
     {
-      double s = 0.0;
-      for(int w = 0; w < nwarps; w++) s += sm.red[w * 16 + threadIdx.x];
-      F.B.partial()[1024 + blockIdx.x * 16 + threadIdx.x] = s;
+      for(int w = blockIdx.x; w < 2 * nslice; w += npair)
+      {
+        const int pass = w / nslice, slice = w % nslice;
+        const SmemMol& M = pass == 0 ? sm.mN : sm.mO;
+        __syncthreads();
+        if((int) threadIdx.x < ms)
+        {
+          const int a = threadIdx.x;
+          sm.T.fx[a] = M.a[3][a]; sm.T.fy[a] = M.a[4][a]; sm.T.fz[a] = M.a[5][a];
+          sm.T.q[a] = M.a[6][a] * M.a[8][a]; sm.T.scale[a] = M.a[7][a]; sm.T.type[a] = M.type[a]; sm.T.slot[a] = 0;
+        }
+        __syncthreads();
+        group_energy<0>(P, W, S, F, &sm, (int) F.molecule, ms, slice, nslice, part + (size_t) w * 8);
+      }
     }
-    grid_barrier(F.bar, phase);
-    if(blockIdx.x == 0 && threadIdx.x == 0)
+    double* ew = part + GBF_PART_EWALD;
+    if(F.do_ewald) ewald_slice(P, F, dyn, sm.red, &sm.mO, 0, ms, &sm.mN, ms, ew);
+    grid_barrier(F, phase);
+    if(blockIdx.x == 0)
     {
-      const volatile double* p = F.B.partial() + 1024;
-      double* r = F.B.result(4);
-      for(int k = 0; k < 6; k++)
+      // delta = sum(new) - sum(old) over the slices in fixed order (mc_single_particle.h:183-200); overlap of NEW only (:768-769)
+      if(threadIdx.x < 7)
       {
         double n = 0.0, o = 0.0;
-        for(unsigned int b = 0; b < gridDim.x; b++) { n += p[b * 16 + k]; o += p[b * 16 + 7 + k]; }
-        r[k] = n - o;
+        for(int b = 0; b < nslice; b++) { n += __ldcg(part + (size_t) b * 8 + threadIdx.x); o += __ldcg(part + (size_t)(nslice + b) * 8 + threadIdx.x); }
+        if(threadIdx.x < 6) sm.res[64 + threadIdx.x] = n - o;
+        else { sm.res[64 + 6] = n > 0.0 ? 1.0 : 0.0; sm.res[64 + 7] = n > 0.0 ? 0.0 : 1.0; }
       }
-      double fl = 0.0;
-      for(unsigned int b = 0; b < gridDim.x; b++) fl += p[b * 16 + 6];
-      r[6] = fl > 0.0 ? 1.0 : 0.0; r[7] = 1.0 - r[6];
+      __syncthreads();
+      const bool run = !F.check_overlap || sm.res[64 + 6] == 0.0;
+      if(F.do_ewald) ewald_total_slot(F, &sm, ew, run);
+      export_molecule(F, sm.mN, GBK_BUF_NEW);
+      export_molecule(F, sm.mO, GBK_BUF_OLD);
     }
-    grid_barrier(F.bar, phase);
-    if(F.do_ewald) fused_ewald_stage(P, F, dyn, sm.red, GBK_BUF_OLD, 0, ms, GBK_BUF_NEW, ms, F.check_overlap ? F.B.result(4) + 7 : nullptr, phase);
   }
-  // leave the barrier counter at zero for the next launch (every CTA has passed the last barrier once CTA 0 gets here
-  // only if it is the last to arrive; so the reset is done by the last CTA through a second counter)
-  __syncthreads();
-  if(threadIdx.x == 0)
+  // publish: CTA 0 holds every result slot; it stores them to the host and then raises the sequence flag, so the host
+  // needs neither a copy nor a stream synchronisation to read the outcome of the move
+  if(blockIdx.x == 0)
   {
-    __threadfence();
-    if(atomicAdd(F.bar + 1, 1u) == gridDim.x - 1) { F.bar[0] = 0u; F.bar[1] = 0u; }
+    __syncthreads();
+    if(threadIdx.x < 128) { F.host_result[threadIdx.x] = sm.res[threadIdx.x]; F.B.result(0)[threadIdx.x] = sm.res[threadIdx.x]; }
+    __threadfence_system();
+    __syncthreads();
+    if(threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(F.host_flag) = F.seq;
   }
+#ifdef GBK_PHASE_TIMING
+  GBK_MARK();
+  if(blockIdx.x == 0 && threadIdx.x == 0 && F.seq >= 20000 && F.seq < 20040)
+  {
+    printf("kind %d grid %d:", F.kind, gridDim.x);
+    for(int i = 1; i < g_nmarks; i++) printf(" %lld", g_marks[i] - g_marks[i - 1]);
+    printf("\n");
+  }
+#endif
 }

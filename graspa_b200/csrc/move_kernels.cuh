@@ -58,12 +58,12 @@ struct CbmcArgs
 // Host_sum_Widom_HGGG_SEPARATE (:42-87) in front.  Sums run in trial order like the host code (rosenbluth_warp).
 // result layout: r[0] rosenbluth, r[1] stored_r, r[2..5] energy, r[6..8] selected pos, r[9] success, r[10] selected,
 // r[11] nsurv, r[12] uniform used, r[13] growth still alive (success and running product > 1e-150), r[14] running product
-__device__ __forceinline__ void cbmc_finish_warp(const DevParams& P, const CbmcArgs& A, bool is_chain, double* r)
+__device__ __forceinline__ void cbmc_finish_core(const DevParams& P, int ty, bool is_chain, int ntrials, int norm, double uniform, double stored_r,
+                                                 const double* E, const int* F, double* r)
 {
   const int lane = (int) lane_id();
-  const double* E = A.B.stage_e(); const int* F = A.B.stage_flag();
   double e[6] = {0, 0, 0, 0, 0, 0}; bool surv = false;
-  if(lane < A.ntrials)
+  if(lane < ntrials)
   {
 #pragma unroll
     for(int k = 0; k < 6; k++) e[k] = E[6 * lane + k];
@@ -72,10 +72,9 @@ __device__ __forceinline__ void cbmc_finish_warp(const DevParams& P, const CbmcA
   // HH terms (a framework component grown against framework components) count with HG: VDW_Coulomb.cu:1232-1235
   double tot = (e[0] + e[2]) + e[4];
   if(P.vdw_real_bias) tot += (e[1] + e[3]) + e[5];
-  const int ty = A.cbmc_type;
   const bool insertion_like = (ty == 0 /*CBMC_INSERTION*/ || ty == 2 /*REINSERTION_INSERTION*/ || (is_chain && ty == 4 /*IDENTITY_SWAP_NEW*/));
   const bool needs_survivor = insertion_like || ty == 4;
-  const RosenResult rr = rosenbluth_warp(-P.beta * tot, surv, A.ntrials, A.uniform, insertion_like);
+  const RosenResult rr = rosenbluth_warp(-P.beta * tot, surv, ntrials, uniform, insertion_like);
   const int ns = rr.nsurv;
   const bool good = needs_survivor ? (ns > 0 && !(rr.R < 1e-150)) : true;
   const int sel = rr.sel_lane;
@@ -90,12 +89,18 @@ __device__ __forceinline__ void cbmc_finish_warp(const DevParams& P, const CbmcA
   if(!is_chain)
   {
     if(ty == 2) r[1] = rr.R_minus_sel;                                                          // StoredR, mc_widom.h:365
-    if(ty == 3) avg += (A.stored_slot >= 0) ? A.B.result(A.stored_slot)[1] : A.stored_r;        // REINSERTION_RETRACE :366
-    if(ty != 4 && ty != 5) avg /= (double) A.norm;                                              // :369-370
+    if(ty == 3) avg += stored_r;                                                                // REINSERTION_RETRACE :366
+    if(ty != 4 && ty != 5) avg /= (double) norm;                                                // :369-370
   }
-  else avg = rr.R / (double) A.norm;                                                            // :601
+  else avg = rr.R / (double) norm;                                                              // :601
   if(!P.vdw_real_bias) avg *= exp(-P.beta * (hgr + ggr));                                       // :373-377, :603-607
   r[0] = avg; r[2] = hgv; r[3] = hgr; r[4] = ggv; r[5] = ggr; r[9] = 1.0; r[10] = sel;
+}
+
+__device__ __forceinline__ void cbmc_finish_warp(const DevParams& P, const CbmcArgs& A, bool is_chain, double* r)
+{
+  const double stored = (A.stored_slot >= 0) ? A.B.result(A.stored_slot)[1] : A.stored_r;
+  cbmc_finish_core(P, A.cbmc_type, is_chain, A.ntrials, A.norm, A.uniform, stored, A.B.stage_e(), A.B.stage_flag(), r);
 }
 
 // pair energies of the trial group in *T for this CTA's slice of the atom ranges; partial sums go to
@@ -303,7 +308,16 @@ struct ProposeArgs
   CompView C; MoveBufs B; int new_molid;
 };
 
-__device__ __forceinline__ void propose_atom(const DevParams& P, const ProposeArgs& A, int i)
+// one atom of a molecule in flight: Cartesian, fractional, charge, scaling factors, pseudo-atom type
+struct AtomRec { double x, y, z, fx, fy, fz, q, scale, scoul; int type; };
+
+__device__ __forceinline__ void store_atom(const MoveBufs& B, int buf, int i, const AtomRec& r)
+{
+  B.mol(buf, 0)[i] = r.x; B.mol(buf, 1)[i] = r.y; B.mol(buf, 2)[i] = r.z; B.mol(buf, 3)[i] = r.fx; B.mol(buf, 4)[i] = r.fy; B.mol(buf, 5)[i] = r.fz;
+  B.mol(buf, 6)[i] = r.q; B.mol(buf, 7)[i] = r.scale; B.mol(buf, 8)[i] = r.scoul; B.mol_type(buf)[i] = r.type;
+}
+
+__device__ __forceinline__ void propose_atom(const DevParams& P, const ProposeArgs& A, int i, AtomRec& nw, AtomRec& od)
 {
   const long long rp = A.start + i;
   const double x = A.C.x[rp], y = A.C.y[rp], z = A.C.z[rp];
@@ -345,21 +359,19 @@ __device__ __forceinline__ void propose_atom(const DevParams& P, const ProposeAr
       break;
     }
   }
-  const double q = A.C.q[rp], sc = A.C.scale[rp], scc = A.C.scoul[rp]; const int ty = A.C.type[rp];
-  double fx, fy, fz;
-  to_frac(P, nx, ny, nz, fx, fy, fz);
-  A.B.mol(GBK_BUF_NEW, 0)[i] = nx; A.B.mol(GBK_BUF_NEW, 1)[i] = ny; A.B.mol(GBK_BUF_NEW, 2)[i] = nz;
-  A.B.mol(GBK_BUF_NEW, 3)[i] = fx; A.B.mol(GBK_BUF_NEW, 4)[i] = fy; A.B.mol(GBK_BUF_NEW, 5)[i] = fz;
-  A.B.mol(GBK_BUF_NEW, 6)[i] = q; A.B.mol(GBK_BUF_NEW, 7)[i] = sc; A.B.mol(GBK_BUF_NEW, 8)[i] = scc; A.B.mol_type(GBK_BUF_NEW)[i] = ty;
-  to_frac(P, x, y, z, fx, fy, fz);
-  A.B.mol(GBK_BUF_OLD, 0)[i] = x; A.B.mol(GBK_BUF_OLD, 1)[i] = y; A.B.mol(GBK_BUF_OLD, 2)[i] = z;
-  A.B.mol(GBK_BUF_OLD, 3)[i] = fx; A.B.mol(GBK_BUF_OLD, 4)[i] = fy; A.B.mol(GBK_BUF_OLD, 5)[i] = fz;
-  A.B.mol(GBK_BUF_OLD, 6)[i] = q; A.B.mol(GBK_BUF_OLD, 7)[i] = sc; A.B.mol(GBK_BUF_OLD, 8)[i] = scc; A.B.mol_type(GBK_BUF_OLD)[i] = ty;
+  nw.q = od.q = A.C.q[rp]; nw.scale = od.scale = A.C.scale[rp]; nw.scoul = od.scoul = A.C.scoul[rp]; nw.type = od.type = A.C.type[rp];
+  nw.x = nx; nw.y = ny; nw.z = nz; to_frac(P, nx, ny, nz, nw.fx, nw.fy, nw.fz);
+  od.x = x; od.y = y; od.z = z; to_frac(P, x, y, z, od.fx, od.fy, od.fz);
 }
 
 __global__ void k_single_propose(DevParams P, ProposeArgs A)
 {
-  if((int) threadIdx.x < A.ms) propose_atom(P, A, threadIdx.x);
+  if((int) threadIdx.x < A.ms)
+  {
+    AtomRec nw, od;
+    propose_atom(P, A, threadIdx.x, nw, od);
+    store_atom(A.B, GBK_BUF_NEW, threadIdx.x, nw); store_atom(A.B, GBK_BUF_OLD, threadIdx.x, od);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -690,15 +690,16 @@ void print_energy(const char* tag, const Energy& E)
 
 int main(int argc, char** argv)
 {
-  if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
+  if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--timing] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
   const std::string dir = argv[1];
-  bool sequential_widom = false, staged = false; const char* trace_path = nullptr;
+  bool sequential_widom = false, staged = false, timing = false; const char* trace_path = nullptr;
   long o_init = -1, o_equil = -1, o_prod = -1;
   for(int i = 2; i < argc; i++)
   {
     const std::string a = argv[i];
     if(a == "--sequential-widom") sequential_widom = true;
     else if(a == "--staged") staged = true;
+    else if(a == "--timing") timing = true;
     else if(a == "--trace" && i + 1 < argc) trace_path = argv[++i];
     else if(a == "--init" && i + 1 < argc) o_init = std::atol(argv[++i]);
     else if(a == "--equil" && i + 1 < argc) o_equil = std::atol(argv[++i]);
@@ -730,6 +731,7 @@ int main(int argc, char** argv)
   const Energy E0 = total_energy(S);
   print_energy("INITIAL", E0);
 
+  if(timing) GB(gb_timing_enable(S.e, 1));
   const auto t0 = std::chrono::steady_clock::now();
   int wcomp = -1;
   const bool batched = !sequential_widom && widom_only(S, wcomp) && S.d.init_cycles == 0 && S.d.equil_cycles == 0;
@@ -762,6 +764,11 @@ int main(int argc, char** argv)
   std::printf("{\"moves\": %ld, \"cycles\": %ld, \"seconds\": %.6f, \"moves_per_s\": %.3f, \"cycles_per_s\": %.3f, \"widom_path\": \"%s\", \"move_calls\": \"%s\", \"rng_draws\": %llu, \"pool_refills\": %ld, \"kernel_launches\": %lld}\n",
               S.moves_done, cycles, secs, S.moves_done / secs, cycles / secs, batched ? "batched-exact" : "sequential", S.fused ? "fused" : "staged",
               (unsigned long long) S.rng.consumed(), S.pool_rounds, (long long) launches);
+  if(timing)
+  {
+    double ms = 0.0; int64_t n = 0; gb_timing_read(S.e, 0, &ms, &n, 0);
+    std::printf("device time of the move kernels (CUDA events, serialises the run): %.3f ms over %lld launches = %.2f us each\n", ms, (long long) n, n ? 1e3 * ms / n : 0.0);
+  }
   if(S.trace) std::fclose(S.trace);
   gb_engine_destroy(S.e);
   return 0;
