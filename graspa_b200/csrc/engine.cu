@@ -96,7 +96,6 @@ struct gb_engine
   DevBuf<int> d_stage, d_iscratch;
   DevBuf<long long> d_idx0, d_idx1;
   DevBuf<unsigned int> d_ticket;
-  DevBuf<unsigned long long> d_flags;    // barrier flags of k_move, one per CTA
   double* h_pinned = nullptr;            // 4 KB pinned result slot
   unsigned long long move_seq = 0;       // sequence number of the last k_move launch (published to h_pinned + 256)
 
@@ -328,7 +327,6 @@ int gb_engine_create(gb_engine** out, int device)
   CUDA_TRY(cudaEventCreate(&e->ev0)); CUDA_TRY(cudaEventCreate(&e->ev1));
   CUDA_TRY(cudaMallocHost(&e->h_pinned, 4096)); memset(e->h_pinned, 0, 4096);
   CUDA_TRY(e->d_ticket.reserve(16)); CUDA_TRY(cudaMemset(e->d_ticket.p, 0, 16 * sizeof(unsigned int)));
-  CUDA_TRY(e->d_flags.reserve(256)); CUDA_TRY(cudaMemset(e->d_flags.p, 0, 256 * sizeof(unsigned long long)));
   CUDA_TRY(e->d_result.reserve(512));
   {
     // dynamic + static shared memory must stay within the opt-in limit
@@ -340,7 +338,7 @@ int gb_engine_create(gb_engine** out, int device)
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_widom_ewald));
     CUDA_TRY(cudaFuncSetAttribute(k_widom_ewald, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_move));
-    CUDA_TRY(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, GBF_MAX_DYN_SMEM));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_ewald_delta));
     CUDA_TRY(cudaFuncSetAttribute(k_ewald_delta, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
     e->smem_optin -= 1024;   // head room for static shared memory of the kernels
@@ -364,7 +362,7 @@ int gb_engine_destroy(gb_engine* e)
   for(int i = 0; i < 3; i++) e->d_sf[i].release();
   e->d_ktab.release(); e->d_pool.release(); e->d_rec.release(); e->d_out8.release(); e->d_partial.release(); e->d_sums.release();
   e->d_uni.release(); e->d_scratch.release(); e->d_result.release(); e->d_stage.release(); e->d_iscratch.release();
-  e->d_idx0.release(); e->d_idx1.release(); e->d_ticket.release(); e->d_flags.release(); e->d_mv.release(); e->d_mvi.release(); e->d_ewpos.release();
+  e->d_idx0.release(); e->d_idx1.release(); e->d_ticket.release(); e->d_mv.release(); e->d_mvi.release(); e->d_ewpos.release();
   if(e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
   cudaStreamDestroy(e->stream);

@@ -22,8 +22,10 @@
 
 enum { GBF_INSERTION = 0, GBF_DELETION = 1, GBF_REINSERTION = 2, GBF_SINGLE = 3 };
 #define GBF_MAX_GROUPS 96           // trial groups of one stage: ntrials + 1 + norient <= 65
-#define GBF_PART_HALF 2048          // doubles per parity half of MoveBufs::partial()
-#define GBF_PART_EWALD 1536         // Ewald CTA partials start here inside a half (pair partials: groups * nsplit * 8 <= 1536)
+#define GBF_PART_HALF 4096          // doubles per parity half of MoveBufs::partial()
+#define GBF_MAX_DYN_SMEM (160 * 1024)
+#define GBF_MAX_ITEMS 192           // (group, split) items of one stage; each publishes one 128-byte record
+#define GBF_PART_EWALD (GBF_MAX_ITEMS * 16)   // Ewald CTA records (32 bytes each) start here inside a half
 
 struct FusedArgs
 {
@@ -37,8 +39,6 @@ struct FusedArgs
   CompView C; MoveBufs B;
   SegList L;                              // live ranges with the kinds of THIS move
   KTable K; const double* same_sf; const double* cross_sf; double* temp_sf;
-  unsigned long long* flags;              // one barrier flag per CTA, monotonic across launches
-  unsigned long long epoch;               // 8 * sequence number of this launch
   double* host_result;                    // pinned host memory (UVA): the 8 result slots are stored there directly ...
   unsigned long long* host_flag;          // ... followed by this move's sequence number, which the host polls
   unsigned long long seq;
@@ -53,23 +53,27 @@ __device__ int g_nmarks;
 #define GBK_MARK() do { } while(0)
 #endif
 
-// all CTAs of the grid are co-resident (the host launches at most one CTA per SM, <= 256 CTAs): CTA b raises flag b,
-// thread t of every CTA waits for flag t
-__device__ __forceinline__ void grid_barrier(const FusedArgs& F, unsigned int& phase)
+// Cross-CTA hand-over without barriers or fences.  A CTA publishes a partial sum as 16-byte stores {lo, tag, hi, tag}:
+// every 8-byte half carries its own validity tag (8-byte accesses are single-copy atomic), so a consumer that polls the
+// 16 bytes with a volatile load and finds both tags equal to this stage's tag has the value -- no flag, no fence, one L2
+// round trip.  Tags are unique per (launch, stage); the halves of MoveBufs::partial() alternate between stages, and a CTA
+// only publishes stage s+1 after it has consumed ALL of stage s, so a record is never overwritten while someone still
+// polls for its previous content.  All CTAs are co-resident (grid <= number of SMs), so polling cannot deadlock.
+__device__ __forceinline__ void ll_store(double* rec, int j, double v, unsigned int tag)
 {
-  phase++;
-  const unsigned long long want = F.epoch + phase;
-  __syncthreads();
-  if(threadIdx.x == 0) { __threadfence(); *reinterpret_cast<volatile unsigned long long*>(F.flags + blockIdx.x) = want; }
-  if(threadIdx.x < gridDim.x)
-  {
-    const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(F.flags + threadIdx.x);
-    while(*f < want) { }
-    __threadfence();
-  }
-  __syncthreads();
-  GBK_MARK();
+  const unsigned int lo = (unsigned int) __double2loint(v), hi = (unsigned int) __double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(rec + 2 * j), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
 }
+
+__device__ __forceinline__ bool ll_load(const double* rec, int j, unsigned int tag, double& v)
+{
+  unsigned int lo, t0, hi, t1;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(rec + 2 * j) : "memory");
+  v = __hiloint2double((int) hi, (int) lo);
+  return t0 == tag && t1 == tag;
+}
+
+__device__ __forceinline__ unsigned int stage_tag(unsigned long long seq, int stage) { return (unsigned int) (seq * 4ULL + (unsigned long long) stage + 1ULL); }
 
 struct SmemMol { double a[9][GBK_MV_MOL_SLOTS]; int type[GBK_MV_MOL_SLOTS]; };   // x y z fx fy fz q scale scoul
 
@@ -82,12 +86,12 @@ __device__ __forceinline__ void put_atom(SmemMol& M, int i, const AtomRec& r)
 struct FusedSmem
 {
   TrialGroup T;
-  WarpQueue Q[8];
+  WarpQueueG Q[8];
   double red[8 * 16];
   double etab[(GBK_ERFC_DEG + 1) * GBK_ERFC_NINT];
   double E[GBF_MAX_GROUPS * 6]; int Fl[GBF_MAX_GROUPS];     // collected trial energies / overlap flags of the last stage
   double Ekeep[33 * 6]; int Fkeep[33];                      // reinsertion: the retrace groups of stage 1, finished at the end
-  double res[8 * 16];                                       // the result slots (MoveBufs::result layout)
+  __align__(32) double res[8 * 16];                                       // the result slots (MoveBufs::result layout)
   SmemMol mN, mO;                                           // molecule being grown / proposed, and its old image
 };
 
@@ -99,7 +103,7 @@ __device__ __forceinline__ double* part_half(const FusedArgs& F, int par) { retu
 __device__ __forceinline__ int stage_nsplit(const FusedArgs& F, int ngroups)
 {
   const int ns = (F.natoms + 255) / 256;                   // one 32-atom iteration per warp if the grid allows it
-  const int cap = max(1, min(GBF_PART_EWALD / (8 * max(ngroups, 1)), (int) gridDim.x / max(ngroups, 1)));
+  const int cap = max(1, min(GBF_MAX_ITEMS / max(ngroups, 1), (int) gridDim.x / max(ngroups, 1)));
   return max(1, min(ns, cap));
 }
 
@@ -158,11 +162,11 @@ __device__ __forceinline__ void set_trial(TrialGroup& T, int a, const AtomRec& r
 // pair energies of the trial group in sm->T against slice `split` of the live ranges; 7 partial sums to out8
 template <int CS>
 __device__ __forceinline__ void group_energy(const DevParams& P, const PairTables& W, const SysView& S, const FusedArgs& F, FusedSmem* sm,
-                                             int new_molid, int cs, int split, int nsplit, double* out8)
+                                             int new_molid, int cs, int split, int nsplit, double* rec, unsigned int tag)
 {
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = (int) lane_id();
   double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
-  pair_group_generic<CS>(P, W, S, F.L, F.comp, new_molid, -1, -1, &sm->T, cs, sm->Q + warp, split * nwarps + warp, nsplit * nwarps, e6, flag);
+  pair_group_flat<CS>(P, W, S, F.L, F.comp, new_molid, &sm->T, cs, sm->Q + warp, split * nwarps + warp, nsplit * nwarps, e6, flag);
 #pragma unroll
   for(int k = 0; k < 6; k++) e6[k] = warp_sum(e6[k]);
   flag = __any_sync(0xffffffffu, flag);
@@ -172,7 +176,7 @@ __device__ __forceinline__ void group_energy(const DevParams& P, const PairTable
   {
     double s = 0.0;
     for(int w = 0; w < nwarps; w++) s += sm->red[w * 8 + threadIdx.x];
-    out8[threadIdx.x] = s;
+    ll_store(rec, threadIdx.x, s, tag);
   }
 }
 
@@ -181,6 +185,7 @@ __device__ __forceinline__ void run_stage(const DevParams& P, const SysView& S, 
                                           const StageSeg* segs, int nseg, int ngroups, int nsplit, int par)
 {
   double* part = part_half(F, par);
+  const unsigned int tag = stage_tag(F.seq, par);
   for(int w = blockIdx.x; w < ngroups * nsplit; w += gridDim.x)
   {
     const int gg = w / nsplit, split = w % nsplit;
@@ -197,28 +202,52 @@ __device__ __forceinline__ void run_stage(const DevParams& P, const SysView& S, 
     }
     __syncthreads();
     const int new_molid = (type == 0 || type == 4) ? F.nmol : (int) F.molecule;
-    double* out8 = part + (size_t) w * 8;
-    if(cs == 1)      group_energy<1>(P, W, S, F, sm, new_molid, cs, split, nsplit, out8);
-    else if(cs == 2) group_energy<2>(P, W, S, F, sm, new_molid, cs, split, nsplit, out8);
-    else             group_energy<0>(P, W, S, F, sm, new_molid, cs, split, nsplit, out8);
+    double* rec = part + (size_t) w * 16;
+    if(cs == 1)      group_energy<1>(P, W, S, F, sm, new_molid, cs, split, nsplit, rec, tag);
+    else if(cs == 2) group_energy<2>(P, W, S, F, sm, new_molid, cs, split, nsplit, rec, tag);
+    else             group_energy<0>(P, W, S, F, sm, new_molid, cs, split, nsplit, rec, tag);
+  }
+  GBK_MARK();
+}
+
+// wait for `nitems` published records of 7 sums (stage tag `tag`) and copy them to stash[item * 8 + j]
+__device__ __forceinline__ void fetch_records(const double* part, int nitems, unsigned int tag, double* stash)
+{
+  for(int w = threadIdx.x; w < nitems; w += blockDim.x)
+  {
+    const double* rec = part + (size_t) w * 16;
+    double v[7]; bool ok;
+    do
+    {
+      ok = true;
+#pragma unroll
+      for(int j = 0; j < 7; j++) ok = ll_load(rec, j, tag, v[j]) && ok;
+    } while(!ok);
+#pragma unroll
+    for(int j = 0; j < 7; j++) stash[w * 8 + j] = v[j];
   }
 }
 
-// fixed-order sum of the split partials of every group of the stage (one thread per group), by EVERY CTA
-__device__ __forceinline__ void collect_stage(const FusedArgs& F, FusedSmem* sm, int ngroups, int nsplit, int par)
+// fixed-order sum of the split partials of every group of the stage, by EVERY CTA: one thread per (group, split) item
+// polls that item's record, then one thread per group adds the sums in split order
+__device__ __forceinline__ void collect_stage(const FusedArgs& F, FusedSmem* sm, double* stash, int ngroups, int nsplit, int par)
 {
+  __syncthreads();
+  fetch_records(part_half(F, par), ngroups * nsplit, stage_tag(F.seq, par), stash);
+  __syncthreads();
   if((int) threadIdx.x < ngroups)
   {
-    const double* p = part_half(F, par) + (size_t) threadIdx.x * nsplit * 8;
+    const double* p = stash + (size_t) threadIdx.x * nsplit * 8;
     double s[7] = {0, 0, 0, 0, 0, 0, 0};
     for(int k = 0; k < nsplit; k++)
 #pragma unroll
-      for(int j = 0; j < 7; j++) s[j] += __ldcg(p + k * 8 + j);
+      for(int j = 0; j < 7; j++) s[j] += p[k * 8 + j];
 #pragma unroll
     for(int j = 0; j < 6; j++) sm->E[6 * threadIdx.x + j] = s[j];
     sm->Fl[threadIdx.x] = s[6] > 0.0 ? 1 : 0;
   }
   __syncthreads();
+  GBK_MARK();
 }
 
 // Boltzmann weights / selection / Rosenbluth factor of one segment into result slot `slot` (all threads call; warp 0 works)
@@ -236,6 +265,7 @@ __device__ __forceinline__ void finish_segment(const DevParams& P, const FusedAr
     }
   }
   __syncthreads();
+  GBK_MARK();
 }
 
 // the selected trial joins the molecule being grown (Mol.pos[0] = NewMol.pos[FirstBeadTrial], mc_widom.h:230-241 / 590-599);
@@ -264,6 +294,7 @@ __device__ __forceinline__ void adopt_selection(const DevParams& P, const FusedA
     }
   }
   __syncthreads();
+  GBK_MARK();
 }
 
 // Ewald Fourier delta of [old atoms | new atoms]: the last `ne` CTAs of the grid each take 256 k-vectors; CTA partial
@@ -282,6 +313,14 @@ __device__ __forceinline__ void ewald_slice(const DevParams& P, const FusedArgs&
   cplx* ey = ex + (size_t) n * kx1; cplx* ez = ey + (size_t) n * ky1;
   double* qeff = reinterpret_cast<double*>(ez + (size_t) n * kz1);
   double* pos3 = qeff + n;
+  // the k-vector of this thread and its stored structure factors do not depend on the eik tables: issue those loads first
+  const int kk0 = slice * blockDim.x + threadIdx.x;
+  int kp0 = 0, slot0 = 0; double temp0 = 0.0, ore0 = 0.0, oim0 = 0.0, cre0 = 0.0, cim0 = 0.0;
+  if(kk0 < F.K.nact)
+  {
+    kp0 = F.K.kpack[kk0]; temp0 = F.K.temp[kk0]; slot0 = F.K.slot[kk0];
+    ore0 = F.same_sf[2 * slot0]; oim0 = F.same_sf[2 * slot0 + 1]; cre0 = F.cross_sf[2 * slot0]; cim0 = F.cross_sf[2 * slot0 + 1];
+  }
   __syncthreads();
   for(int i = threadIdx.x; i < n; i += blockDim.x)
   {
@@ -300,19 +339,22 @@ __device__ __forceinline__ void ewald_slice(const DevParams& P, const FusedArgs&
   build_eik(P, pos3, n, ex, ey, ez, threadIdx.x, blockDim.x);
   __syncthreads();
   double same = 0.0, cross = 0.0;
-  for(int kk = slice * blockDim.x + threadIdx.x; kk < F.K.nact; kk += ne * blockDim.x)
+  for(int kk = kk0; kk < F.K.nact; kk += ne * blockDim.x)
   {
-    int kx, ky, kz; unpack_k(F.K.kpack[kk], kx, ky, kz);
+    int kp = kp0, slot = slot0; double temp = temp0, ore = ore0, oim = oim0, cre = cre0, cim = cim0;
+    if(kk != kk0)
+    {
+      kp = F.K.kpack[kk]; temp = F.K.temp[kk]; slot = F.K.slot[kk];
+      ore = F.same_sf[2 * slot]; oim = F.same_sf[2 * slot + 1]; cre = F.cross_sf[2 * slot]; cim = F.cross_sf[2 * slot + 1];
+    }
+    int kx, ky, kz; unpack_k(kp, kx, ky, kz);
     const cplx co = ck_sum(ex, ey, ez, qeff, n, 0, nold, kx, ky, kz);
     const cplx cn = ck_sum(ex, ey, ez, qeff, n, nold, n, kx, ky, kz);
-    const double temp = F.K.temp[kk];
-    const int slot = F.K.slot[kk];
-    const double ore = F.same_sf[2 * slot], oim = F.same_sf[2 * slot + 1];
     const double nre = ore + cn.re - co.re, nim = oim + cn.im - co.im;
     same += temp * (nre * nre + nim * nim);
     same -= temp * (ore * ore + oim * oim);
     F.temp_sf[2 * slot] = nre; F.temp_sf[2 * slot + 1] = nim;
-    cross += temp * (F.cross_sf[2 * slot] * (cn.re - co.re) + F.cross_sf[2 * slot + 1] * (cn.im - co.im));
+    cross += temp * (cre * (cn.re - co.re) + cim * (cn.im - co.im));
   }
   same = warp_sum(same); cross = warp_sum(cross);
   __syncthreads();
@@ -322,17 +364,36 @@ __device__ __forceinline__ void ewald_slice(const DevParams& P, const FusedArgs&
   {
     double s = 0.0, c = 0.0;
     for(int w = 0; w < (int)(blockDim.x >> 5); w++) { s += red[w]; c += red[8 + w]; }
-    out2[2 * slice] = s; out2[2 * slice + 1] = c;
+    const unsigned int tag = stage_tag(F.seq, 2);
+    ll_store(out2 + 4 * slice, 0, s, tag); ll_store(out2 + 4 * slice, 1, c, tag);
+  }
+  GBK_MARK();
+}
+
+// wait for the records of the Ewald CTAs and copy {same, cross} to stash[2 * b]
+__device__ __forceinline__ void fetch_ewald(const FusedArgs& F, const double* in2, double* stash)
+{
+  const int ne = ewald_ctas(F);
+  const unsigned int tag = stage_tag(F.seq, 2);
+  for(int w = threadIdx.x; w < 2 * ne; w += blockDim.x)
+  {
+    double v;
+    while(!ll_load(in2 + 4 * (w >> 1), w & 1, tag, v)) { }
+    stash[w] = v;
   }
 }
 
 // CTA 0: result slot 5 = {same, 2 * cross} summed over the Ewald CTAs in fixed order
-__device__ __forceinline__ void ewald_total_slot(const FusedArgs& F, FusedSmem* sm, const double* in2, bool run)
+__device__ __forceinline__ void ewald_total_slot(const FusedArgs& F, FusedSmem* sm, double* stash, const double* in2, bool run)
 {
+  const int ne = ewald_ctas(F);
+  __syncthreads();
+  if(run) fetch_ewald(F, in2, stash);
+  __syncthreads();
   if(threadIdx.x == 0)
   {
     double s = 0.0, c = 0.0;
-    if(run) { const int ne = ewald_ctas(F); for(int b = 0; b < ne; b++) { s += __ldcg(in2 + 2 * b); c += __ldcg(in2 + 2 * b + 1); } }
+    if(run) for(int b = 0; b < ne; b++) { s += stash[2 * b]; c += stash[2 * b + 1]; }
     sm->res[16 * 5] = s; sm->res[16 * 5 + 1] = 2.0 * c;
   }
   __syncthreads();
@@ -349,12 +410,13 @@ __device__ __forceinline__ void export_molecule(const FusedArgs& F, const SmemMo
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 k_move(DevParams P, SysView S, FusedArgs F)
 {
-  extern __shared__ __align__(16) unsigned char dyn[];
-  __shared__ FusedSmem sm;
-  unsigned int phase = 0;
+  // dynamic shared memory: [FusedSmem | scratch: eik tables of the Ewald stage / stash of the collect steps (>= 12 KB)]
+  extern __shared__ __align__(128) unsigned char dyn_all[];
+  FusedSmem& sm = *reinterpret_cast<FusedSmem*>(dyn_all);
+  unsigned char* dyn = dyn_all + ((sizeof(FusedSmem) + 127) / 128) * 128;
 #ifdef GBK_PHASE_TIMING
   if(blockIdx.x == 0 && threadIdx.x == 0) g_nmarks = 0;
 #endif
@@ -362,6 +424,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
   stage_erfc_table(P, sm.etab);
   if(threadIdx.x < 128) sm.res[threadIdx.x] = 0.0;
   __syncthreads();
+  GBK_MARK();
   PairTables W; W.etab = sm.etab; W.ffp = P.ffA; W.unit = false;
   const int ms = F.ms;
   const int no = ms > 1 ? F.norient : 0;
@@ -372,8 +435,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
     sg[0].type = 0; sg[0].chain = 0; sg[0].n = F.ntrials; sg[0].pool_off = F.pool_off;
     int nsplit = stage_nsplit(F, F.ntrials);
     run_stage(P, S, F, &sm, W, sg, 1, F.ntrials, nsplit, 0);
-    grid_barrier(F, phase);
-    collect_stage(F, &sm, F.ntrials, nsplit, 0);
+    collect_stage(F, &sm, reinterpret_cast<double*>(dyn), F.ntrials, nsplit, 0);
     finish_segment(P, F, &sm, 0, false, F.ntrials, F.u0, 0.0, sm.E, sm.Fl, 0, 1.0);
     adopt_selection(P, F, &sm, 0, false, F.pool_off, 0);
     bool alive = sm.res[13] != 0.0;
@@ -381,25 +443,20 @@ k_move(DevParams P, SysView S, FusedArgs F)
     {
       sg[0].chain = 1; sg[0].n = no; sg[0].pool_off = F.pool_off + F.ntrials;
       nsplit = stage_nsplit(F, no);
-      if(alive) run_stage(P, S, F, &sm, W, sg, 1, no, nsplit, 1);
-      grid_barrier(F, phase);
       if(alive)
       {
-        collect_stage(F, &sm, no, nsplit, 1);
+        run_stage(P, S, F, &sm, W, sg, 1, no, nsplit, 1);
+        collect_stage(F, &sm, reinterpret_cast<double*>(dyn), no, nsplit, 1);
         finish_segment(P, F, &sm, 0, true, no, F.u1, 0.0, sm.E, sm.Fl, 1, sm.res[14]);
         adopt_selection(P, F, &sm, 0, true, F.pool_off + F.ntrials, 1);
         alive = sm.res[16 + 13] != 0.0;
       }
     }
     double* ew = part_half(F, 0) + GBF_PART_EWALD;
-    if(F.do_ewald)
-    {
-      if(alive) ewald_slice(P, F, dyn, sm.red, nullptr, 0, 0, &sm.mN, ms, ew);
-      grid_barrier(F, phase);
-    }
+    if(F.do_ewald && alive) ewald_slice(P, F, dyn, sm.red, nullptr, 0, 0, &sm.mN, ms, ew);
     if(blockIdx.x == 0)
     {
-      if(F.do_ewald) ewald_total_slot(F, &sm, ew, alive);
+      if(F.do_ewald) ewald_total_slot(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
       export_molecule(F, sm.mN, GBK_BUF_GROWN);
     }
   }
@@ -414,10 +471,9 @@ k_move(DevParams P, SysView S, FusedArgs F)
     run_stage(P, S, F, &sm, W, sg, ms > 1 ? 2 : 1, ngroups, nsplit, 0);
     double* ew = part_half(F, 0) + GBF_PART_EWALD;
     if(F.do_ewald) ewald_slice(P, F, dyn, sm.red, nullptr, F.molecule * ms, ms, &sm.mN, 0, ew);
-    grid_barrier(F, phase);
     if(blockIdx.x == 0)
     {
-      collect_stage(F, &sm, ngroups, nsplit, 0);
+      collect_stage(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
       finish_segment(P, F, &sm, 1, false, F.ntrials, 0.0, 0.0, sm.E, sm.Fl, 0, 1.0);
       bool alive = sm.res[13] != 0.0;
       if(ms > 1 && alive)
@@ -430,7 +486,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
         const long long start = F.molecule * ms;
         sm.res[6] = F.C.x[start]; sm.res[7] = F.C.y[start]; sm.res[8] = F.C.z[start];
       }
-      if(F.do_ewald) ewald_total_slot(F, &sm, ew, alive);
+      if(F.do_ewald) ewald_total_slot(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
     }
   }
   else if(F.kind == GBF_REINSERTION)
@@ -443,8 +499,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
     const int ngroups = F.ntrials + 1 + no;
     int nsplit = stage_nsplit(F, ngroups);
     run_stage(P, S, F, &sm, W, sg, ms > 1 ? 3 : 2, ngroups, nsplit, 0);
-    grid_barrier(F, phase);
-    collect_stage(F, &sm, ngroups, nsplit, 0);
+    collect_stage(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
     if(blockIdx.x == 0)
     {
       if((int) threadIdx.x < 6 * (1 + no)) sm.Ekeep[threadIdx.x] = sm.E[6 * F.ntrials + threadIdx.x];
@@ -460,11 +515,10 @@ k_move(DevParams P, SysView S, FusedArgs F)
       StageSeg sc[1];
       sc[0].type = 2; sc[0].chain = 1; sc[0].n = no; sc[0].pool_off = F.pool_off + F.ntrials;
       nsplit = stage_nsplit(F, no);
-      if(alive) run_stage(P, S, F, &sm, W, sc, 1, no, nsplit, 1);
-      grid_barrier(F, phase);
       if(alive)
       {
-        collect_stage(F, &sm, no, nsplit, 1);
+        run_stage(P, S, F, &sm, W, sc, 1, no, nsplit, 1);
+        collect_stage(F, &sm, reinterpret_cast<double*>(dyn), no, nsplit, 1);
         finish_segment(P, F, &sm, 2, true, no, F.u1, 0.0, sm.E, sm.Fl, 1, sm.res[14]);
         adopt_selection(P, F, &sm, 2, true, F.pool_off + F.ntrials, 1);
         alive = sm.res[16 + 13] != 0.0;
@@ -472,11 +526,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
       nl = 1;
     }
     double* ew = part_half(F, 0) + GBF_PART_EWALD;
-    if(F.do_ewald)
-    {
-      if(alive) ewald_slice(P, F, dyn, sm.red, nullptr, F.molecule * ms, ms, &sm.mN, ms, ew);
-      grid_barrier(F, phase);
-    }
+    if(F.do_ewald && alive) ewald_slice(P, F, dyn, sm.red, nullptr, F.molecule * ms, ms, &sm.mN, ms, ew);
     if(blockIdx.x == 0)
     {
       if(alive)
@@ -490,7 +540,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
         }
         if(ms > 1) finish_segment(P, F, &sm, 3, true, no, 0.0, 0.0, sm.Ekeep + 6, sm.Fkeep + 1, 3, sm.res[16 * nl + 14]);
       }
-      if(F.do_ewald) ewald_total_slot(F, &sm, ew, alive);
+      if(F.do_ewald) ewald_total_slot(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
       export_molecule(F, sm.mN, GBK_BUF_TEMP);            // tempMolStorage, StoreNewLocation_Reinsertion
     }
   }
@@ -509,7 +559,8 @@ k_move(DevParams P, SysView S, FusedArgs F)
     __syncthreads();
     const int ne = F.do_ewald ? ewald_ctas(F) : 0;
     const int npair = max(1, (int) gridDim.x - ne);          // CTAs that share the pair items
-    const int nslice = max(1, min((F.natoms + 255) / 256, GBF_PART_EWALD / 16));
+    const int nslice = max(1, min((F.natoms + 255) / 256, GBF_MAX_ITEMS / 2));
+    const unsigned int tag0 = stage_tag(F.seq, 0);
     double* part = part_half(F, 0);
     if((int) blockIdx.x < npair)
     {
@@ -525,25 +576,36 @@ k_move(DevParams P, SysView S, FusedArgs F)
           sm.T.q[a] = M.a[6][a] * M.a[8][a]; sm.T.scale[a] = M.a[7][a]; sm.T.type[a] = M.type[a]; sm.T.slot[a] = 0;
         }
         __syncthreads();
-        group_energy<0>(P, W, S, F, &sm, (int) F.molecule, ms, slice, nslice, part + (size_t) w * 8);
+        group_energy<0>(P, W, S, F, &sm, (int) F.molecule, ms, slice, nslice, part + (size_t) w * 16, tag0);
       }
     }
     double* ew = part + GBF_PART_EWALD;
     if(F.do_ewald) ewald_slice(P, F, dyn, sm.red, &sm.mO, 0, ms, &sm.mN, ms, ew);
-    grid_barrier(F, phase);
     if(blockIdx.x == 0)
     {
       // delta = sum(new) - sum(old) over the slices in fixed order (mc_single_particle.h:183-200); overlap of NEW only (:768-769)
+      double* stash = reinterpret_cast<double*>(dyn);
+      __syncthreads();
+      fetch_records(part, 2 * nslice, tag0, stash);
+      if(F.do_ewald) fetch_ewald(F, ew, stash + GBF_MAX_ITEMS * 8);
+      __syncthreads();
+      GBK_MARK();
       if(threadIdx.x < 7)
       {
         double n = 0.0, o = 0.0;
-        for(int b = 0; b < nslice; b++) { n += __ldcg(part + (size_t) b * 8 + threadIdx.x); o += __ldcg(part + (size_t)(nslice + b) * 8 + threadIdx.x); }
+        for(int b = 0; b < nslice; b++) { n += stash[b * 8 + threadIdx.x]; o += stash[(nslice + b) * 8 + threadIdx.x]; }
         if(threadIdx.x < 6) sm.res[64 + threadIdx.x] = n - o;
         else { sm.res[64 + 6] = n > 0.0 ? 1.0 : 0.0; sm.res[64 + 7] = n > 0.0 ? 0.0 : 1.0; }
       }
       __syncthreads();
-      const bool run = !F.check_overlap || sm.res[64 + 6] == 0.0;
-      if(F.do_ewald) ewald_total_slot(F, &sm, ew, run);
+      if(threadIdx.x == 0)
+      {
+        const bool run = !F.check_overlap || sm.res[64 + 6] == 0.0;
+        double sS = 0.0, cS = 0.0;
+        if(run) for(int b = 0; b < ne; b++) { sS += stash[GBF_MAX_ITEMS * 8 + 2 * b]; cS += stash[GBF_MAX_ITEMS * 8 + 2 * b + 1]; }
+        sm.res[16 * 5] = sS; sm.res[16 * 5 + 1] = 2.0 * cS;
+      }
+      __syncthreads();
       export_molecule(F, sm.mN, GBK_BUF_NEW);
       export_molecule(F, sm.mO, GBK_BUF_OLD);
     }
@@ -553,10 +615,16 @@ k_move(DevParams P, SysView S, FusedArgs F)
   if(blockIdx.x == 0)
   {
     __syncthreads();
-    if(threadIdx.x < 128) { F.host_result[threadIdx.x] = sm.res[threadIdx.x]; F.B.result(0)[threadIdx.x] = sm.res[threadIdx.x]; }
-    __threadfence_system();
-    __syncthreads();
-    if(threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(F.host_flag) = F.seq;
+    GBK_MARK();
+    if(threadIdx.x < 32)
+    {
+      // one warp stores the 1 KB block (32 B per lane), ONE system-scope fence orders it before the flag
+      const double4 v = reinterpret_cast<const double4*>(sm.res)[threadIdx.x];
+      reinterpret_cast<double4*>(F.host_result)[threadIdx.x] = v;
+      reinterpret_cast<double4*>(F.B.result(0))[threadIdx.x] = v;
+      __syncwarp();
+      if(threadIdx.x == 0) { __threadfence_system(); *reinterpret_cast<volatile unsigned long long*>(F.host_flag) = F.seq; }
+    }
   }
 #ifdef GBK_PHASE_TIMING
   GBK_MARK();

@@ -68,21 +68,23 @@ __device__ __forceinline__ RosenResult rosenbluth_warp(double lb, bool surv, int
   if(mask == 0u) return r;
   double largest = -INFINITY;
   for(unsigned m = mask; m; m &= m - 1) { const int b = __ffs(m) - 1; largest = fmax(largest, __shfl_sync(0xffffffffu, lb, b)); }
+  // every lane evaluates its own two exponentials once; the sums below only move them around, in trial order
+  const double w_shift = exp(lb - largest), w_plain = exp(lb);
   int sel = __ffs(mask) - 1;
   if(do_select)
   {
     double sum = 0.0;
-    for(unsigned m = mask; m; m &= m - 1) { const int b = __ffs(m) - 1; sum += exp(__shfl_sync(0xffffffffu, lb, b) - largest); }
+    for(unsigned m = mask; m; m &= m - 1) { const int b = __ffs(m) - 1; sum += __shfl_sync(0xffffffffu, w_shift, b); }
     const double ws = uniform * sum;
     unsigned m = mask; int b = __ffs(m) - 1; m &= m - 1;
-    double cumw = exp(__shfl_sync(0xffffffffu, lb, b) - largest);
-    while(cumw < ws && m) { b = __ffs(m) - 1; m &= m - 1; cumw += exp(__shfl_sync(0xffffffffu, lb, b) - largest); }
+    double cumw = __shfl_sync(0xffffffffu, w_shift, b);
+    while(cumw < ws && m) { b = __ffs(m) - 1; m &= m - 1; cumw += __shfl_sync(0xffffffffu, w_shift, b); }
     sel = b;
   }
   double R = 0.0, Rsel = 0.0;
   for(unsigned m = mask; m; m &= m - 1)
   {
-    const int b = __ffs(m) - 1; const double w = exp(__shfl_sync(0xffffffffu, lb, b));
+    const int b = __ffs(m) - 1; const double w = __shfl_sync(0xffffffffu, w_plain, b);
     R += w; if(b == sel) Rsel = w;
   }
   r.sel_lane = sel; r.R = R; r.R_minus_sel = R - Rsel;

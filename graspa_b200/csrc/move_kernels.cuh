@@ -24,8 +24,8 @@ struct MoveBufs
   // result slots of 16 doubles: 0 first bead (new), 1 chain (new), 2 first bead (old/retrace), 3 chain (old/retrace),
   // 4 single-body delta, 5 Ewald {same, 2*cross}, 6-7 spare.  Fused move calls read all of them back in one copy.
   __host__ __device__ double* result(int slot = 0) const { return stage_e() + GBK_MV_MAXT * 6 + 16 * slot; }
-  __host__ __device__ double* partial() const { return result(0) + 128; }                                     // 4096 doubles of CTA partials
-  static size_t doubles() { return 9 * GBK_MV_TRIAL_SLOTS + 36 * GBK_MV_MOL_SLOTS + GBK_MV_MAXT * 6 + 128 + 4096; }
+  __host__ __device__ double* partial() const { return result(0) + 128; }                                     // 8192 doubles of CTA partials (128-byte aligned)
+  static size_t doubles() { return 9 * GBK_MV_TRIAL_SLOTS + 36 * GBK_MV_MOL_SLOTS + GBK_MV_MAXT * 6 + 128 + 8192; }
   static size_t ints() { return GBK_MV_TRIAL_SLOTS + 4 * GBK_MV_MOL_SLOTS + GBK_MV_MAXT + 16; }
 };
 

@@ -191,3 +191,96 @@ __device__ __forceinline__ void pair_group_generic(const DevParams& P, const Pai
     flag |= acc.flag;
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Latency-oriented flavour for the single-move kernels, where one warp sees only a handful of system atoms and
+// what costs is the number of DEPENDENT memory round trips, not arithmetic:
+//   * the live ranges are walked as ONE concatenated index space (one pass, not one pass per range);
+//   * type, charge and scaling factors of a system atom are fetched in the same round trip as its position and
+//     travel through the queue, so the drain needs no second trip to global memory.
+// ---------------------------------------------------------------------------------------------
+struct WarpQueueG
+{
+  double r2[GBK_QCAP];
+  double qe[GBK_QCAP];       // charge * scaleCoul of the system atom
+  double sc[GBK_QCAP];       // its LJ scaling factor
+  int    code[GBK_QCAP];     // trial atom | type << 6 | kind << 20
+};
+
+__device__ __forceinline__ void drain_flat(const DevParams& P, const PairTables& W, const TrialGroup* T, const WarpQueueG* Q,
+                                           int lane, int off, int n, double* e6, int& flag)
+{
+  if(lane < n)
+  {
+    const double r2 = Q->r2[off + lane];
+    const int code = Q->code[off + lane];
+    const int a = code & 63, type = (code >> 6) & 0x3fff, kind = code >> 20;
+    const int row = type * P.ntypes + T->type[a];
+    double scaling = T->scale[a];
+    if(!P.all_unit_scale) scaling *= Q->sc[off + lane];
+    const double qq = Q->qe[off + lane] * T->q[a];
+    double ev, er; int fl;
+    pair_energy(P, W.etab, W.ffp, W.unit, r2, row, scaling, qq, ev, er, fl);
+    e6[0] += (kind == 0) ? ev : 0.0; e6[1] += (kind == 0) ? er : 0.0;
+    e6[2] += (kind == 1) ? ev : 0.0; e6[3] += (kind == 1) ? er : 0.0;
+    e6[4] += (kind == 2) ? ev : 0.0; e6[5] += (kind == 2) ? er : 0.0;
+    flag |= fl;
+  }
+}
+
+// e6 = lane-partial sums {HHv, HHr, HGv, HGr, GGv, GGr}; atoms of molecule new_molid of component new_comp are skipped
+template <int CS>
+__device__ __forceinline__ void pair_group_flat(const DevParams& P, const PairTables& W, const SysView& S, const SegList& L,
+                                                int new_comp, int new_molid, const TrialGroup* T, int cs_dyn, WarpQueueG* Q,
+                                                int wslice, int nslice, double* e6, int& flag)
+{
+  const int lane = (int) lane_id();
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int cs = CS > 0 ? CS : cs_dyn;
+  const double cut_max = P.no_charges ? P.cut_vdw2 : fmax(P.cut_vdw2, P.cut_coul2);
+  CellRegs<0> C; C.load(P);
+  int total = 0;
+  for(int s = 0; s < L.nseg; s++) total += L.count[s];
+  int qn = 0;
+  for(int base = 32 * wslice; base < total; base += 32 * nslice)
+  {
+    const int v = base + lane;
+    bool valid = v < total;
+    int off = valid ? v : total - 1, s = 0;
+    while(s + 1 < L.nseg && off >= L.count[s]) { off -= L.count[s]; s++; }
+    const int i = L.start[s] + off;
+    const double ax = S.fx[i], ay = S.fy[i], az = S.fz[i];
+    const int m = S.molid[i], type = S.type[i];
+    double qe = S.q[i], sc = 1.0;
+    if(!P.all_unit_scale) { qe *= S.scoul[i]; sc = S.scale[i]; }
+    valid = valid && !(L.comp[s] == new_comp && m == new_molid);
+    const int tag = (type << 6) | (L.kind[s] << 20);
+    for(int a = 0; a < cs; a++)
+    {
+      const double r2 = C.r2(ax - T->fx[a], ay - T->fy[a], az - T->fz[a]);
+      const bool hit = valid && (r2 < cut_max);
+      const unsigned mk = __ballot_sync(0xffffffffu, hit);
+      if(hit) { const int p = qn + __popc(mk & lt_mask); Q->r2[p] = r2; Q->qe[p] = qe; Q->sc[p] = sc; Q->code[p] = tag | a; }
+      qn += __popc(mk);
+      if(CS == 0 && qn >= GBK_QCAP - 32)
+      {
+        __syncwarp();
+        do { qn -= 32; drain_flat(P, W, T, Q, lane, qn, 32, e6, flag); } while(qn >= 32);
+        __syncwarp();
+      }
+    }
+    if(CS > 0 && qn >= GBK_QCAP - 32 * CS)
+    {
+      __syncwarp();
+      do { qn -= 32; drain_flat(P, W, T, Q, lane, qn, 32, e6, flag); } while(qn >= 32);
+      __syncwarp();
+    }
+  }
+  if(qn > 0)
+  {
+    __syncwarp();
+    while(qn >= 32) { qn -= 32; drain_flat(P, W, T, Q, lane, qn, 32, e6, flag); }
+    if(qn > 0) drain_flat(P, W, T, Q, lane, 0, qn, e6, flag);
+    __syncwarp();
+  }
+}
