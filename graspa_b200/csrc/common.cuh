@@ -7,6 +7,15 @@
 #include "erfc_table.inc"
 
 #define GBK_PI 3.14159265358979323846
+#ifdef GBK_PHASE_TIMING
+#include <cstdio>
+__device__ long long g_marks[64];
+__device__ int g_nmarks;
+#define GBK_MARK() do { if(blockIdx.x == 0 && threadIdx.x == 0) g_marks[g_nmarks++] = clock64(); } while(0)
+#else
+#define GBK_MARK() do { } while(0)
+#endif
+
 #define GBK_MAX_SEG 16
 #define GBK_QCAP 128           // per-warp in-cutoff queue entries (up to 31 left over + 3 x 32 pushed per iteration)
 #define GBK_MAX_CS 32          // max atoms of one trial group handled by the warp pair loop

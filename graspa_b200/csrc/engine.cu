@@ -97,6 +97,7 @@ struct gb_engine
   DevBuf<long long> d_idx0, d_idx1;
   DevBuf<unsigned int> d_ticket;
   double* h_pinned = nullptr;            // 4 KB pinned result slot
+  double* h_results = nullptr;           // 2 KB of h_pinned: tagged result records of k_move
   unsigned long long move_seq = 0;       // sequence number of the last k_move launch (published to h_pinned + 256)
 
   // single-move path
@@ -325,7 +326,7 @@ int gb_engine_create(gb_engine** out, int device)
   e->smem_optin = (size_t) optin;
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&e->ev0)); CUDA_TRY(cudaEventCreate(&e->ev1));
-  CUDA_TRY(cudaMallocHost(&e->h_pinned, 4096)); memset(e->h_pinned, 0, 4096);
+  CUDA_TRY(cudaMallocHost(&e->h_pinned, 8192)); memset(e->h_pinned, 0, 8192); e->h_results = e->h_pinned + 512;
   CUDA_TRY(e->d_ticket.reserve(16)); CUDA_TRY(cudaMemset(e->d_ticket.p, 0, 16 * sizeof(unsigned int)));
   CUDA_TRY(e->d_result.reserve(512));
   {

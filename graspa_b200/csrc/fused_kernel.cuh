@@ -39,19 +39,10 @@ struct FusedArgs
   CompView C; MoveBufs B;
   SegList L;                              // live ranges with the kinds of THIS move
   KTable K; const double* same_sf; const double* cross_sf; double* temp_sf;
-  double* host_result;                    // pinned host memory (UVA): the 8 result slots are stored there directly ...
-  unsigned long long* host_flag;          // ... followed by this move's sequence number, which the host polls
-  unsigned long long seq;
+  double* host_result;                    // pinned host memory (UVA): 128 tagged 16-byte records the host polls
+  unsigned long long seq;                 // launch counter; its low 32 bits tag every record of this launch
 };
 
-#ifdef GBK_PHASE_TIMING
-#include <cstdio>
-__device__ long long g_marks[64];
-__device__ int g_nmarks;
-#define GBK_MARK() do { if(blockIdx.x == 0 && threadIdx.x == 0) g_marks[g_nmarks++] = clock64(); } while(0)
-#else
-#define GBK_MARK() do { } while(0)
-#endif
 
 // Cross-CTA hand-over without barriers or fences.  A CTA publishes a partial sum as 16-byte stores {lo, tag, hi, tag}:
 // every 8-byte half carries its own validity tag (8-byte accesses are single-copy atomic), so a consumer that polls the
@@ -93,6 +84,8 @@ struct FusedSmem
   double Ekeep[33 * 6]; int Fkeep[33];                      // reinsertion: the retrace groups of stage 1, finished at the end
   __align__(32) double res[8 * 16];                                       // the result slots (MoveBufs::result layout)
   SmemMol mN, mO;                                           // molecule being grown / proposed, and its old image
+  SmemMol tmpl, exist;                                      // template molecule (slot 0 of the component) and the selected molecule
+  double pool[3 * (2 * 32 + 2 * 32 + 1)];                   // the random-pool entries this move consumes
 };
 
 // one segment of a stage: n trial groups of one CBMC type
@@ -107,51 +100,48 @@ __device__ __forceinline__ int stage_nsplit(const FusedArgs& F, int ngroups)
   return max(1, min(ns, cap));
 }
 
-// get_random_trial_position, mc_widom.h:122-213
-__device__ __forceinline__ AtomRec first_bead_atom(const DevParams& P, const FusedArgs& F, int type, int g, long long pool_off)
+// get_random_trial_position, mc_widom.h:122-213 (template / selected molecule / pool entries come from shared memory)
+__device__ __forceinline__ AtomRec first_bead_atom(const DevParams& P, const FusedArgs& F, const FusedSmem* sm, int type, int g, long long pool_off)
 {
   const bool insertion_like = (type == 0 || type == 4);
-  const long long start = insertion_like ? 0 : F.molecule * F.ms;
+  const SmemMol& M = insertion_like ? sm->tmpl : sm->exist;
   AtomRec r; r.scale = F.scale0; r.scoul = F.scale1;
-  if(!insertion_like) { r.scale = F.C.scale[start]; r.scoul = F.C.scoul[start]; }
+  if(!insertion_like) { r.scale = M.a[7][0]; r.scoul = M.a[8][0]; }
   const bool existing = (type == 1 || type == 3 || type == 5) && g == 0;
-  if(existing) { r.x = F.C.x[start]; r.y = F.C.y[start]; r.z = F.C.z[start]; }
-  else { const double* u = F.pool3 + 3 * (pool_off + g); r.x = P.cell[0] * u[0]; r.y = P.cell[4] * u[1]; r.z = P.cell[8] * u[2]; }
+  if(existing) { r.x = M.a[0][0]; r.y = M.a[1][0]; r.z = M.a[2][0]; }
+  else { const double* u = sm->pool + 3 * (pool_off - F.pool_off + g); r.x = P.cell[0] * u[0]; r.y = P.cell[4] * u[1]; r.z = P.cell[8] * u[2]; }
   to_frac(P, r.x, r.y, r.z, r.fx, r.fy, r.fz);
-  r.q = F.C.q[start]; r.type = F.C.type[start];
+  r.q = M.a[6][0]; r.type = M.type[0];
   return r;
 }
 
 // get_random_trial_orientation, mc_widom.h:215-303: atom 1 + a of orientation g around the first bead (fbx, fby, fbz)
-__device__ __forceinline__ AtomRec chain_atom(const DevParams& P, const FusedArgs& F, int type, int g, int a, long long pool_off,
+__device__ __forceinline__ AtomRec chain_atom(const DevParams& P, const FusedArgs& F, const FusedSmem* sm, int type, int g, int a, long long pool_off,
                                               double fbx, double fby, double fbz, double scale, double scoul)
 {
   const bool insertion_like = (type == 0 || type == 4);
-  const long long start = (insertion_like ? 0 : F.molecule * F.ms) + 1;        // start_position, mc_widom.h:536-556
-  double vx = F.C.x[1 + a] - F.C.x[0], vy = F.C.y[1 + a] - F.C.y[0], vz = F.C.z[1 + a] - F.C.z[0];   // :256
+  const SmemMol& M = insertion_like ? sm->tmpl : sm->exist;                    // start_position, mc_widom.h:536-556
+  const SmemMol& G = sm->tmpl;
+  double vx = G.a[0][1 + a] - G.a[0][0], vy = G.a[1][1 + a] - G.a[1][0], vz = G.a[2][1 + a] - G.a[2][0];   // :256
   AtomRec r;
-  if((type == 1 || type == 3 || type == 5) && g == 0) { r.x = F.C.x[start + a]; r.y = F.C.y[start + a]; r.z = F.C.z[start + a]; }
+  if((type == 1 || type == 3 || type == 5) && g == 0) { r.x = M.a[0][1 + a]; r.y = M.a[1][1 + a]; r.z = M.a[2][1 + a]; }
   else
   {
-    const double* u = F.pool3 + 3 * (pool_off + g);
+    const double* u = sm->pool + 3 * (pool_off - F.pool_off + g);
     rotate_quaternion(vx, vy, vz, u[0], u[1], u[2]);
     r.x = fbx + vx; r.y = fby + vy; r.z = fbz + vz;
   }
   to_frac(P, r.x, r.y, r.z, r.fx, r.fy, r.fz);
   r.scale = scale; r.scoul = scoul;
-  r.q = F.C.q[start + a]; r.type = F.C.type[start + a];
+  r.q = M.a[6][1 + a]; r.type = M.type[1 + a];
   return r;
 }
 
 // first bead the orientations of `type` are grown around: the selected trial (growth) or the existing atom (deletion / retrace)
 __device__ __forceinline__ void chain_anchor(const FusedArgs& F, const FusedSmem* sm, int type, double& x, double& y, double& z, double& scale, double& scoul)
 {
-  if(type == 1 || type == 3 || type == 5)
-  {
-    const long long start = F.molecule * F.ms;
-    x = F.C.x[start]; y = F.C.y[start]; z = F.C.z[start]; scale = F.C.scale[start]; scoul = F.C.scoul[start];
-  }
-  else { x = sm->mN.a[0][0]; y = sm->mN.a[1][0]; z = sm->mN.a[2][0]; scale = sm->mN.a[7][0]; scoul = sm->mN.a[8][0]; }
+  const SmemMol& M = (type == 1 || type == 3 || type == 5) ? sm->exist : sm->mN;
+  x = M.a[0][0]; y = M.a[1][0]; z = M.a[2][0]; scale = M.a[7][0]; scoul = M.a[8][0];
 }
 
 __device__ __forceinline__ void set_trial(TrialGroup& T, int a, const AtomRec& r)
@@ -194,11 +184,11 @@ __device__ __forceinline__ void run_stage(const DevParams& P, const SysView& S, 
     const int type = segs[si].type; const bool chain = segs[si].chain != 0; const long long off = segs[si].pool_off;
     const int cs = chain ? F.ms - 1 : 1;
     __syncthreads();
-    if(!chain) { if(threadIdx.x == 0) set_trial(sm->T, 0, first_bead_atom(P, F, type, g, off)); }
+    if(!chain) { if(threadIdx.x == 0) set_trial(sm->T, 0, first_bead_atom(P, F, sm, type, g, off)); }
     else if((int) threadIdx.x < cs)
     {
       double ax, ay, az, sc, scc; chain_anchor(F, sm, type, ax, ay, az, sc, scc);
-      set_trial(sm->T, threadIdx.x, chain_atom(P, F, type, g, threadIdx.x, off, ax, ay, az, sc, scc));
+      set_trial(sm->T, threadIdx.x, chain_atom(P, F, sm, type, g, threadIdx.x, off, ax, ay, az, sc, scc));
     }
     __syncthreads();
     const int new_molid = (type == 0 || type == 4) ? F.nmol : (int) F.molecule;
@@ -282,7 +272,7 @@ __device__ __forceinline__ void adopt_selection(const DevParams& P, const FusedA
     {
       if(threadIdx.x == 0)
       {
-        const AtomRec a = first_bead_atom(P, F, type, sel, pool_off);
+        const AtomRec a = first_bead_atom(P, F, sm, type, sel, pool_off);
         put_atom(sm->mN, 0, a);
         r[6] = a.x; r[7] = a.y; r[8] = a.z;
       }
@@ -290,7 +280,7 @@ __device__ __forceinline__ void adopt_selection(const DevParams& P, const FusedA
     else if((int) threadIdx.x < F.ms - 1)
     {
       double ax, ay, az, sc, scc; chain_anchor(F, sm, type, ax, ay, az, sc, scc);
-      put_atom(sm->mN, 1 + threadIdx.x, chain_atom(P, F, type, sel, threadIdx.x, pool_off, ax, ay, az, sc, scc));
+      put_atom(sm->mN, 1 + threadIdx.x, chain_atom(P, F, sm, type, sel, threadIdx.x, pool_off, ax, ay, az, sc, scc));
     }
   }
   __syncthreads();
@@ -301,7 +291,7 @@ __device__ __forceinline__ void adopt_selection(const DevParams& P, const FusedA
 // {same, cross} goes to out2[2 * slice].  old atoms: component slots (oldS == nullptr) or a shared-memory molecule.
 __device__ __forceinline__ int ewald_ctas(const FusedArgs& F) { return min((int) gridDim.x, (F.K.nact + 255) / 256); }
 
-__device__ __forceinline__ void ewald_slice(const DevParams& P, const FusedArgs& F, unsigned char* dyn, double* red, const SmemMol* oldS, long long old_start,
+__device__ __forceinline__ void ewald_slice(const DevParams& P, const FusedArgs& F, unsigned char* dyn, double* red, const SmemMol* oldS,
                                             int nold, const SmemMol* newS, int nnew, double* out2)
 {
   const int ne = ewald_ctas(F);
@@ -326,8 +316,7 @@ __device__ __forceinline__ void ewald_slice(const DevParams& P, const FusedArgs&
   {
     if(i < nold)
     {
-      if(oldS == nullptr) { pos3[3 * i] = F.C.x[old_start + i]; pos3[3 * i + 1] = F.C.y[old_start + i]; pos3[3 * i + 2] = F.C.z[old_start + i]; qeff[i] = F.C.scoul[old_start + i] * F.C.q[old_start + i]; }
-      else { pos3[3 * i] = oldS->a[0][i]; pos3[3 * i + 1] = oldS->a[1][i]; pos3[3 * i + 2] = oldS->a[2][i]; qeff[i] = oldS->a[8][i] * oldS->a[6][i]; }
+      { pos3[3 * i] = oldS->a[0][i]; pos3[3 * i + 1] = oldS->a[1][i]; pos3[3 * i + 2] = oldS->a[2][i]; qeff[i] = oldS->a[8][i] * oldS->a[6][i]; }
     }
     else
     {
@@ -421,13 +410,50 @@ k_move(DevParams P, SysView S, FusedArgs F)
   if(blockIdx.x == 0 && threadIdx.x == 0) g_nmarks = 0;
 #endif
   GBK_MARK();
-  stage_erfc_table(P, sm.etab);
-  if(threadIdx.x < 128) sm.res[threadIdx.x] = 0.0;
+  const int ms = F.ms;
+  const int no = ms > 1 ? F.norient : 0;
+  // prologue, one round trip to L2 for everything a stage set-up needs: warp 0 fetches the template molecule, the selected
+  // molecule and the pool entries of this move (or builds the translation / rotation proposal) while warps 1-7 stage the erfc table
+  if(threadIdx.x < 32)
+  {
+    if(F.kind == GBF_SINGLE)
+    {
+      if((int) threadIdx.x < ms)
+      {
+        ProposeArgs A; memset(&A, 0, sizeof(A));
+        A.move_type = F.move_type; A.ms = ms; A.start = F.molecule * ms; A.pool_index = F.pool_off; A.pool3 = F.pool3;
+        A.maxc[0] = F.maxc[0]; A.maxc[1] = F.maxc[1]; A.maxc[2] = F.maxc[2]; A.C = F.C; A.B = F.B;
+        AtomRec nw, od;
+        propose_atom(P, A, threadIdx.x, nw, od);
+        put_atom(sm.mN, threadIdx.x, nw); put_atom(sm.mO, threadIdx.x, od);
+      }
+    }
+    else
+    {
+      const int npool = F.ntrials + no + (F.kind == GBF_REINSERTION ? 1 + no : 0);
+      for(int i = threadIdx.x; i < 3 * npool; i += 32) sm.pool[i] = F.pool3[3 * F.pool_off + i];
+      if((int) threadIdx.x < ms)
+      {
+        const int i = threadIdx.x;
+        sm.tmpl.a[0][i] = F.C.x[i]; sm.tmpl.a[1][i] = F.C.y[i]; sm.tmpl.a[2][i] = F.C.z[i];
+        sm.tmpl.a[6][i] = F.C.q[i]; sm.tmpl.a[7][i] = F.C.scale[i]; sm.tmpl.a[8][i] = F.C.scoul[i]; sm.tmpl.type[i] = F.C.type[i];
+        if(F.kind != GBF_INSERTION)
+        {
+          const long long j = F.molecule * ms + i;
+          sm.exist.a[0][i] = F.C.x[j]; sm.exist.a[1][i] = F.C.y[j]; sm.exist.a[2][i] = F.C.z[j];
+          sm.exist.a[6][i] = F.C.q[j]; sm.exist.a[7][i] = F.C.scale[j]; sm.exist.a[8][i] = F.C.scoul[j]; sm.exist.type[i] = F.C.type[j];
+        }
+      }
+    }
+  }
+  else
+  {
+    for(int i = threadIdx.x - 32; i < (GBK_ERFC_DEG + 1) * GBK_ERFC_NINT; i += blockDim.x - 32) sm.etab[i] = __ldg(&P.erfc_tab[i]);
+    if(threadIdx.x - 32 < 128) sm.res[threadIdx.x - 32] = 0.0;
+  }
   __syncthreads();
   GBK_MARK();
   PairTables W; W.etab = sm.etab; W.ffp = P.ffA; W.unit = false;
-  const int ms = F.ms;
-  const int no = ms > 1 ? F.norient : 0;
 
   if(F.kind == GBF_INSERTION)
   {
@@ -453,7 +479,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
       }
     }
     double* ew = part_half(F, 0) + GBF_PART_EWALD;
-    if(F.do_ewald && alive) ewald_slice(P, F, dyn, sm.red, nullptr, 0, 0, &sm.mN, ms, ew);
+    if(F.do_ewald && alive) ewald_slice(P, F, dyn, sm.red, &sm.exist, 0, &sm.mN, ms, ew);
     if(blockIdx.x == 0)
     {
       if(F.do_ewald) ewald_total_slot(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
@@ -470,7 +496,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
     const int nsplit = stage_nsplit(F, ngroups);
     run_stage(P, S, F, &sm, W, sg, ms > 1 ? 2 : 1, ngroups, nsplit, 0);
     double* ew = part_half(F, 0) + GBF_PART_EWALD;
-    if(F.do_ewald) ewald_slice(P, F, dyn, sm.red, nullptr, F.molecule * ms, ms, &sm.mN, 0, ew);
+    if(F.do_ewald) ewald_slice(P, F, dyn, sm.red, &sm.exist, ms, &sm.mN, 0, ew);
     if(blockIdx.x == 0)
     {
       collect_stage(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
@@ -483,8 +509,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
       }
       if(threadIdx.x == 0 && sm.res[9] != 0.0 && sm.res[11] > 0.0)
       {
-        const long long start = F.molecule * ms;
-        sm.res[6] = F.C.x[start]; sm.res[7] = F.C.y[start]; sm.res[8] = F.C.z[start];
+        sm.res[6] = sm.exist.a[0][0]; sm.res[7] = sm.exist.a[1][0]; sm.res[8] = sm.exist.a[2][0];
       }
       if(F.do_ewald) ewald_total_slot(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
     }
@@ -526,7 +551,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
       nl = 1;
     }
     double* ew = part_half(F, 0) + GBF_PART_EWALD;
-    if(F.do_ewald && alive) ewald_slice(P, F, dyn, sm.red, nullptr, F.molecule * ms, ms, &sm.mN, ms, ew);
+    if(F.do_ewald && alive) ewald_slice(P, F, dyn, sm.red, &sm.exist, ms, &sm.mN, ms, ew);
     if(blockIdx.x == 0)
     {
       if(alive)
@@ -535,8 +560,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
         finish_segment(P, F, &sm, 3, false, 1, 0.0, sm.res[1], sm.Ekeep, sm.Fkeep, 2, 1.0);
         if(threadIdx.x == 0 && sm.res[32 + 9] != 0.0 && sm.res[32 + 11] > 0.0)
         {
-          const long long start = F.molecule * ms;
-          sm.res[32 + 6] = F.C.x[start]; sm.res[32 + 7] = F.C.y[start]; sm.res[32 + 8] = F.C.z[start];
+          sm.res[32 + 6] = sm.exist.a[0][0]; sm.res[32 + 7] = sm.exist.a[1][0]; sm.res[32 + 8] = sm.exist.a[2][0];
         }
         if(ms > 1) finish_segment(P, F, &sm, 3, true, no, 0.0, 0.0, sm.Ekeep + 6, sm.Fkeep + 1, 3, sm.res[16 * nl + 14]);
       }
@@ -547,16 +571,6 @@ k_move(DevParams P, SysView S, FusedArgs F)
   else
   {
     // ---- translation / rotation: every CTA builds the proposal; items = (new | old) x atom slices; Ewald CTAs at the grid's end
-    if((int) threadIdx.x < ms)
-    {
-      ProposeArgs A; memset(&A, 0, sizeof(A));
-      A.move_type = F.move_type; A.ms = ms; A.start = F.molecule * ms; A.pool_index = F.pool_off; A.pool3 = F.pool3;
-      A.maxc[0] = F.maxc[0]; A.maxc[1] = F.maxc[1]; A.maxc[2] = F.maxc[2]; A.C = F.C; A.B = F.B;
-      AtomRec nw, od;
-      propose_atom(P, A, threadIdx.x, nw, od);
-      put_atom(sm.mN, threadIdx.x, nw); put_atom(sm.mO, threadIdx.x, od);
-    }
-    __syncthreads();
     const int ne = F.do_ewald ? ewald_ctas(F) : 0;
     const int npair = max(1, (int) gridDim.x - ne);          // CTAs that share the pair items
     const int nslice = max(1, min((F.natoms + 255) / 256, GBF_MAX_ITEMS / 2));
@@ -580,7 +594,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
       }
     }
     double* ew = part + GBF_PART_EWALD;
-    if(F.do_ewald) ewald_slice(P, F, dyn, sm.red, &sm.mO, 0, ms, &sm.mN, ms, ew);
+    if(F.do_ewald) ewald_slice(P, F, dyn, sm.red, &sm.mO, ms, &sm.mN, ms, ew);
     if(blockIdx.x == 0)
     {
       // delta = sum(new) - sum(old) over the slices in fixed order (mc_single_particle.h:183-200); overlap of NEW only (:768-769)
@@ -616,14 +630,12 @@ k_move(DevParams P, SysView S, FusedArgs F)
   {
     __syncthreads();
     GBK_MARK();
-    if(threadIdx.x < 32)
+    // every double goes out as one 16-byte store {lo, tag, hi, tag}: the host polls the tags, no system-scope fence needed
+    if(threadIdx.x < 128)
     {
-      // one warp stores the 1 KB block (32 B per lane), ONE system-scope fence orders it before the flag
-      const double4 v = reinterpret_cast<const double4*>(sm.res)[threadIdx.x];
-      reinterpret_cast<double4*>(F.host_result)[threadIdx.x] = v;
-      reinterpret_cast<double4*>(F.B.result(0))[threadIdx.x] = v;
-      __syncwarp();
-      if(threadIdx.x == 0) { __threadfence_system(); *reinterpret_cast<volatile unsigned long long*>(F.host_flag) = F.seq; }
+      const double v = sm.res[threadIdx.x];
+      ll_store(F.host_result, threadIdx.x, v, (unsigned int) F.seq);
+      F.B.result(0)[threadIdx.x] = v;
     }
   }
 #ifdef GBK_PHASE_TIMING

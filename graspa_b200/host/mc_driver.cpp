@@ -60,6 +60,13 @@ struct CompState
   std::vector<double> rw, rw2, rn; std::vector<Energy> wE;
 };
 
+struct CallClock
+{
+  double& acc; long& n; std::chrono::steady_clock::time_point t0;
+  CallClock(double& a, long& c) : acc(a), n(c), t0(std::chrono::steady_clock::now()) {}
+  ~CallClock() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); n++; }
+};
+
 struct Sim
 {
   deck::Deck d;
@@ -73,6 +80,7 @@ struct Sim
   int nblock = 5; long block_size = 1; bool production = false;
   long moves_done = 0;
   bool fused = true;                              // one host round trip per move (gb_move_*); false: the stage calls
+  double call_s[4] = {0, 0, 0, 0}; long call_n[4] = {0, 0, 0, 0};   // host time inside gb_move_{insertion,deletion,reinsertion,single_body}
   std::FILE* trace = nullptr;
 };
 
@@ -203,7 +211,7 @@ Growth insertion_body(Sim& S, int comp)
     // one round trip for the whole Insertion_Body
     const double u[2] = {S.rng.peek(0), S.rng.peek(1)};
     gb_move_result m;
-    GB(gb_move_insertion(S.e, comp, (int64_t) S.pool_off, u, scale, &m));
+    { CallClock cc(S.call_s[0], S.call_n[0]); GB(gb_move_insertion(S.e, comp, (int64_t) S.pool_off, u, scale, &m)); }
     S.rng.advance(m.uniforms_used); pool_update(S, m.pool_used);
     if(!m.success) return G;
     G.sel_fb = m.first_bead.selected; G.sel_or = m.chain.selected;
@@ -307,7 +315,7 @@ void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run + Deleti
   if(fused)
   {
     gb_move_result m;
-    GB(gb_move_deletion(S.e, comp, mol, (int64_t) S.pool_off, scale, &m));
+    { CallClock cc(S.call_s[1], S.call_n[1]); GB(gb_move_deletion(S.e, comp, mol, (int64_t) S.pool_off, scale, &m)); }
     pool_update(S, m.pool_used);
     if(!m.success) { trace_move(S, "deletion", comp, mol, 0, 0.0); return; }
     W = m.first_bead.rosenbluth;
@@ -367,7 +375,7 @@ void move_reinsertion(Sim& S, int comp, long mol)  // ReinsertionMove::Run, move
   {
     const double u[2] = {S.rng.peek(0), S.rng.peek(1)};
     gb_move_result m;
-    GB(gb_move_reinsertion(S.e, comp, mol, (int64_t) S.pool_off, u, &m));
+    { CallClock cc(S.call_s[2], S.call_n[2]); GB(gb_move_reinsertion(S.e, comp, mol, (int64_t) S.pool_off, u, &m)); }
     S.rng.advance(m.uniforms_used); pool_update(S, m.pool_used);
     if(!m.success) { trace_move(S, "reinsertion", comp, mol, 0, 0.0); return; }
     double Wn = m.first_bead.rosenbluth, Wo = m.old_first_bead.rosenbluth;
@@ -457,7 +465,7 @@ void move_single_body(Sim& S, int comp, long mol, int move_type)   // SingleBody
   if(S.fused)
   {
     gb_move_result m;
-    GB(gb_move_single_body(S.e, move_type, comp, mol, maxc, (int64_t) S.pool_off, &m));
+    { CallClock cc(S.call_s[3], S.call_n[3]); GB(gb_move_single_body(S.e, move_type, comp, mol, maxc, (int64_t) S.pool_off, &m)); }
     pool_update(S, ms);
     d = m.delta; overlap = m.overlap; ew[0] = m.ewald[0]; ew[1] = m.ewald[1];
   }
@@ -764,6 +772,15 @@ int main(int argc, char** argv)
   std::printf("{\"moves\": %ld, \"cycles\": %ld, \"seconds\": %.6f, \"moves_per_s\": %.3f, \"cycles_per_s\": %.3f, \"widom_path\": \"%s\", \"move_calls\": \"%s\", \"rng_draws\": %llu, \"pool_refills\": %ld, \"kernel_launches\": %lld}\n",
               S.moves_done, cycles, secs, S.moves_done / secs, cycles / secs, batched ? "batched-exact" : "sequential", S.fused ? "fused" : "staged",
               (unsigned long long) S.rng.consumed(), S.pool_rounds, (long long) launches);
+  if(S.fused)
+  {
+    const char* nm[4] = {"insertion", "deletion", "reinsertion", "translation/rotation"};
+    double tot = 0.0;
+    for(int k = 0; k < 4; k++) tot += S.call_s[k];
+    std::printf("host time inside the move calls: %.3f s of %.3f s;", tot, secs);
+    for(int k = 0; k < 4; k++) if(S.call_n[k]) std::printf(" %s %.2f us x %ld;", nm[k], 1e6 * S.call_s[k] / S.call_n[k], S.call_n[k]);
+    std::printf("\n");
+  }
   if(timing)
   {
     double ms = 0.0; int64_t n = 0; gb_timing_read(S.e, 0, &ms, &n, 0);
