@@ -13,6 +13,10 @@ index ranges (weak scaling: fixed per-GPU batch) and only the block sums are all
 value : inputs (random pool, uniforms) already resident in HBM; sums read back.
 e2e   : the same step through the C ABI with HOST (pinned) buffers: H2D of the randoms and D2H of the sums inside
         the timed region.
+Timing: CUDA events recorded on the engine's own stream (made torch's current stream), max over ranks.
+Extra keys (N=1 only, skipped with --no-secondary): "gcmc" -- cycles/s of the sequential Markov chain on the reference's
+CO2-MFI example through the host driver (one kernel per move), with the reference's own CUDA build (oracle/_ref) timed
+beside it on the same GPU when the binary is present.
 """
 from __future__ import annotations
 
@@ -31,6 +35,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from tests.conftest import load_config  # noqa: E402  (fixture loader only: committed .npz, no oracle)
+
+# dram bytes per insertion of k_widom_pair measured by ncu (profiles/r1_pair_kernel.md); bench.py cannot run under ncu itself
+NCU_DRAM_BYTES_PER_INSERTION = 510.0
 
 METRIC = "widom_insertions_per_s"
 UNIT = "insertions/s"
@@ -96,6 +103,62 @@ def cpu_sample(box, ff, s, z, comp, target_s=12.0, seed=7):
     return dict(value=n / dt, n=n, seconds=dt, cores=orc.max_threads(), counts=[int(c) for c in counts], mean_W=float(out[:, 0].mean()))
 
 
+def _tail_json(text):
+    for ln in reversed(text.strip().splitlines()):
+        ln = ln.strip()
+        if ln.startswith("{") and ln.endswith("}"):
+            try:
+                return json.loads(ln)
+            except Exception:
+                pass
+    return None
+
+
+def gcmc_secondary(cycles=5000):
+    """GCMC cycles/s on the reference's CO2-MFI example (BASELINE.json configs[0]'s GCMC sibling): the host driver
+    (graspa_b200/host/graspa_b200_mc, one k_move launch per Monte Carlo move) and, when present, the reference's own
+    CUDA program built from /root/reference by oracle/build_ref.sh, both for `cycles` initialisation cycles."""
+    import shutil
+    import tempfile
+    deck = os.path.join(ROOT, "oracle", "_ref", "examples", "CO2-MFI")
+    drv = os.path.join(ROOT, "graspa_b200", "host", "graspa_b200_mc")
+    out = {"workload": f"CO2-MFI example deck, {cycles} initialisation cycles, seed 0", "unit": "cycles/s"}
+    if not (os.path.isdir(deck) and os.path.exists(drv)):
+        out["unavailable"] = "host driver or example deck not built (oracle/build_ref.sh, make -C graspa_b200/host)"
+        return out
+    try:
+        r = subprocess.run([drv, deck, "--init", str(cycles)], capture_output=True, text=True, timeout=300)
+        j = _tail_json(r.stdout.split("host time inside")[0]) or {}
+        out["value"] = j.get("cycles_per_s"); out["moves_per_s"] = j.get("moves_per_s"); out["kernel_launches"] = j.get("kernel_launches")
+        for ln in r.stdout.splitlines():
+            if ln.startswith("ENERGY DRIFT"):
+                out["energy_drift"] = float(ln.split(":")[-1])
+    except Exception as ex:  # noqa: BLE001
+        out["error"] = str(ex)
+    ref = os.path.join(ROOT, "oracle", "_ref", "graspa_ref_cuda.x")
+    if os.path.exists(ref):
+        d = tempfile.mkdtemp(prefix="gcmc_ref_")
+        try:
+            for f in os.listdir(deck):
+                shutil.copy(os.path.join(deck, f), d)
+            inp = os.path.join(d, "simulation.input")
+            os.chmod(inp, 0o644)
+            txt = open(inp).read().splitlines()
+            txt = [f"NumberOfInitializationCycles {cycles}" if t.startswith("NumberOfInitializationCycles") else t for t in txt]
+            open(inp, "w").write("\n".join(txt) + "\n")
+            t0 = time.perf_counter()
+            r = subprocess.run([ref], cwd=d, capture_output=True, text=True, timeout=600)
+            wall = time.perf_counter() - t0
+            took = [ln for ln in r.stdout.splitlines() if ln.startswith("Work took")]
+            secs = float(took[-1].split()[2]) if took else wall
+            out["reference_cuda"] = {"value": cycles / secs, "seconds": secs, "what": "the reference's own CUDA program (sm_100 build of /root/reference) on the same GPU, same deck"}
+        except Exception as ex:  # noqa: BLE001
+            out["reference_cuda"] = {"error": str(ex)}
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -133,6 +196,7 @@ def main():
     ap.add_argument("--batch", type=int, default=400000, help="Widom insertions per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the GCMC cycles/s section")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -151,9 +215,18 @@ def main():
     box, ff, s, z = load_config("E")
     comp = int(z["comp"]); B = args.batch
     eng = engine.Engine(local).setup(box, ff, s, float(z["beta"]), 10, 10)
+    # the engine launches on its own stream: make it torch's current stream so that events, copies and NCCL share it
+    ext = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local))
+    torch.cuda.set_stream(ext)
     eng.total_ewald(store=True)                                  # structure factors built on the GPU
     eng.set_exclusion_constants(comp, float(z["excl"][0]), float(z["excl"][1]))
     fp64_peak = eng.measure_fp64_peak()
+    hbm_peak, hbm_src = 6458.7, "fallback of B200_PROFILING.md"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:  # noqa: BLE001
+        pass
 
     # ---- synthetic inputs: this rank's contiguous index range of the job
     gen = torch.Generator(device="cuda"); gen.manual_seed(1234 + rank)
@@ -183,10 +256,12 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps):
-        barrier(); t0 = time.perf_counter()
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        barrier(); ev0.record(ext)
         for _ in range(steps):
             out = fn()
-        barrier(); dt = time.perf_counter() - t0
+        ev1.record(ext); barrier()
+        dt = ev0.elapsed_time(ev1) * 1e-3
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         return dt, out
@@ -233,7 +308,17 @@ def main():
                             "peak_source": "DFMA microbenchmark run in this process (gb_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                             "flop_per_insertion": f_pair, "launch_ms": t_pair * 1e3, "share_of_step": ms_pair / max(ms_pair + ms_ew, 1e-9),
                             "ewald_kernel": {"achieved": f_k * B / (ms_ew / max(n_ew / 2, 1) * 1e-3) / 1e12, "unit": "TFLOP/s", "launch_ms": ms_ew / max(n_ew / 2, 1)},
-                            "hbm": {"algorithmic_bytes_per_insertion": 20 * 24 + 16 + 8 * 8, "note": "framework and structure factors are shared-memory resident; HBM is not the binding roof"}}
+                            "hbm": {"algorithmic_bytes_per_insertion": 20 * 24 + 16 + 8 * 8,
+                                    "achieved_gbs": (20 * 24 + 16 + 8 * 8) * B / t_pair / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                                    "note": "framework atoms, erfc and LJ tables are shared-memory resident: the pair kernel reads 496 B and writes 64 B per insertion, "
+                                            "so HBM (frac %.4f) is not the binding roof; the FP64 pipe is" % ((20 * 24 + 16 + 8 * 8) * B / t_pair / 1e9 / hbm_peak)}}
+        line["roofline"]["traffic"] = NCU_DRAM_BYTES_PER_INSERTION * B
+        line["roofline"]["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one k_widom_pair launch from profiles/ (ncu --set full), "
+                                              "scaled per insertion: %.0f B" % NCU_DRAM_BYTES_PER_INSERTION)
+    if world == 1 and not args.no_secondary:
+        torch.cuda.set_stream(torch.cuda.default_stream())
+        eng.close()
+        line["gcmc"] = gcmc_secondary()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

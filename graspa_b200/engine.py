@@ -71,6 +71,18 @@ class GbCbmcResult(C.Structure):
                 ("success", C.c_int32), ("selected", C.c_int32), ("n_survivors", C.c_int32), ("reserved", C.c_int32)]
 
 
+class GbMoveResult(C.Structure):
+    _fields_ = [("first_bead", GbCbmcResult), ("chain", GbCbmcResult), ("old_first_bead", GbCbmcResult), ("old_chain", GbCbmcResult),
+                ("ewald", C.c_double * 2), ("tail", C.c_double), ("delta", GbMoveEnergy), ("overlap", C.c_int32),
+                ("uniforms_used", C.c_int32), ("pool_used", C.c_int32), ("success", C.c_int32)]
+
+    def as_dict(self):
+        d = {k: Engine._cbmc_dict(getattr(self, k), 0) for k in ("first_bead", "chain", "old_first_bead", "old_chain")}
+        d.update(ewald=(self.ewald[0], self.ewald[1]), tail=self.tail, delta=self.delta.as_dict(), overlap=bool(self.overlap),
+                 uniforms_used=self.uniforms_used, pool_used=self.pool_used, success=bool(self.success))
+        return d
+
+
 class GbWidomInputs(C.Structure):
     _fields_ = [("pool3", C.c_void_p), ("n_pool", C.c_int64), ("fb_index", C.c_void_p), ("or_index", C.c_void_p),
                 ("uniforms", C.c_void_p), ("inputs_on_device", C.c_int32), ("n_blocks", C.c_int32)]
@@ -352,6 +364,28 @@ class Engine:
         self._chk(self.lib.gb_widom_batch(self.h, C.c_int32(comp), C.c_int64(n), C.byref(inp), C.c_void_p(d_out8) if d_out8 else None,
                                           None, C.c_int32(1), _p(sums, f64p)))
         return sums
+
+    # ------------------------------------------------------------ fused moves (one kernel, one host round trip per move)
+    def move_insertion(self, comp, pool_offset, uniforms, scale=(1.0, 1.0)):
+        u = (C.c_double * 2)(*uniforms); sc = (C.c_double * 2)(*scale); r = GbMoveResult()
+        self._chk(self.lib.gb_move_insertion(self.h, C.c_int32(comp), C.c_int64(pool_offset), u, sc, C.byref(r))); return r.as_dict()
+
+    def move_deletion(self, comp, molecule, pool_offset, scale=(1.0, 1.0)):
+        sc = (C.c_double * 2)(*scale); r = GbMoveResult()
+        self._chk(self.lib.gb_move_deletion(self.h, C.c_int32(comp), C.c_int64(molecule), C.c_int64(pool_offset), sc, C.byref(r))); return r.as_dict()
+
+    def move_reinsertion(self, comp, molecule, pool_offset, uniforms):
+        u = (C.c_double * 2)(*uniforms); r = GbMoveResult()
+        self._chk(self.lib.gb_move_reinsertion(self.h, C.c_int32(comp), C.c_int64(molecule), C.c_int64(pool_offset), u, C.byref(r))); return r.as_dict()
+
+    def move_single_body(self, move_type, comp, molecule, max_change, pool_offset):
+        mc = (C.c_double * 3)(*max_change); r = GbMoveResult()
+        self._chk(self.lib.gb_move_single_body(self.h, C.c_int32(move_type), C.c_int32(comp), C.c_int64(molecule), mc, C.c_int64(pool_offset), C.byref(r)))
+        return r.as_dict()
+
+    def stream(self):
+        """cudaStream_t of the engine as an int (wrap with torch.cuda.ExternalStream to record events on it)"""
+        return int(self.lib.gb_stream(self.h) or 0)
 
     # ------------------------------------------------------------ instrumentation
     def launch_count(self, reset=False):

@@ -254,3 +254,87 @@ def test_energy_drift_over_a_short_gcmc_run(gpu_engine_factory):
     sb, _, _ = eng.download_structure_factors()
     assert np.max(np.abs(sa - sb)) < 1e-8
     eng.close()
+
+
+def _same(a, b, tol=1e-11, floor=1e-6):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return bool(np.all(np.abs(a - b) <= tol * np.maximum(np.abs(b), floor) + tol * float(np.abs(b).max() if b.size else 0.0)))
+
+
+def test_one_kernel_moves_match_the_stage_calls(gpu_engine_factory):
+    """gb_move_* (one kernel, one host round trip) against the stage calls of the same move -- which the tests above pin to
+    the oracle.  Same pool offsets and uniforms; energies agree to summation order (1e-11), selections exactly."""
+    box, ff, s, z, eng = _setup(gpu_engine_factory)
+    comp = 1; ms = 3
+    rng = np.random.default_rng(31)
+    pool = rng.random((1024, 3)); eng.upload_random_pool(pool)
+    # ---- insertion
+    for rep in range(8):
+        off = 50 * rep; u = rng.random(2)
+        fb = eng.cbmc_first_bead(CBMC_INSERTION, comp, 0, off, u[0])
+        ch = eng.cbmc_chain(CBMC_INSERTION, comp, 0, off + 10, u[1]) if fb["success"] and fb["rosenbluth"] > 1e-150 else None
+        ok = ch is not None and ch["success"] and fb["rosenbluth"] * ch["rosenbluth"] > 1e-150
+        ew = eng.ewald_delta(comp, INSERTION, location=ch["selected"]) if ok else None
+        grown = eng.cbmc_grown_positions(comp) if ok else None
+        m = eng.move_insertion(comp, off, u)
+        assert m["success"] == ok
+        assert m["first_bead"]["success"] == fb["success"] and m["first_bead"]["n_survivors"] == fb["n_survivors"]
+        if fb["success"] and fb["n_survivors"] > 0:
+            assert m["first_bead"]["selected"] == fb["selected"]
+            assert _same(m["first_bead"]["rosenbluth"], fb["rosenbluth"]) and _same(m["first_bead"]["energy"], fb["energy"])
+        if ok:
+            assert m["chain"]["selected"] == ch["selected"] and _same(m["chain"]["rosenbluth"], ch["rosenbluth"])
+            assert _same(m["chain"]["energy"], ch["energy"])
+            assert _same(m["ewald"], ew, tol=1e-10)
+            assert np.allclose(eng.cbmc_grown_positions(comp), grown, rtol=0, atol=1e-12)
+            assert m["uniforms_used"] == 2 and m["pool_used"] == 20
+    # ---- deletion
+    for mol in (0, 7, 19):
+        off = 600 + 25 * (mol % 5)
+        fb = eng.cbmc_first_bead(CBMC_DELETION, comp, mol, off, 0.5)
+        ch = eng.cbmc_chain(CBMC_DELETION, comp, mol, off + 10, 0.5)
+        ew = eng.ewald_delta(comp, DELETION, location=mol * ms)
+        m = eng.move_deletion(comp, mol, off)
+        assert m["success"] and m["first_bead"]["selected"] == 0 and m["uniforms_used"] == 0
+        assert _same(m["first_bead"]["rosenbluth"], fb["rosenbluth"]) and _same(m["chain"]["rosenbluth"], ch["rosenbluth"])
+        assert _same(m["first_bead"]["energy"], fb["energy"]) and _same(m["chain"]["energy"], ch["energy"])
+        assert _same(m["ewald"], ew, tol=1e-10)
+    # ---- reinsertion
+    for mol, off in ((5, 200), (12, 300), (2, 420)):
+        u = rng.random(2)
+        fb = eng.cbmc_first_bead(REINSERTION_INSERTION, comp, mol, off, u[0])
+        alive = fb["success"] and fb["rosenbluth"] > 1e-150
+        ch = eng.cbmc_chain(REINSERTION_INSERTION, comp, mol, off + 10, u[1]) if alive else None
+        alive = alive and ch["success"] and fb["rosenbluth"] * ch["rosenbluth"] > 1e-150
+        m_ref = None
+        if alive:
+            eng.reinsertion_store(comp)
+            rb = eng.cbmc_first_bead(REINSERTION_RETRACE, comp, mol, off + 20, 0.5, stored_r=fb["stored_r"])
+            rc = eng.cbmc_chain(REINSERTION_RETRACE, comp, mol, off + 21, 0.5)
+            ew = eng.ewald_delta(comp, REINSERTION, location=mol * ms)
+            m_ref = (rb, rc, ew)
+        m = eng.move_reinsertion(comp, mol, off, u)
+        assert m["success"] == alive
+        if alive:
+            rb, rc, ew = m_ref
+            assert m["first_bead"]["selected"] == fb["selected"] and m["chain"]["selected"] == ch["selected"]
+            assert _same(m["first_bead"]["stored_r"], fb["stored_r"])
+            assert _same(m["first_bead"]["rosenbluth"], fb["rosenbluth"]) and _same(m["chain"]["rosenbluth"], ch["rosenbluth"])
+            assert _same(m["old_first_bead"]["rosenbluth"], rb["rosenbluth"]) and _same(m["old_chain"]["rosenbluth"], rc["rosenbluth"])
+            assert _same(m["old_chain"]["energy"], rc["energy"])
+            assert _same(m["ewald"], ew, tol=1e-10)
+            assert m["pool_used"] == 31            # 10 positions + 10 orientations + 1 retrace position + 10 retrace orientations
+    # ---- translation / rotation
+    for k, (mt, mol) in enumerate([(TRANSLATION, 3), (ROTATION, 11), (TRANSLATION, 19), (ROTATION, 0)]):
+        maxc = np.array([0.8, 0.6, 0.7]) if mt == TRANSLATION else np.array([0.5, 0.4, 0.3])
+        eng.single_body_propose(mt, comp, mol, maxc, 900 + k)
+        d, ov = eng.single_body_delta(comp)
+        ew = eng.ewald_delta(comp, mt)
+        m = eng.move_single_body(mt, comp, mol, maxc, 900 + k)
+        assert m["overlap"] == bool(ov)
+        got = np.array([m["delta"][k2] for k2 in ("HHVDW", "HHReal", "HGVDW", "HGReal", "GGVDW", "GGReal")])
+        ref = np.array([d[k2] for k2 in ("HHVDW", "HHReal", "HGVDW", "HGReal", "GGVDW", "GGReal")])
+        assert np.max(np.abs(got - ref)) < 1e-11 * 1e4
+        if not ov:
+            assert _same(m["ewald"], ew, tol=1e-10)
+    eng.close()
