@@ -204,6 +204,7 @@ def main():
     import torch
     import torch.distributed as dist
     from graspa_b200 import engine
+    from graspa_b200.shard import reduce_block_sums
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -234,20 +235,19 @@ def main():
     d_uni = torch.rand((B, 2), dtype=torch.float64, device="cuda", generator=gen)
     h_pool = torch.empty((B * 20, 3), dtype=torch.float64).pin_memory(); h_pool.copy_(d_pool)
     h_uni = torch.empty((B, 2), dtype=torch.float64).pin_memory(); h_uni.copy_(d_uni)
-    d_sums = torch.zeros((5, 12), dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
 
+    # weak scaling: every rank owns B insertions of a job of B*world; bins are assigned on the global index
+    my_shard = (rank * B, B * world)
+    dev = torch.device("cuda", local)
+
     def step_device():
-        sums = eng.widom_batch_device(comp, B, d_pool.data_ptr(), B * 20, d_uni.data_ptr())
-        if world > 1:
-            d_sums.copy_(torch.from_numpy(sums)); dist.all_reduce(d_sums); return d_sums.cpu().numpy()
-        return sums
+        sums = eng.widom_batch_device(comp, B, d_pool.data_ptr(), B * 20, d_uni.data_ptr(), shard=my_shard)
+        return reduce_block_sums(sums, device=dev)          # NCCL all-reduce of the 5 x 12 block sums (identity at N=1)
 
     def step_e2e():
-        _, _, sums = eng.widom_batch(comp, h_pool.numpy(), h_uni.numpy(), want_outputs=False)
-        if world > 1:
-            d_sums.copy_(torch.from_numpy(sums)); dist.all_reduce(d_sums); return d_sums.cpu().numpy()
-        return sums
+        _, _, sums = eng.widom_batch(comp, h_pool.numpy(), h_uni.numpy(), want_outputs=False, shard=my_shard)
+        return reduce_block_sums(sums, device=dev)
 
     def barrier():
         torch.cuda.synchronize()

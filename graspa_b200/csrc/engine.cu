@@ -981,6 +981,8 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   B.ktab = e->d_ktab.p; B.nact = e->nact; B.nact_pad = e->nact_pad; B.do_ewald = do_ewald ? 1 : 0;
   B.excl_const = C.rigid ? (C.excl_intra + C.excl_atom) * 1.0 : 0.0;
   B.tail = e->h_pinned[8]; B.nbins = nbins;
+  B.gn = in->global_n > 0 ? in->global_n : n; B.gfirst = in->global_n > 0 ? in->global_first : 0;
+  if(B.gfirst < 0 || B.gfirst + n > B.gn) return fail(GB_ERR_ARG, "shard [global_first, global_first + n) outside the job");
   const size_t per_warpB = ((size_t) ms * (e->P.kmax[0] + e->P.kmax[1] + e->P.kmax[2] + 3) * sizeof(cplx) + (size_t) ms * 4 * sizeof(double) + 15) / 16 * 16;
   const size_t fixedB = 16 + warpsB * per_warpB + (size_t) warpsB * nbins * 12 * sizeof(double) + 64;
   const size_t ktab_bytes = ((size_t) e->nact_pad * 44 + 15) / 16 * 16;

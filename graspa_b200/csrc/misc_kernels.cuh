@@ -127,7 +127,7 @@ struct WidomB
   int do_ewald;
   double excl_const;       // (ExclusionIntra + ExclusionAtom) * scale^2, Ewald_Energy_Functions.h:553-556
   double tail;             // TailCorrectionDifference for this component (same for every ghost insertion)
-  int nbins;
+  int nbins; long long gfirst, gn;   // bins on the global insertion index (sharded jobs)
   double* out8; int* out_stage;      // may be null
   double* partial;                   // [gridDim.x][nbins][12]
 };
@@ -165,7 +165,7 @@ k_widom_ewald(DevParams P, WidomB B)
   for(long long ins = gw; ins < B.n; ins += tw)
   {
     const int st = B.stage[ins];
-    const int bin = (int)((ins * B.nbins) / B.n);
+    const int bin = (int)(((B.gfirst + ins) * B.nbins) / B.gn);
     double* mybin = bins + ((size_t) warp * B.nbins + bin) * 12;
     double o8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if(st == 0)

@@ -698,6 +698,33 @@ void print_energy(const char* tag, const Energy& E)
 
 int main(int argc, char** argv)
 {
+  // self-test modes that need no GPU (tests/test_host_driver.py)
+  if(argc >= 4 && std::string(argv[1]) == "--rng-dump")
+  {
+    // first N uniforms of Get_Uniform_Random() after std::srand(seed): draws and look-ahead must agree with libc
+    GlibcRand g((unsigned) std::atol(argv[2])); const long n = std::atol(argv[3]);
+    for(long i = 0; i < n; i++)
+    {
+      const double ahead = (i % 7 == 0) ? g.peek(3) : -1.0;      // exercise the look-ahead buffer
+      const double u = g.uniform();
+      std::printf("%.17g\n", u);
+      if(ahead >= 0.0) { const double a = g.peek(2); if(a != ahead) { std::fprintf(stderr, "peek mismatch at %ld\n", i); return 3; } }
+    }
+    return 0;
+  }
+  if(argc >= 3 && std::string(argv[1]) == "--parse-only")
+  {
+    try
+    {
+      deck::Deck d = deck::load(argv[2]);
+      std::printf("{\"framework_atoms\": %zu, \"components\": %zu, \"alpha\": %.9f, \"kmax\": [%d, %d, %d], \"volume\": %.6f, \"beta\": %.10f, "
+                  "\"init_cycles\": %ld, \"equil_cycles\": %ld, \"prod_cycles\": %ld, \"seed\": %ld}\n",
+                  d.ftype.size(), d.comps.size(), d.alpha, d.kmax[0], d.kmax[1], d.kmax[2], d.volume, d.beta,
+                  (long) d.init_cycles, (long) d.equil_cycles, (long) d.prod_cycles, (long) d.random_seed);
+    }
+    catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
+    return 0;
+  }
   if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--timing] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
   const std::string dir = argv[1];
   bool sequential_widom = false, staged = false, timing = false; const char* trace_path = nullptr;

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GB_ABI_VERSION 1
+#define GB_ABI_VERSION 2
 
 enum {
   GB_OK = 0,
@@ -282,6 +282,10 @@ typedef struct {
   const double* uniforms;
   int32_t inputs_on_device;      /* 0: the four pointers above are host memory (copied inside the call) */
   int32_t n_blocks;              /* block-average bins (Components::Nblock = 5); insertion i -> bin i*n_blocks/n */
+  /* sharding (one process per GPU): this call evaluates insertions [global_first, global_first + n) of a
+   * job of global_n insertions; bins are assigned on the GLOBAL index so that the all-reduced sums equal the
+   * single-GPU ones.  global_n = 0: the call is the whole job. */
+  int64_t global_first; int64_t global_n;
 } gb_widom_inputs;
 
 /* per insertion outputs (any may be NULL): out8[i*8 + {W, HGVDW, HGReal, GGVDW, GGReal, GGEwaldE, HGEwaldE, TailE}],

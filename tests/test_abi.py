@@ -24,7 +24,9 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in syms if not hasattr(lib, s)]
     assert not missing, missing
     assert sorted(engine.DECLARED_SYMBOLS) == syms
-    assert lib.gb_abi_version() == 1
+    import re
+    want = int(re.search(r"#define GB_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "graspa_b200.h")).read()).group(1))
+    assert lib.gb_abi_version() == want == 2
 
 
 def test_engine_creation_fails_loudly_without_gpu():

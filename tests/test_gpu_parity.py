@@ -200,3 +200,28 @@ def test_widom_properties_full_size(gpu_engine_factory):
     assert abs(sums[:, 0].sum() - out[:, 0].sum()) <= 1e-11 * out[:, 0].sum()
     assert sums[:, 2].sum() == n and (sums[:, 2] == n // 5).all()
     eng.close()
+
+
+def test_widom_shards_bin_on_the_global_index(gpu_engine_factory):
+    """a job cut into contiguous index ranges (gb_widom_inputs.global_first/global_n) gives, after summing the
+    per-shard block sums (what the NCCL all-reduce does), the single-call sums: counts exactly, sums to association."""
+    from graspa_b200.shard import shard_range
+    box, ff, s, z = load_config("A")
+    comp = int(z["comp"]); n = 1003
+    eng = gpu_engine_factory(box, ff, s, float(z["beta"]), 10, 10)
+    eng.upload_structure_factors(z["sf_ads"], z["sf_fw"]); eng.set_exclusion_constants(comp, float(z["excl"][0]), float(z["excl"][1]))
+    rng = np.random.default_rng(5)
+    rnd = rng.random((n, 20, 3)); uni = rng.random((n, 2))
+    out, stage, whole = eng.widom_batch(comp, rnd.reshape(-1, 3), uni, n_blocks=5)
+    for world in (2, 3, 8):
+        acc = np.zeros_like(whole); outs = []
+        for r in range(world):
+            first, cnt = shard_range(n, world, r)
+            o, st, sm = eng.widom_batch(comp, rnd[first:first + cnt].reshape(-1, 3), uni[first:first + cnt], n_blocks=5, shard=(first, n))
+            acc += sm; outs.append(o)
+        assert np.array_equal(np.concatenate(outs), out)                          # per-insertion results do not depend on the cut
+        assert np.array_equal(acc[:, 2], whole[:, 2]) and np.array_equal(acc[:, 10], whole[:, 10])
+        assert np.max(np.abs(acc - whole) / np.maximum(np.abs(whole), 1e-300)) < 1e-12
+    with pytest.raises(Exception):
+        eng.widom_batch(comp, rnd[:10].reshape(-1, 3), uni[:10], shard=(n - 5, n))   # range sticks out of the job
+    eng.close()
