@@ -85,6 +85,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def host_cores():
+    """threads the CPU arm uses: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which would
+    otherwise silently make the baseline single-threaded)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def oracle_setup(box, ff, s, z, comp):
     from oracle import oracle as orc
     orc.build()
@@ -95,12 +104,13 @@ def cpu_sample(box, ff, s, z, comp, target_s=12.0, seed=7):
     """oracle Widom batch on the host cores, bounded to ~target_s seconds; also yields the per-insertion pair counts"""
     orc, ws = oracle_setup(box, ff, s, z, comp)
     rng = np.random.default_rng(seed)
-    n0 = 64 * max(1, orc.max_threads() // 8)
-    t0 = time.perf_counter(); orc.widom_batch(ws, rng.random((n0, 20, 3)), rng.random((n0, 2))); dt = time.perf_counter() - t0
+    nt = host_cores()
+    n0 = 64 * max(1, nt // 8)
+    t0 = time.perf_counter(); orc.widom_batch(ws, rng.random((n0, 20, 3)), rng.random((n0, 2)), nthreads=nt); dt = time.perf_counter() - t0
     n = int(max(n0, min(200000, n0 * target_s / max(dt, 1e-3))))
     rnd = rng.random((n, 20, 3)); uni = rng.random((n, 2))
-    t0 = time.perf_counter(); out, stage, counts = orc.widom_batch(ws, rnd, uni); dt = time.perf_counter() - t0
-    return dict(value=n / dt, n=n, seconds=dt, cores=orc.max_threads(), counts=[int(c) for c in counts], mean_W=float(out[:, 0].mean()))
+    t0 = time.perf_counter(); out, stage, counts = orc.widom_batch(ws, rnd, uni, nthreads=nt); dt = time.perf_counter() - t0
+    return dict(value=n / dt, n=n, seconds=dt, cores=nt, counts=[int(c) for c in counts], mean_W=float(out[:, 0].mean()))
 
 
 def _tail_json(text):
@@ -168,21 +178,22 @@ def run_reference(args):
     orc, ws = oracle_setup(box, ff, s, z, comp)
     rng = np.random.default_rng(17)
     # bounded sample per step: sized from a probe so that warmup+steps stay within a few minutes
-    n0 = 64
-    t0 = time.perf_counter(); orc.widom_batch(ws, rng.random((n0, 20, 3)), rng.random((n0, 2))); rate = n0 / (time.perf_counter() - t0)
+    nt = host_cores()
+    n0 = 64 * max(1, nt // 8)
+    t0 = time.perf_counter(); orc.widom_batch(ws, rng.random((n0, 20, 3)), rng.random((n0, 2)), nthreads=nt); rate = n0 / (time.perf_counter() - t0)
     per_step = int(max(64, min(100000, rate * 60.0 / max(1, args.steps + args.warmup))))
     rnd = rng.random((per_step, 20, 3)); uni = rng.random((per_step, 2))
     for _ in range(args.warmup):
-        orc.widom_batch(ws, rnd, uni)
+        orc.widom_batch(ws, rnd, uni, nthreads=nt)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.widom_batch(ws, rnd, uni)
+        orc.widom_batch(ws, rnd, uni, nthreads=nt)
     dt = time.perf_counter() - t0
     v = per_step * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": WORKLOAD, "insertions_per_step": per_step},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.max_threads(), "kind": "port",
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
                              "sample": f"{per_step} insertions/step x {args.steps} steps of the same workload, OpenMP over insertions"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
