@@ -36,6 +36,8 @@ struct DevParams
   int all_unit_scale;                 // every system atom has scale == scaleCoul == 1
   int cell_mode;                      // 0 general, 1 lower triangular (CIF cells, read_data.cpp:1545-1547), 2 orthorhombic
   int erfc_table_ok;                  // alpha*sqrt(cut_coul2) < GBK_ERFC_XMAX: every in-cutoff pair is inside the erfc table
+  double cull_w[3];                   // tile culling: r_cut * |column i of the inverse cell| (reach of the cutoff sphere along fractional axis i)
+  double cull_rcut;                   // sqrt(max(cut_vdw2, cut_coul2)) (cut_vdw2 alone without charges)
   const double4* __restrict__ ffA;    // LJ: {4*eps, sigma^2, shift, 1/sigma^2}; 12-6-4: {C12, C6, C4, shift}
   const double*  __restrict__ ffB;    // 12-6-4: C10
   const double*  __restrict__ erfc_tab;   // device copy of h_erfc_table

@@ -75,7 +75,7 @@ struct gb_engine
   std::vector<long long> npseudo;          // Components::NumberOfPseudoAtoms
 
   // framework pack
-  DevBuf<double> d_pack; int pack_n = 0, pack_npad = 0; bool pack_dirty = true;
+  DevBuf<double> d_pack; int pack_n = 0, pack_npad = 0, pack_ntp = 0; bool pack_dirty = true;
 
   // Ewald
   long long nvec = 0;
@@ -182,25 +182,117 @@ int ready(gb_engine* e)
   for(int c = 0; c < e->ncomp; c++) if(!e->comps[c].uploaded) return fail(GB_ERR_STATE, "component " + std::to_string(c) + " has not been uploaded");
   CUDA_TRY(cudaSetDevice(e->device));
   e->P.erfc_table_ok = (e->P.alpha * std::sqrt(e->P.cut_coul2) < GBK_ERFC_XMAX) ? 1 : 0;
+  {
+    // reach of the cutoff sphere along each fractional axis: |s_i| = |r . inv[:,i]| <= |r| |inv[:,i]|  (tile culling)
+    const double rc = std::sqrt(e->P.no_charges ? e->P.cut_vdw2 : std::max(e->P.cut_vdw2, e->P.cut_coul2));
+    e->P.cull_rcut = rc;
+    for(int i = 0; i < 3; i++)
+    {
+      const double nrm = std::sqrt(e->P.inv[i] * e->P.inv[i] + e->P.inv[3 + i] * e->P.inv[3 + i] + e->P.inv[6 + i] * e->P.inv[6 + i]);
+      e->P.cull_w[i] = rc * nrm * (1.0 + 1e-12) + 1e-12;
+    }
+  }
   return sync_slots_to_device(e);
 }
 
-// framework pack for TMA staging.  Only valid for moves whose exclusions do not touch host components.
+// bytes of the staged pack: 5 arrays of npad (the type array is int, stored in a double-wide slot) + 10 tile arrays of ntp
+static size_t pack_bytes_for(int npad, int ntp) { return gbk_pack_bytes(npad, ntp); }
+
+// framework pack for TMA staging (tile-sorted, see pair.cuh).  Only valid for moves whose exclusions do not touch host components.
 int ensure_pack(gb_engine* e, bool& usable, size_t extra_smem)
 {
   usable = false;
   SegList L = seg_list(e, 1);
   int n = 0; for(int s = 0; s < L.nseg; s++) n += L.count[s];
   if(n == 0 || !e->P.all_unit_scale) return GB_OK;
-  const int npad = (n + 31) / 32 * 32;
-  if((size_t) npad * 36 + 64 + extra_smem > e->smem_optin) return GB_OK;
+  const int npad = (n + 31) / 32 * 32, ntiles = npad / 32, ntp = (ntiles + 31) / 32 * 32;
+  if(pack_bytes_for(npad, ntp) + 64 + extra_smem > e->smem_optin) return GB_OK;
   if(e->pack_dirty || e->pack_n != n)
   {
-    CUDA_TRY(e->d_pack.reserve((size_t) npad * 5));
-    k_build_pack<<<(npad + 255) / 256, 256, 0, e->stream>>>(e->dfx.p, e->dfy.p, e->dfz.p, e->dq.p, e->dscoul.p, e->dtype.p, L, npad, e->d_pack.p);
-    e->launches++;
-    CUDA_TRY(cudaGetLastError());
-    e->pack_n = n; e->pack_npad = npad; e->pack_dirty = false;
+    // ---- fetch the host components' live atoms (fractional coordinates, charge, type)
+    std::vector<double> f[3], q(n), sc(n); std::vector<int> ty(n);
+    for(int k = 0; k < 3; k++) f[k].resize(n);
+    int acc = 0;
+    for(int s = 0; s < L.nseg; s++)
+    {
+      const size_t b8 = (size_t) L.count[s] * sizeof(double);
+      CUDA_TRY(cudaMemcpyAsync(f[0].data() + acc, e->dfx.p + L.start[s], b8, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(f[1].data() + acc, e->dfy.p + L.start[s], b8, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(f[2].data() + acc, e->dfz.p + L.start[s], b8, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(q.data() + acc, e->dq.p + L.start[s], b8, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(sc.data() + acc, e->dscoul.p + L.start[s], b8, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(ty.data() + acc, e->dtype.p + L.start[s], (size_t) L.count[s] * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+      acc += L.count[s];
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for(int k = 0; k < 3; k++) for(int i = 0; i < n; i++) { f[k][i] -= std::floor(f[k][i]); if(f[k][i] >= 1.0) f[k][i] = 0.0; }
+    // ---- k-d split into tiles of 32 atoms: full tiles go left, so only the last tile can be partial
+    const double* H = e->P.cell;
+    const double len[3] = { std::sqrt(H[0] * H[0] + H[1] * H[1] + H[2] * H[2]), std::sqrt(H[3] * H[3] + H[4] * H[4] + H[5] * H[5]),
+                            std::sqrt(H[6] * H[6] + H[7] * H[7] + H[8] * H[8]) };
+    std::vector<int> idx(n);
+    for(int i = 0; i < n; i++) idx[i] = i;
+    std::vector<std::pair<int, int>> todo; todo.push_back({0, n});
+    while(!todo.empty())
+    {
+      const int lo = todo.back().first, hi = todo.back().second; todo.pop_back();
+      const int m = (hi - lo + 31) / 32;
+      if(m <= 1) continue;
+      const int nl = (m / 2) * 32;
+      int axis = 0; double best = -1.0;
+      for(int k = 0; k < 3; k++)
+      {
+        double mn = 1e300, mx = -1e300;
+        for(int i = lo; i < hi; i++) { mn = std::min(mn, f[k][idx[i]]); mx = std::max(mx, f[k][idx[i]]); }
+        if((mx - mn) * len[k] > best) { best = (mx - mn) * len[k]; axis = k; }
+      }
+      const std::vector<double>& fa = f[axis];
+      std::nth_element(idx.begin() + lo, idx.begin() + lo + nl, idx.begin() + hi, [&](int a, int b) { return fa[a] < fa[b] || (fa[a] == fa[b] && a < b); });
+      todo.push_back({lo, lo + nl}); todo.push_back({lo + nl, hi});
+    }
+    // ---- pack [x | y | z | q*scoul | type] + tile table [lo xyz | hi xyz | centre xyz | radius]
+    std::vector<double> pk(gbk_pack_bytes(npad, ntp) / sizeof(double), 0.0);
+    double* X = pk.data(); double* Y = X + npad; double* Z = Y + npad; double* Q = Z + npad; int* T = reinterpret_cast<int*>(Q + npad);
+    double* tile = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(pk.data()) + (size_t) npad * 36);
+    for(int i = 0; i < npad; i++)
+    {
+      if(i < n)
+      {
+        const int j = idx[i];
+        X[i] = H[0] * f[0][j] + H[3] * f[1][j] + H[6] * f[2][j];
+        Y[i] = H[1] * f[0][j] + H[4] * f[1][j] + H[7] * f[2][j];
+        Z[i] = H[2] * f[0][j] + H[5] * f[1][j] + H[8] * f[2][j];
+        Q[i] = q[j] * sc[j]; T[i] = ty[j];
+      }
+      else { X[i] = Y[i] = Z[i] = 1e30; Q[i] = 0.0; T[i] = 0; }
+    }
+    for(int t = 0; t < ntp; t++)
+    {
+      double lo3[3] = {1e30, 1e30, 1e30}, hi3[3] = {1e30, 1e30, 1e30}, c3[3] = {0, 0, 0}, rad = 0.0;
+      if(t < ntiles)
+      {
+        const int i0 = t * 32, i1 = std::min(n, i0 + 32);
+        for(int k = 0; k < 3; k++) { lo3[k] = 1e300; hi3[k] = -1e300; }
+        for(int i = i0; i < i1; i++)
+        {
+          const int j = idx[i];
+          for(int k = 0; k < 3; k++) { lo3[k] = std::min(lo3[k], f[k][j]); hi3[k] = std::max(hi3[k], f[k][j]); }
+          c3[0] += X[i]; c3[1] += Y[i]; c3[2] += Z[i];
+        }
+        for(int k = 0; k < 3; k++) c3[k] /= (double) (i1 - i0);
+        for(int i = i0; i < i1; i++)
+          rad = std::max(rad, std::sqrt((X[i] - c3[0]) * (X[i] - c3[0]) + (Y[i] - c3[1]) * (Y[i] - c3[1]) + (Z[i] - c3[2]) * (Z[i] - c3[2])));
+        rad = rad * (1.0 + 1e-12) + 1e-9;
+        // the fractional coordinates the kernel reconstructs differ from f by rounding: widen the box by a few ulps
+        for(int k = 0; k < 3; k++) { lo3[k] -= 1e-12; hi3[k] += 1e-12; }
+      }
+      for(int k = 0; k < 3; k++) { tile[(size_t) k * ntp + t] = lo3[k]; tile[(size_t)(3 + k) * ntp + t] = hi3[k]; tile[(size_t)(6 + k) * ntp + t] = c3[k]; }
+      tile[(size_t) 9 * ntp + t] = rad;
+    }
+    CUDA_TRY(e->d_pack.reserve(pk.size()));
+    CUDA_TRY(cudaMemcpyAsync(e->d_pack.p, pk.data(), pk.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));          // pk is a local
+    e->pack_n = n; e->pack_npad = npad; e->pack_ntp = ntp; e->pack_dirty = false;
   }
   usable = true;
   return GB_OK;
@@ -879,7 +971,7 @@ static int widom_stage_a(gb_engine* e, int comp, long long n, const double* d_po
   const int rec_stride = 5 + 3 * ms;
   CUDA_TRY(e->d_rec.reserve((size_t) n * rec_stride)); CUDA_TRY(e->d_stage.reserve((size_t) n));
   const int warpsA = 16;
-  const size_t per_warpA = (sizeof(TrialGroup) + sizeof(WarpQueue) + (size_t) e->norient * (cs > 0 ? cs : 1) * 6 * sizeof(double) + 15) / 16 * 16;
+  const size_t per_warpA = widom_per_warp_bytes(e->norient, cs);
   bool use_pack = false;
   const bool stage_ff = e->ntypes <= 24;
   const size_t ff_bytes = stage_ff ? (size_t) e->ntypes * e->ntypes * sizeof(double4) : 0;
@@ -889,7 +981,7 @@ static int widom_stage_a(gb_engine* e, int comp, long long n, const double* d_po
   A.ntrials = e->ntrials; A.norient = e->norient; A.ms = ms; A.comp = comp; A.new_molid = C.natoms / ms;
   A.tx = e->dx.p + C.offset; A.ty = e->dy.p + C.offset; A.tz = e->dz.p + C.offset; A.tq = e->dq.p + C.offset;
   A.tscoul = e->dscoul.p + C.offset; A.ttype = e->dtype.p + C.offset;
-  A.pack = e->d_pack.p; A.npad = e->pack_npad; A.use_pack = use_pack ? 1 : 0; A.stage_ff = stage_ff ? 1 : 0;
+  A.pack = e->d_pack.p; A.npad = e->pack_npad; A.ntp = e->pack_ntp; A.pack_n = e->pack_n; A.use_pack = use_pack ? 1 : 0; A.stage_ff = stage_ff ? 1 : 0;
   A.first_bead_only = first_bead_only;
   A.rec = e->d_rec.p; A.stage = e->d_stage.p;
   SegList L = seg_list(e, 0);
@@ -899,7 +991,7 @@ static int widom_stage_a(gb_engine* e, int comp, long long n, const double* d_po
     for(int s = 0; s < L.nseg; s++) if(L.comp[s] < e->nhost) { L.staged[s] = 1; L.start[s] = acc; acc += L.count[s]; }
   }
   const size_t headA = (GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD + ff_bytes + sizeof(SegList) + 15) / 16 * 16;
-  const size_t smemA = headA + (use_pack ? ((size_t) e->pack_npad * 36 + 15) / 16 * 16 : 0) + warpsA * per_warpA;
+  const size_t smemA = headA + (use_pack ? pack_bytes_for(e->pack_npad, e->pack_ntp) : 0) + warpsA * per_warpA;
   if(smemA > e->smem_optin) return fail(GB_ERR_ARG, "Widom stage A shared memory exceeds the device limit");
   const int gridA = (int) std::min<long long>((n + warpsA - 1) / warpsA, e->prop.multiProcessorCount);
   Timer tm(e, 0);

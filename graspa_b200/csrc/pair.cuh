@@ -284,3 +284,177 @@ __device__ __forceinline__ void pair_group_flat(const DevParams& P, const PairTa
     __syncwarp();
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Tile-culled pair loop over the staged framework pack.
+// 92 % of the nominal pair flops are minimum-image distance checks against atoms that are nowhere near the trial atom.
+// The pack is sorted by a k-d split into 32-atom tiles (host side, ensure_pack); each tile carries its fractional
+// bounding box and a Cartesian bounding sphere.  One lane tests one tile:
+//   * per fractional axis, the wrapped interval [lo - t, hi - t] must reach into [-w, w], w = r_cut * |column of the
+//     inverse cell| -- a necessary condition for ANY atom of the tile to be inside the cutoff under the reference's
+//     convention (maths.cuh:437-448: every fractional difference is wrapped independently);
+//   * if the whole interval wraps with ONE integer shift on every axis, the tile is "uniform": the reference's image
+//     of every atom of the tile is atom - n.H, so the distance is a plain Cartesian difference against the shifted
+//     trial position t' = t + n.H (6 FP64 instructions per pair instead of 21) and the bounding sphere is tested
+//     against t' exactly;
+//   * tiles that straddle a half-box boundary take the general path (Cartesian difference -> fractional -> wrap).
+// Results differ from the untiled loop by summation order and by the rounding of Cartesian versus fractional
+// differences (1e-16 relative).
+// ---------------------------------------------------------------------------------------------
+// bytes of the staged pack: 4 double arrays + 1 int array of npad entries, then 10 tile arrays of ntp entries
+__host__ __device__ inline size_t gbk_pack_bytes(int npad, int ntp) { return ((size_t) npad * 36 + (size_t) ntp * 80 + 15) / 16 * 16; }
+
+struct TileView
+{
+  const double* pack;     // [x | y | z | q*scoul | type(int)] each npad long (Cartesian, wrapped into the primary cell)
+  const double* tile;     // [lo x,y,z | hi x,y,z | centre x,y,z | radius] each ntp long
+  int npad, ntp, n, ntiles;
+  __device__ __forceinline__ double x(int i) const { return pack[i]; }
+  __device__ __forceinline__ double y(int i) const { return pack[npad + i]; }
+  __device__ __forceinline__ double z(int i) const { return pack[2 * npad + i]; }
+  __device__ __forceinline__ double q(int i) const { return pack[3 * npad + i]; }
+  __device__ __forceinline__ int type(int i) const { return reinterpret_cast<const int*>(pack + 4 * (size_t) npad)[i]; }
+  __device__ __forceinline__ double lo(int k, int t) const { return tile[k * ntp + t]; }
+  __device__ __forceinline__ double hi(int k, int t) const { return tile[(3 + k) * ntp + t]; }
+  __device__ __forceinline__ double c(int k, int t) const { return tile[(6 + k) * ntp + t]; }
+  __device__ __forceinline__ double rad(int t) const { return tile[9 * ntp + t]; }
+};
+
+template <int CELL>
+struct InvRegs
+{
+  double i0, i1, i2, i3, i4, i5, i6, i7, i8;
+  __device__ __forceinline__ void load(const DevParams& P)
+  {
+    i0 = P.inv[0]; i1 = P.inv[1]; i2 = P.inv[2]; i3 = P.inv[3]; i4 = P.inv[4]; i5 = P.inv[5]; i6 = P.inv[6]; i7 = P.inv[7]; i8 = P.inv[8];
+  }
+  __device__ __forceinline__ void frac(double dx, double dy, double dz, double& sx, double& sy, double& sz) const
+  {
+    if(CELL == 2) { sx = i0 * dx; sy = i4 * dy; sz = i8 * dz; }
+    else if(CELL == 1) { sx = i0 * dx + i3 * dy + i6 * dz; sy = i4 * dy + i7 * dz; sz = i8 * dz; }
+    else { sx = i0 * dx + i3 * dy + i6 * dz; sy = i1 * dx + i4 * dy + i7 * dz; sz = i2 * dx + i5 * dy + i8 * dz; }
+  }
+};
+
+__device__ __forceinline__ double round_magic(double d)
+{
+  const double M = 6755399441055744.0;
+  return __dsub_rn(__dadd_rn(d, M), M);
+}
+
+// drain for the tile path: queue codes are (pack index << 6) | trial atom, type and charge come from the pack
+__device__ __forceinline__ void drain_tiles(const DevParams& P, const PairTables& W, const TileView& V, const TrialGroup* T, const WarpQueue* Q,
+                                            int lane, int off, int n, PairAcc<1>& acc)
+{
+  if(lane < n)
+  {
+    const double r2 = Q->r2[off + lane];
+    const int code = Q->code[off + lane];
+    const int i = code >> 6, a = code & 63;
+    const int row = V.type(i) * P.ntypes + T->type[a];
+    const double qq = V.q(i) * T->q[a];
+    double ev, er; int fl;
+    pair_energy(P, W.etab, W.ffp, W.unit, r2, row, T->scale[a], qq, ev, er, fl);
+    acc.vdw[0] += ev; acc.real[0] += er; acc.flag |= fl;
+  }
+}
+
+// one trial atom `a` (fractional tf*, Cartesian tc*) against the whole pack
+template <int CELL>
+__device__ __forceinline__ void pair_tiles_atom(const DevParams& P, const PairTables& W, const TileView& V, const TrialGroup* T, int a,
+                                                double tfx, double tfy, double tfz, double tcx, double tcy, double tcz,
+                                                WarpQueue* Q, int& qn, PairAcc<1>& acc)
+{
+  GBK_ASSUME_SHARED(V.pack); GBK_ASSUME_SHARED(V.tile);
+  const int lane = (int) lane_id();
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const double cut_max = P.cull_rcut * P.cull_rcut;
+  CellRegs<CELL> C; C.load(P);
+  for(int tb = 0; tb < V.ntiles; tb += 32)
+  {
+    const int t = tb + lane;
+    bool visit = false, fast = false;
+    double px = 0.0, py = 0.0, pz = 0.0;       // shifted trial position t' of a uniform tile
+    if(t < V.ntiles)
+    {
+      const double ax = V.lo(0, t) - tfx, bx = V.hi(0, t) - tfx;
+      const double ay = V.lo(1, t) - tfy, by = V.hi(1, t) - tfy;
+      const double az = V.lo(2, t) - tfz, bz = V.hi(2, t) - tfz;
+      const double nax = round_magic(ax), nbx = round_magic(bx), nay = round_magic(ay), nby = round_magic(by), naz = round_magic(az), nbz = round_magic(bz);
+      const bool ux = nax == nbx, uy = nay == nby, uz = naz == nbz;
+      const bool okx = ux ? ((ax - nax <= P.cull_w[0]) && (bx - nax >= -P.cull_w[0])) : ((ax - nax <= P.cull_w[0]) || (bx - nbx >= -P.cull_w[0]));
+      const bool oky = uy ? ((ay - nay <= P.cull_w[1]) && (by - nay >= -P.cull_w[1])) : ((ay - nay <= P.cull_w[1]) || (by - nby >= -P.cull_w[1]));
+      const bool okz = uz ? ((az - naz <= P.cull_w[2]) && (bz - naz >= -P.cull_w[2])) : ((az - naz <= P.cull_w[2]) || (bz - nbz >= -P.cull_w[2]));
+      visit = okx && oky && okz;
+      fast = ux && uy && uz;
+      if(visit && fast)
+      {
+        // t' = t + n.H (rows of the cell are the lattice vectors)
+        px = tcx + (C.c0 * nax + C.c3 * nay + C.c6 * naz);
+        py = tcy + (C.c1 * nax + C.c4 * nay + C.c7 * naz);
+        pz = tcz + (C.c2 * nax + C.c5 * nay + C.c8 * naz);
+        const double dx = V.c(0, t) - px, dy = V.c(1, t) - py, dz = V.c(2, t) - pz;
+        const double reach = P.cull_rcut + V.rad(t);
+        visit = (dx * dx + dy * dy + dz * dz) <= reach * reach * (1.0 + 1e-12);
+      }
+    }
+    unsigned mfast = __ballot_sync(0xffffffffu, visit && fast);
+    unsigned mslow = __ballot_sync(0xffffffffu, visit && !fast);
+    for(; mfast; mfast &= mfast - 1)
+    {
+      const int l = __ffs(mfast) - 1;
+      const double sx = __shfl_sync(0xffffffffu, px, l), sy = __shfl_sync(0xffffffffu, py, l), sz = __shfl_sync(0xffffffffu, pz, l);
+      const int i = (tb + l) * 32 + lane;
+      const double dx = V.x(i) - sx, dy = V.y(i) - sy, dz = V.z(i) - sz;
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      const bool hit = r2 < cut_max;                       // padded atoms sit at 1e30
+      const unsigned mk = __ballot_sync(0xffffffffu, hit);
+      if(hit) { const int p = qn + __popc(mk & lt_mask); Q->r2[p] = r2; Q->code[p] = (i << 6) | a; }
+      qn += __popc(mk);
+      if(qn >= 32)
+      {
+        __syncwarp();
+        qn -= 32; drain_tiles(P, W, V, T, Q, lane, qn, 32, acc);
+        __syncwarp();
+      }
+    }
+    if(mslow)
+    {
+      InvRegs<CELL> I; I.load(P);
+      for(; mslow; mslow &= mslow - 1)
+      {
+        const int l = __ffs(mslow) - 1;
+        const int i = (tb + l) * 32 + lane;
+        double sx, sy, sz;
+        I.frac(V.x(i) - tcx, V.y(i) - tcy, V.z(i) - tcz, sx, sy, sz);
+        const double r2 = C.r2(sx, sy, sz);
+        const bool hit = (i < V.n) && (r2 < cut_max);
+        const unsigned mk = __ballot_sync(0xffffffffu, hit);
+        if(hit) { const int p = qn + __popc(mk & lt_mask); Q->r2[p] = r2; Q->code[p] = (i << 6) | a; }
+        qn += __popc(mk);
+        if(qn >= 32)
+        {
+          __syncwarp();
+          qn -= 32; drain_tiles(P, W, V, T, Q, lane, qn, 32, acc);
+          __syncwarp();
+        }
+      }
+    }
+  }
+}
+
+// every trial atom of the group against the pack; the queue is drained at the end
+template <int CELL>
+__device__ __forceinline__ void pair_tiles_group(const DevParams& P, const PairTables& W, const TileView& V, const TrialGroup* T, int cs,
+                                                 const double* tc /* Cartesian [cs][3] */, WarpQueue* Q, PairAcc<1>& acc)
+{
+  int qn = 0;
+  for(int a = 0; a < cs; a++)
+    pair_tiles_atom<CELL>(P, W, V, T, a, T->fx[a], T->fy[a], T->fz[a], tc[3 * a], tc[3 * a + 1], tc[3 * a + 2], Q, qn, acc);
+  if(qn > 0)
+  {
+    __syncwarp();
+    drain_tiles(P, W, V, T, Q, (int) lane_id(), 0, qn, acc);
+    __syncwarp();
+  }
+}

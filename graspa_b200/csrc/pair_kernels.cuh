@@ -124,64 +124,61 @@ struct WidomA
   // template molecule = slot 0 of the component (mc_widom.h:256): Cartesian positions, charge, scaleCoul, type
   const double* __restrict__ tx; const double* __restrict__ ty; const double* __restrict__ tz;
   const double* __restrict__ tq; const double* __restrict__ tscoul; const int* __restrict__ ttype;
-  const double* __restrict__ pack; int npad; int use_pack; int stage_ff;
+  const double* __restrict__ pack; int npad, ntp, pack_n; int use_pack; int stage_ff;
   int first_bead_only;                         // 1: write the first-bead success code into stage[] and stop there
   double* rec;        // per insertion: [W12, HGv, HGr, GGv, GGr, x0,y0,z0, x1,...]  stride 5 + 3*ms
   int* stage;         // 0 ok, 1 first bead failed, 2 chain failed
 };
+
+// per-warp scratch of the Widom pair kernel: trial group, queue, chain coordinates (fractional + Cartesian), first-bead Cartesian
+__host__ __device__ inline size_t widom_per_warp_bytes(int norient, int cs)
+{
+  return (sizeof(TrialGroup) + sizeof(WarpQueue) + (size_t) norient * (cs > 0 ? cs : 1) * 6 * sizeof(double) + 4 * sizeof(double) + 15) / 16 * 16;
+}
 
 // per-warp context of the Widom pair kernel
 struct WidomCtx
 {
   PairTables W;
   SysView Sg;        // global slot arrays
-  SysView Ss;        // staged pack view (shared memory)
+  TileView V;        // staged, tile-sorted pack of the host components (shared memory); V.pack == nullptr: not staged
   const SegList* L;  // in shared memory
   TrialGroup* T; WarpQueue* Q;
 };
 
-// energies of the group currently in *T against every segment: out[s] = {HGv, HGr, GGv, GGr} per slot, flags bitmask
-template <int CS, int NS, int CELL>
-__device__ __forceinline__ void widom_group(const DevParams& P, const WidomCtx& X, int comp, int new_molid, int cs_dyn,
-                                            double out[NS][4], int& flags)
+// energies of the group currently in *T (Cartesian copies in tc[cs][3]) against every segment: out = {HGv, HGr, GGv, GGr}
+template <int CS, int CELL>
+__device__ __forceinline__ void widom_group(const DevParams& P, const WidomCtx& X, int comp, int new_molid, int cs_dyn, const double* tc,
+                                            double out[4], int& flag)
 {
   const SegList& L = *X.L;
-  double part[NS][4];
-#pragma unroll
-  for(int s = 0; s < NS; s++) { part[s][0] = part[s][1] = part[s][2] = part[s][3] = 0.0; }
+  double part[4] = {0.0, 0.0, 0.0, 0.0};
   int fl = 0;
+  const int cs = CS > 0 ? CS : cs_dyn;
+  if(X.V.pack != nullptr)
+  {
+    // all staged segments are host components (kind HG) and live in ONE tile-sorted pack
+    PairAcc<1> acc; acc.clear();
+    pair_tiles_group<CELL>(P, X.W, X.V, X.T, cs, tc, X.Q, acc);
+    part[0] += acc.vdw[0]; part[1] += acc.real[0]; fl |= acc.flag;
+  }
   const int nseg = L.nseg;
   for(int g = 0; g < nseg; g++)
   {
-    PairAcc<NS> acc; acc.clear();
+    if(L.staged[g]) continue;
+    PairAcc<1> acc; acc.clear();
     const int start = L.start[g], end = start + L.count[g];
     const bool gg = L.kind[g] == 2;
-    if(L.staged[g])
-    {
-      const SysAccess<true> S = make_access<true>(X.Ss);
-      pair_range<CS, NS, CELL, true, false>(P, X.W, S, start, end, -1, -1, X.T, cs_dyn, X.Q, 0, 1, acc);
-    }
-    else
-    {
-      const SysAccess<false> S = make_access<false>(X.Sg);
-      const int eb = (L.comp[g] == comp) ? new_molid : -1;
-      pair_range<CS, NS, CELL, false, true>(P, X.W, S, start, end, -1, eb, X.T, cs_dyn, X.Q, 0, 1, acc);
-    }
-#pragma unroll
-    for(int s = 0; s < NS; s++)
-    {
-      part[s][0] += gg ? 0.0 : acc.vdw[s]; part[s][1] += gg ? 0.0 : acc.real[s];
-      part[s][2] += gg ? acc.vdw[s] : 0.0; part[s][3] += gg ? acc.real[s] : 0.0;
-    }
+    const SysAccess<false> S = make_access<false>(X.Sg);
+    const int eb = (L.comp[g] == comp) ? new_molid : -1;
+    pair_range<CS, 1, CELL, false, true>(P, X.W, S, start, end, -1, eb, X.T, cs_dyn, X.Q, 0, 1, acc);
+    part[0] += gg ? 0.0 : acc.vdw[0]; part[1] += gg ? 0.0 : acc.real[0];
+    part[2] += gg ? acc.vdw[0] : 0.0; part[3] += gg ? acc.real[0] : 0.0;
     fl |= acc.flag;
   }
 #pragma unroll
-  for(int s = 0; s < NS; s++)
-#pragma unroll
-    for(int k = 0; k < 4; k++) out[s][k] = warp_sum(part[s][k]);
-  flags = 0;
-#pragma unroll
-  for(int s = 0; s < NS; s++) if(__any_sync(0xffffffffu, (fl >> s) & 1)) flags |= 1 << s;
+  for(int k = 0; k < 4; k++) out[k] = warp_sum(part[k]);
+  flag = __any_sync(0xffffffffu, fl & 1) ? 1 : 0;
 }
 
 template <int CELL>
@@ -197,26 +194,27 @@ k_widom_pair(DevParams P, SysView Sg, SegList Lin, WidomA A)
   SegList* L = reinterpret_cast<SegList*>(smem + GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD + ff_bytes);
   const size_t head = (GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD + ff_bytes + sizeof(SegList) + 15) / 16 * 16;
   double* pack = reinterpret_cast<double*>(smem + head);
-  const size_t pack_bytes = A.use_pack ? ((size_t) A.npad * 36 + 15) / 16 * 16 : 0;
+  const size_t pack_bytes = A.use_pack ? gbk_pack_bytes(A.npad, A.ntp) : 0;
   unsigned char* wbase = smem + head + pack_bytes;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = lane_id();
   const int cs = A.ms - 1;
-  const size_t per_warp = (sizeof(TrialGroup) + sizeof(WarpQueue) + (size_t) A.norient * (cs > 0 ? cs : 1) * 6 * sizeof(double) + 15) / 16 * 16;
+  const size_t per_warp = widom_per_warp_bytes(A.norient, cs);
   TrialGroup* T = reinterpret_cast<TrialGroup*>(wbase + warp * per_warp);
   WarpQueue* Q = reinterpret_cast<WarpQueue*>(reinterpret_cast<unsigned char*>(T) + sizeof(TrialGroup));
   double* chain_f = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(Q) + sizeof(WarpQueue));   // fractional [norient][cs][3]
   double* chain_c = chain_f + (size_t) A.norient * (cs > 0 ? cs : 1) * 3;                                  // Cartesian
+  double* fb_c = chain_c + (size_t) A.norient * (cs > 0 ? cs : 1) * 3;                                     // Cartesian first-bead trial
 
   stage_erfc_table(P, etab);
   if(A.stage_ff) for(int i = threadIdx.x; i < P.ntypes * P.ntypes; i += blockDim.x) fftab[i] = P.ffA[i];
   if(threadIdx.x == 0) *L = Lin;
-  WidomCtx X; X.W.etab = etab; X.W.ffp = A.stage_ff ? fftab : P.ffA; X.W.unit = P.all_unit_scale != 0; X.Sg = Sg; X.Ss = Sg; X.L = L; X.T = T; X.Q = Q;
+  WidomCtx X; X.W.etab = etab; X.W.ffp = A.stage_ff ? fftab : P.ffA; X.W.unit = P.all_unit_scale != 0; X.Sg = Sg; X.L = L; X.T = T; X.Q = Q;
+  X.V.pack = nullptr; X.V.tile = nullptr; X.V.npad = 0; X.V.ntp = 0; X.V.n = 0; X.V.ntiles = 0;
   if(A.use_pack)
   {
     stage_bulk(pack, A.pack, (uint32_t) pack_bytes, bar);
-    X.Ss.fx = pack; X.Ss.fy = pack + A.npad; X.Ss.fz = pack + 2 * (size_t) A.npad; X.Ss.q = pack + 3 * (size_t) A.npad;
-    X.Ss.type = reinterpret_cast<const int*>(pack + 4 * (size_t) A.npad);
-    X.Ss.scale = nullptr; X.Ss.scoul = nullptr; X.Ss.molid = nullptr;
+    X.V.pack = pack; X.V.tile = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(pack) + (size_t) A.npad * 36);
+    X.V.npad = A.npad; X.V.ntp = A.ntp; X.V.n = A.pack_n; X.V.ntiles = A.npad / 32;
   }
   __syncthreads();
   const long long gw = (long long) blockIdx.x * nwarps + warp, tw = (long long) gridDim.x * nwarps;
@@ -236,32 +234,20 @@ k_widom_pair(DevParams P, SysView Sg, SegList Lin, WidomA A)
       to_frac(P, px, py, pz, fsx, fsy, fsz);
     }
     double my_e[4] = {0, 0, 0, 0}; int my_flag = 0;
-    // two first-bead trials share every loaded framework atom (slots 0 and 1); an odd last trial goes alone
-    int t = 0;
-    for(; t + 1 < A.ntrials; t += 2)
-    {
-      const int src = t + (lane & 1);
-      const double bx = __shfl_sync(0xffffffffu, fsx, src), by = __shfl_sync(0xffffffffu, fsy, src), bz = __shfl_sync(0xffffffffu, fsz, src);
-      if(lane < 2)
-      {
-        T->fx[lane] = bx; T->fy[lane] = by; T->fz[lane] = bz;
-        T->q[lane] = q0; T->scale[lane] = 1.0; T->type[lane] = type0; T->slot[lane] = lane;
-      }
-      __syncwarp();
-      double e[2][4]; int fl;
-      widom_group<2, 2, CELL>(P, X, A.comp, A.new_molid, 2, e, fl);
-      if(lane == t)     { my_e[0] = e[0][0]; my_e[1] = e[0][1]; my_e[2] = e[0][2]; my_e[3] = e[0][3]; my_flag = fl & 1; }
-      if(lane == t + 1) { my_e[0] = e[1][0]; my_e[1] = e[1][1]; my_e[2] = e[1][2]; my_e[3] = e[1][3]; my_flag = (fl >> 1) & 1; }
-      __syncwarp();
-    }
-    if(t < A.ntrials)
+    // one tile-culled pass per first-bead trial
+    for(int t = 0; t < A.ntrials; t++)
     {
       const double bx = __shfl_sync(0xffffffffu, fsx, t), by = __shfl_sync(0xffffffffu, fsy, t), bz = __shfl_sync(0xffffffffu, fsz, t);
-      if(lane == 0) { T->fx[0] = bx; T->fy[0] = by; T->fz[0] = bz; T->q[0] = q0; T->scale[0] = 1.0; T->type[0] = type0; T->slot[0] = 0; }
+      const double cx = __shfl_sync(0xffffffffu, px, t), cy = __shfl_sync(0xffffffffu, py, t), cz = __shfl_sync(0xffffffffu, pz, t);
+      if(lane == 0)
+      {
+        T->fx[0] = bx; T->fy[0] = by; T->fz[0] = bz; T->q[0] = q0; T->scale[0] = 1.0; T->type[0] = type0; T->slot[0] = 0;
+        fb_c[0] = cx; fb_c[1] = cy; fb_c[2] = cz;
+      }
       __syncwarp();
-      double e[1][4]; int fl;
-      widom_group<1, 1, CELL>(P, X, A.comp, A.new_molid, 1, e, fl);
-      if(lane == t) { my_e[0] = e[0][0]; my_e[1] = e[0][1]; my_e[2] = e[0][2]; my_e[3] = e[0][3]; my_flag = fl & 1; }
+      double e[4]; int fl;
+      widom_group<1, CELL>(P, X, A.comp, A.new_molid, 1, fb_c, e, fl);
+      if(lane == t) { my_e[0] = e[0]; my_e[1] = e[1]; my_e[2] = e[2]; my_e[3] = e[3]; my_flag = fl; }
       __syncwarp();
     }
     double tot = my_e[0] + my_e[2]; if(P.vdw_real_bias) tot += my_e[1] + my_e[3];
@@ -313,12 +299,13 @@ k_widom_pair(DevParams P, SysView Sg, SegList Lin, WidomA A)
           T->q[lane] = A.tq[1 + lane] * A.tscoul[1 + lane]; T->scale[lane] = 1.0; T->type[lane] = A.ttype[1 + lane]; T->slot[lane] = 0;
         }
         __syncwarp();
-        double e[1][4]; int fl;
-        if(cs == 1)      widom_group<1, 1, CELL>(P, X, A.comp, A.new_molid, cs, e, fl);
-        else if(cs == 2) widom_group<2, 1, CELL>(P, X, A.comp, A.new_molid, cs, e, fl);
-        else if(cs == 3) widom_group<3, 1, CELL>(P, X, A.comp, A.new_molid, cs, e, fl);
-        else             widom_group<0, 1, CELL>(P, X, A.comp, A.new_molid, cs, e, fl);
-        if(lane == o) { my_e[0] = e[0][0]; my_e[1] = e[0][1]; my_e[2] = e[0][2]; my_e[3] = e[0][3]; my_flag = fl & 1; }
+        double e[4]; int fl;
+        const double* tc = chain_c + (size_t) o * cs * 3;
+        if(cs == 1)      widom_group<1, CELL>(P, X, A.comp, A.new_molid, cs, tc, e, fl);
+        else if(cs == 2) widom_group<2, CELL>(P, X, A.comp, A.new_molid, cs, tc, e, fl);
+        else if(cs == 3) widom_group<3, CELL>(P, X, A.comp, A.new_molid, cs, tc, e, fl);
+        else             widom_group<0, CELL>(P, X, A.comp, A.new_molid, cs, tc, e, fl);
+        if(lane == o) { my_e[0] = e[0]; my_e[1] = e[1]; my_e[2] = e[2]; my_e[3] = e[3]; my_flag = fl; }
         __syncwarp();
       }
       double tot2 = my_e[0] + my_e[2]; if(P.vdw_real_bias) tot2 += my_e[1] + my_e[3];
