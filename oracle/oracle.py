@@ -131,6 +131,13 @@ def cell_from_cif(a, b, c, al, be, ga, n):
     return cell
 
 
+def pbc(v, box: Box):
+    """minimum image of one difference vector, in place (maths.cuh:427-450)"""
+    ob = c_box(box)
+    lib().orc_pbc(_p(v, f64p), C.byref(ob))
+    return v
+
+
 def ff_mix(eps, sig, shifted, tail, cutoff_vdw):
     n = len(eps)
     eps = np.ascontiguousarray(eps, dtype=np.float64); sig = np.ascontiguousarray(sig, dtype=np.float64)

@@ -28,6 +28,25 @@ def load_config(name):
     return box, ff, system, z
 
 
+ENERGY_TO_KELVIN = 1.20272430057          # the reference's internal energy unit -> K (read_data.cpp:1200)
+
+
+def load_nist(b):
+    """-> (box, ff, system, printed) of Box-<b> of the reference's NIST SPC/E known-answer example
+    (tests/golden/nist_spce.npz, written by tests/golden/make_nist.py).  printed = the reference's own output.txt values
+    {vdw_gg, real_gg, ewald_gg (Fourier - self - intra), tail, total, fourier_gg}, internal units."""
+    z = dict(np.load(os.path.join(GOLDEN, "nist_spce.npz")))
+    ff = ForceField(z["eps"], z["sigma"], z["shift"], float(z["cutoff_vdw"]), float(z["cutoff_coul"]), overlap=float(z["overlap"]),
+                    use_tail=z["use_tail"], tail_energy=z["tail_energy"])
+    box = Box(z[f"b{b}_cell"], alpha=float(z[f"b{b}_alpha"]), kmax=tuple(int(k) for k in z[f"b{b}_kmax"]),
+              recip_cutoff=float(z[f"b{b}_recip_cutoff"]), use_lammps_ewald=True)
+    pos = z[f"b{b}_pos"]; n = len(pos); ms = len(z["mol_type"]); nm = n // ms
+    system = System(1, np.array([0, n]), np.array([0, ms]), pos, np.tile(z["mol_charge"], nm), np.tile(z["mol_type"], nm),
+                    np.repeat(np.arange(nm), ms), alloc=np.array([0, n]))
+    keys = ("vdw_gg", "real_gg", "ewald_gg", "tail", "total", "fourier_gg")
+    return box, ff, system, dict(zip(keys, (float(x) for x in z[f"b{b}_printed"])))
+
+
 def rel_err(a, b, floor=0.0):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.maximum(np.abs(b), floor), 1e-300)))

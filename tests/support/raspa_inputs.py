@@ -107,7 +107,7 @@ def read_cif(path, names, pseudo_charge, unitcells, use_cif_charge):
         fpos.append([float(t[cols[1]]), float(t[cols[2]]), float(t[cols[3]])])
         typ.append(j)
         chg.append(float(t[cols[4]]) if (use_cif_charge and 4 in cols) else pseudo_charge[j])
-    fpos = np.array(fpos); typ = np.array(typ, dtype=np.int64); chg = np.array(chg)
+    fpos = np.array(fpos, dtype=np.float64).reshape(-1, 3); typ = np.array(typ, dtype=np.int64); chg = np.array(chg, dtype=np.float64)
     nx, ny, nz = unitcells
     shift = np.array([1.0 / nx, 1.0 / ny, 1.0 / nz])
     P, T, Q = [], [], []
@@ -122,6 +122,62 @@ def read_cif(path, names, pseudo_charge, unitcells, use_cif_charge):
     return cell, np.concatenate(P), np.concatenate(T), np.concatenate(Q)
 
 
+def apply_tail_overrides(ffdef, names, eps, sig, shifted, cut_vdw, ut, te):
+    """OverWriteTailCorrection, read_data.cpp:1132-1176 ("I J truncated yes" under "# rules to overwrite"); edits ut/te in place"""
+    if not os.path.exists(ffdef):
+        return
+    with open(ffdef) as f:
+        lines = f.read().splitlines()
+    nover = int(_terms(lines[1])[0])
+    n = len(names)
+    for ln in lines[3:3 + nover]:
+        t = _terms(ln)
+        if len(t) == 4 and t[3] == "yes":
+            i, j = names.index(t[0]), names.index(t[1])
+            _, _, _, _, te1 = orc.ff_mix(eps, sig, [shifted] * n, [True] * n, cut_vdw)
+            ut[i * n + j] = 1; ut[j * n + i] = 1; te[i * n + j] = te1[i * n + j]; te[j * n + i] = te1[i * n + j]
+
+
+def lammps_recip_cutoff(cell, kmax):
+    """ReciprocalCutOff of the LAMMPS-style Ewald set-up, read_data.cpp:669-685 (the tilt factors are zeroed there)"""
+    lx, ly, lz = cell[0], cell[4], cell[8]
+    ux, vy, wz = 2 * np.pi / lx, 2 * np.pi / ly, 2 * np.pi / lz
+    kx = kmax[0] * ux; ky = kmax[0] * 0.0 + kmax[1] * vy; kz = kmax[0] * 0.0 + kmax[1] * 0.0 + kmax[2] * wz
+    return max(kx * kx, ky * ky, kz * kz) * 1.00001
+
+
+def read_restart_positions(path, adsorbate_index, molsize, box=None, with_charge=False):
+    """RASPA-2 restart file -> positions (n, 3) [and charges] of one adsorbate component, RestartFileParser
+    read_data.cpp:3000-3221: the block starts two lines after "Component: <i>"; `interval` position lines, then velocity,
+    force, charge, scaling blocks of the same length.  Atoms other than the first of a molecule are re-wrapped to the
+    nearest image of the first one (:3147-3160) when `box` is given."""
+    with open(path) as f:
+        lines = f.read().splitlines()
+    start = None; nmol = 0
+    for k, ln in enumerate(lines):
+        if ln.find(f"Component: {adsorbate_index}") == 0:
+            nmol = int(_terms(ln)[3]); start = k + 2
+            break
+    if start is None or nmol == 0:
+        return (np.zeros((0, 3)), np.zeros(0)) if with_charge else np.zeros((0, 3))
+    interval = nmol * molsize
+    pos = np.zeros((interval, 3)); chg = np.zeros(interval)
+    first = None
+    for a in range(interval):
+        t = _terms(lines[start + a])
+        assert t[0].startswith("Adsorbate-atom-position"), "Cannot find matching strings in the range for reading positions!"
+        p = np.array([float(t[3]), float(t[4]), float(t[5])])
+        if int(t[2]) == 0:
+            first = p
+        elif box is not None:
+            v = np.ascontiguousarray(p - first)
+            orc.pbc(v, box)
+            p = first + v
+        pos[a] = p
+        chg[a] = float(_terms(lines[start + 3 * interval + a])[3])
+    return (pos, chg) if with_charge else pos
+
+
 def load_deck(folder, unitcells=None, extra_alloc=0):
     """-> dict(box, ff, system, beta, ntrials, norient, names, sim).  Rigid single-component framework decks
     (configs A, B, D, E); separated framework components (config C) are handled by the host library, not here."""
@@ -131,19 +187,7 @@ def load_deck(folder, unitcells=None, extra_alloc=0):
     assert pnames == names, "pseudo_atoms.def must list the force-field names in order (read_data.cpp:1344)"
     cut_vdw = float(sim.get("CutOffVDW", [12.0])[0]); cut_coul = float(sim.get("CutOffCoulomb", [12.0])[0])
     e, s, sh, ut, te = orc.ff_mix(eps, sig, [shifted] * len(eps), [tail] * len(eps), cut_vdw)
-    # OverWriteTailCorrection, read_data.cpp:1132-1176 ("I J truncated yes" under "# rules to overwrite")
-    ffdef = os.path.join(folder, "force_field.def")
-    if os.path.exists(ffdef):
-        with open(ffdef) as f:
-            lines = f.read().splitlines()
-        nover = int(_terms(lines[1])[0])
-        n = len(names)
-        for ln in lines[3:3 + nover]:
-            t = _terms(ln)
-            if len(t) == 4 and t[3] == "yes":
-                i, j = names.index(t[0]), names.index(t[1])
-                _, _, _, _, te1 = orc.ff_mix(eps, sig, [shifted] * n, [True] * n, cut_vdw)
-                ut[i * n + j] = 1; ut[j * n + i] = 1; te[i * n + j] = te1[i * n + j]; te[j * n + i] = te1[i * n + j]
+    apply_tail_overrides(os.path.join(folder, "force_field.def"), names, eps, sig, shifted, cut_vdw, ut, te)
     charge_method = sim.get("ChargeMethod", ["None"])[0].lower()
     no_charges = charge_method != "ewald"
     ff = ForceField(e, s, sh, cut_vdw, cut_coul, overlap=float(sim.get("OverlapCriteria", [1e5])[0]), no_charges=no_charges,

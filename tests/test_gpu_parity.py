@@ -225,3 +225,23 @@ def test_widom_shards_bin_on_the_global_index(gpu_engine_factory):
     with pytest.raises(Exception):
         eng.widom_batch(comp, rnd[:10].reshape(-1, 3), uni[:10], shard=(n - 5, n))   # range sticks out of the job
     eng.close()
+
+
+@pytest.mark.parametrize("b", [1, 2, 3, 4])
+def test_nist_spce_known_answers(gpu_engine_factory, b):
+    """The reference's known-answer example (Examples/Reference_NIST_SPCE): total energies of 100-400 SPC/E waters in
+    triclinic boxes through the C ABI against the reference's printed output.txt values (5 decimals), LAMMPS-style
+    Ewald set-up, an empty framework component, O-O tail correction."""
+    from tests.conftest import load_nist
+    box, ff, s, ref = load_nist(b)
+    eng = gpu_engine_factory(box, ff, s)
+    v = eng.total_vdw_real(); E = eng.total_ewald(store=True); tail = eng.tail_total()
+    assert v["HHVDW"] == 0.0 and v["HGVDW"] == 0.0 and v["HHReal"] == 0.0 and v["HGReal"] == 0.0
+    assert abs(v["GGVDW"] - ref["vdw_gg"]) <= 1e-10 * abs(ref["vdw_gg"]) + 1e-5
+    assert abs(v["GGReal"] - ref["real_gg"]) <= 1e-10 * abs(ref["real_gg"]) + 1e-5
+    assert abs(E["GGEwaldE"] - ref["ewald_gg"]) <= 1e-10 * abs(ref["ewald_gg"]) + 1e-5
+    assert E["HHEwaldE"] == 0.0 and E["HGEwaldE"] == 0.0
+    assert abs(tail - ref["tail"]) <= 1e-5
+    total = v["GGVDW"] + v["GGReal"] + E["GGEwaldE"] + tail
+    assert abs(total - ref["total"]) <= 2e-5
+    eng.close()

@@ -82,3 +82,39 @@ def test_ewald_setup_matches_published_parameters(oracle):
     box, ff, s, z = load_config("B")
     b = oracle.ewald_setup(box, 12.0, 1e-6)
     assert abs(b.alpha - 0.265058) < 5e-7 and b.kmax == (11, 11, 7) and b.nvec == 4140
+
+
+# NIST SPC/E reference calculations in non-cuboid cells, as tabulated in the reference's
+# Examples/Reference_NIST_SPCE/readme.md:7-17 (Kelvin): E_disp, E_tail, E_real, number of wave vectors, E_fourier,
+# E_self + E_intra, E_total
+NIST_SPCE = {
+    1: (111992.0, -4109.19, -727219.0, 831, 44677.0, -146595.0, -721254.0),
+    2: (43286.0, -2105.61, -476902.0, 1068, 44409.4, -109946.0, -501259.0),
+    3: (14403.3, -1027.3, -297129.0, 838, 28897.4, -73298.0, -328153.0),
+    4: (25025.1, -163.091, -171462.0, 1028, 22337.2, -36648.0, -160912.0),
+}
+
+
+@pytest.mark.parametrize("b", [1, 2, 3, 4])
+def test_nist_spce_known_answers(oracle, b):
+    """The reference's own known-answer test for this path: total VDW / real / Fourier / self+intra / tail of 100-400
+    SPC/E waters in triclinic boxes, LAMMPS-style Ewald set-up.  The oracle must reproduce the reference's printed
+    energies to every printed decimal, and NIST's table to its 6 significant figures."""
+    from tests.conftest import load_nist, ENERGY_TO_KELVIN as K
+    box, ff, s, ref = load_nist(b)
+    v = oracle.total_vdw_real(box, ff, s)                 # HHv, HHr, HGv, HGr, GGv, GGr
+    E, sa, sf = oracle.ewald_total(box, s)                # GG (Fourier - self - intra), HH, HG
+    tail = oracle.tail_total(ff, pseudo_atom_counts(s, ff.ntypes), box.volume)
+    assert v[0] == v[1] == v[2] == v[3] == 0.0 and E[1] == E[2] == 0.0
+    # the reference's printed values (5 decimals)
+    assert abs(v[4] - ref["vdw_gg"]) < 1e-5 and abs(v[5] - ref["real_gg"]) < 1e-5
+    assert abs(E[0] - ref["ewald_gg"]) < 1e-5 and abs(tail - ref["tail"]) < 1e-5
+    assert abs(v.sum() + E.sum() + tail - ref["total"]) < 2e-5
+    # NIST's table
+    disp, etail, real, nk, fourier, self_intra, total = NIST_SPCE[b]
+    assert int((np.abs(sa.reshape(-1, 2)).sum(axis=1) > 0).sum()) == nk
+    assert abs(v[4] * K - disp) <= 1e-5 * abs(disp) and abs(tail * K - etail) <= 1e-5 * abs(etail)
+    assert abs(v[5] * K - real) <= 1e-5 * abs(real)
+    assert abs(ref["fourier_gg"] * K - fourier) <= 5e-5 * abs(fourier)
+    assert abs((E[0] - ref["fourier_gg"]) * K - self_intra) <= 5e-5 * abs(self_intra)
+    assert abs((v.sum() + E.sum() + tail) * K - total) <= 1e-5 * abs(total)
