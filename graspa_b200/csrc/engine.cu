@@ -590,7 +590,7 @@ int gb_upload_atoms(gb_engine* e, int32_t c, const gb_atoms* a)
 {
   if(!e || !a) return fail(GB_ERR_ARG, "null argument");
   if(c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "component out of range");
-  if(a->n_live > a->n_upload || a->n_upload > a->n_alloc || a->molsize <= 0) return fail(GB_ERR_ARG, "inconsistent atom counts");
+  if(a->n_live > a->n_upload || a->n_upload > a->n_alloc || (a->molsize <= 0 && a->n_alloc > 0)) return fail(GB_ERR_ARG, "inconsistent atom counts");   // an empty component (a box without framework atoms) may have molsize 0
   if(!e->have_ff) return fail(GB_ERR_STATE, "upload the force field before atoms");
   if(e->committed && !e->device_stale && e->nslots > 0)
   {
@@ -618,7 +618,7 @@ int gb_upload_atoms(gb_engine* e, int32_t c, const gb_atoms* a)
   {
     for(int i = 0; i < C.natoms; i++) { const int t = e->htype[(size_t) C.offset + i]; if(t >= 0 && t < e->ntypes) e->npseudo[t]--; }
   }
-  C.molsize = (int) a->molsize; C.natoms = (int) a->n_live; C.uploaded = true;
+  C.molsize = std::max(1, (int) a->molsize); C.natoms = (int) a->n_live; C.uploaded = true;
   for(int64_t i = 0; i < a->n_upload; i++)
   {
     const size_t g = (size_t) C.offset + i;

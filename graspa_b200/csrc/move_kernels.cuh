@@ -47,7 +47,8 @@ struct CbmcArgs
   long long pool_off;
   const double* __restrict__ pool3;
   double uniform, scale, scale_coul, stored_r;
-  double preset[3]; int has_preset;
+  double preset[3]; int has_preset;   // 1: preset[] holds the position; 2: read it from preset_src (copy_firstbead_to_new, mc_swap_moves.h:178-181)
+  const double* preset_src[3];
   CompView C;                  // slots of the component (index 0 = slot 0 of the component)
   MoveBufs B;
   unsigned int* ticket;
@@ -167,6 +168,7 @@ k_cbmc_first_bead(DevParams P, SysView S, SegList L, CbmcArgs A, int nsplit)
     double x, y, z;
     const bool existing = (ty == 1 || ty == 3 || ty == 5) && t == 0;
     if(existing) { x = A.C.x[start]; y = A.C.y[start]; z = A.C.z[start]; }
+    else if(ty == 4 && A.has_preset == 2) { x = A.preset_src[0][0]; y = A.preset_src[1][0]; z = A.preset_src[2][0]; }
     else if(ty == 4 && A.has_preset) { x = A.preset[0]; y = A.preset[1]; z = A.preset[2]; }
     else { const double* r = A.pool3 + 3 * (A.pool_off + t); x = P.cell[0] * r[0]; y = P.cell[4] * r[1]; z = P.cell[8] * r[2]; }
     double fx, fy, fz; to_frac(P, x, y, z, fx, fy, fz);

@@ -31,7 +31,7 @@ DECLARED_SYMBOLS = [
     "gb_trial_energies", "gb_single_body_propose", "gb_single_body_delta", "gb_single_body_delta_explicit",
     "gb_ewald_delta", "gb_ewald_delta_identity_swap", "gb_ewald_delta_explicit", "gb_ewald_commit",
     "gb_tail_total", "gb_tail_difference", "gb_tail_identity_swap",
-    "gb_accept_translation", "gb_accept_insertion", "gb_accept_deletion", "gb_accept_reinsertion", "gb_append_molecule",
+    "gb_accept_translation", "gb_accept_insertion", "gb_accept_deletion", "gb_accept_reinsertion", "gb_accept_identity_swap", "gb_append_molecule",
     "gb_number_of_molecules", "gb_total_vdw_real", "gb_total_ewald", "gb_widom_batch", "gb_widom_first_bead_success",
     "gb_launch_count", "gb_timing_enable", "gb_timing_read", "gb_measure_fp64_peak",
 ]
@@ -332,6 +332,9 @@ class Engine:
 
     def accept_reinsertion(self, comp, molecule):
         self._chk(self.lib.gb_accept_reinsertion(self.h, C.c_int32(comp), C.c_int64(molecule)))
+
+    def accept_identity_swap(self, old_comp, old_molecule, new_comp):
+        self._chk(self.lib.gb_accept_identity_swap(self.h, C.c_int32(old_comp), C.c_int64(old_molecule), C.c_int32(new_comp)))
 
     def append_molecule(self, comp, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64)

@@ -8,6 +8,7 @@
 // "rules to overwrite" of force_field.def, Ewald with the RASPA-2 heuristic or the LAMMPS-style explicit set-up.
 // Not read (the engine has no use for them yet): separated framework components, block pockets, CBCF/TMMC keywords.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -325,6 +326,74 @@ inline void setup_ewald(Deck& d)
   d.recip_cutoff = std::pow(1.05 * (double) m, 2);
 }
 
+// ComputeFugacity, equations_of_state.h:121-330 (Peng-Robinson mixture, no binary interaction parameters) with the
+// cubic solver of :61-118.  Runs when any adsorbate asks for "FugacityCoefficient PR-EOS" and then overrides the
+// coefficients of EVERY adsorbate, as the reference does (:137-147).
+inline void compute_fugacity(Deck& d)
+{
+  bool need = false;
+  for(const auto& c : d.comps) if(c.fugacity_coeff < 0.0) need = true;
+  if(!need) return;
+  const double Rg = 8.314, P = d.pressure_pa, T = d.temperature;
+  const size_t n = d.comps.size();
+  std::vector<double> x(n), a(n), b(n), A(n), B(n);
+  double sum = 0.0;
+  for(size_t i = 0; i < n; i++)
+  {
+    const Component& c = d.comps[i];
+    x[i] = c.mol_fraction; sum += x[i];
+    const double Tr = T / c.tc;
+    const double kappa = 0.37464 + 1.54226 * c.acentric - 0.26992 * std::pow(c.acentric, 2);
+    const double alpha = std::pow(1.0 + kappa * (1.0 - std::sqrt(Tr)), 2);
+    a[i] = 0.45724 * alpha * std::pow(Rg * c.tc, 2) / c.pc;
+    b[i] = 0.07780 * Rg * c.tc / c.pc;
+    A[i] = a[i] * P / std::pow(Rg * T, 2);
+    B[i] = b[i] * P / (Rg * T);
+  }
+  if(std::fabs(sum - 1.0) > 0.0001) throw std::runtime_error("Sum of Mol Fractions does not equal 1.0");
+  double Amix = 0.0, Bmix = 0.0;
+  for(size_t i = 0; i < n; i++)
+  {
+    Bmix += x[i] * b[i];
+    for(size_t j = 0; j < n; j++) Amix += x[i] * x[j] * std::sqrt(a[i] * a[j]);
+  }
+  Amix *= P / std::pow(Rg * T, 2);
+  Bmix *= P / (Rg * T);
+  // Z^3 + (Bmix - 1) Z^2 + (Amix - 3 Bmix^2 - 2 Bmix) Z - (Amix Bmix - Bmix^2 - Bmix^3) = 0
+  const double c3 = 1.0, c2 = Bmix - 1.0, c1 = Amix - 3.0 * std::pow(Bmix, 2) - 2.0 * Bmix, c0 = -(Amix * Bmix - std::pow(Bmix, 2) - std::pow(Bmix, 3));
+  std::vector<double> Z;
+  {
+    const double PI = 3.14159265358979323846, THIRD = 1.0 / 3.0;
+    const double W = c2 / c3 * THIRD;
+    double Pp = std::pow(c1 / c3 * THIRD - std::pow(W, 2), 3);
+    const double Q = -.5 * (2.0 * std::pow(W, 3) - (c1 * W - c0) / c3);
+    double DIS = std::pow(Q, 2) + Pp;
+    if(DIS < 0.0)
+    {
+      const double PHI = std::acos(std::max(-1.0, std::min(1.0, Q / std::sqrt(-Pp))));
+      Pp = 2.0 * std::pow((-Pp), 0.5 * THIRD);
+      for(int i = 0; i < 3; i++) Z.push_back(Pp * std::cos((PHI + 2.0 * (double) i * PI) * THIRD) - W);
+      std::sort(Z.begin(), Z.end());
+    }
+    else { DIS = std::sqrt(DIS); Z.push_back(std::cbrt(Q + DIS) + std::cbrt(Q - DIS) - W); }
+    for(double& z : Z) z = z - (c0 + z * (c1 + z * (c2 + z * c3))) / (c1 + z * (2.0 * c2 + z * 3.0 * c3));   // one Newton step
+  }
+  if(Z.size() == 3) std::sort(Z.begin(), Z.end(), [](double u, double v) { return u > v; });   // descending, :247-262
+  for(size_t i = 0; i < n; i++)
+  {
+    std::vector<double> phi(Z.size());
+    double sumAij = 0.0;
+    for(size_t k = 0; k < n; k++) sumAij += 2.0 * x[k] * std::sqrt(A[i] * A[k]);
+    for(size_t j = 0; j < Z.size(); j++)
+      phi[j] = std::exp((B[i] / Bmix) * (Z[j] - 1.0) - std::log(Z[j] - Bmix)
+                        - (Amix / (2.0 * std::sqrt(2.0) * Bmix)) * (sumAij / Amix - B[i] / Bmix) *
+                        std::log((Z[j] + (1.0 + std::sqrt(2.0)) * Bmix) / (Z[j] + (1.0 - std::sqrt(2.0)) * Bmix)));
+    double f = phi[0];
+    if(Z.size() == 3 && Z[2] > 0.0 && phi[0] > phi[2]) f = phi[2];                               // :309-330
+    d.comps[i].fugacity_coeff = f;
+  }
+}
+
 inline Deck load(const std::string& dir)
 {
   Deck d;
@@ -337,6 +406,7 @@ inline Deck load(const std::string& dir)
   const double kB = 1.380649e-23, mass_unit = 1.6605402e-27, length_unit = 1e-10, time_unit = 1e-12;
   d.beta = 1.0 / (kB / (mass_unit * std::pow(length_unit, 2) / std::pow(time_unit, 2)) * d.temperature);
   d.pressure = d.pressure_pa / (mass_unit / (length_unit * std::pow(time_unit, 2)));
+  compute_fugacity(d);
   return d;
 }
 

@@ -52,7 +52,8 @@ struct CompState
   // cumulative move probabilities, Move_Statistics::NormalizeProbabilities data_struct.h:569-608
   double cTrans = 0, cRot = 0, cSpecial = 0, cWidom = 0, cReins = 0, cIdentity = 0, cCBCF = 0, cSwap = 0, total_prob = 0;
   double max_trans[3] = {1, 1, 1}, max_rot[3] = {0, 0, 0};
-  MoveCount trans, rot, ins, del, reins, widom;
+  MoveCount trans, rot, ins, del, reins, widom, idswap_add, idswap_remove;
+  std::vector<MoveCount> idswap_to;             // IdentitySwap_Total_TO / _Acc_TO per destination component
   MoveCount trans_window, rot_window;           // TranslationTotal/Accepted are reset every 500 cycles
   long nmol = 0;
   bool has_charge = false;
@@ -491,6 +492,87 @@ void move_single_body(Sim& S, int comp, long mol, int move_type)   // SingleBody
   else trace_move(S, move_type == GB_TRANSLATION ? "translation" : "rotation", comp, mol, 0, 0.0);
 }
 
+// IdentitySwapMove, mc_swap_moves.h:199-431: a molecule of OLDComponent is regrown in place as a molecule of NEWComponent
+void move_identity_swap(Sim& S)
+{
+  long adsorbates = 0;
+  for(int c = 1; c < S.ncomp; c++) adsorbates += S.C[c].nmol;
+  if(adsorbates == 0) return;                                       // :217-221 (TotalNumberOfMolecules - NumberOfFrameworks == 0)
+  int oldc = 0, newc = 0; long nold = 0;
+  while(oldc == 0 || oldc >= S.ncomp || newc == 0 || newc >= S.ncomp || nold == 0)
+  {
+    oldc = (int) (size_t) (S.rng.uniform() * (double) (S.ncomp - 1)) + 1;
+    newc = (int) (size_t) (S.rng.uniform() * (double) (S.ncomp - 1)) + 1;
+    nold = S.C[oldc].nmol;
+  }
+  const long new_mol = S.C[newc].nmol;
+  const long old_mol = (long) (size_t) (S.rng.uniform() * (double) S.C[oldc].nmol);
+  CompState& XO = S.C[oldc]; CompState& XN = S.C[newc];
+  XO.idswap_remove.total++; XN.idswap_add.total++;
+  if(XO.idswap_to.empty()) XO.idswap_to.assign(S.ncomp, MoveCount());
+  XO.idswap_to[newc].total++;
+  const int ms_new = S.d.comps[newc - 1].ms(), ms_old = S.d.comps[oldc - 1].ms();
+  const double scale[2] = {1.0, 1.0};
+  gb_cbmc_result r; int32_t used = 0;
+  // ---- insertion leg: first bead preset to the old molecule's first atom, old molecule excluded (:260-296)
+  pool_check(S, 1);
+  GB(gb_cbmc_first_bead(S.e, GB_IDENTITY_SWAP_NEW, newc, new_mol, (int64_t) S.pool_off, 0.0, scale, 0.0, oldc, old_mol, nullptr, &r, &used));
+  pool_update(S, 1);
+  double Wn = r.rosenbluth;
+  if(!r.success || Wn <= 1e-150) { trace_move(S, "identity_swap", oldc, old_mol, 0, 0.0); return; }
+  Energy En; En.HGVDW = r.energy[0]; En.HGReal = r.energy[1]; En.GGVDW = r.energy[2]; En.GGReal = r.energy[3];
+  if(ms_new > 1)
+  {
+    pool_check(S, S.d.n_trial_orientations);
+    GB(gb_cbmc_chain(S.e, GB_IDENTITY_SWAP_NEW, newc, new_mol, (int64_t) S.pool_off, S.rng.peek(0), oldc, old_mol, &r, &used));
+    pool_update(S, S.d.n_trial_orientations);
+    S.rng.advance(used);
+    if(!r.success) { trace_move(S, "identity_swap", oldc, old_mol, 0, 0.0); return; }
+    Wn *= r.rosenbluth;
+    if(Wn <= 1e-150) { trace_move(S, "identity_swap", oldc, old_mol, 0, 0.0); return; }
+    En.HGVDW += r.energy[0]; En.HGReal += r.energy[1]; En.GGVDW += r.energy[2]; En.GGReal += r.energy[3];
+  }
+  GB(gb_reinsertion_store(S.e, newc));                               // StoreNewLocation_Reinsertion -> tempMolStorage (:299)
+  // ---- retrace leg (:336-351)
+  pool_check(S, 1);
+  GB(gb_cbmc_first_bead(S.e, GB_IDENTITY_SWAP_OLD, oldc, old_mol, (int64_t) S.pool_off, 0.0, scale, 0.0, -1, -1, nullptr, &r, &used));
+  pool_update(S, 1);
+  double Wo = r.rosenbluth;
+  Energy Eo; Eo.HGVDW = r.energy[0]; Eo.HGReal = r.energy[1]; Eo.GGVDW = r.energy[2]; Eo.GGReal = r.energy[3];
+  if(ms_old > 1)
+  {
+    pool_check(S, S.d.n_trial_orientations);
+    GB(gb_cbmc_chain(S.e, GB_IDENTITY_SWAP_OLD, oldc, old_mol, (int64_t) S.pool_off, 0.0, -1, -1, &r, &used));
+    pool_update(S, S.d.n_trial_orientations);
+    Wo *= r.rosenbluth;
+    Eo.HGVDW += r.energy[0]; Eo.HGReal += r.energy[1]; Eo.GGVDW += r.energy[2]; Eo.GGReal += r.energy[3];
+  }
+  Energy E = En; E.add(Eo, -1.0);
+  if(!S.d.no_charges)                                               // :354-360
+  {
+    double ew[2];
+    GB(gb_ewald_delta_identity_swap(S.e, oldc, newc, old_mol * ms_old, ew));
+    E.GGEwald = ew[0]; E.HGEwald = ew[1];
+    Wn *= std::exp(-S.d.beta * (ew[0] + ew[1]));
+  }
+  double tail = 0.0;
+  GB(gb_tail_identity_swap(S.e, newc, oldc, &tail));                 // :361-362
+  E.Tail = tail;
+  Wn *= std::exp(-S.d.beta * tail);
+  const double pre = prefactor(S, newc, true) * prefactor(S, oldc, false);
+  const double pacc = pre * (Wn / S.d.comps[newc - 1].ideal_rosenbluth) / (Wo / S.d.comps[oldc - 1].ideal_rosenbluth);
+  const double R = S.rng.uniform();
+  if(R < pacc)
+  {
+    GB(gb_accept_identity_swap(S.e, oldc, old_mol, newc));
+    XN.idswap_add.accepted++; XO.idswap_remove.accepted++; XO.idswap_to[newc].accepted++;
+    if(newc != oldc) { XN.nmol++; XO.nmol--; }
+    S.running.add(E);
+    trace_move(S, "identity_swap", oldc, old_mol, 1, E.total());
+  }
+  else trace_move(S, "identity_swap", oldc, old_mol, 0, 0.0);
+}
+
 // RunMoves, axpy.cu:102-298
 void run_move(Sim& S, long cycle)
 {
@@ -505,7 +587,7 @@ void run_move(Sim& S, long cycle)
   else if(R < X.cSpecial) { }
   else if(R < X.cWidom) move_widom(S, comp, cycle);
   else if(R < X.cReins) { if(X.nmol > 0) move_reinsertion(S, comp, mol); }
-  else if(R < X.cIdentity) { std::fprintf(stderr, "identity swap is not driven by this host program yet\n"); std::exit(2); }
+  else if(R < X.cIdentity) move_identity_swap(S);
   else if(R < X.cCBCF) { }
   else if(R < X.cSwap)
   {
@@ -718,9 +800,11 @@ int main(int argc, char** argv)
     {
       deck::Deck d = deck::load(argv[2]);
       std::printf("{\"framework_atoms\": %zu, \"components\": %zu, \"alpha\": %.9f, \"kmax\": [%d, %d, %d], \"volume\": %.6f, \"beta\": %.10f, "
-                  "\"init_cycles\": %ld, \"equil_cycles\": %ld, \"prod_cycles\": %ld, \"seed\": %ld}\n",
+                  "\"init_cycles\": %ld, \"equil_cycles\": %ld, \"prod_cycles\": %ld, \"seed\": %ld, \"fugacity_coeff\": [",
                   d.ftype.size(), d.comps.size(), d.alpha, d.kmax[0], d.kmax[1], d.kmax[2], d.volume, d.beta,
                   (long) d.init_cycles, (long) d.equil_cycles, (long) d.prod_cycles, (long) d.random_seed);
+      for(size_t c = 0; c < d.comps.size(); c++) std::printf("%s%.10f", c ? ", " : "", d.comps[c].fugacity_coeff);
+      std::printf("]}\n");
     }
     catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
     return 0;
@@ -791,6 +875,10 @@ int main(int argc, char** argv)
     std::printf("Component %d (%s): molecules %ld | translation %ld/%ld rotation %ld/%ld insertion %ld/%ld deletion %ld/%ld reinsertion %ld/%ld widom %ld\n",
                 c, S.d.comps[c - 1].name.c_str(), X.nmol, X.trans.accepted, X.trans.total, X.rot.accepted, X.rot.total, X.ins.accepted, X.ins.total,
                 X.del.accepted, X.del.total, X.reins.accepted, X.reins.total, X.widom.total);
+    if(X.idswap_add.total + X.idswap_remove.total > 0)
+      for(int t = 1; t < S.ncomp && !X.idswap_to.empty(); t++)
+        std::printf("Identity Swap Performed, FROM [%s (%d)] TO [%s (%d)]: %ld (%ld Accepted)\n", S.d.comps[c - 1].name.c_str(), c, S.d.comps[t - 1].name.c_str(), t,
+                    X.idswap_to[t].total, X.idswap_to[t].accepted);
     if(X.widom.total > 0) print_widom(S, c);
   }
   const long cycles = S.d.init_cycles + S.d.equil_cycles + S.d.prod_cycles;

@@ -160,7 +160,8 @@ int  gb_get_pseudo_atom_counts(gb_engine* e, int64_t* counts);
  * for CBMC_INSERTION / REINSERTION_INSERTION with >=1 survivor -- *uniform_used reports it);
  * scale = proposed_scale {vdw, coulomb}; stored_r = CBMC.StoredR (input for REINSERTION_RETRACE);
  * exclude_{comp,mol} = Sims.ExcludeList[0] (-1 for none).
- * For IDENTITY_SWAP_NEW the single trial position is preset_pos (copy_firstbead_to_new, mc_swap_moves.h:178-197). */
+ * For IDENTITY_SWAP_NEW the single trial position is preset_pos, or with preset_pos NULL the first atom of molecule
+ * exclude_mol of component exclude_comp read on the device (copy_firstbead_to_new, mc_swap_moves.h:178-181, :267). */
 int  gb_cbmc_first_bead(gb_engine* e, int32_t cbmc_type, int32_t component, int64_t molecule, int64_t pool_offset,
                         double uniform, const double scale[2], double stored_r, int32_t exclude_comp, int64_t exclude_mol,
                         const double* preset_pos, gb_cbmc_result* result, int32_t* uniform_used);
@@ -232,6 +233,8 @@ int  gb_single_body_delta_explicit(gb_engine* e, int32_t component, int64_t moli
 /* returns {same-type, 2*cross-type} exactly like the reference's double2, exclusion constants applied.
  * location = the reference's Location argument (selected trial for INSERTION, UpdateLocation for DELETION/REINSERTION). */
 int  gb_ewald_delta(gb_engine* e, int32_t component, int32_t move_type, int64_t location, const double scale[2], double out[2]);
+/* old molecule = slots [update_location, +molsize) of old_component; new molecule = tempMolStorage, i.e. the molecule kept by
+ * gb_reinsertion_store(new_component) after its IDENTITY_SWAP_NEW growth (mc_swap_moves.h:355) */
 int  gb_ewald_delta_identity_swap(gb_engine* e, int32_t old_component, int32_t new_component, int64_t update_location, double out[2]);
 /* explicit atoms: n_old old atoms followed by n_new new atoms (Sims.Old layout) */
 int  gb_ewald_delta_explicit(gb_engine* e, int32_t component_is_framework, int32_t n_old, int32_t n_new, const double* pos,
@@ -254,6 +257,10 @@ int  gb_accept_translation(gb_engine* e, int32_t component);          /* commits
 int  gb_accept_insertion(gb_engine* e, int32_t component);            /* commits the molecule grown by the last CBMC insertion (+ Ewald swap) */
 int  gb_accept_deletion(gb_engine* e, int32_t component, int64_t molecule);
 int  gb_accept_reinsertion(gb_engine* e, int32_t component, int64_t molecule);
+/* IdentitySwapMove accept branch (mc_swap_moves.h:393-422: Update_deletion_data + Update_IdentitySwap_Insertion_data +
+ * Update_NumberOfMolecules x2, or Update_Reinsertion_data when both species are the same; + Update_Vector_Ewald).
+ * The new molecule is the one stored by gb_reinsertion_store(new_component) after its IDENTITY_SWAP_NEW growth. */
+int  gb_accept_identity_swap(gb_engine* e, int32_t old_component, int64_t old_molecule, int32_t new_component);
 /* append a caller-supplied molecule (restart ingestion, CreateMolecule) */
 int  gb_append_molecule(gb_engine* e, int32_t component, const double* pos, const double* scale, const double* charge,
                         const double* scale_coul, const uint64_t* type);

@@ -338,3 +338,83 @@ def test_one_kernel_moves_match_the_stage_calls(gpu_engine_factory):
         if not ov:
             assert _same(m["ewald"], ew, tol=1e-10)
     eng.close()
+
+
+def _totals(eng):
+    v = eng.total_vdw_real(); w = eng.total_ewald(store=False)
+    return (v["HHVDW"] + v["HGVDW"] + v["GGVDW"] + v["HHReal"] + v["HGReal"] + v["GGReal"]
+            + w["HHEwaldE"] + w["HGEwaldE"] + w["GGEwaldE"] + eng.tail_total())
+
+
+def test_identity_swap_stages_and_commit(gpu_engine_factory, oracle):
+    """IdentitySwapMove (mc_swap_moves.h:199-431) on the Xe/Kr mixture (config D, no charges): IDENTITY_SWAP_NEW first
+    bead at the old molecule's position with the old molecule excluded, IDENTITY_SWAP_OLD retrace, tail difference,
+    then the commit: total energy recomputed from scratch must move by exactly the reported delta."""
+    from graspa_b200.types import IDENTITY_SWAP_NEW, IDENTITY_SWAP_OLD, species_counts, pseudo_atom_counts
+    box, ff, s, z, eng = _setup(gpu_engine_factory, "D", grow=None)
+    beta = float(z["beta"])
+    pool = np.random.default_rng(5).random((64, 3)); eng.upload_random_pool(pool)
+    E0 = _totals(eng)
+    running = 0.0
+    nmol = {1: int(s.natoms[1]), 2: int(s.natoms[2])}
+    cur = s
+    for step, (oldc, newc, mol) in enumerate([(1, 2, 3), (2, 1, 0), (2, 2, 5), (1, 2, nmol[1] - 2)]):
+        o = int(cur.offsets[oldc])
+        old_pos = eng.download_atoms(oldc)["pos"][mol] if hasattr(eng, "download_atoms") else cur.pos[o + mol]
+        fb = eng.cbmc_first_bead(IDENTITY_SWAP_NEW, newc, nmol[newc], step, 0.5, excl_comp=oldc, excl_mol=mol)
+        assert fb["success"] and fb["uniform_used"] == 0 and fb["selected"] == 0
+        assert np.allclose(fb["selected_pos"], old_pos, atol=0, rtol=0)
+        eng.reinsertion_store(newc)
+        rb = eng.cbmc_first_bead(IDENTITY_SWAP_OLD, oldc, mol, step, 0.5)
+        assert rb["success"] and rb["selected"] == 0
+        tail = eng.tail_identity_swap(newc, oldc)
+        if step == 0:
+            # oracle: one trial atom of the NEW species at the old position against the system minus the old molecule
+            tr = TrialAtoms(np.array([old_pos]), np.array([cur.charge[int(cur.offsets[newc])]]), np.array([cur.type[int(cur.offsets[newc])]]))
+            e, f, _ = oracle.trial_energies(box, ff, cur, 1, 1, tr, newc, nmol[newc], excl_comp=oldc, excl_mol=mol)
+            assert _close(fb["energy"], e[0]) and abs(fb["rosenbluth"] - np.exp(-beta * e[0].sum())) <= 1e-9 * fb["rosenbluth"]
+            tr_o = TrialAtoms(np.array([old_pos]), np.array([cur.charge[o]]), np.array([cur.type[o]]))
+            eo, fo, _ = oracle.trial_energies(box, ff, cur, 1, 1, tr_o, oldc, mol)
+            assert _close(rb["energy"], eo[0]) and abs(rb["rosenbluth"] - np.exp(-beta * eo[0].sum())) <= 1e-9 * rb["rosenbluth"]
+            npseudo = pseudo_atom_counts(cur, ff.ntypes)
+            t_ref = oracle.tail_identity_swap(ff, npseudo, box.volume, species_counts(cur, newc, ff.ntypes), species_counts(cur, oldc, ff.ntypes))
+            assert abs(tail - t_ref) <= 1e-12 * max(1.0, abs(t_ref))
+        delta = float(np.sum(fb["energy"]) - np.sum(rb["energy"]) + tail)
+        eng.accept_identity_swap(oldc, mol, newc)
+        if newc != oldc:
+            nmol[newc] += 1; nmol[oldc] -= 1
+        assert eng.number_of_molecules(newc) == nmol[newc] and eng.number_of_molecules(oldc) == nmol[oldc]
+        running += delta
+        E1 = _totals(eng)
+        assert abs((E1 - E0) - running) <= 1e-9 * max(1.0, abs(E1)), (step, E1 - E0, running)
+    eng.close()
+
+
+def test_identity_swap_same_species_with_charges(gpu_engine_factory, oracle):
+    """CO2 -> CO2 identity swap in CO2-MFI (config B): chain growth with the old molecule excluded, Ewald delta of
+    GPU_EwaldDifference_IdentitySwap (old molecule out, stored new molecule in), commit, energy drift."""
+    from graspa_b200.types import IDENTITY_SWAP_NEW, IDENTITY_SWAP_OLD
+    box, ff, s, z, eng = _setup(gpu_engine_factory, "B")
+    comp = 1; ms = 3; mol = 4
+    pool = np.random.default_rng(6).random((64, 3)); eng.upload_random_pool(pool)
+    eng.total_ewald(store=True)
+    E0 = _totals(eng)
+    o = int(s.offsets[comp]); nm = int(s.natoms[comp]) // ms
+    fb = eng.cbmc_first_bead(IDENTITY_SWAP_NEW, comp, nm, 0, 0.5, excl_comp=comp, excl_mol=mol)
+    assert fb["success"] and np.array_equal(fb["selected_pos"], s.pos[o + mol * ms])
+    ch = eng.cbmc_chain(IDENTITY_SWAP_NEW, comp, nm, 1, 0.41, excl_comp=comp, excl_mol=mol)
+    assert ch["success"] and ch["uniform_used"] == 1
+    new_pos = eng.cbmc_grown_positions(comp)
+    eng.reinsertion_store(comp)
+    rb = eng.cbmc_first_bead(IDENTITY_SWAP_OLD, comp, mol, 11, 0.5)
+    rc = eng.cbmc_chain(IDENTITY_SWAP_OLD, comp, mol, 12, 0.5)
+    ew = eng.ewald_delta_identity_swap(comp, comp, mol * ms)
+    q = s.charge[o:o + ms]
+    pos = np.concatenate([s.pos[o + mol * ms:o + mol * ms + ms], new_pos])
+    ref, _, _ = oracle.ewald_delta(box, pos, np.concatenate([q, q]), np.ones(2 * ms), ms, ms, z["sf_ads"], z["sf_fw"])
+    assert _close(ew, ref, scale=max(1.0, float(np.abs(ref).max())))       # the two exclusion constants cancel (same species)
+    delta = float(np.sum(fb["energy"]) + np.sum(ch["energy"]) - np.sum(rb["energy"]) - np.sum(rc["energy"]) + ew[0] + ew[1])
+    eng.accept_identity_swap(comp, mol, comp)
+    E1 = _totals(eng)
+    assert abs((E1 - E0) - delta) <= 1e-9 * max(1.0, abs(E1)), (E1 - E0, delta)
+    eng.close()
