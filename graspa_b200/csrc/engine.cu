@@ -48,6 +48,7 @@ struct Comp
   int offset = 0, alloc = 0, molsize = 0, natoms = 0;
   bool uploaded = false;
   double excl_intra = 0.0, excl_atom = 0.0; int rigid = 1, has_charge = 0;
+  double* d_pocket = nullptr; int npocket = 0, pocket_invert = 0;      // block pockets: npocket x {x, y, z, radius} on the device
 };
 
 } // namespace
@@ -456,6 +457,7 @@ int gb_engine_destroy(gb_engine* e)
   e->d_ktab.release(); e->d_pool.release(); e->d_rec.release(); e->d_out8.release(); e->d_partial.release(); e->d_sums.release();
   e->d_uni.release(); e->d_scratch.release(); e->d_result.release(); e->d_stage.release(); e->d_iscratch.release();
   e->d_idx0.release(); e->d_idx1.release(); e->d_ticket.release(); e->d_mv.release(); e->d_mvi.release(); e->d_ewpos.release();
+  for(auto& C : e->comps) if(C.d_pocket) cudaFree(C.d_pocket);
   if(e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
   cudaStreamDestroy(e->stream);
@@ -694,6 +696,27 @@ int gb_set_exclusion_constants(gb_engine* e, int32_t c, double intra, double ato
 {
   if(!e || c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "bad component");
   e->comps[c].excl_intra = intra; e->comps[c].excl_atom = atom; e->comps[c].rigid = rigid; e->comps[c].has_charge = has_charge;
+  return GB_OK;
+}
+
+// ReadBlockingPockets / ReplicateBlockPockets (read_data.cpp:3290-3454) leave Cartesian centres and radii per component;
+// BlockedPocket (:3466-3640) tests trial positions against them on the host.  Here the list lives on the device and the
+// move kernels run the test themselves (first-bead trials, grown molecules, translation / rotation proposals).
+int gb_set_block_pockets(gb_engine* e, int32_t c, int32_t n, const double* centers, const double* radii, int32_t invert)
+{
+  if(!e || c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "bad component");
+  if(n < 0 || (n > 0 && (!centers || !radii))) return fail(GB_ERR_ARG, "bad block-pocket list");
+  CUDA_TRY(cudaSetDevice(e->device));
+  Comp& C = e->comps[c];
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if(C.d_pocket) { cudaFree(C.d_pocket); C.d_pocket = nullptr; }
+  C.npocket = 0; C.pocket_invert = invert ? 1 : 0;
+  if(n == 0) return GB_OK;
+  std::vector<double> h((size_t) 4 * n);
+  for(int i = 0; i < n; i++) { h[4 * i] = centers[3 * i]; h[4 * i + 1] = centers[3 * i + 1]; h[4 * i + 2] = centers[3 * i + 2]; h[4 * i + 3] = radii[i]; }
+  CUDA_TRY(cudaMalloc(&C.d_pocket, h.size() * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(C.d_pocket, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  C.npocket = n;
   return GB_OK;
 }
 
@@ -1010,6 +1033,7 @@ int gb_widom_first_bead_success(gb_engine* e, int32_t comp, int64_t n, const dou
   if(n <= 0 || !pool3 || !fb_index || !code) return fail(GB_ERR_ARG, "bad arguments");
   if(comp < e->nhost || comp >= e->ncomp) return fail(GB_ERR_ARG, "Widom component must be an adsorbate component");
   if(!e->have_cbmc) return fail(GB_ERR_STATE, "gb_set_cbmc has not been called");
+  if(e->comps[comp].npocket > 0) return fail(GB_ERR_UNIMPLEMENTED, "block pockets are applied by the single-move path, not by the batched Widom kernel");
   CUDA_TRY(e->d_pool.reserve((size_t) n_pool * 3));
   CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, pool3, (size_t) n_pool * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   e->n_pool = n_pool;
@@ -1029,6 +1053,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   if(comp < e->nhost || comp >= e->ncomp) return fail(GB_ERR_ARG, "Widom component must be an adsorbate component");
   if(!e->have_cbmc) return fail(GB_ERR_STATE, "gb_set_cbmc has not been called");
   const Comp& C = e->comps[comp];
+  if(C.npocket > 0) return fail(GB_ERR_UNIMPLEMENTED, "block pockets are applied by the single-move path (gb_move_insertion / stage calls), not by the batched Widom kernel");
   const int ms = C.molsize, cs = ms - 1;
   if(cs > GBK_MAX_CS) return fail(GB_ERR_ARG, "molecule too large for the CBMC chain stage");
   const bool do_ewald = !e->P.no_charges && C.has_charge && e->nact > 0;

@@ -86,6 +86,7 @@ struct FusedSmem
   SmemMol mN, mO;                                           // molecule being grown / proposed, and its old image
   SmemMol tmpl, exist;                                      // template molecule (slot 0 of the component) and the selected molecule
   double pool[3 * (2 * 32 + 2 * 32 + 1)];                   // the random-pool entries this move consumes
+  int blocked;                                              // block-pocket flag of the trial group being evaluated
 };
 
 // one segment of a stage: n trial groups of one CBMC type
@@ -166,6 +167,7 @@ __device__ __forceinline__ void group_energy(const DevParams& P, const PairTable
   {
     double s = 0.0;
     for(int w = 0; w < nwarps; w++) s += sm->red[w * 8 + threadIdx.x];
+    if(threadIdx.x == 6 && sm->blocked) s += 1.0;                       // block pockets flag the trial like an overlap
     ll_store(rec, threadIdx.x, s, tag);
   }
 }
@@ -184,11 +186,32 @@ __device__ __forceinline__ void run_stage(const DevParams& P, const SysView& S, 
     const int type = segs[si].type; const bool chain = segs[si].chain != 0; const long long off = segs[si].pool_off;
     const int cs = chain ? F.ms - 1 : 1;
     __syncthreads();
-    if(!chain) { if(threadIdx.x == 0) set_trial(sm->T, 0, first_bead_atom(P, F, sm, type, g, off)); }
-    else if((int) threadIdx.x < cs)
+    if(!chain)
     {
-      double ax, ay, az, sc, scc; chain_anchor(F, sm, type, ax, ay, az, sc, scc);
-      set_trial(sm->T, threadIdx.x, chain_atom(P, F, sm, type, g, threadIdx.x, off, ax, ay, az, sc, scc));
+      if(threadIdx.x == 0)
+      {
+        const AtomRec fb = first_bead_atom(P, F, sm, type, g, off);
+        set_trial(sm->T, 0, fb);
+        // block pockets, mc_widom.h:445-497: growth types; a blocked starting bead (trial 0) flags every trial
+        int blk = 0;
+        if((type == 0 || type == 2 || type == 4) && F.C.npocket > 0)
+        {
+          AtomRec f0 = fb;
+          if(g > 0) f0 = first_bead_atom(P, F, sm, type, 0, off);
+          blk = blocked_pocket(P, F.C, f0.x, f0.y, f0.z) ? 1 : 0;
+          if(!blk && g > 0) blk = blocked_pocket(P, F.C, fb.x, fb.y, fb.z) ? 1 : 0;
+        }
+        sm->blocked = blk;
+      }
+    }
+    else
+    {
+      if((int) threadIdx.x < cs)
+      {
+        double ax, ay, az, sc, scc; chain_anchor(F, sm, type, ax, ay, az, sc, scc);
+        set_trial(sm->T, threadIdx.x, chain_atom(P, F, sm, type, g, threadIdx.x, off, ax, ay, az, sc, scc));
+      }
+      if(threadIdx.x == 0) sm->blocked = 0;
     }
     __syncthreads();
     const int new_molid = (type == 0 || type == 4) ? F.nmol : (int) F.molecule;
@@ -284,6 +307,19 @@ __device__ __forceinline__ void adopt_selection(const DevParams& P, const FusedA
     }
   }
   __syncthreads();
+  // block pockets: every atom of the grown molecule is tested after the chain growth of an insertion / reinsertion
+  // (mc_swap_utilities.h:35-78, move_struct.h:208-250); a blocked atom fails the construction, the selection's random
+  // number stays consumed.  Every CTA takes the same decision from the same shared-memory molecule.
+  if(have && chain && (type == 0 || type == 2 || type == 4) && F.C.npocket > 0)
+  {
+    if(threadIdx.x == 0)
+    {
+      bool blk = false;
+      for(int a = 0; a < F.ms && !blk; a++) blk = blocked_pocket(P, F.C, sm->mN.a[0][a], sm->mN.a[1][a], sm->mN.a[2][a]);
+      if(blk) { r[0] = 0.0; r[9] = 0.0; r[13] = 0.0; r[14] = 0.0; }
+    }
+    __syncthreads();
+  }
   GBK_MARK();
 }
 
@@ -450,6 +486,16 @@ k_move(DevParams P, SysView S, FusedArgs F)
   {
     for(int i = threadIdx.x - 32; i < (GBK_ERFC_DEG + 1) * GBK_ERFC_NINT; i += blockDim.x - 32) sm.etab[i] = __ldg(&P.erfc_tab[i]);
     if(threadIdx.x - 32 < 128) sm.res[threadIdx.x - 32] = 0.0;
+  }
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    // translation / rotation: a block pocket containing any atom of the proposal counts as an overlap
+    // (SingleBody_Prepare, mc_single_particle.h:83-119); the CBMC kinds set the flag per trial group in run_stage
+    int blk = 0;
+    if(F.kind == GBF_SINGLE && F.C.npocket > 0)
+      for(int a = 0; a < ms && !blk; a++) blk = blocked_pocket(P, F.C, sm.mN.a[0][a], sm.mN.a[1][a], sm.mN.a[2][a]) ? 1 : 0;
+    sm.blocked = blk;
   }
   __syncthreads();
   GBK_MARK();

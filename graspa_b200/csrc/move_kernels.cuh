@@ -35,7 +35,38 @@ struct CompView
   const double* __restrict__ x; const double* __restrict__ y; const double* __restrict__ z;
   const double* __restrict__ q; const double* __restrict__ scale; const double* __restrict__ scoul;
   const int* __restrict__ type;
+  // block pockets of the component (gb_set_block_pockets): npocket x {x, y, z, radius}, Cartesian centres
+  const double* __restrict__ pocket; int npocket, pocket_invert;
 };
+
+// BlockedPocket, read_data.cpp:3466-3640 (RASPA-2's rule): a point is blocked when it lies inside any block-pocket sphere
+// (InvertBlockPockets: when it lies outside all of them).  The difference centre - point goes through the same
+// truncating nearest-image round as the reference's apply_pbc_raspa2 lambda.
+__device__ __forceinline__ bool blocked_pocket(const DevParams& P, const CompView& C, double x, double y, double z)
+{
+  if(C.npocket <= 0) return false;
+  for(int i = 0; i < C.npocket; i++)
+  {
+    double dx = C.pocket[4 * i] - x, dy = C.pocket[4 * i + 1] - y, dz = C.pocket[4 * i + 2] - z;
+    if(P.cubic)
+    {
+      dx -= P.cell[0] * (double) static_cast<int>(dx / P.cell[0] + ((dx >= 0.0) ? 0.5 : -0.5));
+      dy -= P.cell[4] * (double) static_cast<int>(dy / P.cell[4] + ((dy >= 0.0) ? 0.5 : -0.5));
+      dz -= P.cell[8] * (double) static_cast<int>(dz / P.cell[8] + ((dz >= 0.0) ? 0.5 : -0.5));
+    }
+    else
+    {
+      const double sx = P.inv[0] * dx + P.inv[3] * dy + P.inv[6] * dz, sy = P.inv[1] * dx + P.inv[4] * dy + P.inv[7] * dz, sz = P.inv[2] * dx + P.inv[5] * dy + P.inv[8] * dz;
+      const double tx = sx - (double) static_cast<int>(sx + ((sx >= 0.0) ? 0.5 : -0.5));
+      const double ty = sy - (double) static_cast<int>(sy + ((sy >= 0.0) ? 0.5 : -0.5));
+      const double tz = sz - (double) static_cast<int>(sz + ((sz >= 0.0) ? 0.5 : -0.5));
+      dx = P.cell[0] * tx + P.cell[3] * ty + P.cell[6] * tz; dy = P.cell[1] * tx + P.cell[4] * ty + P.cell[7] * tz; dz = P.cell[2] * tx + P.cell[5] * ty + P.cell[8] * tz;
+    }
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    if(r < C.pocket[4 * i + 3]) return C.pocket_invert == 0;
+  }
+  return C.pocket_invert != 0;
+}
 
 struct CbmcArgs
 {
@@ -150,6 +181,7 @@ k_cbmc_first_bead(DevParams P, SysView S, SegList L, CbmcArgs A, int nsplit)
   __shared__ double red[8 * 8];
   __shared__ double etab[(GBK_ERFC_DEG + 1) * GBK_ERFC_NINT];
   __shared__ bool last;
+  __shared__ int blocked_s;
   if(A.dep_slot >= 0 && A.B.result(A.dep_slot)[13] == 0.0)
   {
     // the stage this one depends on failed (or left a Rosenbluth weight <= 1e-150): report failure, consume nothing
@@ -179,10 +211,22 @@ k_cbmc_first_bead(DevParams P, SysView S, SegList L, CbmcArgs A, int nsplit)
       A.B.tr(6)[t] = q; A.B.tr(7)[t] = scale; A.B.tr(8)[t] = scoul; A.B.tr_type()[t] = type;
     }
     T.fx[0] = fx; T.fy[0] = fy; T.fz[0] = fz; T.q[0] = q * scoul; T.scale[0] = scale; T.type[0] = type; T.slot[0] = 0;
+    // block pockets, mc_widom.h:445-497: growth types only; a blocked STARTING bead (trial 0) flags every trial,
+    // otherwise each trial is flagged on its own
+    int blk = 0;
+    if((ty == 0 || ty == 2 || ty == 4) && A.C.npocket > 0)
+    {
+      double x0 = x, y0 = y, z0 = z;
+      if(t > 0) { const double* r0 = A.pool3 + 3 * A.pool_off; x0 = P.cell[0] * r0[0]; y0 = P.cell[4] * r0[1]; z0 = P.cell[8] * r0[2]; }
+      blk = blocked_pocket(P, A.C, x0, y0, z0) ? 1 : 0;
+      if(!blk && t > 0) blk = blocked_pocket(P, A.C, x, y, z) ? 1 : 0;
+    }
+    blocked_s = blk;
   }
   __syncthreads();
   PairTables W; W.etab = etab; W.ffp = P.ffA; W.unit = false;
   cbmc_group_energy<1>(P, W, S, L, A, &T, Q, red, 1, t, split, nsplit);
+  if(threadIdx.x == 6 && blocked_s) A.B.partial()[(size_t)(t * nsplit + split) * 8 + 6] = 1.0;   // same thread that stored the overlap flag
   __syncthreads();
   if(threadIdx.x == 0) { __threadfence(); last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1); }
   __syncthreads();
@@ -273,6 +317,16 @@ k_cbmc_chain(DevParams P, SysView S, SegList L, CbmcArgs A, int nsplit)
       r[14] = (A.dep_slot >= 0 ? A.B.result(A.dep_slot)[14] : 1.0) * r[0];   // CBMC.Rosenbluth *= averagedRosen, mc_widom.h:611
       r[13] = (r[9] != 0.0 && r[14] > 1e-150) ? 1.0 : 0.0;                  // mc_swap_utilities.h:32
       sel_s = (r[9] != 0.0 && r[11] > 0.0) ? (int) r[10] : -1;
+      // block pockets: after the chain growth of an insertion / reinsertion / identity swap EVERY atom of the grown
+      // molecule is tested (mc_swap_utilities.h:35-78, move_struct.h:208-250, mc_swap_moves.h:299-330); a blocked atom
+      // fails the construction (Rosenbluth 0) -- the selection's random number stays consumed
+      const int ty = A.cbmc_type;
+      if(sel_s >= 0 && (ty == 0 || ty == 2 || ty == 4) && A.C.npocket > 0)
+      {
+        bool blk = blocked_pocket(P, A.C, A.B.mol(GBK_BUF_GROWN, 0)[0], A.B.mol(GBK_BUF_GROWN, 1)[0], A.B.mol(GBK_BUF_GROWN, 2)[0]);
+        for(int a = 0; a < cs && !blk; a++) { const int j = sel_s * cs + a; blk = blocked_pocket(P, A.C, A.B.tr(0)[j], A.B.tr(1)[j], A.B.tr(2)[j]); }
+        if(blk) { r[0] = 0.0; r[9] = 0.0; r[13] = 0.0; r[14] = 0.0; sel_s = -1; }
+      }
       *A.ticket = 0u;
     }
   }
@@ -366,14 +420,20 @@ __device__ __forceinline__ void propose_atom(const DevParams& P, const ProposeAr
   od.x = x; od.y = y; od.z = z; to_frac(P, x, y, z, od.fx, od.fy, od.fz);
 }
 
+// result(6)[0] = 1 when a block pocket contains an atom of the proposal: the move is then treated as an overlap
+// (SingleBody_Prepare sets device_flag and returns early, mc_single_particle.h:83-119)
 __global__ void k_single_propose(DevParams P, ProposeArgs A)
 {
+  bool blk = false;
   if((int) threadIdx.x < A.ms)
   {
     AtomRec nw, od;
     propose_atom(P, A, threadIdx.x, nw, od);
     store_atom(A.B, GBK_BUF_NEW, threadIdx.x, nw); store_atom(A.B, GBK_BUF_OLD, threadIdx.x, od);
+    if(A.move_type != 3) blk = blocked_pocket(P, A.C, nw.x, nw.y, nw.z);          // Do_New moves only
   }
+  const int any = __syncthreads_or(blk ? 1 : 0);
+  if(threadIdx.x == 0) A.B.result(6)[0] = any ? 1.0 : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -439,6 +499,7 @@ k_single_body(DevParams P, SysView S, SegList L, SingleBodyArgs A)
     }
     double fl = 0.0;
     for(unsigned int b = 0; b < gridDim.x; b++) fl += p[b * 16 + 6];     // overlap of the NEW configuration only (:768-769)
+    if(A.do_new && A.B.result(6)[0] != 0.0) fl += 1.0;                   // blocked by a block pocket (k_single_propose)
     r[6] = fl > 0.0 ? 1.0 : 0.0;
     r[7] = 1.0 - r[6];                                                   // "no overlap": dependency flag of the Ewald stage
     *A.ticket = 0u;

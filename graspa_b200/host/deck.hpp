@@ -52,6 +52,9 @@ struct Component
   double p_translation = 0, p_rotation = 0, p_widom = 0, p_reinsertion = 0, p_identity = 0, p_swap = 0;   // raw inputs
   int create_molecules = 0;
   bool use_pr_eos = false;
+  // block pockets (BlockPockets yes / BlockPocketsFilename X / InvertBlockPockets, read_data.cpp:2532-2575)
+  bool use_pockets = false, invert_pockets = false; std::string pocket_file;
+  std::vector<double> pocket_centers, pocket_radii;           // replicated, Cartesian (ReplicateBlockPockets :3362-3454)
   // molecule definition
   std::vector<double> pos;      // 3*ms
   std::vector<int> type; std::vector<double> charge;
@@ -74,6 +77,16 @@ struct Deck
   bool lammps_ewald = false; double lammps_alpha = 0.0; int lammps_kmax[3] = {0, 0, 0};
   long movies_every = 5000, print_every = 5000;
   std::vector<Component> comps;                                     // adsorbates, in input order
+  // SeparateFrameworkComponents: framework components 1.. (Framework_Component_<i>.def + the Framework_Component_ blocks
+  // of simulation.input, read_data.cpp:530-607, 1860-1930); component 0 keeps every atom not listed there
+  struct FrameworkComponent
+  {
+    std::string name; int nmol = 0, molsize = 0; std::vector<int> atom_index;      // unit-cell atom indices, molecule-major
+    double p_translation = 0, p_rotation = 0, p_special = 0, p_reinsertion = 0;
+    std::vector<double> pos; std::vector<int> type; std::vector<double> charge; std::vector<int> molid;   // supercell atoms
+  };
+  bool separate_framework = false; int n_framework_components = 1;
+  std::vector<FrameworkComponent> fw;                               // fw[i - 1] = framework component i
   // force field
   std::vector<std::string> names; std::vector<double> eps_in, sig_in, mass, pseudo_charge;
   bool shifted = false, tail = false;
@@ -114,11 +127,29 @@ inline void read_simulation_input(Deck& d, const std::string& dir)
 {
   auto L = read_lines(dir + "/simulation.input");
   Component* cur = nullptr;
+  int fw_block = 0;
   for(auto& line : L)
   {
     auto t = terms(line);
     if(t.empty() || t[0][0] == '#') continue;
     auto has = [&](const char* k) { return line.find(k) != std::string::npos; };      // the reference matches by substring
+    // ReadFrameworkComponentMoves, read_data.cpp:530-607
+    if(has("END_OF_Framework_Component_")) { fw_block = 0; continue; }
+    if(t[0] == "Framework_Component_" && t.size() >= 2)
+    {
+      fw_block = std::stoi(t[1]);
+      if(fw_block >= 1 && (int) d.fw.size() < fw_block) d.fw.resize(fw_block);
+      continue;
+    }
+    if(fw_block >= 1)
+    {
+      Deck::FrameworkComponent& F = d.fw[fw_block - 1];
+      if(has("TranslationProbability")) F.p_translation = std::stod(t[1]);
+      if(has("RotationProbability")) F.p_rotation = std::stod(t[1]);
+      if(has("RotationSpecialProbability")) F.p_special = std::stod(t[1]);
+      if(has("ReinsertionProbability")) F.p_reinsertion = std::stod(t[1]);
+      continue;
+    }
     if(t[0] == "Component" && t.size() >= 4) { d.comps.emplace_back(); cur = &d.comps.back(); cur->name = t[3]; continue; }
     if(cur)
     {
@@ -132,11 +163,16 @@ inline void read_simulation_input(Deck& d, const std::string& dir)
       else if(has("FugacityCoefficient")) { if(ieq(t[1], "PR-EOS")) { cur->use_pr_eos = true; cur->fugacity_coeff = -1.0; } else cur->fugacity_coeff = std::stod(t[1]); }
       else if(has("MolFraction")) cur->mol_fraction = std::stod(t[1]);
       else if(has("CreateNumberOfMolecules")) cur->create_molecules = std::stoi(t[1]);
+      else if(has("BlockPocketsFilename")) cur->pocket_file = t[1] + ".block";
+      else if(has("InvertBlockPockets")) cur->invert_pockets = ieq(t[1], "yes");
+      else if(has("BlockPockets")) { if(ieq(t[1], "yes")) cur->use_pockets = true; }
       continue;
     }
     if(has("NumberOfInitializationCycles")) d.init_cycles = std::stol(t[1]);
     else if(has("NumberOfEquilibrationCycles")) d.equil_cycles = std::stol(t[1]);
     else if(has("NumberOfProductionCycles")) d.prod_cycles = std::stol(t[1]);
+    else if(has("SeparateFrameworkComponents")) d.separate_framework = ieq(t[1], "yes");
+    else if(has("NumberofFrameworkComponents")) d.n_framework_components = std::stoi(t[1]);
     else if(has("UseMaxStep")) d.use_max_step = ieq(t[1], "yes");
     else if(has("MaxStepPerCycle")) d.max_step_per_cycle = std::stol(t[1]);
     else if(has("RandomSeed")) d.random_seed = std::stoi(t[1]);
@@ -195,6 +231,25 @@ inline void read_force_field(Deck& d, const std::string& dir)
   if(ffdef)
   {
     auto F = read_lines(dir + "/force_field.def");
+    // OverWrite_Mixing_Rule, read_data.cpp:924-1130: "<I> <J> lennard-jones <eps> <sig>" lines under the FIRST
+    // "mixing rules to overwrite" marker replace the mixed pair parameters (and the shift)
+    {
+      size_t start = 0, nmix = 0;
+      for(size_t k = 0; k < F.size(); k++)
+      {
+        if(F[k].find("mixing rules to overwrite") != std::string::npos && start == 0) start = k;
+        if(start > 0 && k == start + 1) { auto t = terms(F[k]); if(!t.empty()) nmix = (size_t) std::stol(t[0]); }
+      }
+      for(size_t k = start + 3; nmix > 0 && k < start + 3 + nmix && k < F.size(); k++)
+      {
+        auto t = terms(F[k]);
+        if(t.size() != 5) continue;
+        const int i = type_of(d, t[0]), j = type_of(d, t[1]);
+        const double e = std::stod(t[3]) / 1.20272430057, sg = std::stod(t[4]);
+        d.eps[i * n + j] = d.eps[j * n + i] = e; d.sigma[i * n + j] = d.sigma[j * n + i] = sg;
+        if(d.shifted) d.shift[i * n + j] = d.shift[j * n + i] = lj_energy(e, sg, cutsq);
+      }
+    }
     if(F.size() > 1)
     {
       const int nover = std::stoi(terms(F.at(1)).at(0));
@@ -290,16 +345,101 @@ inline void read_framework(Deck& d, const std::string& dir)
     uq.push_back((d.use_cif_charges && col[4] >= 0) ? std::stod(t[col[4]]) : d.pseudo_charge[ty]);
     d.framework_mass += d.mass[ty];
   }
+  // DetermineFrameworkComponent + CheckFrameworkComponentAtomOrder (read_data.cpp:1398-1478): unit-cell atoms listed in
+  // Framework_Component_<i>.def leave component 0 and are kept in the order of that file (molecule-major)
+  std::vector<int> owner(ut.size(), 0);
+  for(size_t f = 0; f < d.fw.size(); f++)
+  {
+    // an index that no CIF atom carries never matches in DetermineFrameworkComponent (the NaX example lists one): drop it
+    std::vector<int> kept;
+    for(int idx : d.fw[f].atom_index) if(idx >= 0 && idx < (int) ut.size()) { owner[idx] = (int) f + 1; kept.push_back(idx); }
+    d.fw[f].atom_index = kept;
+    if((int) kept.size() != d.fw[f].nmol * d.fw[f].molsize)
+      throw std::runtime_error("In CheckFrameworkCIF function, NMol and value in FrameworkComponentDef don't match!!!!");
+  }
   const double sx = (double) 1 / nx, sy = (double) 1 / ny, sz = (double) 1 / nz;
+  auto place = [&](size_t A, int ix, int jy, int kz, std::vector<double>& pos) {
+    const double fx = (uf[3 * A] + ix) * sx, fy = (uf[3 * A + 1] + jy) * sy, fz = (uf[3 * A + 2] + kz) * sz;
+    pos.push_back(fx * d.cell[0] + fy * d.cell[3] + fz * d.cell[6]);
+    pos.push_back(fx * d.cell[1] + fy * d.cell[4] + fz * d.cell[7]);
+    pos.push_back(fx * d.cell[2] + fy * d.cell[5] + fz * d.cell[8]);
+  };
   for(int ix = 0; ix < nx; ix++) for(int jy = 0; jy < ny; jy++) for(int kz = 0; kz < nz; kz++)
     for(size_t A = 0; A < ut.size(); A++)
     {
-      const double fx = (uf[3 * A] + ix) * sx, fy = (uf[3 * A + 1] + jy) * sy, fz = (uf[3 * A + 2] + kz) * sz;
-      d.fpos.push_back(fx * d.cell[0] + fy * d.cell[3] + fz * d.cell[6]);
-      d.fpos.push_back(fx * d.cell[1] + fy * d.cell[4] + fz * d.cell[7]);
-      d.fpos.push_back(fx * d.cell[2] + fy * d.cell[5] + fz * d.cell[8]);
+      if(owner[A] != 0) continue;
+      place(A, ix, jy, kz, d.fpos);
       d.ftype.push_back(ut[A]); d.fcharge.push_back(uq[A]);
     }
+  for(size_t f = 0; f < d.fw.size(); f++)
+  {
+    Deck::FrameworkComponent& F = d.fw[f];
+    if(F.molsize > 1 && nx * ny * nz > 1) throw std::runtime_error("separated framework molecules with several atoms need UnitCells 1 1 1 (atoms of a molecule must stay contiguous)");
+    for(int ix = 0; ix < nx; ix++) for(int jy = 0; jy < ny; jy++) for(int kz = 0; kz < nz; kz++)
+    {
+      const int cell_id = (ix * ny + jy) * nz + kz;
+      for(size_t k = 0; k < F.atom_index.size(); k++)
+      {
+        const size_t A = (size_t) F.atom_index[k];
+        place(A, ix, jy, kz, F.pos);
+        F.type.push_back(ut[A]); F.charge.push_back(uq[A]);
+        F.molid.push_back(F.nmol * cell_id + (int) (k / (size_t) F.molsize));       // :1728-1733
+      }
+    }
+  }
+}
+
+// ReadFrameworkSpeciesDefinitions, read_data.cpp:1860-1930: Framework_Component_<i>.def
+inline void read_framework_components(Deck& d, const std::string& dir)
+{
+  if(!d.separate_framework || d.n_framework_components <= 1) { d.fw.clear(); return; }
+  d.fw.resize(d.n_framework_components - 1);
+  for(int i = 1; i < d.n_framework_components; i++)
+  {
+    Deck::FrameworkComponent& F = d.fw[i - 1];
+    auto L = read_lines(dir + "/Framework_Component_" + std::to_string(i) + ".def");
+    for(auto& s : L)
+    {
+      auto t = terms(s);
+      if(t.size() < 2) continue;
+      if(s.find("Framework_Component_Name") != std::string::npos) F.name = t[1];
+      else if(s.find("Number_of_Molecules_for_Framework_component") != std::string::npos) F.nmol = std::stoi(t[1]);
+      else if(s.find("Number_of_atoms_for_each_molecule") != std::string::npos) F.molsize = std::stoi(t[1]);
+      else if(s.find("Atom_Indices_for_Molecule") != std::string::npos)
+        for(size_t k = 2; k < t.size(); k++) F.atom_index.push_back(std::stoi(t[k]));
+    }
+    if(F.nmol <= 0 || F.molsize <= 0) throw std::runtime_error("Framework_Component_" + std::to_string(i) + ".def: missing molecule count or size");
+  }
+}
+
+// ReadBlockPockets + ReplicateBlockPockets, read_data.cpp:3320-3454
+inline void read_block_pockets(Deck& d, const std::string& dir)
+{
+  for(auto& c : d.comps)
+  {
+    if(!c.use_pockets || c.pocket_file.empty()) { c.use_pockets = c.use_pockets && !c.pocket_file.empty(); continue; }
+    std::ifstream f(dir + "/" + c.pocket_file);
+    if(!f) throw std::runtime_error("Cannot open block pocket file: " + c.pocket_file);
+    size_t n = 0; f >> n;
+    std::vector<double> cen(3 * n), rad(n);
+    double maxc = 0.0;
+    for(size_t i = 0; i < n; i++) { f >> cen[3 * i] >> cen[3 * i + 1] >> cen[3 * i + 2] >> rad[i]; for(int k = 0; k < 3; k++) maxc = std::max(maxc, std::fabs(cen[3 * i + k])); }
+    const int nx = d.unitcells[0], ny = d.unitcells[1], nz = d.unitcells[2];
+    if(maxc > 1.5)       // Cartesian input: to fractional coordinates of ONE unit cell by the cell's diagonal (:3399-3411)
+    {
+      const double cx = d.cell[0] / nx, cy = d.cell[4] / ny, cz = d.cell[8] / nz;
+      for(size_t i = 0; i < n; i++) { cen[3 * i] /= cx; cen[3 * i + 1] /= cy; cen[3 * i + 2] /= cz; }
+    }
+    for(size_t i = 0; i < n; i++)
+      for(int j = 0; j < nx; j++) for(int k = 0; k < ny; k++) for(int l = 0; l < nz; l++)
+      {
+        const double vx = (cen[3 * i] + j) / nx, vy = (cen[3 * i + 1] + k) / ny, vz = (cen[3 * i + 2] + l) / nz;
+        c.pocket_centers.push_back(d.cell[0] * vx + d.cell[3] * vy + d.cell[6] * vz);
+        c.pocket_centers.push_back(d.cell[1] * vx + d.cell[4] * vy + d.cell[7] * vz);
+        c.pocket_centers.push_back(d.cell[2] * vx + d.cell[5] * vy + d.cell[8] * vz);
+        c.pocket_radii.push_back(rad[i]);
+      }
+  }
 }
 
 // read_Ewald_Parameters_from_input, read_data.cpp:609-702
@@ -400,7 +540,9 @@ inline Deck load(const std::string& dir)
   read_simulation_input(d, dir);
   read_force_field(d, dir);
   for(auto& c : d.comps) read_molecule(d, c, dir);
+  read_framework_components(d, dir);
   read_framework(d, dir);
+  read_block_pockets(d, dir);
   if(!d.no_charges) setup_ewald(d);
   // Setup_Box_Temperature_Pressure, fxn_main.h:115-127 with Units data_struct.h:58-68
   const double kB = 1.380649e-23, mass_unit = 1.6605402e-27, length_unit = 1e-10, time_unit = 1e-12;

@@ -55,6 +55,7 @@ struct CompState
   MoveCount trans, rot, ins, del, reins, widom, idswap_add, idswap_remove;
   std::vector<MoveCount> idswap_to;             // IdentitySwap_Total_TO / _Acc_TO per destination component
   MoveCount trans_window, rot_window;           // TranslationTotal/Accepted are reset every 500 cycles
+  MoveCount trans_cum, rot_cum;                 // CumTranslationTotal/...: what the reference prints (print_statistics.cuh:41-44)
   long nmol = 0;
   bool has_charge = false;
   // Rosenbluth statistics per block: sum W, sum W^2, count; W-weighted widom energies
@@ -75,15 +76,20 @@ struct Sim
   GlibcRand rng;
   std::vector<double> pool; size_t pool_size = 333334, pool_off = 0; long pool_rounds = 0;
   int ncomp = 0;                                  // total components incl. framework (component 0)
+  int nhost = 1;                                  // framework components (NComponents.y): 0 = the rigid rest, 1.. = separated, movable ones
   std::vector<CompState> C;
   long total_molecules = 1;                       // TotalNumberOfMolecules counts the framework as one
   Energy running;                                 // SystemComponents.deltaE
+  double initial_framework_ewald = 0.0;           // SystemComponents.InitialFrameworkEwald
   int nblock = 5; long block_size = 1; bool production = false;
   long moves_done = 0;
   bool fused = true;                              // one host round trip per move (gb_move_*); false: the stage calls
   double call_s[4] = {0, 0, 0, 0}; long call_n[4] = {0, 0, 0, 0};   // host time inside gb_move_{insertion,deletion,reinsertion,single_body}
   std::FILE* trace = nullptr;
 };
+
+inline int comp_ms(const Sim& S, int c) { return c == 0 ? 0 : (c < S.nhost ? S.d.fw[c - 1].molsize : S.d.comps[c - S.nhost].ms()); }
+inline const char* comp_name(const Sim& S, int c) { return c == 0 ? S.d.framework_name.c_str() : (c < S.nhost ? S.d.fw[c - 1].name.c_str() : S.d.comps[c - S.nhost].name.c_str()); }
 
 void pool_reset(Sim& S)                           // RandomNumber::ResetRandom
 {
@@ -113,14 +119,30 @@ void setup_engine(Sim& S)
   box.cubic = !((std::fabs(d.cell[3]) + std::fabs(d.cell[6]) + std::fabs(d.cell[7])) > 1e-10);
   box.use_lammps_ewald = d.lammps_ewald ? 1 : 0;
   GB(gb_upload_box(S.e, &box));
-  S.ncomp = 1 + (int) d.comps.size();
-  GB(gb_set_components(S.e, S.ncomp, 1));
+  S.nhost = 1 + (int) d.fw.size();
+  S.ncomp = S.nhost + (int) d.comps.size();
+  GB(gb_set_components(S.e, S.ncomp, S.nhost));
   {
     const size_t nf = d.ftype.size();
     std::vector<uint64_t> ty(nf), mol(nf, 0); std::vector<double> one(nf, 1.0);
     for(size_t i = 0; i < nf; i++) ty[i] = (uint64_t) d.ftype[i];
     gb_atoms a{d.fpos.data(), one.data(), d.fcharge.data(), one.data(), ty.data(), mol.data(), (int64_t) nf, (int64_t) nf, (int64_t) nf, (int64_t) nf};
     GB(gb_upload_atoms(S.e, 0, &a));
+  }
+  for(size_t f = 0; f < d.fw.size(); f++)
+  {
+    // separated framework component: its own slot range, MolID per molecule, movable (CheckFrameworkCIF read_data.cpp:1700-1790)
+    const deck::Deck::FrameworkComponent& F = d.fw[f];
+    const size_t n = F.type.size();
+    std::vector<uint64_t> ty(n), mol(n); std::vector<double> one(n, 1.0);
+    for(size_t i = 0; i < n; i++) { ty[i] = (uint64_t) F.type[i]; mol[i] = (uint64_t) F.molid[i]; }
+    gb_atoms a{F.pos.data(), one.data(), F.charge.data(), one.data(), ty.data(), mol.data(), (int64_t) n, (int64_t) n, (int64_t) n, (int64_t) F.molsize};
+    GB(gb_upload_atoms(S.e, (int32_t) (f + 1), &a));
+    S.C[f + 1].nmol = (long) (n / (size_t) F.molsize);
+    bool charged = false;
+    for(size_t i = 0; i < n; i++) if(std::fabs(F.charge[i]) > 1e-10) charged = true;
+    S.C[f + 1].has_charge = charged;
+    S.total_molecules += S.C[f + 1].nmol;
   }
   for(size_t c = 0; c < d.comps.size(); c++)
   {
@@ -130,7 +152,7 @@ void setup_engine(Sim& S)
     for(int i = 0; i < ms; i++) ty[i] = (uint64_t) M.type[i];
     // slot 0 holds the template molecule (read_data.cpp:2122-2147); Allocate_size = AdsorbateAllocateSpace (fxn_main.h:46-62)
     gb_atoms a{M.pos.data(), one.data(), M.charge.data(), one.data(), ty.data(), mol.data(), ms, 0, (int64_t) std::max<long>(d.adsorbate_allocate, ms), ms};
-    GB(gb_upload_atoms(S.e, (int32_t) (c + 1), &a));
+    GB(gb_upload_atoms(S.e, (int32_t) (c + S.nhost), &a));
   }
   GB(gb_set_cbmc(S.e, d.n_trial_positions, d.n_trial_orientations, d.beta));
   // rigid exclusion constants from the template molecule, Calculate_Exclusion_Energy_Rigid ewald_preparation.h:261-298, 351-366
@@ -164,17 +186,32 @@ void setup_engine(Sim& S)
       const double ps = d.prefactor * d.alpha / std::sqrt(3.14159265358979323846);
       for(int i = 0; i < M.ms(); i++) { self += ps * M.charge[i] * M.charge[i]; if(std::fabs(M.charge[i]) > 1e-10) charged = true; }
     }
-    GB(gb_set_exclusion_constants(S.e, (int32_t) (c + 1), intra, self, 1, charged ? 1 : 0));
-    S.C[c + 1].has_charge = charged;
+    GB(gb_set_exclusion_constants(S.e, (int32_t) (c + S.nhost), intra, self, 1, charged ? 1 : 0));
+    S.C[c + S.nhost].has_charge = charged;
+    if(M.use_pockets && !M.pocket_radii.empty())
+      GB(gb_set_block_pockets(S.e, (int32_t) (c + S.nhost), (int32_t) M.pocket_radii.size(), M.pocket_centers.data(), M.pocket_radii.data(), M.invert_pockets ? 1 : 0));
   }
 }
 
 // ------------------------------------------------------------------------------------------------ probabilities
 void setup_probabilities(Sim& S)
 {
+  for(size_t f = 0; f < S.d.fw.size(); f++)        // ReadFrameworkComponentMoves: translation, rotation, special rotation, reinsertion
+  {
+    const deck::Deck::FrameworkComponent& F = S.d.fw[f]; CompState& X = S.C[f + 1];
+    double t = F.p_translation, r = F.p_rotation, sp = F.p_special, re = F.p_reinsertion;
+    double tot = t + r + sp + re;
+    if(tot > 1e-10) { t /= tot; r /= tot; sp /= tot; re /= tot; tot = 1.0; }
+    X.total_prob = tot;
+    X.cTrans = t; X.cRot = r + X.cTrans; X.cSpecial = sp + X.cRot; X.cWidom = X.cSpecial; X.cReins = re + X.cWidom;
+    X.cIdentity = X.cReins; X.cCBCF = X.cIdentity; X.cSwap = X.cCBCF;
+    X.max_trans[0] = S.d.cell[0] * 0.1; X.max_trans[1] = S.d.cell[4] * 0.1; X.max_trans[2] = S.d.cell[8] * 0.1;
+    for(int k = 0; k < 3; k++) X.max_rot[k] = 30.0 / (180 / 3.1415);
+    if(sp > 0.0 || re > 0.0) { std::fprintf(stderr, "graspa_b200_mc: special rotation / reinsertion of framework components is not driven by this host program\n"); std::exit(2); }
+  }
   for(size_t c = 0; c < S.d.comps.size(); c++)
   {
-    const deck::Component& M = S.d.comps[c]; CompState& X = S.C[c + 1];
+    const deck::Component& M = S.d.comps[c]; CompState& X = S.C[c + S.nhost];
     double t = M.p_translation, r = M.p_rotation, sp = 0.0, w = M.p_widom, re = M.p_reinsertion, id = M.p_identity, sw = M.p_swap, cb = 0.0;
     double tot = t + r + sp + w + re + id + sw + cb;
     if(tot > 1e-10) { t /= tot; r /= tot; sp /= tot; w /= tot; sw /= tot; cb /= tot; re /= tot; id /= tot; tot = 1.0; }
@@ -190,7 +227,7 @@ void setup_probabilities(Sim& S)
 
 double prefactor(const Sim& S, int comp, bool insertion)          // GetPrefactor, mc_utilities.h:315-351
 {
-  const deck::Component& M = S.d.comps[comp - 1];
+  const deck::Component& M = S.d.comps[comp - S.nhost];
   const double N = (double) S.C[comp].nmol;
   if(insertion) return S.d.beta * M.mol_fraction * S.d.pressure * M.fugacity_coeff * S.d.volume / (1.0 + N);
   return N / (S.d.beta * M.mol_fraction * S.d.pressure * M.fugacity_coeff * S.d.volume);
@@ -203,7 +240,7 @@ struct Growth { bool success = false; double W = 0.0; Energy E; int sel_fb = 0, 
 Growth insertion_body(Sim& S, int comp)
 {
   Growth G;
-  const int ms = S.d.comps[comp - 1].ms();
+  const int ms = S.d.comps[comp - S.nhost].ms();
   const double scale[2] = {1.0, 1.0};
   gb_cbmc_result r; int32_t used = 0;
   pool_check(S, S.d.n_trial_positions);
@@ -291,7 +328,7 @@ void move_insertion(Sim& S, int comp)              // InsertionMove::Run, move_s
   X.ins.total++;
   Growth G = insertion_body(S, comp);
   if(!G.success) { trace_move(S, "insertion", comp, X.nmol, 0, 0.0); return; }
-  const double pacc = prefactor(S, comp, true) * G.W / S.d.comps[comp - 1].ideal_rosenbluth;
+  const double pacc = prefactor(S, comp, true) * G.W / S.d.comps[comp - S.nhost].ideal_rosenbluth;
   const double R = S.rng.uniform();
   if(R < pacc)
   {
@@ -307,7 +344,7 @@ void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run + Deleti
 {
   CompState& X = S.C[comp];
   X.del.total++;
-  const int ms = S.d.comps[comp - 1].ms();
+  const int ms = S.d.comps[comp - S.nhost].ms();
   const double scale[2] = {1.0, 1.0};
   gb_cbmc_result r; int32_t used = 0;
   pool_check(S, S.d.n_trial_positions);
@@ -351,7 +388,7 @@ void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run + Deleti
   }
   W /= std::exp(-S.d.beta * tail);
   E.Tail = -tail;
-  const double pacc = pre * S.d.comps[comp - 1].ideal_rosenbluth / W;
+  const double pacc = pre * S.d.comps[comp - S.nhost].ideal_rosenbluth / W;
   const double R = S.rng.uniform();
   if(R < pacc)
   {
@@ -367,7 +404,7 @@ void move_reinsertion(Sim& S, int comp, long mol)  // ReinsertionMove::Run, move
 {
   CompState& X = S.C[comp];
   X.reins.total++;
-  const int ms = S.d.comps[comp - 1].ms();
+  const int ms = S.d.comps[comp - S.nhost].ms();
   const double scale[2] = {1.0, 1.0};
   gb_cbmc_result r; int32_t used = 0;
   // insertion leg
@@ -459,7 +496,7 @@ void move_single_body(Sim& S, int comp, long mol, int move_type)   // SingleBody
   MoveCount& cnt = move_type == GB_TRANSLATION ? X.trans : X.rot;
   MoveCount& win = move_type == GB_TRANSLATION ? X.trans_window : X.rot_window;
   cnt.total++; win.total++;
-  const int ms = S.d.comps[comp - 1].ms();
+  const int ms = comp_ms(S, comp);
   const double* maxc = move_type == GB_TRANSLATION ? X.max_trans : X.max_rot;
   pool_check(S, ms);
   gb_move_energy d; int32_t overlap = 0; double ew[2] = {0.0, 0.0};
@@ -479,7 +516,11 @@ void move_single_body(Sim& S, int comp, long mol, int move_type)   // SingleBody
   }
   if(overlap) { trace_move(S, move_type == GB_TRANSLATION ? "translation" : "rotation", comp, mol, 0, 0.0); return; }
   Energy E; E.HHVDW = d.HHVDW; E.HGVDW = d.HGVDW; E.GGVDW = d.GGVDW; E.HHReal = d.HHReal; E.HGReal = d.HGReal; E.GGReal = d.GGReal;
-  if(!S.d.no_charges && X.has_charge) { E.GGEwald = ew[0]; E.HGEwald = ew[1]; }
+  if(!S.d.no_charges && X.has_charge)
+  {
+    // {same type, cross}: a moved framework component books the same-type term as host-host (mc_single_particle.h:214-224)
+    if(comp < S.nhost) { E.HHEwald = ew[0]; E.HGEwald = ew[1]; } else { E.GGEwald = ew[0]; E.HGEwald = ew[1]; }
+  }
   const double pacc = 1.0 * std::exp(-S.d.beta * E.total());
   const double R = S.rng.uniform();
   if(R < pacc)
@@ -496,13 +537,13 @@ void move_single_body(Sim& S, int comp, long mol, int move_type)   // SingleBody
 void move_identity_swap(Sim& S)
 {
   long adsorbates = 0;
-  for(int c = 1; c < S.ncomp; c++) adsorbates += S.C[c].nmol;
+  for(int c = S.nhost; c < S.ncomp; c++) adsorbates += S.C[c].nmol;
   if(adsorbates == 0) return;                                       // :217-221 (TotalNumberOfMolecules - NumberOfFrameworks == 0)
   int oldc = 0, newc = 0; long nold = 0;
   while(oldc == 0 || oldc >= S.ncomp || newc == 0 || newc >= S.ncomp || nold == 0)
   {
-    oldc = (int) (size_t) (S.rng.uniform() * (double) (S.ncomp - 1)) + 1;
-    newc = (int) (size_t) (S.rng.uniform() * (double) (S.ncomp - 1)) + 1;
+    oldc = (int) (size_t) (S.rng.uniform() * (double) (S.ncomp - S.nhost)) + S.nhost;
+    newc = (int) (size_t) (S.rng.uniform() * (double) (S.ncomp - S.nhost)) + S.nhost;
     nold = S.C[oldc].nmol;
   }
   const long new_mol = S.C[newc].nmol;
@@ -511,7 +552,7 @@ void move_identity_swap(Sim& S)
   XO.idswap_remove.total++; XN.idswap_add.total++;
   if(XO.idswap_to.empty()) XO.idswap_to.assign(S.ncomp, MoveCount());
   XO.idswap_to[newc].total++;
-  const int ms_new = S.d.comps[newc - 1].ms(), ms_old = S.d.comps[oldc - 1].ms();
+  const int ms_new = S.d.comps[newc - S.nhost].ms(), ms_old = S.d.comps[oldc - S.nhost].ms();
   const double scale[2] = {1.0, 1.0};
   gb_cbmc_result r; int32_t used = 0;
   // ---- insertion leg: first bead preset to the old molecule's first atom, old molecule excluded (:260-296)
@@ -560,7 +601,7 @@ void move_identity_swap(Sim& S)
   E.Tail = tail;
   Wn *= std::exp(-S.d.beta * tail);
   const double pre = prefactor(S, newc, true) * prefactor(S, oldc, false);
-  const double pacc = pre * (Wn / S.d.comps[newc - 1].ideal_rosenbluth) / (Wo / S.d.comps[oldc - 1].ideal_rosenbluth);
+  const double pacc = pre * (Wn / S.d.comps[newc - S.nhost].ideal_rosenbluth) / (Wo / S.d.comps[oldc - S.nhost].ideal_rosenbluth);
   const double R = S.rng.uniform();
   if(R < pacc)
   {
@@ -597,9 +638,10 @@ void run_move(Sim& S, long cycle)
   }
 }
 
-void update_max(double* m, MoveCount& w, double cap)           // Update_Max_Translation / Update_Max_Rotation
+void update_max(double* m, MoveCount& w, MoveCount& cum, double cap)           // Update_Max_Translation / Update_Max_Rotation
 {
   if(w.total == 0) return;
+  cum.total += w.total; cum.accepted += w.accepted;
   const double ratio = (double) w.accepted / (double) w.total;
   for(int k = 0; k < 3; k++) { m[k] *= (ratio > 0.5) ? 1.05 : 0.95; if(m[k] < 0.01) m[k] = 0.01; if(m[k] > cap) m[k] = cap; }
   w.total = 0; w.accepted = 0;
@@ -616,7 +658,7 @@ void run_phase(Sim& S, long cycles, bool production)
     if(S.d.use_max_step && steps > S.d.max_step_per_cycle) steps = S.d.max_step_per_cycle;
     for(long j = 0; j < steps; j++) run_move(S, i);
     if(i % 500 == 0)
-      for(int c = 1; c < S.ncomp; c++) { update_max(S.C[c].max_trans, S.C[c].trans_window, 5.0); update_max(S.C[c].max_rot, S.C[c].rot_window, 3.14); }
+      for(int c = 1; c < S.ncomp; c++) { update_max(S.C[c].max_trans, S.C[c].trans_window, S.C[c].trans_cum, 5.0); update_max(S.C[c].max_rot, S.C[c].rot_window, S.C[c].rot_cum, 3.14); }
   }
 }
 
@@ -635,7 +677,8 @@ bool widom_only(const Sim& S, int& comp)
     found = c;
   }
   comp = found;
-  return found >= 0 && S.d.n_trial_positions == S.d.n_trial_orientations && S.d.comps[found - 1].ms() > 1 && S.d.use_max_step && S.d.max_step_per_cycle == 1;
+  if(found >= 0 && (found < S.nhost || S.d.comps[found - S.nhost].use_pockets)) return false;
+  return found >= 0 && S.d.n_trial_positions == S.d.n_trial_orientations && S.d.comps[found - S.nhost].ms() > 1 && S.d.use_max_step && S.d.max_step_per_cycle == 1;
 }
 
 } // namespace
@@ -738,7 +781,7 @@ void print_widom(Sim& S, int comp)
   const long ncell = (long) S.d.unitcells[0] * S.d.unitcells[1] * S.d.unitcells[2];
   const double rho = S.d.framework_mass * ncell * 1.0e-3 / (NA * S.d.volume * 1.0e-30);
   double tw = 0, tw2 = 0, th = 0, th2 = 0;
-  std::printf("=====================Rosenbluth Summary For Component [%d] (%s)=====================\n", comp, S.d.comps[comp - 1].name.c_str());
+  std::printf("=====================Rosenbluth Summary For Component [%d] (%s)=====================\n", comp, S.d.comps[comp - S.nhost].name.c_str());
   for(int b = 0; b < S.nblock; b++)
   {
     std::printf("=====BLOCK %d=====\nWidom Performed: %.1f\n", b, X.rn[b]);
@@ -765,7 +808,9 @@ Energy total_energy(Sim& S)
   gb_move_energy v, w; double tail = 0.0;
   GB(gb_total_vdw_real(S.e, &v)); GB(gb_total_ewald(S.e, 0, &w)); GB(gb_tail_total(S.e, &tail));
   Energy E; E.HHVDW = v.HHVDW; E.HGVDW = v.HGVDW; E.GGVDW = v.GGVDW; E.HHReal = v.HHReal; E.HGReal = v.HGReal; E.GGReal = v.GGReal;
-  E.HHEwald = w.HHEwaldE; E.HGEwald = w.HGEwaldE; E.GGEwald = w.GGEwaldE; E.Tail = tail;
+  // Ewald_Total books the framework's own term into the guest-guest sum as well (ewald_preparation.h:174); the stage
+  // summary takes it out again (fxn_main.h:318) and reports host-host relative to the initial framework (:324-326)
+  E.HHEwald = w.HHEwaldE - S.initial_framework_ewald; E.HGEwald = w.HGEwaldE; E.GGEwald = w.GGEwaldE - w.HHEwaldE; E.Tail = tail;
   return E;
 }
 
@@ -804,6 +849,10 @@ int main(int argc, char** argv)
                   d.ftype.size(), d.comps.size(), d.alpha, d.kmax[0], d.kmax[1], d.kmax[2], d.volume, d.beta,
                   (long) d.init_cycles, (long) d.equil_cycles, (long) d.prod_cycles, (long) d.random_seed);
       for(size_t c = 0; c < d.comps.size(); c++) std::printf("%s%.10f", c ? ", " : "", d.comps[c].fugacity_coeff);
+      std::printf("], \"framework_components\": [%zu", d.ftype.size());
+      for(const auto& F : d.fw) std::printf(", %zu", F.type.size());
+      std::printf("], \"block_pockets\": [");
+      for(size_t c = 0; c < d.comps.size(); c++) std::printf("%s%zu", c ? ", " : "", d.comps[c].pocket_radii.size());
       std::printf("]}\n");
     }
     catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
@@ -829,7 +878,7 @@ int main(int argc, char** argv)
   if(o_init >= 0) S.d.init_cycles = o_init;
   if(o_equil >= 0) S.d.equil_cycles = o_equil;
   if(o_prod >= 0) S.d.prod_cycles = o_prod;
-  S.C.assign(1 + S.d.comps.size(), CompState());
+  S.C.assign(1 + S.d.fw.size() + S.d.comps.size(), CompState());
   if(trace_path) S.trace = std::fopen(trace_path, "w");
   S.fused = !staged;
   setup_engine(S);
@@ -846,7 +895,7 @@ int main(int argc, char** argv)
   S.pool[0] = 2.3; S.pool[1] = 4.5; S.pool[2] = 6.7;
   GB(gb_upload_random_pool(S.e, S.pool.data(), (int64_t) S.pool_size));
   // initial energies + structure factors (Check_Simulation_Energy(INITIAL), fxn_main.h:282-404)
-  { gb_move_energy w; GB(gb_total_ewald(S.e, 1, &w)); }
+  { gb_move_energy w; GB(gb_total_ewald(S.e, 1, &w)); S.initial_framework_ewald = w.HHEwaldE; }
   const Energy E0 = total_energy(S);
   print_energy("INITIAL", E0);
 
@@ -873,11 +922,15 @@ int main(int argc, char** argv)
   {
     const CompState& X = S.C[c];
     std::printf("Component %d (%s): molecules %ld | translation %ld/%ld rotation %ld/%ld insertion %ld/%ld deletion %ld/%ld reinsertion %ld/%ld widom %ld\n",
-                c, S.d.comps[c - 1].name.c_str(), X.nmol, X.trans.accepted, X.trans.total, X.rot.accepted, X.rot.total, X.ins.accepted, X.ins.total,
+                c, comp_name(S, c), X.nmol, X.trans.accepted, X.trans.total, X.rot.accepted, X.rot.total, X.ins.accepted, X.ins.total,
                 X.del.accepted, X.del.total, X.reins.accepted, X.reins.total, X.widom.total);
+    // the reference prints max(cumulative up to the last 500-cycle update, current window)
+    std::printf("Translation Performed: %ld\nTranslation Accepted: %ld\nRotation Performed: %ld\nRotation Accepted: %ld\n",
+                std::max(X.trans_cum.total, X.trans_window.total), std::max(X.trans_cum.accepted, X.trans_window.accepted),
+                std::max(X.rot_cum.total, X.rot_window.total), std::max(X.rot_cum.accepted, X.rot_window.accepted));
     if(X.idswap_add.total + X.idswap_remove.total > 0)
-      for(int t = 1; t < S.ncomp && !X.idswap_to.empty(); t++)
-        std::printf("Identity Swap Performed, FROM [%s (%d)] TO [%s (%d)]: %ld (%ld Accepted)\n", S.d.comps[c - 1].name.c_str(), c, S.d.comps[t - 1].name.c_str(), t,
+      for(int t = S.nhost; t < S.ncomp && !X.idswap_to.empty(); t++)
+        std::printf("Identity Swap Performed, FROM [%s (%d)] TO [%s (%d)]: %ld (%ld Accepted)\n", comp_name(S, c), c, comp_name(S, t), t,
                     X.idswap_to[t].total, X.idswap_to[t].accepted);
     if(X.widom.total > 0) print_widom(S, c);
   }

@@ -142,6 +142,13 @@ int  gb_download_structure_factors(gb_engine* e, double* adsorbate_eik, double* 
 int  gb_set_exclusion_constants(gb_engine* e, int32_t component, double exclusion_intra, double exclusion_atom, int32_t rigid, int32_t has_partial_charge);
 /* the device random pool, RandomNumber::DeviceRandom/ResetRandom data_struct.h:1300-1327: n double3 */
 int  gb_upload_random_pool(gb_engine* e, const double* random3, int64_t n);
+/* block pockets of one component: n spheres, Cartesian centres (3n) and radii (n) as ReadBlockingPockets /
+ * ReplicateBlockPockets leave them (read_data.cpp:3290-3454), invert = InvertBlockPockets.  Replaces the host-side
+ * BlockedPocket() calls of the kept drivers (read_data.cpp:3466-3640; mc_widom.h:445-497 first-bead trials,
+ * mc_swap_utilities.h:35-78 / move_struct.h:208-250 / mc_swap_moves.h:299-330 grown molecules,
+ * mc_single_particle.h:83-119 translation / rotation proposals): the move kernels run the test on the device and report
+ * a blocked trial as an overlap, a blocked grown molecule as a failed construction.  n = 0 removes the list. */
+int  gb_set_block_pockets(gb_engine* e, int32_t component, int32_t n, const double* centers, const double* radii, int32_t invert);
 /* Widom/CBMC parameters, WidomStruct data_struct.h:1271-1278 and Components::Beta */
 int  gb_set_cbmc(gb_engine* e, int32_t n_trial_positions, int32_t n_trial_orientations, double beta);
 /* host mirror of Components::NumberOfPseudoAtoms (live atoms of each force-field type), kept by the engine

@@ -44,7 +44,7 @@ if [ "$WHAT" = "all" ] || [ "$WHAT" = "examples" ]; then
     mkdir -p "$OUT/examples/$ex"
     # inputs only: no committed outputs, no restart dumps
     find "$REF/Examples/$ex" -maxdepth 1 -type f \
-        \( -name '*.def' -o -name '*.cif' -o -name 'simulation.input' \) \
+        \( -name '*.def' -o -name '*.cif' -o -name '*.block' -o -name 'simulation.input' \) \
         -exec cp {} "$OUT/examples/$ex/" \;
   done
 fi

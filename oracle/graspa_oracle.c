@@ -127,6 +127,35 @@ void orc_pbc(double* p, const orc_box* b)
   }
 }
 
+/* BlockedPocket, read_data.cpp:3466-3640: 1 when pos lies inside any of the n spheres {x, y, z, radius} (invert: when it
+ * lies outside all of them).  The difference centre - pos takes the nearest image with RASPA-2's rule (apply_pbc_raspa2:
+ * cubic boxes divide by the cell edge, :3519-3528; otherwise the fractional round of :3531-3547). */
+int orc_blocked_pocket(const orc_box* b, const double* pockets, int n, int invert, const double* pos)
+{
+  const double* C = b->cell; const double* I = b->inv;
+  if(n <= 0) return 0;
+  for(int i = 0; i < n; i++)
+  {
+    double dx = pockets[4*i] - pos[0], dy = pockets[4*i+1] - pos[1], dz = pockets[4*i+2] - pos[2];
+    if(b->cubic)
+    {
+      dx -= C[0] * (int)(dx / C[0] + ((dx >= 0.0) ? 0.5 : -0.5));
+      dy -= C[4] * (int)(dy / C[4] + ((dy >= 0.0) ? 0.5 : -0.5));
+      dz -= C[8] * (int)(dz / C[8] + ((dz >= 0.0) ? 0.5 : -0.5));
+    }
+    else
+    {
+      double sx = I[0]*dx + I[3]*dy + I[6]*dz, sy = I[1]*dx + I[4]*dy + I[7]*dz, sz = I[2]*dx + I[5]*dy + I[8]*dz;
+      double tx = sx - (int)(sx + ((sx >= 0.0) ? 0.5 : -0.5));
+      double ty = sy - (int)(sy + ((sy >= 0.0) ? 0.5 : -0.5));
+      double tz = sz - (int)(sz + ((sz >= 0.0) ? 0.5 : -0.5));
+      dx = C[0]*tx + C[3]*ty + C[6]*tz; dy = C[1]*tx + C[4]*ty + C[7]*tz; dz = C[2]*tx + C[5]*ty + C[8]*tz;
+    }
+    if(sqrt(dx*dx + dy*dy + dz*dz) < pockets[4*i+3]) return invert ? 0 : 1;
+  }
+  return invert ? 1 : 0;
+}
+
 /* maths.cuh:452-494 */
 void orc_vdw(const double* F, double rr, double scaling, int use1264, double* result)
 {

@@ -75,7 +75,8 @@ void   orc_ff_mix(int ntypes, const double* eps_in, const double* sig_in, const 
                   double cutoff_vdw_sq, double* eps, double* sigma, double* shift, int* use_tail, double* tail_e); /* read_data.cpp:1179-1247, 833-873 */
 
 /* ---- pair primitives ---- */
-void   orc_pbc(double* v, const orc_box* box);                                  /* maths.cuh:427-450 */
+void   orc_pbc(double* v, const orc_box* box);
+int    orc_blocked_pocket(const orc_box* box, const double* pockets4, int n, int invert, const double* pos); /* read_data.cpp:3466-3640 */                                  /* maths.cuh:427-450 */
 void   orc_vdw(const double* ffarg, double rr, double scaling, int use1264, double* result); /* maths.cuh:452-494 */
 double orc_coulomb_real(double qa, double qb, double r, double scaling, double prefactor, double alpha); /* maths.cuh:496-500 */
 

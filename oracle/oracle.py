@@ -138,6 +138,14 @@ def pbc(v, box: Box):
     return v
 
 
+def blocked_pocket(box: Box, centers, radii, pos, invert=False):
+    """BlockedPocket (read_data.cpp:3466-3640) for one Cartesian position"""
+    pk = np.ascontiguousarray(np.concatenate([np.asarray(centers, dtype=np.float64).reshape(-1, 3), np.asarray(radii, dtype=np.float64).reshape(-1, 1)], axis=1))
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    ob = c_box(box)
+    return bool(lib().orc_blocked_pocket(C.byref(ob), _p(pk, f64p), C.c_int(pk.shape[0]), C.c_int(int(invert)), _p(pos, f64p)))
+
+
 def ff_mix(eps, sig, shifted, tail, cutoff_vdw):
     n = len(eps)
     eps = np.ascontiguousarray(eps, dtype=np.float64); sig = np.ascontiguousarray(sig, dtype=np.float64)

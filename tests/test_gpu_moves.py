@@ -418,3 +418,79 @@ def test_identity_swap_same_species_with_charges(gpu_engine_factory, oracle):
     E1 = _totals(eng)
     assert abs((E1 - E0) - delta) <= 1e-9 * max(1.0, abs(E1)), (E1 - E0, delta)
     eng.close()
+
+
+def test_block_pockets_in_the_move_kernels(gpu_engine_factory, oracle):
+    """gb_set_block_pockets: the device-side BlockedPocket test (read_data.cpp:3466-3640) as the kept drivers apply it --
+    first-bead trials (a blocked starting bead flags every trial, mc_widom.h:445-497), the grown molecule after the chain
+    stage (mc_swap_utilities.h:35-78), translation proposals (mc_single_particle.h:83-119) -- stage calls and fused
+    calls against the oracle's flags."""
+    box, ff, s, z, eng = _setup(gpu_engine_factory, "B")
+    comp = 1; ms = 3; beta = float(z["beta"])
+    rng = np.random.default_rng(31)
+    pool = rng.random((4096, 3)); eng.upload_random_pool(pool)
+    # pockets that cover roughly a third of the box
+    cen = rng.random((40, 3)) * np.array([box.cell[0], box.cell[4], box.cell[8]]); rad = 3.0 + 3.0 * rng.random(40)
+    eng.set_block_pockets(comp, cen, rad)
+    blocked = lambda p: oracle.blocked_pocket(box, cen, rad, p)
+    nmol = int(s.natoms[comp]) // ms
+    seen = dict(all=0, some=0, none=0, grown=0)
+    for k in range(60):
+        off = 20 * k; u = 0.37
+        tr = oracle.trial_positions(box, s, CBMC_INSERTION, comp, 0, 10, pool[off:off + 10])
+        e, f, _ = oracle.trial_energies(box, ff, s, 10, 1, tr, comp, nmol)
+        bl = np.array([blocked(p) for p in tr.pos])
+        f2 = f.copy()
+        if bl[0]: f2[:] = 1
+        else: f2[1:] |= bl[1:].astype(f2.dtype)
+        seen["all" if bl[0] else ("some" if bl.any() else "none")] += 1
+        ref = oracle.cbmc_finish(CBMC_INSERTION, False, e, f2, beta, 10, u)
+        for fused in (False, True):
+            if fused:
+                m = eng.move_insertion(comp, off, (u, 0.61)); fb = m["first_bead"]
+            else:
+                fb = eng.cbmc_first_bead(CBMC_INSERTION, comp, 0, off, u)
+            assert fb["n_survivors"] == ref["nsurv"], (k, fused, fb, ref)
+            assert fb["success"] == ref["success"]
+            if not ref["success"]:
+                continue
+            assert fb["selected"] == ref["selected"] and abs(fb["rosenbluth"] - ref["rosenbluth"]) <= 1e-9 * ref["rosenbluth"]
+            # chain stage: the grown molecule is checked atom by atom
+            if fused:
+                ch = m["chain"]; grown_ok = m["success"]
+            else:
+                ch = eng.cbmc_chain(CBMC_INSERTION, comp, 0, off + 10, 0.61); grown_ok = ch["success"]
+            t2 = oracle.trial_orientations(s, CBMC_INSERTION, comp, 1, ms - 1, 10, pool[off + 10:off + 20], tr.pos[ref["selected"]])
+            e2, fl2, _ = oracle.trial_energies(box, ff, s, 10, ms - 1, t2, comp, nmol)
+            ref2 = oracle.cbmc_finish(CBMC_INSERTION, True, e2, fl2, beta, 10, 0.61)
+            if ref2["success"] and ref["rosenbluth"] * ref2["rosenbluth"] > 1e-150:
+                sel = ref2["selected"]
+                mol = np.concatenate([[tr.pos[ref["selected"]]], t2.pos[sel * (ms - 1):(sel + 1) * (ms - 1)]])
+                grown_blocked = any(blocked(p) for p in mol)
+                seen["grown"] += int(grown_blocked)
+                assert bool(grown_ok) == (not grown_blocked), (k, fused, grown_ok, grown_blocked)
+            else:
+                assert not grown_ok
+    assert seen["all"] > 3 and seen["some"] > 3 and seen["grown"] > 0, seen
+    # translation: a proposal with an atom inside a pocket is reported as an overlap, by both paths
+    o = int(s.offsets[comp]); nb = 0
+    for k in range(40):
+        mol = k % nmol; off = 2000 + 3 * k
+        new = eng.single_body_propose(TRANSLATION, comp, mol, (2.0, 2.0, 2.0), off)
+        d, ov = eng.single_body_delta(comp)
+        old = TrialAtoms(s.pos[o + mol * ms:o + mol * ms + ms], s.charge[o:o + ms], s.type[o:o + ms])
+        nw = TrialAtoms(new, s.charge[o:o + ms], s.type[o:o + ms])
+        _, ov_ref = oracle.single_body_delta(box, ff, s, comp, mol, old, nw)
+        bl = any(blocked(p) for p in new)
+        nb += int(bl)
+        assert bool(ov) == bool(ov_ref or bl)
+        m = eng.move_single_body(TRANSLATION, comp, mol, (2.0, 2.0, 2.0), off)
+        assert bool(m["overlap"]) == bool(ov_ref or bl)
+    assert nb > 3
+    # removing the list restores the plain behaviour
+    eng.set_block_pockets(comp, np.zeros((0, 3)), np.zeros(0))
+    fb = eng.cbmc_first_bead(CBMC_INSERTION, comp, 0, 0, 0.37)
+    tr = oracle.trial_positions(box, s, CBMC_INSERTION, comp, 0, 10, pool[0:10])
+    e, f, _ = oracle.trial_energies(box, ff, s, 10, 1, tr, comp, nmol)
+    assert fb["n_survivors"] == int((f == 0).sum())
+    eng.close()
