@@ -124,49 +124,75 @@ def _tail_json(text):
     return None
 
 
-def gcmc_secondary(cycles=5000):
-    """GCMC cycles/s on the reference's CO2-MFI example (BASELINE.json configs[0]'s GCMC sibling): the host driver
-    (graspa_b200/host/graspa_b200_mc, one k_move launch per Monte Carlo move) and, when present, the reference's own
-    CUDA program built from /root/reference by oracle/build_ref.sh, both for `cycles` initialisation cycles."""
+def _deck_pair(name, init, prod, unit):
+    """One example deck of the reference through the host driver (graspa_b200/host/graspa_b200_mc) and, when present, through
+    the reference's own CUDA program built from /root/reference by oracle/build_ref.sh, same seed, same cycle counts.
+    unit "cycles/s": Monte Carlo cycles of the sequential Markov chain; "insertions/s": Widom moves of a Widom-only deck."""
     import shutil
     import tempfile
-    deck = os.path.join(ROOT, "oracle", "_ref", "examples", "CO2-MFI")
+    deck = os.path.join(ROOT, "oracle", "_ref", "examples", name)
     drv = os.path.join(ROOT, "graspa_b200", "host", "graspa_b200_mc")
-    out = {"workload": f"CO2-MFI example deck, {cycles} initialisation cycles, seed 0", "unit": "cycles/s"}
+    n = init + prod
+    out = {"workload": f"{name} example deck, {init} initialisation + {prod} production cycles, seed 0", "unit": unit}
     if not (os.path.isdir(deck) and os.path.exists(drv)):
         out["unavailable"] = "host driver or example deck not built (oracle/build_ref.sh, make -C graspa_b200/host)"
         return out
     try:
-        r = subprocess.run([drv, deck, "--init", str(cycles)], capture_output=True, text=True, timeout=300)
+        r = subprocess.run([drv, deck, "--init", str(init), "--equil", "0", "--prod", str(prod)], capture_output=True, text=True, timeout=300)
         j = _tail_json(r.stdout.split("host time inside")[0]) or {}
         out["value"] = j.get("cycles_per_s"); out["moves_per_s"] = j.get("moves_per_s"); out["kernel_launches"] = j.get("kernel_launches")
+        out["seconds"] = j.get("seconds"); out["path"] = j.get("widom_path") if unit == "insertions/s" else j.get("move_calls")
         for ln in r.stdout.splitlines():
             if ln.startswith("ENERGY DRIFT"):
                 out["energy_drift"] = float(ln.split(":")[-1])
+            if ln.startswith("Averaged Rosenbluth Weight:"):
+                out["mean_W"] = float(ln.split(":")[1].split("+/-")[0])
+            if ln.startswith("FINAL"):
+                out["final_total_energy"] = float(ln.split("Total:")[-1])
     except Exception as ex:  # noqa: BLE001
         out["error"] = str(ex)
     ref = os.path.join(ROOT, "oracle", "_ref", "graspa_ref_cuda.x")
     if os.path.exists(ref):
-        d = tempfile.mkdtemp(prefix="gcmc_ref_")
+        d = tempfile.mkdtemp(prefix="deck_ref_")
         try:
             for f in os.listdir(deck):
                 shutil.copy(os.path.join(deck, f), d)
             inp = os.path.join(d, "simulation.input")
             os.chmod(inp, 0o644)
             txt = open(inp).read().splitlines()
-            txt = [f"NumberOfInitializationCycles {cycles}" if t.startswith("NumberOfInitializationCycles") else t for t in txt]
+            sub = {"NumberOfInitializationCycles": init, "NumberOfEquilibrationCycles": 0, "NumberOfProductionCycles": prod}
+            txt = [next((f"{k} {v}" for k, v in sub.items() if t.startswith(k)), t) for t in txt]
             open(inp, "w").write("\n".join(txt) + "\n")
             t0 = time.perf_counter()
             r = subprocess.run([ref], cwd=d, capture_output=True, text=True, timeout=600)
             wall = time.perf_counter() - t0
             took = [ln for ln in r.stdout.splitlines() if ln.startswith("Work took")]
+            if not took and os.path.exists(os.path.join(d, "output.txt")):
+                took = [ln for ln in open(os.path.join(d, "output.txt")).read().splitlines() if ln.startswith("Work took")]
             secs = float(took[-1].split()[2]) if took else wall
-            out["reference_cuda"] = {"value": cycles / secs, "seconds": secs, "what": "the reference's own CUDA program (sm_100 build of /root/reference) on the same GPU, same deck"}
+            out["reference_cuda"] = {"value": n / secs, "seconds": secs,
+                                     "what": "the reference's own CUDA program (sm_100 build of /root/reference) on the same GPU, same deck, same seed"}
+            if out.get("value"):
+                out["speedup_vs_reference_cuda"] = out["value"] / (n / secs)
         except Exception as ex:  # noqa: BLE001
             out["reference_cuda"] = {"error": str(ex)}
         finally:
             shutil.rmtree(d, ignore_errors=True)
     return out
+
+
+def gcmc_secondary(cycles=5000):
+    """GCMC cycles/s of the sequential Markov chain on the reference's CO2-MFI example (one k_move launch per move)"""
+    return _deck_pair("CO2-MFI", cycles, 0, "cycles/s")
+
+
+def more_secondaries():
+    """the other example decks of BASELINE.json's configs, each beside the reference's own CUDA build:
+    Xe/Kr mixture with identity swaps, NaX with movable cations and block pockets, and the Henry-coefficient Widom deck
+    (the host driver replays the reference's random stream there: RNG-exact batched insertions)"""
+    return {"gcmc_xekr": _deck_pair("XeKr-Mixture", 20000, 0, "cycles/s"),
+            "gcmc_nax": _deck_pair("CO2_NaX_Zeolite", 5000, 0, "cycles/s"),
+            "widom_henry": _deck_pair("Henrys_coefficient", 0, 20000, "insertions/s")}
 
 
 def run_reference(args):
@@ -304,7 +330,9 @@ def main():
                        "parallelism": f"widom-shard x{world}", "cache": "inputs per step (random pool %.0f MB) exceed the 126 MB L2" % (B * 20 * 24 / 1e6),
                        "mean_W": float(sums[:, 0].sum() / max(total_count, 1.0)), "failed_fraction": float(sums[:, 10].sum() / max(total_count, 1.0))},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * 20 * 24 + B * 16), "d2h_bytes_per_step": int(5 * 12 * 8)},
-            "gpu_launches": int(launches), "clocks": sampler.summary()}
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "kernels": {"k_widom_pair_ms": ms_pair / max(n_pair, 1), "k_widom_ewald_ms": ms_ew / max(n_ew / 2, 1),
+                        "how": "CUDA events around each launch on the engine's stream, averaged over the timed steps"}}
     # ---- CPU baseline + algorithmic flop count on a bounded sample of the same workload
     cpu = None
     if not args.no_cpu_baseline:
@@ -330,6 +358,7 @@ def main():
         torch.cuda.set_stream(torch.cuda.default_stream())
         eng.close()
         line["gcmc"] = gcmc_secondary()
+        line.update(more_secondaries())
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

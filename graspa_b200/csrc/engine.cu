@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 #include <atomic>
 
@@ -68,6 +69,9 @@ struct gb_engine
 
   int ncomp = 0, nhost = 0;
   std::vector<Comp> comps;
+  // tail-correction deltas already evaluated on the device, keyed by (count delta per type, N_pseudo per type): the delta is a
+  // function of integer occupation numbers only, and a GCMC run revisits the same few hundred states over and over
+  std::map<std::vector<long long>, double> tail_memo;
   int nslots = 0;
   // host staging of the slot arrays (authoritative until the first device-side commit)
   std::vector<double> hx, hy, hz, hq, hscale, hscoul; std::vector<int> htype, hmolid;
@@ -372,6 +376,23 @@ int tail_device(gb_engine* e, const std::vector<int>* dcount, double* d_out)
   return GB_OK;
 }
 
+// tail delta for a change of `d` pseudo-atoms per type at the current occupation, evaluated by k_tail once per distinct state
+int tail_delta_memo(gb_engine* e, const std::vector<int>& d, double* out)
+{
+  std::vector<long long> key; key.reserve(2 * (size_t) e->ntypes);
+  for(int i = 0; i < e->ntypes; i++) key.push_back(d[i]);
+  for(int i = 0; i < e->ntypes; i++) key.push_back(e->npseudo[i]);
+  auto it = e->tail_memo.find(key);
+  if(it != e->tail_memo.end()) { *out = it->second; return GB_OK; }
+  int rc = tail_device(e, &d, e->d_result.p + 8); if(rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 8, e->d_result.p + 8, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  *out = e->h_pinned[8];
+  if(e->tail_memo.size() > 200000) e->tail_memo.clear();
+  e->tail_memo.emplace(std::move(key), *out);
+  return GB_OK;
+}
+
 std::vector<int> species_counts(gb_engine* e, int comp)
 {
   std::vector<int> c(e->ntypes, 0);
@@ -497,7 +518,7 @@ int gb_upload_forcefield(gb_engine* e, const gb_forcefield* ff, const gb_tail_ta
   e->P.ntypes = n; e->P.cut_vdw2 = ff->cutoff_vdw_sq; e->P.cut_coul2 = ff->cutoff_coul_sq; e->P.overlap = ff->overlap_criteria;
   e->P.no_charges = ff->no_charges; e->P.vdw_real_bias = ff->vdw_real_bias; e->P.use1264 = ff->use1264;
   e->P.ffA = e->d_ffA.p; e->P.ffB = e->d_ffB.p;
-  e->tail_use.assign(n2, 0); e->tail_e.assign(n2, 0.0); e->has_tail = false;
+  e->tail_use.assign(n2, 0); e->tail_e.assign(n2, 0.0); e->has_tail = false; e->tail_memo.clear();
   if(tail && tail->use_tail && tail->energy)
   {
     if(tail->size != n) return fail(GB_ERR_ARG, "tail table size differs from force-field size");
@@ -513,6 +534,7 @@ int gb_upload_forcefield(gb_engine* e, const gb_forcefield* ff, const gb_tail_ta
 
 int gb_upload_box(gb_engine* e, const gb_box* box)
 {
+  if(e) e->tail_memo.clear();                                     // the tail deltas carry 1 / volume
   if(!e || !box) return fail(GB_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(e->device));
   for(int i = 0; i < 9; i++) { e->P.cell[i] = box->cell[i]; e->P.inv[i] = box->inverse_cell[i]; }
@@ -878,11 +900,7 @@ int gb_tail_difference(gb_engine* e, int32_t c, int32_t move_type, double* out)
   std::vector<int> d = species_counts(e, c);
   const int sign = (move_type == GB_DELETION) ? -1 : 1;     // every other type keeps sign = +1 (:40-61)
   for(auto& v : d) v *= sign;
-  rc = tail_device(e, &d, e->d_result.p + 8); if(rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 8, e->d_result.p + 8, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
-  *out = e->h_pinned[8];
-  return GB_OK;
+  return tail_delta_memo(e, d, out);
 }
 
 int gb_tail_identity_swap(gb_engine* e, int32_t newc, int32_t oldc, double* out)
@@ -891,11 +909,7 @@ int gb_tail_identity_swap(gb_engine* e, int32_t newc, int32_t oldc, double* out)
   if(newc < 0 || newc >= e->ncomp || oldc < 0 || oldc >= e->ncomp) return fail(GB_ERR_ARG, "bad component");
   std::vector<int> dn = species_counts(e, newc), dold = species_counts(e, oldc);
   for(int i = 0; i < e->ntypes; i++) dn[i] -= dold[i];
-  rc = tail_device(e, &dn, e->d_result.p + 8); if(rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 8, e->d_result.p + 8, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
-  *out = e->h_pinned[8];
-  return GB_OK;
+  return tail_delta_memo(e, dn, out);
 }
 
 // ---------------------------------------------------------------------------------------------- totals

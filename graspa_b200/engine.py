@@ -111,7 +111,7 @@ def load_library(path=None):
     """dlopen the engine.  Fails loudly when the library has not been built: there is no fallback."""
     global _LIB
     if _LIB is None:
-        p = path or LIB_PATH
+        p = path or os.environ.get("GRASPA_B200_LIB") or LIB_PATH      # the override serves kernel experiments (build_dbg/)
         if not os.path.exists(p):
             raise EngineError(f"{p} is missing: build it with graspa_b200.engine.build() / make -C graspa_b200/csrc; "
                               "graspa_b200 has no CPU or Python fallback")
