@@ -168,6 +168,10 @@ __device__ __forceinline__ double erfc_table_eval(const double* __restrict__ tab
 // One in-cutoff pair: LJ 12-6 (+soft core, +shift) or 12-6-4 polynomial (maths.cuh:452-494) and the
 // real-space Ewald term (maths.cuh:496-500).  One rsqrt feeds both.
 // ffp: the LJ table (shared-memory copy or P.ffA); unit: warp-uniform "every scaling factor of this group is 1".
+// libdevice's erfc for arguments beyond the table (alpha r > 6: never reached with the reference's Ewald set-ups); kept out
+// of line so that its ~200 instructions are not replicated into every inlined copy of pair_energy
+__device__ __noinline__ double erfc_beyond_table(double x) { return erfc(x); }
+
 __device__ __forceinline__ void pair_energy(const DevParams& P, const double* __restrict__ etab, const double4* __restrict__ ffp, bool unit,
                                             double r2, int row, double scaling, double qq_scaled,
                                             double& e_vdw, double& e_real, int& flag)
@@ -204,7 +208,7 @@ __device__ __forceinline__ void pair_energy(const DevParams& P, const double* __
   {
     const double r = r2 * rinv;
     const double x = P.alpha * r;
-    const double ec = (P.erfc_table_ok || x < GBK_ERFC_XMAX) ? erfc_table_eval(etab, x) : erfc(x);
+    const double ec = (P.erfc_table_ok || x < GBK_ERFC_XMAX) ? erfc_table_eval(etab, x) : erfc_beyond_table(x);
     e_real = P.prefactor * qq_scaled * ec * rinv;
   }
 }

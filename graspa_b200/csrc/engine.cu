@@ -1106,7 +1106,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   // ---- stage B
   rc = ensure_ktab(e); if(rc) return rc;
-  const int warpsB = 8;
+  const int warpsB = GBK_EWALD_THREADS / 32;
   WidomB B;
   B.rec = e->d_rec.p; B.stage = e->d_stage.p; B.n = n; B.ms = ms; B.tq = e->dq.p + C.offset; B.tscoul = e->dscoul.p + C.offset;
   B.ktab = e->d_ktab.p; B.nact = e->nact; B.nact_pad = e->nact_pad; B.do_ewald = do_ewald ? 1 : 0;

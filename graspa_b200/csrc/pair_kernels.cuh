@@ -246,7 +246,7 @@ k_widom_pair(DevParams P, SysView Sg, SegList Lin, WidomA A)
       }
       __syncwarp();
       double e[4]; int fl;
-      widom_group<1, CELL>(P, X, A.comp, A.new_molid, 1, fb_c, e, fl);
+      widom_group<0, CELL>(P, X, A.comp, A.new_molid, 1, fb_c, e, fl);
       if(lane == t) { my_e[0] = e[0]; my_e[1] = e[1]; my_e[2] = e[2]; my_e[3] = e[3]; my_flag = fl; }
       __syncwarp();
     }
@@ -301,10 +301,10 @@ k_widom_pair(DevParams P, SysView Sg, SegList Lin, WidomA A)
         __syncwarp();
         double e[4]; int fl;
         const double* tc = chain_c + (size_t) o * cs * 3;
-        if(cs == 1)      widom_group<1, CELL>(P, X, A.comp, A.new_molid, cs, tc, e, fl);
-        else if(cs == 2) widom_group<2, CELL>(P, X, A.comp, A.new_molid, cs, tc, e, fl);
-        else if(cs == 3) widom_group<3, CELL>(P, X, A.comp, A.new_molid, cs, tc, e, fl);
-        else             widom_group<0, CELL>(P, X, A.comp, A.new_molid, cs, tc, e, fl);
+        // one instantiation for every chain size: the tile loop takes the atoms one by one anyway, and five inlined copies
+        // of the pair loops (17 400 SASS instructions in all) cost more in instruction-cache misses (stall_no_instruction
+        // 0.34 -> 0.26 per issue) than the register-resident trial atoms of the CS-specialised variants saved
+        widom_group<0, CELL>(P, X, A.comp, A.new_molid, cs, tc, e, fl);
         if(lane == o) { my_e[0] = e[0]; my_e[1] = e[1]; my_e[2] = e[2]; my_e[3] = e[3]; my_flag = fl; }
         __syncwarp();
       }
