@@ -1117,10 +1117,17 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   const size_t per_warpB = ((size_t) ms * (e->P.kmax[0] + e->P.kmax[1] + e->P.kmax[2] + 3) * sizeof(cplx) + (size_t) ms * 4 * sizeof(double) + 15) / 16 * 16;
   const size_t fixedB = 16 + warpsB * per_warpB + (size_t) warpsB * nbins * 12 * sizeof(double) + 64;
   const size_t ktab_bytes = ((size_t) e->nact_pad * 44 + 15) / 16 * 16;
+#ifdef GBK_EWALD_NO_STAGE
+  B.stage_ktab = 0;
+#else
   B.stage_ktab = (do_ewald && fixedB + ktab_bytes <= e->smem_optin) ? 1 : 0;
+#endif
   const size_t smemB = fixedB + (B.stage_ktab ? ktab_bytes : 0);
   if(smemB > e->smem_optin) return fail(GB_ERR_ARG, "Widom stage B shared memory exceeds the device limit");
-  const int gridB = (int) std::min<long long>((n + warpsB - 1) / warpsB, e->prop.multiProcessorCount);
+#ifndef GBK_EWALD_CTAS
+#define GBK_EWALD_CTAS 1
+#endif
+  const int gridB = (int) std::min<long long>((n + warpsB - 1) / warpsB, (long long) e->prop.multiProcessorCount * GBK_EWALD_CTAS);
   if(out8 && !outputs_on_device) { CUDA_TRY(e->d_out8.reserve((size_t) n * 8)); B.out8 = e->d_out8.p; } else B.out8 = out8;
   B.out_stage = nullptr;   // stage already lives in d_stage
   CUDA_TRY(e->d_partial.reserve((size_t) gridB * nbins * 12)); CUDA_TRY(e->d_sums.reserve((size_t) nbins * 12));

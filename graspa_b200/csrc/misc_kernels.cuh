@@ -135,7 +135,10 @@ struct WidomB
 #ifndef GBK_EWALD_THREADS
 #define GBK_EWALD_THREADS 384   // 12 warps per SM: 13.8 ms per 400 000 insertions against 15.8 ms with 8 and 16.3 ms with 16 (128-register cap)
 #endif
-__global__ void __launch_bounds__(GBK_EWALD_THREADS, 1)
+#ifndef GBK_EWALD_CTAS
+#define GBK_EWALD_CTAS 1
+#endif
+__global__ void __launch_bounds__(GBK_EWALD_THREADS, GBK_EWALD_CTAS)
 k_widom_ewald(DevParams P, WidomB B)
 {
   extern __shared__ __align__(16) unsigned char smem[];

@@ -534,10 +534,12 @@ inline void compute_fugacity(Deck& d)
   }
 }
 
-inline Deck load(const std::string& dir)
+inline Deck load(const std::string& dir, double pressure_override = -1.0, double temperature_override = -1.0)
 {
   Deck d;
   read_simulation_input(d, dir);
+  if(pressure_override >= 0.0) d.pressure_pa = pressure_override;          // one isotherm point per process (and per GPU)
+  if(temperature_override >= 0.0) d.temperature = temperature_override;
   read_force_field(d, dir);
   for(auto& c : d.comps) read_molecule(d, c, dir);
   read_framework_components(d, dir);

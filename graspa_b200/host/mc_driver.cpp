@@ -55,7 +55,8 @@ struct CompState
   MoveCount trans, rot, ins, del, reins, widom, idswap_add, idswap_remove;
   std::vector<MoveCount> idswap_to;             // IdentitySwap_Total_TO / _Acc_TO per destination component
   MoveCount trans_window, rot_window;           // TranslationTotal/Accepted are reset every 500 cycles
-  MoveCount trans_cum, rot_cum;                 // CumTranslationTotal/...: what the reference prints (print_statistics.cuh:41-44)
+  MoveCount trans_cum, rot_cum;
+  double load_sum = 0.0; long load_n = 0;       // production average of the number of molecules (one sample per cycle)                 // CumTranslationTotal/...: what the reference prints (print_statistics.cuh:41-44)
   long nmol = 0;
   bool has_charge = false;
   // Rosenbluth statistics per block: sum W, sum W^2, count; W-weighted widom energies
@@ -83,6 +84,7 @@ struct Sim
   double initial_framework_ewald = 0.0;           // SystemComponents.InitialFrameworkEwald
   int nblock = 5; long block_size = 1; bool production = false;
   long moves_done = 0;
+  int device = -1;                                // CUDA device of the engine (-1: the current one)
   bool fused = true;                              // one host round trip per move (gb_move_*); false: the stage calls
   double call_s[4] = {0, 0, 0, 0}; long call_n[4] = {0, 0, 0, 0};   // host time inside gb_move_{insertion,deletion,reinsertion,single_body}
   std::FILE* trace = nullptr;
@@ -105,7 +107,7 @@ inline void pool_update(Sim& S, size_t change) { S.pool_off += change; }
 void setup_engine(Sim& S)
 {
   deck::Deck& d = S.d;
-  GB(gb_engine_create(&S.e, -1));
+  GB(gb_engine_create(&S.e, S.device));
   const int n = d.ntypes();
   std::vector<double> zeros(n * n, 0.0);
   gb_forcefield ff{d.eps.data(), d.sigma.data(), zeros.data(), d.shift.data(), zeros.data(), d.cutoff_vdw * d.cutoff_vdw, d.cutoff_coul * d.cutoff_coul,
@@ -657,6 +659,7 @@ void run_phase(Sim& S, long cycles, bool production)
     if(steps < S.total_molecules) steps = S.total_molecules;
     if(S.d.use_max_step && steps > S.d.max_step_per_cycle) steps = S.d.max_step_per_cycle;
     for(long j = 0; j < steps; j++) run_move(S, i);
+    if(production) for(int c = S.nhost; c < S.ncomp; c++) { S.C[c].load_sum += (double) S.C[c].nmol; S.C[c].load_n++; }
     if(i % 500 == 0)
       for(int c = 1; c < S.ncomp; c++) { update_max(S.C[c].max_trans, S.C[c].trans_window, S.C[c].trans_cum, 5.0); update_max(S.C[c].max_rot, S.C[c].rot_window, S.C[c].rot_cum, 3.14); }
   }
@@ -861,7 +864,7 @@ int main(int argc, char** argv)
   if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--timing] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
   const std::string dir = argv[1];
   bool sequential_widom = false, staged = false, timing = false; const char* trace_path = nullptr;
-  long o_init = -1, o_equil = -1, o_prod = -1;
+  long o_init = -1, o_equil = -1, o_prod = -1; double o_pressure = -1.0, o_temperature = -1.0; int o_device = -1; long o_seed = -1;
   for(int i = 2; i < argc; i++)
   {
     const std::string a = argv[i];
@@ -872,9 +875,15 @@ int main(int argc, char** argv)
     else if(a == "--init" && i + 1 < argc) o_init = std::atol(argv[++i]);
     else if(a == "--equil" && i + 1 < argc) o_equil = std::atol(argv[++i]);
     else if(a == "--prod" && i + 1 < argc) o_prod = std::atol(argv[++i]);
+    else if(a == "--pressure" && i + 1 < argc) o_pressure = std::atof(argv[++i]);        // Pa: one isotherm point per process / GPU
+    else if(a == "--temperature" && i + 1 < argc) o_temperature = std::atof(argv[++i]);
+    else if(a == "--device" && i + 1 < argc) o_device = std::atoi(argv[++i]);
+    else if(a == "--seed" && i + 1 < argc) o_seed = std::atol(argv[++i]);
   }
   Sim S;
-  try { S.d = deck::load(dir); } catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
+  try { S.d = deck::load(dir, o_pressure, o_temperature); } catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
+  if(o_seed >= 0) S.d.random_seed = (int) o_seed;
+  S.device = o_device;
   if(o_init >= 0) S.d.init_cycles = o_init;
   if(o_equil >= 0) S.d.equil_cycles = o_equil;
   if(o_prod >= 0) S.d.prod_cycles = o_prod;
@@ -937,6 +946,11 @@ int main(int argc, char** argv)
   const long cycles = S.d.init_cycles + S.d.equil_cycles + S.d.prod_cycles;
   int64_t launches = 0; gb_launch_count(S.e, &launches, 0);
   std::printf("Work took %.6f seconds\n", secs);
+  std::printf("{\"pressure_pa\": %.6g, \"temperature\": %.6g, \"loading\": [", S.d.pressure_pa, S.d.temperature);
+  for(int c = S.nhost; c < S.ncomp; c++)
+    std::printf("%s{\"component\": \"%s\", \"molecules\": %ld, \"production_average\": %.6f}", c > S.nhost ? ", " : "", comp_name(S, c), S.C[c].nmol,
+                S.C[c].load_n ? S.C[c].load_sum / (double) S.C[c].load_n : (double) S.C[c].nmol);
+  std::printf("]}\n");
   std::printf("{\"moves\": %ld, \"cycles\": %ld, \"seconds\": %.6f, \"moves_per_s\": %.3f, \"cycles_per_s\": %.3f, \"widom_path\": \"%s\", \"move_calls\": \"%s\", \"rng_draws\": %llu, \"pool_refills\": %ld, \"kernel_launches\": %lld}\n",
               S.moves_done, cycles, secs, S.moves_done / secs, cycles / secs, batched ? "batched-exact" : "sequential", S.fused ? "fused" : "staged",
               (unsigned long long) S.rng.consumed(), S.pool_rounds, (long long) launches);

@@ -494,3 +494,21 @@ def test_block_pockets_in_the_move_kernels(gpu_engine_factory, oracle):
     e, f, _ = oracle.trial_energies(box, ff, s, 10, 1, tr, comp, nmol)
     assert fb["n_survivors"] == int((f == 0).sum())
     eng.close()
+
+
+def test_isotherm_points_as_independent_boxes():
+    """graspa_b200.boxes: one host-driver process per isotherm point, dealt over the visible GPUs, nothing exchanged.
+    Loading must grow with pressure and every box must conserve energy (running sum vs recomputed totals)."""
+    import os
+    import torch
+    from graspa_b200.boxes import run_boxes, DRIVER, ROOT
+    deck = os.path.join(ROOT, "oracle", "_ref", "examples", "CO2-MFI")
+    if not (os.path.exists(DRIVER) and os.path.isdir(deck)):
+        pytest.skip("host driver / example deck not built")
+    pts = [{"pressure": 1.0e3}, {"pressure": 1.0e5}]
+    res, wall = run_boxes(deck, pts, gpus=max(1, min(2, torch.cuda.device_count())), init=300, prod=300)
+    assert all(r["returncode"] == 0 for r in res), res
+    lo, hi = res[0]["loading"][0]["production_average"], res[1]["loading"][0]["production_average"]
+    assert hi > lo >= 0.0
+    assert all(abs(r["energy_drift"]) < 1e-6 for r in res)
+    assert abs(res[0]["pressure_pa"] - 1.0e3) < 1e-9 and abs(res[1]["pressure_pa"] - 1.0e5) < 1e-9
