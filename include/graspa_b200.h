@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GB_ABI_VERSION 2
+#define GB_ABI_VERSION 3
 
 enum {
   GB_OK = 0,
