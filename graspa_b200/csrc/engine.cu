@@ -109,6 +109,7 @@ struct gb_engine
   DevBuf<double> d_mv, d_ewpos; DevBuf<int> d_mvi;
   int last_fb_selected = 0, last_cbmc_comp = -1; long long last_cbmc_selected = 0;
   int sb_comp = -1, sb_type = -1; long long sb_molecule = 0;
+  double lambda_scale[2] = {1.0, 1.0};            // new scaling factors of the last gb_lambda_change_delta
   bool committed = false;                // device slots changed by accept calls: the device is authoritative
 
   long long launches = 0;
@@ -824,7 +825,7 @@ int gb_trial_energies(gb_engine* e, int32_t ntr, int32_t cs, const double* pos, 
 // ---------------------------------------------------------------------------------------------- Ewald delta
 // enqueue the Ewald delta kernel (no synchronisation): result {same, 2*cross} goes to d_result2, skipped when *d_dep == 0
 static int ewald_delta_enqueue(gb_engine* e, bool framework_moved, int nold, int nnew, const double* d_pos3, const double* d_qeff,
-                               double* d_result2, const double* d_dep)
+                               double* d_result2, const double* d_dep, bool same_is_temp = false)
 {
   const int n = nold + nnew;
   if(n <= 0 || n > GBK_EW_MAX_ATOMS) return fail(GB_ERR_ARG, "Ewald delta supports 1..64 moved atoms");
@@ -832,6 +833,7 @@ static int ewald_delta_enqueue(gb_engine* e, bool framework_moved, int nold, int
   A.pos3 = d_pos3; A.qeff = d_qeff; A.nold = nold; A.nnew = nnew;
   A.K.kpack = e->d_kpack.p; A.K.temp = e->d_ktemp.p; A.K.slot = e->d_kslot.p; A.K.nact = e->nact;
   A.same_sf = framework_moved ? e->d_sf[e->i_fw].p : e->d_sf[e->i_ads].p;
+  if(same_is_temp) A.same_sf = e->d_sf[e->i_tmp].p;   // UseTempVector (second step of a CBCF deletion, Ewald_Energy_Functions.h:713-716): read and written per k in place
   A.cross_sf = framework_moved ? e->d_sf[e->i_ads].p : e->d_sf[e->i_fw].p;
   A.temp_sf = e->d_sf[e->i_tmp].p;     // only active k are written; inactive entries of all three arrays stay zero
   const int nblk = (e->nact + 127) / 128;
@@ -847,10 +849,11 @@ static int ewald_delta_enqueue(gb_engine* e, bool framework_moved, int nold, int
   return GB_OK;
 }
 
-static int ewald_delta_launch(gb_engine* e, bool framework_moved, int nold, int nnew, const double* d_pos3, const double* d_qeff, double out[2])
+static int ewald_delta_launch(gb_engine* e, bool framework_moved, int nold, int nnew, const double* d_pos3, const double* d_qeff, double out[2],
+                              bool same_is_temp = false)
 {
   if(e->nact == 0) { out[0] = 0.0; out[1] = 0.0; return GB_OK; }
-  int rc = ewald_delta_enqueue(e, framework_moved, nold, nnew, d_pos3, d_qeff, e->d_result.p, nullptr); if(rc) return rc;
+  int rc = ewald_delta_enqueue(e, framework_moved, nold, nnew, d_pos3, d_qeff, e->d_result.p, nullptr, same_is_temp); if(rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(e->h_pinned, e->d_result.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   out[0] = e->h_pinned[0]; out[1] = e->h_pinned[1];

@@ -542,6 +542,20 @@ __global__ void k_copy_buffer(MoveBufs B, int dst_buf, int src_buf, int n)
   for(int k = 0; k < 9; k++) B.mol(dst_buf, k)[i] = B.mol(src_buf, k)[i];
   B.mol_type(dst_buf)[i] = B.mol_type(src_buf)[i];
 }
+// overwrite the two scaling factors of a molecule buffer (the NEW side of a lambda change: same atoms, new lambda)
+__global__ void k_set_buffer_scale(MoveBufs B, int buf, int n, double scale, double scoul)
+{
+  const int i = threadIdx.x;
+  if(i >= n) return;
+  B.mol(buf, 7)[i] = scale; B.mol(buf, 8)[i] = scoul;
+}
+// commit of an accepted lambda change: the molecule's slots take the new scaling factors (mc_cbcfc.h acceptance)
+__global__ void k_commit_scale(SlotArrays S, int dst, int n, double scale, double scoul)
+{
+  const int i = threadIdx.x;
+  if(i >= n) return;
+  S.scale[dst + i] = scale; S.scoul[dst + i] = scoul;
+}
 __global__ void k_load_buffer(DevParams P, MoveBufs B, int dst_buf, CompView C, long long start, int n, const double* pos3_override)
 {
   const int i = threadIdx.x;

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GB_ABI_VERSION 3
+#define GB_ABI_VERSION 4
 
 enum {
   GB_OK = 0,
@@ -247,6 +247,21 @@ int  gb_ewald_delta_identity_swap(gb_engine* e, int32_t old_component, int32_t n
 int  gb_ewald_delta_explicit(gb_engine* e, int32_t component_is_framework, int32_t n_old, int32_t n_new, const double* pos,
                              const double* charge, const double* scale_coul, double out[2]);
 int  gb_ewald_commit(gb_engine* e, int32_t component);                 /* Update_Vector_Ewald */
+
+/* ------------------------------------------------------------------------------------------------
+ * CB/CFC lambda change of one (fractional) molecule  (replaces, inside CBCF_LambdaChange mc_cbcfc.h:20-140:
+ *   Prepare_LambdaChange<<<>>> + Calculate_Single_Body_Energy_VDWReal_LambdaChange<<<>>> VDW_Coulomb.cu:843-1036 + the host
+ *   sum of Blocksum; GPU_EwaldDifference_LambdaChange Ewald_Energy_Functions.h:637-788; and the acceptance's scale update.
+ *   The Wang-Landau / lambda-bin bookkeeping of mc_cbcfc.h stays with the kept driver.)
+ * ------------------------------------------------------------------------------------------------ */
+/* delta = E(new_scale) - E(stored scale) of the molecule against every other atom; new_scale = {vdw, coulomb} as
+ * Lambda.SET_SCALE returns them; overlap = flag[0] (from the NEW lambda only, :993-994) */
+int  gb_lambda_change_delta(gb_engine* e, int32_t component, int64_t molecule, const double new_scale[2], gb_move_energy* delta, int32_t* overlap);
+/* {same-type, 2*cross-type}, rigid exclusion x (new^2 - old^2) taken out (:778-780); use_temp_vector: the second step of a
+ * CBCF deletion continues from tempEik (:713-716).  Call after gb_lambda_change_delta of the same molecule. */
+int  gb_ewald_delta_lambda_change(gb_engine* e, int32_t component, const double old_scale[2], const double new_scale[2],
+                                  int32_t use_temp_vector, double out[2]);
+int  gb_accept_lambda_change(gb_engine* e, int32_t component, int64_t molecule, const double new_scale[2]);
 
 /* ------------------------------------------------------------------------------------------------
  * tail corrections  (replaces TailCorrection_Energy_Functions.h:3-113)

@@ -512,3 +512,45 @@ def test_isotherm_points_as_independent_boxes():
     assert hi > lo >= 0.0
     assert all(abs(r["energy_drift"]) < 1e-6 for r in res)
     assert abs(res[0]["pressure_pa"] - 1.0e3) < 1e-9 and abs(res[1]["pressure_pa"] - 1.0e5) < 1e-9
+
+
+def test_cbcfc_lambda_change_vs_oracle(gpu_engine_factory, oracle):
+    """CB/CFC lambda change of one molecule (CBCF_LambdaChange mc_cbcfc.h:20-140): VDW + real delta of
+    Calculate_Single_Body_Energy_VDWReal_LambdaChange (VDW_Coulomb.cu:843-1036, soft-core LJ of maths.cuh:452-494), the
+    Fourier delta of GPU_EwaldDifference_LambdaChange with its exclusion term (Ewald_Energy_Functions.h:637-788), and the
+    commit: after accepting lambda = 0.35 the total energy recomputed from scratch moves by the reported delta; going on
+    from there to lambda = 0.8 starts from the stored fractional scaling factors."""
+    box, ff, s, z, eng = _setup(gpu_engine_factory, "B")
+    comp = 1; ms = 3; mol = 6
+    o = int(s.offsets[comp]); a0 = o + mol * ms
+    eng.total_ewald(store=True)
+    E0 = _totals(eng)
+    excl = float(z["excl"][0]) + float(z["excl"][1])
+    old_scale = (1.0, 1.0); running = 0.0
+    cur = s
+    for new_scale in ((0.35, 0.35 ** 5), (0.8, 0.8 ** 5), (1.0, 1.0)):
+        d, ov = eng.lambda_change_delta(comp, mol, new_scale)
+        pos = cur.pos[a0:a0 + ms]; q = cur.charge[a0:a0 + ms]; ty = cur.type[a0:a0 + ms]
+        old = TrialAtoms(pos, q, ty, np.full(ms, old_scale[0]), np.full(ms, old_scale[1]))
+        new = TrialAtoms(pos, q, ty, np.full(ms, new_scale[0]), np.full(ms, new_scale[1]))
+        ref, ov_ref = oracle.single_body_delta(box, ff, cur, comp, mol, old, new)
+        got = np.array([d["HHVDW"], d["HHReal"], d["HGVDW"], d["HGReal"], d["GGVDW"], d["GGReal"]])
+        assert bool(ov) == bool(ov_ref)
+        assert _close(got, ref, scale=max(1.0, float(np.abs(ref).max())))
+        ew = eng.ewald_delta_lambda_change(comp, old_scale, new_scale)
+        sa, sf, _ = eng.download_structure_factors()
+        ref_ew, _, _ = oracle.ewald_delta(box, np.concatenate([pos, pos]), np.concatenate([q, q]),
+                                          np.concatenate([np.full(ms, old_scale[1]), np.full(ms, new_scale[1])]), ms, ms, sa, sf)
+        ref_ew[0] -= excl * (new_scale[1] ** 2 - old_scale[1] ** 2)
+        assert _close(ew, ref_ew, scale=max(1.0, float(np.abs(ref_ew).max())))
+        eng.accept_lambda_change(comp, mol, new_scale)
+        running += float(got.sum() + ew[0] + ew[1])
+        E1 = _totals(eng)
+        assert abs((E1 - E0) - running) <= 1e-9 * max(1.0, abs(E1)), (new_scale, E1 - E0, running)
+        # the oracle's copy of the system follows the commit
+        sc = cur.scale.copy(); scc = cur.scale_coul.copy(); sc[a0:a0 + ms] = new_scale[0]; scc[a0:a0 + ms] = new_scale[1]
+        from graspa_b200.types import System
+        cur = System(cur.nhost, cur.natoms, cur.molsize, cur.pos, cur.charge, cur.type, cur.molid, sc, scc, alloc=cur.alloc)
+        old_scale = new_scale
+    assert abs(running) <= 1e-7 * max(1.0, abs(E0))          # back at lambda = 1: the three deltas cancel
+    eng.close()
