@@ -691,6 +691,33 @@ int gb_download_atoms(gb_engine* e, int32_t c, double* pos, double* scale, doubl
   return GB_OK;
 }
 
+// Snapshot of LIVE molecules only (restart / movie writers, write_data.h:109-263, axpy.cu:25-69): the reference copies every
+// component's Allocate_size slots back (10 240 per adsorbate by default); a writer needs size = N_molecules x Molsize.
+int gb_snapshot_molecules(gb_engine* e, int32_t c, int64_t first, int64_t count, double* pos, double* charge, double* scale, double* scale_coul)
+{
+  int rc = ready(e); if(rc) return rc;
+  if(c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "component out of range");
+  const Comp& C = e->comps[c];
+  const int64_t nmol = C.natoms / C.molsize;
+  if(first < 0 || count < 0 || first + count > nmol) return fail(GB_ERR_ARG, "molecule range outside the live molecules");
+  const size_t n = (size_t) count * C.molsize, o = (size_t) C.offset + (size_t) first * C.molsize;
+  if(n == 0) return GB_OK;
+  std::vector<double> t(n * 3);
+  const size_t b = n * sizeof(double);
+  if(pos)
+  {
+    CUDA_TRY(cudaMemcpyAsync(t.data(), e->dx.p + o, b, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(t.data() + n, e->dy.p + o, b, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(t.data() + 2 * n, e->dz.p + o, b, cudaMemcpyDeviceToHost, e->stream));
+  }
+  if(charge) CUDA_TRY(cudaMemcpyAsync(charge, e->dq.p + o, b, cudaMemcpyDeviceToHost, e->stream));
+  if(scale) CUDA_TRY(cudaMemcpyAsync(scale, e->dscale.p + o, b, cudaMemcpyDeviceToHost, e->stream));
+  if(scale_coul) CUDA_TRY(cudaMemcpyAsync(scale_coul, e->dscoul.p + o, b, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if(pos) for(size_t i = 0; i < n; i++) { pos[3 * i] = t[i]; pos[3 * i + 1] = t[n + i]; pos[3 * i + 2] = t[2 * n + i]; }
+  return GB_OK;
+}
+
 int gb_upload_structure_factors(gb_engine* e, const double* ads, const double* fw)
 {
   if(!e) return fail(GB_ERR_ARG, "null engine");

@@ -25,7 +25,7 @@ i32p = C.POINTER(C.c_int32)
 # every symbol include/graspa_b200.h declares (tests check the library exports all of them)
 DECLARED_SYMBOLS = [
     "gb_abi_version", "gb_last_error", "gb_engine_create", "gb_engine_destroy", "gb_device_info", "gb_synchronize", "gb_stream",
-    "gb_upload_forcefield", "gb_upload_box", "gb_set_components", "gb_upload_atoms", "gb_download_atoms",
+    "gb_upload_forcefield", "gb_upload_box", "gb_set_components", "gb_upload_atoms", "gb_download_atoms", "gb_snapshot_molecules",
     "gb_upload_structure_factors", "gb_download_structure_factors", "gb_set_exclusion_constants", "gb_upload_random_pool", "gb_set_block_pockets",
     "gb_set_cbmc", "gb_get_pseudo_atom_counts", "gb_cbmc_first_bead", "gb_cbmc_chain", "gb_cbmc_grown_positions", "gb_reinsertion_store", "gb_move_insertion", "gb_move_deletion", "gb_move_reinsertion", "gb_move_single_body",
     "gb_trial_energies", "gb_single_body_propose", "gb_single_body_delta", "gb_single_body_delta_explicit",
@@ -259,6 +259,12 @@ class Engine:
         m = GbMoveEnergy(); self._chk(self.lib.gb_total_ewald(self.h, C.c_int32(int(store)), C.byref(m))); return m.as_dict()
 
     # ------------------------------------------------------------ single-move path
+    def snapshot_molecules(self, comp, first, count):
+        n = int(count) * int(self.system.molsize[comp])
+        pos = np.zeros((n, 3)); q = np.zeros(n); sc = np.zeros(n); scc = np.zeros(n)
+        self._chk(self.lib.gb_snapshot_molecules(self.h, C.c_int32(comp), C.c_int64(first), C.c_int64(count), _p(pos, f64p), _p(q, f64p), _p(sc, f64p), _p(scc, f64p)))
+        return dict(pos=pos, charge=q, scale=sc, scale_coul=scc)
+
     def set_block_pockets(self, comp, centers, radii, invert=False):
         centers = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3); radii = np.ascontiguousarray(radii, dtype=np.float64)
         self._chk(self.lib.gb_set_block_pockets(self.h, C.c_int32(comp), C.c_int32(len(radii)), _p(centers, f64p), _p(radii, f64p), C.c_int32(int(invert))))

@@ -52,6 +52,8 @@ struct Component
   double p_translation = 0, p_rotation = 0, p_widom = 0, p_reinsertion = 0, p_identity = 0, p_swap = 0;   // raw inputs
   int create_molecules = 0;
   bool use_pr_eos = false;
+  // molecules read from RestartInitial/System_0/restartfile (RestartFile yes): positions 3 x n, charges n; molecule-major
+  std::vector<double> restart_pos, restart_charge;
   // block pockets (BlockPockets yes / BlockPocketsFilename X / InvertBlockPockets, read_data.cpp:2532-2575)
   bool use_pockets = false, invert_pockets = false; std::string pocket_file;
   std::vector<double> pocket_centers, pocket_radii;           // replicated, Cartesian (ReplicateBlockPockets :3362-3454)
@@ -71,7 +73,7 @@ struct Deck
   int n_trial_positions = 8, n_trial_orientations = 8;            // WidomStruct defaults, data_struct.h:1275-1276
   long adsorbate_allocate = 10240;
   std::string framework_name; int unitcells[3] = {1, 1, 1};
-  bool use_cif_charges = false, no_charges = true;
+  bool use_cif_charges = false, no_charges = true, restart_file = false;
   double temperature = 300.0, pressure_pa = 0.0;
   double overlap = 1e5, cutoff_vdw = 12.0, cutoff_coul = 12.0, ewald_precision = 1e-6;
   bool lammps_ewald = false; double lammps_alpha = 0.0; int lammps_kmax[3] = {0, 0, 0};
@@ -173,6 +175,7 @@ inline void read_simulation_input(Deck& d, const std::string& dir)
     else if(has("NumberOfProductionCycles")) d.prod_cycles = std::stol(t[1]);
     else if(has("SeparateFrameworkComponents")) d.separate_framework = ieq(t[1], "yes");
     else if(has("NumberofFrameworkComponents")) d.n_framework_components = std::stoi(t[1]);
+    else if(has("RestartFile")) d.restart_file = ieq(t[1], "yes");
     else if(has("UseMaxStep")) d.use_max_step = ieq(t[1], "yes");
     else if(has("MaxStepPerCycle")) d.max_step_per_cycle = std::stol(t[1]);
     else if(has("RandomSeed")) d.random_seed = std::stoi(t[1]);
@@ -466,6 +469,57 @@ inline void setup_ewald(Deck& d)
   d.recip_cutoff = std::pow(1.05 * (double) m, 2);
 }
 
+// PBC(), maths.cuh:427-450
+inline void min_image(const Deck& d, double* v)
+{
+  const double* I = d.inv; const double* C = d.cell;
+  const bool cubic = !((std::fabs(C[3]) + std::fabs(C[6]) + std::fabs(C[7])) > 1e-10);
+  if(cubic)
+  {
+    v[0] -= static_cast<int>(v[0] * I[0] + ((v[0] >= 0.0) ? 0.5 : -0.5)) * C[0];
+    v[1] -= static_cast<int>(v[1] * I[4] + ((v[1] >= 0.0) ? 0.5 : -0.5)) * C[4];
+    v[2] -= static_cast<int>(v[2] * I[8] + ((v[2] >= 0.0) ? 0.5 : -0.5)) * C[8];
+    return;
+  }
+  double sx = I[0] * v[0] + I[3] * v[1] + I[6] * v[2], sy = I[1] * v[0] + I[4] * v[1] + I[7] * v[2], sz = I[2] * v[0] + I[5] * v[1] + I[8] * v[2];
+  sx -= static_cast<int>(sx + ((sx >= 0.0) ? 0.5 : -0.5)); sy -= static_cast<int>(sy + ((sy >= 0.0) ? 0.5 : -0.5)); sz -= static_cast<int>(sz + ((sz >= 0.0) ? 0.5 : -0.5));
+  v[0] = C[0] * sx + C[3] * sy + C[6] * sz; v[1] = C[1] * sx + C[4] * sy + C[7] * sz; v[2] = C[2] * sx + C[5] * sy + C[8] * sz;
+}
+
+// RestartFileParser, read_data.cpp:3000-3221 (RASPA-2 restart file): per adsorbate component the block starts two lines
+// after "Component: <i>"; `interval` position lines, then velocity, force, charge and scaling blocks of the same length.
+// Atoms other than the first of a molecule are re-wrapped to the nearest image of the first (:3147-3160).
+inline void read_restart(Deck& d, const std::string& dir)
+{
+  if(!d.restart_file) return;
+  auto L = read_lines(dir + "/RestartInitial/System_0/restartfile");
+  for(size_t ci = 0; ci < d.comps.size(); ci++)
+  {
+    Component& c = d.comps[ci];
+    const std::string key = "Component: " + std::to_string(ci);
+    size_t start = 0; long nmol = 0; bool found = false;
+    for(size_t k = 0; k < L.size(); k++)
+      if(L[k].find(key) == 0) { nmol = std::stol(terms(L[k]).at(3)); start = k + 2; found = true; break; }
+    if(!found || nmol == 0) continue;
+    const size_t ms = (size_t) c.ms(), interval = (size_t) nmol * ms;
+    if(start + 5 * interval > L.size()) throw std::runtime_error("restart file shorter than its molecule count says");
+    c.restart_pos.resize(3 * interval); c.restart_charge.resize(interval);
+    double first[3] = {0, 0, 0};
+    for(size_t a = 0; a < interval; a++)
+    {
+      auto t = terms(L[start + a]);
+      if(t.size() < 6 || t[0].find("Adsorbate-atom-position") != 0) throw std::runtime_error("Cannot find matching strings in the range for reading positions!");
+      double p[3] = {std::stod(t[3]), std::stod(t[4]), std::stod(t[5])};
+      if(std::stol(t[2]) == 0) { first[0] = p[0]; first[1] = p[1]; first[2] = p[2]; }
+      else { double v[3] = {p[0] - first[0], p[1] - first[1], p[2] - first[2]}; min_image(d, v); for(int k = 0; k < 3; k++) p[k] = first[k] + v[k]; }
+      for(int k = 0; k < 3; k++) c.restart_pos[3 * a + k] = p[k];
+      c.restart_charge[a] = std::stod(terms(L[start + 3 * interval + a]).at(3));
+      const double lambda = std::stod(terms(L[start + 4 * interval + a]).at(3));
+      if(lambda < 1.0) throw std::runtime_error("restart file holds a fractional molecule: that needs the CB/CFC driver");
+    }
+  }
+}
+
 // ComputeFugacity, equations_of_state.h:121-330 (Peng-Robinson mixture, no binary interaction parameters) with the
 // cubic solver of :61-118.  Runs when any adsorbate asks for "FugacityCoefficient PR-EOS" and then overrides the
 // coefficients of EVERY adsorbate, as the reference does (:137-147).
@@ -545,6 +599,7 @@ inline Deck load(const std::string& dir, double pressure_override = -1.0, double
   read_framework_components(d, dir);
   read_framework(d, dir);
   read_block_pockets(d, dir);
+  read_restart(d, dir);
   if(!d.no_charges) setup_ewald(d);
   // Setup_Box_Temperature_Pressure, fxn_main.h:115-127 with Units data_struct.h:58-68
   const double kB = 1.380649e-23, mass_unit = 1.6605402e-27, length_unit = 1e-10, time_unit = 1e-12;

@@ -153,8 +153,23 @@ void setup_engine(Sim& S)
     std::vector<uint64_t> ty(ms), mol(ms, 0); std::vector<double> one(ms, 1.0);
     for(int i = 0; i < ms; i++) ty[i] = (uint64_t) M.type[i];
     // slot 0 holds the template molecule (read_data.cpp:2122-2147); Allocate_size = AdsorbateAllocateSpace (fxn_main.h:46-62)
-    gb_atoms a{M.pos.data(), one.data(), M.charge.data(), one.data(), ty.data(), mol.data(), ms, 0, (int64_t) std::max<long>(d.adsorbate_allocate, ms), ms};
-    GB(gb_upload_atoms(S.e, (int32_t) (c + S.nhost), &a));
+    const long nrest = (long) (M.restart_charge.size() / (size_t) std::max(ms, 1));
+    if(nrest > 0)
+    {
+      // RestartFileParser (read_data.cpp:3000-3221): the molecules of the restart file fill the slots from 0
+      const size_t n = (size_t) nrest * ms;
+      std::vector<uint64_t> rty(n), rmol(n); std::vector<double> rone(n, 1.0);
+      for(size_t i = 0; i < n; i++) { rty[i] = (uint64_t) M.type[i % ms]; rmol[i] = (uint64_t) (i / ms); }
+      gb_atoms a{M.restart_pos.data(), rone.data(), M.restart_charge.data(), rone.data(), rty.data(), rmol.data(), (int64_t) n, (int64_t) n,
+                 (int64_t) std::max<long>(d.adsorbate_allocate, (long) n), ms};
+      GB(gb_upload_atoms(S.e, (int32_t) (c + S.nhost), &a));
+      S.C[c + S.nhost].nmol = nrest; S.total_molecules += nrest;
+    }
+    else
+    {
+      gb_atoms a{M.pos.data(), one.data(), M.charge.data(), one.data(), ty.data(), mol.data(), ms, 0, (int64_t) std::max<long>(d.adsorbate_allocate, ms), ms};
+      GB(gb_upload_atoms(S.e, (int32_t) (c + S.nhost), &a));
+    }
   }
   GB(gb_set_cbmc(S.e, d.n_trial_positions, d.n_trial_orientations, d.beta));
   // rigid exclusion constants from the template molecule, Calculate_Exclusion_Energy_Rigid ewald_preparation.h:261-298, 351-366
@@ -806,6 +821,56 @@ void print_widom(Sim& S, int comp)
   std::printf("Averaged Henry Coefficient [mol/kg/Pa]: %.10g +/- %.10g\n", ah, 2.0 * std::pow(std::fmax(ah2 - ah * ah, 0.0), 0.5));
 }
 
+// RASPA-2 restart file of the final configuration (the layout of write_data.h:109-263: cell, move maxima, components, then
+// per component the position / velocity / force / charge / scaling / fixed blocks), from one device-to-host snapshot of the
+// LIVE atoms of each adsorbate component.
+void write_restart(Sim& S, const std::string& path)
+{
+  std::FILE* f = std::fopen(path.c_str(), "w");
+  if(!f) { std::fprintf(stderr, "graspa_b200_mc: cannot write %s\n", path.c_str()); return; }
+  const double* C = S.d.cell;
+  std::fprintf(f, "Cell info:\n========================================================================\nnumber-of-unit-cells: 1 1 1\n");
+  const char* nm[3] = {"a", "b", "c"};
+  for(int k = 0; k < 3; k++) std::fprintf(f, "unit-cell-vector-%s: %.15g %.15g %.15g\n", nm[k], C[3 * k], C[3 * k + 1], C[3 * k + 2]);
+  std::fprintf(f, "\n");
+  for(int k = 0; k < 3; k++) std::fprintf(f, "cell-vector-%s: %.15g %.15g %.15g\n", nm[k], C[3 * k], C[3 * k + 1], C[3 * k + 2]);
+  std::fprintf(f, "\ncell-lengths: %.15g %.15g %.15g \ncell-angles: 90 90 90 \n\n\n", C[0], C[4], C[8]);
+  std::fprintf(f, "Maximum changes for MC-moves:\n========================================================================\n"
+                  "Maximum-volume-change: 0.006250\nMaximum-Gibbs-volume-change: 0.025000\n"
+                  "Maximum-box-shape-change: 0.100000 0.100000 0.100000, 0.100000 0.100000 0.100000, 0.100000 0.100000 0.100000\n\n\n");
+  std::fprintf(f, "Acceptance targets for MC-moves:\n========================================================================\n"
+                  "Target-volume-change: 0.500000\nTarget-box-shape-change: 0.500000\nTarget-Gibbs-volume-change: 0.500000\n\n\n");
+  long nads = 0;
+  for(int c = S.nhost; c < S.ncomp; c++) nads += S.C[c].nmol;
+  std::fprintf(f, "Components: %d (Adsorbates %ld, Cations 0)\n========================================================================\n", S.ncomp - S.nhost, nads);
+  for(int c = S.nhost; c < S.ncomp; c++)
+  {
+    const int k = c - S.nhost; const CompState& X = S.C[c];
+    std::fprintf(f, "Components %d (%s) \n\n", k, comp_name(S, c));
+    std::fprintf(f, "Maximum-translation-change component %d: %.6f %.6f %.6f\n", k, X.max_trans[0], X.max_trans[1], X.max_trans[2]);
+    std::fprintf(f, "Maximum-translation-in-plane-change component %d: 0.000000,0.000000,0.000000\n", k);
+    std::fprintf(f, "Maximum-rotation-change component %d: %.6f %.6f %.6f\n\n", k, X.max_rot[0], X.max_rot[1], X.max_rot[2]);
+  }
+  std::fprintf(f, "Reactions: 0\n");
+  long prev = 0;
+  for(int c = S.nhost; c < S.ncomp; c++)
+  {
+    const int ms = comp_ms(S, c); const long nmol = S.C[c].nmol; const size_t n = (size_t) nmol * ms;
+    std::vector<double> pos(3 * std::max<size_t>(n, 1)), sc(std::max<size_t>(n, 1)), q(std::max<size_t>(n, 1));
+    GB(gb_snapshot_molecules(S.e, c, 0, nmol, pos.data(), q.data(), sc.data(), nullptr));     // live molecules only
+    std::fprintf(f, "\nComponent: %d   Adsorbate %ld molecules of %s\n------------------------------------------------------------------------\n",
+                 c - S.nhost, nmol, comp_name(S, c));
+    for(size_t j = 0; j < n; j++) std::fprintf(f, "Adsorbate-atom-position: %ld %zu %.15g  %.15g  %.15g\n", prev + (long) (j / ms), j % ms, pos[3 * j], pos[3 * j + 1], pos[3 * j + 2]);
+    for(size_t j = 0; j < n; j++) std::fprintf(f, "Adsorbate-atom-velocity: %ld %zu 0  0  0\n", prev + (long) (j / ms), j % ms);
+    for(size_t j = 0; j < n; j++) std::fprintf(f, "Adsorbate-atom-force: %ld %zu 0  0  0\n", prev + (long) (j / ms), j % ms);
+    for(size_t j = 0; j < n; j++) std::fprintf(f, "Adsorbate-atom-charge: %ld %zu %.15g\n", prev + (long) (j / ms), j % ms, q[j]);
+    for(size_t j = 0; j < n; j++) std::fprintf(f, "Adsorbate-atom-scaling: %ld %zu %.15g\n", prev + (long) (j / ms), j % ms, sc[j]);
+    for(size_t j = 0; j < n; j++) std::fprintf(f, "Adsorbate-atom-fixed: %ld %zu 0 0 0\n", prev + (long) (j / ms), j % ms);
+    prev += nmol;
+  }
+  std::fclose(f);
+}
+
 Energy total_energy(Sim& S)
 {
   gb_move_energy v, w; double tail = 0.0;
@@ -863,7 +928,7 @@ int main(int argc, char** argv)
   }
   if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--timing] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
   const std::string dir = argv[1];
-  bool sequential_widom = false, staged = false, timing = false; const char* trace_path = nullptr;
+  bool sequential_widom = false, staged = false, timing = false; const char* trace_path = nullptr; const char* restart_out = nullptr;
   long o_init = -1, o_equil = -1, o_prod = -1; double o_pressure = -1.0, o_temperature = -1.0; int o_device = -1; long o_seed = -1;
   for(int i = 2; i < argc; i++)
   {
@@ -879,6 +944,7 @@ int main(int argc, char** argv)
     else if(a == "--temperature" && i + 1 < argc) o_temperature = std::atof(argv[++i]);
     else if(a == "--device" && i + 1 < argc) o_device = std::atoi(argv[++i]);
     else if(a == "--seed" && i + 1 < argc) o_seed = std::atol(argv[++i]);
+    else if(a == "--write-restart" && i + 1 < argc) restart_out = argv[++i];
   }
   Sim S;
   try { S.d = deck::load(dir, o_pressure, o_temperature); } catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
@@ -924,6 +990,7 @@ int main(int argc, char** argv)
 
   const Energy E1 = total_energy(S);
   print_energy("FINAL  ", E1);
+  if(restart_out) write_restart(S, restart_out);
   Energy D = E1; D.add(E0, -1.0);
   print_energy("RUNNING", S.running);
   std::printf("ENERGY DRIFT (FINAL - INITIAL - RUNNING) Total Energy: %.6e\n", D.total() - S.running.total());

@@ -135,6 +135,10 @@ int  gb_upload_atoms(gb_engine* e, int32_t component, const gb_atoms* atoms);
 /* Atoms of one component back to the host (restart writers, write_data.h:109-263).  Arrays sized n_alloc. */
 int  gb_download_atoms(gb_engine* e, int32_t component, double* pos, double* scale, double* charge, double* scale_coul,
                        uint64_t* type, uint64_t* molid, int64_t* n_live);
+/* Snapshot of `count` LIVE molecules starting at molecule `first` (positions 3 x n, charge / scale / scale_coul n, any may be
+ * NULL): what the RASPA-2 restart and LAMMPS movie writers need (write_data.h:109-263, axpy.cu:25-69) without copying the
+ * component's whole Allocate_size back. */
+int  gb_snapshot_molecules(gb_engine* e, int32_t component, int64_t first, int64_t count, double* pos, double* charge, double* scale, double* scale_coul);
 /* stored structure factors, nvec complex (re,im); Allocate_Copy_Ewald_Vector fxn_main.h:235-280 */
 int  gb_upload_structure_factors(gb_engine* e, const double* adsorbate_eik, const double* framework_eik);
 int  gb_download_structure_factors(gb_engine* e, double* adsorbate_eik, double* framework_eik, double* temp_eik);

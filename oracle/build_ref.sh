@@ -47,6 +47,14 @@ if [ "$WHAT" = "all" ] || [ "$WHAT" = "examples" ]; then
         \( -name '*.def' -o -name '*.cif' -o -name '*.block' -o -name 'simulation.input' \) \
         -exec cp {} "$OUT/examples/$ex/" \;
   done
+  # the NIST SPC/E known-answer decks: inputs + the RASPA-2 restart file they start from
+  for b in 1 2 3 4; do
+    d="$OUT/examples/Reference_NIST_SPCE/Box-$b"
+    mkdir -p "$d/RestartInitial/System_0"
+    find "$REF/Examples/Reference_NIST_SPCE/Box-$b" -maxdepth 1 -type f \
+        \( -name '*.def' -o -name "Box-$b.cif" -o -name 'simulation.input' \) -exec cp {} "$d/" \;
+    cp "$REF/Examples/Reference_NIST_SPCE/Box-$b/RestartInitial/System_0/restartfile" "$d/RestartInitial/System_0/"
+  done
 fi
 
 if [ "$WHAT" = "all" ] || [ "$WHAT" = "cuda" ]; then

@@ -554,3 +554,33 @@ def test_cbcfc_lambda_change_vs_oracle(gpu_engine_factory, oracle):
         old_scale = new_scale
     assert abs(running) <= 1e-7 * max(1.0, abs(E0))          # back at lambda = 1: the three deltas cancel
     eng.close()
+
+
+@pytest.mark.parametrize("b", [1, 4])
+def test_host_driver_reads_and_writes_raspa2_restarts(b, tmp_path):
+    """The NIST SPC/E decks end to end through the C++ host driver: `RestartFile yes` (RestartFileParser,
+    read_data.cpp:3000-3221), zero cycles, the printed initial energies against the reference's own output.txt values
+    (tests/golden/nist_spce.npz), then the snapshot written by --write-restart read back: same molecules."""
+    import os
+    import subprocess
+    from graspa_b200.boxes import DRIVER, ROOT
+    from tests.conftest import load_nist
+    from tests.support.raspa_inputs import read_restart_positions
+    deck = os.path.join(ROOT, "oracle", "_ref", "examples", "Reference_NIST_SPCE", f"Box-{b}")
+    if not (os.path.exists(DRIVER) and os.path.isdir(deck)):
+        pytest.skip("host driver / NIST decks not built (oracle/build_ref.sh examples)")
+    out = tmp_path / "restartfile"
+    r = subprocess.run([DRIVER, deck, "--write-restart", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    box, ff, s, ref = load_nist(b)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("INITIAL")][0]
+    val = lambda key: float(line.split(key + ":")[1].split(",")[0])
+    assert abs(val("VDW [Guest-Guest]") - ref["vdw_gg"]) < 2e-5
+    assert abs(val("Real [Guest-Guest]") - ref["real_gg"]) < 2e-5
+    assert abs(val("Ewald [Guest-Guest]") - ref["ewald_gg"]) < 2e-5
+    assert abs(val("Tail") - ref["tail"]) < 2e-5
+    assert abs(val("Total") - ref["total"]) < 5e-5
+    n = int(s.natoms[1])
+    pos, chg = read_restart_positions(str(out), 0, 3, box, with_charge=True)
+    assert pos.shape == (n, 3)
+    assert np.max(np.abs(pos - s.pos[:n])) < 1e-9 and np.max(np.abs(chg - s.charge[:n])) < 1e-12
