@@ -113,6 +113,31 @@ def cpu_sample(box, ff, s, z, comp, target_s=12.0, seed=7):
     return dict(value=n / dt, n=n, seconds=dt, cores=nt, counts=[int(c) for c in counts], mean_W=float(out[:, 0].mean()))
 
 
+def reference_host_sample(box, ff, s, z, comp, target_s=6.0, seed=11):
+    """The reference's OWN host routines (PBC / VDW / CoulombReal of maths.cuh:427-500, compiled in place into
+    oracle/_ref/libgraspa_ref_host.so by oracle/build_ref.sh) on the trial-energy part of the same workload: first-bead style
+    trial atoms against the framework, one host thread (the reference's host code is serial).  Reported as pairs/s and as the
+    insertions/s it would sustain on the pair part alone (103 680 pairs per insertion in config E)."""
+    from oracle import oracle as orc
+    from graspa_b200.types import CBMC_INSERTION
+    if not orc.ref_available():
+        return {"unavailable": "oracle/_ref/libgraspa_ref_host.so not built (needs /root/reference at build time)"}
+    rng = np.random.default_rng(seed)
+    new_molid = int(s.natoms[comp]) // int(s.molsize[comp])
+    nsys = int(s.natoms[:s.nhost].sum())
+    n = 64; dt = 0.0; t = None
+    while True:
+        t = orc.trial_positions(box, s, CBMC_INSERTION, comp, 0, n, rng.random((n, 3)))
+        t0 = time.perf_counter(); orc.ref_trial_energies(box, ff, s, n, 1, t, comp, new_molid); dt = time.perf_counter() - t0
+        if dt > 0.5 * target_s or n >= 1 << 20:
+            break
+        n = int(min(1 << 20, max(2 * n, n * 0.8 * target_s / max(dt, 1e-4))))
+    pairs = float(n) * nsys
+    per_ins = float(nsys) * (10 + 10 * (int(s.molsize[comp]) - 1))
+    return {"kind": "reference", "cores": 1, "pairs_per_s": pairs / dt, "insertions_per_s_pair_part": pairs / dt / per_ins,
+            "sample": f"{n} trial atoms x {nsys} framework atoms in {dt:.1f} s through ref_trial_energies (the reference's PBC/VDW/CoulombReal)"}
+
+
 def _tail_json(text):
     for ln in reversed(text.strip().splitlines()):
         ln = ln.strip()
@@ -339,6 +364,10 @@ def main():
         cpu = cpu_sample(box, ff, s, z, comp)
         line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                                 "sample": f"{cpu['n']} insertions of the same workload in {cpu['seconds']:.1f} s, OpenMP over insertions"}
+        try:
+            line["cpu_baseline"]["reference_host_routines"] = reference_host_sample(box, ff, s, z, comp)
+        except Exception as ex:  # noqa: BLE001
+            line["cpu_baseline"]["reference_host_routines"] = {"error": str(ex)}
         f_pair, f_k = flops_per_insertion(cpu["counts"], cpu["n"])
         t_pair = ms_pair / max(n_pair, 1) * 1e-3
         achieved = f_pair * B / t_pair / 1e12
