@@ -37,7 +37,7 @@ if ROOT not in sys.path:
 from tests.conftest import load_config  # noqa: E402  (fixture loader only: committed .npz, no oracle)
 
 # dram bytes per insertion of k_widom_pair measured by ncu (profiles/r1_pair_kernel.md); bench.py cannot run under ncu itself
-NCU_DRAM_BYTES_PER_INSERTION = 510.0
+NCU_DRAM_BYTES_PER_INSERTION = 501.4
 
 METRIC = "widom_insertions_per_s"
 UNIT = "insertions/s"

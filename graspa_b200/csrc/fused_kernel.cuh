@@ -13,14 +13,16 @@
 //   * CTA 0 stores the result block straight into pinned host memory and raises a sequence flag the host polls.
 // Barriers per move: translation/rotation 1, deletion 1, insertion 3 (2 for single-bead molecules), reinsertion 3.
 // Covers Insertion_Body / Deletion_Body (mc_swap_utilities.h:3-225), the reinsertion growth + retrace
-// (move_struct.h:186-338) and SingleBody_Prepare + SingleBody_Calculation (mc_single_particle.h:10-241).
+// (move_struct.h:186-338), SingleBody_Prepare + SingleBody_Calculation (mc_single_particle.h:10-241) and the energy part of
+// IdentitySwapMove (mc_swap_moves.h:199-362: nothing there depends on a selection except the Ewald delta -- the new first
+// bead is the old molecule's first atom -- so growth of the new species and retrace of the old one share ONE stage).
 #pragma once
 #include "common.cuh"
 #include "pair.cuh"
 #include "ewald.cuh"
 #include "move_kernels.cuh"
 
-enum { GBF_INSERTION = 0, GBF_DELETION = 1, GBF_REINSERTION = 2, GBF_SINGLE = 3 };
+enum { GBF_INSERTION = 0, GBF_DELETION = 1, GBF_REINSERTION = 2, GBF_SINGLE = 3, GBF_IDSWAP = 4 };
 #define GBF_MAX_GROUPS 96           // trial groups of one stage: ntrials + 1 + norient <= 65
 #define GBF_PART_HALF 4096          // doubles per parity half of MoveBufs::partial()
 #define GBF_MAX_DYN_SMEM (160 * 1024)
@@ -37,6 +39,8 @@ struct FusedArgs
   int natoms;                             // atoms in the live ranges of L
   const double* __restrict__ pool3;
   CompView C; MoveBufs B;
+  // identity swap: F.comp / F.C / F.ms / F.nmol describe the NEW species; the molecule that leaves is `molecule` of old_comp
+  int old_comp, ms2, nold_ew, nnew_ew; CompView C2;
   SegList L;                              // live ranges with the kinds of THIS move
   KTable K; const double* same_sf; const double* cross_sf; double* temp_sf;
   double* host_result;                    // pinned host memory (UVA): 128 tagged 16-byte records the host polls
@@ -85,6 +89,7 @@ struct FusedSmem
   __align__(32) double res[8 * 16];                                       // the result slots (MoveBufs::result layout)
   SmemMol mN, mO;                                           // molecule being grown / proposed, and its old image
   SmemMol tmpl, exist;                                      // template molecule (slot 0 of the component) and the selected molecule
+  SmemMol tmpl2;                                            // identity swap: template of the OLD species (geometry of its retrace orientations)
   double pool[3 * (2 * 32 + 2 * 32 + 1)];                   // the random-pool entries this move consumes
   int blocked;                                              // block-pocket flag of the trial group being evaluated
 };
@@ -110,6 +115,7 @@ __device__ __forceinline__ AtomRec first_bead_atom(const DevParams& P, const Fus
   if(!insertion_like) { r.scale = M.a[7][0]; r.scoul = M.a[8][0]; }
   const bool existing = (type == 1 || type == 3 || type == 5) && g == 0;
   if(existing) { r.x = M.a[0][0]; r.y = M.a[1][0]; r.z = M.a[2][0]; }
+  else if(type == 4) { r.x = sm->exist.a[0][0]; r.y = sm->exist.a[1][0]; r.z = sm->exist.a[2][0]; }     // copy_firstbead_to_new, mc_swap_moves.h:178-181
   else { const double* u = sm->pool + 3 * (pool_off - F.pool_off + g); r.x = P.cell[0] * u[0]; r.y = P.cell[4] * u[1]; r.z = P.cell[8] * u[2]; }
   to_frac(P, r.x, r.y, r.z, r.fx, r.fy, r.fz);
   r.q = M.a[6][0]; r.type = M.type[0];
@@ -122,7 +128,7 @@ __device__ __forceinline__ AtomRec chain_atom(const DevParams& P, const FusedArg
 {
   const bool insertion_like = (type == 0 || type == 4);
   const SmemMol& M = insertion_like ? sm->tmpl : sm->exist;                    // start_position, mc_widom.h:536-556
-  const SmemMol& G = sm->tmpl;
+  const SmemMol& G = (F.kind == GBF_IDSWAP && type == 5) ? sm->tmpl2 : sm->tmpl;
   double vx = G.a[0][1 + a] - G.a[0][0], vy = G.a[1][1 + a] - G.a[1][0], vz = G.a[2][1 + a] - G.a[2][0];   // :256
   AtomRec r;
   if((type == 1 || type == 3 || type == 5) && g == 0) { r.x = M.a[0][1 + a]; r.y = M.a[1][1 + a]; r.z = M.a[2][1 + a]; }
@@ -157,7 +163,7 @@ __device__ __forceinline__ void group_energy(const DevParams& P, const PairTable
 {
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = (int) lane_id();
   double e6[6] = {0, 0, 0, 0, 0, 0}; int flag = 0;
-  pair_group_flat<CS>(P, W, S, F.L, F.comp, new_molid, &sm->T, cs, sm->Q + warp, split * nwarps + warp, nsplit * nwarps, e6, flag);
+  pair_group_flat<CS>(P, W, S, F.L, F.kind == GBF_IDSWAP ? F.old_comp : F.comp, new_molid, &sm->T, cs, sm->Q + warp, split * nwarps + warp, nsplit * nwarps, e6, flag);
 #pragma unroll
   for(int k = 0; k < 6; k++) e6[k] = warp_sum(e6[k]);
   flag = __any_sync(0xffffffffu, flag);
@@ -184,7 +190,8 @@ __device__ __forceinline__ void run_stage(const DevParams& P, const SysView& S, 
     int g = gg, si = 0;
     while(si + 1 < nseg && g >= segs[si].n) { g -= segs[si].n; si++; }
     const int type = segs[si].type; const bool chain = segs[si].chain != 0; const long long off = segs[si].pool_off;
-    const int cs = chain ? F.ms - 1 : 1;
+    const int msg = (F.kind == GBF_IDSWAP && type == 5) ? F.ms2 : F.ms;
+    const int cs = chain ? msg - 1 : 1;
     __syncthreads();
     if(!chain)
     {
@@ -214,7 +221,9 @@ __device__ __forceinline__ void run_stage(const DevParams& P, const SysView& S, 
       if(threadIdx.x == 0) sm->blocked = 0;
     }
     __syncthreads();
-    const int new_molid = (type == 0 || type == 4) ? F.nmol : (int) F.molecule;
+    // molecule skipped by the pair loops: the one being grown / retraced; identity swap: the molecule that leaves, for the
+    // growth of the new species (Sims.ExcludeList[0], mc_swap_moves.h:268) and for its own retrace alike
+    const int new_molid = (F.kind == GBF_IDSWAP) ? (int) F.molecule : ((type == 0 || type == 4) ? F.nmol : (int) F.molecule);
     double* rec = part + (size_t) w * 16;
     if(cs == 1)      group_energy<1>(P, W, S, F, sm, new_molid, cs, split, nsplit, rec, tag);
     else if(cs == 2) group_energy<2>(P, W, S, F, sm, new_molid, cs, split, nsplit, rec, tag);
@@ -466,19 +475,27 @@ k_move(DevParams P, SysView S, FusedArgs F)
     }
     else
     {
-      const int npool = F.ntrials + no + (F.kind == GBF_REINSERTION ? 1 + no : 0);
+      const int npool = F.kind == GBF_IDSWAP ? 2 + no + (F.ms2 > 1 ? F.norient : 0) : F.ntrials + no + (F.kind == GBF_REINSERTION ? 1 + no : 0);
       for(int i = threadIdx.x; i < 3 * npool; i += 32) sm.pool[i] = F.pool3[3 * F.pool_off + i];
       if((int) threadIdx.x < ms)
       {
         const int i = threadIdx.x;
         sm.tmpl.a[0][i] = F.C.x[i]; sm.tmpl.a[1][i] = F.C.y[i]; sm.tmpl.a[2][i] = F.C.z[i];
         sm.tmpl.a[6][i] = F.C.q[i]; sm.tmpl.a[7][i] = F.C.scale[i]; sm.tmpl.a[8][i] = F.C.scoul[i]; sm.tmpl.type[i] = F.C.type[i];
-        if(F.kind != GBF_INSERTION)
+        if(F.kind != GBF_INSERTION && F.kind != GBF_IDSWAP)
         {
           const long long j = F.molecule * ms + i;
           sm.exist.a[0][i] = F.C.x[j]; sm.exist.a[1][i] = F.C.y[j]; sm.exist.a[2][i] = F.C.z[j];
           sm.exist.a[6][i] = F.C.q[j]; sm.exist.a[7][i] = F.C.scale[j]; sm.exist.a[8][i] = F.C.scoul[j]; sm.exist.type[i] = F.C.type[j];
         }
+      }
+      if(F.kind == GBF_IDSWAP && (int) threadIdx.x < F.ms2)
+      {
+        const int i = threadIdx.x; const long long j = F.molecule * F.ms2 + i;
+        sm.exist.a[0][i] = F.C2.x[j]; sm.exist.a[1][i] = F.C2.y[j]; sm.exist.a[2][i] = F.C2.z[j];
+        sm.exist.a[6][i] = F.C2.q[j]; sm.exist.a[7][i] = F.C2.scale[j]; sm.exist.a[8][i] = F.C2.scoul[j]; sm.exist.type[i] = F.C2.type[j];
+        sm.tmpl2.a[0][i] = F.C2.x[i]; sm.tmpl2.a[1][i] = F.C2.y[i]; sm.tmpl2.a[2][i] = F.C2.z[i];
+        to_frac(P, sm.exist.a[0][i], sm.exist.a[1][i], sm.exist.a[2][i], sm.exist.a[3][i], sm.exist.a[4][i], sm.exist.a[5][i]);
       }
     }
   }
@@ -612,6 +629,48 @@ k_move(DevParams P, SysView S, FusedArgs F)
       }
       if(F.do_ewald) ewald_total_slot(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
       export_molecule(F, sm.mN, GBK_BUF_TEMP);            // tempMolStorage, StoreNewLocation_Reinsertion
+    }
+  }
+  else if(F.kind == GBF_IDSWAP)
+  {
+    // growth of the new species at the old molecule's first atom + retrace of the old molecule: one stage
+    const int no2 = F.ms2 > 1 ? F.norient : 0;
+    StageSeg sg[4]; int ns = 0;
+    const long long off1 = F.pool_off + 1, off2 = off1 + no, off3 = off2 + 1;
+    sg[ns].type = 4; sg[ns].chain = 0; sg[ns].n = 1; sg[ns].pool_off = F.pool_off; ns++;
+    if(ms > 1) { sg[ns].type = 4; sg[ns].chain = 1; sg[ns].n = no; sg[ns].pool_off = off1; ns++; }
+    sg[ns].type = 5; sg[ns].chain = 0; sg[ns].n = 1; sg[ns].pool_off = off2; ns++;
+    if(F.ms2 > 1) { sg[ns].type = 5; sg[ns].chain = 1; sg[ns].n = no2; sg[ns].pool_off = off3; ns++; }
+    const int ngroups = 2 + no + no2;
+    // the new species' first bead is known before anything is evaluated: its chain trials grow around it right away
+    if(threadIdx.x == 0) { const AtomRec a = first_bead_atom(P, F, &sm, 4, 0, F.pool_off); put_atom(sm.mN, 0, a); }
+    __syncthreads();
+    const int nsplit = stage_nsplit(F, ngroups);
+    run_stage(P, S, F, &sm, W, sg, ns, ngroups, nsplit, 0);
+    collect_stage(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
+    finish_segment(P, F, &sm, 4, false, 1, 0.0, 0.0, sm.E, sm.Fl, 0, 1.0);
+    if(threadIdx.x == 0 && sm.res[9] != 0.0) { sm.res[6] = sm.mN.a[0][0]; sm.res[7] = sm.mN.a[1][0]; sm.res[8] = sm.mN.a[2][0]; }
+    __syncthreads();
+    bool alive = sm.res[13] != 0.0;
+    if(ms > 1 && alive)
+    {
+      finish_segment(P, F, &sm, 4, true, no, F.u0, 0.0, sm.E + 6, sm.Fl + 1, 1, sm.res[14]);
+      adopt_selection(P, F, &sm, 4, true, off1, 1);
+      alive = sm.res[16 + 13] != 0.0;
+    }
+    double* ew = part_half(F, 0) + GBF_PART_EWALD;
+    if(F.do_ewald && alive) ewald_slice(P, F, dyn, sm.red, &sm.exist, F.nold_ew, &sm.mN, F.nnew_ew, ew);
+    if(blockIdx.x == 0)
+    {
+      if(alive)
+      {
+        const int g2 = 1 + no;
+        finish_segment(P, F, &sm, 5, false, 1, 0.0, 0.0, sm.E + 6 * g2, sm.Fl + g2, 2, 1.0);
+        if(threadIdx.x == 0 && sm.res[32 + 9] != 0.0) { sm.res[32 + 6] = sm.exist.a[0][0]; sm.res[32 + 7] = sm.exist.a[1][0]; sm.res[32 + 8] = sm.exist.a[2][0]; }
+        if(F.ms2 > 1) finish_segment(P, F, &sm, 5, true, no2, 0.0, 0.0, sm.E + 6 * (g2 + 1), sm.Fl + g2 + 1, 3, sm.res[32 + 14]);
+      }
+      if(F.do_ewald) ewald_total_slot(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
+      export_molecule(F, sm.mN, GBK_BUF_TEMP);            // tempMolStorage: what gb_accept_identity_swap commits
     }
   }
   else

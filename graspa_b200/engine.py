@@ -27,7 +27,7 @@ DECLARED_SYMBOLS = [
     "gb_abi_version", "gb_last_error", "gb_engine_create", "gb_engine_destroy", "gb_device_info", "gb_synchronize", "gb_stream",
     "gb_upload_forcefield", "gb_upload_box", "gb_set_components", "gb_upload_atoms", "gb_download_atoms", "gb_snapshot_molecules",
     "gb_upload_structure_factors", "gb_download_structure_factors", "gb_set_exclusion_constants", "gb_upload_random_pool", "gb_set_block_pockets",
-    "gb_set_cbmc", "gb_get_pseudo_atom_counts", "gb_cbmc_first_bead", "gb_cbmc_chain", "gb_cbmc_grown_positions", "gb_reinsertion_store", "gb_move_insertion", "gb_move_deletion", "gb_move_reinsertion", "gb_move_single_body",
+    "gb_set_cbmc", "gb_get_pseudo_atom_counts", "gb_cbmc_first_bead", "gb_cbmc_chain", "gb_cbmc_grown_positions", "gb_reinsertion_store", "gb_move_insertion", "gb_move_deletion", "gb_move_reinsertion", "gb_move_single_body", "gb_move_identity_swap",
     "gb_trial_energies", "gb_single_body_propose", "gb_single_body_delta", "gb_single_body_delta_explicit",
     "gb_ewald_delta", "gb_ewald_delta_identity_swap", "gb_ewald_delta_explicit", "gb_ewald_commit",
     "gb_lambda_change_delta", "gb_ewald_delta_lambda_change", "gb_accept_lambda_change",
@@ -406,6 +406,12 @@ class Engine:
     def move_reinsertion(self, comp, molecule, pool_offset, uniforms):
         u = (C.c_double * 2)(*uniforms); r = GbMoveResult()
         self._chk(self.lib.gb_move_reinsertion(self.h, C.c_int32(comp), C.c_int64(molecule), C.c_int64(pool_offset), u, C.byref(r))); return r.as_dict()
+
+    def move_identity_swap(self, old_comp, old_molecule, new_comp, pool_offset, uniform):
+        r = GbMoveResult()
+        self._chk(self.lib.gb_move_identity_swap(self.h, C.c_int32(old_comp), C.c_int64(old_molecule), C.c_int32(new_comp), C.c_int64(pool_offset),
+                                                 C.c_double(uniform), C.byref(r)))
+        return r.as_dict()
 
     def move_single_body(self, move_type, comp, molecule, max_change, pool_offset):
         mc = (C.c_double * 3)(*max_change); r = GbMoveResult()

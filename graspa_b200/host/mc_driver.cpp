@@ -86,7 +86,7 @@ struct Sim
   long moves_done = 0;
   int device = -1;                                // CUDA device of the engine (-1: the current one)
   bool fused = true;                              // one host round trip per move (gb_move_*); false: the stage calls
-  double call_s[4] = {0, 0, 0, 0}; long call_n[4] = {0, 0, 0, 0};   // host time inside gb_move_{insertion,deletion,reinsertion,single_body}
+  double call_s[5] = {0, 0, 0, 0, 0}; long call_n[5] = {0, 0, 0, 0, 0};   // host time inside gb_move_{insertion,deletion,reinsertion,single_body,identity_swap}
   std::FILE* trace = nullptr;
 };
 
@@ -572,6 +572,37 @@ void move_identity_swap(Sim& S)
   const int ms_new = S.d.comps[newc - S.nhost].ms(), ms_old = S.d.comps[oldc - S.nhost].ms();
   const double scale[2] = {1.0, 1.0};
   gb_cbmc_result r; int32_t used = 0;
+  const size_t need = 2 + (ms_new > 1 ? (size_t) S.d.n_trial_orientations : 0) + (ms_old > 1 ? (size_t) S.d.n_trial_orientations : 0);
+  if(S.fused && !(S.pool_off + need >= S.pool_size))
+  {
+    // one kernel, one host round trip: growth at the old molecule's first atom + retrace + Ewald + tail
+    gb_move_result m;
+    { CallClock cc(S.call_s[4], S.call_n[4]); GB(gb_move_identity_swap(S.e, oldc, old_mol, newc, (int64_t) S.pool_off, S.rng.peek(0), &m)); }
+    S.rng.advance(m.uniforms_used); pool_update(S, m.pool_used);
+    if(!m.success) { trace_move(S, "identity_swap", oldc, old_mol, 0, 0.0); return; }
+    double Wn = m.first_bead.rosenbluth, Wo = m.old_first_bead.rosenbluth;
+    Energy En, Eo;
+    En.HGVDW = m.first_bead.energy[0]; En.HGReal = m.first_bead.energy[1]; En.GGVDW = m.first_bead.energy[2]; En.GGReal = m.first_bead.energy[3];
+    Eo.HGVDW = m.old_first_bead.energy[0]; Eo.HGReal = m.old_first_bead.energy[1]; Eo.GGVDW = m.old_first_bead.energy[2]; Eo.GGReal = m.old_first_bead.energy[3];
+    if(ms_new > 1) { Wn *= m.chain.rosenbluth; En.HGVDW += m.chain.energy[0]; En.HGReal += m.chain.energy[1]; En.GGVDW += m.chain.energy[2]; En.GGReal += m.chain.energy[3]; }
+    if(ms_old > 1) { Wo *= m.old_chain.rosenbluth; Eo.HGVDW += m.old_chain.energy[0]; Eo.HGReal += m.old_chain.energy[1]; Eo.GGVDW += m.old_chain.energy[2]; Eo.GGReal += m.old_chain.energy[3]; }
+    Energy E = En; E.add(Eo, -1.0);
+    if(!S.d.no_charges) { E.GGEwald = m.ewald[0]; E.HGEwald = m.ewald[1]; Wn *= std::exp(-S.d.beta * (m.ewald[0] + m.ewald[1])); }
+    E.Tail = m.tail; Wn *= std::exp(-S.d.beta * m.tail);
+    const double pre = prefactor(S, newc, true) * prefactor(S, oldc, false);
+    const double pacc = pre * (Wn / S.d.comps[newc - S.nhost].ideal_rosenbluth) / (Wo / S.d.comps[oldc - S.nhost].ideal_rosenbluth);
+    const double R = S.rng.uniform();
+    if(R < pacc)
+    {
+      GB(gb_accept_identity_swap(S.e, oldc, old_mol, newc));
+      XN.idswap_add.accepted++; XO.idswap_remove.accepted++; XO.idswap_to[newc].accepted++;
+      if(newc != oldc) { XN.nmol++; XO.nmol--; }
+      S.running.add(E);
+      trace_move(S, "identity_swap", oldc, old_mol, 1, E.total());
+    }
+    else trace_move(S, "identity_swap", oldc, old_mol, 0, 0.0);
+    return;
+  }
   // ---- insertion leg: first bead preset to the old molecule's first atom, old molecule excluded (:260-296)
   pool_check(S, 1);
   GB(gb_cbmc_first_bead(S.e, GB_IDENTITY_SWAP_NEW, newc, new_mol, (int64_t) S.pool_off, 0.0, scale, 0.0, oldc, old_mol, nullptr, &r, &used));
@@ -1023,11 +1054,11 @@ int main(int argc, char** argv)
               (unsigned long long) S.rng.consumed(), S.pool_rounds, (long long) launches);
   if(S.fused)
   {
-    const char* nm[4] = {"insertion", "deletion", "reinsertion", "translation/rotation"};
+    const char* nm[5] = {"insertion", "deletion", "reinsertion", "translation/rotation", "identity swap"};
     double tot = 0.0;
-    for(int k = 0; k < 4; k++) tot += S.call_s[k];
+    for(int k = 0; k < 5; k++) tot += S.call_s[k];
     std::printf("host time inside the move calls: %.3f s of %.3f s;", tot, secs);
-    for(int k = 0; k < 4; k++) if(S.call_n[k]) std::printf(" %s %.2f us x %ld;", nm[k], 1e6 * S.call_s[k] / S.call_n[k], S.call_n[k]);
+    for(int k = 0; k < 5; k++) if(S.call_n[k]) std::printf(" %s %.2f us x %ld;", nm[k], 1e6 * S.call_s[k] / S.call_n[k], S.call_n[k]);
     std::printf("\n");
   }
   if(timing)

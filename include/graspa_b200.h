@@ -219,6 +219,12 @@ typedef struct {
 int  gb_move_insertion(gb_engine* e, int32_t component, int64_t pool_offset, const double uniforms[2], const double scale[2], gb_move_result* out);
 int  gb_move_deletion(gb_engine* e, int32_t component, int64_t molecule, int64_t pool_offset, const double scale[2], gb_move_result* out);
 int  gb_move_reinsertion(gb_engine* e, int32_t component, int64_t molecule, int64_t pool_offset, const double uniforms[2], gb_move_result* out);
+/* the energy part of IdentitySwapMove (mc_swap_moves.h:256-362) in one kernel: result slots first_bead / chain = growth of the
+ * new species, old_first_bead / old_chain = retrace of the molecule that leaves; ewald and tail as the reference's
+ * GPU_EwaldDifference_IdentitySwap / TailCorrectionIdentitySwap return them; the grown molecule is left in tempMolStorage
+ * for gb_accept_identity_swap.  uniform = the draw of the new species' orientation selection (see uniforms_used). */
+int  gb_move_identity_swap(gb_engine* e, int32_t old_component, int64_t old_molecule, int32_t new_component, int64_t pool_offset,
+                           double uniform, gb_move_result* out);
 int  gb_move_single_body(gb_engine* e, int32_t move_type, int32_t component, int64_t molecule, const double max_change[3],
                          int64_t pool_offset, gb_move_result* out);
 

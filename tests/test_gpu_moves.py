@@ -368,6 +368,13 @@ def test_identity_swap_stages_and_commit(gpu_engine_factory, oracle):
         rb = eng.cbmc_first_bead(IDENTITY_SWAP_OLD, oldc, mol, step, 0.5)
         assert rb["success"] and rb["selected"] == 0
         tail = eng.tail_identity_swap(newc, oldc)
+        # the one-kernel move reports the same numbers as the three stage calls
+        m = eng.move_identity_swap(oldc, mol, newc, step, 0.5)
+        assert m["success"] and m["pool_used"] == 2 and m["uniforms_used"] == 0
+        assert abs(m["first_bead"]["rosenbluth"] - fb["rosenbluth"]) <= 1e-12 * fb["rosenbluth"]          # summation order differs
+        assert abs(m["old_first_bead"]["rosenbluth"] - rb["rosenbluth"]) <= 1e-12 * rb["rosenbluth"]
+        assert _close(m["first_bead"]["energy"], fb["energy"]) and _close(m["old_first_bead"]["energy"], rb["energy"])
+        assert m["tail"] == tail and np.array_equal(m["first_bead"]["selected_pos"], fb["selected_pos"])
         if step == 0:
             # oracle: one trial atom of the NEW species at the old position against the system minus the old molecule
             tr = TrialAtoms(np.array([old_pos]), np.array([cur.charge[int(cur.offsets[newc])]]), np.array([cur.type[int(cur.offsets[newc])]]))
@@ -414,7 +421,16 @@ def test_identity_swap_same_species_with_charges(gpu_engine_factory, oracle):
     ref, _, _ = oracle.ewald_delta(box, pos, np.concatenate([q, q]), np.ones(2 * ms), ms, ms, z["sf_ads"], z["sf_fw"])
     assert _close(ew, ref, scale=max(1.0, float(np.abs(ref).max())))       # the two exclusion constants cancel (same species)
     delta = float(np.sum(fb["energy"]) + np.sum(ch["energy"]) - np.sum(rb["energy"]) - np.sum(rc["energy"]) + ew[0] + ew[1])
+    # the one-kernel move (same pool layout: growth at 0 and 1.., retrace behind it) against the stage calls
+    m = eng.move_identity_swap(comp, mol, comp, 0, 0.41)
+    assert m["success"] and m["pool_used"] == 22 and m["uniforms_used"] == 1
+    assert m["chain"]["selected"] == ch["selected"]
+    for a, b in ((m["first_bead"], fb), (m["chain"], ch), (m["old_first_bead"], rb), (m["old_chain"], rc)):
+        assert abs(a["rosenbluth"] - b["rosenbluth"]) <= 1e-12 * abs(b["rosenbluth"]) and _close(a["energy"], b["energy"])
+    assert _close(np.array(m["ewald"]), ew, scale=max(1.0, float(np.abs(ew).max())))
+    assert np.allclose(eng.snapshot_molecules(comp, 0, 1)["pos"], s.pos[o:o + ms])        # nothing committed yet
     eng.accept_identity_swap(comp, mol, comp)
+    assert np.allclose(eng.snapshot_molecules(comp, mol, 1)["pos"], new_pos, atol=1e-12)  # the fused call left the same molecule in tempMolStorage
     E1 = _totals(eng)
     assert abs((E1 - E0) - delta) <= 1e-9 * max(1.0, abs(E1)), (E1 - E0, delta)
     eng.close()
