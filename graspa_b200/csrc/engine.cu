@@ -605,7 +605,8 @@ int gb_set_components(gb_engine* e, int32_t n_total, int32_t n_host)
 {
   if(!e) return fail(GB_ERR_ARG, "null engine");
   if(n_total <= 0 || n_total > GBK_MAX_SEG || n_host < 0 || n_host > n_total) return fail(GB_ERR_ARG, "bad component counts");
-  e->ncomp = n_total; e->nhost = n_host; e->comps.assign(n_total, Comp());
+  for(auto& C : e->comps) if(C.d_pocket) { cudaFree(C.d_pocket); C.d_pocket = nullptr; }     // block-pocket lists belong to the old layout
+  e->ncomp = n_total; e->nhost = n_host; e->comps.assign(n_total, Comp()); e->tail_memo.clear();
   e->nslots = 0; e->hx.clear(); e->hy.clear(); e->hz.clear(); e->hq.clear(); e->hscale.clear(); e->hscoul.clear(); e->htype.clear(); e->hmolid.clear();
   e->device_stale = true;
   return GB_OK;
