@@ -87,7 +87,7 @@ struct Sim
   int device = -1;                                // CUDA device of the engine (-1: the current one)
   bool fused = true;                              // one host round trip per move (gb_move_*); false: the stage calls
   double call_s[5] = {0, 0, 0, 0, 0}; long call_n[5] = {0, 0, 0, 0, 0};   // host time inside gb_move_{insertion,deletion,reinsertion,single_body,identity_swap}
-  std::FILE* trace = nullptr;
+  std::FILE* trace = nullptr; long trace_lines = 0;   // one trace line per RunMoves call (moves that do nothing included)
 };
 
 inline int comp_ms(const Sim& S, int c) { return c == 0 ? 0 : (c < S.nhost ? S.d.fw[c - 1].molsize : S.d.comps[c - S.nhost].ms()); }
@@ -327,7 +327,8 @@ void record_rosen(Sim& S, int comp, double W, const Energy& E, long cycle)      
 
 void trace_move(Sim& S, const char* kind, int comp, long mol, int accepted, double dE)
 {
-  if(S.trace) std::fprintf(S.trace, "%ld %s %d %ld %d %.10e\n", S.moves_done, kind, comp, mol, accepted, dE);
+  if(S.trace) std::fprintf(S.trace, "%ld %s %d %ld %d %.12e\n", S.moves_done, kind, comp, mol, accepted, dE);
+  S.trace_lines++;
 }
 
 // ------------------------------------------------------------------------------------------------ moves
@@ -671,6 +672,7 @@ void run_move(Sim& S, long cycle)
   const double R = S.rng.uniform();
   const CompState& X = S.C[comp];
   S.moves_done++;
+  const long lines_before = S.trace_lines;
   if(R < X.cTrans) { if(X.nmol > 0) move_single_body(S, comp, mol, GB_TRANSLATION); }
   else if(R < X.cRot) { if(X.nmol > 0) move_single_body(S, comp, mol, GB_ROTATION); }
   else if(R < X.cSpecial) { }
@@ -684,6 +686,7 @@ void run_move(Sim& S, long cycle)
     else if(X.nmol > 0) move_deletion(S, comp, mol);
     else S.C[comp].del.total += 0;
   }
+  if(S.trace_lines == lines_before) trace_move(S, "none", comp, mol, 0, 0.0);     // the selected move had nothing to act on
 }
 
 void update_max(double* m, MoveCount& w, MoveCount& cum, double cap)           // Update_Max_Translation / Update_Max_Rotation

@@ -74,4 +74,26 @@ if [ "$WHAT" = "all" ] || [ "$WHAT" = "cuda" ]; then
   )
   rm -rf "$SCR"
 fi
+if [ "$WHAT" = "trace" ]; then
+  # the same program with ONE added line: RunMoves (axpy.cu:297) appends "component movetype deltaE" of every move to the
+  # file named by $GRASPA_TRACE -- the accept/reject sequence the parity check compares move by move
+  # (scripts/compare_trace.sh).  The line is inserted into the scratch copy only.
+  echo "[build_ref] reference CUDA program with a move trace (sm_100)"
+  SCR="$(mktemp -d /tmp/graspa_ref_trace.XXXXXX)"
+  cp -r "$REF/src_clean/." "$SCR/"
+  chmod -R u+w "$SCR"
+  sed -i '268s/{OLDComponent, OLDMolInComponent}/{(int) OLDComponent, (int) OLDMolInComponent}/' "$SCR/mc_swap_moves.h"
+  grep -n "SystemComponents.deltaE += DeltaE;" "$SCR/axpy.cu" | head -1 | grep -q "^297:" || { echo "axpy.cu:297 is not the deltaE accumulation any more"; exit 1; }
+  sed -i '297i\  { static FILE* gtf = getenv("GRASPA_TRACE") ? fopen(getenv("GRASPA_TRACE"), "w") : nullptr; if(gtf) fprintf(gtf, "%zu %d %.12e\\n", comp, MoveType, DeltaE.total()); }' "$SCR/axpy.cu"
+  FLAGS="-O3 -std=c++20 -arch=sm_100 --expt-relaxed-constexpr -w -Xcompiler -fopenmp -rdc=true -x cu"
+  ( cd "$SCR"
+    for f in axpy.cu main.cpp read_data.cpp data_struct.cpp VDW_Coulomb.cu; do
+      "$NVCC" $FLAGS -c "$f" -o "${f%.*}.o" &
+    done
+    wait
+    "$NVCC" -arch=sm_100 -rdc=true -Xcompiler -fopenmp main.o read_data.o axpy.o data_struct.o VDW_Coulomb.o -o "$OUT/graspa_ref_cuda_trace.x"
+  )
+  sed -n '295,299p' "$SCR/axpy.cu"
+  rm -rf "$SCR"
+fi
 echo "[build_ref] done: $(ls "$OUT")"
