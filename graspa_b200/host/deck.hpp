@@ -606,6 +606,15 @@ inline Deck load(const std::string& dir, double pressure_override = -1.0, double
   d.beta = 1.0 / (kB / (mass_unit * std::pow(length_unit, 2) / std::pow(time_unit, 2)) * d.temperature);
   d.pressure = d.pressure_pa / (mass_unit / (length_unit * std::pow(time_unit, 2)));
   compute_fugacity(d);
+  // prepare_MixtureStats (fxn_main.h:639-656, called for mixtures only, main.cpp:326-330): the mol fractions are divided by
+  // their sum over every component but component 0 -- which includes each separated framework component with its default 1.0
+  // (fxn_main.h:70).  Runs after the equation of state, which sees the fractions as given (main.cpp:240).
+  if(d.comps.size() > 1)
+  {
+    double tot = (double) d.fw.size();
+    for(const auto& c : d.comps) tot += c.mol_fraction;
+    for(auto& c : d.comps) c.mol_fraction /= tot;
+  }
   return d;
 }
 

@@ -25,6 +25,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -408,6 +409,10 @@ void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run + Deleti
   E.Tail = -tail;
   const double pacc = pre * S.d.comps[comp - S.nhost].ideal_rosenbluth / W;
   const double R = S.rng.uniform();
+  if(std::getenv("GB_DEBUG_MOVE") && S.moves_done == std::atol(std::getenv("GB_DEBUG_MOVE")))
+    std::fprintf(stderr, "deletion debug nmol:"), [&]{ for(int c = 1; c < S.ncomp; c++) std::fprintf(stderr, " %ld", S.C[c].nmol); std::fprintf(stderr, "\n"); }(),
+    std::fprintf(stderr, "deletion debug move %ld comp %d mol %ld: W %.12e ewald %.12e %.12e tail %.6e pre %.12e pacc %.12e R %.12e E %.10e %.10e %.10e %.10e fused %d\n",
+                 S.moves_done, comp, mol, W, ew[0], ew[1], tail, pre, pacc, R, E.HGVDW, E.HGReal, E.GGVDW, E.GGReal, (int) fused);
   if(R < pacc)
   {
     GB(gb_accept_deletion(S.e, comp, mol));

