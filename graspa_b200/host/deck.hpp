@@ -93,6 +93,9 @@ struct Deck
   std::vector<std::string> names; std::vector<double> eps_in, sig_in, mass, pseudo_charge;
   bool shifted = false, tail = false;
   std::vector<double> eps, sigma, shift, tail_energy; std::vector<int> use_tail;   // n*n
+  // UseLJ1264 yes: eps / sigma hold the polynomial coefficients C12 / C6, z the r^-4 coefficient, c10 the r^-10 one
+  // (ForceField_Processing read_data.cpp:1196-1230, VDW maths.cuh:452-476)
+  bool use1264 = false; std::vector<double> c4_in, z, c10;
   // framework
   double cell[9] = {0}, inv[9] = {0}, volume = 0;
   std::vector<double> fpos; std::vector<int> ftype; std::vector<double> fcharge;  // supercell atoms
@@ -176,6 +179,7 @@ inline void read_simulation_input(Deck& d, const std::string& dir)
     else if(has("SeparateFrameworkComponents")) d.separate_framework = ieq(t[1], "yes");
     else if(has("NumberofFrameworkComponents")) d.n_framework_components = std::stoi(t[1]);
     else if(has("RestartFile")) d.restart_file = ieq(t[1], "yes");
+    else if(has("UseLJ1264")) d.use1264 = ieq(t[1], "yes");
     else if(has("UseMaxStep")) d.use_max_step = ieq(t[1], "yes");
     else if(has("MaxStepPerCycle")) d.max_step_per_cycle = std::stol(t[1]);
     else if(has("RandomSeed")) d.random_seed = std::stoi(t[1]);
@@ -209,6 +213,7 @@ inline void read_force_field(Deck& d, const std::string& dir)
   {
     auto t = terms(L.at(7 + i));
     d.names.push_back(t.at(0)); d.eps_in.push_back(std::stod(t.at(2))); d.sig_in.push_back(std::stod(t.at(3)));
+    d.c4_in.push_back((t.at(1) == "lennard-jones-1264" && t.size() >= 5) ? std::stod(t[4]) : 0.0);       // read_data.cpp:819-823
   }
   auto P = read_lines(dir + "/pseudo_atoms.def");
   const int np = std::stoi(terms(P.at(1)).at(0));
@@ -222,10 +227,25 @@ inline void read_force_field(Deck& d, const std::string& dir)
   }
   const double cutsq = d.cutoff_vdw * d.cutoff_vdw;
   d.eps.assign(n * n, 0); d.sigma.assign(n * n, 0); d.shift.assign(n * n, 0); d.tail_energy.assign(n * n, 0); d.use_tail.assign(n * n, 0);
+  d.z.assign(n * n, 0); d.c10.assign(n * n, 0);
+  // shift of the polynomial form, Get_Shifted_Value_Coeff read_data.cpp:750-758
+  auto poly_shift = [&](double C12, double C6, double C4, double C10) {
+    const double ri2 = 1.0 / cutsq, ri4 = ri2 * ri2, ri6 = ri4 * ri2, ri10 = ri4 * ri6, ri12 = ri6 * ri6;
+    return C12 * ri12 - C6 * ri6 + C10 * ri10 + C4 * ri4;
+  };
+  if(d.use1264 && d.tail) throw std::runtime_error("tail corrections with UseLJ1264 are not read by this host program");
   for(int i = 0; i < n; i++)
     for(int j = 0; j < n; j++)
     {
       const double e = std::sqrt(d.eps_in[i] * d.eps_in[j]) / 1.20272430057, s = 0.5 * (d.sig_in[i] + d.sig_in[j]);
+      if(d.use1264)
+      {
+        const double s2 = s * s, s6 = s2 * s2 * s2, s12 = s6 * s6;
+        const double C12 = 4.0 * e * s12, C6 = 4.0 * e * s6, C4 = 0.5 * (d.c4_in[i] + d.c4_in[j]) / 1.20272430057;
+        d.eps[i * n + j] = C12; d.sigma[i * n + j] = C6; d.z[i * n + j] = C4;
+        d.shift[i * n + j] = d.shifted ? poly_shift(C12, C6, C4, 0.0) : 0.0;
+        continue;
+      }
       d.eps[i * n + j] = e; d.sigma[i * n + j] = s;
       d.shift[i * n + j] = d.shifted ? lj_energy(e, s, cutsq) : 0.0;
       if(d.tail) { d.use_tail[i * n + j] = 1; d.tail_energy[i * n + j] = tail_value(e, s, cutsq); }
@@ -246,11 +266,44 @@ inline void read_force_field(Deck& d, const std::string& dir)
       for(size_t k = start + 3; nmix > 0 && k < start + 3 + nmix && k < F.size(); k++)
       {
         auto t = terms(F[k]);
-        if(t.size() != 5) continue;
+        const bool is1264 = t.size() == 6 && t[2] == "lennard-jones-1264";
+        if(t.size() != 5 && !is1264) continue;
         const int i = type_of(d, t[0]), j = type_of(d, t[1]);
         const double e = std::stod(t[3]) / 1.20272430057, sg = std::stod(t[4]);
+        if(d.use1264)
+        {
+          const double s2 = sg * sg, s6 = s2 * s2 * s2, s12 = s6 * s6, C12 = 4.0 * e * s12, C6 = 4.0 * e * s6;
+          const double C4 = is1264 ? std::stod(t[5]) / 1.20272430057 : 0.0;
+          d.eps[i * n + j] = d.eps[j * n + i] = C12; d.sigma[i * n + j] = d.sigma[j * n + i] = C6;
+          d.z[i * n + j] = d.z[j * n + i] = C4; d.c10[i * n + j] = d.c10[j * n + i] = 0.0;
+          if(d.shifted) d.shift[i * n + j] = d.shift[j * n + i] = poly_shift(C12, C6, C4, 0.0);
+          continue;
+        }
         d.eps[i * n + j] = d.eps[j * n + i] = e; d.sigma[i * n + j] = d.sigma[j * n + i] = sg;
         if(d.shifted) d.shift[i * n + j] = d.shift[j * n + i] = lj_energy(e, sg, cutsq);
+      }
+      // "defined interactions" of the GENERIC2_HC form (UseLJ1264 only, read_data.cpp:1000-1049):
+      // U = p0 exp(-p1 r) - p2/r^4 - p3/r^6 - p4/r^8 - p5/r^12  ->  C12 = -p5, C6 = p3, C4 = -p2, C10 = 0
+      if(d.use1264)
+      {
+        size_t dstart = 0, ndef = 0, done = 0;
+        for(size_t k = 0; k < F.size(); k++)
+        {
+          if(F[k].find("number of defined interactions") != std::string::npos && dstart == 0) dstart = k;
+          if(dstart > 0 && k == dstart + 1) { auto t = terms(F[k]); if(!t.empty()) ndef = (size_t) std::stol(t[0]); }
+        }
+        for(size_t k = dstart + 2; ndef > 0 && done < ndef && k < F.size(); k++)
+        {
+          auto t = terms(F[k]);
+          if(t.size() < 9 || t[2] != "GENERIC2_HC") continue;
+          done++;
+          int i, j;
+          try { i = type_of(d, t[0]); j = type_of(d, t[1]); } catch(const std::exception&) { continue; }
+          const double C12 = -std::stod(t[8]) / 1.20272430057, C6 = std::stod(t[6]) / 1.20272430057, C4 = -std::stod(t[5]) / 1.20272430057;
+          d.eps[i * n + j] = d.eps[j * n + i] = C12; d.sigma[i * n + j] = d.sigma[j * n + i] = C6;
+          d.z[i * n + j] = d.z[j * n + i] = C4; d.c10[i * n + j] = d.c10[j * n + i] = 0.0;
+          if(d.shifted) d.shift[i * n + j] = d.shift[j * n + i] = poly_shift(C12, C6, C4, 0.0);
+        }
       }
     }
     if(F.size() > 1)

@@ -110,9 +110,8 @@ void setup_engine(Sim& S)
   deck::Deck& d = S.d;
   GB(gb_engine_create(&S.e, S.device));
   const int n = d.ntypes();
-  std::vector<double> zeros(n * n, 0.0);
-  gb_forcefield ff{d.eps.data(), d.sigma.data(), zeros.data(), d.shift.data(), zeros.data(), d.cutoff_vdw * d.cutoff_vdw, d.cutoff_coul * d.cutoff_coul,
-                   d.overlap, n, d.no_charges ? 1 : 0, 1 /* VDWRealBias stays true: SURVEY section 5 */, 0};
+  gb_forcefield ff{d.eps.data(), d.sigma.data(), d.z.data(), d.shift.data(), d.c10.data(), d.cutoff_vdw * d.cutoff_vdw, d.cutoff_coul * d.cutoff_coul,
+                   d.overlap, n, d.no_charges ? 1 : 0, 1 /* VDWRealBias stays true: SURVEY section 5 */, d.use1264 ? 1 : 0};
   gb_tail_table tail{d.use_tail.data(), d.tail_energy.data(), n, 0};
   GB(gb_upload_forcefield(S.e, &ff, &tail));
   gb_box box; std::memset(&box, 0, sizeof(box));
@@ -960,7 +959,23 @@ int main(int argc, char** argv)
       for(const auto& F : d.fw) std::printf(", %zu", F.type.size());
       std::printf("], \"block_pockets\": [");
       for(size_t c = 0; c < d.comps.size(); c++) std::printf("%s%zu", c ? ", " : "", d.comps[c].pocket_radii.size());
-      std::printf("]}\n");
+      std::printf("]");
+      if(d.use1264)
+      {
+        // pairs with an r^-4 term: [name i, name j, C12, C6, C4, shift] in internal units
+        std::printf(", \"lj1264\": [");
+        const int n = (int) d.names.size(); bool first = true;
+        for(int i = 0; i < n; i++)
+          for(int j = i; j < n; j++)
+            if(d.z[i * n + j] != 0.0)
+            {
+              std::printf("%s[\"%s\", \"%s\", %.12e, %.12e, %.12e, %.12e]", first ? "" : ", ", d.names[i].c_str(), d.names[j].c_str(),
+                          d.eps[i * n + j], d.sigma[i * n + j], d.z[i * n + j], d.shift[i * n + j]);
+              first = false;
+            }
+        std::printf("]");
+      }
+      std::printf("}\n");
     }
     catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
     return 0;

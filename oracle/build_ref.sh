@@ -40,7 +40,7 @@ fi
 
 if [ "$WHAT" = "all" ] || [ "$WHAT" = "examples" ]; then
   echo "[build_ref] example decks"
-  for ex in Henrys_coefficient CO2-MFI CO2_NaX_Zeolite XeKr-Mixture Ar_MgMOF74_UFF Bae-Mixture BlockPocket CO2_MgMOF74_UFF Tail-Correction Ionic-MOF-mixtures; do
+  for ex in Henrys_coefficient CO2-MFI CO2_NaX_Zeolite XeKr-Mixture Ar_MgMOF74_UFF Bae-Mixture BlockPocket CO2_MgMOF74_UFF Tail-Correction Ionic-MOF-mixtures TIP4PEW-MgMOF-LJ1264; do
     mkdir -p "$OUT/examples/$ex"
     # inputs only: no committed outputs, no restart dumps
     find "$REF/Examples/$ex" -maxdepth 1 -type f \

@@ -245,3 +245,58 @@ def test_nist_spce_known_answers(gpu_engine_factory, b):
     total = v["GGVDW"] + v["GGReal"] + E["GGEwaldE"] + tail
     assert abs(total - ref["total"]) <= 2e-5
     eng.close()
+
+
+def _as_1264(ff, seed=3):
+    """the same Lennard-Jones table restated in the polynomial form UseLJ1264 uses (read_data.cpp:1196-1230:
+    C12 = 4 eps sigma^12, C6 = 4 eps sigma^6), plus r^-4 and r^-10 terms of a size that matters at adsorption distances"""
+    from graspa_b200.types import ForceField
+    rng = np.random.default_rng(seed)
+    n = ff.ntypes
+    s6 = ff.sigma ** 6
+    c4 = rng.normal(size=(n, n)) * 30.0; c4 = 0.5 * (c4 + c4.T)
+    c10 = rng.normal(size=(n, n)) * 3.0e4; c10 = 0.5 * (c10 + c10.T)
+    C12 = 4.0 * ff.epsilon * s6 * s6; C6 = 4.0 * ff.epsilon * s6
+    ri2 = 1.0 / ff.cutoff_vdw_sq
+    shift = C12 * ri2 ** 6 - C6 * ri2 ** 3 + c10.ravel() * ri2 ** 5 + c4.ravel() * ri2 ** 2      # Get_Shifted_Value_Coeff read_data.cpp:750-758
+    return ForceField(C12, C6, shift, ff.cutoff_vdw, ff.cutoff_coul, overlap=ff.overlap, no_charges=ff.no_charges, use1264=True,
+                      z=c4.ravel(), c10=c10.ravel())
+
+
+@pytest.mark.parametrize("name", ["A", "B"])
+def test_polynomial_1264_potential_vs_oracle(gpu_engine_factory, oracle, name):
+    """UseLJ1264: U = C12/r^12 - C6/r^6 + C10/r^10 + C4/r^4 - shift (VDW, maths.cuh:452-476) through trial energies,
+    whole-system totals and a Widom batch"""
+    box, ff0, s, z = load_config(name)
+    ff = _as_1264(ff0)
+    comp = int(z["comp"]); ms = int(s.molsize[comp])
+    eng = gpu_engine_factory(box, ff, s, float(z["beta"]), 10, 10)
+    rng = np.random.default_rng(17)
+    L = np.array([box.cell[0], box.cell[4], box.cell[8]])
+    n = 64 * 3
+    tr = TrialAtoms(rng.random((n, 3)) * L, rng.normal(size=n) * 0.3, rng.integers(0, ff.ntypes, size=n))
+    e_gpu, f_gpu = eng.trial_energies(64, 3, tr, comp, 999)
+    e_cpu, f_cpu, _ = oracle.trial_energies(box, ff, s, 64, 3, tr, comp, 999)
+    assert (f_gpu == f_cpu).all()
+    e_gpu, f_gpu = eng.trial_energies(n, 1, tr, comp, 999)            # single atoms: enough of them survive OverlapCriteria
+    e_cpu, f_cpu, _ = oracle.trial_energies(box, ff, s, n, 1, tr, comp, 999)
+    assert (f_gpu == f_cpu).all() and (f_cpu == 0).sum() > 30
+    ok = f_cpu == 0
+    assert np.max(np.abs(e_gpu[ok] - e_cpu[ok]) / _scale(e_cpu[ok])) < ETOL
+    # the r^-4 / r^-10 terms are really in play
+    e_lj, f_lj, _ = oracle.trial_energies(box, ff0, s, n, 1, tr, comp, 999)
+    both = ok & (f_lj == 0)
+    assert np.max(np.abs(e_lj[both] - e_cpu[both])) > 1.0
+    got = eng.total_vdw_real()
+    ref = oracle.total_vdw_real(box, ff, s)
+    g = np.array([got["HHVDW"], got["HHReal"], got["HGVDW"], got["HGReal"], got["GGVDW"], got["GGReal"]])
+    assert rel_err(g, ref, floor=max(1.0, float(np.abs(ref).max()) * 1e-6)) < ETOL
+    nw = 256
+    rnd = rng.random((nw, 20, 3)); uni = rng.random((nw, 2))
+    ws = oracle.WidomSetup(box, ff, s, comp, float(z["beta"]), 10, 10, z["sf_ads"], z["sf_fw"])
+    wref, rstage, _ = oracle.widom_batch(ws, rnd, uni)
+    eng.upload_structure_factors(z["sf_ads"], z["sf_fw"]); eng.set_exclusion_constants(comp, *ws.excl)
+    out, stage, sums = eng.widom_batch(comp, rnd.reshape(-1, 3), uni)
+    assert (np.where(stage == 3, 2, stage) == rstage).all()
+    assert rel_err(out[:, 0], wref[:, 0], floor=1e-290) < 1e-9
+    eng.close()
