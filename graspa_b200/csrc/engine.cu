@@ -91,6 +91,9 @@ struct gb_engine
   int i_ads = 0, i_fw = 1, i_tmp = 2;     // pointer swap = index swap (Update_Vector_Ewald)
   bool have_sf = false;
   DevBuf<double> d_ktab; bool ktab_dirty = true;
+  // volume move (gb_volume_move_trial / _finish): the state to fall back to on rejection
+  gb_box cur_box{}, vol_old_box{}; bool vol_pending = false, vol_had_sf = false; long long vol_old_nvec = 0;
+  DevBuf<double> d_vol_xyz, d_vol_sf;
 
   // CBMC
   int ntrials = 10, norient = 10; bool have_cbmc = false;
@@ -533,11 +536,13 @@ int gb_upload_forcefield(gb_engine* e, const gb_forcefield* ff, const gb_tail_ta
   return GB_OK;
 }
 
-int gb_upload_box(gb_engine* e, const gb_box* box)
+namespace {
+// Box scalars, active k table and structure-factor storage for `box`.  Does not touch the atom slots.
+int apply_box(gb_engine* e, const gb_box* box)
 {
-  if(e) e->tail_memo.clear();                                     // the tail deltas carry 1 / volume
-  if(!e || !box) return fail(GB_ERR_ARG, "null argument");
+  e->tail_memo.clear();                                           // the tail deltas carry 1 / volume
   CUDA_TRY(cudaSetDevice(e->device));
+  e->cur_box = *box;
   for(int i = 0; i < 9; i++) { e->P.cell[i] = box->cell[i]; e->P.inv[i] = box->inverse_cell[i]; }
   e->P.volume = box->volume; e->P.alpha = box->alpha; e->P.prefactor = box->prefactor; e->P.recip_cutoff = box->reciprocal_cutoff;
   e->P.cubic = box->cubic; e->P.use_lammps = box->use_lammps_ewald;
@@ -597,7 +602,17 @@ int gb_upload_box(gb_engine* e, const gb_box* box)
     CUDA_TRY(cudaMemset(e->d_sf[i].p, 0, (size_t) std::max<long long>(2 * e->nvec, 2) * sizeof(double)));
   }
   e->i_ads = 0; e->i_fw = 1; e->i_tmp = 2; e->have_sf = false; e->ktab_dirty = true;
-  e->have_box = true; e->device_stale = true;
+  e->have_box = true;
+  return GB_OK;
+}
+} // namespace
+
+int gb_upload_box(gb_engine* e, const gb_box* box)
+{
+  if(!e || !box) return fail(GB_ERR_ARG, "null argument");
+  if(e->vol_pending) return fail(GB_ERR_STATE, "a volume move is pending: call gb_volume_move_finish first");
+  int rc = apply_box(e, box); if(rc) return rc;
+  e->device_stale = true;
   return GB_OK;
 }
 
@@ -944,16 +959,33 @@ int gb_tail_identity_swap(gb_engine* e, int32_t newc, int32_t oldc, double* out)
 }
 
 // ---------------------------------------------------------------------------------------------- totals
-int gb_total_vdw_real(gb_engine* e, gb_move_energy* out)
+namespace {
+int total_vdw_real_impl(gb_engine* e, gb_move_energy* out, int32_t* overlap);
+int total_ewald_impl(gb_engine* e, int32_t store, bool device_convention, gb_move_energy* out);
+}
+
+int gb_total_vdw_real(gb_engine* e, gb_move_energy* out) { return total_vdw_real_impl(e, out, nullptr); }
+int gb_total_ewald(gb_engine* e, int32_t store, gb_move_energy* out) { return total_ewald_impl(e, store, false, out); }
+
+namespace {
+// overlap != NULL: also report whether any pair trips OverlapCriteria or r^2 < 0.01 (VDWCoulEnergy_Total, VDW_Coulomb.cu:1385-1386)
+int total_vdw_real_impl(gb_engine* e, gb_move_energy* out, int32_t* overlap)
 {
   int rc = ready(e); if(rc) return rc;
   if(!out) return fail(GB_ERR_ARG, "null out");
   memset(out, 0, sizeof(*out));
-  TotalArgs A; A.L = seg_list(e, 0); A.nhost = e->nhost;
+  if(overlap) *overlap = 0;
+  TotalArgs A; A.L = seg_list(e, 0); A.nhost = e->nhost; A.flag = nullptr;
   int nlive = 0; for(int s = 0; s < A.L.nseg; s++) nlive += A.L.count[s];
   if(nlive == 0) return GB_OK;
   CUDA_TRY(e->d_scratch.reserve((size_t) nlive * 6 + 8));
   A.out = e->d_scratch.p;
+  if(overlap)
+  {
+    CUDA_TRY(e->d_iscratch.reserve(16));
+    CUDA_TRY(cudaMemsetAsync(e->d_iscratch.p, 0, sizeof(int), e->stream));
+    A.flag = e->d_iscratch.p;
+  }
   Timer tm(e, 0);
   k_total_vdw_real<<<nlive, 128, 0, e->stream>>>(e->P, sys_view(e), A);
   k_reduce_partials<<<1, 32, 0, e->stream>>>(e->d_scratch.p, nlive, 6, e->d_result.p + 16);
@@ -964,10 +996,18 @@ int gb_total_vdw_real(gb_engine* e, gb_move_energy* out)
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   const double* r = e->h_pinned + 16;
   out->HHVDW = r[0]; out->HHReal = r[1]; out->HGVDW = r[2]; out->HGReal = r[3]; out->GGVDW = r[4]; out->GGReal = r[5];
+  if(overlap)
+  {
+    int f = 0;
+    CUDA_TRY(cudaMemcpy(&f, e->d_iscratch.p, sizeof(int), cudaMemcpyDeviceToHost));
+    *overlap = f ? 1 : 0;
+  }
   return GB_OK;
 }
 
-int gb_total_ewald(gb_engine* e, int32_t store, gb_move_energy* out)
+// device_convention = false: the terms as the CPU Ewald_Total reports them (GG includes HH, ewald_preparation.h:174);
+// true: as the device Ewald_TotalEnergy does (HH, HG, GG separate, each minus its own exclusions; Ewald_Energy_Functions.h:1366-1428)
+int total_ewald_impl(gb_engine* e, int32_t store, bool device_convention, gb_move_energy* out)
 {
   int rc = ready(e); if(rc) return rc;
   if(!out) return fail(GB_ERR_ARG, "null out");
@@ -1016,15 +1056,105 @@ int gb_total_ewald(gb_engine* e, int32_t store, gb_move_energy* out)
   CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 32, e->d_result.p + 32, (8 + 2 * GBK_MAX_SEG) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   double GG = e->h_pinned[32], HH = e->h_pinned[33], HG = e->h_pinned[34];
-  GG += HH;                                                            // ewald_preparation.h:174
+  if(!device_convention) GG += HH;                                     // ewald_preparation.h:174
   for(int c = 0; c < e->ncomp; c++)
   {
     const double self = e->h_pinned[40 + 2 * c], intra = e->h_pinned[40 + 2 * c + 1];
+    if(device_convention)
+    {
+      if(c < e->nhost) { HH -= self; HH -= intra; } else { GG -= self; GG -= intra; }
+      continue;
+    }
     GG -= self; GG -= intra;
     if(c < e->nhost && A.has_fw) { HH -= self; HH -= intra; }
   }
   out->GGEwaldE = GG; out->HHEwaldE = HH; out->HGEwaldE = HG;
   if(store) { e->have_sf = true; e->ktab_dirty = true; }
+  return GB_OK;
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// NPT volume move (VolumeMove, mc_box.h:196-320)
+// ------------------------------------------------------------------------------------------------
+int gb_volume_move_trial(gb_engine* e, const gb_box* new_box, double scale, gb_move_energy* out, int32_t* overlap)
+{
+  int rc = ready(e); if(rc) return rc;
+  if(!new_box || !out || !overlap) return fail(GB_ERR_ARG, "null argument");
+  if(e->vol_pending) return fail(GB_ERR_STATE, "a volume move is already pending");
+  if(!(scale > 0.0)) return fail(GB_ERR_ARG, "scale must be positive");
+  memset(out, 0, sizeof(*out)); *overlap = 0;
+  const size_t n = (size_t) e->nslots;
+  // 1. what a rejection falls back to: positions, box, stored structure factors
+  CUDA_TRY(e->d_vol_xyz.reserve(3 * n + 8));
+  CUDA_TRY(cudaMemcpyAsync(e->d_vol_xyz.p, e->dx.p, n * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->d_vol_xyz.p + n, e->dy.p, n * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->d_vol_xyz.p + 2 * n, e->dz.p, n * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  e->vol_old_box = e->cur_box; e->vol_had_sf = e->have_sf; e->vol_old_nvec = e->nvec;
+  const size_t sfn = (size_t) std::max<long long>(2 * e->nvec, 2);
+  CUDA_TRY(e->d_vol_sf.reserve(2 * sfn));
+  CUDA_TRY(cudaMemcpyAsync(e->d_vol_sf.p, e->d_sf[e->i_ads].p, sfn * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->d_vol_sf.p + sfn, e->d_sf[e->i_fw].p, sfn * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  // 2. ScalePositions (mc_box.h:41-64): every molecule of components >= 1 moves with its first atom, rigid about it
+  ScaleArgs SA; memset(&SA, 0, sizeof(SA)); SA.scale = scale;
+  long long nmol = 0;
+  for(int c = 1; c < e->ncomp && SA.nseg < GBK_MAX_SEG; c++)
+  {
+    const Comp& C = e->comps[c];
+    if(C.natoms == 0) continue;
+    SA.start[SA.nseg] = C.offset; SA.ms[SA.nseg] = C.molsize; SA.nmol[SA.nseg] = C.natoms / C.molsize; nmol += SA.nmol[SA.nseg]; SA.nseg++;
+  }
+  if(nmol > 0)
+  {
+    k_scale_molecules<<<(unsigned)((nmol + 127) / 128), 128, 0, e->stream>>>(e->P, SA, e->dx.p, e->dy.p, e->dz.p);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->vol_pending = true; e->committed = true;
+  // 3. the new box: scalars, k table, empty structure factors; fractional coordinates of every slot
+  rc = apply_box(e, new_box); if(rc) return rc;
+  rc = ready(e); if(rc) return rc;
+  if(n > 0)
+  {
+    k_frac_update<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->P, e->dx.p, e->dy.p, e->dz.p, e->dfx.p, e->dfy.p, e->dfz.p, 0, (int) n);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  e->pack_dirty = true;
+  // 4. total energies of the scaled system; the structure factors of the new state are stored on the way
+  gb_move_energy v, w;
+  rc = total_vdw_real_impl(e, &v, overlap); if(rc) return rc;
+  rc = total_ewald_impl(e, 1, true, &w); if(rc) return rc;
+  *out = v; out->HHEwaldE = w.HHEwaldE; out->HGEwaldE = w.HGEwaldE; out->GGEwaldE = w.GGEwaldE;
+  return GB_OK;
+}
+
+int gb_volume_move_finish(gb_engine* e, int32_t accept)
+{
+  if(!e) return fail(GB_ERR_ARG, "null engine");
+  if(!e->vol_pending) return fail(GB_ERR_STATE, "no volume move is pending");
+  CUDA_TRY(cudaSetDevice(e->device));
+  e->vol_pending = false;
+  if(accept) return GB_OK;                                            // CopyScaledPositions + swap of the structure factors: already in place
+  // Revert_Boxsize (mc_box.h:129-190) + the old positions and structure factors
+  const size_t n = (size_t) e->nslots;
+  int rc = apply_box(e, &e->vol_old_box); if(rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->dx.p, e->d_vol_xyz.p, n * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->dy.p, e->d_vol_xyz.p + n, n * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->dz.p, e->d_vol_xyz.p + 2 * n, n * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  const size_t sfn = (size_t) std::max<long long>(2 * e->vol_old_nvec, 2);
+  CUDA_TRY(cudaMemcpyAsync(e->d_sf[e->i_ads].p, e->d_vol_sf.p, sfn * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->d_sf[e->i_fw].p, e->d_vol_sf.p + sfn, sfn * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  e->have_sf = e->vol_had_sf; e->ktab_dirty = true; e->pack_dirty = true;
+  rc = ready(e); if(rc) return rc;
+  if(n > 0)
+  {
+    k_frac_update<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->P, e->dx.p, e->dy.p, e->dz.p, e->dfx.p, e->dfy.p, e->dfz.p, 0, (int) n);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
   return GB_OK;
 }
 

@@ -14,6 +14,39 @@ __global__ void k_frac_update(DevParams P, const double* __restrict__ x, const d
   if(i < count) to_frac(P, x[start + i], y[start + i], z[start + i], fx[start + i], fy[start + i], fz[start + i]);
 }
 
+// ScalePositions (mc_box.h:18-64): a molecule follows its first atom, which scales with the box; the other atoms keep their
+// minimum-image offset from it (old box).  One thread per molecule of the listed components.
+struct ScaleArgs { int nseg; int start[GBK_MAX_SEG], ms[GBK_MAX_SEG], nmol[GBK_MAX_SEG]; double scale; };
+
+__global__ void k_scale_molecules(DevParams P, ScaleArgs A, double* x, double* y, double* z)
+{
+  long long m = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  int seg = 0;
+  while(seg < A.nseg && m >= A.nmol[seg]) { m -= A.nmol[seg]; seg++; }
+  if(seg >= A.nseg) return;
+  const int first = A.start[seg] + (int) m * A.ms[seg];
+  const double cx = x[first], cy = y[first], cz = z[first];
+  for(int a = 0; a < A.ms[seg]; a++)
+  {
+    double dx = x[first + a] - cx, dy = y[first + a] - cy, dz = z[first + a] - cz;
+    if(P.cubic)
+    {
+      dx -= (double) static_cast<int>(dx * P.inv[0] + ((dx >= 0.0) ? 0.5 : -0.5)) * P.cell[0];
+      dy -= (double) static_cast<int>(dy * P.inv[4] + ((dy >= 0.0) ? 0.5 : -0.5)) * P.cell[4];
+      dz -= (double) static_cast<int>(dz * P.inv[8] + ((dz >= 0.0) ? 0.5 : -0.5)) * P.cell[8];
+    }
+    else
+    {
+      double sx = P.inv[0] * dx + P.inv[3] * dy + P.inv[6] * dz, sy = P.inv[1] * dx + P.inv[4] * dy + P.inv[7] * dz, sz = P.inv[2] * dx + P.inv[5] * dy + P.inv[8] * dz;
+      sx -= (double) static_cast<int>(sx + ((sx >= 0.0) ? 0.5 : -0.5));
+      sy -= (double) static_cast<int>(sy + ((sy >= 0.0) ? 0.5 : -0.5));
+      sz -= (double) static_cast<int>(sz + ((sz >= 0.0) ? 0.5 : -0.5));
+      dx = P.cell[0] * sx + P.cell[3] * sy + P.cell[6] * sz; dy = P.cell[1] * sx + P.cell[4] * sy + P.cell[7] * sz; dz = P.cell[2] * sx + P.cell[5] * sy + P.cell[8] * sz;
+    }
+    x[first + a] = cx * A.scale + dx; y[first + a] = cy * A.scale + dy; z[first + a] = cz * A.scale + dz;
+  }
+}
+
 // staged pack of the framework (all host components' live atoms): [fx | fy | fz | q | type], each npad long
 __global__ void k_build_pack(const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
                              const double* __restrict__ q, const double* __restrict__ scoul, const int* __restrict__ type,

@@ -67,7 +67,7 @@ k_trial_energies(DevParams P, SysView S, SegList L, TrialBuf B, int cs, int new_
 // total VDW + real: every live atom is a one-atom "trial group" against all live atoms with the own-molecule
 // exclusion; 0.5 x the double-counted sum, exactly the reference's CPU loop structure (VDW_Coulomb.cu:94-206).
 // ---------------------------------------------------------------------------------------------
-struct TotalArgs { SegList L; int nhost; double* out; /* [natoms_live][6] */ };
+struct TotalArgs { SegList L; int nhost; double* out; /* [natoms_live][6] */ int* flag; /* NULL or one word: any overlapping pair */ };
 
 __global__ void __launch_bounds__(128)
 k_total_vdw_real(DevParams P, SysView S, TotalArgs A)
@@ -106,6 +106,7 @@ k_total_vdw_real(DevParams P, SysView S, TotalArgs A)
     for(int w = 0; w < nwarps; w++) s += red[w * 8 + threadIdx.x];
     A.out[(size_t) blockIdx.x * 6 + threadIdx.x] = 0.5 * s;
   }
+  if(A.flag && __any_sync(0xffffffffu, flag) && lane_id() == 0) atomicOr(A.flag, 1);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -33,7 +33,8 @@ DECLARED_SYMBOLS = [
     "gb_lambda_change_delta", "gb_ewald_delta_lambda_change", "gb_accept_lambda_change",
     "gb_tail_total", "gb_tail_difference", "gb_tail_identity_swap",
     "gb_accept_translation", "gb_accept_insertion", "gb_accept_deletion", "gb_accept_reinsertion", "gb_accept_identity_swap", "gb_append_molecule",
-    "gb_number_of_molecules", "gb_total_vdw_real", "gb_total_ewald", "gb_widom_batch", "gb_widom_first_bead_success",
+    "gb_number_of_molecules", "gb_total_vdw_real", "gb_total_ewald", "gb_volume_move_trial", "gb_volume_move_finish",
+    "gb_widom_batch", "gb_widom_first_bead_success",
     "gb_launch_count", "gb_timing_enable", "gb_timing_read", "gb_measure_fp64_peak",
 ]
 
@@ -164,13 +165,30 @@ class Engine:
         self._chk(self.lib.gb_upload_forcefield(self.h, C.byref(g), C.byref(t)))
         self.ff = ff
 
-    def upload_box(self, box: Box):
+    @staticmethod
+    def _gb_box(box: Box):
         g = GbBox()
         g.cell[:] = list(box.cell); g.inverse_cell[:] = list(box.inv)
         g.volume = box.volume; g.alpha = box.alpha; g.prefactor = box.prefactor; g.reciprocal_cutoff = box.recip_cutoff
         g.kmax[:] = list(box.kmax); g.cubic = int(box.cubic); g.use_lammps_ewald = int(box.use_lammps_ewald)
+        return g
+
+    def upload_box(self, box: Box):
+        g = self._gb_box(box)
         self._chk(self.lib.gb_upload_box(self.h, C.byref(g)))
         self.box = box
+
+    def volume_move_trial(self, new_box: Box, scale):
+        """VolumeMove up to the acceptance test (mc_box.h:196-254) -> (energies of the scaled system, overlap flag)"""
+        g = self._gb_box(new_box); m = GbMoveEnergy(); ov = C.c_int32(0)
+        self._chk(self.lib.gb_volume_move_trial(self.h, C.byref(g), C.c_double(scale), C.byref(m), C.byref(ov)))
+        self._pending_box = new_box
+        return m.as_dict(), int(ov.value)
+
+    def volume_move_finish(self, accept):
+        self._chk(self.lib.gb_volume_move_finish(self.h, C.c_int32(int(bool(accept)))))
+        if accept:
+            self.box = self._pending_box
 
     def upload_system(self, s: System):
         self._chk(self.lib.gb_set_components(self.h, C.c_int32(s.ncomp), C.c_int32(s.nhost)))

@@ -96,6 +96,8 @@ struct Deck
   // UseLJ1264 yes: eps / sigma hold the polynomial coefficients C12 / C6, z the r^-4 coefficient, c10 the r^-10 one
   // (ForceField_Processing read_data.cpp:1196-1230, VDW maths.cuh:452-476)
   bool use1264 = false; std::vector<double> c4_in, z, c10;
+  double volume_move_prob = 0.0;           // NPTVolumeChangeProbability (Components::VolumeMoveProbability)
+  double ewald_tol1 = 0.0;                 // Boxsize::tol1: kmax follows the box in a volume move (mc_box.h:84-94)
   // framework
   double cell[9] = {0}, inv[9] = {0}, volume = 0;
   std::vector<double> fpos; std::vector<int> ftype; std::vector<double> fcharge;  // supercell atoms
@@ -180,6 +182,7 @@ inline void read_simulation_input(Deck& d, const std::string& dir)
     else if(has("NumberofFrameworkComponents")) d.n_framework_components = std::stoi(t[1]);
     else if(has("RestartFile")) d.restart_file = ieq(t[1], "yes");
     else if(has("UseLJ1264")) d.use1264 = ieq(t[1], "yes");
+    else if(has("NPTVolumeChangeProbability")) { const double v = std::stod(t[1]); if(v > 0) d.volume_move_prob = v; }      // read_data.cpp:404-413
     else if(has("UseMaxStep")) d.use_max_step = ieq(t[1], "yes");
     else if(has("MaxStepPerCycle")) d.max_step_per_cycle = std::stol(t[1]);
     else if(has("RandomSeed")) d.random_seed = std::stoi(t[1]);
@@ -514,7 +517,7 @@ inline void setup_ewald(Deck& d)
   const double tol = std::sqrt(std::fabs(std::log(p * rc)));
   const double alpha = std::sqrt(std::fabs(std::log(p * rc * tol))) / rc;
   const double tol1 = std::sqrt(-std::log(p * rc * std::pow(2.0 * tol * alpha, 2)));
-  d.alpha = alpha;
+  d.alpha = alpha; d.ewald_tol1 = tol1;
   d.kmax[0] = (int) std::round(0.25 + d.cell[0] * alpha * tol1 / PI);
   d.kmax[1] = (int) std::round(0.25 + d.cell[4] * alpha * tol1 / PI);
   d.kmax[2] = (int) std::round(0.25 + d.cell[8] * alpha * tol1 / PI);

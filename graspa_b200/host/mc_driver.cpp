@@ -51,7 +51,7 @@ struct Energy   // MoveEnergy, data_struct.h:416-431 (terms this driver touches)
 struct CompState
 {
   // cumulative move probabilities, Move_Statistics::NormalizeProbabilities data_struct.h:569-608
-  double cTrans = 0, cRot = 0, cSpecial = 0, cWidom = 0, cReins = 0, cIdentity = 0, cCBCF = 0, cSwap = 0, total_prob = 0;
+  double cTrans = 0, cRot = 0, cSpecial = 0, cWidom = 0, cReins = 0, cIdentity = 0, cCBCF = 0, cSwap = 0, cVolume = 0, total_prob = 0;
   double max_trans[3] = {1, 1, 1}, max_rot[3] = {0, 0, 0};
   MoveCount trans, rot, ins, del, reins, widom, idswap_add, idswap_remove;
   std::vector<MoveCount> idswap_to;             // IdentitySwap_Total_TO / _Acc_TO per destination component
@@ -83,6 +83,8 @@ struct Sim
   long total_molecules = 1;                       // TotalNumberOfMolecules counts the framework as one
   Energy running;                                 // SystemComponents.deltaE
   double initial_framework_ewald = 0.0;           // SystemComponents.InitialFrameworkEwald
+  Energy createmol_energy;                        // SystemComponents.CreateMol_Energy: the energy the running deltas start from
+  MoveCount vol_window, vol_total; double vol_max_change = 0.025;   // VolumeMoveAttempts/Accepted, VolumeMoveMaxChange (data_struct.h:1028-1034)
   int nblock = 5; long block_size = 1; bool production = false;
   long moves_done = 0;
   int device = -1;                                // CUDA device of the engine (-1: the current one)
@@ -230,11 +232,14 @@ void setup_probabilities(Sim& S)
   {
     const deck::Component& M = S.d.comps[c]; CompState& X = S.C[c + S.nhost];
     double t = M.p_translation, r = M.p_rotation, sp = 0.0, w = M.p_widom, re = M.p_reinsertion, id = M.p_identity, sw = M.p_swap, cb = 0.0;
-    double tot = t + r + sp + w + re + id + sw + cb;
+    // the volume-move probability enters the total but is itself NOT divided by it (NormalizeProbabilities, data_struct.h:569-608):
+    // the window [cSwap, 1) it ends up with is vol / total all the same
+    const double vol = S.d.volume_move_prob;
+    double tot = t + r + sp + w + re + id + sw + cb + vol;
     if(tot > 1e-10) { t /= tot; r /= tot; sp /= tot; w /= tot; sw /= tot; cb /= tot; re /= tot; id /= tot; tot = 1.0; }
     X.total_prob = tot;
     X.cTrans = t; X.cRot = r + X.cTrans; X.cSpecial = sp + X.cRot; X.cWidom = w + X.cSpecial; X.cReins = re + X.cWidom;
-    X.cIdentity = id + X.cReins; X.cCBCF = cb + X.cIdentity; X.cSwap = sw + X.cCBCF;
+    X.cIdentity = id + X.cReins; X.cCBCF = cb + X.cIdentity; X.cSwap = sw + X.cCBCF; X.cVolume = vol + X.cSwap;
     // InitializeMaxTranslationRotation fxn_main.h:151-160 then Prepare... :222-227 (0.1 x box lengths, 30 degrees)
     X.max_trans[0] = S.d.cell[0] * 0.1; X.max_trans[1] = S.d.cell[4] * 0.1; X.max_trans[2] = S.d.cell[8] * 0.1;
     for(int k = 0; k < 3; k++) X.max_rot[k] = 30.0 / (180 / 3.1415);
@@ -668,6 +673,90 @@ void move_identity_swap(Sim& S)
 }
 
 // RunMoves, axpy.cu:102-298
+// VolumeMove, mc_box.h:196-320: ln V random walk, molecules follow their first atom, total energies of the scaled system
+void move_volume(Sim& S, int comp)
+{
+  deck::Deck& d = S.d;
+  S.vol_window.total++;
+  const double oldV = d.volume;
+  const double newV = std::exp(std::log(oldV) + S.vol_max_change * 2.0 * (S.rng.uniform() - 0.5));
+  const double scale = std::cbrt(newV / oldV), inv_scale = 1.0 / scale;
+  gb_box box; std::memset(&box, 0, sizeof(box));
+  for(int i = 0; i < 9; i++) { box.cell[i] = d.cell[i] * scale; box.inverse_cell[i] = d.inv[i] * inv_scale; }
+  box.volume = newV; box.alpha = d.alpha; box.prefactor = d.prefactor;
+  box.cubic = !((std::fabs(d.cell[3]) + std::fabs(d.cell[6]) + std::fabs(d.cell[7])) > 1e-10);
+  box.use_lammps_ewald = d.lammps_ewald ? 1 : 0;
+  for(int k = 0; k < 3; k++) box.kmax[k] = d.kmax[k];
+  box.reciprocal_cutoff = d.recip_cutoff;
+  if(!d.no_charges)
+  {
+    // ScalePositions, mc_box.h:84-94 (1 / pi as the literal the reference multiplies by)
+    for(int k = 0; k < 3; k++) box.kmax[k] = (int) std::round(0.25 + box.cell[4 * k] * d.alpha * d.ewald_tol1 * 0.31830988618);
+    box.reciprocal_cutoff = std::pow(1.05 * (double) std::max(box.kmax[0], std::max(box.kmax[1], box.kmax[2])), 2);
+  }
+  gb_move_energy m; int32_t overlap = 0;
+  GB(gb_volume_move_trial(S.e, &box, scale, &m, &overlap));
+  Energy N; N.HHVDW = m.HHVDW; N.HGVDW = m.HGVDW; N.GGVDW = m.GGVDW; N.HHReal = m.HHReal; N.HGReal = m.HGReal; N.GGReal = m.GGReal;
+  N.HHEwald = m.HHEwaldE; N.HGEwald = m.HGEwaldE; N.GGEwald = m.GGEwaldE;
+  GB(gb_tail_total(S.e, &N.Tail));
+  bool accept = false; Energy D;
+  if(!overlap)
+  {
+    const double nmol = (double) (S.total_molecules - S.nhost);     // Get_TotalNumberOfMolecule_In_Box: no framework "molecules"
+    D = N; D.add(S.createmol_energy, -1.0); D.add(S.running, -1.0);
+    const double pacc = std::exp((nmol + 1.0) * std::log(newV / oldV) - (D.total() + d.pressure * (newV - oldV)) * d.beta);
+    if(S.rng.uniform() < pacc) accept = true;
+  }
+  GB(gb_volume_move_finish(S.e, accept ? 1 : 0));
+  if(accept)
+  {
+    S.vol_window.accepted++;
+    S.running.add(D);
+    for(int i = 0; i < 9; i++) { d.cell[i] = box.cell[i]; d.inv[i] = box.inverse_cell[i]; }
+    d.volume = newV; d.recip_cutoff = box.reciprocal_cutoff;
+    for(int k = 0; k < 3; k++) d.kmax[k] = box.kmax[k];
+  }
+  // RunMoves books no energy change for this move itself (VolumeMove adds to deltaE on its own, mc_box.h:288): the trace line carries zeros
+  trace_move(S, "volume", comp, accept ? 1 : 0, 0, 0.0);
+}
+
+void update_max_volume_change(Sim& S, long cycle)     // Update_Max_VolumeChange, mc_utilities.h:691-712
+{
+  if(S.vol_window.total == 0) return;
+  const double ratio = (double) S.vol_window.accepted / (double) S.vol_window.total;
+  double c = ratio / 0.5;
+  if(c > 1.5) c = 1.5; else if(c < 0.5) c = 0.5;
+  S.vol_max_change *= c;
+  if(S.vol_max_change < 0.0005) S.vol_max_change = 0.0005;
+  if(S.vol_max_change > 0.5) S.vol_max_change = 0.5;
+  std::printf("CYCLE: %ld, AccRatio: %.5f, compare_to_target_ratio: %.5f, MaxVolumeChange: %.5f\n", cycle, ratio, c, S.vol_max_change);
+  S.vol_total.total += S.vol_window.total; S.vol_total.accepted += S.vol_window.accepted;
+  S.vol_window = MoveCount();
+}
+
+// CreateMolecule_InOneBox, axpy.cu:300-372: CBMC insertions that are taken whenever they can be built (RANDOM = 1e-100,
+// move_struct.h:57-59: no acceptance uniform is drawn) until CreateNumberOfMolecules of each species are in the box
+void create_molecules(Sim& S)
+{
+  for(int comp = S.nhost; comp < S.ncomp; comp++)
+  {
+    long todo = S.d.comps[comp - S.nhost].create_molecules, fails = 0;
+    CompState& X = S.C[comp];
+    while(todo > 0)
+    {
+      Growth G = insertion_body(S, comp);
+      const double pacc = G.success ? prefactor(S, comp, true) * G.W / S.d.comps[comp - S.nhost].ideal_rosenbluth : 0.0;
+      if(G.success && 1e-100 < pacc)
+      {
+        GB(gb_accept_insertion(S.e, comp));
+        X.nmol++; S.total_molecules++; todo--;
+        S.running.add(G.E);
+      }
+      else if(++fails > 10000000000L) die("bad insertions when creating molecules");
+    }
+  }
+}
+
 void run_move(Sim& S, long cycle)
 {
   int comp = 0;
@@ -690,6 +779,7 @@ void run_move(Sim& S, long cycle)
     else if(X.nmol > 0) move_deletion(S, comp, mol);
     else S.C[comp].del.total += 0;
   }
+  else if(R < X.cVolume) move_volume(S, comp);
   if(S.trace_lines == lines_before) trace_move(S, "none", comp, mol, 0, 0.0);     // the selected move had nothing to act on
 }
 
@@ -714,7 +804,10 @@ void run_phase(Sim& S, long cycles, bool production)
     for(long j = 0; j < steps; j++) run_move(S, i);
     if(production) for(int c = S.nhost; c < S.ncomp; c++) { S.C[c].load_sum += (double) S.C[c].nmol; S.C[c].load_n++; }
     if(i % 500 == 0)
+    {
       for(int c = 1; c < S.ncomp; c++) { update_max(S.C[c].max_trans, S.C[c].trans_window, S.C[c].trans_cum, 5.0); update_max(S.C[c].max_rot, S.C[c].rot_window, S.C[c].rot_cum, 3.14); }
+      update_max_volume_change(S, i);
+    }
   }
 }
 
@@ -1025,8 +1118,23 @@ int main(int argc, char** argv)
   GB(gb_upload_random_pool(S.e, S.pool.data(), (int64_t) S.pool_size));
   // initial energies + structure factors (Check_Simulation_Energy(INITIAL), fxn_main.h:282-404)
   { gb_move_energy w; GB(gb_total_ewald(S.e, 1, &w)); S.initial_framework_ewald = w.HHEwaldE; }
-  const Energy E0 = total_energy(S);
+  Energy E0 = total_energy(S);
   print_energy("INITIAL", E0);
+  {
+    long ncreate = 0; for(const auto& M : S.d.comps) ncreate += M.create_molecules;
+    if(ncreate > 0)
+    {
+      create_molecules(S);
+      // Check_Simulation_Energy(CREATEMOL) (main.cpp:340): the energies are computed afresh and the running deltas restart from
+      // them; the stored structure factors stay the incrementally updated ones (Allocate_Copy_Ewald_Vector runs at INITIAL only)
+      const Energy created = total_energy(S);
+      Energy dC = created; dC.add(E0, -1.0);
+      std::printf("CREATE MOLECULE: %ld molecules, running %.5f, recomputed %.5f\n", ncreate, S.running.total(), dC.total());
+      E0 = created; S.running = Energy();
+      print_energy("CREATED", E0);
+    }
+  }
+  S.createmol_energy = E0;
 
   if(timing) GB(gb_timing_enable(S.e, 1));
   const auto t0 = std::chrono::steady_clock::now();
@@ -1064,6 +1172,10 @@ int main(int argc, char** argv)
                     X.idswap_to[t].total, X.idswap_to[t].accepted);
     if(X.widom.total > 0) print_widom(S, c);
   }
+  if(S.d.volume_move_prob > 0.0)
+    std::printf("Volume Move: %ld/%ld accepted, final volume %.5f, cell %.5f %.5f %.5f, kmax %d %d %d, MaxVolumeChange %.5f\n",
+                S.vol_total.accepted + S.vol_window.accepted, S.vol_total.total + S.vol_window.total, S.d.volume, S.d.cell[0], S.d.cell[4], S.d.cell[8],
+                S.d.kmax[0], S.d.kmax[1], S.d.kmax[2], S.vol_max_change);
   const long cycles = S.d.init_cycles + S.d.equil_cycles + S.d.prod_cycles;
   int64_t launches = 0; gb_launch_count(S.e, &launches, 0);
   std::printf("Work took %.6f seconds\n", secs);

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GB_ABI_VERSION 4
+#define GB_ABI_VERSION 5
 
 enum {
   GB_OK = 0,
@@ -306,6 +306,18 @@ int  gb_total_vdw_real(gb_engine* e, gb_move_energy* out);
 /* total Fourier energy incl. self and intra-molecular exclusion; store_structure_factors != 0 also (re)initialises
  * AdsorbateEik / FrameworkEik from the current positions (what Ewald_Total + Allocate_Copy_Ewald_Vector do at init) */
 int  gb_total_ewald(gb_engine* e, int32_t store_structure_factors, gb_move_energy* out);
+
+/* NPT volume move (VolumeMove, mc_box.h:196-320).  gb_volume_move_trial does what the reference does between drawing the new
+ * volume and the acceptance test: ScalePositions (every molecule of components >= 1 follows its first atom, which scales by
+ * `scale` = cbrt(V_new / V_old); the other atoms keep their offset), the new box (`new_box`: cell * scale, inverse / scale,
+ * volume, kmax and reciprocal cut-off recomputed by the caller as mc_box.h:84-94 does), Total_VDW_Coulomb_Energy with the
+ * overlap flag, and Ewald_TotalEnergy in the DEVICE routine's convention (HH, HG, GG separate; Ewald_Energy_Functions.h:1366-1428),
+ * whose structure factors become the stored ones.  The tail term is gb_tail_total afterwards (it reads the new volume).
+ * gb_volume_move_finish(accept != 0) keeps that state (CopyScaledPositions + the swap of the structure factors);
+ * accept == 0 puts positions, box and structure factors back (Revert_Boxsize).  Until finish is called no other state-changing
+ * entry point may be used. */
+int  gb_volume_move_trial(gb_engine* e, const gb_box* new_box, double scale, gb_move_energy* new_total, int32_t* overlap);
+int  gb_volume_move_finish(gb_engine* e, int32_t accept);
 
 /* ------------------------------------------------------------------------------------------------
  * batched Widom insertions  (the whole of Insertion_Body mc_swap_utilities.h:3-133 for n independent ghost

@@ -47,6 +47,12 @@ if [ "$WHAT" = "all" ] || [ "$WHAT" = "examples" ]; then
         \( -name '*.def' -o -name '*.cif' -o -name '*.block' -o -name 'simulation.input' \) \
         -exec cp {} "$OUT/examples/$ex/" \;
   done
+  # the NPT example predates keywords the current reader insists on (Check_Inputs_In_read_data_cpp, read_data.cpp:115-131):
+  # its Widom_Trials / Widom_Orientation are spelled the current way and UseChargesFromCIFFile is stated
+  mkdir -p "$OUT/examples/NPTMC"
+  find "$REF/Examples/NPTMC" -maxdepth 1 -type f \( -name '*.def' -o -name '*.cif' -o -name 'simulation.input' \) -exec cp {} "$OUT/examples/NPTMC/" \;
+  chmod u+w "$OUT/examples/NPTMC/simulation.input"
+  sed -i 's/^Widom_Trials .*/NumberOfTrialPositions 10/; s/^Widom_Orientation .*/NumberOfTrialOrientations 10\nUseChargesFromCIFFile yes/' "$OUT/examples/NPTMC/simulation.input"
   # the NIST SPC/E known-answer decks: inputs + the RASPA-2 restart file they start from
   for b in 1 2 3 4; do
     d="$OUT/examples/Reference_NIST_SPCE/Box-$b"

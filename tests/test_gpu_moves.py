@@ -6,6 +6,7 @@ import pytest
 
 from graspa_b200.types import (TrialAtoms, CBMC_INSERTION, CBMC_DELETION, REINSERTION_INSERTION, REINSERTION_RETRACE,
                                TRANSLATION, ROTATION, INSERTION, DELETION, REINSERTION)
+from graspa_b200.types import pseudo_atom_counts
 from tests.conftest import load_config
 
 pytestmark = pytest.mark.gpu
@@ -600,3 +601,89 @@ def test_host_driver_reads_and_writes_raspa2_restarts(b, tmp_path):
     pos, chg = read_restart_positions(str(out), 0, 3, box, with_charge=True)
     assert pos.shape == (n, 3)
     assert np.max(np.abs(pos - s.pos[:n])) < 1e-9 and np.max(np.abs(chg - s.charge[:n])) < 1e-12
+
+
+def _scaled_state(box, s, scale, dk=0):
+    """what ScalePositions leaves (mc_box.h:18-94): cell * scale, every molecule of components >= 1 moved with its first atom,
+    kmax grown by dk so that the number of wave vectors really changes; -> (new Box, new System)"""
+    from graspa_b200.types import Box, System
+    kmax = tuple(int(k) + dk for k in box.kmax)
+    nb = Box(box.cell * scale, alpha=box.alpha, kmax=kmax, recip_cutoff=(1.05 * max(kmax)) ** 2, prefactor=box.prefactor)
+    pos = s.pos.copy()
+    for c in range(1, s.ncomp):
+        o = int(s.offsets[c]); ms = int(s.molsize[c])
+        for m in range(int(s.natoms[c]) // ms):
+            first = s.pos[o + m * ms].copy()
+            d = s.pos[o + m * ms:o + (m + 1) * ms] - first
+            f = d @ box.inv.reshape(3, 3)              # minimum image of the offsets (PBC, maths.cuh:427-450)
+            f -= np.trunc(f + np.where(f >= 0.0, 0.5, -0.5))
+            pos[o + m * ms:o + (m + 1) * ms] = first * scale + f @ box.cell.reshape(3, 3)
+    return nb, System(s.nhost, s.natoms.copy(), s.molsize.copy(), pos, s.charge.copy(), s.type.copy(), s.molid.copy(), alloc=s.alloc.copy())
+
+
+@pytest.mark.parametrize("scale,dk", [(1.013, 1), (0.991, 0)])
+def test_npt_volume_move_vs_oracle(gpu_engine_factory, oracle, scale, dk):
+    """gb_volume_move_trial / _finish (VolumeMove, mc_box.h:196-320): energies of the scaled system against the oracle's totals
+    on the restated ScalePositions result, rejection restores positions, box and structure factors exactly, acceptance leaves a
+    state on which the next move's deltas are those of the new box."""
+    box, ff, s, z, eng = _setup(gpu_engine_factory)
+    comp = 1; ms = 3; o = int(s.offsets[comp]); nmol = int(s.natoms[comp]) // ms
+    E0 = eng.total_ewald(store=True); V0 = eng.total_vdw_real()
+    sa0, sf0, _ = eng.download_structure_factors()
+    p0 = eng.snapshot_molecules(comp, 0, nmol)["pos"]
+    nb, ns = _scaled_state(box, s, scale, dk)
+
+    def check_trial():
+        got, ov = eng.volume_move_trial(nb, scale)
+        ref = oracle.total_vdw_real(nb, ff, ns)       # HHv, HHr, HGv, HGr, GGv, GGr
+        g = np.array([got["HHVDW"], got["HHReal"], got["HGVDW"], got["HGReal"], got["GGVDW"], got["GGReal"]])
+        assert np.max(np.abs(g - ref)) < ETOL * max(1.0, float(np.abs(ref).max()))
+        Ew, sa, sf = oracle.ewald_total(nb, ns)       # GG (incl. HH), HH, HG as the CPU routine reports them
+        dev = np.array([Ew[0] - Ew[1], Ew[1], Ew[2]])   # the device routine keeps HH out of GG
+        ge = np.array([got["GGEwaldE"], got["HHEwaldE"], got["HGEwaldE"]])
+        assert np.max(np.abs(ge - dev)) < ETOL * max(1.0, float(np.abs(dev).max()))
+        assert ov == 0
+        assert np.allclose(eng.snapshot_molecules(comp, 0, nmol)["pos"], ns.pos[o:o + nmol * ms], rtol=0, atol=1e-11)
+        return sa, sf
+
+    check_trial()
+    with pytest.raises(Exception):
+        eng.upload_box(box)                            # nothing else may change the state while the move is pending
+    eng.volume_move_finish(False)
+    # rejected: bitwise the state before the trial
+    assert np.array_equal(eng.snapshot_molecules(comp, 0, nmol)["pos"], p0)
+    sa1, sf1, _ = eng.download_structure_factors()
+    assert np.array_equal(sa1, sa0) and np.array_equal(sf1, sf0)
+    assert eng.total_vdw_real() == V0 and eng.total_ewald(store=False) == E0
+    # accepted: stored structure factors are those of the new state and the next move's deltas belong to the new box
+    sa_ref, sf_ref = check_trial()
+    eng.volume_move_finish(True)
+    sa2, sf2, _ = eng.download_structure_factors()
+    mag = max(1.0, float(np.abs(sf_ref).max()))
+    assert np.max(np.abs(sa2 - sa_ref)) < 1e-9 * mag and np.max(np.abs(sf2 - sf_ref)) < 1e-9 * mag
+    assert abs(eng.tail_total() - oracle.tail_total(ff, pseudo_atom_counts(ns, ff.ntypes), nb.volume)) < 1e-9
+    rng = np.random.default_rng(5)
+    pool = rng.random((8, 3)); eng.upload_random_pool(pool)
+    mol = 7; maxc = np.array([0.6, 0.7, 0.5])
+    newp = eng.single_body_propose(TRANSLATION, comp, mol, maxc, 0)
+    oldp = ns.pos[o + mol * ms:o + mol * ms + ms]
+    assert np.allclose(newp, oldp + maxc * 2.0 * (pool[0] - 0.5), rtol=0, atol=1e-11)
+    d, ov = eng.single_body_delta(comp)
+    q = s.charge[o:o + ms]; ty = s.type[o:o + ms]
+    ref, rov = oracle.single_body_delta(nb, ff, ns, comp, mol, TrialAtoms(oldp, q, ty), TrialAtoms(newp, q, ty))
+    got = np.array([d["HHVDW"], d["HHReal"], d["HGVDW"], d["HGReal"], d["GGVDW"], d["GGReal"]])
+    assert ov == rov and np.max(np.abs(got - ref)) < ETOL * 1e4
+    ew = eng.ewald_delta(comp, TRANSLATION)
+    ewr, _, _ = oracle.ewald_delta(nb, np.concatenate([oldp, newp]), np.concatenate([q, q]), np.ones(2 * ms), ms, ms, sa_ref, sf_ref)
+    assert _close(ew, ewr, scale=max(1.0, float(np.abs(ewr).max())))
+    eng.close()
+
+
+def test_npt_volume_move_reports_overlap(gpu_engine_factory):
+    """a strong compression pushes molecules into each other / the framework: the overlap flag of Total_VDW_Coulomb_Energy"""
+    box, ff, s, z, eng = _setup(gpu_engine_factory)
+    nb, ns = _scaled_state(box, s, 0.70)
+    _, ov = eng.volume_move_trial(nb, 0.70)
+    assert ov == 1
+    eng.volume_move_finish(False)
+    eng.close()
