@@ -49,7 +49,7 @@ struct Component
 {
   std::string name;
   double ideal_rosenbluth = 1.0, fugacity_coeff = 1.0, mol_fraction = 1.0;
-  double p_translation = 0, p_rotation = 0, p_widom = 0, p_reinsertion = 0, p_identity = 0, p_swap = 0;   // raw inputs
+  double p_translation = 0, p_rotation = 0, p_widom = 0, p_reinsertion = 0, p_identity = 0, p_swap = 0, p_gibbs_xfer = 0;   // raw inputs
   int create_molecules = 0;
   bool use_pr_eos = false;
   // molecules read from RestartInitial/System_0/restartfile (RestartFile yes): positions 3 x n, charges n; molecule-major
@@ -97,6 +97,8 @@ struct Deck
   // (ForceField_Processing read_data.cpp:1196-1230, VDW maths.cuh:452-476)
   bool use1264 = false; std::vector<double> c4_in, z, c10;
   double volume_move_prob = 0.0;           // NPTVolumeChangeProbability (Components::VolumeMoveProbability)
+  double gibbs_volume_prob = 0.0;          // GibbsVolumeChangeProbability (Gibbs::GibbsBoxProb)
+  int n_simulations = 1; bool single_simulation = true;
   double ewald_tol1 = 0.0;                 // Boxsize::tol1: kmax follows the box in a volume move (mc_box.h:84-94)
   // framework
   double cell[9] = {0}, inv[9] = {0}, volume = 0;
@@ -130,8 +132,9 @@ inline double tail_value(double eps, double sig, double cutsq)
   return 16.0 * 3.14159265358979323846 / 2.0 * eps * (term1 - term2);
 }
 
-inline void read_simulation_input(Deck& d, const std::string& dir)
+inline void read_simulation_input(Deck& d, const std::string& dir, int box = 0)
 {
+  const size_t bx = (size_t) box;      // per-box columns: termsScannedLined[1 + BoxIndex] (read_data.cpp:2530-2570)
   auto L = read_lines(dir + "/simulation.input");
   Component* cur = nullptr;
   int fw_block = 0;
@@ -166,10 +169,11 @@ inline void read_simulation_input(Deck& d, const std::string& dir)
       else if(has("WidomProbability")) cur->p_widom = std::stod(t[1]);
       else if(has("ReinsertionProbability")) cur->p_reinsertion = std::stod(t[1]);
       else if(has("IdentityChangeProbability")) cur->p_identity = std::stod(t[1]);
+      else if(has("GibbsParticleXferProbability")) cur->p_gibbs_xfer = std::stod(t[1]);            // read_data.cpp:2386-2390
       else if(has("SwapProbability")) cur->p_swap = std::stod(t[1]);
       else if(has("FugacityCoefficient")) { if(ieq(t[1], "PR-EOS")) { cur->use_pr_eos = true; cur->fugacity_coeff = -1.0; } else cur->fugacity_coeff = std::stod(t[1]); }
       else if(has("MolFraction")) cur->mol_fraction = std::stod(t[1]);
-      else if(has("CreateNumberOfMolecules")) cur->create_molecules = std::stoi(t[1]);
+      else if(has("CreateNumberOfMolecules")) cur->create_molecules = std::stoi(t.at(1 + bx));
       else if(has("BlockPocketsFilename")) cur->pocket_file = t[1] + ".block";
       else if(has("InvertBlockPockets")) cur->invert_pockets = ieq(t[1], "yes");
       else if(has("BlockPockets")) { if(ieq(t[1], "yes")) cur->use_pockets = true; }
@@ -189,8 +193,11 @@ inline void read_simulation_input(Deck& d, const std::string& dir)
     else if(has("NumberOfTrialPositions")) d.n_trial_positions = std::stoi(t[1]);
     else if(has("NumberOfTrialOrientations")) d.n_trial_orientations = std::stoi(t[1]);
     else if(has("AdsorbateAllocateSpace")) d.adsorbate_allocate = std::stol(t[1]);
-    else if(has("FrameworkName")) d.framework_name = t[1];
-    else if(has("UnitCells") && t.size() >= 5) { d.unitcells[0] = std::stoi(t[2]); d.unitcells[1] = std::stoi(t[3]); d.unitcells[2] = std::stoi(t[4]); }
+    else if(has("FrameworkName")) d.framework_name = t.at(1 + bx);
+    else if(has("UnitCells") && t.size() >= 5) { if(std::stoi(t[1]) == box) { d.unitcells[0] = std::stoi(t[2]); d.unitcells[1] = std::stoi(t[3]); d.unitcells[2] = std::stoi(t[4]); } }
+    else if(has("NumberOfSimulations")) d.n_simulations = std::stoi(t[1]);
+    else if(has("SingleSimulation")) d.single_simulation = ieq(t[1], "yes");
+    else if(has("GibbsVolumeChangeProbability")) { const double v = std::stod(t[1]); if(v > 0) d.gibbs_volume_prob = v; }     // read_data.cpp:389-403
     else if(has("UseChargesFromCIFFile")) d.use_cif_charges = ieq(t[1], "yes");
     else if(has("ChargeMethod")) d.no_charges = !ieq(t[1], "Ewald");
     else if(has("Temperature")) d.temperature = std::stod(t[1]);
@@ -644,10 +651,10 @@ inline void compute_fugacity(Deck& d)
   }
 }
 
-inline Deck load(const std::string& dir, double pressure_override = -1.0, double temperature_override = -1.0)
+inline Deck load(const std::string& dir, double pressure_override = -1.0, double temperature_override = -1.0, int box = 0)
 {
   Deck d;
-  read_simulation_input(d, dir);
+  read_simulation_input(d, dir, box);
   if(pressure_override >= 0.0) d.pressure_pa = pressure_override;          // one isotherm point per process (and per GPU)
   if(temperature_override >= 0.0) d.temperature = temperature_override;
   read_force_field(d, dir);

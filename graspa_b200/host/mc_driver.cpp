@@ -29,6 +29,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <memory>
 
 namespace {
 
@@ -51,7 +52,7 @@ struct Energy   // MoveEnergy, data_struct.h:416-431 (terms this driver touches)
 struct CompState
 {
   // cumulative move probabilities, Move_Statistics::NormalizeProbabilities data_struct.h:569-608
-  double cTrans = 0, cRot = 0, cSpecial = 0, cWidom = 0, cReins = 0, cIdentity = 0, cCBCF = 0, cSwap = 0, cVolume = 0, total_prob = 0;
+  double cTrans = 0, cRot = 0, cSpecial = 0, cWidom = 0, cReins = 0, cIdentity = 0, cCBCF = 0, cSwap = 0, cVolume = 0, cGibbsXfer = 0, cGibbsVolume = 0, total_prob = 0;
   double max_trans[3] = {1, 1, 1}, max_rot[3] = {0, 0, 0};
   MoveCount trans, rot, ins, del, reins, widom, idswap_add, idswap_remove;
   std::vector<MoveCount> idswap_to;             // IdentitySwap_Total_TO / _Acc_TO per destination component
@@ -71,12 +72,30 @@ struct CallClock
   ~CallClock() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); n++; }
 };
 
-struct Sim
+struct Sim;
+// what the boxes of one run share: ONE glibc rand() stream and ONE random pool (Vars.Random), the trace, the Gibbs statistics
+struct Shared
 {
-  deck::Deck d;
-  gb_engine* e = nullptr;
   GlibcRand rng;
   std::vector<double> pool; size_t pool_size = 333334, pool_off = 0; long pool_rounds = 0;
+  std::FILE* trace = nullptr; long trace_lines = 0;   // one trace line per RunMoves call (moves that do nothing included)
+  long moves_done = 0;
+  std::vector<Sim*> boxes;
+  // Gibbs, data_struct.h:66-79
+  MoveCount gibbs_vol_window, gibbs_vol_total, gibbs_xfer; double gibbs_max_change = 0.1, gibbs_total_volume = 0.0;
+};
+
+struct Sim                                        // one simulation box
+{
+  Shared& sh;
+  GlibcRand& rng; std::vector<double>& pool; size_t& pool_size; size_t& pool_off; long& pool_rounds;
+  std::FILE*& trace; long& trace_lines; long& moves_done;
+  explicit Sim(Shared& s) : sh(s), rng(s.rng), pool(s.pool), pool_size(s.pool_size), pool_off(s.pool_off), pool_rounds(s.pool_rounds),
+                            trace(s.trace), trace_lines(s.trace_lines), moves_done(s.moves_done) { s.boxes.push_back(this); }
+  Sim(const Sim&) = delete; Sim& operator=(const Sim&) = delete;
+  int box_index = 0;
+  deck::Deck d;
+  gb_engine* e = nullptr;
   int ncomp = 0;                                  // total components incl. framework (component 0)
   int nhost = 1;                                  // framework components (NComponents.y): 0 = the rigid rest, 1.. = separated, movable ones
   std::vector<CompState> C;
@@ -86,11 +105,9 @@ struct Sim
   Energy createmol_energy;                        // SystemComponents.CreateMol_Energy: the energy the running deltas start from
   MoveCount vol_window, vol_total; double vol_max_change = 0.025;   // VolumeMoveAttempts/Accepted, VolumeMoveMaxChange (data_struct.h:1028-1034)
   int nblock = 5; long block_size = 1; bool production = false;
-  long moves_done = 0;
   int device = -1;                                // CUDA device of the engine (-1: the current one)
   bool fused = true;                              // one host round trip per move (gb_move_*); false: the stage calls
   double call_s[5] = {0, 0, 0, 0, 0}; long call_n[5] = {0, 0, 0, 0, 0};   // host time inside gb_move_{insertion,deletion,reinsertion,single_body,identity_swap}
-  std::FILE* trace = nullptr; long trace_lines = 0;   // one trace line per RunMoves call (moves that do nothing included)
 };
 
 inline int comp_ms(const Sim& S, int c) { return c == 0 ? 0 : (c < S.nhost ? S.d.fw[c - 1].molsize : S.d.comps[c - S.nhost].ms()); }
@@ -101,7 +118,7 @@ void pool_reset(Sim& S)                           // RandomNumber::ResetRandom
   S.pool_off = 0;
   for(size_t i = 0; i < S.pool_size; i++) { S.pool[3 * i] = S.rng.uniform(); S.pool[3 * i + 1] = S.rng.uniform(); S.pool[3 * i + 2] = S.rng.uniform(); }
   for(size_t i = S.pool_size * 3; i < 1000000; i++) S.rng.uniform();
-  GB(gb_upload_random_pool(S.e, S.pool.data(), (int64_t) S.pool_size));
+  for(Sim* b : S.sh.boxes) if(b->e) GB(gb_upload_random_pool(b->e, S.pool.data(), (int64_t) S.pool_size));     // every box reads the same pool
   S.pool_rounds++;
 }
 inline void pool_check(Sim& S, size_t change) { if(S.pool_off + change >= S.pool_size) pool_reset(S); }
@@ -235,11 +252,13 @@ void setup_probabilities(Sim& S)
     // the volume-move probability enters the total but is itself NOT divided by it (NormalizeProbabilities, data_struct.h:569-608):
     // the window [cSwap, 1) it ends up with is vol / total all the same
     const double vol = S.d.volume_move_prob;
-    double tot = t + r + sp + w + re + id + sw + cb + vol;
-    if(tot > 1e-10) { t /= tot; r /= tot; sp /= tot; w /= tot; sw /= tot; cb /= tot; re /= tot; id /= tot; tot = 1.0; }
+    double gx = M.p_gibbs_xfer, gv = S.d.gibbs_volume_prob;
+    double tot = t + r + sp + w + re + id + sw + cb + vol + gx + gv;
+    if(tot > 1e-10) { t /= tot; r /= tot; sp /= tot; w /= tot; sw /= tot; cb /= tot; re /= tot; id /= tot; gx /= tot; gv /= tot; tot = 1.0; }
     X.total_prob = tot;
     X.cTrans = t; X.cRot = r + X.cTrans; X.cSpecial = sp + X.cRot; X.cWidom = w + X.cSpecial; X.cReins = re + X.cWidom;
     X.cIdentity = id + X.cReins; X.cCBCF = cb + X.cIdentity; X.cSwap = sw + X.cCBCF; X.cVolume = vol + X.cSwap;
+    X.cGibbsXfer = gx + X.cVolume; X.cGibbsVolume = gv + X.cGibbsXfer;
     // InitializeMaxTranslationRotation fxn_main.h:151-160 then Prepare... :222-227 (0.1 x box lengths, 30 degrees)
     X.max_trans[0] = S.d.cell[0] * 0.1; X.max_trans[1] = S.d.cell[4] * 0.1; X.max_trans[2] = S.d.cell[8] * 0.1;
     for(int k = 0; k < 3; k++) X.max_rot[k] = 30.0 / (180 / 3.1415);
@@ -363,10 +382,11 @@ void move_insertion(Sim& S, int comp)              // InsertionMove::Run, move_s
   else trace_move(S, "insertion", comp, X.nmol, 0, 0.0);
 }
 
-void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run + Deletion_Body, move_struct.h:148-167, mc_swap_utilities.h:135-225
+// Deletion_Body, mc_swap_utilities.h:135-225: retrace of molecule `mol`; W and the molecule's energy terms (sign of an existing molecule)
+Growth deletion_body(Sim& S, int comp, long mol)
 {
+  Growth G;
   CompState& X = S.C[comp];
-  X.del.total++;
   const int ms = S.d.comps[comp - S.nhost].ms();
   const double scale[2] = {1.0, 1.0};
   gb_cbmc_result r; int32_t used = 0;
@@ -378,7 +398,7 @@ void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run + Deleti
     gb_move_result m;
     { CallClock cc(S.call_s[1], S.call_n[1]); GB(gb_move_deletion(S.e, comp, mol, (int64_t) S.pool_off, scale, &m)); }
     pool_update(S, m.pool_used);
-    if(!m.success) { trace_move(S, "deletion", comp, mol, 0, 0.0); return; }
+    if(!m.success) return G;
     W = m.first_bead.rosenbluth;
     E.HGVDW = m.first_bead.energy[0]; E.HGReal = m.first_bead.energy[1]; E.GGVDW = m.first_bead.energy[2]; E.GGReal = m.first_bead.energy[3];
     if(ms > 1) { W *= m.chain.rosenbluth; E.HGVDW += m.chain.energy[0]; E.HGReal += m.chain.energy[1]; E.GGVDW += m.chain.energy[2]; E.GGReal += m.chain.energy[3]; }
@@ -386,24 +406,23 @@ void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run + Deleti
   }
   else
   {
-  GB(gb_cbmc_first_bead(S.e, GB_CBMC_DELETION, comp, mol, (int64_t) S.pool_off, 0.0, scale, 0.0, -1, -1, nullptr, &r, &used));
-  pool_update(S, S.d.n_trial_positions);
-  W = r.rosenbluth;
-  if(!r.success || W <= 1e-150) { trace_move(S, "deletion", comp, mol, 0, 0.0); return; }
-  E.HGVDW = r.energy[0]; E.HGReal = r.energy[1]; E.GGVDW = r.energy[2]; E.GGReal = r.energy[3];
-  if(ms > 1)
-  {
-    pool_check(S, S.d.n_trial_orientations);
-    GB(gb_cbmc_chain(S.e, GB_CBMC_DELETION, comp, mol, (int64_t) S.pool_off, 0.0, -1, -1, &r, &used));
-    pool_update(S, S.d.n_trial_orientations);
-    W *= r.rosenbluth;
-    E.HGVDW += r.energy[0]; E.HGReal += r.energy[1]; E.GGVDW += r.energy[2]; E.GGReal += r.energy[3];
+    GB(gb_cbmc_first_bead(S.e, GB_CBMC_DELETION, comp, mol, (int64_t) S.pool_off, 0.0, scale, 0.0, -1, -1, nullptr, &r, &used));
+    pool_update(S, S.d.n_trial_positions);
+    W = r.rosenbluth;
+    if(!r.success || W <= 1e-150) return G;
+    E.HGVDW = r.energy[0]; E.HGReal = r.energy[1]; E.GGVDW = r.energy[2]; E.GGReal = r.energy[3];
+    if(ms > 1)
+    {
+      pool_check(S, S.d.n_trial_orientations);
+      GB(gb_cbmc_chain(S.e, GB_CBMC_DELETION, comp, mol, (int64_t) S.pool_off, 0.0, -1, -1, &r, &used));
+      pool_update(S, S.d.n_trial_orientations);
+      W *= r.rosenbluth;
+      E.HGVDW += r.energy[0]; E.HGReal += r.energy[1]; E.GGVDW += r.energy[2]; E.GGReal += r.energy[3];
+    }
+    if(W <= 1e-150) return G;
+    if(!S.d.no_charges && X.has_charge) GB(gb_ewald_delta(S.e, comp, GB_DELETION, mol * ms, scale, ew));
+    GB(gb_tail_difference(S.e, comp, GB_DELETION, &tail));
   }
-  if(W <= 1e-150) { trace_move(S, "deletion", comp, mol, 0, 0.0); return; }
-  if(!S.d.no_charges && X.has_charge) GB(gb_ewald_delta(S.e, comp, GB_DELETION, mol * ms, scale, ew));
-  GB(gb_tail_difference(S.e, comp, GB_DELETION, &tail));
-  }
-  const double pre = prefactor(S, comp, false);
   if(!S.d.no_charges && X.has_charge)
   {
     W /= std::exp(-S.d.beta * (ew[0] + ew[1]));
@@ -411,18 +430,24 @@ void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run + Deleti
   }
   W /= std::exp(-S.d.beta * tail);
   E.Tail = -tail;
-  const double pacc = pre * S.d.comps[comp - S.nhost].ideal_rosenbluth / W;
+  G.success = true; G.W = W; G.E = E;
+  return G;
+}
+
+void move_deletion(Sim& S, int comp, long mol)     // DeletionMove::Run, move_struct.h:148-167
+{
+  CompState& X = S.C[comp];
+  X.del.total++;
+  const Growth G = deletion_body(S, comp, mol);
+  if(!G.success) { trace_move(S, "deletion", comp, mol, 0, 0.0); return; }
+  const double pacc = prefactor(S, comp, false) * S.d.comps[comp - S.nhost].ideal_rosenbluth / G.W;
   const double R = S.rng.uniform();
-  if(std::getenv("GB_DEBUG_MOVE") && S.moves_done == std::atol(std::getenv("GB_DEBUG_MOVE")))
-    std::fprintf(stderr, "deletion debug nmol:"), [&]{ for(int c = 1; c < S.ncomp; c++) std::fprintf(stderr, " %ld", S.C[c].nmol); std::fprintf(stderr, "\n"); }(),
-    std::fprintf(stderr, "deletion debug move %ld comp %d mol %ld: W %.12e ewald %.12e %.12e tail %.6e pre %.12e pacc %.12e R %.12e E %.10e %.10e %.10e %.10e fused %d\n",
-                 S.moves_done, comp, mol, W, ew[0], ew[1], tail, pre, pacc, R, E.HGVDW, E.HGReal, E.GGVDW, E.GGReal, (int) fused);
   if(R < pacc)
   {
     GB(gb_accept_deletion(S.e, comp, mol));
     X.nmol--; S.total_molecules--; X.del.accepted++;
-    S.running.add(E, -1.0);                                   // energy.take_negative()
-    trace_move(S, "deletion", comp, mol, 1, -E.total());
+    S.running.add(G.E, -1.0);                                   // energy.take_negative()
+    trace_move(S, "deletion", comp, mol, 1, -G.E.total());
   }
   else trace_move(S, "deletion", comp, mol, 0, 0.0);
 }
@@ -717,7 +742,7 @@ void move_volume(Sim& S, int comp)
     for(int k = 0; k < 3; k++) d.kmax[k] = box.kmax[k];
   }
   // RunMoves books no energy change for this move itself (VolumeMove adds to deltaE on its own, mc_box.h:288): the trace line carries zeros
-  trace_move(S, "volume", comp, accept ? 1 : 0, 0, 0.0);
+  trace_move(S, "volume", comp, 0, accept ? 1 : 0, 0.0);
 }
 
 void update_max_volume_change(Sim& S, long cycle)     // Update_Max_VolumeChange, mc_utilities.h:691-712
@@ -757,6 +782,136 @@ void create_molecules(Sim& S)
   }
 }
 
+// the box and k table of `S` scaled to volume newV (ScalePositions, mc_box.h:66-94)
+gb_box scaled_box(const Sim& S, double newV, double& scale)
+{
+  const deck::Deck& d = S.d;
+  scale = std::cbrt(newV / d.volume);
+  const double inv_scale = 1.0 / scale;
+  gb_box box; std::memset(&box, 0, sizeof(box));
+  for(int i = 0; i < 9; i++) { box.cell[i] = d.cell[i] * scale; box.inverse_cell[i] = d.inv[i] * inv_scale; }
+  box.volume = newV; box.alpha = d.alpha; box.prefactor = d.prefactor;
+  box.cubic = !((std::fabs(d.cell[3]) + std::fabs(d.cell[6]) + std::fabs(d.cell[7])) > 1e-10);
+  box.use_lammps_ewald = d.lammps_ewald ? 1 : 0;
+  for(int k = 0; k < 3; k++) box.kmax[k] = d.kmax[k];
+  box.reciprocal_cutoff = d.recip_cutoff;
+  if(!d.no_charges)
+  {
+    for(int k = 0; k < 3; k++) box.kmax[k] = (int) std::round(0.25 + box.cell[4 * k] * d.alpha * d.ewald_tol1 * 0.31830988618);
+    box.reciprocal_cutoff = std::pow(1.05 * (double) std::max(box.kmax[0], std::max(box.kmax[1], box.kmax[2])), 2);
+  }
+  return box;
+}
+
+void adopt_box(Sim& S, const gb_box& box)
+{
+  deck::Deck& d = S.d;
+  for(int i = 0; i < 9; i++) { d.cell[i] = box.cell[i]; d.inv[i] = box.inverse_cell[i]; }
+  d.volume = box.volume; d.recip_cutoff = box.reciprocal_cutoff;
+  for(int k = 0; k < 3; k++) d.kmax[k] = box.kmax[k];
+}
+
+inline double molecules_in_box(const Sim& S) { return (double) (S.total_molecules - S.nhost); }      // Get_TotalNumberOfMolecule_In_Box
+
+// NVTGibbsMove, mc_box.h:322-478: the two boxes exchange volume at constant total volume
+void move_gibbs_volume(Sim& S0, int comp)
+{
+  Shared& H = S0.sh;
+  if(H.boxes.size() != 2) { trace_move(S0, "gibbs_volume", comp, 0, 0, 0.0); return; }
+  int sel = 0, oth = 1;
+  if(S0.rng.uniform() > 0.5) { sel = 1; oth = 0; }
+  Sim& A = *H.boxes[sel]; Sim& B = *H.boxes[oth];
+  H.gibbs_vol_window.total++;
+  const double oldVA = A.d.volume, oldVB = B.d.volume, totalV = oldVA + oldVB;
+  const double expdV = std::exp(std::log(oldVA / oldVB) + H.gibbs_max_change * 2.0 * (S0.rng.uniform() - 0.5));
+  const double newVA = expdV * totalV / (1.0 + expdV), newVB = totalV - newVA;
+  const double cut = std::max(S0.d.cutoff_vdw * S0.d.cutoff_vdw, S0.d.cutoff_coul * S0.d.cutoff_coul);
+  if(std::pow(std::cbrt(newVA), 2) < 4.0 * cut || std::pow(std::cbrt(newVB), 2) < 4.0 * cut) { trace_move(S0, "gibbs_volume", comp, 0, 0, 0.0); return; }
+  // boxes are scaled in index order; after an overlap in the first one the second is still scaled but not evaluated (mc_box.h:386-389)
+  Sim* bx[2] = {H.boxes[0], H.boxes[1]};
+  const double newV[2] = {sel == 0 ? newVA : newVB, sel == 0 ? newVB : newVA};
+  gb_box nb[2]; Energy N[2]; bool overlap = false;
+  for(int k = 0; k < 2; k++)
+  {
+    double scale = 1.0;
+    nb[k] = scaled_box(*bx[k], newV[k], scale);
+    gb_move_energy m; int32_t ov = 0;
+    GB(gb_volume_move_trial(bx[k]->e, &nb[k], scale, &m, &ov));
+    if(overlap) continue;
+    if(ov) overlap = true;
+    N[k].HHVDW = m.HHVDW; N[k].HGVDW = m.HGVDW; N[k].GGVDW = m.GGVDW; N[k].HHReal = m.HHReal; N[k].HGReal = m.HGReal; N[k].GGReal = m.GGReal;
+    N[k].HHEwald = m.HHEwaldE; N[k].HGEwald = m.HGEwaldE; N[k].GGEwald = m.GGEwaldE;
+    GB(gb_tail_total(bx[k]->e, &N[k].Tail));
+  }
+  bool accept = false; Energy D[2];
+  if(!overlap)
+  {
+    for(int k = 0; k < 2; k++) { D[k] = N[k]; D[k].add(bx[k]->createmol_energy, -1.0); D[k].add(bx[k]->running, -1.0); }
+    const double pacc = std::exp(-A.d.beta * (D[0].total() + D[1].total()) + (molecules_in_box(A) + 1.0) * std::log(newVA / oldVA)
+                                 + (molecules_in_box(B) + 1.0) * std::log(newVB / oldVB));
+    if(S0.rng.uniform() < pacc) accept = true;
+  }
+  for(int k = 0; k < 2; k++)
+  {
+    GB(gb_volume_move_finish(bx[k]->e, accept ? 1 : 0));
+    if(accept) { bx[k]->running.add(D[k]); adopt_box(*bx[k], nb[k]); }
+  }
+  if(accept) H.gibbs_vol_window.accepted++;
+  if(std::fabs(H.boxes[0]->d.volume + H.boxes[1]->d.volume - H.gibbs_total_volume) > 0.1) die("Gibbs volume move: the total volume drifted");
+  trace_move(S0, "gibbs_volume", comp, 0, accept ? 1 : 0, 0.0);
+}
+
+void update_max_gibbs_volume(Shared& H)               // Update_Max_GibbsVolume, mc_box.h:480-498
+{
+  if(H.gibbs_vol_window.total > 0)
+  {
+    const double ratio = (double) H.gibbs_vol_window.accepted / (double) H.gibbs_vol_window.total;
+    double v = ratio / 0.5;
+    if(v > 1.5) v = 1.5; else if(ratio < 0.5) v = 0.5;               // the lower clamp tests the raw ratio, as the reference does
+    H.gibbs_max_change *= v;
+    if(H.gibbs_max_change < 0.0005) H.gibbs_max_change = 0.0005;
+    if(H.gibbs_max_change > 0.5) H.gibbs_max_change = 0.5;
+  }
+  H.gibbs_vol_total.total += H.gibbs_vol_window.total; H.gibbs_vol_total.accepted += H.gibbs_vol_window.accepted;
+  H.gibbs_vol_window = MoveCount();
+}
+
+Growth deletion_body(Sim& S, int comp, long mol);
+
+// GibbsParticleXferMove, move_struct.h:408-515: CBMC insertion in one box, CBMC deletion of a random molecule of the other
+void move_gibbs_transfer(Sim& S0, int comp)
+{
+  Shared& H = S0.sh;
+  if(H.boxes.size() != 2) { trace_move(S0, "gibbs_transfer", comp, 0, 0, 0.0); return; }
+  H.gibbs_xfer.total++;
+  int sel = 0, oth = 1;
+  if(S0.rng.uniform() > 0.5) { sel = 1; oth = 0; }
+  Sim& A = *H.boxes[sel]; Sim& B = *H.boxes[oth];
+  long del_mol = 0;
+  if(B.C[comp].nmol >= 1)
+  {
+    (void) (long) (size_t) (S0.rng.uniform() * (double) A.C[comp].nmol);          // InsertionSelectedMol: drawn, not used by the growth
+    del_mol = (long) (size_t) (S0.rng.uniform() * (double) B.C[comp].nmol);
+  }
+  else die("Gibbs particle transfer out of an empty box is not driven by this host program");
+  Growth GI = insertion_body(A, comp);
+  if(!GI.success) { trace_move(S0, "gibbs_transfer", comp, del_mol, 0, 0.0); return; }
+  Growth GD = deletion_body(B, comp, del_mol);
+  if(!GD.success) { trace_move(S0, "gibbs_transfer", comp, del_mol, 0, 0.0); return; }
+  long nA = 0, nB = 0;
+  for(int c = A.nhost; c < A.ncomp; c++) nA += A.C[c].nmol;
+  for(int c = B.nhost; c < B.ncomp; c++) nB += B.C[c].nmol;
+  const double pacc = (GI.W * (double) nB * A.d.volume) / (GD.W * (double) (nA + 1) * B.d.volume);
+  if(S0.rng.uniform() < pacc)
+  {
+    GB(gb_accept_insertion(A.e, comp)); A.C[comp].nmol++; A.total_molecules++; A.running.add(GI.E);
+    GB(gb_accept_deletion(B.e, comp, del_mol)); B.C[comp].nmol--; B.total_molecules--; B.running.add(GD.E, -1.0);
+    H.gibbs_xfer.accepted++;
+    trace_move(S0, "gibbs_transfer", comp, del_mol, 1, 0.0);
+  }
+  else trace_move(S0, "gibbs_transfer", comp, del_mol, 0, 0.0);
+}
+
 void run_move(Sim& S, long cycle)
 {
   int comp = 0;
@@ -780,6 +935,8 @@ void run_move(Sim& S, long cycle)
     else S.C[comp].del.total += 0;
   }
   else if(R < X.cVolume) move_volume(S, comp);
+  else if(R < X.cGibbsXfer) move_gibbs_transfer(S, comp);
+  else if(R < X.cGibbsVolume) move_gibbs_volume(S, comp);
   if(S.trace_lines == lines_before) trace_move(S, "none", comp, mol, 0, 0.0);     // the selected move had nothing to act on
 }
 
@@ -1020,6 +1177,59 @@ void print_energy(const char* tag, const Energy& E)
               tag, E.HHVDW, E.HGVDW, E.GGVDW, E.HHReal, E.HGReal, E.GGReal, E.HHEwald, E.HGEwald, E.GGEwald, E.Tail, E.total());
 }
 
+// Check_Simulation_Energy(INITIAL) -> CreateMolecule_InOneBox -> Check_Simulation_Energy(CREATEMOL) for one box (main.cpp:333-340);
+// -> the energy the running deltas of this box start from
+Energy initial_state(Sim& S)
+{
+  // initial energies + structure factors (Check_Simulation_Energy(INITIAL), fxn_main.h:282-404)
+  { gb_move_energy w; GB(gb_total_ewald(S.e, 1, &w)); S.initial_framework_ewald = w.HHEwaldE; }
+  Energy E0 = total_energy(S);
+  print_energy("INITIAL", E0);
+  long ncreate = 0; for(const auto& M : S.d.comps) ncreate += M.create_molecules;
+  if(ncreate > 0)
+  {
+    create_molecules(S);
+    // Check_Simulation_Energy(CREATEMOL) (main.cpp:340): the energies are computed afresh and the running deltas restart from
+    // them; the stored structure factors stay the incrementally updated ones (Allocate_Copy_Ewald_Vector runs at INITIAL only)
+    const Energy created = total_energy(S);
+    Energy dC = created; dC.add(E0, -1.0);
+    std::printf("CREATE MOLECULE: %ld molecules, running %.5f, recomputed %.5f\n", ncreate, S.running.total(), dC.total());
+    E0 = created; S.running = Energy();
+    print_energy("CREATED", E0);
+  }
+  S.createmol_energy = E0;
+  return E0;
+}
+
+// Run_Simulation_MultipleBoxes, axpy.cu:593-625: per cycle and per box slot a box is DRAWN, and runs max(20, N) moves
+void run_phase_boxes(Shared& H, long cycles, bool production)
+{
+  const size_t nb = H.boxes.size();
+  for(Sim* b : H.boxes) { b->production = production; if(production) b->block_size = std::max<long>(1, cycles / b->nblock); }
+  for(long i = 0; i < cycles; i++)
+  {
+    for(size_t k = 0; k < nb; k++)
+    {
+      Sim& S = *H.boxes[(size_t) (H.rng.uniform() * (double) nb)];
+      long steps = 20;
+      if(steps < S.total_molecules) steps = S.total_molecules;
+      if(S.d.use_max_step && steps > S.d.max_step_per_cycle) steps = S.d.max_step_per_cycle;
+      for(long j = 0; j < steps; j++) run_move(S, i);
+    }
+    for(Sim* b : H.boxes)
+    {
+      Sim& S = *b;
+      if(production) for(int c = S.nhost; c < S.ncomp; c++) { S.C[c].load_sum += (double) S.C[c].nmol; S.C[c].load_n++; }
+      if(i % 500 == 0)
+      {
+        for(int c = 1; c < S.ncomp; c++) { update_max(S.C[c].max_trans, S.C[c].trans_window, S.C[c].trans_cum, 5.0); update_max(S.C[c].max_rot, S.C[c].rot_window, S.C[c].rot_cum, 3.14); }
+        update_max_volume_change(S, i);
+      }
+    }
+    if(i > 0 && i % 500 == 0) update_max_gibbs_volume(H);
+  }
+}
+
 } // namespace
 
 int main(int argc, char** argv)
@@ -1093,7 +1303,7 @@ int main(int argc, char** argv)
     else if(a == "--seed" && i + 1 < argc) o_seed = std::atol(argv[++i]);
     else if(a == "--write-restart" && i + 1 < argc) restart_out = argv[++i];
   }
-  Sim S;
+  Shared SH; Sim S(SH);
   try { S.d = deck::load(dir, o_pressure, o_temperature); } catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
   if(o_seed >= 0) S.d.random_seed = (int) o_seed;
   S.device = o_device;
@@ -1105,6 +1315,20 @@ int main(int argc, char** argv)
   S.fused = !staged;
   setup_engine(S);
   setup_probabilities(S);
+  // two boxes run together (NumberOfSimulations 2, SingleSimulation no): the Gibbs ensemble of the reference's examples
+  std::unique_ptr<Sim> S2;
+  if(S.d.n_simulations == 2 && !S.d.single_simulation)
+  {
+    S2.reset(new Sim(SH)); S2->box_index = 1;
+    try { S2->d = deck::load(dir, o_pressure, o_temperature, 1); } catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: box 1: %s\n", ex.what()); return 1; }
+    S2->d.random_seed = S.d.random_seed; S2->d.init_cycles = S.d.init_cycles; S2->d.equil_cycles = S.d.equil_cycles; S2->d.prod_cycles = S.d.prod_cycles;
+    S2->device = o_device; S2->fused = !staged;
+    S2->C.assign(1 + S2->d.fw.size() + S2->d.comps.size(), CompState());
+    setup_engine(*S2);
+    setup_probabilities(*S2);
+    std::printf("graspa_b200_mc: box 1: %zu framework atoms, kmax %d %d %d, volume %.5f\n", S2->d.ftype.size(), S2->d.kmax[0], S2->d.kmax[1], S2->d.kmax[2], S2->d.volume);
+  }
+  else if(S.d.n_simulations > 1 && !S.d.single_simulation) { std::fprintf(stderr, "graspa_b200_mc: %d boxes run together are not driven by this host program\n", S.d.n_simulations); return 2; }
   std::printf("graspa_b200_mc: %s, %zu framework atoms, %zu adsorbate component(s), alpha %.6f, kmax %d %d %d, volume %.5f, beta %.8f\n",
               dir.c_str(), S.d.ftype.size(), S.d.comps.size(), S.d.alpha, S.d.kmax[0], S.d.kmax[1], S.d.kmax[2], S.d.volume, S.d.beta);
   // Random.Setup(333334): std::srand(RANDOMSEED) then the first pool (main.cpp:145, data_struct.h:1338-1346)
@@ -1115,32 +1339,23 @@ int main(int argc, char** argv)
   // element 0 of the device pool with {2.3, 4.5, 6.7} and copies the pool back to the host (data_struct.h:1280-1285, 1322-1328):
   // the very first trial position of a run comes from those three numbers.
   S.pool[0] = 2.3; S.pool[1] = 4.5; S.pool[2] = 6.7;
-  GB(gb_upload_random_pool(S.e, S.pool.data(), (int64_t) S.pool_size));
-  // initial energies + structure factors (Check_Simulation_Energy(INITIAL), fxn_main.h:282-404)
-  { gb_move_energy w; GB(gb_total_ewald(S.e, 1, &w)); S.initial_framework_ewald = w.HHEwaldE; }
-  Energy E0 = total_energy(S);
-  print_energy("INITIAL", E0);
-  {
-    long ncreate = 0; for(const auto& M : S.d.comps) ncreate += M.create_molecules;
-    if(ncreate > 0)
-    {
-      create_molecules(S);
-      // Check_Simulation_Energy(CREATEMOL) (main.cpp:340): the energies are computed afresh and the running deltas restart from
-      // them; the stored structure factors stay the incrementally updated ones (Allocate_Copy_Ewald_Vector runs at INITIAL only)
-      const Energy created = total_energy(S);
-      Energy dC = created; dC.add(E0, -1.0);
-      std::printf("CREATE MOLECULE: %ld molecules, running %.5f, recomputed %.5f\n", ncreate, S.running.total(), dC.total());
-      E0 = created; S.running = Energy();
-      print_energy("CREATED", E0);
-    }
-  }
-  S.createmol_energy = E0;
+  for(Sim* b : SH.boxes) GB(gb_upload_random_pool(b->e, S.pool.data(), (int64_t) S.pool_size));
+  Energy E0 = initial_state(S);
+  Energy E0b;
+  if(S2) { std::printf("--- box 1\n"); E0b = initial_state(*S2); SH.gibbs_total_volume = S.d.volume + S2->d.volume; }
 
   if(timing) GB(gb_timing_enable(S.e, 1));
   const auto t0 = std::chrono::steady_clock::now();
   int wcomp = -1;
   const bool batched = !sequential_widom && widom_only(S, wcomp) && S.d.init_cycles == 0 && S.d.equil_cycles == 0;
-  if(batched) run_widom_batched_v2(S, wcomp, S.d.prod_cycles);
+  if(S2)
+  {
+    run_phase_boxes(SH, S.d.init_cycles, false);
+    run_phase_boxes(SH, S.d.equil_cycles, false);
+    run_phase_boxes(SH, S.d.prod_cycles, true);
+    GB(gb_synchronize(S2->e));
+  }
+  else if(batched) run_widom_batched_v2(S, wcomp, S.d.prod_cycles);
   else
   {
     run_phase(S, S.d.init_cycles, false);
@@ -1176,8 +1391,37 @@ int main(int argc, char** argv)
     std::printf("Volume Move: %ld/%ld accepted, final volume %.5f, cell %.5f %.5f %.5f, kmax %d %d %d, MaxVolumeChange %.5f\n",
                 S.vol_total.accepted + S.vol_window.accepted, S.vol_total.total + S.vol_window.total, S.d.volume, S.d.cell[0], S.d.cell[4], S.d.cell[8],
                 S.d.kmax[0], S.d.kmax[1], S.d.kmax[2], S.vol_max_change);
+  if(S2)
+  {
+    Sim& B = *S2;
+    const Energy F1 = total_energy(B);
+    std::printf("--- box 1\n");
+    print_energy("FINAL  ", F1);
+    Energy Db = F1; Db.add(E0b, -1.0);
+    print_energy("RUNNING", B.running);
+    std::printf("ENERGY DRIFT (FINAL - INITIAL - RUNNING) Total Energy: %.6e\n", Db.total() - B.running.total());
+    for(int c = 1; c < B.ncomp; c++)
+    {
+      const CompState& X = B.C[c];
+      std::printf("Component %d (%s): molecules %ld | translation %ld/%ld rotation %ld/%ld insertion %ld/%ld deletion %ld/%ld reinsertion %ld/%ld widom %ld\n",
+                  c, comp_name(B, c), X.nmol, X.trans.accepted, X.trans.total, X.rot.accepted, X.rot.total, X.ins.accepted, X.ins.total,
+                  X.del.accepted, X.del.total, X.reins.accepted, X.reins.total, X.widom.total);
+    }
+    std::printf("Gibbs Volume Move: %ld/%ld accepted, MaxGibbsBoxChange %.5f; Gibbs Particle Transfer: %ld/%ld accepted\n",
+                SH.gibbs_vol_total.accepted + SH.gibbs_vol_window.accepted, SH.gibbs_vol_total.total + SH.gibbs_vol_window.total, SH.gibbs_max_change,
+                SH.gibbs_xfer.accepted, SH.gibbs_xfer.total);
+    std::printf("Box volumes: %.5f %.5f; molecules:", S.d.volume, B.d.volume);
+    for(int c = S.nhost; c < S.ncomp; c++) std::printf(" %ld/%ld", S.C[c].nmol, B.C[c].nmol);
+    std::printf("\n");
+    std::printf("{\"box\": 1, \"loading\": [");
+    for(int c = B.nhost; c < B.ncomp; c++)
+      std::printf("%s{\"component\": \"%s\", \"molecules\": %ld, \"production_average\": %.6f}", c > B.nhost ? ", " : "", comp_name(B, c), B.C[c].nmol,
+                  B.C[c].load_n ? B.C[c].load_sum / (double) B.C[c].load_n : (double) B.C[c].nmol);
+    std::printf("]}\n");
+  }
   const long cycles = S.d.init_cycles + S.d.equil_cycles + S.d.prod_cycles;
   int64_t launches = 0; gb_launch_count(S.e, &launches, 0);
+  if(S2) { int64_t l2 = 0; gb_launch_count(S2->e, &l2, 0); launches += l2; }
   std::printf("Work took %.6f seconds\n", secs);
   std::printf("{\"pressure_pa\": %.6g, \"temperature\": %.6g, \"loading\": [", S.d.pressure_pa, S.d.temperature);
   for(int c = S.nhost; c < S.ncomp; c++)
@@ -1202,6 +1446,7 @@ int main(int argc, char** argv)
     std::printf("device time of the move kernels (CUDA events, serialises the run): %.3f ms over %lld launches = %.2f us each\n", ms, (long long) n, n ? 1e3 * ms / n : 0.0);
   }
   if(S.trace) std::fclose(S.trace);
+  if(S2) gb_engine_destroy(S2->e);
   gb_engine_destroy(S.e);
   return 0;
 }

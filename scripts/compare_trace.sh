@@ -15,7 +15,7 @@ import sys
 ref = [l.split() for l in open(sys.argv[1])]
 our = [l.split() for l in open(sys.argv[2])]
 n = min(len(ref), len(our))
-mism = None; acc = 0; worst = 0.0; comp_mism = 0; nmism = 0; zero_swaps = 0
+mism = None; acc = 0; worst = 0.0; comp_mism = 0; nmism = 0; zero_swaps = 0; box_moves = 0; box_acc = 0
 for k in range(n):
     rc, rd = int(ref[k][0]), float(ref[k][2])
     oc, oa, od = int(our[k][2]), int(our[k][4]), float(our[k][5])
@@ -23,6 +23,12 @@ for k in range(n):
     acc += ra
     if our[k][1] == "identity_swap": oc = rc      # the reference's TempVal.component is the NEW species until the retrace starts, ours prints the OLD one
     if rc != oc: comp_mism += 1
+    if our[k][1] in ("volume", "gibbs_volume", "gibbs_transfer"):
+        # these moves add to the running energy on their own (mc_box.h:288, move_struct.h:488-489): RunMoves, and with it the
+        # reference's trace line, carries a zero whether they were accepted or not.  Their decisions show in every later
+        # move (the state differs otherwise) and in the attempt / acceptance counters of the two outputs.
+        box_moves += 1; box_acc += oa
+        continue
     if oa == 1 and od == 0.0 and our[k][1] == "identity_swap" and ra == 0:
         zero_swaps += 1                 # an accepted swap of a monatomic molecule into its own species changes no energy at all
         continue
@@ -33,5 +39,6 @@ for k in range(n):
 print(f"moves: reference {len(ref)}, ours {len(our)}; compared {n}; accepted (non-zero energy change) in the reference {acc}")
 print(f"moves whose component or accept/reject decision differs: {nmism} (first: {mism}); component mismatches: {comp_mism}")
 print(f"accepted same-species identity swaps with exactly zero energy change (indistinguishable from a rejection in the reference's trace): {zero_swaps}")
+print(f"volume / Gibbs moves (decision not in the reference's trace line, see the counters of the outputs): {box_moves}, accepted here {box_acc}")
 print(f"largest relative difference of an accepted move's energy change: {worst:.3e}")
 PY
