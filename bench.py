@@ -217,7 +217,10 @@ def more_secondaries():
     (the host driver replays the reference's random stream there: RNG-exact batched insertions)"""
     return {"gcmc_xekr": _deck_pair("XeKr-Mixture", 20000, 0, "cycles/s"),
             "gcmc_nax": _deck_pair("CO2_NaX_Zeolite", 5000, 0, "cycles/s"),
-            "widom_henry": _deck_pair("Henrys_coefficient", 0, 20000, "insertions/s")}
+            "widom_henry": _deck_pair("Henrys_coefficient", 0, 20000, "insertions/s"),
+            # the total-energy path in a loop: NPT volume moves (one box) and the two-box Gibbs ensemble
+            "npt_co2": _deck_pair("NPTMC", 600, 0, "cycles/s"),
+            "gibbs_co2": _deck_pair("NVT-Gibbs", 20, 0, "cycles/s")}
 
 
 def run_reference(args):

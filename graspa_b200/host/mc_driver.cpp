@@ -1263,6 +1263,22 @@ int main(int argc, char** argv)
       std::printf("], \"block_pockets\": [");
       for(size_t c = 0; c < d.comps.size(); c++) std::printf("%s%zu", c ? ", " : "", d.comps[c].pocket_radii.size());
       std::printf("]");
+      if(d.n_simulations > 1 && !d.single_simulation)
+      {
+        // boxes run together (Gibbs ensemble): the per-box columns of the deck
+        std::printf(", \"boxes\": [");
+        for(int b = 0; b < d.n_simulations; b++)
+        {
+          const deck::Deck db = b == 0 ? d : deck::load(argv[2], -1.0, -1.0, b);
+          std::printf("%s{\"volume\": %.6f, \"kmax\": [%d, %d, %d], \"create\": [", b ? ", " : "", db.volume, db.kmax[0], db.kmax[1], db.kmax[2]);
+          for(size_t c = 0; c < db.comps.size(); c++) std::printf("%s%d", c ? ", " : "", db.comps[c].create_molecules);
+          std::printf("]}");
+        }
+        std::printf("], \"gibbs_volume_prob\": %.6f, \"gibbs_xfer_prob\": [", d.gibbs_volume_prob);
+        for(size_t c = 0; c < d.comps.size(); c++) std::printf("%s%.6f", c ? ", " : "", d.comps[c].p_gibbs_xfer);
+        std::printf("]");
+      }
+      if(d.volume_move_prob > 0.0) std::printf(", \"npt_volume_prob\": %.6f", d.volume_move_prob);
       if(d.use1264)
       {
         // pairs with an r^-4 term: [name i, name j, C12, C6, C4, shift] in internal units
@@ -1407,6 +1423,9 @@ int main(int argc, char** argv)
                   c, comp_name(B, c), X.nmol, X.trans.accepted, X.trans.total, X.rot.accepted, X.rot.total, X.ins.accepted, X.ins.total,
                   X.del.accepted, X.del.total, X.reins.accepted, X.reins.total, X.widom.total);
     }
+    if(B.d.volume_move_prob > 0.0)
+      std::printf("Volume Move: %ld/%ld accepted, final volume %.5f, MaxVolumeChange %.5f\n", B.vol_total.accepted + B.vol_window.accepted,
+                  B.vol_total.total + B.vol_window.total, B.d.volume, B.vol_max_change);
     std::printf("Gibbs Volume Move: %ld/%ld accepted, MaxGibbsBoxChange %.5f; Gibbs Particle Transfer: %ld/%ld accepted\n",
                 SH.gibbs_vol_total.accepted + SH.gibbs_vol_window.accepted, SH.gibbs_vol_total.total + SH.gibbs_vol_window.total, SH.gibbs_max_change,
                 SH.gibbs_xfer.accepted, SH.gibbs_xfer.total);

@@ -54,10 +54,13 @@ if [ "$WHAT" = "all" ] || [ "$WHAT" = "examples" ]; then
   chmod u+w "$OUT/examples/NPTMC/simulation.input"
   sed -i 's/^Widom_Trials .*/NumberOfTrialPositions 10/; s/^Widom_Orientation .*/NumberOfTrialOrientations 10\nUseChargesFromCIFFile yes/' "$OUT/examples/NPTMC/simulation.input"
   # the Gibbs-ensemble example (two boxes run together) lacks UseChargesFromCIFFile, which the current reader requires
-  mkdir -p "$OUT/examples/NVT-Gibbs"
-  find "$REF/Examples/NVT-Gibbs" -maxdepth 1 -type f \( -name '*.def' -o -name '*.cif' -o -name 'simulation.input' \) -exec cp {} "$OUT/examples/NVT-Gibbs/" \;
-  chmod u+w "$OUT/examples/NVT-Gibbs/simulation.input"
-  grep -q UseChargesFromCIFFile "$OUT/examples/NVT-Gibbs/simulation.input" || sed -i 's/^ChargeMethod .*/&\nUseChargesFromCIFFile yes/' "$OUT/examples/NVT-Gibbs/simulation.input"
+  for ex in NVT-Gibbs NPT-Gibbs; do
+    mkdir -p "$OUT/examples/$ex"
+    find "$REF/Examples/$ex" -maxdepth 1 -type f \( -name '*.def' -o -name '*.cif' -o -name 'simulation.input' \) -exec cp {} "$OUT/examples/$ex/" \;
+    chmod u+w "$OUT/examples/$ex/simulation.input"
+    grep -q UseChargesFromCIFFile "$OUT/examples/$ex/simulation.input" || sed -i 's/^ChargeMethod .*/&\nUseChargesFromCIFFile yes/' "$OUT/examples/$ex/simulation.input"
+    sed -i '/^SaveOutputToFile/d' "$OUT/examples/$ex/simulation.input"      # output goes to stdout like everywhere else
+  done
   # the NIST SPC/E known-answer decks: inputs + the RASPA-2 restart file they start from
   for b in 1 2 3 4; do
     d="$OUT/examples/Reference_NIST_SPCE/Box-$b"
