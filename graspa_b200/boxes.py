@@ -50,10 +50,16 @@ def run_boxes(deck, points, gpus=1, init=None, prod=None, equil=0, driver=DRIVER
     queues = assign_boxes(len(points), gpus)
     results = [None] * len(points)
 
+    # each driver process sees only its own GPU: CUDA start-up enumerates every visible device, which costs seconds per
+    # process on an 8-GPU node and is paid once per box
+    visible = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+
     def worker(g):
+        env = dict(os.environ)
+        env["CUDA_VISIBLE_DEVICES"] = visible[g] if g < len(visible) else str(g)
         for b in queues[g]:
             pt = points[b]
-            cmd = [driver, deck, "--device", str(g)]
+            cmd = [driver, deck, "--device", "0"]
             if init is not None:
                 cmd += ["--init", str(init)]
             cmd += ["--equil", str(equil)]
@@ -68,7 +74,7 @@ def run_boxes(deck, points, gpus=1, init=None, prod=None, equil=0, driver=DRIVER
             cmd += list(extra)
             t0 = time.perf_counter()
             try:
-                r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
                 rc, text, err = r.returncode, r.stdout, r.stderr
             except subprocess.TimeoutExpired as ex:
                 rc, text, err = -9, ex.stdout or "", "timeout"

@@ -22,9 +22,10 @@ def test_boxes_are_dealt_round_robin():
 def test_results_are_gathered_per_box_in_input_order(tmp_path):
     fake = tmp_path / "fake_driver.sh"
     fake.write_text("""#!/bin/bash
-# stand-in for graspa_b200_mc: echoes the flags it was given in the driver's output format
+# stand-in for graspa_b200_mc: echoes the flags it was given in the driver's output format; the GPU of a box is the ONE
+# device its process can see (CUDA_VISIBLE_DEVICES), addressed as device 0
 dev=-1; p=0
-while [ $# -gt 0 ]; do case "$1" in --device) dev=$2; shift;; --pressure) p=$2; shift;; esac; shift; done
+while [ $# -gt 0 ]; do case "$1" in --device) [ "$2" = 0 ] && dev=$CUDA_VISIBLE_DEVICES; shift;; --pressure) p=$2; shift;; esac; shift; done
 echo "FINAL   VDW [Host-Host]: 0.0, Total: -$p"
 echo "ENERGY DRIFT (FINAL - INITIAL - RUNNING) Total Energy: 1.0e-10"
 echo "{\\"pressure_pa\\": $p, \\"temperature\\": 300, \\"loading\\": [{\\"component\\": \\"X\\", \\"molecules\\": $dev, \\"production_average\\": 1.5}]}"
