@@ -687,3 +687,52 @@ def test_npt_volume_move_reports_overlap(gpu_engine_factory):
     assert ov == 1
     eng.volume_move_finish(False)
     eng.close()
+
+
+def _run_driver(deck_name, *flags):
+    import os
+    import subprocess
+    from graspa_b200.boxes import DRIVER, ROOT
+    deck = os.path.join(ROOT, "oracle", "_ref", "examples", deck_name)
+    if not (os.path.exists(DRIVER) and os.path.isdir(deck)):
+        pytest.skip("host driver / example deck not built (oracle/build_ref.sh examples, make -C graspa_b200/host)")
+    r = subprocess.run([DRIVER, deck, *flags], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout.splitlines()
+
+
+def _term(line, key):
+    return float(line.split(key + ":")[1].split(",")[0])
+
+
+def test_host_driver_npt_example_matches_the_reference_run():
+    """Examples/NPTMC (100 CO2 created in an empty box, NPT volume moves), 1500 + 500 cycles, seed 0: the numbers below are the
+    reference CUDA program's own for the same deck and seed (profiles/r1_trace_parity.txt: 202 000 moves, no decision differs)"""
+    out = _run_driver("NPTMC", "--init", "1500", "--equil", "0", "--prod", "500")
+    final = [ln for ln in out if ln.startswith("FINAL")][0]
+    assert abs(_term(final, "VDW [Guest-Guest]") + 6116.32502) < 2e-5 and abs(_term(final, "Real [Guest-Guest]") + 2450.30981) < 2e-5
+    vol = [ln for ln in out if ln.startswith("Volume Move:")][0]
+    assert "4704/6448 accepted" in vol
+    cyc = [ln for ln in out if ln.startswith("CYCLE:")]
+    assert cyc[1] == "CYCLE: 500, AccRatio: 0.83496, compare_to_target_ratio: 1.50000, MaxVolumeChange: 0.05625"
+    drift = float([ln for ln in out if ln.startswith("ENERGY DRIFT")][0].split(":")[-1])
+    assert abs(drift) < 1e-6
+
+
+def test_host_driver_gibbs_example_matches_the_reference_run():
+    """Examples/NVT-Gibbs (two boxes run together, 852 + 151 CO2, particle transfers and volume exchange), 30 + 20 cycles, seed 0:
+    counters and final energies of both boxes as the reference CUDA program prints them; molecules and volume are conserved"""
+    out = _run_driver("NVT-Gibbs", "--init", "30", "--equil", "0", "--prod", "20")
+    finals = [ln for ln in out if ln.startswith("FINAL")]
+    assert len(finals) == 2
+    assert abs(_term(finals[0], "VDW [Guest-Guest]") + 669378.85067) < 2e-5 and abs(_term(finals[0], "Real [Guest-Guest]") + 218849.56576) < 2e-5
+    assert abs(_term(finals[1], "VDW [Guest-Guest]") + 3399.58198) < 2e-5 and abs(_term(finals[1], "Real [Guest-Guest]") + 1465.16641) < 2e-5
+    g = [ln for ln in out if ln.startswith("Gibbs Volume Move:")][0]
+    assert "Gibbs Volume Move: 139/1286 accepted" in g and "Gibbs Particle Transfer: 3228/13332 accepted" in g
+    bv = [ln for ln in out if ln.startswith("Box volumes:")][0]
+    v0, v1 = (float(x) for x in bv.split(":")[1].split(";")[0].split())
+    assert abs(v0 + v1 - (39.0 ** 3 + 71.0 ** 3)) < 1e-6
+    n0, n1 = (int(x) for x in bv.split("molecules:")[1].split()[0].split("/"))
+    assert n0 + n1 == 852 + 151
+    drifts = [float(ln.split(":")[-1]) for ln in out if ln.startswith("ENERGY DRIFT")]
+    assert len(drifts) == 2 and all(abs(d) < 1e-5 for d in drifts)
