@@ -7,6 +7,7 @@
 #include "fused_kernel.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -91,6 +92,8 @@ struct gb_engine
   int i_ads = 0, i_fw = 1, i_tmp = 2;     // pointer swap = index swap (Update_Vector_Ewald)
   bool have_sf = false;
   DevBuf<double> d_ktab; bool ktab_dirty = true;
+  // row-ordered k table of k_widom_ewald: a lane owns one (kx, ky) row and walks kz with its warp in lockstep
+  std::vector<int> h_rowidx, h_rowmeta, h_round; DevBuf<int> d_rowidx, d_rowmeta, d_round; DevBuf<double> d_rtab; int nrounds = 0, npos = 0;
   // volume move (gb_volume_move_trial / _finish): the state to fall back to on rejection
   gb_box cur_box{}, vol_old_box{}; bool vol_pending = false, vol_had_sf = false; long long vol_old_nvec = 0;
   DevBuf<double> d_vol_xyz, d_vol_sf;
@@ -329,6 +332,18 @@ __global__ void k_build_ktab(const double* __restrict__ temp, const int* __restr
   }
 }
 
+// the same gathered in row order: 5 arrays of npos [temp | sa.re | sa.im | sf.re | sf.im]; unused positions carry temp = 0
+__global__ void k_build_rtab(const double* __restrict__ temp, const int* __restrict__ slot, const int* __restrict__ rowidx,
+                             const double* __restrict__ sa, const double* __restrict__ sf, int npos, double* rtab)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if(p >= npos) return;
+  const int k = rowidx[p];
+  double t = 0.0, ar = 0.0, ai = 0.0, fr = 0.0, fi = 0.0;
+  if(k >= 0) { const int s = slot[k]; t = temp[k]; ar = sa[2 * s]; ai = sa[2 * s + 1]; fr = sf[2 * s]; fi = sf[2 * s + 1]; }
+  rtab[p] = t; rtab[(size_t) npos + p] = ar; rtab[2 * (size_t) npos + p] = ai; rtab[3 * (size_t) npos + p] = fr; rtab[4 * (size_t) npos + p] = fi;
+}
+
 int ensure_ktab(gb_engine* e)
 {
   if(!e->ktab_dirty) return GB_OK;
@@ -338,6 +353,13 @@ int ensure_ktab(gb_engine* e)
                                                                    e->nact, e->nact_pad, e->d_ktab.p);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
+  if(e->npos > 0)
+  {
+    CUDA_TRY(e->d_rtab.reserve((size_t) e->npos * 5));
+    k_build_rtab<<<(e->npos + 255) / 256, 256, 0, e->stream>>>(e->d_ktemp.p, e->d_kslot.p, e->d_rowidx.p, e->d_sf[e->i_ads].p, e->d_sf[e->i_fw].p, e->npos, e->d_rtab.p);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
   e->ktab_dirty = false;
   return GB_OK;
 }
@@ -589,6 +611,42 @@ int apply_box(gb_engine* e, const gb_box* box)
       e->h_kslot.push_back((int) kxyz);
     }
   e->nact = (int) e->h_kpack.size(); e->nact_pad = (e->nact + 31) / 32 * 32;
+  {
+    // rows (kx, ky) of the active list, longest kz reach first; 32 rows per round, positions [round][j = |kz|][sign][lane]
+    std::map<int, std::vector<int>> rows;                  // key = kpack >> 8 (kx, ky), values = active indices
+    std::vector<int> order;
+    for(int k = 0; k < e->nact; k++) { const int key = e->h_kpack[k] >> 8; if(!rows.count(key)) order.push_back(key); rows[key].push_back(k); }
+    auto reach = [&](int key) { int m = 0; for(int k : rows[key]) m = std::max(m, std::abs((e->h_kpack[k] & 255) - 128)); return m; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return reach(a) > reach(b); });
+    e->nrounds = ((int) order.size() + 31) / 32;
+    e->h_round.assign(2 * (size_t) std::max(e->nrounds, 1), 0); e->h_rowmeta.assign(32 * (size_t) std::max(e->nrounds, 1), (128 << 8));
+    e->h_rowidx.clear();
+    for(int g = 0; g < e->nrounds; g++)
+    {
+      const int m = reach(order[(size_t) g * 32]);
+      const int off = (int) e->h_rowidx.size();
+      e->h_round[2 * g] = off; e->h_round[2 * g + 1] = m;
+      e->h_rowidx.resize((size_t) off + (size_t) (m + 1) * 64, -1);
+      for(int l = 0; l < 32 && (size_t) g * 32 + l < order.size(); l++)
+      {
+        const int key = order[(size_t) g * 32 + l];
+        e->h_rowmeta[(size_t) g * 32 + l] = key << 8;
+        for(int k : rows[key])
+        {
+          const int kz = (e->h_kpack[k] & 255) - 128, j = std::abs(kz), sgn = kz < 0 ? 1 : 0;
+          e->h_rowidx[(size_t) off + ((size_t) j * 2 + sgn) * 32 + l] = k;
+        }
+      }
+    }
+    e->npos = (int) e->h_rowidx.size();
+    if(e->npos > 0)
+    {
+      CUDA_TRY(e->d_rowidx.reserve(e->npos)); CUDA_TRY(e->d_rowmeta.reserve(e->h_rowmeta.size())); CUDA_TRY(e->d_round.reserve(e->h_round.size()));
+      CUDA_TRY(cudaMemcpy(e->d_rowidx.p, e->h_rowidx.data(), e->npos * sizeof(int), cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(e->d_rowmeta.p, e->h_rowmeta.data(), e->h_rowmeta.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(e->d_round.p, e->h_round.data(), e->h_round.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+  }
   if(e->nact > 0)
   {
     CUDA_TRY(e->d_kpack.reserve(e->nact)); CUDA_TRY(e->d_kslot.reserve(e->nact)); CUDA_TRY(e->d_ktemp.reserve(e->nact));
@@ -1271,6 +1329,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   WidomB B;
   B.rec = e->d_rec.p; B.stage = e->d_stage.p; B.n = n; B.ms = ms; B.tq = e->dq.p + C.offset; B.tscoul = e->dscoul.p + C.offset;
   B.ktab = e->d_ktab.p; B.nact = e->nact; B.nact_pad = e->nact_pad; B.do_ewald = do_ewald ? 1 : 0;
+  B.rtab = e->d_rtab.p; B.npos = e->npos; B.rowmeta = e->d_rowmeta.p; B.rounds = e->d_round.p; B.nrounds = (e->npos > 0 && C.molsize <= 4 && !std::getenv("GB_EWALD_FLAT")) ? e->nrounds : 0;      // GB_EWALD_FLAT: the one-k-per-lane loop, for A/B timing
   B.excl_const = C.rigid ? (C.excl_intra + C.excl_atom) * 1.0 : 0.0;
   B.tail = e->h_pinned[8]; B.nbins = nbins;
   B.gn = in->global_n > 0 ? in->global_n : n; B.gfirst = in->global_n > 0 ? in->global_first : 0;

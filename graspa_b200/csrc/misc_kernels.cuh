@@ -157,6 +157,8 @@ struct WidomB
   const double* __restrict__ tq; const double* __restrict__ tscoul;   // template charges
   // staged k table: [temp (nact) | sa (2 nact) | sf (2 nact) | kpack (nact int)]
   const double* __restrict__ ktab; int nact; int nact_pad; int stage_ktab;
+  // row-ordered table (nrounds > 0: molecules of <= 4 atoms): a lane owns one (kx, ky) row of a round, the warp walks |kz| in lockstep
+  const double* __restrict__ rtab; int npos; const int* __restrict__ rowmeta; const int* __restrict__ rounds; int nrounds;
   int do_ewald;
   double excl_const;       // (ExclusionIntra + ExclusionAtom) * scale^2, Ewald_Energy_Functions.h:553-556
   double tail;             // TailCorrectionDifference for this component (same for every ghost insertion)
@@ -224,6 +226,61 @@ k_widom_ewald(DevParams P, WidomB B)
 #elif defined(GBK_EWALD_UNROLL) && GBK_EWALD_UNROLL == 4
 #pragma unroll 4
 #endif
+        if(B.nrounds > 0)
+        {
+          // e^{i kx x} e^{i ky y} q is formed once per row and lane; e^{i kz z} is the same shared-memory word for the whole warp, and
+          // +kz / -kz come out of one load.  Half the instructions per wave vector of the flat loop below.
+          const double* __restrict__ Tt = B.rtab;
+          const double* __restrict__ Tar = B.rtab + B.npos; const double* __restrict__ Tai = B.rtab + 2 * (size_t) B.npos;
+          const double* __restrict__ Tfr = B.rtab + 3 * (size_t) B.npos; const double* __restrict__ Tfi = B.rtab + 4 * (size_t) B.npos;
+          for(int g = 0; g < B.nrounds; g++)
+          {
+            const int off = B.rounds[2 * g] + lane, m = B.rounds[2 * g + 1];
+            const int meta = B.rowmeta[g * 32 + lane];
+            const int kx = meta >> 16, ky = ((meta >> 8) & 255) - 128, aky = ky < 0 ? -ky : ky;
+            cplx a[4];
+#pragma unroll
+            for(int i = 0; i < 4; i++)
+            {
+              a[i].re = 0.0; a[i].im = 0.0;
+              if(i < n)
+              {
+                cplx t1 = ey[aky * n + i]; if(ky < 0) t1.im = -t1.im;
+                const cplx exy = cmul(ex[kx * n + i], t1);
+                a[i].re = qeff[i] * exy.re; a[i].im = qeff[i] * exy.im;
+              }
+            }
+            for(int j = 0; j <= m; j++)
+            {
+              double pr = 0.0, pi = 0.0, mr = 0.0, mi = 0.0;
+#pragma unroll
+              for(int i = 0; i < 4; i++)
+                if(i < n)
+                {
+                  const cplx b = ez[j * n + i];
+                  const double rr = a[i].re * b.re, ii = a[i].im * b.im, ri = a[i].re * b.im, ir = a[i].im * b.re;
+                  pr += rr - ii; pi += ri + ir;          // a * b
+                  mr += rr + ii; mi += ir - ri;          // a * conj(b)
+                }
+              const int p0 = off + j * 64, p1 = p0 + 32;
+              {
+                const double temp = Tt[p0], ore = Tar[p0], oim = Tai[p0];
+                const double nre = ore + pr, nim = oim + pi;
+                same += temp * (nre * nre + nim * nim);
+                same -= temp * (ore * ore + oim * oim);
+                cross += temp * (Tfr[p0] * pr + Tfi[p0] * pi);
+              }
+              {
+                const double temp = Tt[p1], ore = Tar[p1], oim = Tai[p1];
+                const double nre = ore + mr, nim = oim + mi;
+                same += temp * (nre * nre + nim * nim);
+                same -= temp * (ore * ore + oim * oim);
+                cross += temp * (Tfr[p1] * mr + Tfi[p1] * mi);
+              }
+            }
+          }
+        }
+        else
         for(int kk = lane; kk < B.nact; kk += 32)
         {
           int kx, ky, kz; unpack_k(g_kp[kk], kx, ky, kz);
