@@ -233,6 +233,7 @@ k_widom_ewald(DevParams P, WidomB B)
           const double* __restrict__ Tt = B.rtab;
           const double* __restrict__ Tar = B.rtab + B.npos; const double* __restrict__ Tai = B.rtab + 2 * (size_t) B.npos;
           const double* __restrict__ Tfr = B.rtab + 3 * (size_t) B.npos; const double* __restrict__ Tfi = B.rtab + 4 * (size_t) B.npos;
+          double same1 = 0.0, cross1 = 0.0;
           for(int g = 0; g < B.nrounds; g++)
           {
             const int off = B.rounds[2 * g] + lane, m = B.rounds[2 * g + 1];
@@ -263,22 +264,21 @@ k_widom_ewald(DevParams P, WidomB B)
                   mr += rr + ii; mi += ir - ri;          // a * conj(b)
                 }
               const int p0 = off + j * 64, p1 = p0 + 32;
+              // |S + d|^2 - |S|^2 = |d|^2 + 2 Re(conj(S) d): no cancellation of the stored term, and one accumulation per
+              // wave vector on each of four independent accumulators
               {
                 const double temp = Tt[p0], ore = Tar[p0], oim = Tai[p0];
-                const double nre = ore + pr, nim = oim + pi;
-                same += temp * (nre * nre + nim * nim);
-                same -= temp * (ore * ore + oim * oim);
+                same += temp * ((pr * pr + pi * pi) + 2.0 * (ore * pr + oim * pi));
                 cross += temp * (Tfr[p0] * pr + Tfi[p0] * pi);
               }
               {
                 const double temp = Tt[p1], ore = Tar[p1], oim = Tai[p1];
-                const double nre = ore + mr, nim = oim + mi;
-                same += temp * (nre * nre + nim * nim);
-                same -= temp * (ore * ore + oim * oim);
-                cross += temp * (Tfr[p1] * mr + Tfi[p1] * mi);
+                same1 += temp * ((mr * mr + mi * mi) + 2.0 * (ore * mr + oim * mi));
+                cross1 += temp * (Tfr[p1] * mr + Tfi[p1] * mi);
               }
             }
           }
+          same += same1; cross += cross1;
         }
         else
         for(int kk = lane; kk < B.nact; kk += 32)
