@@ -300,3 +300,35 @@ def test_polynomial_1264_potential_vs_oracle(gpu_engine_factory, oracle, name):
     assert (np.where(stage == 3, 2, stage) == rstage).all()
     assert rel_err(out[:, 0], wref[:, 0], floor=1e-290) < 1e-9
     eng.close()
+
+
+def test_widom_fourier_row_walk_equals_the_flat_loop(gpu_engine_factory, oracle):
+    """k_widom_ewald walks the active wave vectors by (kx, ky) rows (a lane per row, |kz| in lockstep); the one-k-per-lane loop
+    it replaced stays for molecules of more than four atoms and behind GB_EWALD_FLAT.  Same W and Fourier terms from both,
+    and from the oracle, in a triclinic (A) and an orthorhombic box with adsorbates present (B)."""
+    import os
+    for name in ("A", "B"):
+        box, ff, s, z = load_config(name)
+        comp = int(z["comp"]); n = 512
+        rng = np.random.default_rng(31)
+        rnd = rng.random((n, 20, 3)); uni = rng.random((n, 2))
+        ws = oracle.WidomSetup(box, ff, s, comp, float(z["beta"]), 10, 10, z["sf_ads"], z["sf_fw"])
+        ref, rstage, _ = oracle.widom_batch(ws, rnd, uni)
+        eng = gpu_engine_factory(box, ff, s, float(z["beta"]), 10, 10)
+        eng.upload_structure_factors(z["sf_ads"], z["sf_fw"]); eng.set_exclusion_constants(comp, *ws.excl)
+        out_rows, st_rows, _ = eng.widom_batch(comp, rnd.reshape(-1, 3), uni)
+        os.environ["GB_EWALD_FLAT"] = "1"
+        try:
+            out_flat, st_flat, _ = eng.widom_batch(comp, rnd.reshape(-1, 3), uni)
+        finally:
+            del os.environ["GB_EWALD_FLAT"]
+        assert (st_rows == st_flat).all()
+        ok = st_rows == 0
+        assert ok.sum() > 50
+        # columns 5, 6: the same-species and cross Fourier terms of the insertion
+        scale = np.abs(out_flat[ok][:, 5:7]).max()
+        assert np.max(np.abs(out_rows[ok][:, 5:7] - out_flat[ok][:, 5:7])) < 1e-11 * max(1.0, scale)
+        assert not np.array_equal(out_rows[ok][:, 5:7], out_flat[ok][:, 5:7]) or scale == 0.0     # two different summation orders really ran
+        assert rel_err(out_rows[ok][:, 0], out_flat[ok][:, 0], floor=1e-290) < 1e-10
+        assert rel_err(out_rows[:, 0], ref[:, 0], floor=1e-290) < 1e-9
+        eng.close()
