@@ -99,6 +99,7 @@ struct Deck
   double volume_move_prob = 0.0;           // NPTVolumeChangeProbability (Components::VolumeMoveProbability)
   double gibbs_volume_prob = 0.0;          // GibbsVolumeChangeProbability (Gibbs::GibbsBoxProb)
   int n_simulations = 1; bool single_simulation = true;
+  bool restart_lammps = false, lmp_read_box = false; int lmp_start_component = 0;      // RestartInputFileType LAMMPS
   double ewald_tol1 = 0.0;                 // Boxsize::tol1: kmax follows the box in a volume move (mc_box.h:84-94)
   // framework
   double cell[9] = {0}, inv[9] = {0}, volume = 0;
@@ -184,6 +185,9 @@ inline void read_simulation_input(Deck& d, const std::string& dir, int box = 0)
     else if(has("NumberOfProductionCycles")) d.prod_cycles = std::stol(t[1]);
     else if(has("SeparateFrameworkComponents")) d.separate_framework = ieq(t[1], "yes");
     else if(has("NumberofFrameworkComponents")) d.n_framework_components = std::stoi(t[1]);
+    else if(has("RestartInputFileType")) d.restart_lammps = ieq(t[1], "LAMMPS");                     // read_data.cpp:2750-2767
+    else if(has("LMPData_Comp_to_Start_with")) d.lmp_start_component = std::stoi(t[1]);
+    else if(has("Read_Boxsize")) d.lmp_read_box = ieq(t[1], "yes");
     else if(has("RestartFile")) d.restart_file = ieq(t[1], "yes");
     else if(has("UseLJ1264")) d.use1264 = ieq(t[1], "yes");
     else if(has("NPTVolumeChangeProbability")) { const double v = std::stod(t[1]); if(v > 0) d.volume_move_prob = v; }      // read_data.cpp:404-413
@@ -554,7 +558,7 @@ inline void min_image(const Deck& d, double* v)
 // Atoms other than the first of a molecule are re-wrapped to the nearest image of the first (:3147-3160).
 inline void read_restart(Deck& d, const std::string& dir)
 {
-  if(!d.restart_file) return;
+  if(!d.restart_file || d.restart_lammps) return;
   auto L = read_lines(dir + "/RestartInitial/System_0/restartfile");
   for(size_t ci = 0; ci < d.comps.size(); ci++)
   {
@@ -573,12 +577,91 @@ inline void read_restart(Deck& d, const std::string& dir)
       auto t = terms(L[start + a]);
       if(t.size() < 6 || t[0].find("Adsorbate-atom-position") != 0) throw std::runtime_error("Cannot find matching strings in the range for reading positions!");
       double p[3] = {std::stod(t[3]), std::stod(t[4]), std::stod(t[5])};
-      if(std::stol(t[2]) == 0) { first[0] = p[0]; first[1] = p[1]; first[2] = p[2]; }
-      else { double v[3] = {p[0] - first[0], p[1] - first[1], p[2] - first[2]}; min_image(d, v); for(int k = 0; k < 3; k++) p[k] = first[k] + v[k]; }
+      // The reference means to place every atom at its minimum image from the molecule's first atom, but its `first_bead_pos` is
+      // declared inside the line loop (read_data.cpp:3147-3157) and holds nothing when the other atoms reach it; as built with
+      // nvcc / gcc it is zero, so atoms 1.. end up at their minimum image from the ORIGIN while atom 0 stays where the file has it.
+      // Energies do not notice (every pair goes through PBC), rotations about atom 0 do: the accept/reject sequence of a run that
+      // starts from a RASPA-2 restart file only matches with the same coordinates.
+      (void) first;
+      if(std::stol(t[2]) != 0) { double v[3] = {p[0], p[1], p[2]}; min_image(d, v); for(int k = 0; k < 3; k++) p[k] = v[k]; }
       for(int k = 0; k < 3; k++) c.restart_pos[3 * a + k] = p[k];
       c.restart_charge[a] = std::stod(terms(L[start + 3 * interval + a]).at(3));
       const double lambda = std::stod(terms(L[start + 4 * interval + a]).at(3));
       if(lambda < 1.0) throw std::runtime_error("restart file holds a fractional molecule: that needs the CB/CFC driver");
+    }
+  }
+}
+
+// LMPDataFileParser, read_data.cpp:2811-2998: the initial configuration from LMPDataInitial/System_0/init.data.  Atom lines carry
+// "id mol type q x y z # component atomname"; atoms are put in id order, grouped by component name, cut into molecules of the
+// component's size; the first atom of a molecule stays where the file puts it (WrapInBox takes its argument by value, so it
+// wraps nothing) and the others are placed at their minimum image from it.
+inline void read_lammps_box(Deck& d, const std::string& dir)
+{
+  if(!(d.restart_file && d.restart_lammps && d.lmp_read_box)) return;
+  auto L = read_lines(dir + "/LMPDataInitial/System_0/init.data");
+  bool fx = false, fy = false, fz = false, ft = false;
+  double c3 = 0, c6 = 0, c7 = 0;
+  for(auto& ln : L)
+  {
+    auto t = terms(ln);
+    auto has = [&](const char* k) { return ln.find(k) != std::string::npos; };
+    if(has("xlo") && has("xhi")) { d.cell[0] = std::stod(t.at(1)) - std::stod(t.at(0)); fx = true; }
+    if(has("ylo") && has("yhi")) { d.cell[4] = std::stod(t.at(1)) - std::stod(t.at(0)); fy = true; }
+    if(has("zlo") && has("zhi")) { d.cell[8] = std::stod(t.at(1)) - std::stod(t.at(0)); fz = true; }
+    if(has("xy") && has("xz") && has("yz")) { c3 = std::stod(t.at(0)); c6 = std::stod(t.at(1)); c7 = std::stod(t.at(2)); ft = true; }
+    if(has("atom types")) break;
+  }
+  if(!(fx && fy && fz)) throw std::runtime_error("no box size region in LMPDataInitial/System_0/init.data");
+  d.cell[1] = d.cell[2] = d.cell[5] = 0.0;
+  d.cell[3] = ft ? c3 : 0.0; d.cell[6] = ft ? c6 : 0.0; d.cell[7] = ft ? c7 : 0.0;
+  invert_cell(d.cell, d.inv, d.volume);
+}
+
+inline void read_lammps_data(Deck& d, const std::string& dir)
+{
+  if(!(d.restart_file && d.restart_lammps)) return;
+  if(d.lmp_start_component < 1) throw std::runtime_error("LMPData_Comp_to_Start_with 0 (framework atoms from the data file) is not read by this host program");
+  auto L = read_lines(dir + "/LMPDataInitial/System_0/init.data");
+  struct Rec { long id; int type; double q, p[3]; int comp; };
+  std::vector<Rec> atoms; size_t total = 0, start = 0;
+  for(size_t k = 0; k < L.size(); k++)
+  {
+    auto t = terms(L[k]);
+    if(k < 3 && L[k].find("toms") != std::string::npos && !t.empty()) total = (size_t) std::stol(t[0]);
+    if(L[k].find("Atoms") != std::string::npos) { start = k + 2; continue; }
+    if(start > 0 && k >= start && atoms.size() < total)
+    {
+      if(t.size() != 10) throw std::runtime_error("LAMMPS data file: atom line " + std::to_string(k + 1) + " needs 10 fields (id mol type q x y z # component atom)");
+      Rec r; r.id = std::stol(t[0]) - 1; r.type = std::stoi(t[2]) - 1; r.q = std::stod(t[3]);
+      for(int m = 0; m < 3; m++) r.p[m] = std::stod(t[4 + m]);
+      r.comp = -1;
+      for(size_t c = 0; c < d.comps.size(); c++) if(d.comps[c].name == t[8]) r.comp = (int) c;
+      atoms.push_back(r);
+    }
+  }
+  std::stable_sort(atoms.begin(), atoms.end(), [](const Rec& a, const Rec& b) { return a.id < b.id; });
+  const int nfw = 1 + (int) d.fw.size();
+  for(size_t ci = 0; ci < d.comps.size(); ci++)
+  {
+    if((int) ci + nfw < d.lmp_start_component) continue;
+    Component& c = d.comps[ci];
+    const size_t ms = (size_t) c.ms();
+    std::vector<const Rec*> mine;
+    for(const Rec& r : atoms) if(r.comp == (int) ci) mine.push_back(&r);
+    if(mine.empty()) continue;
+    if(mine.size() % ms != 0) throw std::runtime_error("LAMMPS data file: atoms of component " + c.name + " are not a whole number of molecules");
+    c.restart_pos.resize(3 * mine.size()); c.restart_charge.resize(mine.size());
+    double first[3] = {0, 0, 0};
+    for(size_t a = 0; a < mine.size(); a++)
+    {
+      const Rec& r = *mine[a];
+      if(r.type != c.type[a % ms]) throw std::runtime_error("LAMMPS data file: atom types of component " + c.name + " do not follow its molecule definition");
+      double p[3] = {r.p[0], r.p[1], r.p[2]};
+      if(a % ms == 0) { for(int m = 0; m < 3; m++) first[m] = p[m]; }
+      else { double v[3] = {p[0] - first[0], p[1] - first[1], p[2] - first[2]}; min_image(d, v); for(int m = 0; m < 3; m++) p[m] = first[m] + v[m]; }
+      for(int m = 0; m < 3; m++) c.restart_pos[3 * a + m] = p[m];
+      c.restart_charge[a] = r.q;
     }
   }
 }
@@ -662,7 +745,9 @@ inline Deck load(const std::string& dir, double pressure_override = -1.0, double
   read_framework_components(d, dir);
   read_framework(d, dir);
   read_block_pockets(d, dir);
+  read_lammps_box(d, dir);
   read_restart(d, dir);
+  read_lammps_data(d, dir);
   if(!d.no_charges) setup_ewald(d);
   // Setup_Box_Temperature_Pressure, fxn_main.h:115-127 with Units data_struct.h:58-68
   const double kB = 1.380649e-23, mass_unit = 1.6605402e-27, length_unit = 1e-10, time_unit = 1e-12;

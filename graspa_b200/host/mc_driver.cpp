@@ -196,12 +196,17 @@ void setup_engine(Sim& S)
   {
     const deck::Component& M = d.comps[c];
     double intra = 0.0, self = 0.0; bool charged = false;
+    // the routine looks at the component's FIRST molecule as it sits in the system: the molecule definition, or molecule 0 of the
+    // restart / LAMMPS data file when the run starts from one (its geometry and charges carry the rounding of that file)
+    const bool from_restart = M.restart_charge.size() >= (size_t) M.ms() && M.ms() > 0;
+    const double* mp = from_restart ? M.restart_pos.data() : M.pos.data();
+    const double* mq = from_restart ? M.restart_charge.data() : M.charge.data();
     if(!d.no_charges)
     {
       for(int i = 0; i + 1 < M.ms(); i++)
         for(int j = i + 1; j < M.ms(); j++)
         {
-          double v[3] = {M.pos[3 * i] - M.pos[3 * j], M.pos[3 * i + 1] - M.pos[3 * j + 1], M.pos[3 * i + 2] - M.pos[3 * j + 2]};
+          double v[3] = {mp[3 * i] - mp[3 * j], mp[3 * i + 1] - mp[3 * j + 1], mp[3 * i + 2] - mp[3 * j + 2]};
           // PBC(), maths.cuh:427-450
           const double* I = d.inv; const double* Cc = d.cell;
           if(box.cubic)
@@ -217,10 +222,10 @@ void setup_engine(Sim& S)
             v[0] = Cc[0] * sx + Cc[3] * sy + Cc[6] * sz; v[1] = Cc[1] * sx + Cc[4] * sy + Cc[7] * sz; v[2] = Cc[2] * sx + Cc[5] * sy + Cc[8] * sz;
           }
           const double r = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-          intra += d.prefactor * M.charge[i] * M.charge[j] * std::erf(d.alpha * r) / r;
+          intra += d.prefactor * mq[i] * mq[j] * std::erf(d.alpha * r) / r;
         }
       const double ps = d.prefactor * d.alpha / std::sqrt(3.14159265358979323846);
-      for(int i = 0; i < M.ms(); i++) { self += ps * M.charge[i] * M.charge[i]; if(std::fabs(M.charge[i]) > 1e-10) charged = true; }
+      for(int i = 0; i < M.ms(); i++) { self += ps * mq[i] * mq[i]; if(std::fabs(mq[i]) > 1e-10) charged = true; }
     }
     GB(gb_set_exclusion_constants(S.e, (int32_t) (c + S.nhost), intra, self, 1, charged ? 1 : 0));
     S.C[c + S.nhost].has_charge = charged;

@@ -61,6 +61,16 @@ if [ "$WHAT" = "all" ] || [ "$WHAT" = "examples" ]; then
     grep -q UseChargesFromCIFFile "$OUT/examples/$ex/simulation.input" || sed -i 's/^ChargeMethod .*/&\nUseChargesFromCIFFile yes/' "$OUT/examples/$ex/simulation.input"
     sed -i '/^SaveOutputToFile/d' "$OUT/examples/$ex/simulation.input"      # output goes to stdout like everywhere else
   done
+  # GCMC of TIP4P water continuing from a RASPA-2 restart file
+  d="$OUT/examples/Restart-Examples"
+  mkdir -p "$d/RestartInitial/System_0"
+  find "$REF/Examples/Restart-Examples" -maxdepth 1 -type f \( -name '*.def' -o -name '*.cif' -o -name 'simulation.input' \) -exec cp {} "$d/" \;
+  cp "$REF/Examples/Restart-Examples/RestartInitial/System_0/restartfile" "$d/RestartInitial/System_0/"
+  # ... and from a LAMMPS data file (RestartInputFileType LAMMPS)
+  d="$OUT/examples/Restart-LAMMPS"
+  mkdir -p "$d/LMPDataInitial/System_0"
+  find "$REF/Examples/Restart-Examples/Read-LAMMPS" -maxdepth 1 -type f \( -name '*.def' -o -name '*.cif' -o -name 'simulation.input' \) -exec cp {} "$d/" \;
+  cp "$REF/Examples/Restart-Examples/Read-LAMMPS/LMPDataInitial/System_0/init.data" "$d/LMPDataInitial/System_0/"
   # the NIST SPC/E known-answer decks: inputs + the RASPA-2 restart file they start from
   for b in 1 2 3 4; do
     d="$OUT/examples/Reference_NIST_SPCE/Box-$b"

@@ -6,7 +6,7 @@ set -u
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 NAME="$1"; NI="$2"; NP="${3:-0}"
 OUT="$ROOT/gpurun_out/trace_$NAME"; rm -rf "$OUT"; mkdir -p "$OUT/ref"
-cp "$ROOT/oracle/_ref/examples/$NAME/"* "$OUT/ref/"; chmod u+w "$OUT/ref/"*
+cp -r "$ROOT/oracle/_ref/examples/$NAME/"* "$OUT/ref/"; chmod -R u+w "$OUT/ref/"*
 sed -i "s/^NumberOfInitializationCycles.*/NumberOfInitializationCycles $NI/; s/^NumberOfEquilibrationCycles.*/NumberOfEquilibrationCycles 0/; s/^NumberOfProductionCycles.*/NumberOfProductionCycles $NP/" "$OUT/ref/simulation.input"
 ( cd "$OUT/ref" && GRASPA_TRACE="$OUT/ref_trace.txt" timeout 1500 "$ROOT/oracle/_ref/graspa_ref_cuda_trace.x" > output.txt 2> stderr.txt; echo "reference exit $?" )
 timeout 1500 "$ROOT/graspa_b200/host/graspa_b200_mc" "$OUT/ref" --init "$NI" --equil 0 --prod "$NP" --trace "$OUT/our_trace.txt" > "$OUT/ours.txt" 2>&1; echo "ours exit $?"
