@@ -1284,6 +1284,17 @@ int main(int argc, char** argv)
         std::printf("]");
       }
       if(d.volume_move_prob > 0.0) std::printf(", \"npt_volume_prob\": %.6f", d.volume_move_prob);
+      if(d.restart_file)
+      {
+        // molecules taken from the restart / LAMMPS data file, and where atom 1 of the first one sits
+        std::printf(", \"restart\": {\"format\": \"%s\", \"molecules\": [", d.restart_lammps ? "LAMMPS" : "RASPA");
+        for(size_t c = 0; c < d.comps.size(); c++) std::printf("%s%zu", c ? ", " : "", d.comps[c].restart_charge.size() / (size_t) std::max(1, d.comps[c].ms()));
+        std::printf("]");
+        if(!d.comps.empty() && d.comps[0].restart_pos.size() >= 6)
+          std::printf(", \"first_molecule\": [[%.9f, %.9f, %.9f], [%.9f, %.9f, %.9f]]", d.comps[0].restart_pos[0], d.comps[0].restart_pos[1], d.comps[0].restart_pos[2],
+                      d.comps[0].restart_pos[3], d.comps[0].restart_pos[4], d.comps[0].restart_pos[5]);
+        std::printf("}");
+      }
       if(d.use1264)
       {
         // pairs with an r^-4 term: [name i, name j, C12, C6, C4, shift] in internal units
