@@ -99,27 +99,30 @@ __device__ __forceinline__ RosenResult rosenbluth_warp(double lb, bool surv, int
   const unsigned mask = __ballot_sync(0xffffffffu, surv && lane < ntr);
   r.nsurv = __popc(mask);
   if(mask == 0u) return r;
-  double largest = -INFINITY;
-  for(unsigned m = mask; m; m &= m - 1) { const int b = __ffs(m) - 1; largest = fmax(largest, __shfl_sync(0xffffffffu, lb, b)); }
+  // the largest surviving exponent: a maximum does not depend on the order it is taken in (log-step butterfly, not a trial loop)
+  double largest = (surv && lane < ntr) ? lb : -INFINITY;
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) largest = fmax(largest, __shfl_xor_sync(0xffffffffu, largest, o));
   // every lane evaluates its own two exponentials once; the sums below only move them around, in trial order
   const double w_shift = exp(lb - largest), w_plain = exp(lb);
   int sel = __ffs(mask) - 1;
+  // one pass for both running sums (the shifted weights of the selection and the plain Rosenbluth factor), each in trial order
+  double sum = 0.0, R = 0.0;
+  for(unsigned m = mask; m; m &= m - 1)
+  {
+    const int b = __ffs(m) - 1;
+    sum += __shfl_sync(0xffffffffu, w_shift, b);
+    R += __shfl_sync(0xffffffffu, w_plain, b);
+  }
   if(do_select)
   {
-    double sum = 0.0;
-    for(unsigned m = mask; m; m &= m - 1) { const int b = __ffs(m) - 1; sum += __shfl_sync(0xffffffffu, w_shift, b); }
     const double ws = uniform * sum;
     unsigned m = mask; int b = __ffs(m) - 1; m &= m - 1;
     double cumw = __shfl_sync(0xffffffffu, w_shift, b);
     while(cumw < ws && m) { b = __ffs(m) - 1; m &= m - 1; cumw += __shfl_sync(0xffffffffu, w_shift, b); }
     sel = b;
   }
-  double R = 0.0, Rsel = 0.0;
-  for(unsigned m = mask; m; m &= m - 1)
-  {
-    const int b = __ffs(m) - 1; const double w = __shfl_sync(0xffffffffu, w_plain, b);
-    R += w; if(b == sel) Rsel = w;
-  }
+  const double Rsel = __shfl_sync(0xffffffffu, w_plain, sel);
   r.sel_lane = sel; r.R = R; r.R_minus_sel = R - Rsel;
   r.success = 1;
   return r;
