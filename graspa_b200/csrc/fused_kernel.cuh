@@ -17,6 +17,9 @@
 // IdentitySwapMove (mc_swap_moves.h:199-362: nothing there depends on a selection except the Ewald delta -- the new first
 // bead is the old molecule's first atom -- so growth of the new species and retrace of the old one share ONE stage).
 #pragma once
+#ifndef GBF_SPLIT_ATOMS
+#define GBF_SPLIT_ATOMS 256
+#endif
 #include "common.cuh"
 #include "pair.cuh"
 #include "ewald.cuh"
@@ -101,7 +104,7 @@ __device__ __forceinline__ double* part_half(const FusedArgs& F, int par) { retu
 
 __device__ __forceinline__ int stage_nsplit(const FusedArgs& F, int ngroups)
 {
-  const int ns = (F.natoms + 255) / 256;                   // one 32-atom iteration per warp if the grid allows it
+  const int ns = (F.natoms + GBF_SPLIT_ATOMS - 1) / GBF_SPLIT_ATOMS;   // system atoms per (group, split) item; 256 = one 32-atom iteration per warp
   const int cap = max(1, min(GBF_MAX_ITEMS / max(ngroups, 1), (int) gridDim.x / max(ngroups, 1)));
   return max(1, min(ns, cap));
 }
