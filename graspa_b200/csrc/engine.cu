@@ -92,6 +92,7 @@ struct gb_engine
   int i_ads = 0, i_fw = 1, i_tmp = 2;     // pointer swap = index swap (Update_Vector_Ewald)
   bool have_sf = false;
   DevBuf<double> d_ktab; bool ktab_dirty = true;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // host-input Widom batches: H2D of chunk c+1 under the kernels of chunk c
   // row-ordered k table of k_widom_ewald: a lane owns one (kx, ky) row and walks kz with its warp in lockstep
   std::vector<int> h_rowidx, h_rowmeta, h_round; DevBuf<int> d_rowidx, d_rowmeta, d_round; DevBuf<double> d_rtab; int nrounds = 0, npos = 0;
   // volume move (gb_volume_move_trial / _finish): the state to fall back to on rejection
@@ -501,6 +502,7 @@ int gb_engine_destroy(gb_engine* e)
   e->dq.release(); e->dscale.release(); e->dscoul.release(); e->dtype.release(); e->dmolid.release();
   e->d_pack.release(); e->d_kpack.release(); e->d_kslot.release(); e->d_ktemp.release();
   for(int i = 0; i < 3; i++) e->d_sf[i].release();
+  if(e->copy_stream) { cudaStreamDestroy(e->copy_stream); for(int c = 0; c < 8; c++) if(e->ev_chunk[c]) cudaEventDestroy(e->ev_chunk[c]); }
   e->d_ktab.release(); e->d_pool.release(); e->d_rec.release(); e->d_out8.release(); e->d_partial.release(); e->d_sums.release();
   e->d_uni.release(); e->d_scratch.release(); e->d_result.release(); e->d_stage.release(); e->d_iscratch.release();
   e->d_idx0.release(); e->d_idx1.release(); e->d_ticket.release(); e->d_mv.release(); e->d_mvi.release(); e->d_ewpos.release();
@@ -1218,14 +1220,16 @@ int gb_volume_move_finish(gb_engine* e, int32_t accept)
 
 // ---------------------------------------------------------------------------------------------- batched Widom
 // stage A launch shared by gb_widom_batch and gb_widom_first_bead_success
+// ins0 / n_total: this launch covers insertions [ins0, ins0 + n) of a batch of n_total (its inputs already point at ins0)
 static int widom_stage_a(gb_engine* e, int comp, long long n, const double* d_pool, const long long* d_fb, const long long* d_or, const double* d_uni,
-                         int first_bead_only)
+                         int first_bead_only, long long ins0 = 0, long long n_total = 0)
 {
   int rc;
   const Comp& C = e->comps[comp];
   const int ms = C.molsize, cs = ms - 1;
   const int rec_stride = 5 + 3 * ms;
-  CUDA_TRY(e->d_rec.reserve((size_t) n * rec_stride)); CUDA_TRY(e->d_stage.reserve((size_t) n));
+  if(n_total < ins0 + n) n_total = ins0 + n;
+  if(ins0 == 0) { CUDA_TRY(e->d_rec.reserve((size_t) n_total * rec_stride)); CUDA_TRY(e->d_stage.reserve((size_t) n_total)); }
   const int warpsA = 16;
   const size_t per_warpA = widom_per_warp_bytes(e->norient, cs);
   bool use_pack = false;
@@ -1239,7 +1243,7 @@ static int widom_stage_a(gb_engine* e, int comp, long long n, const double* d_po
   A.tscoul = e->dscoul.p + C.offset; A.ttype = e->dtype.p + C.offset;
   A.pack = e->d_pack.p; A.npad = e->pack_npad; A.ntp = e->pack_ntp; A.pack_n = e->pack_n; A.use_pack = use_pack ? 1 : 0; A.stage_ff = stage_ff ? 1 : 0;
   A.first_bead_only = first_bead_only;
-  A.rec = e->d_rec.p; A.stage = e->d_stage.p;
+  A.rec = e->d_rec.p + (size_t) ins0 * rec_stride; A.stage = e->d_stage.p + ins0;
   SegList L = seg_list(e, 0);
   if(use_pack)
   {
@@ -1298,7 +1302,40 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   // ---- inputs on the device
   const double* d_pool = in->pool3; const long long* d_fb = (const long long*) in->fb_index; const long long* d_or = (const long long*) in->or_index;
   const double* d_uni = in->uniforms;
-  if(!in->inputs_on_device)
+  // host inputs in the packed layout and a batch worth pipelining: the randoms go up in chunks on a second stream while the pair
+  // kernel already works on the chunks that have arrived (measured: 2-4 chunks are equivalent, 8 lose more in kernel tails than
+  // they hide; default = a first chunk of n/8 and the rest, so that 7/8 of the 0.48 KB per insertion travel under compute)
+  const int nchunk = (!in->inputs_on_device && !in->fb_index && n >= 65536 && in->n_pool >= n * per && !std::getenv("GB_WIDOM_NO_OVERLAP")) ? (std::getenv("GB_WIDOM_CHUNKS") ? std::max(2, std::min(8, std::atoi(std::getenv("GB_WIDOM_CHUNKS")))) : 2) : 1;
+  if(nchunk > 1)
+  {
+    if(!e->copy_stream)
+    {
+      CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+      for(int c = 0; c < 8; c++) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_chunk[c], cudaEventDisableTiming));
+    }
+    CUDA_TRY(e->d_pool.reserve((size_t) in->n_pool * 3)); CUDA_TRY(e->d_uni.reserve((size_t) n * 2));
+    d_pool = e->d_pool.p; d_uni = e->d_uni.p;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));                      // nothing of an earlier call may still read the buffers
+    long long c0[9];
+    for(int c = 0; c <= nchunk; c++) c0[c] = (n * c / nchunk) / 32 * 32;
+    if(nchunk == 2) c0[1] = (n / 8) / 32 * 32;          // a short first chunk gets the kernels going, the rest travels under it
+    c0[nchunk] = n;
+    for(int c = 0; c < nchunk; c++)
+    {
+      const long long a = c0[c], b = c0[c + 1];
+      const size_t po = (size_t) a * per * 3, pn = (size_t) ((c + 1 == nchunk ? (long long) in->n_pool : b * per) - a * per) * 3;
+      CUDA_TRY(cudaMemcpyAsync(e->d_pool.p + po, in->pool3 + po, pn * sizeof(double), cudaMemcpyHostToDevice, e->copy_stream));
+      CUDA_TRY(cudaMemcpyAsync(e->d_uni.p + 2 * a, in->uniforms + 2 * a, (size_t) (b - a) * 2 * sizeof(double), cudaMemcpyHostToDevice, e->copy_stream));
+      CUDA_TRY(cudaEventRecord(e->ev_chunk[c], e->copy_stream));
+    }
+    for(int c = 0; c < nchunk; c++)
+    {
+      const long long a = c0[c], b = c0[c + 1];
+      CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_chunk[c], 0));
+      rc = widom_stage_a(e, comp, b - a, d_pool + (size_t) a * per * 3, nullptr, nullptr, d_uni + 2 * a, 0, a, n); if(rc) return rc;
+    }
+  }
+  else if(!in->inputs_on_device)
   {
     CUDA_TRY(e->d_pool.reserve((size_t) in->n_pool * 3));
     CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, in->pool3, (size_t) in->n_pool * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
@@ -1317,7 +1354,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   if(!in->fb_index && in->n_pool < n * per) return fail(GB_ERR_ARG, "random pool smaller than n*(trial positions+orientations)");
 
   // ---- stage A
-  rc = widom_stage_a(e, comp, n, d_pool, d_fb, d_or, d_uni, 0); if(rc) return rc;
+  if(nchunk == 1) { rc = widom_stage_a(e, comp, n, d_pool, d_fb, d_or, d_uni, 0); if(rc) return rc; }
   // ---- tail (constant over the batch)
   std::vector<int> dc = species_counts(e, comp);
   rc = tail_device(e, &dc, e->d_result.p + 8); if(rc) return rc;
