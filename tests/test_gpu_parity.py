@@ -332,3 +332,26 @@ def test_widom_fourier_row_walk_equals_the_flat_loop(gpu_engine_factory, oracle)
         assert rel_err(out_rows[ok][:, 0], out_flat[ok][:, 0], floor=1e-290) < 1e-10
         assert rel_err(out_rows[:, 0], ref[:, 0], floor=1e-290) < 1e-9
         eng.close()
+
+
+def test_widom_host_batches_are_pipelined_without_changing_results(gpu_engine_factory):
+    """Host-input batches of >= 65 536 insertions go up in chunks on a copy stream while the pair kernel already runs on what has
+    arrived (gb_widom_batch); per-insertion results, stage codes and block sums are bitwise those of the single-copy path
+    (GB_WIDOM_NO_OVERLAP=1) and of other chunk counts (ragged chunk boundaries included)."""
+    import os
+    box, ff, s, z = load_config("A")
+    comp = 1; n = 70001                                  # not a multiple of anything the chunking rounds to
+    rng = np.random.default_rng(8)
+    rnd = rng.random((n * 20, 3)); uni = rng.random((n, 2))
+    eng = gpu_engine_factory(box, ff, s, float(z["beta"]), 10, 10)
+    eng.upload_structure_factors(z["sf_ads"], z["sf_fw"]); eng.set_exclusion_constants(comp, float(z["excl"][0]), float(z["excl"][1]))
+    out, stage, sums = eng.widom_batch(comp, rnd, uni)
+    for key, val in (("GB_WIDOM_NO_OVERLAP", "1"), ("GB_WIDOM_CHUNKS", "5"), ("GB_WIDOM_CHUNKS", "8")):
+        os.environ[key] = val
+        try:
+            o2, s2, m2 = eng.widom_batch(comp, rnd, uni)
+        finally:
+            del os.environ[key]
+        assert np.array_equal(o2, out) and np.array_equal(s2, stage) and np.array_equal(m2, sums), (key, val)
+    assert (stage == 0).sum() > n // 2 and sums[:, 2].sum() == n
+    eng.close()
