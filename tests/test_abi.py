@@ -49,3 +49,21 @@ def test_product_does_not_reference_oracle():
                     if not re.search(r"nothing .* oracle|never .* oracle|includes, links or calls oracle", t):
                         bad.append(fn)
     assert not bad, bad
+
+
+def test_integration_adapter_snippet_compiles_against_the_header(tmp_path):
+    """The reference-side adapter shown in INTEGRATION.md (section 1) must stay in step with include/graspa_b200.h: it is cut
+    out of the document and compiled (syntax + types) against stand-ins of the reference structs it reads."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    start = doc.index("```cpp") + 6
+    code = doc[start:doc.index("```", start)].replace('#include "data_struct.h"', '#include "ref_stub.h"')
+    src = tmp_path / "adapter.cpp"
+    src.write_text(code + "\nint main() { return 0; }\n")
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "support"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
