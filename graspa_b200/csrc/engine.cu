@@ -127,6 +127,16 @@ struct gb_engine
 
 namespace {
 
+// Every copy and memset of the engine goes through ITS stream.  The stream is non-blocking, so the legacy default stream is not
+// ordered against it: a plain cudaMemcpy from pageable memory returns once the data is staged, cudaMemset does not wait at all, and
+// a kernel on the engine's stream could still see the old contents (the k tables of the previous box in a volume move).
+cudaError_t copy_on_stream(gb_engine* e, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind)
+{
+  cudaError_t err = cudaMemcpyAsync(dst, src, bytes, kind, e->stream);
+  if(err != cudaSuccess) return err;
+  return cudaStreamSynchronize(e->stream);
+}
+
 SysView sys_view(gb_engine* e)
 {
   SysView S; S.fx = e->dfx.p; S.fy = e->dfy.p; S.fz = e->dfz.p; S.q = e->dq.p; S.scale = e->dscale.p; S.scoul = e->dscoul.p;
@@ -468,7 +478,7 @@ int gb_engine_create(gb_engine** out, int device)
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&e->ev0)); CUDA_TRY(cudaEventCreate(&e->ev1));
   CUDA_TRY(cudaMallocHost(&e->h_pinned, 8192)); memset(e->h_pinned, 0, 8192); e->h_results = e->h_pinned + 512;
-  CUDA_TRY(e->d_ticket.reserve(16)); CUDA_TRY(cudaMemset(e->d_ticket.p, 0, 16 * sizeof(unsigned int)));
+  CUDA_TRY(e->d_ticket.reserve(16)); CUDA_TRY(cudaMemsetAsync(e->d_ticket.p, 0, 16 * sizeof(unsigned int), e->stream));
   CUDA_TRY(e->d_result.reserve(512));
   {
     // dynamic + static shared memory must stay within the opt-in limit
@@ -486,7 +496,7 @@ int gb_engine_create(gb_engine** out, int device)
     e->smem_optin -= 1024;   // head room for static shared memory of the kernels
   }
   CUDA_TRY(e->d_erfc.reserve((GBK_ERFC_DEG + 1) * GBK_ERFC_NINT));
-  CUDA_TRY(cudaMemcpy(e->d_erfc.p, h_erfc_table, sizeof(h_erfc_table), cudaMemcpyHostToDevice));
+  CUDA_TRY(copy_on_stream(e, e->d_erfc.p, h_erfc_table, sizeof(h_erfc_table), cudaMemcpyHostToDevice));
   e->P.erfc_tab = e->d_erfc.p;
   *out = e;
   return GB_OK;
@@ -540,8 +550,8 @@ int gb_upload_forcefield(gb_engine* e, const gb_forcefield* ff, const gb_tail_ta
     else { A[i] = make_double4(ff->epsilon[i], ff->sigma[i], ff->z[i], ff->shift[i]); B[i] = ff->c10 ? ff->c10[i] : 0.0; }
   }
   CUDA_TRY(e->d_ffA.reserve(n2)); CUDA_TRY(e->d_ffB.reserve(n2));
-  CUDA_TRY(cudaMemcpy(e->d_ffA.p, A.data(), n2 * sizeof(double4), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(e->d_ffB.p, B.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(copy_on_stream(e, e->d_ffA.p, A.data(), n2 * sizeof(double4), cudaMemcpyHostToDevice));
+  CUDA_TRY(copy_on_stream(e, e->d_ffB.p, B.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
   e->ntypes = n;
   e->P.ntypes = n; e->P.cut_vdw2 = ff->cutoff_vdw_sq; e->P.cut_coul2 = ff->cutoff_coul_sq; e->P.overlap = ff->overlap_criteria;
   e->P.no_charges = ff->no_charges; e->P.vdw_real_bias = ff->vdw_real_bias; e->P.use1264 = ff->use1264;
@@ -553,8 +563,8 @@ int gb_upload_forcefield(gb_engine* e, const gb_forcefield* ff, const gb_tail_ta
     for(size_t i = 0; i < n2; i++) { e->tail_use[i] = tail->use_tail[i]; e->tail_e[i] = tail->energy[i]; if(tail->use_tail[i]) e->has_tail = true; }
   }
   CUDA_TRY(e->d_tail_use.reserve(n2)); CUDA_TRY(e->d_tail_e.reserve(n2));
-  CUDA_TRY(cudaMemcpy(e->d_tail_use.p, e->tail_use.data(), n2 * sizeof(int), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(e->d_tail_e.p, e->tail_e.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(copy_on_stream(e, e->d_tail_use.p, e->tail_use.data(), n2 * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(copy_on_stream(e, e->d_tail_e.p, e->tail_e.data(), n2 * sizeof(double), cudaMemcpyHostToDevice));
   e->npseudo.assign(n, 0);
   e->have_ff = true;
   return GB_OK;
@@ -644,22 +654,22 @@ int apply_box(gb_engine* e, const gb_box* box)
     if(e->npos > 0)
     {
       CUDA_TRY(e->d_rowidx.reserve(e->npos)); CUDA_TRY(e->d_rowmeta.reserve(e->h_rowmeta.size())); CUDA_TRY(e->d_round.reserve(e->h_round.size()));
-      CUDA_TRY(cudaMemcpy(e->d_rowidx.p, e->h_rowidx.data(), e->npos * sizeof(int), cudaMemcpyHostToDevice));
-      CUDA_TRY(cudaMemcpy(e->d_rowmeta.p, e->h_rowmeta.data(), e->h_rowmeta.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CUDA_TRY(cudaMemcpy(e->d_round.p, e->h_round.data(), e->h_round.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CUDA_TRY(copy_on_stream(e, e->d_rowidx.p, e->h_rowidx.data(), e->npos * sizeof(int), cudaMemcpyHostToDevice));
+      CUDA_TRY(copy_on_stream(e, e->d_rowmeta.p, e->h_rowmeta.data(), e->h_rowmeta.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CUDA_TRY(copy_on_stream(e, e->d_round.p, e->h_round.data(), e->h_round.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
   }
   if(e->nact > 0)
   {
     CUDA_TRY(e->d_kpack.reserve(e->nact)); CUDA_TRY(e->d_kslot.reserve(e->nact)); CUDA_TRY(e->d_ktemp.reserve(e->nact));
-    CUDA_TRY(cudaMemcpy(e->d_kpack.p, e->h_kpack.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(e->d_kslot.p, e->h_kslot.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(e->d_ktemp.p, e->h_ktemp.data(), e->nact * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(copy_on_stream(e, e->d_kpack.p, e->h_kpack.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(copy_on_stream(e, e->d_kslot.p, e->h_kslot.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(copy_on_stream(e, e->d_ktemp.p, e->h_ktemp.data(), e->nact * sizeof(double), cudaMemcpyHostToDevice));
   }
   for(int i = 0; i < 3; i++)
   {
     CUDA_TRY(e->d_sf[i].reserve((size_t) std::max<long long>(2 * e->nvec, 2)));
-    CUDA_TRY(cudaMemset(e->d_sf[i].p, 0, (size_t) std::max<long long>(2 * e->nvec, 2) * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(e->d_sf[i].p, 0, (size_t) std::max<long long>(2 * e->nvec, 2) * sizeof(double), e->stream));
   }
   e->i_ads = 0; e->i_fw = 1; e->i_tmp = 2; e->have_sf = false; e->ktab_dirty = true;
   e->have_box = true;
@@ -699,10 +709,10 @@ int gb_upload_atoms(gb_engine* e, int32_t c, const gb_atoms* a)
     CUDA_TRY(cudaSetDevice(e->device));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     const size_t n = (size_t) e->nslots, b = n * sizeof(double);
-    CUDA_TRY(cudaMemcpy(e->hx.data(), e->dx.p, b, cudaMemcpyDeviceToHost)); CUDA_TRY(cudaMemcpy(e->hy.data(), e->dy.p, b, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(e->hz.data(), e->dz.p, b, cudaMemcpyDeviceToHost)); CUDA_TRY(cudaMemcpy(e->hq.data(), e->dq.p, b, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(e->hscale.data(), e->dscale.p, b, cudaMemcpyDeviceToHost)); CUDA_TRY(cudaMemcpy(e->hscoul.data(), e->dscoul.p, b, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(e->htype.data(), e->dtype.p, n * sizeof(int), cudaMemcpyDeviceToHost)); CUDA_TRY(cudaMemcpy(e->hmolid.data(), e->dmolid.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(copy_on_stream(e, e->hx.data(), e->dx.p, b, cudaMemcpyDeviceToHost)); CUDA_TRY(copy_on_stream(e, e->hy.data(), e->dy.p, b, cudaMemcpyDeviceToHost));
+    CUDA_TRY(copy_on_stream(e, e->hz.data(), e->dz.p, b, cudaMemcpyDeviceToHost)); CUDA_TRY(copy_on_stream(e, e->hq.data(), e->dq.p, b, cudaMemcpyDeviceToHost));
+    CUDA_TRY(copy_on_stream(e, e->hscale.data(), e->dscale.p, b, cudaMemcpyDeviceToHost)); CUDA_TRY(copy_on_stream(e, e->hscoul.data(), e->dscoul.p, b, cudaMemcpyDeviceToHost));
+    CUDA_TRY(copy_on_stream(e, e->htype.data(), e->dtype.p, n * sizeof(int), cudaMemcpyDeviceToHost)); CUDA_TRY(copy_on_stream(e, e->hmolid.data(), e->dmolid.p, n * sizeof(int), cudaMemcpyDeviceToHost));
     e->committed = false;
   }
   Comp& C = e->comps[c];
@@ -800,8 +810,8 @@ int gb_upload_structure_factors(gb_engine* e, const double* ads, const double* f
   if(!e->have_box) return fail(GB_ERR_STATE, "upload the box first");
   CUDA_TRY(cudaSetDevice(e->device));
   const size_t b = (size_t) e->nvec * 2 * sizeof(double);
-  if(ads) CUDA_TRY(cudaMemcpy(e->d_sf[e->i_ads].p, ads, b, cudaMemcpyHostToDevice));
-  if(fw)  CUDA_TRY(cudaMemcpy(e->d_sf[e->i_fw].p, fw, b, cudaMemcpyHostToDevice));
+  if(ads) CUDA_TRY(copy_on_stream(e, e->d_sf[e->i_ads].p, ads, b, cudaMemcpyHostToDevice));
+  if(fw)  CUDA_TRY(copy_on_stream(e, e->d_sf[e->i_fw].p, fw, b, cudaMemcpyHostToDevice));
   e->have_sf = true; e->ktab_dirty = true;
   return GB_OK;
 }
@@ -812,9 +822,9 @@ int gb_download_structure_factors(gb_engine* e, double* ads, double* fw, double*
   CUDA_TRY(cudaSetDevice(e->device));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   const size_t b = (size_t) e->nvec * 2 * sizeof(double);
-  if(ads) CUDA_TRY(cudaMemcpy(ads, e->d_sf[e->i_ads].p, b, cudaMemcpyDeviceToHost));
-  if(fw)  CUDA_TRY(cudaMemcpy(fw, e->d_sf[e->i_fw].p, b, cudaMemcpyDeviceToHost));
-  if(tmp) CUDA_TRY(cudaMemcpy(tmp, e->d_sf[e->i_tmp].p, b, cudaMemcpyDeviceToHost));
+  if(ads) CUDA_TRY(copy_on_stream(e, ads, e->d_sf[e->i_ads].p, b, cudaMemcpyDeviceToHost));
+  if(fw)  CUDA_TRY(copy_on_stream(e, fw, e->d_sf[e->i_fw].p, b, cudaMemcpyDeviceToHost));
+  if(tmp) CUDA_TRY(copy_on_stream(e, tmp, e->d_sf[e->i_tmp].p, b, cudaMemcpyDeviceToHost));
   return GB_OK;
 }
 
@@ -841,7 +851,7 @@ int gb_set_block_pockets(gb_engine* e, int32_t c, int32_t n, const double* cente
   std::vector<double> h((size_t) 4 * n);
   for(int i = 0; i < n; i++) { h[4 * i] = centers[3 * i]; h[4 * i + 1] = centers[3 * i + 1]; h[4 * i + 2] = centers[3 * i + 2]; h[4 * i + 3] = radii[i]; }
   CUDA_TRY(cudaMalloc(&C.d_pocket, h.size() * sizeof(double)));
-  CUDA_TRY(cudaMemcpy(C.d_pocket, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(copy_on_stream(e, C.d_pocket, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
   C.npocket = n;
   return GB_OK;
 }
@@ -1059,7 +1069,7 @@ int total_vdw_real_impl(gb_engine* e, gb_move_energy* out, int32_t* overlap)
   if(overlap)
   {
     int f = 0;
-    CUDA_TRY(cudaMemcpy(&f, e->d_iscratch.p, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(copy_on_stream(e, &f, e->d_iscratch.p, sizeof(int), cudaMemcpyDeviceToHost));
     *overlap = f ? 1 : 0;
   }
   return GB_OK;

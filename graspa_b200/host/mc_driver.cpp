@@ -943,6 +943,8 @@ void run_move(Sim& S, long cycle)
   else if(R < X.cGibbsXfer) move_gibbs_transfer(S, comp);
   else if(R < X.cGibbsVolume) move_gibbs_volume(S, comp);
   if(S.trace_lines == lines_before) trace_move(S, "none", comp, mol, 0, 0.0);     // the selected move had nothing to act on
+  static const bool sync_every_move = std::getenv("GB_SYNC_EVERY_MOVE") != nullptr;   // debugging aid: drain every engine's stream after each move
+  if(sync_every_move) for(Sim* b : S.sh.boxes) GB(gb_synchronize(b->e));
 }
 
 void update_max(double* m, MoveCount& w, MoveCount& cum, double cap)           // Update_Max_Translation / Update_Max_Rotation
