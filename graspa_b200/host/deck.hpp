@@ -571,7 +571,6 @@ inline void read_restart(Deck& d, const std::string& dir)
     const size_t ms = (size_t) c.ms(), interval = (size_t) nmol * ms;
     if(start + 5 * interval > L.size()) throw std::runtime_error("restart file shorter than its molecule count says");
     c.restart_pos.resize(3 * interval); c.restart_charge.resize(interval);
-    double first[3] = {0, 0, 0};
     for(size_t a = 0; a < interval; a++)
     {
       auto t = terms(L[start + a]);
@@ -582,7 +581,6 @@ inline void read_restart(Deck& d, const std::string& dir)
       // nvcc / gcc it is zero, so atoms 1.. end up at their minimum image from the ORIGIN while atom 0 stays where the file has it.
       // Energies do not notice (every pair goes through PBC), rotations about atom 0 do: the accept/reject sequence of a run that
       // starts from a RASPA-2 restart file only matches with the same coordinates.
-      (void) first;
       if(std::stol(t[2]) != 0) { double v[3] = {p[0], p[1], p[2]}; min_image(d, v); for(int k = 0; k < 3; k++) p[k] = v[k]; }
       for(int k = 0; k < 3; k++) c.restart_pos[3 * a + k] = p[k];
       c.restart_charge[a] = std::stod(terms(L[start + 3 * interval + a]).at(3));

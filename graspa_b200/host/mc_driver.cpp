@@ -895,7 +895,7 @@ void move_gibbs_transfer(Sim& S0, int comp)
   long del_mol = 0;
   if(B.C[comp].nmol >= 1)
   {
-    (void) (long) (size_t) (S0.rng.uniform() * (double) A.C[comp].nmol);          // InsertionSelectedMol: drawn, not used by the growth
+    S0.rng.uniform();                                                              // InsertionSelectedMol: drawn (move_struct.h:438), not used by the growth
     del_mol = (long) (size_t) (S0.rng.uniform() * (double) B.C[comp].nmol);
   }
   else die("Gibbs particle transfer out of an empty box is not driven by this host program");
