@@ -1182,20 +1182,22 @@ int gb_volume_move_trial(gb_engine* e, const gb_box* new_box, double scale, gb_m
   }
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   e->vol_pending = true; e->committed = true;
-  // 3. the new box: scalars, k table, empty structure factors; fractional coordinates of every slot
-  rc = apply_box(e, new_box); if(rc) return rc;
-  rc = ready(e); if(rc) return rc;
+  // 3. the new box: scalars, k table, empty structure factors; fractional coordinates of every slot.
+  //    From here on a failure puts the old state back before it is reported, so that the engine is never left half-scaled.
+  auto undo = [&](int code) { const std::string msg = gb_last_error(); gb_volume_move_finish(e, 0); return fail(code, msg); };
+  rc = apply_box(e, new_box); if(rc) return undo(rc);
+  rc = ready(e); if(rc) return undo(rc);
   if(n > 0)
   {
     k_frac_update<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->P, e->dx.p, e->dy.p, e->dz.p, e->dfx.p, e->dfy.p, e->dfz.p, 0, (int) n);
     e->launches++;
-    CUDA_TRY(cudaGetLastError());
+    if(cudaGetLastError() != cudaSuccess) return undo(GB_ERR_CUDA);
   }
   e->pack_dirty = true;
   // 4. total energies of the scaled system; the structure factors of the new state are stored on the way
   gb_move_energy v, w;
-  rc = total_vdw_real_impl(e, &v, overlap); if(rc) return rc;
-  rc = total_ewald_impl(e, 1, true, &w); if(rc) return rc;
+  rc = total_vdw_real_impl(e, &v, overlap); if(rc) return undo(rc);
+  rc = total_ewald_impl(e, 1, true, &w); if(rc) return undo(rc);
   *out = v; out->HHEwaldE = w.HHEwaldE; out->HGEwaldE = w.HGEwaldE; out->GGEwaldE = w.GGEwaldE;
   return GB_OK;
 }
