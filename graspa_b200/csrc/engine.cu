@@ -654,17 +654,17 @@ int apply_box(gb_engine* e, const gb_box* box)
     if(e->npos > 0)
     {
       CUDA_TRY(e->d_rowidx.reserve(e->npos)); CUDA_TRY(e->d_rowmeta.reserve(e->h_rowmeta.size())); CUDA_TRY(e->d_round.reserve(e->h_round.size()));
-      CUDA_TRY(copy_on_stream(e, e->d_rowidx.p, e->h_rowidx.data(), e->npos * sizeof(int), cudaMemcpyHostToDevice));
-      CUDA_TRY(copy_on_stream(e, e->d_rowmeta.p, e->h_rowmeta.data(), e->h_rowmeta.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CUDA_TRY(copy_on_stream(e, e->d_round.p, e->h_round.data(), e->h_round.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpyAsync(e->d_rowidx.p, e->h_rowidx.data(), e->npos * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(e->d_rowmeta.p, e->h_rowmeta.data(), e->h_rowmeta.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(e->d_round.p, e->h_round.data(), e->h_round.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     }
   }
   if(e->nact > 0)
   {
     CUDA_TRY(e->d_kpack.reserve(e->nact)); CUDA_TRY(e->d_kslot.reserve(e->nact)); CUDA_TRY(e->d_ktemp.reserve(e->nact));
-    CUDA_TRY(copy_on_stream(e, e->d_kpack.p, e->h_kpack.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice));
-    CUDA_TRY(copy_on_stream(e, e->d_kslot.p, e->h_kslot.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice));
-    CUDA_TRY(copy_on_stream(e, e->d_ktemp.p, e->h_ktemp.data(), e->nact * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpyAsync(e->d_kpack.p, e->h_kpack.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->d_kslot.p, e->h_kslot.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->d_ktemp.p, e->h_ktemp.data(), e->nact * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   }
   for(int i = 0; i < 3; i++)
   {
@@ -673,6 +673,7 @@ int apply_box(gb_engine* e, const gb_box* box)
   }
   e->i_ads = 0; e->i_fw = 1; e->i_tmp = 2; e->have_sf = false; e->ktab_dirty = true;
   e->have_box = true;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));       // one wait for all the table uploads above (their host vectors are rebuilt by the next call)
   return GB_OK;
 }
 } // namespace
