@@ -410,3 +410,25 @@ def ref_inverse_matrix(cell):
     cell = np.ascontiguousarray(cell, dtype=np.float64); inv = np.zeros(9); det = C.c_double(0)
     ref().ref_inverse_matrix(_p(cell, f64p), _p(inv, f64p), C.byref(det))
     return inv, det.value
+
+
+def scale_positions(box: Box, sys_: System, scale: float):
+    """ScalePositions (mc_box.h:18-64) restated: every molecule of components >= 1 follows its first atom, which scales with the box;
+    the other atoms keep their minimum-image offset (PBC, maths.cuh:427-450, old box) from it.  -> positions (n, 3) of the scaled state.
+    The framework (component 0) is not scaled (ScaleFirstComponentFramework = false, mc_box.h:204)."""
+    inv = box.inv.reshape(3, 3); cell = box.cell.reshape(3, 3)
+    pos = sys_.pos.copy()
+    for c in range(1, sys_.ncomp):
+        o = int(sys_.offsets[c]); ms = int(sys_.molsize[c])
+        for m in range(int(sys_.natoms[c]) // max(ms, 1)):
+            first = sys_.pos[o + m * ms].copy()
+            d = sys_.pos[o + m * ms:o + (m + 1) * ms] - first
+            if box.cubic:
+                L = np.array([cell[0, 0], cell[1, 1], cell[2, 2]]); iL = np.array([inv[0, 0], inv[1, 1], inv[2, 2]])
+                d = d - np.trunc(d * iL + np.where(d >= 0.0, 0.5, -0.5)) * L
+            else:
+                f = d @ inv
+                f = f - np.trunc(f + np.where(f >= 0.0, 0.5, -0.5))
+                d = f @ cell
+            pos[o + m * ms:o + (m + 1) * ms] = first * scale + d
+    return pos

@@ -609,15 +609,8 @@ def _scaled_state(box, s, scale, dk=0):
     from graspa_b200.types import Box, System
     kmax = tuple(int(k) + dk for k in box.kmax)
     nb = Box(box.cell * scale, alpha=box.alpha, kmax=kmax, recip_cutoff=(1.05 * max(kmax)) ** 2, prefactor=box.prefactor)
-    pos = s.pos.copy()
-    for c in range(1, s.ncomp):
-        o = int(s.offsets[c]); ms = int(s.molsize[c])
-        for m in range(int(s.natoms[c]) // ms):
-            first = s.pos[o + m * ms].copy()
-            d = s.pos[o + m * ms:o + (m + 1) * ms] - first
-            f = d @ box.inv.reshape(3, 3)              # minimum image of the offsets (PBC, maths.cuh:427-450)
-            f -= np.trunc(f + np.where(f >= 0.0, 0.5, -0.5))
-            pos[o + m * ms:o + (m + 1) * ms] = first * scale + f @ box.cell.reshape(3, 3)
+    from oracle import oracle as orc
+    pos = orc.scale_positions(box, s, scale)          # ScalePositions restated in oracle/oracle.py
     return nb, System(s.nhost, s.natoms.copy(), s.molsize.copy(), pos, s.charge.copy(), s.type.copy(), s.molid.copy(), alloc=s.alloc.copy())
 
 
