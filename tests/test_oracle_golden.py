@@ -118,3 +118,19 @@ def test_nist_spce_known_answers(oracle, b):
     assert abs(ref["fourier_gg"] * K - fourier) <= 5e-5 * abs(fourier)
     assert abs((E[0] - ref["fourier_gg"]) * K - self_intra) <= 5e-5 * abs(self_intra)
     assert abs((v.sum() + E.sum() + tail) * K - total) <= 1e-5 * abs(total)
+
+
+def test_scale_positions_properties(oracle):
+    """ScalePositions restatement (mc_box.h:18-64): the identity at scale 1, first atoms scale with the box, molecules stay rigid,
+    the framework does not move"""
+    from tests.conftest import load_config
+    box, ff, s, z = load_config("B")
+    comp = 1; ms = 3; o = int(s.offsets[comp]); nm = int(s.natoms[comp]) // ms
+    assert np.array_equal(oracle.scale_positions(box, s, 1.0)[:int(s.natoms[0])], s.pos[:int(s.natoms[0])])
+    assert np.max(np.abs(oracle.scale_positions(box, s, 1.0) - s.pos)) < 1e-12
+    p = oracle.scale_positions(box, s, 1.05)
+    assert np.array_equal(p[:int(s.natoms[0])], s.pos[:int(s.natoms[0])])
+    old = s.pos[o:o + nm * ms].reshape(nm, ms, 3); new = p[o:o + nm * ms].reshape(nm, ms, 3)
+    assert np.max(np.abs(new[:, 0] - 1.05 * old[:, 0])) < 1e-12
+    d_old = np.linalg.norm(old[:, 1:] - old[:, :1], axis=2); d_new = np.linalg.norm(new[:, 1:] - new[:, :1], axis=2)
+    assert np.max(np.abs(d_old - d_new)) < 1e-12 and d_old.max() < 3.0
