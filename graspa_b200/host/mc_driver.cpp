@@ -1255,6 +1255,51 @@ int main(int argc, char** argv)
     }
     return 0;
   }
+  if(argc >= 3 && std::string(argv[1]) == "--dump-deck")
+  {
+    // the parsed deck as JSON (no GPU needed): what set_up_engine() uploads, for tests/golden/make_golden.py to build the
+    // config C fixture (separated framework components, mixing-rule overrides, shifted potentials, block pockets)
+    try
+    {
+      deck::Deck d = deck::load(argv[2]);
+      auto arr = [](const char* key, const double* v, size_t n, bool last = false) {
+        std::printf("\"%s\": [", key); for(size_t i = 0; i < n; i++) std::printf("%s%.17g", i ? ", " : "", v[i]); std::printf("]%s\n", last ? "" : ",");
+      };
+      auto iarr = [](const char* key, const int* v, size_t n, bool last = false) {
+        std::printf("\"%s\": [", key); for(size_t i = 0; i < n; i++) std::printf("%s%d", i ? ", " : "", v[i]); std::printf("]%s\n", last ? "" : ",");
+      };
+      const size_t n2 = d.names.size() * d.names.size();
+      std::printf("{\n");
+      arr("cell", d.cell, 9); arr("inv", d.inv, 9); iarr("kmax", d.kmax, 3);
+      std::printf("\"volume\": %.17g, \"alpha\": %.17g, \"prefactor\": %.17g, \"recip_cutoff\": %.17g, \"beta\": %.17g, \"temperature\": %.17g,\n",
+                  d.volume, d.alpha, d.prefactor, d.recip_cutoff, d.beta, d.temperature);
+      std::printf("\"cutoff_vdw\": %.17g, \"cutoff_coul\": %.17g, \"overlap\": %.17g, \"no_charges\": %d, \"ntrials\": %d, \"norient\": %d, \"adsorbate_allocate\": %ld,\n",
+                  d.cutoff_vdw, d.cutoff_coul, d.overlap, d.no_charges ? 1 : 0, d.n_trial_positions, d.n_trial_orientations, d.adsorbate_allocate);
+      std::printf("\"names\": ["); for(size_t i = 0; i < d.names.size(); i++) std::printf("%s\"%s\"", i ? ", " : "", d.names[i].c_str()); std::printf("],\n");
+      arr("eps", d.eps.data(), n2); arr("sigma", d.sigma.data(), n2); arr("shift", d.shift.data(), n2);
+      iarr("use_tail", d.use_tail.data(), n2); arr("tail_energy", d.tail_energy.data(), n2);
+      std::printf("\"framework\": [\n");
+      std::printf("{\"molsize\": %zu,\n", d.ftype.size()); arr("pos", d.fpos.data(), d.fpos.size()); arr("charge", d.fcharge.data(), d.fcharge.size());
+      iarr("type", d.ftype.data(), d.ftype.size(), true); std::printf("}");
+      for(const auto& F : d.fw)
+      {
+        std::printf(",\n{\"molsize\": %d,\n", F.molsize); arr("pos", F.pos.data(), F.pos.size()); arr("charge", F.charge.data(), F.charge.size());
+        iarr("molid", F.molid.data(), F.molid.size()); iarr("type", F.type.data(), F.type.size(), true); std::printf("}");
+      }
+      std::printf("],\n\"adsorbates\": [\n");
+      for(size_t c = 0; c < d.comps.size(); c++)
+      {
+        const deck::Component& M = d.comps[c];
+        std::printf("%s{\"name\": \"%s\", \"invert_pockets\": %d,\n", c ? ",\n" : "", M.name.c_str(), M.invert_pockets ? 1 : 0);
+        arr("pos", M.pos.data(), M.pos.size()); arr("charge", M.charge.data(), M.charge.size());
+        arr("pocket_centers", M.pocket_centers.data(), M.pocket_centers.size()); arr("pocket_radii", M.pocket_radii.data(), M.pocket_radii.size());
+        iarr("type", M.type.data(), M.type.size(), true); std::printf("}");
+      }
+      std::printf("]\n}\n");
+    }
+    catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
+    return 0;
+  }
   if(argc >= 3 && std::string(argv[1]) == "--parse-only")
   {
     try

@@ -6,7 +6,7 @@ import pytest
 from graspa_b200.types import TrialAtoms, species_counts, pseudo_atom_counts
 from tests.conftest import load_config, rel_err
 
-CONFIGS = ["A", "E", "B", "D"]
+CONFIGS = ["A", "E", "B", "C", "D"]
 
 
 @pytest.mark.parametrize("name", CONFIGS)
@@ -29,7 +29,7 @@ def test_trial_energies_match_reference(oracle, name):
         assert np.max(np.abs(e - z["tb2_energy"]) / scale) < 1e-10
 
 
-@pytest.mark.parametrize("name", ["A", "E", "B"])
+@pytest.mark.parametrize("name", ["A", "E", "B", "C"])
 def test_ewald_total_and_structure_factors(oracle, name):
     box, ff, s, z = load_config(name)
     E, sa, sf = oracle.ewald_total(box, s)
@@ -66,6 +66,65 @@ def test_widom_insertions_reproduce(oracle, name):
     assert (stage == z["widom_stage"]).all()
     assert rel_err(out[:, 0], z["widom_out"][:, 0], floor=1e-300) < 1e-12
     assert (counts == z["widom_counts"]).all()
+
+
+def _moved(s, z, k):
+    c = int(z["sb_comp"][k]); mol = int(z["sb_mol"][k]); ms = int(s.molsize[c]); o = int(s.offsets[c])
+    sl = slice(o + mol * ms, o + (mol + 1) * ms)
+    old = TrialAtoms(z["sb_old"][k][:3 * ms], s.charge[sl], s.type[sl]); new = TrialAtoms(z["sb_new"][k][:3 * ms], s.charge[sl], s.type[sl])
+    return c, mol, ms, old, new
+
+
+@pytest.mark.parametrize("name", ["B", "C", "D"])
+def test_single_body_delta_matches_reference(oracle, name):
+    """orc_single_body_delta (Calculate_Single_Body_Energy_VDWReal, VDW_Coulomb.cu:626-841, with its HH / HG / GG block layout,
+    mc_single_particle.h:150-165) against new - old through the REFERENCE's pair routines (fixture sb_delta): adsorbate molecules
+    in B, C, D and the movable Na+ of framework component 1 in C (cubic PBC branch, shifted potentials)."""
+    box, ff, s, z = load_config(name)
+    seen_host = False
+    for k in range(len(z["sb_comp"])):
+        c, mol, ms, old, new = _moved(s, z, k)
+        seen_host |= c < s.nhost
+        d, flag = oracle.single_body_delta(box, ff, s, c, mol, old, new)
+        ref = z["sb_delta"][k]
+        assert flag == int(z["sb_flag"][k])
+        assert np.max(np.abs(d - ref)) <= 1e-10 * max(1.0, float(np.abs(ref).max())), (name, k, d, ref)
+    assert seen_host == (name == "C")
+
+
+@pytest.mark.parametrize("name", ["B", "C"])
+def test_ewald_delta_matches_difference_of_reference_totals(oracle, name):
+    """orc_ewald_delta (Fourier_Ewald_Diff, Ewald_Energy_Functions.h:280-397) against Ewald_Total(after) - Ewald_Total(before) of
+    the REFERENCE (fixture sb_ewald), and its temp vector against the reference's structure factors of the moved state.  For a
+    framework component (C, Na+) the same-type vector is FrameworkEik (:460-467)."""
+    box, ff, s, z = load_config(name)
+    for k in range(len(z["sb_comp"])):
+        c, mol, ms, old, new = _moved(s, z, k)
+        host = c < s.nhost
+        same, cross = (z["sf_fw"], z["sf_ads"]) if host else (z["sf_ads"], z["sf_fw"])
+        pos = np.concatenate([old.pos, new.pos]); q = np.concatenate([old.charge, new.charge])
+        got, temp, _ = oracle.ewald_delta(box, pos, q, np.ones(2 * ms), ms, ms, same, cross)
+        ref = z["sb_ewald"][k]
+        # the reference side is a difference of two totals of magnitude 1e5-1e6: 1e-9 of the totals is the resolution
+        tol = 1e-9 * max(1.0, float(np.abs(z["ewald_E"]).max()))
+        assert abs(got[0] - ref[0]) <= tol and abs(got[1] - ref[1]) <= tol, (name, k, got, ref)
+        act = np.abs(temp.reshape(-1, 2)).sum(axis=1) > 0
+        assert np.max(np.abs(temp.reshape(-1, 2)[act] - z["sb_temp"][k].reshape(-1, 2)[act])) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["A", "E", "B", "C"])
+def test_insertion_ewald_delta_matches_reference_totals(oracle, name):
+    """INSERTION: Fourier delta minus the rigid exclusion constants (Ewald_Energy_Functions.h:547-576) = Ewald_Total with the
+    molecule - Ewald_Total without it, both by the reference"""
+    box, ff, s, z = load_config(name)
+    comp = int(z["comp"]); ms = int(s.molsize[comp]); o = int(s.offsets[comp])
+    q = s.charge[o:o + ms]
+    got, temp, _ = oracle.ewald_delta(box, z["ins_pos"], q, np.ones(ms), 0, ms, z["sf_ads"], z["sf_fw"])
+    same = got[0] - float(z["excl"][0]) - float(z["excl"][1])
+    tol = 1e-9 * max(1.0, float(np.abs(z["ewald_E"]).max()))
+    assert abs(same - z["ins_ewald"][0]) <= tol and abs(got[1] - z["ins_ewald"][1]) <= tol
+    act = np.abs(temp.reshape(-1, 2)).sum(axis=1) > 0
+    assert np.max(np.abs(temp.reshape(-1, 2)[act] - z["ins_temp"].reshape(-1, 2)[act])) < 1e-9
 
 
 def test_rng_stream_seed0(oracle):
