@@ -456,6 +456,7 @@ struct Timer
 
 extern "C" {
 
+static int engine_init(gb_engine* e, int device);
 int gb_abi_version(void) { return GB_ABI_VERSION; }
 const char* gb_last_error(void) { return g_err.c_str(); }
 
@@ -472,6 +473,14 @@ int gb_engine_create(gb_engine** out, int device)
   CUDA_TRY(cudaSetDevice(device));
   gb_engine* e = new gb_engine();
   e->device = device;
+  const int rc_init = engine_init(e, device);
+  if(rc_init != GB_OK) { const std::string msg = g_err; gb_engine_destroy(e); return fail(rc_init, msg); }     // nothing of a half-built engine is leaked
+  *out = e;
+  return GB_OK;
+}
+
+static int engine_init(gb_engine* e, int device)
+{
   CUDA_TRY(cudaGetDeviceProperties(&e->prop, device));
   int optin = 0; CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   e->smem_optin = (size_t) optin;
@@ -498,7 +507,6 @@ int gb_engine_create(gb_engine** out, int device)
   CUDA_TRY(e->d_erfc.reserve((GBK_ERFC_DEG + 1) * GBK_ERFC_NINT));
   CUDA_TRY(copy_on_stream(e, e->d_erfc.p, h_erfc_table, sizeof(h_erfc_table), cudaMemcpyHostToDevice));
   e->P.erfc_tab = e->d_erfc.p;
-  *out = e;
   return GB_OK;
 }
 
@@ -506,7 +514,7 @@ int gb_engine_destroy(gb_engine* e)
 {
   if(!e) return GB_OK;
   cudaSetDevice(e->device);
-  cudaStreamSynchronize(e->stream);
+  if(e->stream) cudaStreamSynchronize(e->stream);
   e->d_ffA.release(); e->d_ffB.release(); e->d_erfc.release(); e->d_tail_use.release(); e->d_tail_e.release();
   e->dx.release(); e->dy.release(); e->dz.release(); e->dfx.release(); e->dfy.release(); e->dfz.release();
   e->dq.release(); e->dscale.release(); e->dscoul.release(); e->dtype.release(); e->dmolid.release();
@@ -516,10 +524,12 @@ int gb_engine_destroy(gb_engine* e)
   e->d_ktab.release(); e->d_pool.release(); e->d_rec.release(); e->d_out8.release(); e->d_partial.release(); e->d_sums.release();
   e->d_uni.release(); e->d_scratch.release(); e->d_result.release(); e->d_stage.release(); e->d_iscratch.release();
   e->d_idx0.release(); e->d_idx1.release(); e->d_ticket.release(); e->d_mv.release(); e->d_mvi.release(); e->d_ewpos.release();
+  e->d_vol_xyz.release(); e->d_vol_sf.release(); e->d_rowidx.release(); e->d_rowmeta.release(); e->d_round.release(); e->d_rtab.release();
   for(auto& C : e->comps) if(C.d_pocket) cudaFree(C.d_pocket);
   if(e->h_pinned) cudaFreeHost(e->h_pinned);
-  cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
-  cudaStreamDestroy(e->stream);
+  if(e->ev0) cudaEventDestroy(e->ev0);
+  if(e->ev1) cudaEventDestroy(e->ev1);
+  if(e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return GB_OK;
 }
@@ -574,6 +584,8 @@ namespace {
 // Box scalars, active k table and structure-factor storage for `box`.  Does not touch the atom slots.
 int apply_box(gb_engine* e, const gb_box* box)
 {
+  if(box->kmax[0] > 127 || box->kmax[1] > 127 || box->kmax[2] > 127 || box->kmax[0] < 0 || box->kmax[1] < 0 || box->kmax[2] < 0)
+    return fail(GB_ERR_ARG, "kmax out of range [0,127]");      // before any engine state changes
   e->tail_memo.clear();                                           // the tail deltas carry 1 / volume
   CUDA_TRY(cudaSetDevice(e->device));
   e->cur_box = *box;
@@ -587,8 +599,6 @@ int apply_box(gb_engine* e, const gb_box* box)
     e->P.cell_mode = (upper_zero && lower_zero) ? 2 : (upper_zero ? 1 : 0);
   }
   for(int i = 0; i < 3; i++) e->P.kmax[i] = box->kmax[i];
-  if(box->kmax[0] > 127 || box->kmax[1] > 127 || box->kmax[2] > 127 || box->kmax[0] < 0 || box->kmax[1] < 0 || box->kmax[2] < 0)
-    return fail(GB_ERR_ARG, "kmax out of range [0,127]");
   // active k table: Ewald_Energy_Functions.h:299-334, 358-360
   const int kxm = box->kmax[0], kym = box->kmax[1], kzm = box->kmax[2];
   e->nvec = (long long)(kxm + 1) * (2 * kym + 1) * (2 * kzm + 1);
@@ -683,6 +693,18 @@ int gb_upload_box(gb_engine* e, const gb_box* box)
   if(!e || !box) return fail(GB_ERR_ARG, "null argument");
   if(e->vol_pending) return fail(GB_ERR_STATE, "a volume move is pending: call gb_volume_move_finish first");
   int rc = apply_box(e, box); if(rc) return rc;
+  if(e->committed && !e->device_stale && e->nslots > 0)
+  {
+    // accept calls or a volume move made the device copy authoritative: the host staging arrays are stale and must not be uploaded
+    // over it.  Only the fractional mirror depends on the box; refresh it in place (as gb_volume_move_trial does).
+    const size_t n = (size_t) e->nslots;
+    k_frac_update<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->P, e->dx.p, e->dy.p, e->dz.p, e->dfx.p, e->dfy.p, e->dfz.p, 0, (int) n);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->pack_dirty = true;
+    return GB_OK;
+  }
   e->device_stale = true;
   return GB_OK;
 }
@@ -704,6 +726,10 @@ int gb_upload_atoms(gb_engine* e, int32_t c, const gb_atoms* a)
   if(c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "component out of range");
   if(a->n_live > a->n_upload || a->n_upload > a->n_alloc || (a->molsize <= 0 && a->n_alloc > 0)) return fail(GB_ERR_ARG, "inconsistent atom counts");   // an empty component (a box without framework atoms) may have molsize 0
   if(!e->have_ff) return fail(GB_ERR_STATE, "upload the force field before atoms");
+  if(a->n_upload > 0 && !a->pos) return fail(GB_ERR_ARG, "null positions");
+  if(a->type) for(int64_t i = 0; i < a->n_upload; i++) if(a->type[i] >= (uint64_t) e->ntypes) return fail(GB_ERR_ARG, "atom type outside the force-field table");   // checked before any state changes
+  if(e->comps[c].uploaded && e->comps[c].alloc != (int) a->n_alloc) return fail(GB_ERR_ARG, "component re-uploaded with a different n_alloc");
+  if(!e->comps[c].uploaded) for(int k = 0; k < c; k++) if(!e->comps[k].uploaded) return fail(GB_ERR_STATE, "upload components in order");
   if(e->committed && !e->device_stale && e->nslots > 0)
   {
     // accept calls changed the device copy: bring the host staging arrays up to date before they are re-uploaded
@@ -717,10 +743,8 @@ int gb_upload_atoms(gb_engine* e, int32_t c, const gb_atoms* a)
     e->committed = false;
   }
   Comp& C = e->comps[c];
-  if(C.uploaded && C.alloc != (int) a->n_alloc) return fail(GB_ERR_ARG, "component re-uploaded with a different n_alloc");
   if(!C.uploaded)
   {
-    for(int k = 0; k < c; k++) if(!e->comps[k].uploaded) return fail(GB_ERR_STATE, "upload components in order");
     C.offset = e->nslots; C.alloc = (int) a->n_alloc; e->nslots += C.alloc;
     const size_t n = (size_t) e->nslots;
     e->hx.resize(n, 0.0); e->hy.resize(n, 0.0); e->hz.resize(n, 0.0); e->hq.resize(n, 0.0); e->hscale.resize(n, 1.0); e->hscoul.resize(n, 1.0);
@@ -737,7 +761,6 @@ int gb_upload_atoms(gb_engine* e, int32_t c, const gb_atoms* a)
     e->hx[g] = a->pos[3 * i]; e->hy[g] = a->pos[3 * i + 1]; e->hz[g] = a->pos[3 * i + 2];
     e->hq[g] = a->charge ? a->charge[i] : 0.0; e->hscale[g] = a->scale ? a->scale[i] : 1.0; e->hscoul[g] = a->scale_coul ? a->scale_coul[i] : 1.0;
     e->htype[g] = a->type ? (int) a->type[i] : 0; e->hmolid[g] = a->molid ? (int) a->molid[i] : 0;
-    if(e->htype[g] < 0 || e->htype[g] >= e->ntypes) return fail(GB_ERR_ARG, "atom type outside the force-field table");
   }
   for(int i = 0; i < C.natoms; i++) e->npseudo[e->htype[(size_t) C.offset + i]]++;
   bool hc = false;
@@ -1192,7 +1215,7 @@ int gb_volume_move_trial(gb_engine* e, const gb_box* new_box, double scale, gb_m
   {
     k_frac_update<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->P, e->dx.p, e->dy.p, e->dz.p, e->dfx.p, e->dfy.p, e->dfz.p, 0, (int) n);
     e->launches++;
-    if(cudaGetLastError() != cudaSuccess) return undo(GB_ERR_CUDA);
+    { const cudaError_t le = cudaGetLastError(); if(le != cudaSuccess) { fail(GB_ERR_CUDA, std::string("k_frac_update: ") + cudaGetErrorString(le)); return undo(GB_ERR_CUDA); } }
   }
   e->pack_dirty = true;
   // 4. total energies of the scaled system; the structure factors of the new state are stored on the way

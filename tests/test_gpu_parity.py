@@ -7,7 +7,7 @@ from graspa_b200.types import TrialAtoms, species_counts, pseudo_atom_counts, IN
 from tests.conftest import load_config, rel_err
 
 pytestmark = pytest.mark.gpu
-CONFIGS = ["A", "E", "B", "D"]
+CONFIGS = ["A", "E", "B", "C", "D"]
 ETOL = 1e-10
 
 
@@ -64,7 +64,7 @@ def test_trial_energies_edge_cases(gpu_engine_factory, oracle):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["A", "E", "B"])
+@pytest.mark.parametrize("name", ["A", "E", "B", "C"])
 def test_ewald_total_and_structure_factors(gpu_engine_factory, name):
     box, ff, s, z = load_config(name)
     eng = gpu_engine_factory(box, ff, s)
@@ -78,7 +78,7 @@ def test_ewald_total_and_structure_factors(gpu_engine_factory, name):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["A", "B"])
+@pytest.mark.parametrize("name", ["A", "B", "C"])
 def test_ewald_delta_vs_oracle(gpu_engine_factory, oracle, name):
     box, ff, s, z = load_config(name)
     eng = gpu_engine_factory(box, ff, s)
@@ -116,7 +116,7 @@ def test_tail(gpu_engine_factory, name):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["B", "D"])
+@pytest.mark.parametrize("name", ["B", "C", "D"])
 def test_total_vdw_real_vs_oracle(gpu_engine_factory, oracle, name):
     box, ff, s, z = load_config(name)
     eng = gpu_engine_factory(box, ff, s)
