@@ -120,4 +120,24 @@ if [ "$WHAT" = "trace" ]; then
   sed -n '295,299p' "$SCR/axpy.cu"
   rm -rf "$SCR"
 fi
+if [ "$WHAT" = "dump" ]; then
+  # the same program instrumented by oracle/ref_dump_patch.py (scratch copy only): Insertion_Body writes its trial positions,
+  # per-trial energies, Boltzmann selection and Rosenbluth weights, BlockedPocket its verdicts, to $GRASPA_DUMP.  Run once on the
+  # GPU box (scripts/make_ref_dump.sh); tests/golden/make_ref_dump.py turns the text into the committed fixtures.
+  echo "[build_ref] reference CUDA program with the CBMC dump (sm_100)"
+  SCR="$(mktemp -d /tmp/graspa_ref_dump.XXXXXX)"
+  cp -r "$REF/src_clean/." "$SCR/"
+  chmod -R u+w "$SCR"
+  sed -i '268s/{OLDComponent, OLDMolInComponent}/{(int) OLDComponent, (int) OLDMolInComponent}/' "$SCR/mc_swap_moves.h"
+  python "$HERE/ref_dump_patch.py" "$SCR"
+  FLAGS="-O3 -std=c++20 -arch=sm_100 --expt-relaxed-constexpr -w -Xcompiler -fopenmp -rdc=true -x cu"
+  ( cd "$SCR"
+    for f in axpy.cu main.cpp read_data.cpp data_struct.cpp VDW_Coulomb.cu; do
+      "$NVCC" $FLAGS -c "$f" -o "${f%.*}.o" &
+    done
+    wait
+    "$NVCC" -arch=sm_100 -rdc=true -Xcompiler -fopenmp main.o read_data.o axpy.o data_struct.o VDW_Coulomb.o -o "$OUT/graspa_ref_cuda_dump.x"
+  )
+  rm -rf "$SCR"
+fi
 echo "[build_ref] done: $(ls "$OUT")"
