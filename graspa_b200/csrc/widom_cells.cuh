@@ -1,0 +1,474 @@
+// graspa_b200 -- batched Widom insertions, cell-sorted pair stage (included by engine.cu).
+//
+// Same arithmetic per pair as k_widom_pair (pair_energy, common.cuh) and the same stage logic (Widom_Move_FirstBead_PARTIAL /
+// Widom_Move_Chain_PARTIAL, mc_widom.h:385-614), but the work is laid out for the batch instead of for one insertion:
+//
+//   * every trial atom of the batch (n x NumberOfTrials first beads, then n x NumberOfTrialOrientations x (Molsize-1) chain atoms)
+//     is binned into a grid of small cells of the box (counting sort on the device: histogram, scan, scatter);
+//   * one CTA takes one cell at a time and builds, ONCE for all trial atoms of the cell, the list of system atoms that can be
+//     inside the cutoff of any point of the cell: atoms within r_cut + r_cell of the cell centre, stored as Cartesian vectors
+//     from the centre with the periodic image already chosen (the reference's per-axis nearest image, maths.cuh:437-448, is the
+//     same for every point of the cell unless the atom sits within the cell's extent of a half-box plane; those few atoms go to
+//     a second list that keeps the general wrap);
+//   * a warp then evaluates one trial atom against the list: 3 shared-memory loads, 3 subtractions and a dot product per
+//     candidate -- no minimum image, no tile tests, no shuffles -- and ~70 % of the candidates are inside the cutoff, so the
+//     LJ / erfc body runs in place without a compaction queue.
+//
+// Against the warp-per-insertion kernel (k_widom_pair: k-d tiles tested per trial atom, 1300 distance tests for 450 pairs, 37 % of
+// them on the general minimum-image path in config E) this is ~650 distance tests per trial atom at a third of the instructions
+// each.  Results per trial atom do not depend on what else is in the batch (list order = atom order), so batches can be cut
+// anywhere without changing a bit.
+#pragma once
+#include "common.cuh"
+#include "pair.cuh"
+#include "misc_kernels.cuh"
+#include "move_kernels.cuh"
+
+struct WcGrid
+{
+  int n[3]; int ncells;
+  double inv_n[3];          // 1 / n_k
+  double margin[3];         // half the fractional extent of a cell + guard: a trial of the cell is within margin of the centre, per axis
+  double rcell;             // largest Cartesian distance from a cell centre to a point of its cell
+  int cap_fast, cap_slow;   // list capacities (shared memory)
+  int chunk;                // trial atoms per work item
+};
+
+// live atoms of every component, gathered contiguously (k_wc_pack): fractional coordinates, charge * scaleCoul, type | kind << 16
+struct WcAtoms { const double* __restrict__ fx; const double* __restrict__ fy; const double* __restrict__ fz; const double* __restrict__ q; const int* __restrict__ tk; int n; };
+
+__global__ void k_wc_pack(SysView S, SegList L, int ntot, double* fx, double* fy, double* fz, double* q, int* tk)
+{
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if(v >= ntot) return;
+  int off = v, s = 0;
+  while(s + 1 < L.nseg && off >= L.count[s]) { off -= L.count[s]; s++; }
+  const int i = L.start[s] + off;
+  fx[v] = S.fx[i]; fy[v] = S.fy[i]; fz[v] = S.fz[i]; q[v] = S.q[i] * S.scoul[i];
+  tk[v] = S.type[i] | ((L.kind[s] == 2 ? 1 : 0) << 16);
+}
+
+// cell of a Cartesian point and the Cartesian vector from the cell centre to (the image in the primary cell of) the point
+__device__ __forceinline__ void wc_bin(const DevParams& P, const WcGrid& G, double x, double y, double z, int& cell, double& dx, double& dy, double& dz)
+{
+  double fx, fy, fz; to_frac(P, x, y, z, fx, fy, fz);
+  fx -= floor(fx); fy -= floor(fy); fz -= floor(fz);
+  int ix = (int) (fx * G.n[0]), iy = (int) (fy * G.n[1]), iz = (int) (fz * G.n[2]);
+  ix = min(max(ix, 0), G.n[0] - 1); iy = min(max(iy, 0), G.n[1] - 1); iz = min(max(iz, 0), G.n[2] - 1);
+  const double ex = fx - ((double) ix + 0.5) * G.inv_n[0], ey = fy - ((double) iy + 0.5) * G.inv_n[1], ez = fz - ((double) iz + 0.5) * G.inv_n[2];
+  dx = P.cell[0] * ex + P.cell[3] * ey + P.cell[6] * ez;
+  dy = P.cell[1] * ex + P.cell[4] * ey + P.cell[7] * ez;
+  dz = P.cell[2] * ex + P.cell[5] * ey + P.cell[8] * ez;
+  cell = (ix * G.n[1] + iy) * G.n[2] + iz;
+}
+
+// ---------------------------------------------------------------------------------------------- first-bead trial positions
+struct WcGen
+{
+  const double* __restrict__ pool3; const long long* __restrict__ fb_index;
+  long long n; int ntrials, norient;
+  int* ucell; double* udelta; int* count;
+};
+
+// BoxLength o random (mc_widom.h:137-138), binned.  One thread per (insertion, trial).
+__global__ void k_wc_gen_fb(DevParams P, WcGrid G, WcGen A)
+{
+  const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if(g >= A.n * A.ntrials) return;
+  const long long ins = g / A.ntrials; const int t = (int) (g - ins * A.ntrials);
+  const long long fb_off = A.fb_index ? A.fb_index[ins] : ins * (A.ntrials + A.norient);
+  const double* r = A.pool3 + 3 * (fb_off + t);
+  int cell; double dx, dy, dz;
+  wc_bin(P, G, P.cell[0] * r[0], P.cell[4] * r[1], P.cell[8] * r[2], cell, dx, dy, dz);
+  A.ucell[g] = cell; A.udelta[3 * g] = dx; A.udelta[3 * g + 1] = dy; A.udelta[3 * g + 2] = dz;
+  atomicAdd(&A.count[cell], 1);
+}
+
+// ---------------------------------------------------------------------------------------------- counting sort: scan + work items
+// one block: exclusive scan of the cell counts -> off[]; work items {cell, first sorted index, count} of at most `chunk` trial atoms
+__global__ void __launch_bounds__(1024)
+k_wc_scan(const int* __restrict__ count, int ncells, int chunk, int* off, int* cursor, int* items /* 3 ints each */, int* ctl /* [0] = number of items, [1] = work counter */)
+{
+  __shared__ int wa[32], wb[32];
+  __shared__ int carry[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if(threadIdx.x == 0) { carry[0] = 0; carry[1] = 0; }
+  __syncthreads();
+  for(int base = 0; base < ncells; base += 1024)
+  {
+    const int c = base + threadIdx.x;
+    const int cnt = c < ncells ? count[c] : 0;
+    const int nch = (cnt + chunk - 1) / chunk;
+    int a = cnt, b = nch;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
+    {
+      const int ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
+      if(lane >= o) { a += ta; b += tb; }
+    }
+    if(lane == 31) { wa[warp] = a; wb[warp] = b; }
+    __syncthreads();
+    if(warp == 0)
+    {
+      int x = wa[lane], y = wb[lane];
+#pragma unroll
+      for(int o = 1; o < 32; o <<= 1)
+      {
+        const int tx = __shfl_up_sync(0xffffffffu, x, o), ty = __shfl_up_sync(0xffffffffu, y, o);
+        if(lane >= o) { x += tx; y += ty; }
+      }
+      wa[lane] = x; wb[lane] = y;
+    }
+    __syncthreads();
+    const int exa = carry[0] + (warp ? wa[warp - 1] : 0) + a - cnt;
+    const int exb = carry[1] + (warp ? wb[warp - 1] : 0) + b - nch;
+    if(c < ncells)
+    {
+      off[c] = exa; cursor[c] = 0;
+      for(int k = 0; k < nch; k++) { items[3 * (exb + k)] = c; items[3 * (exb + k) + 1] = exa + k * chunk; items[3 * (exb + k) + 2] = min(chunk, cnt - k * chunk); }
+    }
+    __syncthreads();
+    if(threadIdx.x == 0) { carry[0] += wa[31]; carry[1] += wb[31]; }
+    __syncthreads();
+  }
+  if(threadIdx.x == 0) { off[ncells] = carry[0]; ctl[0] = carry[1]; ctl[1] = 0; }
+}
+
+// sorted records {dx, dy, dz, id}: the order inside a cell is whatever the atomics give; no result depends on it
+__global__ void k_wc_scatter(const int* __restrict__ ucell, const double* __restrict__ udelta, long long ntot, const int* __restrict__ off, int* cursor, double4* srec)
+{
+  const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if(g >= ntot) return;
+  const int c = ucell[g];
+  if(c < 0) return;
+  const int p = off[c] + atomicAdd(&cursor[c], 1);
+  srec[p] = make_double4(udelta[3 * g], udelta[3 * g + 1], udelta[3 * g + 2], __longlong_as_double(g));
+}
+
+// ---------------------------------------------------------------------------------------------- pair energies, cell by cell
+struct WcEnergy
+{
+  WcAtoms atoms;
+  const double4* __restrict__ srec; const int* __restrict__ items; int* ctl;
+  // trial atom a of the molecule: type and charge * scaleCoul (template = slot 0 of the component, mc_widom.h:256)
+  const double* __restrict__ tq; const double* __restrict__ tscoul; const int* __restrict__ ttype; int ms;
+  int amod, abase;          // trial atom of record id: abase + id % amod  (first beads: 0; chain atoms: 1 + id % (ms - 1))
+  int stage_ff;
+  double* e4; int* flag;    // per record id: {HGVDW, HGReal, GGVDW, GGReal}, overlap
+  int* overflow;            // set when a list does not fit its capacity (the caller then falls back to k_widom_pair)
+};
+
+__host__ __device__ inline size_t wc_energy_smem(int ntypes, bool stage_ff, int cap_fast, int cap_slow)
+{
+  size_t b = GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD + (stage_ff ? (size_t) ntypes * ntypes * 32 : 0);
+  b += 64 * 8 + 64 * 4 + 64 * 4;                                  // trial atom tables + warp counters
+  b = (b + 15) / 16 * 16;
+  b += (size_t) (cap_fast + cap_slow) * 36 + 64;
+  return (b + 15) / 16 * 16;
+}
+
+template <int CELL, bool HAS_GG>
+__global__ void __launch_bounds__(512, 1)
+k_wc_energy(DevParams P, WcGrid G, WcEnergy A)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* etab = reinterpret_cast<double*>(smem + GBK_SMEM_TABLES_OFF);
+  double4* fftab = reinterpret_cast<double4*>(smem + GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD);
+  unsigned char* p = smem + GBK_SMEM_TABLES_OFF + GBK_ERFC_BYTES_PAD + (A.stage_ff ? (size_t) P.ntypes * P.ntypes * 32 : 0);
+  double* Tq = reinterpret_cast<double*>(p); p += 64 * 8;
+  int* Ttype = reinterpret_cast<int*>(p); p += 64 * 4;
+  int* wcnt = reinterpret_cast<int*>(p); p += 64 * 4;
+  p = smem + ((size_t) (p - smem) + 15) / 16 * 16;
+  const int CF = G.cap_fast, CS = G.cap_slow;
+  double* Fx = reinterpret_cast<double*>(p); double* Fy = Fx + CF; double* Fz = Fy + CF; double* Fq = Fz + CF;
+  double* Sx = Fq + CF; double* Sy = Sx + CS; double* Sz = Sy + CS; double* Sq = Sz + CS;
+  int* Ftk = reinterpret_cast<int*>(Sq + CS); int* Stk = Ftk + CF;
+  __shared__ int s_item;
+
+  const int lane = (int) lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  stage_erfc_table(P, etab);
+  if(A.stage_ff) for(int i = threadIdx.x; i < P.ntypes * P.ntypes; i += blockDim.x) fftab[i] = P.ffA[i];
+  for(int a = threadIdx.x; a < A.ms && a < 64; a += blockDim.x) { Tq[a] = A.tq[a] * A.tscoul[a]; Ttype[a] = A.ttype[a]; }
+  const double4* ffp = A.stage_ff ? fftab : P.ffA;
+  GBK_ASSUME_SHARED(Fx); GBK_ASSUME_SHARED(Fy); GBK_ASSUME_SHARED(Fz); GBK_ASSUME_SHARED(Fq); GBK_ASSUME_SHARED(Ftk);
+  GBK_ASSUME_SHARED(Sx); GBK_ASSUME_SHARED(Sy); GBK_ASSUME_SHARED(Sz); GBK_ASSUME_SHARED(Sq); GBK_ASSUME_SHARED(Stk);
+  CellRegs<CELL> C; C.load(P);
+  const double cut_max = P.cull_rcut * P.cull_rcut;
+  const double reach = P.cull_rcut + G.rcell;
+  const double R2 = reach * reach * (1.0 + 1e-12);
+  const int nitems = A.ctl[0];
+  __syncthreads();
+
+  for(;;)
+  {
+    if(threadIdx.x == 0) s_item = atomicAdd(&A.ctl[1], 1);
+    __syncthreads();
+    const int item = s_item;
+    if(item >= nitems) break;
+    const int cell = A.items[3 * item], first = A.items[3 * item + 1], cnt = A.items[3 * item + 2];
+    const int iz = cell % G.n[2], iy = (cell / G.n[2]) % G.n[1], ix = cell / (G.n[2] * G.n[1]);
+    const double fcx = ((double) ix + 0.5) * G.inv_n[0], fcy = ((double) iy + 0.5) * G.inv_n[1], fcz = ((double) iz + 0.5) * G.inv_n[2];
+    // ---- candidate lists of the cell, in atom order (deterministic): ballot per warp, counts through shared memory
+    int nfast = 0, nslow = 0;
+    for(int i0 = 0; i0 < A.atoms.n; i0 += blockDim.x)
+    {
+      const int i = i0 + threadIdx.x;
+      int cls = 0; double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+      if(i < A.atoms.n)
+      {
+        const double d0 = frac_wrap(A.atoms.fx[i] - fcx), d1 = frac_wrap(A.atoms.fy[i] - fcy), d2 = frac_wrap(A.atoms.fz[i] - fcz);
+        const bool n0 = fabs(d0) > 0.5 - G.margin[0], n1 = fabs(d1) > 0.5 - G.margin[1], n2 = fabs(d2) > 0.5 - G.margin[2];
+        if(!(n0 || n1 || n2))
+        {
+          // the image is the same for every point of the cell: keep the Cartesian vector from the cell centre
+          double x, y, z;
+          if(CELL == 2) { x = C.c0 * d0; y = C.c4 * d1; z = C.c8 * d2; }
+          else if(CELL == 1) { x = C.c0 * d0 + C.c3 * d1 + C.c6 * d2; y = C.c4 * d1 + C.c7 * d2; z = C.c8 * d2; }
+          else { x = C.c0 * d0 + C.c3 * d1 + C.c6 * d2; y = C.c1 * d0 + C.c4 * d1 + C.c7 * d2; z = C.c2 * d0 + C.c5 * d1 + C.c8 * d2; }
+          if(x * x + y * y + z * z <= R2) { cls = 1; v0 = x; v1 = y; v2 = z; }
+        }
+        else
+        {
+          // within the cell's extent of a half-box plane on some axis: the image depends on the trial.  Necessary per axis for any
+          // trial of the cell to see the atom inside the cutoff: the wrapped fractional difference reaches into [-w, w].
+          const bool ok0 = (fabs(d0) <= P.cull_w[0] + G.margin[0]) || (n0 && P.cull_w[0] + 2.0 * G.margin[0] >= 0.5);
+          const bool ok1 = (fabs(d1) <= P.cull_w[1] + G.margin[1]) || (n1 && P.cull_w[1] + 2.0 * G.margin[1] >= 0.5);
+          const bool ok2 = (fabs(d2) <= P.cull_w[2] + G.margin[2]) || (n2 && P.cull_w[2] + 2.0 * G.margin[2] >= 0.5);
+          if(ok0 && ok1 && ok2) { cls = 2; v0 = d0; v1 = d1; v2 = d2; }
+        }
+      }
+      const unsigned mf = __ballot_sync(0xffffffffu, cls == 1), msl = __ballot_sync(0xffffffffu, cls == 2);
+      if(lane == 0) { wcnt[warp] = __popc(mf); wcnt[32 + warp] = __popc(msl); }
+      __syncthreads();
+      int pf = nfast, ps = nslow;
+      for(int w = 0; w < nwarps; w++)
+      {
+        const int cf = wcnt[w], cs = wcnt[32 + w];
+        if(w < warp) { pf += cf; ps += cs; }
+        nfast += cf; nslow += cs;
+      }
+      if(cls == 1)
+      {
+        const int q = pf + __popc(mf & lt_mask);
+        if(q < CF) { Fx[q] = v0; Fy[q] = v1; Fz[q] = v2; Fq[q] = A.atoms.q[i]; Ftk[q] = A.atoms.tk[i]; }
+      }
+      else if(cls == 2)
+      {
+        const int q = ps + __popc(msl & lt_mask);
+        if(q < CS) { Sx[q] = v0; Sy[q] = v1; Sz[q] = v2; Sq[q] = A.atoms.q[i]; Stk[q] = A.atoms.tk[i]; }
+      }
+      __syncthreads();
+    }
+    if(nfast > CF || nslow > CS)
+    {
+      if(threadIdx.x == 0) *A.overflow = 1;
+      nfast = min(nfast, CF); nslow = min(nslow, CS);
+    }
+    // ---- one warp per trial atom of the item
+    for(int t = warp; t < cnt; t += nwarps)
+    {
+      const double4 rec = A.srec[first + t];
+      const long long id = __double_as_longlong(rec.w);
+      const int a = A.abase + (int) (id % A.amod);
+      const int ttype = Ttype[a]; const double tq = Tq[a];
+      double ev0 = 0.0, er0 = 0.0, ev1 = 0.0, er1 = 0.0; int fl = 0;
+#pragma unroll 2
+      for(int j = lane; j < nfast; j += 32)
+      {
+        const double dx = Fx[j] - rec.x, dy = Fy[j] - rec.y, dz = Fz[j] - rec.z;
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        if(r2 < cut_max)
+        {
+          const int tk = Ftk[j];
+          double ev, er; int f;
+          pair_energy(P, etab, ffp, true, r2, (tk & 0xffff) * P.ntypes + ttype, 1.0, Fq[j] * tq, ev, er, f);
+          if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
+          else { ev0 += ev; er0 += er; }
+          fl |= f;
+        }
+      }
+      if(nslow > 0)
+      {
+        // fractional offset of the trial from the cell centre: the general wrap (CellRegs::r2) for the atoms near a half-box plane
+        double ox, oy, oz; to_frac(P, rec.x, rec.y, rec.z, ox, oy, oz);
+        for(int j = lane; j < nslow; j += 32)
+        {
+          const double r2 = C.r2(Sx[j] - ox, Sy[j] - oy, Sz[j] - oz);
+          if(r2 < cut_max)
+          {
+            const int tk = Stk[j];
+            double ev, er; int f;
+            pair_energy(P, etab, ffp, true, r2, (tk & 0xffff) * P.ntypes + ttype, 1.0, Sq[j] * tq, ev, er, f);
+            if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
+            else { ev0 += ev; er0 += er; }
+            fl |= f;
+          }
+        }
+      }
+      ev0 = warp_sum(ev0); er0 = warp_sum(er0);
+      if(HAS_GG) { ev1 = warp_sum(ev1); er1 = warp_sum(er1); }
+      fl = __any_sync(0xffffffffu, fl) ? 1 : 0;
+      if(lane == 0)
+      {
+        double4* o = reinterpret_cast<double4*>(A.e4 + 4 * id);
+        *o = make_double4(ev0, er0, ev1, er1);
+        A.flag[id] = fl;
+      }
+    }
+    __syncthreads();          // the lists are rebuilt by the next item
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- selection stages
+struct WcSel
+{
+  const double* __restrict__ pool3; const long long* __restrict__ fb_index; const long long* __restrict__ or_index;
+  const double* __restrict__ uni; long long n;
+  int ntrials, norient, ms;
+  const double* __restrict__ tx; const double* __restrict__ ty; const double* __restrict__ tz;       // template molecule (Cartesian)
+  CompView C;                                   // only the block-pocket fields are used
+  const double* __restrict__ e4; const int* __restrict__ flag;
+  double* fbres;                                // per insertion {W, HGv, HGr, GGv, GGr, x, y, z} of the selected first bead
+  double* rec; int* stage;                      // as k_widom_pair leaves them for k_widom_ewald
+  int first_bead_only;
+  int* ucell; double* udelta; int* count;       // chain atoms, binned (first-bead stage)
+};
+
+// Boltzmann selection of the first bead (CBMC_FirstBead_Finish, mc_widom.h:305-383) + the chain trial atoms
+// (get_random_trial_orientation, :215-303), binned for the second energy pass.  One warp per insertion.
+__global__ void __launch_bounds__(256)
+k_wc_select_fb(DevParams P, WcGrid G, WcSel A)
+{
+  const int lane = (int) lane_id();
+  const long long ins = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if(ins >= A.n) return;
+  const int cs = A.ms - 1, rec_stride = 5 + 3 * A.ms;
+  const long long fb_off = A.fb_index ? A.fb_index[ins] : ins * (A.ntrials + A.norient);
+  const long long or_off = A.or_index ? A.or_index[ins] : fb_off + A.ntrials;
+  double px = 0, py = 0, pz = 0; double e[4] = {0, 0, 0, 0}; int fl = 1;
+  if(lane < A.ntrials)
+  {
+    const double* r = A.pool3 + 3 * (fb_off + lane);
+    px = P.cell[0] * r[0]; py = P.cell[4] * r[1]; pz = P.cell[8] * r[2];
+    const double4 v = *reinterpret_cast<const double4*>(A.e4 + 4 * (ins * A.ntrials + lane));
+    e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w; fl = A.flag[ins * A.ntrials + lane];
+  }
+  if(A.C.npocket > 0)
+  {
+    // mc_widom.h:463-498: a blocked STARTING bead (trial 0) flags every trial, otherwise every blocked trial is flagged on its own
+    const double x0 = __shfl_sync(0xffffffffu, px, 0), y0 = __shfl_sync(0xffffffffu, py, 0), z0 = __shfl_sync(0xffffffffu, pz, 0);
+    bool blk = blocked_pocket(P, A.C, x0, y0, z0);
+    if(!blk && lane > 0 && lane < A.ntrials) blk = blocked_pocket(P, A.C, px, py, pz);
+    if(blk) fl = 1;
+  }
+  double tot = e[0] + e[2]; if(P.vdw_real_bias) tot += e[1] + e[3];
+  RosenResult r1 = rosenbluth_warp(-P.beta * tot, !fl, A.ntrials, A.uni ? A.uni[2 * ins] : 0.5, true);
+  double W = 0.0; int ok = r1.success && !(r1.R < 1e-150);
+  const int sfb = r1.sel_lane;
+  double efb[4];
+#pragma unroll
+  for(int k = 0; k < 4; k++) efb[k] = __shfl_sync(0xffffffffu, e[k], sfb);
+  if(ok)
+  {
+    W = r1.R / (double) A.ntrials;
+    if(!P.vdw_real_bias) W *= exp(-P.beta * (efb[1] + efb[3]));
+    if(W <= 1e-150) ok = 0;
+  }
+  if(A.first_bead_only) { if(lane == 0) A.stage[ins] = ok ? 1 : (r1.nsurv > 0 ? 0 : 2); return; }
+  double* rec = A.rec + (size_t) ins * rec_stride;
+  if(!ok) { if(lane == 0) { A.stage[ins] = 1; rec[0] = 0.0; } return; }
+  const double fbx = __shfl_sync(0xffffffffu, px, sfb), fby = __shfl_sync(0xffffffffu, py, sfb), fbz = __shfl_sync(0xffffffffu, pz, sfb);
+  if(cs == 0)
+  {
+    if(lane == 0) { A.stage[ins] = 0; rec[0] = W; for(int k = 0; k < 4; k++) rec[1 + k] = efb[k]; rec[5] = fbx; rec[6] = fby; rec[7] = fbz; }
+    return;
+  }
+  if(lane == 0)
+  {
+    double* f = A.fbres + 8 * ins;
+    f[0] = W; f[1] = efb[0]; f[2] = efb[1]; f[3] = efb[2]; f[4] = efb[3]; f[5] = fbx; f[6] = fby; f[7] = fbz;
+    A.stage[ins] = -1;                          // chain stage pending
+  }
+  if(lane < A.norient)
+  {
+    const double* r = A.pool3 + 3 * (or_off + lane);
+    for(int a = 0; a < cs; a++)
+    {
+      double vx = A.tx[1 + a] - A.tx[0], vy = A.ty[1 + a] - A.ty[0], vz = A.tz[1 + a] - A.tz[0];
+      rotate_quaternion(vx, vy, vz, r[0], r[1], r[2]);
+      int cell; double dx, dy, dz;
+      wc_bin(P, G, fbx + vx, fby + vy, fbz + vz, cell, dx, dy, dz);
+      const long long g = (ins * A.norient + lane) * cs + a;
+      A.ucell[g] = cell; A.udelta[3 * g] = dx; A.udelta[3 * g + 1] = dy; A.udelta[3 * g + 2] = dz;
+      atomicAdd(&A.count[cell], 1);
+    }
+  }
+}
+
+// Boltzmann selection of the orientation (tail of Widom_Move_Chain_PARTIAL, mc_widom.h:568-611) and the record k_widom_ewald reads
+__global__ void __launch_bounds__(256)
+k_wc_select_chain(DevParams P, WcSel A)
+{
+  const int lane = (int) lane_id();
+  const long long ins = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if(ins >= A.n) return;
+  if(A.stage[ins] != -1) return;
+  const int cs = A.ms - 1, rec_stride = 5 + 3 * A.ms;
+  const long long fb_off = A.fb_index ? A.fb_index[ins] : ins * (A.ntrials + A.norient);
+  const long long or_off = A.or_index ? A.or_index[ins] : fb_off + A.ntrials;
+  const double* f = A.fbres + 8 * ins;
+  double W = f[0];
+  double e[4] = {0, 0, 0, 0}; int fl = 1;
+  if(lane < A.norient)
+  {
+    fl = 0;
+    for(int a = 0; a < cs; a++)
+    {
+      const long long g = (ins * A.norient + lane) * cs + a;
+      const double4 v = *reinterpret_cast<const double4*>(A.e4 + 4 * g);
+      e[0] += v.x; e[1] += v.y; e[2] += v.z; e[3] += v.w; fl |= A.flag[g];
+    }
+  }
+  double tot = e[0] + e[2]; if(P.vdw_real_bias) tot += e[1] + e[3];
+  RosenResult r2 = rosenbluth_warp(-P.beta * tot, !fl, A.norient, A.uni[2 * ins + 1], true);
+  int ok = r2.success && !(r2.R < 1e-150);
+  const int so = r2.sel_lane;
+  double ech[4];
+#pragma unroll
+  for(int k = 0; k < 4; k++) ech[k] = __shfl_sync(0xffffffffu, e[k], so);
+  if(ok)
+  {
+    double W2 = r2.R / (double) A.norient;
+    if(!P.vdw_real_bias) W2 *= exp(-P.beta * (ech[1] + ech[3]));
+    W *= W2;
+    if(W <= 1e-150) ok = 0;
+  }
+  double* rec = A.rec + (size_t) ins * rec_stride;
+  if(!ok) { if(lane == 0) { A.stage[ins] = (r2.nsurv > 0) ? 2 : 3; rec[0] = 0.0; } return; }
+  // positions of the selected orientation (recomputed: one quaternion)
+  int blocked = 0;
+  if(lane == so)
+  {
+    const double* r = A.pool3 + 3 * (or_off + so);
+    if(A.C.npocket > 0 && blocked_pocket(P, A.C, f[5], f[6], f[7])) blocked = 1;
+    for(int a = 0; a < cs; a++)
+    {
+      double vx = A.tx[1 + a] - A.tx[0], vy = A.ty[1 + a] - A.ty[0], vz = A.tz[1 + a] - A.tz[0];
+      rotate_quaternion(vx, vy, vz, r[0], r[1], r[2]);
+      const double cx = f[5] + vx, cy = f[6] + vy, cz = f[7] + vz;
+      rec[8 + 3 * a] = cx; rec[9 + 3 * a] = cy; rec[10 + 3 * a] = cz;
+      // after the growth EVERY atom of the molecule is tested against the block pockets (mc_swap_utilities.h:46-80)
+      if(A.C.npocket > 0 && !blocked && blocked_pocket(P, A.C, cx, cy, cz)) blocked = 1;
+    }
+  }
+  blocked = __shfl_sync(0xffffffffu, blocked, so);
+  if(blocked) { if(lane == 0) { A.stage[ins] = 2; rec[0] = 0.0; } return; }
+  if(lane == 0)
+  {
+    A.stage[ins] = 0;
+    rec[0] = W;
+    for(int k = 0; k < 4; k++) rec[1 + k] = f[1 + k] + ech[k];
+    rec[5] = f[5]; rec[6] = f[6]; rec[7] = f[7];
+  }
+}

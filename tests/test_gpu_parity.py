@@ -138,7 +138,8 @@ def test_widom_batch_vs_golden(gpu_engine_factory, name):
     rnd = z["widom_rnd"].reshape(-1, 3)
     out, stage, sums = eng.widom_batch(comp, rnd, z["widom_uni"], n_blocks=5)
     ref = z["widom_out"]
-    assert (stage == z["widom_stage"]).all()
+    # the engine distinguishes "chain failed" (2) from "chain failed with no surviving orientation" (3); the oracle reports 2 for both
+    assert (np.where(stage == 3, 2, stage) == z["widom_stage"]).all()
     assert rel_err(out[:, 0], ref[:, 0], floor=1e-290) < 1e-9                   # W
     esc = np.abs(ref[:, 1:]).sum(axis=1, keepdims=True) + 1e-3
     assert np.max(np.abs(out[:, 1:] - ref[:, 1:]) / esc) < ETOL                 # energy terms
@@ -147,6 +148,28 @@ def test_widom_batch_vs_golden(gpu_engine_factory, name):
     assert abs(sums[:, 1].sum() - (ref[:, 0] ** 2).sum()) <= 1e-9 * (ref[:, 0] ** 2).sum()
     assert sums[:, 2].sum() == len(ref)
     assert np.allclose(sums[:, 3:10].sum(axis=0), (ref[:, :1] * ref[:, 1:]).sum(axis=0), rtol=1e-8, atol=1e-6)
+    eng.close()
+
+
+def test_widom_batch_vs_the_reference_program(gpu_engine_factory):
+    """gb_widom_batch against numbers the REFERENCE PROGRAM wrote while it ran (tests/golden/ref_dump_widom_A.npz: the first 150
+    Widom insertions of Examples/Henrys_coefficient, seed 0, from the instrumented reference CUDA build): same pool randoms and
+    uniforms in, final Rosenbluth weight within 1e-9 relative and every energy term out."""
+    import os
+    from tests.conftest import GOLDEN
+    box, ff, s, z = load_config("A")
+    d = dict(np.load(os.path.join(GOLDEN, "ref_dump_widom_A.npz")))
+    comp = int(z["comp"])
+    eng = gpu_engine_factory(box, ff, s, float(z["beta"]), 10, 10)
+    eng.upload_structure_factors(z["sf_ads"], z["sf_fw"]); eng.set_exclusion_constants(comp, float(z["excl"][0]), float(z["excl"][1]))
+    rnd = np.concatenate([d["fb_rnd"], d["ch_rnd"]], axis=1)
+    uni = np.stack([d["fbs"][:, 3], d["chs"][:, 3]], axis=1)
+    out, stage, sums = eng.widom_batch(comp, rnd.reshape(-1, 3), uni)
+    ref = d["ins"]
+    assert (stage == 0).all() and d["has_ins"].all()
+    assert np.max(np.abs(out[:, 0] - ref[:, 0]) / ref[:, 0]) < 1e-9
+    esc = np.abs(ref[:, 1:]).sum(axis=1, keepdims=True) + 1e-3
+    assert np.max(np.abs(out[:, 1:] - ref[:, 1:]) / esc) < 1e-9
     eng.close()
 
 
