@@ -5,6 +5,7 @@
 #include "pair_kernels.cuh"
 #include "move_kernels.cuh"
 #include "fused_kernel.cuh"
+#include "widom_cells.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -99,6 +100,10 @@ struct gb_engine
   gb_box cur_box{}, vol_old_box{}; bool vol_pending = false, vol_had_sf = false; long long vol_old_nvec = 0;
   DevBuf<double> d_vol_xyz, d_vol_sf;
 
+  // cell-sorted Widom pair stage (widom_cells.cuh)
+  DevBuf<double> wc_udelta, wc_e4, wc_fbres, wc_afx, wc_afy, wc_afz, wc_aq; DevBuf<double4> wc_srec;
+  DevBuf<int> wc_ucell, wc_flag, wc_count, wc_off, wc_cursor, wc_items, wc_ctl, wc_atk;
+  bool wc_overflowed = false;            // a candidate list did not fit once: this engine keeps to k_widom_pair
   // CBMC
   int ntrials = 10, norient = 10; bool have_cbmc = false;
   DevBuf<double> d_pool; long long n_pool = 0;
@@ -498,6 +503,12 @@ static int engine_init(gb_engine* e, int device)
     CUDA_TRY(cudaFuncSetAttribute(k_widom_pair<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_widom_ewald));
     CUDA_TRY(cudaFuncSetAttribute(k_widom_ewald, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_move));
     CUDA_TRY(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, GBF_MAX_DYN_SMEM));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_ewald_delta));
@@ -524,6 +535,8 @@ int gb_engine_destroy(gb_engine* e)
   e->d_ktab.release(); e->d_pool.release(); e->d_rec.release(); e->d_out8.release(); e->d_partial.release(); e->d_sums.release();
   e->d_uni.release(); e->d_scratch.release(); e->d_result.release(); e->d_stage.release(); e->d_iscratch.release();
   e->d_idx0.release(); e->d_idx1.release(); e->d_ticket.release(); e->d_mv.release(); e->d_mvi.release(); e->d_ewpos.release();
+  e->wc_udelta.release(); e->wc_e4.release(); e->wc_fbres.release(); e->wc_afx.release(); e->wc_afy.release(); e->wc_afz.release(); e->wc_aq.release(); e->wc_srec.release();
+  e->wc_ucell.release(); e->wc_flag.release(); e->wc_count.release(); e->wc_off.release(); e->wc_cursor.release(); e->wc_items.release(); e->wc_ctl.release(); e->wc_atk.release();
   e->d_vol_xyz.release(); e->d_vol_sf.release(); e->d_rowidx.release(); e->d_rowmeta.release(); e->d_round.release(); e->d_rtab.release();
   for(auto& C : e->comps) if(C.d_pocket) cudaFree(C.d_pocket);
   if(e->h_pinned) cudaFreeHost(e->h_pinned);
@@ -1257,10 +1270,17 @@ int gb_volume_move_finish(gb_engine* e, int32_t accept)
 // ---------------------------------------------------------------------------------------------- batched Widom
 // stage A launch shared by gb_widom_batch and gb_widom_first_bead_success
 // ins0 / n_total: this launch covers insertions [ins0, ins0 + n) of a batch of n_total (its inputs already point at ins0)
+static bool widom_cells_wanted(gb_engine* e, int comp, long long n_total);
+static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double* d_pool, const long long* d_fb, const long long* d_or, const double* d_uni,
+                               int first_bead_only, long long ins0, long long n_total);
+
 static int widom_stage_a(gb_engine* e, int comp, long long n, const double* d_pool, const long long* d_fb, const long long* d_or, const double* d_uni,
                          int first_bead_only, long long ins0 = 0, long long n_total = 0)
 {
   int rc;
+  // large batches (and components with block pockets) take the cell-sorted pair stage; the choice is made on the size of the WHOLE
+  // batch so that the chunks of a pipelined upload all go the same way
+  if(widom_cells_wanted(e, comp, n_total > 0 ? n_total : ins0 + n)) return widom_stage_a_cells(e, comp, n, d_pool, d_fb, d_or, d_uni, first_bead_only, ins0, n_total);
   const Comp& C = e->comps[comp];
   const int ms = C.molsize, cs = ms - 1;
   const int rec_stride = 5 + 3 * ms;
@@ -1300,13 +1320,146 @@ static int widom_stage_a(gb_engine* e, int comp, long long n, const double* d_po
   return GB_OK;
 }
 
+// ---- cell-sorted pair stage (widom_cells.cuh): same inputs and the same rec / stage outputs as widom_stage_a
+static bool widom_cells_wanted(gb_engine* e, int comp, long long n_total)
+{
+  const Comp& C = e->comps[comp];
+  if(!e->P.all_unit_scale || C.molsize > 33 || e->wc_overflowed) return false;
+  const char* env = std::getenv("GB_WIDOM_PATH");             // A/B measurements and tests: "cells" / "warp"
+  if(env && std::strcmp(env, "cells") == 0) return true;
+  if(env && std::strcmp(env, "warp") == 0) return C.npocket > 0;
+  return C.npocket > 0 || n_total >= 16384;                    // below that the per-cell list build is not amortised
+}
+
+static int widom_cells_grid(gb_engine* e, WcGrid& G)
+{
+  const double* H = e->P.cell;
+  double h = 2.0;
+  if(const char* env = std::getenv("GB_WC_H")) h = std::max(0.5, std::atof(env));
+  for(;;)
+  {
+    long long nc = 1;
+    for(int k = 0; k < 3; k++)
+    {
+      const double len = std::sqrt(H[3 * k] * H[3 * k] + H[3 * k + 1] * H[3 * k + 1] + H[3 * k + 2] * H[3 * k + 2]);
+      G.n[k] = std::max(1, (int) std::lround(len / h));
+      nc *= G.n[k];
+    }
+    if(nc <= 32768) { G.ncells = (int) nc; break; }
+    h *= 1.1;
+  }
+  G.rcell = 0.0;
+  for(int k = 0; k < 3; k++) { G.inv_n[k] = 1.0 / (double) G.n[k]; G.margin[k] = 0.5 * G.inv_n[k] + 1e-9; }
+  for(int sx = -1; sx <= 1; sx += 2) for(int sy = -1; sy <= 1; sy += 2)
+  {
+    const double f[3] = {0.5 * sx * G.inv_n[0], 0.5 * sy * G.inv_n[1], 0.5 * G.inv_n[2]};
+    const double x = H[0] * f[0] + H[3] * f[1] + H[6] * f[2], y = H[1] * f[0] + H[4] * f[1] + H[7] * f[2], z = H[2] * f[0] + H[5] * f[1] + H[8] * f[2];
+    G.rcell = std::max(G.rcell, std::sqrt(x * x + y * y + z * z));
+  }
+  G.rcell = G.rcell * (1.0 + 1e-9) + 1e-9;
+  G.chunk = 512;
+  if(const char* env = std::getenv("GB_WC_CHUNK")) G.chunk = std::max(32, std::atoi(env));
+  return GB_OK;
+}
+
+static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double* d_pool, const long long* d_fb, const long long* d_or, const double* d_uni,
+                               int first_bead_only, long long ins0, long long n_total)
+{
+  const Comp& C = e->comps[comp];
+  const int ms = C.molsize, cs = ms - 1;
+  const int rec_stride = 5 + 3 * ms;
+  if(n_total < ins0 + n) n_total = ins0 + n;
+  if(ins0 == 0) { CUDA_TRY(e->d_rec.reserve((size_t) n_total * rec_stride)); CUDA_TRY(e->d_stage.reserve((size_t) n_total)); }
+  WcGrid G; int rc = widom_cells_grid(e, G); if(rc) return rc;
+  // ---- live atoms of every component, contiguous
+  SegList L = seg_list(e, 0);
+  int ntot = 0, nads = 0;
+  for(int s = 0; s < L.nseg; s++) { ntot += L.count[s]; if(L.kind[s] == 2) nads += L.count[s]; }
+  const size_t na = (size_t) std::max(ntot, 1);
+  CUDA_TRY(e->wc_afx.reserve(na)); CUDA_TRY(e->wc_afy.reserve(na)); CUDA_TRY(e->wc_afz.reserve(na)); CUDA_TRY(e->wc_aq.reserve(na)); CUDA_TRY(e->wc_atk.reserve(na));
+  if(ntot > 0)
+  {
+    k_wc_pack<<<(ntot + 255) / 256, 256, 0, e->stream>>>(sys_view(e), L, ntot, e->wc_afx.p, e->wc_afy.p, e->wc_afz.p, e->wc_aq.p, e->wc_atk.p);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  // ---- capacities and shared memory of the energy kernel
+  const bool stage_ff = e->ntypes <= 24;
+  G.cap_fast = std::min(std::max(ntot, 32), 2304); G.cap_slow = std::min(std::max(ntot, 32), 768);
+  while(wc_energy_smem(e->ntypes, stage_ff, G.cap_fast, G.cap_slow) > e->smem_optin && G.cap_fast > 256) { G.cap_fast -= 128; G.cap_slow = std::max(128, G.cap_slow - 32); }
+  const size_t smemE = wc_energy_smem(e->ntypes, stage_ff, G.cap_fast, G.cap_slow);
+  if(smemE > e->smem_optin) return fail(GB_ERR_ARG, "cell-sorted Widom stage: shared memory exceeds the device limit");
+  // ---- buffers
+  const long long nfb = n * e->ntrials, nch = n * (long long) e->norient * cs, nmax = std::max(nfb, nch);
+  CUDA_TRY(e->wc_ucell.reserve((size_t) nmax)); CUDA_TRY(e->wc_udelta.reserve((size_t) nmax * 3)); CUDA_TRY(e->wc_srec.reserve((size_t) nmax));
+  CUDA_TRY(e->wc_e4.reserve((size_t) nmax * 4)); CUDA_TRY(e->wc_flag.reserve((size_t) nmax)); CUDA_TRY(e->wc_fbres.reserve((size_t) n * 8));
+  CUDA_TRY(e->wc_count.reserve((size_t) G.ncells + 1)); CUDA_TRY(e->wc_off.reserve((size_t) G.ncells + 1)); CUDA_TRY(e->wc_cursor.reserve((size_t) G.ncells + 1));
+  CUDA_TRY(e->wc_items.reserve(3 * ((size_t) G.ncells + (size_t) (nmax / G.chunk) + 2))); CUDA_TRY(e->wc_ctl.reserve(8));
+  WcEnergy E;
+  E.atoms.fx = e->wc_afx.p; E.atoms.fy = e->wc_afy.p; E.atoms.fz = e->wc_afz.p; E.atoms.q = e->wc_aq.p; E.atoms.tk = e->wc_atk.p; E.atoms.n = ntot;
+  E.srec = e->wc_srec.p; E.items = e->wc_items.p; E.ctl = e->wc_ctl.p;
+  E.tq = e->dq.p + C.offset; E.tscoul = e->dscoul.p + C.offset; E.ttype = e->dtype.p + C.offset; E.ms = ms;
+  E.stage_ff = stage_ff ? 1 : 0; E.e4 = e->wc_e4.p; E.flag = e->wc_flag.p; E.overflow = e->wc_ctl.p + 2;
+  const int gridE = e->prop.multiProcessorCount;
+  int thrE = 512;
+  if(const char* env = std::getenv("GB_WC_THREADS")) thrE = std::min(768, std::max(64, std::atoi(env) / 32 * 32));
+  auto sort_and_energy = [&](long long nitems_src, int amod, int abase) -> int
+  {
+    k_wc_scan<<<1, 1024, 0, e->stream>>>(e->wc_count.p, G.ncells, G.chunk, e->wc_off.p, e->wc_cursor.p, e->wc_items.p, e->wc_ctl.p);
+    k_wc_scatter<<<(unsigned) ((nitems_src + 255) / 256), 256, 0, e->stream>>>(e->wc_ucell.p, e->wc_udelta.p, nitems_src, e->wc_off.p, e->wc_cursor.p, e->wc_srec.p);
+    E.amod = amod; E.abase = abase;
+    const bool gg = nads > 0;
+    if(e->P.cell_mode == 2)      { if(gg) k_wc_energy<2, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else k_wc_energy<2, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); }
+    else if(e->P.cell_mode == 1) { if(gg) k_wc_energy<1, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else k_wc_energy<1, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); }
+    else                         { if(gg) k_wc_energy<0, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else k_wc_energy<0, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); }
+    e->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return GB_OK;
+  };
+  Timer tm(e, 0);
+  // ---- first beads
+  CUDA_TRY(cudaMemsetAsync(e->wc_count.p, 0, ((size_t) G.ncells + 1) * sizeof(int), e->stream));
+  if(ins0 == 0) CUDA_TRY(cudaMemsetAsync(e->wc_ctl.p + 2, 0, sizeof(int), e->stream));
+  WcGen Gn; Gn.pool3 = d_pool; Gn.fb_index = d_fb; Gn.n = n; Gn.ntrials = e->ntrials; Gn.norient = e->norient;
+  Gn.ucell = e->wc_ucell.p; Gn.udelta = e->wc_udelta.p; Gn.count = e->wc_count.p;
+  k_wc_gen_fb<<<(unsigned) ((nfb + 255) / 256), 256, 0, e->stream>>>(e->P, G, Gn);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  rc = sort_and_energy(nfb, 1, 0); if(rc) return rc;
+  // ---- first-bead selection + chain trial atoms
+  WcSel S;
+  S.pool3 = d_pool; S.fb_index = d_fb; S.or_index = d_or; S.uni = d_uni; S.n = n; S.ntrials = e->ntrials; S.norient = e->norient; S.ms = ms;
+  S.tx = e->dx.p + C.offset; S.ty = e->dy.p + C.offset; S.tz = e->dz.p + C.offset;
+  memset(&S.C, 0, sizeof(S.C)); S.C.pocket = C.d_pocket; S.C.npocket = C.npocket; S.C.pocket_invert = C.pocket_invert;
+  S.e4 = e->wc_e4.p; S.flag = e->wc_flag.p; S.fbres = e->wc_fbres.p;
+  S.rec = e->d_rec.p + (size_t) ins0 * rec_stride; S.stage = e->d_stage.p + ins0; S.first_bead_only = first_bead_only;
+  S.ucell = e->wc_ucell.p; S.udelta = e->wc_udelta.p; S.count = e->wc_count.p;
+  if(cs > 0 && !first_bead_only)
+  {
+    CUDA_TRY(cudaMemsetAsync(e->wc_count.p, 0, ((size_t) G.ncells + 1) * sizeof(int), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->wc_ucell.p, 0xFF, (size_t) nch * sizeof(int), e->stream));           // -1: insertions whose first bead failed leave no chain atoms
+  }
+  k_wc_select_fb<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, e->stream>>>(e->P, G, S);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  if(cs > 0 && !first_bead_only)
+  {
+    rc = sort_and_energy(nch, cs, 1); if(rc) return rc;
+    k_wc_select_chain<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, e->stream>>>(e->P, S);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  tm.stop(first_bead_only || cs == 0 ? 6 : 10);
+  return GB_OK;
+}
+
 int gb_widom_first_bead_success(gb_engine* e, int32_t comp, int64_t n, const double* pool3, int64_t n_pool, const int64_t* fb_index, int32_t* code)
 {
   int rc = ready(e); if(rc) return rc;
   if(n <= 0 || !pool3 || !fb_index || !code) return fail(GB_ERR_ARG, "bad arguments");
   if(comp < e->nhost || comp >= e->ncomp) return fail(GB_ERR_ARG, "Widom component must be an adsorbate component");
   if(!e->have_cbmc) return fail(GB_ERR_STATE, "gb_set_cbmc has not been called");
-  if(e->comps[comp].npocket > 0) return fail(GB_ERR_UNIMPLEMENTED, "block pockets are applied by the single-move path, not by the batched Widom kernel");
+  if(e->comps[comp].npocket > 0 && !widom_cells_wanted(e, comp, n)) return fail(GB_ERR_UNIMPLEMENTED, "block pockets need the cell-sorted Widom stage (unit scaling factors, molecules of <= 33 atoms)");
   CUDA_TRY(e->d_pool.reserve((size_t) n_pool * 3));
   CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, pool3, (size_t) n_pool * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   e->n_pool = n_pool;
@@ -1326,7 +1479,8 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   if(comp < e->nhost || comp >= e->ncomp) return fail(GB_ERR_ARG, "Widom component must be an adsorbate component");
   if(!e->have_cbmc) return fail(GB_ERR_STATE, "gb_set_cbmc has not been called");
   const Comp& C = e->comps[comp];
-  if(C.npocket > 0) return fail(GB_ERR_UNIMPLEMENTED, "block pockets are applied by the single-move path (gb_move_insertion / stage calls), not by the batched Widom kernel");
+  const bool cells = widom_cells_wanted(e, comp, n);
+  if(C.npocket > 0 && !cells) return fail(GB_ERR_UNIMPLEMENTED, "block pockets need the cell-sorted Widom stage (unit scaling factors, molecules of <= 33 atoms)");
   const int ms = C.molsize, cs = ms - 1;
   if(cs > GBK_MAX_CS) return fail(GB_ERR_ARG, "molecule too large for the CBMC chain stage");
   const bool do_ewald = !e->P.no_charges && C.has_charge && e->nact > 0;
@@ -1442,7 +1596,15 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
     if(outputs_on_device) CUDA_TRY(cudaMemcpyAsync(stage, e->d_stage.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
     else CUDA_TRY(cudaMemcpyAsync(stage, e->d_stage.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   }
+  if(cells) CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<int*>(e->h_pinned + 12), e->wc_ctl.p + 2, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if(cells && *reinterpret_cast<int*>(e->h_pinned + 12) != 0)
+  {
+    // a candidate list of the cell-sorted stage did not fit its shared-memory capacity (very dense system or very long cutoff):
+    // nothing of this call is kept, the batch is evaluated again by the warp-per-insertion kernel, and the engine stays with it
+    e->wc_overflowed = true;
+    return gb_widom_batch(e, comp, n, in, out8, stage, outputs_on_device, sums);
+  }
   if(sums) for(size_t i = 0; i < hs.size(); i++) sums[i] = hs[i];
   return GB_OK;
 }

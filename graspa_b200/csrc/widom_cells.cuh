@@ -168,7 +168,7 @@ __host__ __device__ inline size_t wc_energy_smem(int ntypes, bool stage_ff, int 
 }
 
 template <int CELL, bool HAS_GG>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(768, 1)
 k_wc_energy(DevParams P, WcGrid G, WcEnergy A)
 {
   extern __shared__ __align__(16) unsigned char smem[];

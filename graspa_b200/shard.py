@@ -21,6 +21,48 @@ def shard_range(n_total: int, world: int, rank: int):
     return first, count
 
 
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs of a sharded job: a pure function of the GLOBAL insertion index
+# ------------------------------------------------------------------------------------------------
+DOUBLES_PER_INSERTION = 64          # 20 double3 of the random pool (10 positions + 10 orientations), 2 uniforms, 2 spare
+_GAMMA, _M1, _M2 = 0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB
+
+
+def job_uniforms_numpy(first_insertion: int, count: int, seed: int) -> np.ndarray:
+    """(count, 64) uniforms in [0, 1) of insertions [first, first + count) of a job: SplitMix64 of the global element index
+    (counter-based: any rank generates exactly its own range, and the union over ranks is the single-process job)"""
+    idx = (np.arange(first_insertion * DOUBLES_PER_INSERTION, (first_insertion + count) * DOUBLES_PER_INSERTION, dtype=np.uint64) + np.uint64(1))
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + idx * np.uint64(_GAMMA)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(_M1)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(_M2)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)).reshape(count, DOUBLES_PER_INSERTION)
+
+
+def job_uniforms_torch(first_insertion: int, count: int, seed: int, device):
+    """the same numbers generated on `device` with 64-bit integer tensor ops (wrapping multiplies, logical shifts by masking)"""
+    import torch
+
+    def s64(v):
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def lsr(x, k):
+        return (x >> k) & ((1 << (64 - k)) - 1)
+    idx = torch.arange(first_insertion * DOUBLES_PER_INSERTION + 1, (first_insertion + count) * DOUBLES_PER_INSERTION + 1, dtype=torch.int64, device=device)
+    z = idx * s64(_GAMMA) + s64(seed & ((1 << 64) - 1))
+    z = (z ^ lsr(z, 30)) * s64(_M1)
+    z = (z ^ lsr(z, 27)) * s64(_M2)
+    z = z ^ lsr(z, 31)
+    return (lsr(z, 11).to(torch.float64) * (1.0 / 9007199254740992.0)).reshape(count, DOUBLES_PER_INSERTION)
+
+
+def split_job_uniforms(u):
+    """(count, 64) -> random pool (count * 20, 3) in the packed layout of gb_widom_inputs and uniforms (count, 2)"""
+    n = u.shape[0]
+    return u[:, :60].reshape(n * 20, 3), u[:, 60:62]
+
+
 def reduce_block_sums(sums: np.ndarray, device=None):
     """element-wise SUM of the (n_blocks, 12) block sums over all ranks (NCCL when `device` is a CUDA device, gloo on CPU).
     A single-process run returns its input."""

@@ -15,6 +15,14 @@ def _scale(e):
     return np.abs(e).sum(axis=1, keepdims=True) + 1e-3
 
 
+@pytest.fixture(params=["warp", "cells"])
+def widom_path(request, monkeypatch):
+    """both pair stages of gb_widom_batch: the warp-per-insertion kernel (k_widom_pair, small batches) and the cell-sorted one
+    (widom_cells.cuh, batches of >= 16 384 insertions); GB_WIDOM_PATH forces either for any batch size"""
+    monkeypatch.setenv("GB_WIDOM_PATH", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name", CONFIGS)
 def test_trial_energies_vs_golden(gpu_engine_factory, name):
     box, ff, s, z = load_config(name)
@@ -128,7 +136,7 @@ def test_total_vdw_real_vs_oracle(gpu_engine_factory, oracle, name):
 
 
 @pytest.mark.parametrize("name", CONFIGS)
-def test_widom_batch_vs_golden(gpu_engine_factory, name):
+def test_widom_batch_vs_golden(gpu_engine_factory, name, widom_path):
     box, ff, s, z = load_config(name)
     comp = int(z["comp"])
     eng = gpu_engine_factory(box, ff, s, float(z["beta"]), int(z["ntrials"]), int(z["norient"]))
@@ -151,7 +159,7 @@ def test_widom_batch_vs_golden(gpu_engine_factory, name):
     eng.close()
 
 
-def test_widom_batch_vs_the_reference_program(gpu_engine_factory):
+def test_widom_batch_vs_the_reference_program(gpu_engine_factory, widom_path):
     """gb_widom_batch against numbers the REFERENCE PROGRAM wrote while it ran (tests/golden/ref_dump_widom_A.npz: the first 150
     Widom insertions of Examples/Henrys_coefficient, seed 0, from the instrumented reference CUDA build): same pool randoms and
     uniforms in, final Rosenbluth weight within 1e-9 relative and every energy term out."""
@@ -173,7 +181,7 @@ def test_widom_batch_vs_the_reference_program(gpu_engine_factory):
     eng.close()
 
 
-def test_widom_batch_vs_oracle_larger_with_failures(gpu_engine_factory, oracle):
+def test_widom_batch_vs_oracle_larger_with_failures(gpu_engine_factory, oracle, widom_path):
     """1024 insertions in config A with OverlapCriteria lowered so that first beads and chains fail:
     identical stage codes, W within 1e-9, and explicit pool indices (the RNG-exact replay layout)."""
     box, ff, s, z = load_config("A")
@@ -204,7 +212,7 @@ def test_widom_batch_vs_oracle_larger_with_failures(gpu_engine_factory, oracle):
     eng.close()
 
 
-def test_widom_properties_full_size(gpu_engine_factory):
+def test_widom_properties_full_size(gpu_engine_factory, widom_path):
     """size-independent properties at the benchmark shape (config E): determinism, batch-split additivity,
     block sums consistent with per-insertion outputs, W >= 0 and stage/W consistency"""
     box, ff, s, z = load_config("E")
@@ -225,7 +233,7 @@ def test_widom_properties_full_size(gpu_engine_factory):
     eng.close()
 
 
-def test_widom_shards_bin_on_the_global_index(gpu_engine_factory):
+def test_widom_shards_bin_on_the_global_index(gpu_engine_factory, widom_path):
     """a job cut into contiguous index ranges (gb_widom_inputs.global_first/global_n) gives, after summing the
     per-shard block sums (what the NCCL all-reduce does), the single-call sums: counts exactly, sums to association."""
     from graspa_b200.shard import shard_range
@@ -287,7 +295,7 @@ def _as_1264(ff, seed=3):
 
 
 @pytest.mark.parametrize("name", ["A", "B"])
-def test_polynomial_1264_potential_vs_oracle(gpu_engine_factory, oracle, name):
+def test_polynomial_1264_potential_vs_oracle(gpu_engine_factory, oracle, name, widom_path):
     """UseLJ1264: U = C12/r^12 - C6/r^6 + C10/r^10 + C4/r^4 - shift (VDW, maths.cuh:452-476) through trial energies,
     whole-system totals and a Widom batch"""
     box, ff0, s, z = load_config(name)
@@ -357,7 +365,7 @@ def test_widom_fourier_row_walk_equals_the_flat_loop(gpu_engine_factory, oracle)
         eng.close()
 
 
-def test_widom_host_batches_are_pipelined_without_changing_results(gpu_engine_factory):
+def test_widom_host_batches_are_pipelined_without_changing_results(gpu_engine_factory, widom_path):
     """Host-input batches of >= 65 536 insertions go up in chunks on a copy stream while the pair kernel already runs on what has
     arrived (gb_widom_batch); per-insertion results, stage codes and block sums are bitwise those of the single-copy path
     (GB_WIDOM_NO_OVERLAP=1) and of other chunk counts (ragged chunk boundaries included)."""
@@ -377,4 +385,67 @@ def test_widom_host_batches_are_pipelined_without_changing_results(gpu_engine_fa
             del os.environ[key]
         assert np.array_equal(o2, out) and np.array_equal(s2, stage) and np.array_equal(m2, sums), (key, val)
     assert (stage == 0).sum() > n // 2 and sums[:, 2].sum() == n
+    eng.close()
+
+
+def test_widom_paths_agree_and_large_batches_take_the_cell_sorted_stage(gpu_engine_factory, monkeypatch):
+    """the two pair stages give the same insertions (energies to summation order, identical stage codes), with adsorbates present
+    (config B: guest-guest terms) and without (E); an unforced batch of 20 000 takes the cell-sorted stage"""
+    for name in ("E", "B", "C"):
+        box, ff, s, z = load_config(name)
+        comp = int(z["comp"]); n = 20000 if name == "E" else 3000
+        rng = np.random.default_rng(77)
+        rnd = rng.random((n * 20, 3)); uni = rng.random((n, 2))
+        eng = gpu_engine_factory(box, ff, s, float(z["beta"]), 10, 10)
+        eng.upload_structure_factors(z["sf_ads"], z["sf_fw"]); eng.set_exclusion_constants(comp, float(z["excl"][0]), float(z["excl"][1]))
+        res = {}
+        for path in ("warp", "cells"):
+            monkeypatch.setenv("GB_WIDOM_PATH", path)
+            res[path] = eng.widom_batch(comp, rnd, uni)
+        monkeypatch.delenv("GB_WIDOM_PATH")
+        (ow, sw, mw), (oc, sc, mc) = res["warp"], res["cells"]
+        assert np.array_equal(sw, sc)
+        ok = sw == 0
+        assert ok.sum() > n // 4
+        assert rel_err(oc[ok][:, 0], ow[ok][:, 0], floor=1e-290) < 1e-10
+        esc = np.abs(ow[:, 1:]).sum(axis=1, keepdims=True) + 1e-3
+        assert np.max(np.abs(oc[:, 1:] - ow[:, 1:]) / esc) < 1e-11
+        assert not np.array_equal(oc[ok][:, 1:5], ow[ok][:, 1:5])                    # two different summation orders really ran
+        if name == "E":
+            o3, s3, m3 = eng.widom_batch(comp, rnd, uni)                              # unforced: n >= 16 384
+            assert np.array_equal(o3, oc) and np.array_equal(m3, mc)
+        eng.close()
+
+
+def test_widom_batch_honours_block_pockets(gpu_engine_factory):
+    """Config C with its block pockets: the batched path applies the first-bead rule (a blocked starting bead flags every trial,
+    mc_widom.h:463-498) and the grown-molecule rule (mc_swap_utilities.h:46-80) like gb_move_insertion, which
+    test_block_pockets_in_the_move_kernels pins to the oracle; same pool blocks and uniforms through both"""
+    box, ff, s, z = load_config("C")
+    comp = int(z["comp"]); n = 400; beta = float(z["beta"])
+    # the deck's 8 pockets plus wide ones so that a good share of the insertions is touched by the rule
+    rng = np.random.default_rng(91)
+    L = np.array([box.cell[0], box.cell[4], box.cell[8]])
+    centers = np.concatenate([z["pocket_centers"], rng.random((24, 3)) * L]); radii = np.concatenate([z["pocket_radii"], np.full(24, 3.5)])
+    eng = gpu_engine_factory(box, ff, s, beta, 10, 10)
+    eng.upload_structure_factors(z["sf_ads"], z["sf_fw"]); eng.set_exclusion_constants(comp, float(z["excl"][0]), float(z["excl"][1]))
+    rnd = rng.random((n * 20, 3)); uni = rng.random((n, 2))
+    eng.set_block_pockets(comp, centers, radii, invert=bool(z["pocket_invert"]))
+    out, stage, sums = eng.widom_batch(comp, rnd, uni)
+    eng.set_block_pockets(comp, np.zeros((0, 3)), np.zeros(0))
+    out_free, stage_free, _ = eng.widom_batch(comp, rnd, uni)
+    assert (stage != stage_free).sum() > 10                                          # the pockets really change outcomes
+    eng.set_block_pockets(comp, centers, radii, invert=bool(z["pocket_invert"]))
+    eng.upload_random_pool(rnd)
+    tail = eng.tail_difference(comp, INSERTION)
+    nfail = 0
+    for i in range(n):
+        m = eng.move_insertion(comp, 20 * i, uni[i])
+        if not m["success"]:
+            nfail += 1
+            assert stage[i] != 0 and out[i, 0] == 0.0, (i, stage[i])
+            continue
+        W = m["first_bead"]["rosenbluth"] * m["chain"]["rosenbluth"] * np.exp(-beta * (m["ewald"][0] + m["ewald"][1])) * np.exp(-beta * tail)
+        assert stage[i] == 0 and abs(out[i, 0] - W) <= 1e-9 * W, (i, out[i, 0], W)
+    assert nfail > 10 and nfail < n
     eng.close()
