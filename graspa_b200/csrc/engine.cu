@@ -126,7 +126,7 @@ struct gb_engine
 
   long long launches = 0;
   bool timing = false;
-  double ms_pair = 0.0, ms_ewald = 0.0; long long n_pair = 0, n_ewald = 0;
+  double ms_pair = 0.0, ms_ewald = 0.0, ms_wc = 0.0; long long n_pair = 0, n_ewald = 0, n_wc = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -348,6 +348,12 @@ __global__ void k_build_ktab(const double* __restrict__ temp, const int* __restr
   }
 }
 
+__global__ void k_add_sums(const double* __restrict__ src, double* dst, int n)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if(k < n) dst[k] += src[k];
+}
+
 // the same gathered in row order: 5 arrays of npos [temp | sa.re | sa.im | sf.re | sf.im]; unused positions carry temp = 0
 __global__ void k_build_rtab(const double* __restrict__ temp, const int* __restrict__ slot, const int* __restrict__ rowidx,
                              const double* __restrict__ sa, const double* __restrict__ sf, int npos, double* rtab)
@@ -443,18 +449,25 @@ std::vector<int> species_counts(gb_engine* e, int comp)
   return c;
 }
 
+// CUDA-event timing of a group of launches on the engine's stream (only when gb_timing_enable is on).  Families: 0 the pair stage of
+// the batched Widom path and the stage-call pair kernels, 1 the Fourier kernels, 3 the k_wc_energy launches alone (nested inside 0).
+// Each timer owns its events, so timers may nest.
 struct Timer
 {
-  gb_engine* e; int fam; bool on;
-  Timer(gb_engine* e_, int fam_) : e(e_), fam(fam_), on(e_->timing) { if(on) cudaEventRecord(e->ev0, e->stream); }
+  gb_engine* e; int fam; bool on; cudaEvent_t a = nullptr, b = nullptr;
+  Timer(gb_engine* e_, int fam_) : e(e_), fam(fam_), on(e_->timing)
+  {
+    if(on) { on = cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess; if(on) cudaEventRecord(a, e->stream); }
+  }
   void stop(long long launches)
   {
     if(!on) return;
-    cudaEventRecord(e->ev1, e->stream); cudaEventSynchronize(e->ev1);
-    float ms = 0.f; cudaEventElapsedTime(&ms, e->ev0, e->ev1);
-    if(fam == 0) { e->ms_pair += ms; e->n_pair += launches; } else { e->ms_ewald += ms; e->n_ewald += launches; }
+    cudaEventRecord(b, e->stream); cudaEventSynchronize(b);
+    float ms = 0.f; cudaEventElapsedTime(&ms, a, b);
+    if(fam == 0) { e->ms_pair += ms; e->n_pair += launches; } else if(fam == 1) { e->ms_ewald += ms; e->n_ewald += launches; } else { e->ms_wc += ms; e->n_wc += launches; }
     on = false;
   }
+  ~Timer() { if(a) cudaEventDestroy(a); if(b) cudaEventDestroy(b); }
 };
 
 } // namespace
@@ -509,6 +522,12 @@ static int engine_init(gb_engine* e, int device)
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_move));
     CUDA_TRY(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, GBF_MAX_DYN_SMEM));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_ewald_delta));
@@ -1345,7 +1364,7 @@ static int widom_cells_grid(gb_engine* e, WcGrid& G)
       G.n[k] = std::max(1, (int) std::lround(len / h));
       nc *= G.n[k];
     }
-    if(nc <= 32768) { G.ncells = (int) nc; break; }
+    if(nc <= 131072) { G.ncells = (int) nc; break; }
     h *= 1.1;
   }
   G.rcell = 0.0;
@@ -1383,12 +1402,21 @@ static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double
     e->launches++;
     CUDA_TRY(cudaGetLastError());
   }
-  // ---- capacities and shared memory of the energy kernel
+  // ---- launch shape, capacities and shared memory of the energy kernel
+  // mode 1 (default): a lane per trial atom, several small CTAs per SM, each with the lists of its own cell;
+  // mode 0: a warp per trial atom, one large CTA per SM
+  int mode = 1, ctas = 3, thrE = 256;
+  if(const char* env = std::getenv("GB_WC_MODE")) mode = std::atoi(env) ? 1 : 0;
+  if(mode == 0) { ctas = 1; thrE = 768; }
+  if(const char* env = std::getenv("GB_WC_CTAS")) ctas = std::max(1, std::min(mode ? 6 : 1, std::atoi(env)));
+  if(const char* env = std::getenv("GB_WC_THREADS")) thrE = std::min(mode ? 256 : 768, std::max(64, std::atoi(env) / 32 * 32));
   const bool stage_ff = e->ntypes <= 24;
-  G.cap_fast = std::min(std::max(ntot, 32), 2304); G.cap_slow = std::min(std::max(ntot, 32), 768);
-  while(wc_energy_smem(e->ntypes, stage_ff, G.cap_fast, G.cap_slow) > e->smem_optin && G.cap_fast > 256) { G.cap_fast -= 128; G.cap_slow = std::max(128, G.cap_slow - 32); }
+  const size_t budget = std::min(e->smem_optin, (size_t) (e->prop.sharedMemPerMultiprocessor / ctas) - 1024 - 128);
+  G.cap_fast = std::min((std::max(ntot, 32) + 1) & ~1, 2304); G.cap_slow = std::min((std::max(ntot, 32) + 1) & ~1, 768);
+  while(wc_energy_smem(e->ntypes, stage_ff, G.cap_fast, G.cap_slow) > budget && G.cap_fast > 256) { G.cap_fast -= 64; G.cap_slow = std::max(128, G.cap_slow - 16); }
   const size_t smemE = wc_energy_smem(e->ntypes, stage_ff, G.cap_fast, G.cap_slow);
   if(smemE > e->smem_optin) return fail(GB_ERR_ARG, "cell-sorted Widom stage: shared memory exceeds the device limit");
+  if(mode == 1 && !std::getenv("GB_WC_CHUNK")) G.chunk = 32 * (thrE / 32) * 4;
   // ---- buffers
   const long long nfb = n * e->ntrials, nch = n * (long long) e->norient * cs, nmax = std::max(nfb, nch);
   CUDA_TRY(e->wc_ucell.reserve((size_t) nmax)); CUDA_TRY(e->wc_udelta.reserve((size_t) nmax * 3)); CUDA_TRY(e->wc_srec.reserve((size_t) nmax));
@@ -1400,18 +1428,23 @@ static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double
   E.srec = e->wc_srec.p; E.items = e->wc_items.p; E.ctl = e->wc_ctl.p;
   E.tq = e->dq.p + C.offset; E.tscoul = e->dscoul.p + C.offset; E.ttype = e->dtype.p + C.offset; E.ms = ms;
   E.stage_ff = stage_ff ? 1 : 0; E.e4 = e->wc_e4.p; E.flag = e->wc_flag.p; E.overflow = e->wc_ctl.p + 2;
-  const int gridE = e->prop.multiProcessorCount;
-  int thrE = 512;
-  if(const char* env = std::getenv("GB_WC_THREADS")) thrE = std::min(768, std::max(64, std::atoi(env) / 32 * 32));
+  const int gridE = e->prop.multiProcessorCount * ctas;
   auto sort_and_energy = [&](long long nitems_src, int amod, int abase) -> int
   {
     k_wc_scan<<<1, 1024, 0, e->stream>>>(e->wc_count.p, G.ncells, G.chunk, e->wc_off.p, e->wc_cursor.p, e->wc_items.p, e->wc_ctl.p);
     k_wc_scatter<<<(unsigned) ((nitems_src + 255) / 256), 256, 0, e->stream>>>(e->wc_ucell.p, e->wc_udelta.p, nitems_src, e->wc_off.p, e->wc_cursor.p, e->wc_srec.p);
     E.amod = amod; E.abase = abase;
     const bool gg = nads > 0;
-    if(e->P.cell_mode == 2)      { if(gg) k_wc_energy<2, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else k_wc_energy<2, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); }
-    else if(e->P.cell_mode == 1) { if(gg) k_wc_energy<1, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else k_wc_energy<1, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); }
-    else                         { if(gg) k_wc_energy<0, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else k_wc_energy<0, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); }
+#define GBK_WC_LAUNCH(K) do { \
+      if(e->P.cell_mode == 2)      { if(gg) K<2, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<2, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } \
+      else if(e->P.cell_mode == 1) { if(gg) K<1, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<1, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } \
+      else                         { if(gg) K<0, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<0, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } } while(0)
+    {
+      Timer te(e, 3);
+      if(mode == 1) GBK_WC_LAUNCH(k_wc_energy_lt); else GBK_WC_LAUNCH(k_wc_energy);
+      te.stop(1);
+    }
+#undef GBK_WC_LAUNCH
     e->launches += 3;
     CUDA_TRY(cudaGetLastError());
     return GB_OK;
@@ -1488,6 +1521,10 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   if(ms > GBK_EW_MAX_ATOMS) return fail(GB_ERR_ARG, "molecule too large for the Ewald stage");
   const int nbins = in->n_blocks > 0 ? in->n_blocks : 1;
   const int per = e->ntrials + e->norient;
+  // tail-correction difference of one more molecule: constant over the batch, a function of the occupation numbers only, evaluated
+  // once per state (memoised) and BEFORE anything of the batch is queued, so that no synchronisation falls between the stages
+  double tail_value = 0.0;
+  if(e->has_tail) { std::vector<int> dc = species_counts(e, comp); rc = tail_delta_memo(e, dc, &tail_value); if(rc) return rc; }
 
   // ---- inputs on the device
   const double* d_pool = in->pool3; const long long* d_fb = (const long long*) in->fb_index; const long long* d_or = (const long long*) in->or_index;
@@ -1545,11 +1582,6 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
 
   // ---- stage A
   if(nchunk == 1) { rc = widom_stage_a(e, comp, n, d_pool, d_fb, d_or, d_uni, 0); if(rc) return rc; }
-  // ---- tail (constant over the batch)
-  std::vector<int> dc = species_counts(e, comp);
-  rc = tail_device(e, &dc, e->d_result.p + 8); if(rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(e->h_pinned + 8, e->d_result.p + 8, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
   // ---- stage B
   rc = ensure_ktab(e); if(rc) return rc;
   const int warpsB = GBK_EWALD_THREADS / 32;
@@ -1558,7 +1590,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   B.ktab = e->d_ktab.p; B.nact = e->nact; B.nact_pad = e->nact_pad; B.do_ewald = do_ewald ? 1 : 0;
   B.rtab = e->d_rtab.p; B.npos = e->npos; B.rowmeta = e->d_rowmeta.p; B.rounds = e->d_round.p; B.nrounds = (e->npos > 0 && C.molsize <= 4 && !std::getenv("GB_EWALD_FLAT")) ? e->nrounds : 0;      // GB_EWALD_FLAT: the one-k-per-lane loop, for A/B timing
   B.excl_const = C.rigid ? (C.excl_intra + C.excl_atom) * 1.0 : 0.0;
-  B.tail = e->h_pinned[8]; B.nbins = nbins;
+  B.tail = tail_value; B.nbins = nbins;
   B.gn = in->global_n > 0 ? in->global_n : n; B.gfirst = in->global_n > 0 ? in->global_first : 0;
   if(B.gfirst < 0 || B.gfirst + n > B.gn) return fail(GB_ERR_ARG, "shard [global_first, global_first + n) outside the job");
   const size_t per_warpB = ((size_t) ms * (e->P.kmax[0] + e->P.kmax[1] + e->P.kmax[2] + 3) * sizeof(cplx) + (size_t) ms * 4 * sizeof(double) + 15) / 16 * 16;
@@ -1584,12 +1616,15 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
     k_widom_ewald<<<gridB, warpsB * 32, smemB, e->stream>>>(e->P, B);
     k_reduce_partials<<<(nbins * 12 + 63) / 64, 64, 0, e->stream>>>(e->d_partial.p, gridB, nbins * 12, e->d_sums.p);
     e->launches += 2;
+    if(in->sums_device) { k_add_sums<<<(nbins * 12 + 63) / 64, 64, 0, e->stream>>>(e->d_sums.p, in->sums_device, nbins * 12); e->launches++; }
     CUDA_TRY(cudaGetLastError());
     tm.stop(2);
   }
   // ---- outputs
-  std::vector<double> hs((size_t) nbins * 12);
-  CUDA_TRY(cudaMemcpyAsync(hs.data(), e->d_sums.p, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  // the block sums come back through the engine's pinned block (h_pinned + 64 .. : 5 x 12 doubles fit; more bins go through a vector)
+  std::vector<double> hs_big; double* hs = e->h_pinned + 64;
+  if((size_t) nbins * 12 > 400) { hs_big.resize((size_t) nbins * 12); hs = hs_big.data(); }
+  if(sums) CUDA_TRY(cudaMemcpyAsync(hs, e->d_sums.p, (size_t) nbins * 12 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   if(out8 && !outputs_on_device) CUDA_TRY(cudaMemcpyAsync(out8, e->d_out8.p, (size_t) n * 8 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   if(stage)
   {
@@ -1605,7 +1640,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
     e->wc_overflowed = true;
     return gb_widom_batch(e, comp, n, in, out8, stage, outputs_on_device, sums);
   }
-  if(sums) for(size_t i = 0; i < hs.size(); i++) sums[i] = hs[i];
+  if(sums) for(size_t i = 0; i < (size_t) nbins * 12; i++) sums[i] = hs[i];
   return GB_OK;
 }
 
@@ -1623,11 +1658,11 @@ int gb_timing_enable(gb_engine* e, int32_t on) { if(!e) return fail(GB_ERR_ARG, 
 int gb_timing_read(gb_engine* e, int32_t family, double* ms, int64_t* launches, int32_t reset)
 {
   if(!e) return fail(GB_ERR_ARG, "null engine");
-  double m = family == 0 ? e->ms_pair : (family == 1 ? e->ms_ewald : e->ms_pair + e->ms_ewald);
-  long long l = family == 0 ? e->n_pair : (family == 1 ? e->n_ewald : e->n_pair + e->n_ewald);
+  double m = family == 0 ? e->ms_pair : (family == 1 ? e->ms_ewald : (family == 3 ? e->ms_wc : e->ms_pair + e->ms_ewald));
+  long long l = family == 0 ? e->n_pair : (family == 1 ? e->n_ewald : (family == 3 ? e->n_wc : e->n_pair + e->n_ewald));
   if(ms) *ms = m;
   if(launches) *launches = l;
-  if(reset) { e->ms_pair = e->ms_ewald = 0.0; e->n_pair = e->n_ewald = 0; }
+  if(reset) { e->ms_pair = e->ms_ewald = e->ms_wc = 0.0; e->n_pair = e->n_ewald = e->n_wc = 0; }
   return GB_OK;
 }
 

@@ -167,9 +167,11 @@ __host__ __device__ inline size_t wc_energy_smem(int ntypes, bool stage_ff, int 
   return (b + 15) / 16 * 16;
 }
 
-template <int CELL, bool HAS_GG>
-__global__ void __launch_bounds__(768, 1)
-k_wc_energy(DevParams P, WcGrid G, WcEnergy A)
+// MODE 0: a warp per trial atom, lanes over the candidates (warp reduction at the end).
+// MODE 1: a lane per trial atom, the warp walks the candidates in lockstep: every candidate load is a shared-memory BROADCAST
+//         (one wavefront for 32 pairs, two candidates per 16-byte load) and nothing is reduced across lanes.
+template <int CELL, bool HAS_GG, int MODE>
+__device__ __forceinline__ void wc_energy_body(const DevParams& P, const WcGrid& G, const WcEnergy& A)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   double* etab = reinterpret_cast<double*>(smem + GBK_SMEM_TABLES_OFF);
@@ -265,60 +267,139 @@ k_wc_energy(DevParams P, WcGrid G, WcEnergy A)
       if(threadIdx.x == 0) *A.overflow = 1;
       nfast = min(nfast, CF); nslow = min(nslow, CS);
     }
-    // ---- one warp per trial atom of the item
-    for(int t = warp; t < cnt; t += nwarps)
+    if(MODE == 1)
     {
-      const double4 rec = A.srec[first + t];
-      const long long id = __double_as_longlong(rec.w);
-      const int a = A.abase + (int) (id % A.amod);
-      const int ttype = Ttype[a]; const double tq = Tq[a];
-      double ev0 = 0.0, er0 = 0.0, ev1 = 0.0, er1 = 0.0; int fl = 0;
-#pragma unroll 2
-      for(int j = lane; j < nfast; j += 32)
+      // pad both lists to an even length with a candidate that is never inside the cutoff: the loops take two per step
+      if(threadIdx.x == 0)
       {
-        const double dx = Fx[j] - rec.x, dy = Fy[j] - rec.y, dz = Fz[j] - rec.z;
-        const double r2 = dx * dx + dy * dy + dz * dz;
-        if(r2 < cut_max)
-        {
-          const int tk = Ftk[j];
-          double ev, er; int f;
-          pair_energy(P, etab, ffp, true, r2, (tk & 0xffff) * P.ntypes + ttype, 1.0, Fq[j] * tq, ev, er, f);
-          if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
-          else { ev0 += ev; er0 += er; }
-          fl |= f;
-        }
+        if(nfast & 1) { Fx[nfast] = 1e30; Fy[nfast] = 1e30; Fz[nfast] = 1e30; Fq[nfast] = 0.0; Ftk[nfast] = 0; }
       }
-      if(nslow > 0)
+      __syncthreads();
+      const int nf2 = (nfast + 1) & ~1;
+      for(int t0 = warp * 32; t0 < cnt; t0 += nwarps * 32)
       {
-        // fractional offset of the trial from the cell centre: the general wrap (CellRegs::r2) for the atoms near a half-box plane
-        double ox, oy, oz; to_frac(P, rec.x, rec.y, rec.z, ox, oy, oz);
-        for(int j = lane; j < nslow; j += 32)
+        const int t = t0 + lane;
+        const bool valid = t < cnt;
+        const double4 rec = A.srec[first + (valid ? t : cnt - 1)];
+        const long long id = __double_as_longlong(rec.w);
+        const int a = A.abase + (int) (id % A.amod);
+        const int ttype = Ttype[a]; const double tq = Tq[a];
+        double ev0 = 0.0, er0 = 0.0, ev1 = 0.0, er1 = 0.0; int fl = 0;
+        for(int j = 0; j < nf2; j += 2)
         {
-          const double r2 = C.r2(Sx[j] - ox, Sy[j] - oy, Sz[j] - oz);
-          if(r2 < cut_max)
+          const double2 X = *reinterpret_cast<const double2*>(Fx + j), Y = *reinterpret_cast<const double2*>(Fy + j), Z = *reinterpret_cast<const double2*>(Fz + j);
+          const double ax = X.x - rec.x, ay = Y.x - rec.y, az = Z.x - rec.z;
+          const double bx = X.y - rec.x, by = Y.y - rec.y, bz = Z.y - rec.z;
+          const double ra = ax * ax + ay * ay + az * az, rb = bx * bx + by * by + bz * bz;
+          if(ra < cut_max)
           {
-            const int tk = Stk[j];
+            const int tk = Ftk[j];
             double ev, er; int f;
-            pair_energy(P, etab, ffp, true, r2, (tk & 0xffff) * P.ntypes + ttype, 1.0, Sq[j] * tq, ev, er, f);
+            pair_energy(P, etab, ffp, true, ra, (tk & 0xffff) * P.ntypes + ttype, 1.0, Fq[j] * tq, ev, er, f);
+            if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
+            else { ev0 += ev; er0 += er; }
+            fl |= f;
+          }
+          if(rb < cut_max)
+          {
+            const int tk = Ftk[j + 1];
+            double ev, er; int f;
+            pair_energy(P, etab, ffp, true, rb, (tk & 0xffff) * P.ntypes + ttype, 1.0, Fq[j + 1] * tq, ev, er, f);
             if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
             else { ev0 += ev; er0 += er; }
             fl |= f;
           }
         }
-      }
-      ev0 = warp_sum(ev0); er0 = warp_sum(er0);
-      if(HAS_GG) { ev1 = warp_sum(ev1); er1 = warp_sum(er1); }
-      fl = __any_sync(0xffffffffu, fl) ? 1 : 0;
-      if(lane == 0)
-      {
-        double4* o = reinterpret_cast<double4*>(A.e4 + 4 * id);
-        *o = make_double4(ev0, er0, ev1, er1);
-        A.flag[id] = fl;
+        if(nslow > 0)
+        {
+          double ox, oy, oz; to_frac(P, rec.x, rec.y, rec.z, ox, oy, oz);
+          for(int j = 0; j < nslow; j++)
+          {
+            const double r2 = C.r2(Sx[j] - ox, Sy[j] - oy, Sz[j] - oz);
+            if(r2 < cut_max)
+            {
+              const int tk = Stk[j];
+              double ev, er; int f;
+              pair_energy(P, etab, ffp, true, r2, (tk & 0xffff) * P.ntypes + ttype, 1.0, Sq[j] * tq, ev, er, f);
+              if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
+              else { ev0 += ev; er0 += er; }
+              fl |= f;
+            }
+          }
+        }
+        if(valid)
+        {
+          double4* o = reinterpret_cast<double4*>(A.e4 + 4 * id);
+          *o = make_double4(ev0, er0, ev1, er1);
+          A.flag[id] = fl;
+        }
       }
     }
+    else
+    {
+  // ---- one warp per trial atom of the item
+      for(int t = warp; t < cnt; t += nwarps)
+      {
+        const double4 rec = A.srec[first + t];
+        const long long id = __double_as_longlong(rec.w);
+        const int a = A.abase + (int) (id % A.amod);
+        const int ttype = Ttype[a]; const double tq = Tq[a];
+        double ev0 = 0.0, er0 = 0.0, ev1 = 0.0, er1 = 0.0; int fl = 0;
+#pragma unroll 2
+        for(int j = lane; j < nfast; j += 32)
+        {
+          const double dx = Fx[j] - rec.x, dy = Fy[j] - rec.y, dz = Fz[j] - rec.z;
+          const double r2 = dx * dx + dy * dy + dz * dz;
+          if(r2 < cut_max)
+          {
+            const int tk = Ftk[j];
+            double ev, er; int f;
+            pair_energy(P, etab, ffp, true, r2, (tk & 0xffff) * P.ntypes + ttype, 1.0, Fq[j] * tq, ev, er, f);
+            if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
+            else { ev0 += ev; er0 += er; }
+            fl |= f;
+          }
+        }
+        if(nslow > 0)
+        {
+          // fractional offset of the trial from the cell centre: the general wrap (CellRegs::r2) for the atoms near a half-box plane
+          double ox, oy, oz; to_frac(P, rec.x, rec.y, rec.z, ox, oy, oz);
+          for(int j = lane; j < nslow; j += 32)
+          {
+            const double r2 = C.r2(Sx[j] - ox, Sy[j] - oy, Sz[j] - oz);
+            if(r2 < cut_max)
+            {
+              const int tk = Stk[j];
+              double ev, er; int f;
+              pair_energy(P, etab, ffp, true, r2, (tk & 0xffff) * P.ntypes + ttype, 1.0, Sq[j] * tq, ev, er, f);
+              if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
+              else { ev0 += ev; er0 += er; }
+              fl |= f;
+            }
+          }
+        }
+        ev0 = warp_sum(ev0); er0 = warp_sum(er0);
+        if(HAS_GG) { ev1 = warp_sum(ev1); er1 = warp_sum(er1); }
+        fl = __any_sync(0xffffffffu, fl) ? 1 : 0;
+        if(lane == 0)
+        {
+          double4* o = reinterpret_cast<double4*>(A.e4 + 4 * id);
+          *o = make_double4(ev0, er0, ev1, er1);
+          A.flag[id] = fl;
+        }
+      }
+}
     __syncthreads();          // the lists are rebuilt by the next item
   }
 }
+
+template <int CELL, bool HAS_GG>
+__global__ void __launch_bounds__(768, 1)
+k_wc_energy(DevParams P, WcGrid G, WcEnergy A) { wc_energy_body<CELL, HAS_GG, 0>(P, G, A); }
+
+template <int CELL, bool HAS_GG>
+__global__ void __launch_bounds__(256, 3)
+k_wc_energy_lt(DevParams P, WcGrid G, WcEnergy A) { wc_energy_body<CELL, HAS_GG, 1>(P, G, A); }
 
 // ---------------------------------------------------------------------------------------------- selection stages
 struct WcSel

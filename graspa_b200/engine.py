@@ -88,7 +88,7 @@ class GbMoveResult(C.Structure):
 class GbWidomInputs(C.Structure):
     _fields_ = [("pool3", C.c_void_p), ("n_pool", C.c_int64), ("fb_index", C.c_void_p), ("or_index", C.c_void_p),
                 ("uniforms", C.c_void_p), ("inputs_on_device", C.c_int32), ("n_blocks", C.c_int32),
-                ("global_first", C.c_int64), ("global_n", C.c_int64)]
+                ("global_first", C.c_int64), ("global_n", C.c_int64), ("sums_device", C.c_void_p)]
 
 
 class EngineError(RuntimeError):
@@ -387,7 +387,7 @@ class Engine:
         n = C.c_int64(); self._chk(self.lib.gb_number_of_molecules(self.h, C.c_int32(comp), C.byref(n))); return n.value
 
     # ------------------------------------------------------------ batched Widom
-    def widom_batch(self, comp, rnd, uni, fb_index=None, or_index=None, n_blocks=5, want_outputs=True, shard=(0, 0)):
+    def widom_batch(self, comp, rnd, uni, fb_index=None, or_index=None, n_blocks=5, want_outputs=True, shard=(0, 0), d_sums=None):
         """rnd: (n_pool, 3) double3 pool (host); uni: (n, 2).  Packed layout unless indices are given.
         Returns (out8 (n,8) or None, stage (n,) or None, sums (n_blocks, 12))."""
         rnd = np.ascontiguousarray(rnd, dtype=np.float64).reshape(-1, 3)
@@ -396,7 +396,7 @@ class Engine:
         fb = np.ascontiguousarray(fb_index, dtype=np.int64) if fb_index is not None else None
         orr = np.ascontiguousarray(or_index, dtype=np.int64) if or_index is not None else None
         inp = GbWidomInputs(rnd.ctypes.data, rnd.shape[0], fb.ctypes.data if fb is not None else None,
-                            orr.ctypes.data if orr is not None else None, uni.ctypes.data, 0, n_blocks, int(shard[0]), int(shard[1]))
+                            orr.ctypes.data if orr is not None else None, uni.ctypes.data, 0, n_blocks, int(shard[0]), int(shard[1]), d_sums)
         out8 = np.zeros((n, 8)) if want_outputs else None
         stage = np.zeros(n, dtype=np.int32) if want_outputs else None
         sums = np.zeros((n_blocks, 12))
@@ -404,10 +404,11 @@ class Engine:
                                           C.c_int32(0), _p(sums, f64p)))
         return out8, stage, sums
 
-    def widom_batch_device(self, comp, n, d_pool, n_pool, d_uni, n_blocks=5, d_out8=None, shard=(0, 0)):
-        """device-resident inputs (raw device pointers as ints, e.g. torch tensor.data_ptr())"""
-        inp = GbWidomInputs(d_pool, n_pool, None, None, d_uni, 1, n_blocks, int(shard[0]), int(shard[1]))
-        sums = np.zeros((n_blocks, 12))
+    def widom_batch_device(self, comp, n, d_pool, n_pool, d_uni, n_blocks=5, d_out8=None, shard=(0, 0), d_sums=None, want_host_sums=True):
+        """device-resident inputs (raw device pointers as ints, e.g. torch tensor.data_ptr()); d_sums: device pointer of n_blocks*12
+        doubles the block sums are ADDED to on the engine's stream (gb_widom_inputs.sums_device)"""
+        inp = GbWidomInputs(d_pool, n_pool, None, None, d_uni, 1, n_blocks, int(shard[0]), int(shard[1]), d_sums)
+        sums = np.zeros((n_blocks, 12)) if want_host_sums else None
         self._chk(self.lib.gb_widom_batch(self.h, C.c_int32(comp), C.c_int64(n), C.byref(inp), C.c_void_p(d_out8) if d_out8 else None,
                                           None, C.c_int32(1), _p(sums, f64p)))
         return sums

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GB_ABI_VERSION 5
+#define GB_ABI_VERSION 6
 
 enum {
   GB_OK = 0,
@@ -337,12 +337,18 @@ typedef struct {
    * job of global_n insertions; bins are assigned on the GLOBAL index so that the all-reduced sums equal the
    * single-GPU ones.  global_n = 0: the call is the whole job. */
   int64_t global_first; int64_t global_n;
+  /* optional DEVICE pointer to n_blocks*12 doubles: the block sums of this call are ADDED to it on the engine's stream.  A job
+   * evaluated in several calls accumulates there, and a multi-GPU run all-reduces from there (NCCL on the same stream, SURVEY
+   * section 5) without staging through the host.  NULL: not used.  (ABI 6) */
+  double* sums_device;
 } gb_widom_inputs;
 
 /* per insertion outputs (any may be NULL): out8[i*8 + {W, HGVDW, HGReal, GGVDW, GGReal, GGEwaldE, HGEwaldE, TailE}],
  * stage[i] (0 ok, 1 first bead failed, 2 chain failed, 3 chain failed with no surviving orientation).
- * sums[(bin)*12 + {sumW, sumW2, count, sum(W*E) for the 7 energy terms, n_failed, reserved}] on the host, reduced on the device
- * (RecordRosen data_struct.h:627-652 and widom_energy += E*W axpy.cu:177-185). */
+ * sums[(bin)*12 + {sumW, sumW2, count, sum(W*E) for the 7 energy terms, n_failed, reserved}] on the host (may be NULL), reduced on
+ * the device (RecordRosen data_struct.h:627-652 and widom_energy += E*W axpy.cu:177-185).
+ * Batches of >= 16 384 insertions (and components with block pockets) take the cell-sorted pair stage, smaller ones the
+ * warp-per-insertion kernel; both give the same insertions to summation order. */
 int  gb_widom_batch(gb_engine* e, int32_t component, int64_t n, const gb_widom_inputs* in,
                     double* out8, int32_t* stage, int32_t outputs_on_device, double* sums);
 
@@ -360,7 +366,9 @@ int  gb_widom_first_bead_success(gb_engine* e, int32_t component, int64_t n, con
 /* kernels launched by this engine since creation / last reset (bench.py's gpu_launches) */
 int  gb_launch_count(gb_engine* e, int64_t* n, int32_t reset);
 /* elapsed device milliseconds of the engine's kernels of one family since last reset, measured with CUDA events
- * on the engine stream: family 0 = pair kernels, 1 = Ewald kernels, 2 = all.  Timing must be enabled first. */
+ * on the engine stream: family 0 = pair kernels (for gb_widom_batch: its whole pair stage), 1 = Ewald kernels, 2 = all,
+ * 3 = the energy kernel of the cell-sorted Widom pair stage alone (its launches are also inside family 0).  Timing must be
+ * enabled first; a timed call synchronises the host after every timed group. */
 int  gb_timing_enable(gb_engine* e, int32_t on);
 int  gb_timing_read(gb_engine* e, int32_t family, double* ms, int64_t* launches, int32_t reset);
 /* FP64 FMA peak microbenchmark on this device: returns TFLOP/s (2 flop per DFMA) */
