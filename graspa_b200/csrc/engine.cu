@@ -15,6 +15,7 @@
 #include <map>
 #include <vector>
 #include <atomic>
+#include <chrono>
 
 namespace {
 
@@ -103,7 +104,8 @@ struct gb_engine
   // cell-sorted Widom pair stage (widom_cells.cuh)
   DevBuf<double> wc_udelta, wc_e4, wc_fbres, wc_afx, wc_afy, wc_afz, wc_aq; DevBuf<double4> wc_srec;
   DevBuf<int> wc_ucell, wc_flag, wc_count, wc_off, wc_cursor, wc_items, wc_ctl, wc_atk;
-  bool wc_overflowed = false;            // a candidate list did not fit once: this engine keeps to k_widom_pair
+  bool wc_overflowed = false;            // a candidate list did not fit even with one CTA per SM: this engine keeps to k_widom_pair
+  int wc_ctas_cap = 8, wc_last_ctas = 1; // CTAs per SM of the energy kernel: lowered (larger lists per CTA) when a list overflowed
   // CBMC
   int ntrials = 10, norient = 10; bool have_cbmc = false;
   DevBuf<double> d_pool; long long n_pool = 0;
@@ -116,6 +118,7 @@ struct gb_engine
   double* h_pinned = nullptr;            // 4 KB pinned result slot
   double* h_results = nullptr;           // 2 KB of h_pinned: tagged result records of k_move
   unsigned long long move_seq = 0;       // sequence number of the last k_move launch (published to h_pinned + 256)
+  bool move_cooperative = true;          // cudaLaunchCooperativeKernel: co-residency of the move kernel's CTAs guaranteed by the driver
 
   // single-move path
   DevBuf<double> d_mv, d_ewpos; DevBuf<int> d_mvi;
@@ -530,6 +533,10 @@ static int engine_init(gb_engine* e, int device)
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_move));
     CUDA_TRY(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, GBF_MAX_DYN_SMEM));
+    {
+      int coop = 0; CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+      e->move_cooperative = coop != 0 && !(std::getenv("GB_MOVE_COOP") && std::atoi(std::getenv("GB_MOVE_COOP")) == 0);     // GB_MOVE_COOP=0: A/B timing only (1 % on the GCMC decks)
+    }
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_ewald_delta));
     CUDA_TRY(cudaFuncSetAttribute(k_ewald_delta, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
     e->smem_optin -= 1024;   // head room for static shared memory of the kernels
@@ -1340,6 +1347,7 @@ static int widom_stage_a(gb_engine* e, int comp, long long n, const double* d_po
 }
 
 // ---- cell-sorted pair stage (widom_cells.cuh): same inputs and the same rec / stage outputs as widom_stage_a
+static int widom_cells_grid(gb_engine* e, WcGrid& G);
 static bool widom_cells_wanted(gb_engine* e, int comp, long long n_total)
 {
   const Comp& C = e->comps[comp];
@@ -1347,7 +1355,10 @@ static bool widom_cells_wanted(gb_engine* e, int comp, long long n_total)
   const char* env = std::getenv("GB_WIDOM_PATH");             // A/B measurements and tests: "cells" / "warp"
   if(env && std::strcmp(env, "cells") == 0) return true;
   if(env && std::strcmp(env, "warp") == 0) return C.npocket > 0;
-  return C.npocket > 0 || n_total >= 16384;                    // below that the per-cell list build is not amortised
+  if(C.npocket > 0) return true;
+  // the per-cell list build is amortised, and the lanes of the lane-per-trial kernel are filled, from ~64 first-bead trials per cell on
+  WcGrid G; widom_cells_grid(e, G);
+  return n_total * (long long) e->ntrials >= 64LL * G.ncells;
 }
 
 static int widom_cells_grid(gb_engine* e, WcGrid& G)
@@ -1405,10 +1416,13 @@ static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double
   // ---- launch shape, capacities and shared memory of the energy kernel
   // mode 1 (default): a lane per trial atom, several small CTAs per SM, each with the lists of its own cell;
   // mode 0: a warp per trial atom, one large CTA per SM
-  int mode = 1, ctas = 3, thrE = 256;
+  int mode = 1, ctas = 4, thrE = 192;
   if(const char* env = std::getenv("GB_WC_MODE")) mode = std::atoi(env) ? 1 : 0;
   if(mode == 0) { ctas = 1; thrE = 768; }
+  if(mode == 1 && e->wc_ctas_cap < 4) thrE = 256;
   if(const char* env = std::getenv("GB_WC_CTAS")) ctas = std::max(1, std::min(mode ? 6 : 1, std::atoi(env)));
+  ctas = std::max(1, std::min(ctas, e->wc_ctas_cap));
+  e->wc_last_ctas = ctas;
   if(const char* env = std::getenv("GB_WC_THREADS")) thrE = std::min(mode ? 256 : 768, std::max(64, std::atoi(env) / 32 * 32));
   const bool stage_ff = e->ntypes <= 24;
   const size_t budget = std::min(e->smem_optin, (size_t) (e->prop.sharedMemPerMultiprocessor / ctas) - 1024 - 128);
@@ -1635,9 +1649,12 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   if(cells && *reinterpret_cast<int*>(e->h_pinned + 12) != 0)
   {
-    // a candidate list of the cell-sorted stage did not fit its shared-memory capacity (very dense system or very long cutoff):
-    // nothing of this call is kept, the batch is evaluated again by the warp-per-insertion kernel, and the engine stays with it
-    e->wc_overflowed = true;
+    // a candidate list of the cell-sorted stage did not fit its shared-memory capacity (dense system, long cutoff): nothing of this
+    // call is kept; the batch is evaluated again with fewer CTAs per SM (larger lists), in the end by the warp-per-insertion kernel
+    if(e->wc_last_ctas > 1) e->wc_ctas_cap = e->wc_last_ctas - 1;          // fewer CTAs per SM = more shared memory for the lists of each
+    else e->wc_overflowed = true;
+    if(std::getenv("GB_DEBUG")) std::fprintf(stderr, "graspa_b200: cell-sorted Widom stage overflowed its candidate lists (n = %lld, %d CTAs per SM); %s\n", (long long) n,
+                                             e->wc_last_ctas, e->wc_overflowed ? "falling back to k_widom_pair" : "retrying with larger lists");
     return gb_widom_batch(e, comp, n, in, out8, stage, outputs_on_device, sums);
   }
   if(sums) for(size_t i = 0; i < (size_t) nbins * 12; i++) sums[i] = hs[i];

@@ -447,6 +447,9 @@ __device__ __forceinline__ void export_molecule(const FusedArgs& F, const SmemMo
   }
 }
 
+// One kernel for every move kind.  Measured and not kept (profiles/r2_move_kernel.md): one instantiation per kind with the kind as a
+// build-time constant (each carries only its own move's code) -- 10 % SLOWER on all three GCMC decks, because consecutive moves of
+// different kinds then alternate between kernels and every switch starts with cold instruction caches.
 __global__ void __launch_bounds__(256, 1)
 k_move(DevParams P, SysView S, FusedArgs F)
 {
@@ -756,3 +759,4 @@ k_move(DevParams P, SysView S, FusedArgs F)
   }
 #endif
 }
+

@@ -347,8 +347,9 @@ typedef struct {
  * stage[i] (0 ok, 1 first bead failed, 2 chain failed, 3 chain failed with no surviving orientation).
  * sums[(bin)*12 + {sumW, sumW2, count, sum(W*E) for the 7 energy terms, n_failed, reserved}] on the host (may be NULL), reduced on
  * the device (RecordRosen data_struct.h:627-652 and widom_energy += E*W axpy.cu:177-185).
- * Batches of >= 16 384 insertions (and components with block pockets) take the cell-sorted pair stage, smaller ones the
- * warp-per-insertion kernel; both give the same insertions to summation order. */
+ * Batches with >= 64 first-bead trials per 2 A cell of the box (about 70 000 insertions in config E; and every batch of a component
+ * with block pockets) take the cell-sorted pair stage, smaller ones the warp-per-insertion kernel; both give the same insertions
+ * to summation order. */
 int  gb_widom_batch(gb_engine* e, int32_t component, int64_t n, const gb_widom_inputs* in,
                     double* out8, int32_t* stage, int32_t outputs_on_device, double* sums);
 

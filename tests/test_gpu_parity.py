@@ -18,7 +18,7 @@ def _scale(e):
 @pytest.fixture(params=["warp", "cells"])
 def widom_path(request, monkeypatch):
     """both pair stages of gb_widom_batch: the warp-per-insertion kernel (k_widom_pair, small batches) and the cell-sorted one
-    (widom_cells.cuh, batches of >= 16 384 insertions); GB_WIDOM_PATH forces either for any batch size"""
+    (widom_cells.cuh, batches with >= 64 first-bead trials per cell); GB_WIDOM_PATH forces either for any batch size"""
     monkeypatch.setenv("GB_WIDOM_PATH", request.param)
     return request.param
 
@@ -390,10 +390,10 @@ def test_widom_host_batches_are_pipelined_without_changing_results(gpu_engine_fa
 
 def test_widom_paths_agree_and_large_batches_take_the_cell_sorted_stage(gpu_engine_factory, monkeypatch):
     """the two pair stages give the same insertions (energies to summation order, identical stage codes), with adsorbates present
-    (config B: guest-guest terms) and without (E); an unforced batch of 20 000 takes the cell-sorted stage"""
+    (config B: guest-guest terms) and without (E); an unforced batch of 100 000 takes the cell-sorted stage, one of 20 000 does not"""
     for name in ("E", "B", "C"):
         box, ff, s, z = load_config(name)
-        comp = int(z["comp"]); n = 20000 if name == "E" else 3000
+        comp = int(z["comp"]); n = 100000 if name == "E" else 3000
         rng = np.random.default_rng(77)
         rnd = rng.random((n * 20, 3)); uni = rng.random((n, 2))
         eng = gpu_engine_factory(box, ff, s, float(z["beta"]), 10, 10)
@@ -412,8 +412,10 @@ def test_widom_paths_agree_and_large_batches_take_the_cell_sorted_stage(gpu_engi
         assert np.max(np.abs(oc[:, 1:] - ow[:, 1:]) / esc) < 1e-11
         assert not np.array_equal(oc[ok][:, 1:5], ow[ok][:, 1:5])                    # two different summation orders really ran
         if name == "E":
-            o3, s3, m3 = eng.widom_batch(comp, rnd, uni)                              # unforced: n >= 16 384
+            o3, s3, m3 = eng.widom_batch(comp, rnd, uni)                              # unforced: 79 first-bead trials per cell (12 600 cells)
             assert np.array_equal(o3, oc) and np.array_equal(m3, mc)
+            o4, s4, m4 = eng.widom_batch(comp, rnd[:20000 * 20], uni[:20000])         # unforced, 16 per cell: the warp-per-insertion kernel
+            assert np.array_equal(o4, ow[:20000])
         eng.close()
 
 
