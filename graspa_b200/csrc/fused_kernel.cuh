@@ -507,7 +507,8 @@ k_move(DevParams P, SysView S, FusedArgs F)
   }
   else
   {
-    for(int i = threadIdx.x - 32; i < (GBK_ERFC_DEG + 1) * GBK_ERFC_NINT; i += blockDim.x - 32) sm.etab[i] = __ldg(&P.erfc_tab[i]);
+    if(!P.no_charges)          // without charges no pair ever evaluates erfc: one L2 round trip less in the prologue
+      for(int i = threadIdx.x - 32; i < (GBK_ERFC_DEG + 1) * GBK_ERFC_NINT; i += blockDim.x - 32) sm.etab[i] = __ldg(&P.erfc_tab[i]);
     if(threadIdx.x - 32 < 128) sm.res[threadIdx.x - 32] = 0.0;
   }
   __syncthreads();
@@ -530,6 +531,8 @@ k_move(DevParams P, SysView S, FusedArgs F)
     sg[0].type = 0; sg[0].chain = 0; sg[0].n = F.ntrials; sg[0].pool_off = F.pool_off;
     int nsplit = stage_nsplit(F, F.ntrials);
     run_stage(P, S, F, &sm, W, sg, 1, F.ntrials, nsplit, 0);
+    // a single-bead molecule without a Fourier stage has nothing left that depends on the selection: only CTA 0 finishes the move
+    if(ms == 1 && !F.do_ewald && blockIdx.x != 0) return;
     collect_stage(F, &sm, reinterpret_cast<double*>(dyn), F.ntrials, nsplit, 0);
     finish_segment(P, F, &sm, 0, false, F.ntrials, F.u0, 0.0, sm.E, sm.Fl, 0, 1.0);
     adopt_selection(P, F, &sm, 0, false, F.pool_off, 0);
@@ -593,6 +596,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
     const int ngroups = F.ntrials + 1 + no;
     int nsplit = stage_nsplit(F, ngroups);
     run_stage(P, S, F, &sm, W, sg, ms > 1 ? 3 : 2, ngroups, nsplit, 0);
+    if(ms == 1 && !F.do_ewald && blockIdx.x != 0) return;
     collect_stage(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
     if(blockIdx.x == 0)
     {
@@ -653,6 +657,7 @@ k_move(DevParams P, SysView S, FusedArgs F)
     __syncthreads();
     const int nsplit = stage_nsplit(F, ngroups);
     run_stage(P, S, F, &sm, W, sg, ns, ngroups, nsplit, 0);
+    if(ms == 1 && F.ms2 == 1 && !F.do_ewald && blockIdx.x != 0) return;
     collect_stage(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
     finish_segment(P, F, &sm, 4, false, 1, 0.0, 0.0, sm.E, sm.Fl, 0, 1.0);
     if(threadIdx.x == 0 && sm.res[9] != 0.0) { sm.res[6] = sm.mN.a[0][0]; sm.res[7] = sm.mN.a[1][0]; sm.res[8] = sm.mN.a[2][0]; }

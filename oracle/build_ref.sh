@@ -140,4 +140,27 @@ if [ "$WHAT" = "dump" ]; then
   )
   rm -rf "$SCR"
 fi
+if [ "$WHAT" = "overlay" ]; then
+  # the reference's own program with its hot-path call sites bound to graspa_b200's C ABI (oracle/overlay/): scratch copy patched by
+  # overlay_patch.py, compiled with nvcc like the stock build, linked with libgraspa_b200.so (rpath relative to the binary).
+  # Carries the one-line move trace of the `trace` build, so that tests/test_gpu_trace_parity.py can compare it move by move.
+  echo "[build_ref] reference drivers bound to libgraspa_b200.so (sm_100)"
+  SCR="$(mktemp -d /tmp/graspa_ref_overlay.XXXXXX)"
+  cp -r "$REF/src_clean/." "$SCR/"
+  chmod -R u+w "$SCR"
+  sed -i '268s/{OLDComponent, OLDMolInComponent}/{(int) OLDComponent, (int) OLDMolInComponent}/' "$SCR/mc_swap_moves.h"
+  grep -n "SystemComponents.deltaE += DeltaE;" "$SCR/axpy.cu" | head -1 | grep -q "^297:" || { echo "axpy.cu:297 is not the deltaE accumulation any more"; exit 1; }
+  sed -i '297i\  { static FILE* gtf = getenv("GRASPA_TRACE") ? fopen(getenv("GRASPA_TRACE"), "w") : nullptr; if(gtf) fprintf(gtf, "%zu %d %.12e\\n", comp, MoveType, DeltaE.total()); }' "$SCR/axpy.cu"
+  python "$HERE/overlay/overlay_patch.py" "$SCR"
+  FLAGS="-O3 -std=c++20 -arch=sm_100 --expt-relaxed-constexpr -w -Xcompiler -fopenmp -rdc=true -x cu -I$HERE/../include -I$HERE/overlay"
+  ( cd "$SCR"
+    for f in axpy.cu main.cpp read_data.cpp data_struct.cpp VDW_Coulomb.cu; do
+      "$NVCC" $FLAGS -c "$f" -o "${f%.*}.o" &
+    done
+    wait
+    "$NVCC" -arch=sm_100 -rdc=true -Xcompiler -fopenmp main.o read_data.o axpy.o data_struct.o VDW_Coulomb.o -L"$HERE/../graspa_b200" -lgraspa_b200 \
+        -Xlinker -rpath -Xlinker '$ORIGIN/../../graspa_b200' -o "$OUT/graspa_ref_overlay.x"
+  )
+  rm -rf "$SCR"
+fi
 echo "[build_ref] done: $(ls "$OUT")"

@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE / INTEGRATION DEMONSTRATION.  Binds a SCRATCH COPY of the reference's sources (never /root/reference
+itself) to graspa_b200's C ABI: the call sites of SURVEY section 8(b) are redirected to oracle/overlay/graspa_b200_adapter.h, the
+move drivers stay the reference's own code.  oracle/build_ref.sh overlay compiles the result with nvcc and links it with
+libgraspa_b200.so -> oracle/_ref/graspa_ref_overlay.x; tests/test_gpu_trace_parity.py runs it against the stock reference.
+
+What is redirected (file:line of the reference):
+  mc_widom.h:385-507            Widom_Move_FirstBead_PARTIAL  -> gb_cbmc_first_bead
+  mc_widom.h:509-614            Widom_Move_Chain_PARTIAL      -> gb_cbmc_chain
+  Ewald_Energy_Functions.h:438  GPU_EwaldDifference_General   -> gb_ewald_delta
+  Ewald_Energy_Functions.h:423  Update_Vector_Ewald           -> (inside the gb_accept_* calls)
+  mc_single_particle.h:79       get_new_position<<<>>>        -> gb_single_body_propose
+  mc_single_particle.h:174-200  Calculate_Single_Body_Energy_VDWReal<<<>>> + host sum of Blocksum -> gb_single_body_delta
+  mc_utilities.h:294-417        update_translation_position / Update_insertion_data_Parallel / Update_deletion_data_Parallel<<<>>> -> gb_accept_*
+  move_struct.h:271,371         StoreNewLocation_Reinsertion / Update_Reinsertion_data<<<>>> -> gb_reinsertion_store / gb_accept_reinsertion
+  data_struct.h:1300-1320       RandomNumber::ResetRandom     -> + gb_upload_random_pool
+  data_struct.cpp:6-11          Get_Uniform_Random            -> + Peek_Uniform_Random (one value of look-ahead)
+  main.cpp:427                  before the FINAL energy check -> engine state copied back into Sims.d_a (the reference's own CPU + GPU
+                                                                 total-energy routines then judge the run: ENERGY DRIFT)
+  axpy.cu:297                   the one-line move trace of `build_ref.sh trace`
+Scope: the moves of the CO2-MFI deck (translation, rotation, CBMC insertion / deletion, reinsertion)."""
+import sys
+
+
+def patch(path, edits):
+    s = open(path).read()
+    for old, new in edits:
+        assert s.count(old) == 1, (path, s.count(old), old[:80])
+        s = s.replace(old, new)
+    open(path, "w").write(s)
+
+
+def main(scr):
+    patch(f"{scr}/data_struct.cpp", [(
+        "double Get_Uniform_Random()\n{\n  //return (double) (rand()/RAND_MAX);\n  //std::srand(3.0);\n  return static_cast<double>(std::rand()) / RAND_MAX;\n}",
+        "static bool g_uniform_pending = false; static double g_uniform_value = 0.0;\n"
+        "double Peek_Uniform_Random()\n{\n  if(!g_uniform_pending) { g_uniform_value = static_cast<double>(std::rand()) / RAND_MAX; g_uniform_pending = true; }\n  return g_uniform_value;\n}\n"
+        "double Get_Uniform_Random()\n{\n  if(g_uniform_pending) { g_uniform_pending = false; return g_uniform_value; }\n  return static_cast<double>(std::rand()) / RAND_MAX;\n}")])
+    s = open(f"{scr}/data_struct.h").read()
+    assert s.count("struct RandomNumber\n{") == 1
+    s = s.replace("struct RandomNumber\n{", "inline void b200_pool_refreshed(const double3* host_random, size_t n);\nstruct RandomNumber\n{")
+    old = "    cudaMemcpy(device_random, host_random, randomsize * sizeof(double3), cudaMemcpyHostToDevice);\n    Rounds ++;"
+    assert s.count(old) == 1
+    s = s.replace(old, old + "\n    b200_pool_refreshed(host_random, randomsize);")
+    s += '\n#include "graspa_b200_adapter.h"\n'
+    open(f"{scr}/data_struct.h", "w").write(s)
+    patch(f"{scr}/mc_widom.h", [
+        ("inline void Widom_Move_FirstBead_PARTIAL(Variables& Vars, size_t systemId, CBMC_Variables& CBMC)\n{",
+         "inline void Widom_Move_FirstBead_PARTIAL(Variables& Vars, size_t systemId, CBMC_Variables& CBMC)\n{\n  b200_first_bead(Vars, systemId, CBMC); return;"),
+        ("inline void Widom_Move_Chain_PARTIAL(Variables& Vars, size_t systemId, CBMC_Variables& CBMC)\n{",
+         "inline void Widom_Move_Chain_PARTIAL(Variables& Vars, size_t systemId, CBMC_Variables& CBMC)\n{\n  b200_chain(Vars, systemId, CBMC); return;")])
+    patch(f"{scr}/Ewald_Energy_Functions.h", [
+        ("double2 GPU_EwaldDifference_General(Simulations& Sim, ForceField& FF, Components& SystemComponents, size_t SelectedComponent, int MoveType, size_t Location, double2 Scale)\n{",
+         "double2 GPU_EwaldDifference_General(Simulations& Sim, ForceField& FF, Components& SystemComponents, size_t SelectedComponent, int MoveType, size_t Location, double2 Scale)\n{\n"
+         "  if(b200().e) return b200_ewald_delta(SystemComponents, SelectedComponent, MoveType, Location, Scale);"),
+        ("void Update_Vector_Ewald(Boxsize& Box, bool CPU, Components& SystemComponents, size_t SelectedComponent)\n{",
+         "void Update_Vector_Ewald(Boxsize& Box, bool CPU, Components& SystemComponents, size_t SelectedComponent)\n{\n  if(b200().e) return;     // the gb_accept_* calls swap the engine's vectors")])
+    patch(f"{scr}/mc_single_particle.h", [
+        ("  get_new_position<<<1, Molsize>>>(Sims, FF, start_position, SelectedComponent, MaxChange, Random.device_random, Random.offset, MoveType);",
+         "  b200_propose(Vars, systemId, MoveType, SelectedComponent, SelectedMolInComponent, MaxChange, Random.offset);"),
+        ("    Calculate_Single_Body_Energy_VDWReal<<<Total_Nblock, Nthread, Nthread * 2 * sizeof(double)>>>(Sims.Box, Sims.d_a, Sims.Old, Sims.New, FF, Sims.Blocksum, SelectedComponent, Atomsize, Molsize, Sims.device_flag, NBlocks, Do_New, Do_Old, SystemComponents.NComponents);\n\n"
+         "    SystemComponents.flag = Sims.device_flag;\n    cudaDeviceSynchronize();",
+         "    b200_single_body_delta(SystemComponents, SelectedComponent, Do_New, Do_Old);"),
+        ("    // Calculate Ewald //\n", "    b200_take_single_body(tot);\n    // Calculate Ewald //\n")])
+    patch(f"{scr}/mc_utilities.h", [
+        ("  update_translation_position<<<1,Molsize>>>(Sims.d_a, Sims.New, start_position, SelectedComponent);",
+         "  b200_accept_translation(SelectedComponent);"),
+        ("    Update_insertion_data_Parallel<<<1,SystemComponents.Moleculesize[SelectedComponent]>>>(Sims.d_a, Sims.Old, Sims.New, SelectedTrial, SelectedComponent, UpdateLocation, (int) SystemComponents.Moleculesize[SelectedComponent]);",
+         "    b200_accept_insertion(SelectedComponent);"),
+        ("  Update_deletion_data_Parallel<<<1,SystemComponents.Moleculesize[SelectedComponent]>>>(Sims.d_a, SelectedComponent, UpdateLocation, (int) SystemComponents.Moleculesize[SelectedComponent], LastLocation);",
+         "  b200_accept_deletion(SelectedComponent, UpdateLocation / SystemComponents.Moleculesize[SelectedComponent]);")])
+    patch(f"{scr}/move_struct.h", [
+        ("      StoreNewLocation_Reinsertion<<<1,SystemComponents.Moleculesize[SelectedComponent]>>>(Sims.Old, Sims.New, SystemComponents.tempMolStorage, SelectedTrial, SystemComponents.Moleculesize[SelectedComponent]);",
+         "      b200_reinsertion_store(SelectedComponent);"),
+        ("    Update_Reinsertion_data<<<1,SystemComponents.Moleculesize[SelectedComponent]>>>(Sims.d_a, SystemComponents.tempMolStorage, SelectedComponent, UpdateLocation); checkCUDAError(\"error Updating Reinsertion data\");",
+         "    b200_accept_reinsertion(SelectedComponent, SystemComponents.TempVal.molecule);")])
+    patch(f"{scr}/main.cpp", [("    check_energy_wrapper(Vars, i);\n    //Report Random Number Summary", "    b200_sync_back(Vars, i);\n    check_energy_wrapper(Vars, i);\n    //Report Random Number Summary")])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -115,3 +115,53 @@ def test_henry_coefficient_deck_equals_the_reference_program(tmp_path):
             assert abs(a - b) <= 1e-9 * abs(b) + 2e-10, (flags, w, ref_w)
         assert abs(avg - ref_avg) <= 1e-9 * abs(ref_avg) + 2e-10
         assert abs(kh - ref_kh) <= 1e-9 * abs(ref_kh) + 1e-14
+
+
+REF_OVERLAY = os.path.join(ROOT, "oracle", "_ref", "graspa_ref_overlay.x")
+
+
+def test_reference_drivers_bound_to_the_c_abi_reproduce_the_stock_reference(tmp_path):
+    """The drop-in, demonstrated: the reference's OWN program with its hot-path call sites bound to libgraspa_b200.so
+    (oracle/overlay/: the adapter header a maintainer would add + the call-site patch, applied to a scratch copy by
+    oracle/build_ref.sh overlay; RunMoves, Insertion_Body, Deletion_Body, ReinsertionMove, SingleBodyMove, the acceptance tests and
+    every random-number draw remain the reference's code) against the stock reference program, CO2-MFI, 10^4 cycles, seed 0:
+    the same accept/reject sequence move by move, and the reference's own FINAL energy check (its CPU and GPU total-energy
+    routines run on the state the engine leaves) reports no drift."""
+    for need in (REF_TRACE, REF_OVERLAY):
+        if not os.path.exists(need):
+            pytest.skip(f"{need} not built (oracle/build_ref.sh trace / overlay)")
+    d = _deck_copy("CO2-MFI", tmp_path, 10000, 0)
+    traces = {}
+    outs = {}
+    for tag, exe in (("stock", REF_TRACE), ("overlay", REF_OVERLAY)):
+        tr = str(tmp_path / f"{tag}_trace.txt")
+        r = subprocess.run([exe], cwd=d, env=dict(os.environ, GRASPA_TRACE=tr), capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0, (tag, (r.stdout + r.stderr)[-3000:])
+        traces[tag] = [l.split() for l in open(tr)]
+        outs[tag] = r
+    a, b = traces["stock"], traces["overlay"]
+    assert len(a) == len(b) and len(a) > 200000, (len(a), len(b))
+    differ = 0; worst = 0.0; accepted = 0
+    for x, y in zip(a, b):
+        dx, dy = float(x[2]), float(y[2])
+        if x[0] != y[0] or x[1] != y[1] or (dx != 0.0) != (dy != 0.0):
+            differ += 1
+        elif dx != 0.0:
+            accepted += 1
+            worst = max(worst, abs(dx - dy) / abs(dx))
+    print("overlay vs stock:", len(a), "moves,", accepted, "accepted,", differ, "differ, worst relative energy difference", worst)
+    assert differ == 0 and accepted > 50000 and worst < 1e-8
+    # the engine really served the run, and the reference's own end-of-run check is content with the state it left
+    assert "engine kernel launches served the reference's drivers" in outs["overlay"].stderr
+    launches = int(outs["overlay"].stderr.split("graspa_b200 overlay:")[1].split()[0])
+    assert launches > 400000
+    def final_total(text):
+        lines = text.splitlines()
+        k = max(i for i, ln in enumerate(lines) if "*** FINAL STAGE ***" in ln)
+        return float([ln for ln in lines[k:k + 25] if ln.startswith("Total Energy:")][0].split(":")[1].split("(")[0])
+    assert abs(final_total(outs["overlay"].stdout) - final_total(outs["stock"].stdout)) < 2e-5
+    def block_total(text, header):
+        lines = text.splitlines()
+        k = max(i for i, ln in enumerate(lines) if header in ln)
+        return float([ln for ln in lines[k:k + 25] if ln.startswith("Total Energy:")][0].split(":")[1].split("(")[0])
+    assert abs(block_total(outs["overlay"].stdout, "ENERGY DRIFT (CPU FINAL - RUNNING FINAL)")) < 1e-3      # the reference's own criterion (test_examples.py:59-61)
