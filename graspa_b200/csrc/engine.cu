@@ -16,6 +16,7 @@
 #include <vector>
 #include <atomic>
 #include <chrono>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges show up in nsys / ncu --nvtx, cost nothing without a tool attached
 
 namespace {
 
@@ -29,6 +30,9 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
     if(err__ != cudaSuccess)                                                                       \
       return fail(GB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));             \
   } while(0)
+
+// NVTX range for the scope of one ABI call / stage (the reference has only omp_get_wtime stopwatches)
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 
 template <typename T>
 struct DevBuf
@@ -1104,6 +1108,7 @@ namespace {
 // overlap != NULL: also report whether any pair trips OverlapCriteria or r^2 < 0.01 (VDWCoulEnergy_Total, VDW_Coulomb.cu:1385-1386)
 int total_vdw_real_impl(gb_engine* e, gb_move_energy* out, int32_t* overlap)
 {
+  NvtxRange nvtx_call("gb_total_vdw_real");
   int rc = ready(e); if(rc) return rc;
   if(!out) return fail(GB_ERR_ARG, "null out");
   memset(out, 0, sizeof(*out));
@@ -1142,6 +1147,7 @@ int total_vdw_real_impl(gb_engine* e, gb_move_energy* out, int32_t* overlap)
 // true: as the device Ewald_TotalEnergy does (HH, HG, GG separate, each minus its own exclusions; Ewald_Energy_Functions.h:1366-1428)
 int total_ewald_impl(gb_engine* e, int32_t store, bool device_convention, gb_move_energy* out)
 {
+  NvtxRange nvtx_call("gb_total_ewald");
   int rc = ready(e); if(rc) return rc;
   if(!out) return fail(GB_ERR_ARG, "null out");
   memset(out, 0, sizeof(*out));
@@ -1395,6 +1401,7 @@ static int widom_cells_grid(gb_engine* e, WcGrid& G)
 static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double* d_pool, const long long* d_fb, const long long* d_or, const double* d_uni,
                                int first_bead_only, long long ins0, long long n_total)
 {
+  NvtxRange nvtx_stage("widom pair stage (cell-sorted)");
   const Comp& C = e->comps[comp];
   const int ms = C.molsize, cs = ms - 1;
   const int rec_stride = 5 + 3 * ms;
@@ -1521,6 +1528,7 @@ int gb_widom_first_bead_success(gb_engine* e, int32_t comp, int64_t n, const dou
 int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs* in, double* out8, int32_t* stage,
                    int32_t outputs_on_device, double* sums)
 {
+  NvtxRange nvtx_call("gb_widom_batch");
   int rc = ready(e); if(rc) return rc;
   if(!in || n <= 0 || !in->pool3 || !in->uniforms) return fail(GB_ERR_ARG, "bad Widom inputs");
   if(comp < e->nhost || comp >= e->ncomp) return fail(GB_ERR_ARG, "Widom component must be an adsorbate component");
@@ -1626,6 +1634,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   CUDA_TRY(e->d_partial.reserve((size_t) gridB * nbins * 12)); CUDA_TRY(e->d_sums.reserve((size_t) nbins * 12));
   B.partial = e->d_partial.p;
   {
+    NvtxRange nvtx_stage("widom fourier stage");
     Timer tm(e, 1);
     k_widom_ewald<<<gridB, warpsB * 32, smemB, e->stream>>>(e->P, B);
     k_reduce_partials<<<(nbins * 12 + 63) / 64, 64, 0, e->stream>>>(e->d_partial.p, gridB, nbins * 12, e->d_sums.p);
