@@ -1,17 +1,32 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, smoke, bench, ncu launch list of the bench command, one full ncu capture of the Widom
-# pair kernel and of the move kernel.  Everything lands in gpurun_out/ (scratch); summaries are copied to profiles/ by hand.
+# One GPU-box pass (round 2): parity tests, smoke, bench, ncu launch list of the bench command, full ncu captures of the Widom
+# energy kernel (cell-sorted stage), the Widom Fourier kernel and the move kernel.  Everything lands in gpurun_out/ (scratch);
+# summaries are copied to profiles/ by hand (tools/ncu_summary.py).
 set -u
+R=${1:-r2}
+WHAT=${2:-all}     # all | check | prof
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+if [ "$WHAT" != prof ]; then
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 | tee gpurun_out/${R}_gputest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 900 python bench.py > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; tail -c 3000 gpurun_out/bench_r1.json; tail -3 gpurun_out/bench_r1.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1.csv \
-  python bench.py --steps 2 --warmup 3 --batch 40000 --no-cpu-baseline --no-secondary > gpurun_out/bench_under_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_widom_pair -s 3 -c 1 -o gpurun_out/prof_pair_r1 -f \
-  python bench.py --steps 1 --warmup 3 --batch 40000 --no-cpu-baseline --no-secondary > gpurun_out/ncu_pair.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_widom_ewald -s 3 -c 1 -o gpurun_out/prof_ewald_r1 -f \
-  python bench.py --steps 1 --warmup 3 --batch 40000 --no-cpu-baseline --no-secondary > gpurun_out/ncu_ewald.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_move -s 2000 -c 4 -o gpurun_out/prof_move_r1 -f \
-  graspa_b200/host/graspa_b200_mc oracle/_ref/examples/CO2-MFI --init 200 > gpurun_out/ncu_move.log 2>&1
+timeout 900 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err; tail -c 1500 gpurun_out/${R}_bench.json; tail -3 gpurun_out/${R}_bench.err
+for deck in "XeKr-Mixture 20000" "CO2-MFI 3000"; do
+  set -- $deck
+  D=$(mktemp -d /tmp/rc.XXXX); cp -r oracle/_ref/examples/$1/* $D/; chmod -R u+w $D
+  ./graspa_b200/host/graspa_b200_mc $D --init $2 --equil 0 --prod 0 2>&1 | grep -E "cycles_per_s|host time" | tee -a gpurun_out/${R}_moves.log
+  ./graspa_b200/host/graspa_b200_mc $D --init $2 --equil 0 --prod 0 --timing 2>&1 | grep -E "device time" | tee -a gpurun_out/${R}_moves.log
+  rm -rf $D
+done
+fi
+[ "$WHAT" = check ] && exit 0
+NCUB="python bench.py --scaling weak --batch 200000 --no-cpu-baseline --no-secondary"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${R}_launches.csv \
+  $NCUB --steps 2 --warmup 3 > gpurun_out/${R}_bench_under_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_wc_energy_lt -s 8 -c 2 -o gpurun_out/prof_wc_energy_${R} -f \
+  $NCUB --steps 1 --warmup 3 > gpurun_out/${R}_ncu_wc.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_widom_ewald -s 3 -c 1 -o gpurun_out/prof_ewald_${R} -f \
+  $NCUB --steps 1 --warmup 3 > gpurun_out/${R}_ncu_ewald.log 2>&1
+D=$(mktemp -d /tmp/rc.XXXX); cp -r oracle/_ref/examples/XeKr-Mixture/* $D/; chmod -R u+w $D
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_move -s 4000 -c 3 -o gpurun_out/prof_move_${R} -f \
+  graspa_b200/host/graspa_b200_mc $D --init 6000 --equil 0 --prod 0 > gpurun_out/${R}_ncu_move.log 2>&1
 ls -la gpurun_out | tail -12
