@@ -5,6 +5,7 @@
 #include "pair_kernels.cuh"
 #include "move_kernels.cuh"
 #include "fused_kernel.cuh"
+#include "move_server.cuh"
 #include "widom_cells.cuh"
 
 #include <algorithm>
@@ -123,6 +124,17 @@ struct gb_engine
   double* h_results = nullptr;           // 2 KB of h_pinned: tagged result records of k_move
   unsigned long long move_seq = 0;       // sequence number of the last k_move launch (published to h_pinned + 256)
   bool move_cooperative = true;          // cudaLaunchCooperativeKernel: co-residency of the move kernel's CTAs guaranteed by the driver
+  // resident move server (move_server.cuh): one cooperative launch that executes move after move; the fused move calls post
+  // commands to it, the accept calls queue their commits for the next command, every other call stops it first (ready())
+  bool counted = false;
+  bool srv_enabled = true, srv_running = false; int srv_compat = 0, srv_grid = 0; size_t srv_smem = 0;
+  cudaStream_t srv_stream = nullptr;
+  unsigned long long* srv_hcmd = nullptr;        // 4 KB pinned: [0, 2 KB) command records, [2 KB] status word
+  DevBuf<unsigned long long> srv_dcmd, srv_done;
+  DevParams srv_P{}; SysView srv_S{};            // what the running server was launched with
+  unsigned long long srv_next = 0;               // sequence number the server expects next
+  std::vector<CommitOp> pending_commits;         // accepted moves whose state change the next command carries
+  long long srv_starts = 0, srv_commands = 0;
 
   // single-move path
   DevBuf<double> d_mv, d_ewpos; DevBuf<int> d_mvi;
@@ -208,6 +220,14 @@ int sync_slots_to_device(gb_engine* e)
   return GB_OK;
 }
 
+// resident move server (move_server.cuh; host side in fused_moves.inc).  Calls that may run while the server is resident -- they post
+// commands, queue commits, or launch only tiny kernels / copies on the engine's stream -- hold a SrvCompat; every other entry point
+// stops the server (and brings the device slots up to date) in ready().
+struct SrvCompat { gb_engine* e; explicit SrvCompat(gb_engine* e_) : e(e_) { if(e) e->srv_compat++; } ~SrvCompat() { if(e) e->srv_compat--; } };
+int server_stop(gb_engine* e);
+int commit_op(gb_engine* e, const CommitOp& c);
+std::atomic<int> g_engines_alive{0};
+
 int ready(gb_engine* e)
 {
   if(!e) return fail(GB_ERR_ARG, "null engine");
@@ -216,6 +236,7 @@ int ready(gb_engine* e)
   if(e->ncomp == 0) return fail(GB_ERR_STATE, "gb_set_components has not been called");
   for(int c = 0; c < e->ncomp; c++) if(!e->comps[c].uploaded) return fail(GB_ERR_STATE, "component " + std::to_string(c) + " has not been uploaded");
   CUDA_TRY(cudaSetDevice(e->device));
+  if((e->srv_running || !e->pending_commits.empty()) && e->srv_compat == 0) { int rc = server_stop(e); if(rc) return rc; }
   e->P.erfc_table_ok = (e->P.alpha * std::sqrt(e->P.cut_coul2) < GBK_ERFC_XMAX) ? 1 : 0;
   {
     // reach of the cutoff sphere along each fractional axis: |s_i| = |r . inv[:,i]| <= |r| |inv[:,i]|  (tile culling)
@@ -500,6 +521,7 @@ int gb_engine_create(gb_engine** out, int device)
   e->device = device;
   const int rc_init = engine_init(e, device);
   if(rc_init != GB_OK) { const std::string msg = g_err; gb_engine_destroy(e); return fail(rc_init, msg); }     // nothing of a half-built engine is leaked
+  e->counted = true; g_engines_alive++;       // the resident move server is used only while ONE engine lives in the process (header: one engine per GPU)
   *out = e;
   return GB_OK;
 }
@@ -541,6 +563,16 @@ static int engine_init(gb_engine* e, int device)
       int coop = 0; CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
       e->move_cooperative = coop != 0 && !(std::getenv("GB_MOVE_COOP") && std::atoi(std::getenv("GB_MOVE_COOP")) == 0);     // GB_MOVE_COOP=0: A/B timing only (1 % on the GCMC decks)
     }
+    {
+      // resident move server: same scratch capacity as the largest k_move launch; needs a cooperative launch (co-resident CTAs)
+      e->srv_smem = std::min((size_t) optin - 1024, srv_smem_fixed() + (size_t) GBF_MAX_DYN_SMEM - ((sizeof(FusedSmem) + 127) / 128) * 128);
+      CUDA_TRY(cudaFuncSetAttribute(k_move_server, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) e->srv_smem));
+      e->srv_grid = std::min(e->prop.multiProcessorCount, 256);
+      e->srv_enabled = e->move_cooperative && !(std::getenv("GB_MOVE_SERVER") && std::atoi(std::getenv("GB_MOVE_SERVER")) == 0);
+      CUDA_TRY(cudaStreamCreateWithFlags(&e->srv_stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaMallocHost(&e->srv_hcmd, 4096)); memset(e->srv_hcmd, 0, 4096);
+      CUDA_TRY(e->srv_dcmd.reserve(2 * (GBS_NREC + GBS_CREC))); CUDA_TRY(e->srv_done.reserve(256));
+    }
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_ewald_delta));
     CUDA_TRY(cudaFuncSetAttribute(k_ewald_delta, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
     e->smem_optin -= 1024;   // head room for static shared memory of the kernels
@@ -555,6 +587,11 @@ int gb_engine_destroy(gb_engine* e)
 {
   if(!e) return GB_OK;
   cudaSetDevice(e->device);
+  if(e->srv_running || !e->pending_commits.empty()) server_stop(e);
+  if(e->counted) { g_engines_alive--; e->counted = false; }
+  if(e->srv_stream) cudaStreamDestroy(e->srv_stream);
+  if(e->srv_hcmd) cudaFreeHost(e->srv_hcmd);
+  e->srv_dcmd.release(); e->srv_done.release();
   if(e->stream) cudaStreamSynchronize(e->stream);
   e->d_ffA.release(); e->d_ffB.release(); e->d_erfc.release(); e->d_tail_use.release(); e->d_tail_e.release();
   e->dx.release(); e->dy.release(); e->dz.release(); e->dfx.release(); e->dfy.release(); e->dfz.release();
@@ -1077,6 +1114,7 @@ int gb_tail_total(gb_engine* e, double* out)
 int gb_tail_difference(gb_engine* e, int32_t c, int32_t move_type, double* out)
 {
   if(e && e->have_ff && !e->has_tail && out) { *out = 0.0; return GB_OK; }     // HasTailCorrection == false (:39)
+  SrvCompat srv_ok(e);
   int rc = ready(e); if(rc) return rc;
   if(c < 0 || c >= e->ncomp) return fail(GB_ERR_ARG, "bad component");
   if(move_type == GB_CBCF_INSERTION || move_type == GB_CBCF_DELETION) return fail(GB_ERR_UNIMPLEMENTED, "tail corrections are not defined for CBCF moves (TailCorrection_Energy_Functions.h:48-55)");
@@ -1088,6 +1126,7 @@ int gb_tail_difference(gb_engine* e, int32_t c, int32_t move_type, double* out)
 
 int gb_tail_identity_swap(gb_engine* e, int32_t newc, int32_t oldc, double* out)
 {
+  SrvCompat srv_ok(e);
   int rc = ready(e); if(rc) return rc;
   if(newc < 0 || newc >= e->ncomp || oldc < 0 || oldc >= e->ncomp) return fail(GB_ERR_ARG, "bad component");
   std::vector<int> dn = species_counts(e, newc), dold = species_counts(e, oldc);
@@ -1680,6 +1719,21 @@ int gb_launch_count(gb_engine* e, int64_t* n, int32_t reset)
 }
 
 int gb_timing_enable(gb_engine* e, int32_t on) { if(!e) return fail(GB_ERR_ARG, "null engine"); e->timing = on != 0; return GB_OK; }
+
+int gb_move_server(gb_engine* e, int32_t on, int64_t* starts, int64_t* commands)
+{
+  if(!e) return fail(GB_ERR_ARG, "null engine");
+  if(on == 0)
+  {
+    CUDA_TRY(cudaSetDevice(e->device));
+    if(e->srv_running || !e->pending_commits.empty()) { int rc = server_stop(e); if(rc) return rc; }
+    e->srv_enabled = false;
+  }
+  else if(on > 0) e->srv_enabled = e->move_cooperative;
+  if(starts) *starts = e->srv_starts;
+  if(commands) *commands = e->srv_commands;
+  return GB_OK;
+}
 
 int gb_timing_read(gb_engine* e, int32_t family, double* ms, int64_t* launches, int32_t reset)
 {

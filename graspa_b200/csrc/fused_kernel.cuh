@@ -25,16 +25,23 @@
 #include "ewald.cuh"
 #include "move_kernels.cuh"
 
-enum { GBF_INSERTION = 0, GBF_DELETION = 1, GBF_REINSERTION = 2, GBF_SINGLE = 3, GBF_IDSWAP = 4 };
+enum { GBF_INSERTION = 0, GBF_DELETION = 1, GBF_REINSERTION = 2, GBF_SINGLE = 3, GBF_IDSWAP = 4, GBF_EXIT = 5 };
 #define GBF_MAX_GROUPS 96           // trial groups of one stage: ntrials + 1 + norient <= 65
 #define GBF_PART_HALF 4096          // doubles per parity half of MoveBufs::partial()
 #define GBF_MAX_DYN_SMEM (160 * 1024)
 #define GBF_MAX_ITEMS 192           // (group, split) items of one stage; each publishes one 128-byte record
+#define GBF_SPIN_LIMIT (1u << 24)      // polls of a hand-over record before the kernel gives up (__trap)
 #define GBF_PART_EWALD (GBF_MAX_ITEMS * 16)   // Ewald CTA records (32 bytes each) start here inside a half
+
+// a state commit the resident move server applies before the move that carries it (the accept calls queue these instead of
+// launching k_commit_*): op 1 = k_commit_from_buffer(buf -> dst, n, what, molid), op 2 = k_commit_delete(dst <- src, n)
+struct CommitOp { int op, buf, dst, src, n, what, molid, pad; };
 
 struct FusedArgs
 {
   int kind, comp, ms, move_type;          // move_type: GB_TRANSLATION / GB_ROTATION / GB_SPECIAL_ROTATION for GBF_SINGLE
+  int ngrid;                              // CTAs that take part in this move (= gridDim.x of a k_move launch; <= grid of the resident server)
+  int ncommit; CommitOp commit[2];        // resident server only: commits of the previous accepted move, applied first
   long long molecule, pool_off;
   double u0, u1, scale0, scale1, maxc[3];
   int ntrials, norient, nmol;             // nmol = NumberOfMolecule_for_Component (MolID of an inserted molecule)
@@ -105,7 +112,7 @@ __device__ __forceinline__ double* part_half(const FusedArgs& F, int par) { retu
 __device__ __forceinline__ int stage_nsplit(const FusedArgs& F, int ngroups)
 {
   const int ns = (F.natoms + GBF_SPLIT_ATOMS - 1) / GBF_SPLIT_ATOMS;   // system atoms per (group, split) item; 256 = one 32-atom iteration per warp
-  const int cap = max(1, min(GBF_MAX_ITEMS / max(ngroups, 1), (int) gridDim.x / max(ngroups, 1)));
+  const int cap = max(1, min(GBF_MAX_ITEMS / max(ngroups, 1), F.ngrid / max(ngroups, 1)));
   return max(1, min(ns, cap));
 }
 
@@ -187,7 +194,7 @@ __device__ __forceinline__ void run_stage(const DevParams& P, const SysView& S, 
 {
   double* part = part_half(F, par);
   const unsigned int tag = stage_tag(F.seq, par);
-  for(int w = blockIdx.x; w < ngroups * nsplit; w += gridDim.x)
+  for(int w = blockIdx.x; w < ngroups * nsplit; w += F.ngrid)
   {
     const int gg = w / nsplit, split = w % nsplit;
     int g = gg, si = 0;
@@ -241,12 +248,13 @@ __device__ __forceinline__ void fetch_records(const double* part, int nitems, un
   for(int w = threadIdx.x; w < nitems; w += blockDim.x)
   {
     const double* rec = part + (size_t) w * 16;
-    double v[7]; bool ok;
+    double v[7]; bool ok; unsigned int spins = 0;
     do
     {
       ok = true;
 #pragma unroll
       for(int j = 0; j < 7; j++) ok = ll_load(rec, j, tag, v[j]) && ok;
+      if(!ok && ++spins > GBF_SPIN_LIMIT) __trap();           // ~10 s of polling: a record that never comes is an error, not a hang
     } while(!ok);
 #pragma unroll
     for(int j = 0; j < 7; j++) stash[w * 8 + j] = v[j];
@@ -337,13 +345,13 @@ __device__ __forceinline__ void adopt_selection(const DevParams& P, const FusedA
 
 // Ewald Fourier delta of [old atoms | new atoms]: the last `ne` CTAs of the grid each take 256 k-vectors; CTA partial
 // {same, cross} goes to out2[2 * slice].  old atoms: component slots (oldS == nullptr) or a shared-memory molecule.
-__device__ __forceinline__ int ewald_ctas(const FusedArgs& F) { return min((int) gridDim.x, (F.K.nact + 255) / 256); }
+__device__ __forceinline__ int ewald_ctas(const FusedArgs& F) { return min(F.ngrid, (F.K.nact + 255) / 256); }
 
 __device__ __forceinline__ void ewald_slice(const DevParams& P, const FusedArgs& F, unsigned char* dyn, double* red, const SmemMol* oldS,
                                             int nold, const SmemMol* newS, int nnew, double* out2)
 {
   const int ne = ewald_ctas(F);
-  const int slice = (int) blockIdx.x - ((int) gridDim.x - ne);
+  const int slice = (int) blockIdx.x - (F.ngrid - ne);
   if(slice < 0) return;
   const int n = nold + nnew;
   const int kx1 = P.kmax[0] + 1, ky1 = P.kmax[1] + 1, kz1 = P.kmax[2] + 1;
@@ -414,8 +422,8 @@ __device__ __forceinline__ void fetch_ewald(const FusedArgs& F, const double* in
   const unsigned int tag = stage_tag(F.seq, 2);
   for(int w = threadIdx.x; w < 2 * ne; w += blockDim.x)
   {
-    double v;
-    while(!ll_load(in2 + 4 * (w >> 1), w & 1, tag, v)) { }
+    double v; unsigned int spins = 0;
+    while(!ll_load(in2 + 4 * (w >> 1), w & 1, tag, v)) { if(++spins > GBF_SPIN_LIMIT) __trap(); }
     stash[w] = v;
   }
 }
@@ -450,15 +458,49 @@ __device__ __forceinline__ void export_molecule(const FusedArgs& F, const SmemMo
 // One kernel for every move kind.  Measured and not kept (profiles/r2_move_kernel.md): one instantiation per kind with the kind as a
 // build-time constant (each carries only its own move's code) -- 10 % SLOWER on all three GCMC decks, because consecutive moves of
 // different kinds then alternate between kernels and every switch starts with cold instruction caches.
-__global__ void __launch_bounds__(256, 1)
-k_move(DevParams P, SysView S, FusedArgs F)
+// ---- out-of-line copies of the stage routines for the resident server (SRV = true).  k_move inlines every routine at every call
+// site (48 800 SASS instructions, 780 KB): one launch walks through its own kind's code once, so layout does not matter there.  The
+// server executes move after move of every kind on the same SMs, and what it touches must stay inside the instruction caches:
+// one copy of each routine, shared by all kinds.  Arguments are references into shared memory (P, S, F live there in the server).
+#define GBF_OUT __device__ __noinline__
+GBF_OUT void run_stage_out(const DevParams& P, const SysView S, const FusedArgs& F, FusedSmem* sm, PairTables W, const StageSeg* segs, int nseg, int ngroups, int nsplit, int par)
+{ run_stage(P, S, F, sm, W, segs, nseg, ngroups, nsplit, par); }
+GBF_OUT void collect_stage_out(const FusedArgs& F, FusedSmem* sm, double* stash, int ngroups, int nsplit, int par) { collect_stage(F, sm, stash, ngroups, nsplit, par); }
+GBF_OUT void finish_segment_out(const DevParams& P, const FusedArgs& F, FusedSmem* sm, int type, bool chain, int n, double uniform, double stored, const double* E, const int* Fl, int slot, double prev_product)
+{ finish_segment(P, F, sm, type, chain, n, uniform, stored, E, Fl, slot, prev_product); }
+GBF_OUT void adopt_selection_out(const DevParams& P, const FusedArgs& F, FusedSmem* sm, int type, bool chain, long long pool_off, int slot) { adopt_selection(P, F, sm, type, chain, pool_off, slot); }
+GBF_OUT void ewald_slice_out(const DevParams& P, const FusedArgs& F, unsigned char* dyn, double* red, const SmemMol* oldS, int nold, const SmemMol* newS, int nnew, double* out2)
+{ ewald_slice(P, F, dyn, red, oldS, nold, newS, nnew, out2); }
+GBF_OUT void ewald_total_slot_out(const FusedArgs& F, FusedSmem* sm, double* stash, const double* in2, bool run) { ewald_total_slot(F, sm, stash, in2, run); }
+GBF_OUT void export_molecule_out(const FusedArgs& F, const SmemMol& M, int buf) { export_molecule(F, M, buf); }
+GBF_OUT void group_energy0_out(const DevParams& P, PairTables W, const SysView S, const FusedArgs& F, FusedSmem* sm, int new_molid, int cs, int split, int nsplit, double* rec, unsigned int tag)
+{ group_energy<0>(P, W, S, F, sm, new_molid, cs, split, nsplit, rec, tag); }
+
+template <bool SRV> __device__ __forceinline__ void run_stage_d(const DevParams& P, const SysView& S, const FusedArgs& F, FusedSmem* sm, const PairTables& W, const StageSeg* segs, int nseg, int ngroups, int nsplit, int par)
+{ if(SRV) run_stage_out(P, S, F, sm, W, segs, nseg, ngroups, nsplit, par); else run_stage(P, S, F, sm, W, segs, nseg, ngroups, nsplit, par); }
+template <bool SRV> __device__ __forceinline__ void collect_stage_d(const FusedArgs& F, FusedSmem* sm, double* stash, int ngroups, int nsplit, int par)
+{ if(SRV) collect_stage_out(F, sm, stash, ngroups, nsplit, par); else collect_stage(F, sm, stash, ngroups, nsplit, par); }
+template <bool SRV> __device__ __forceinline__ void finish_segment_d(const DevParams& P, const FusedArgs& F, FusedSmem* sm, int type, bool chain, int n, double uniform, double stored, const double* E, const int* Fl, int slot, double prev_product)
+{ if(SRV) finish_segment_out(P, F, sm, type, chain, n, uniform, stored, E, Fl, slot, prev_product); else finish_segment(P, F, sm, type, chain, n, uniform, stored, E, Fl, slot, prev_product); }
+template <bool SRV> __device__ __forceinline__ void adopt_selection_d(const DevParams& P, const FusedArgs& F, FusedSmem* sm, int type, bool chain, long long pool_off, int slot)
+{ if(SRV) adopt_selection_out(P, F, sm, type, chain, pool_off, slot); else adopt_selection(P, F, sm, type, chain, pool_off, slot); }
+template <bool SRV> __device__ __forceinline__ void ewald_slice_d(const DevParams& P, const FusedArgs& F, unsigned char* dyn, double* red, const SmemMol* oldS, int nold, const SmemMol* newS, int nnew, double* out2)
+{ if(SRV) ewald_slice_out(P, F, dyn, red, oldS, nold, newS, nnew, out2); else ewald_slice(P, F, dyn, red, oldS, nold, newS, nnew, out2); }
+template <bool SRV> __device__ __forceinline__ void ewald_total_slot_d(const FusedArgs& F, FusedSmem* sm, double* stash, const double* in2, bool run)
+{ if(SRV) ewald_total_slot_out(F, sm, stash, in2, run); else ewald_total_slot(F, sm, stash, in2, run); }
+template <bool SRV> __device__ __forceinline__ void export_molecule_d(const FusedArgs& F, const SmemMol& M, int buf)
+{ if(SRV) export_molecule_out(F, M, buf); else export_molecule(F, M, buf); }
+template <bool SRV> __device__ __forceinline__ void group_energy0_d(const DevParams& P, const PairTables& W, const SysView& S, const FusedArgs& F, FusedSmem* sm, int new_molid, int cs, int split, int nsplit, double* rec, unsigned int tag)
+{ if(SRV) group_energy0_out(P, W, S, F, sm, new_molid, cs, split, nsplit, rec, tag); else group_energy<0>(P, W, S, F, sm, new_molid, cs, split, nsplit, rec, tag); }
+
+// The whole move, run by every CTA with blockIdx.x < F.ngrid.  SRV = false: the body of one k_move launch (P, S, F are kernel
+// parameters).  SRV = true: one command of the resident server (k_move_server): F and S are shared-memory copies -- the compiler then
+// cannot route the loads of the (mutable) slot arrays through the non-coherent path -- and the erfc table is already staged.
+template <bool SRV>
+__device__ __forceinline__ void move_body(const DevParams& P, const SysView& S, const FusedArgs& F, FusedSmem& sm, unsigned char* dyn)
 {
-  // dynamic shared memory: [FusedSmem | scratch: eik tables of the Ewald stage / stash of the collect steps (>= 12 KB)]
-  extern __shared__ __align__(128) unsigned char dyn_all[];
-  FusedSmem& sm = *reinterpret_cast<FusedSmem*>(dyn_all);
-  unsigned char* dyn = dyn_all + ((sizeof(FusedSmem) + 127) / 128) * 128;
 #ifdef GBK_PHASE_TIMING
-  if(blockIdx.x == 0 && threadIdx.x == 0) g_nmarks = 0;
+  if(!SRV && blockIdx.x == 0 && threadIdx.x == 0) g_nmarks = 0;
 #endif
   GBK_MARK();
   const int ms = F.ms;
@@ -481,33 +523,50 @@ k_move(DevParams P, SysView S, FusedArgs F)
     }
     else
     {
+      // every global load is issued before the first shared-memory store: in the resident server F itself lives in shared memory, and
+      // a store the compiler cannot tell apart from F would otherwise order the loads one after the other (one L2 round trip each)
       const int npool = F.kind == GBF_IDSWAP ? 2 + no + (F.ms2 > 1 ? F.norient : 0) : F.ntrials + no + (F.kind == GBF_REINSERTION ? 1 + no : 0);
-      for(int i = threadIdx.x; i < 3 * npool; i += 32) sm.pool[i] = F.pool3[3 * F.pool_off + i];
-      if((int) threadIdx.x < ms)
+      const CompView Cv = F.C, Cv2 = F.C2;
+      const int kind = F.kind, ms2 = F.ms2, i = threadIdx.x;
+      const long long mol = F.molecule;
+      const double* pool_src = F.pool3 + 3 * F.pool_off;
+      double pv[7]; int np = 0;                       // 3 * npool <= 3 * 129 entries over 32 lanes: at most 13 per lane, 7 in the common case
+      const int n3 = 3 * npool;
+      for(int k = i; k < n3 && np < 7; k += 32) pv[np++] = pool_src[k];
+      double t[6] = {0, 0, 0, 0, 0, 0}, x[6] = {0, 0, 0, 0, 0, 0}, t2[3] = {0, 0, 0}; int tt = 0, xt = 0;
+      const bool has_t = i < ms, has_x = has_t && kind != GBF_INSERTION && kind != GBF_IDSWAP, has_x2 = kind == GBF_IDSWAP && i < ms2;
+      if(has_t) { t[0] = Cv.x[i]; t[1] = Cv.y[i]; t[2] = Cv.z[i]; t[3] = Cv.q[i]; t[4] = Cv.scale[i]; t[5] = Cv.scoul[i]; tt = Cv.type[i]; }
+      if(has_x) { const long long j = mol * ms + i; x[0] = Cv.x[j]; x[1] = Cv.y[j]; x[2] = Cv.z[j]; x[3] = Cv.q[j]; x[4] = Cv.scale[j]; x[5] = Cv.scoul[j]; xt = Cv.type[j]; }
+      if(has_x2)
       {
-        const int i = threadIdx.x;
-        sm.tmpl.a[0][i] = F.C.x[i]; sm.tmpl.a[1][i] = F.C.y[i]; sm.tmpl.a[2][i] = F.C.z[i];
-        sm.tmpl.a[6][i] = F.C.q[i]; sm.tmpl.a[7][i] = F.C.scale[i]; sm.tmpl.a[8][i] = F.C.scoul[i]; sm.tmpl.type[i] = F.C.type[i];
-        if(F.kind != GBF_INSERTION && F.kind != GBF_IDSWAP)
-        {
-          const long long j = F.molecule * ms + i;
-          sm.exist.a[0][i] = F.C.x[j]; sm.exist.a[1][i] = F.C.y[j]; sm.exist.a[2][i] = F.C.z[j];
-          sm.exist.a[6][i] = F.C.q[j]; sm.exist.a[7][i] = F.C.scale[j]; sm.exist.a[8][i] = F.C.scoul[j]; sm.exist.type[i] = F.C.type[j];
-        }
+        const long long j = mol * ms2 + i;
+        x[0] = Cv2.x[j]; x[1] = Cv2.y[j]; x[2] = Cv2.z[j]; x[3] = Cv2.q[j]; x[4] = Cv2.scale[j]; x[5] = Cv2.scoul[j]; xt = Cv2.type[j];
+        t2[0] = Cv2.x[i]; t2[1] = Cv2.y[i]; t2[2] = Cv2.z[i];
       }
-      if(F.kind == GBF_IDSWAP && (int) threadIdx.x < F.ms2)
+      np = 0;
+      for(int k = i; k < n3 && np < 7; k += 32) sm.pool[k] = pv[np++];
+      for(int k = i + 7 * 32; k < n3; k += 32) sm.pool[k] = pool_src[k];
+      if(has_t)
       {
-        const int i = threadIdx.x; const long long j = F.molecule * F.ms2 + i;
-        sm.exist.a[0][i] = F.C2.x[j]; sm.exist.a[1][i] = F.C2.y[j]; sm.exist.a[2][i] = F.C2.z[j];
-        sm.exist.a[6][i] = F.C2.q[j]; sm.exist.a[7][i] = F.C2.scale[j]; sm.exist.a[8][i] = F.C2.scoul[j]; sm.exist.type[i] = F.C2.type[j];
-        sm.tmpl2.a[0][i] = F.C2.x[i]; sm.tmpl2.a[1][i] = F.C2.y[i]; sm.tmpl2.a[2][i] = F.C2.z[i];
-        to_frac(P, sm.exist.a[0][i], sm.exist.a[1][i], sm.exist.a[2][i], sm.exist.a[3][i], sm.exist.a[4][i], sm.exist.a[5][i]);
+        sm.tmpl.a[0][i] = t[0]; sm.tmpl.a[1][i] = t[1]; sm.tmpl.a[2][i] = t[2];
+        sm.tmpl.a[6][i] = t[3]; sm.tmpl.a[7][i] = t[4]; sm.tmpl.a[8][i] = t[5]; sm.tmpl.type[i] = tt;
+      }
+      if(has_x || has_x2)
+      {
+        sm.exist.a[0][i] = x[0]; sm.exist.a[1][i] = x[1]; sm.exist.a[2][i] = x[2];
+        sm.exist.a[6][i] = x[3]; sm.exist.a[7][i] = x[4]; sm.exist.a[8][i] = x[5]; sm.exist.type[i] = xt;
+      }
+      if(has_x2)
+      {
+        sm.tmpl2.a[0][i] = t2[0]; sm.tmpl2.a[1][i] = t2[1]; sm.tmpl2.a[2][i] = t2[2];
+        double f0, f1, f2; to_frac(P, x[0], x[1], x[2], f0, f1, f2);
+        sm.exist.a[3][i] = f0; sm.exist.a[4][i] = f1; sm.exist.a[5][i] = f2;
       }
     }
   }
   else
   {
-    if(!P.no_charges)          // without charges no pair ever evaluates erfc: one L2 round trip less in the prologue
+    if(!SRV && !P.no_charges)  // without charges no pair ever evaluates erfc: one L2 round trip less in the prologue
       for(int i = threadIdx.x - 32; i < (GBK_ERFC_DEG + 1) * GBK_ERFC_NINT; i += blockDim.x - 32) sm.etab[i] = __ldg(&P.erfc_tab[i]);
     if(threadIdx.x - 32 < 128) sm.res[threadIdx.x - 32] = 0.0;
   }
@@ -530,12 +589,12 @@ k_move(DevParams P, SysView S, FusedArgs F)
     StageSeg sg[1];
     sg[0].type = 0; sg[0].chain = 0; sg[0].n = F.ntrials; sg[0].pool_off = F.pool_off;
     int nsplit = stage_nsplit(F, F.ntrials);
-    run_stage(P, S, F, &sm, W, sg, 1, F.ntrials, nsplit, 0);
+    run_stage_d<SRV>(P, S, F, &sm, W, sg, 1, F.ntrials, nsplit, 0);
     // a single-bead molecule without a Fourier stage has nothing left that depends on the selection: only CTA 0 finishes the move
     if(ms == 1 && !F.do_ewald && blockIdx.x != 0) return;
-    collect_stage(F, &sm, reinterpret_cast<double*>(dyn), F.ntrials, nsplit, 0);
-    finish_segment(P, F, &sm, 0, false, F.ntrials, F.u0, 0.0, sm.E, sm.Fl, 0, 1.0);
-    adopt_selection(P, F, &sm, 0, false, F.pool_off, 0);
+    collect_stage_d<SRV>(F, &sm, reinterpret_cast<double*>(dyn), F.ntrials, nsplit, 0);
+    finish_segment_d<SRV>(P, F, &sm, 0, false, F.ntrials, F.u0, 0.0, sm.E, sm.Fl, 0, 1.0);
+    adopt_selection_d<SRV>(P, F, &sm, 0, false, F.pool_off, 0);
     bool alive = sm.res[13] != 0.0;
     if(ms > 1)
     {
@@ -543,19 +602,19 @@ k_move(DevParams P, SysView S, FusedArgs F)
       nsplit = stage_nsplit(F, no);
       if(alive)
       {
-        run_stage(P, S, F, &sm, W, sg, 1, no, nsplit, 1);
-        collect_stage(F, &sm, reinterpret_cast<double*>(dyn), no, nsplit, 1);
-        finish_segment(P, F, &sm, 0, true, no, F.u1, 0.0, sm.E, sm.Fl, 1, sm.res[14]);
-        adopt_selection(P, F, &sm, 0, true, F.pool_off + F.ntrials, 1);
+        run_stage_d<SRV>(P, S, F, &sm, W, sg, 1, no, nsplit, 1);
+        collect_stage_d<SRV>(F, &sm, reinterpret_cast<double*>(dyn), no, nsplit, 1);
+        finish_segment_d<SRV>(P, F, &sm, 0, true, no, F.u1, 0.0, sm.E, sm.Fl, 1, sm.res[14]);
+        adopt_selection_d<SRV>(P, F, &sm, 0, true, F.pool_off + F.ntrials, 1);
         alive = sm.res[16 + 13] != 0.0;
       }
     }
     double* ew = part_half(F, 0) + GBF_PART_EWALD;
-    if(F.do_ewald && alive) ewald_slice(P, F, dyn, sm.red, &sm.exist, 0, &sm.mN, ms, ew);
+    if(F.do_ewald && alive) ewald_slice_d<SRV>(P, F, dyn, sm.red, &sm.exist, 0, &sm.mN, ms, ew);
     if(blockIdx.x == 0)
     {
-      if(F.do_ewald) ewald_total_slot(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
-      export_molecule(F, sm.mN, GBK_BUF_GROWN);
+      if(F.do_ewald) ewald_total_slot_d<SRV>(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
+      export_molecule_d<SRV>(F, sm.mN, GBK_BUF_GROWN);
     }
   }
   else if(F.kind == GBF_DELETION)
@@ -566,24 +625,24 @@ k_move(DevParams P, SysView S, FusedArgs F)
     sg[1].type = 1; sg[1].chain = 1; sg[1].n = no; sg[1].pool_off = F.pool_off + F.ntrials;
     const int ngroups = F.ntrials + no;
     const int nsplit = stage_nsplit(F, ngroups);
-    run_stage(P, S, F, &sm, W, sg, ms > 1 ? 2 : 1, ngroups, nsplit, 0);
+    run_stage_d<SRV>(P, S, F, &sm, W, sg, ms > 1 ? 2 : 1, ngroups, nsplit, 0);
     double* ew = part_half(F, 0) + GBF_PART_EWALD;
-    if(F.do_ewald) ewald_slice(P, F, dyn, sm.red, &sm.exist, ms, &sm.mN, 0, ew);
+    if(F.do_ewald) ewald_slice_d<SRV>(P, F, dyn, sm.red, &sm.exist, ms, &sm.mN, 0, ew);
     if(blockIdx.x == 0)
     {
-      collect_stage(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
-      finish_segment(P, F, &sm, 1, false, F.ntrials, 0.0, 0.0, sm.E, sm.Fl, 0, 1.0);
+      collect_stage_d<SRV>(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
+      finish_segment_d<SRV>(P, F, &sm, 1, false, F.ntrials, 0.0, 0.0, sm.E, sm.Fl, 0, 1.0);
       bool alive = sm.res[13] != 0.0;
       if(ms > 1 && alive)
       {
-        finish_segment(P, F, &sm, 1, true, no, 0.0, 0.0, sm.E + 6 * F.ntrials, sm.Fl + F.ntrials, 1, sm.res[14]);
+        finish_segment_d<SRV>(P, F, &sm, 1, true, no, 0.0, 0.0, sm.E + 6 * F.ntrials, sm.Fl + F.ntrials, 1, sm.res[14]);
         alive = sm.res[16 + 13] != 0.0;
       }
       if(threadIdx.x == 0 && sm.res[9] != 0.0 && sm.res[11] > 0.0)
       {
         sm.res[6] = sm.exist.a[0][0]; sm.res[7] = sm.exist.a[1][0]; sm.res[8] = sm.exist.a[2][0];
       }
-      if(F.do_ewald) ewald_total_slot(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
+      if(F.do_ewald) ewald_total_slot_d<SRV>(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
     }
   }
   else if(F.kind == GBF_REINSERTION)
@@ -595,17 +654,17 @@ k_move(DevParams P, SysView S, FusedArgs F)
     sg[2].type = 3; sg[2].chain = 1; sg[2].n = no;        sg[2].pool_off = F.pool_off + F.ntrials + no + 1;
     const int ngroups = F.ntrials + 1 + no;
     int nsplit = stage_nsplit(F, ngroups);
-    run_stage(P, S, F, &sm, W, sg, ms > 1 ? 3 : 2, ngroups, nsplit, 0);
+    run_stage_d<SRV>(P, S, F, &sm, W, sg, ms > 1 ? 3 : 2, ngroups, nsplit, 0);
     if(ms == 1 && !F.do_ewald && blockIdx.x != 0) return;
-    collect_stage(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
+    collect_stage_d<SRV>(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
     if(blockIdx.x == 0)
     {
       if((int) threadIdx.x < 6 * (1 + no)) sm.Ekeep[threadIdx.x] = sm.E[6 * F.ntrials + threadIdx.x];
       if((int) threadIdx.x < 1 + no) sm.Fkeep[threadIdx.x] = sm.Fl[F.ntrials + threadIdx.x];
       __syncthreads();
     }
-    finish_segment(P, F, &sm, 2, false, F.ntrials, F.u0, 0.0, sm.E, sm.Fl, 0, 1.0);
-    adopt_selection(P, F, &sm, 2, false, F.pool_off, 0);
+    finish_segment_d<SRV>(P, F, &sm, 2, false, F.ntrials, F.u0, 0.0, sm.E, sm.Fl, 0, 1.0);
+    adopt_selection_d<SRV>(P, F, &sm, 2, false, F.pool_off, 0);
     bool alive = sm.res[13] != 0.0;
     int nl = 0;
     if(ms > 1)
@@ -615,30 +674,30 @@ k_move(DevParams P, SysView S, FusedArgs F)
       nsplit = stage_nsplit(F, no);
       if(alive)
       {
-        run_stage(P, S, F, &sm, W, sc, 1, no, nsplit, 1);
-        collect_stage(F, &sm, reinterpret_cast<double*>(dyn), no, nsplit, 1);
-        finish_segment(P, F, &sm, 2, true, no, F.u1, 0.0, sm.E, sm.Fl, 1, sm.res[14]);
-        adopt_selection(P, F, &sm, 2, true, F.pool_off + F.ntrials, 1);
+        run_stage_d<SRV>(P, S, F, &sm, W, sc, 1, no, nsplit, 1);
+        collect_stage_d<SRV>(F, &sm, reinterpret_cast<double*>(dyn), no, nsplit, 1);
+        finish_segment_d<SRV>(P, F, &sm, 2, true, no, F.u1, 0.0, sm.E, sm.Fl, 1, sm.res[14]);
+        adopt_selection_d<SRV>(P, F, &sm, 2, true, F.pool_off + F.ntrials, 1);
         alive = sm.res[16 + 13] != 0.0;
       }
       nl = 1;
     }
     double* ew = part_half(F, 0) + GBF_PART_EWALD;
-    if(F.do_ewald && alive) ewald_slice(P, F, dyn, sm.red, &sm.exist, ms, &sm.mN, ms, ew);
+    if(F.do_ewald && alive) ewald_slice_d<SRV>(P, F, dyn, sm.red, &sm.exist, ms, &sm.mN, ms, ew);
     if(blockIdx.x == 0)
     {
       if(alive)
       {
         // retrace: Rosenbluth weight of the old configuration, with the stored weights of the insertion's other trials
-        finish_segment(P, F, &sm, 3, false, 1, 0.0, sm.res[1], sm.Ekeep, sm.Fkeep, 2, 1.0);
+        finish_segment_d<SRV>(P, F, &sm, 3, false, 1, 0.0, sm.res[1], sm.Ekeep, sm.Fkeep, 2, 1.0);
         if(threadIdx.x == 0 && sm.res[32 + 9] != 0.0 && sm.res[32 + 11] > 0.0)
         {
           sm.res[32 + 6] = sm.exist.a[0][0]; sm.res[32 + 7] = sm.exist.a[1][0]; sm.res[32 + 8] = sm.exist.a[2][0];
         }
-        if(ms > 1) finish_segment(P, F, &sm, 3, true, no, 0.0, 0.0, sm.Ekeep + 6, sm.Fkeep + 1, 3, sm.res[16 * nl + 14]);
+        if(ms > 1) finish_segment_d<SRV>(P, F, &sm, 3, true, no, 0.0, 0.0, sm.Ekeep + 6, sm.Fkeep + 1, 3, sm.res[16 * nl + 14]);
       }
-      if(F.do_ewald) ewald_total_slot(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
-      export_molecule(F, sm.mN, GBK_BUF_TEMP);            // tempMolStorage, StoreNewLocation_Reinsertion
+      if(F.do_ewald) ewald_total_slot_d<SRV>(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
+      export_molecule_d<SRV>(F, sm.mN, GBK_BUF_TEMP);            // tempMolStorage, StoreNewLocation_Reinsertion
     }
   }
   else if(F.kind == GBF_IDSWAP)
@@ -656,39 +715,39 @@ k_move(DevParams P, SysView S, FusedArgs F)
     if(threadIdx.x == 0) { const AtomRec a = first_bead_atom(P, F, &sm, 4, 0, F.pool_off); put_atom(sm.mN, 0, a); }
     __syncthreads();
     const int nsplit = stage_nsplit(F, ngroups);
-    run_stage(P, S, F, &sm, W, sg, ns, ngroups, nsplit, 0);
+    run_stage_d<SRV>(P, S, F, &sm, W, sg, ns, ngroups, nsplit, 0);
     if(ms == 1 && F.ms2 == 1 && !F.do_ewald && blockIdx.x != 0) return;
-    collect_stage(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
-    finish_segment(P, F, &sm, 4, false, 1, 0.0, 0.0, sm.E, sm.Fl, 0, 1.0);
+    collect_stage_d<SRV>(F, &sm, reinterpret_cast<double*>(dyn), ngroups, nsplit, 0);
+    finish_segment_d<SRV>(P, F, &sm, 4, false, 1, 0.0, 0.0, sm.E, sm.Fl, 0, 1.0);
     if(threadIdx.x == 0 && sm.res[9] != 0.0) { sm.res[6] = sm.mN.a[0][0]; sm.res[7] = sm.mN.a[1][0]; sm.res[8] = sm.mN.a[2][0]; }
     __syncthreads();
     bool alive = sm.res[13] != 0.0;
     if(ms > 1 && alive)
     {
-      finish_segment(P, F, &sm, 4, true, no, F.u0, 0.0, sm.E + 6, sm.Fl + 1, 1, sm.res[14]);
-      adopt_selection(P, F, &sm, 4, true, off1, 1);
+      finish_segment_d<SRV>(P, F, &sm, 4, true, no, F.u0, 0.0, sm.E + 6, sm.Fl + 1, 1, sm.res[14]);
+      adopt_selection_d<SRV>(P, F, &sm, 4, true, off1, 1);
       alive = sm.res[16 + 13] != 0.0;
     }
     double* ew = part_half(F, 0) + GBF_PART_EWALD;
-    if(F.do_ewald && alive) ewald_slice(P, F, dyn, sm.red, &sm.exist, F.nold_ew, &sm.mN, F.nnew_ew, ew);
+    if(F.do_ewald && alive) ewald_slice_d<SRV>(P, F, dyn, sm.red, &sm.exist, F.nold_ew, &sm.mN, F.nnew_ew, ew);
     if(blockIdx.x == 0)
     {
       if(alive)
       {
         const int g2 = 1 + no;
-        finish_segment(P, F, &sm, 5, false, 1, 0.0, 0.0, sm.E + 6 * g2, sm.Fl + g2, 2, 1.0);
+        finish_segment_d<SRV>(P, F, &sm, 5, false, 1, 0.0, 0.0, sm.E + 6 * g2, sm.Fl + g2, 2, 1.0);
         if(threadIdx.x == 0 && sm.res[32 + 9] != 0.0) { sm.res[32 + 6] = sm.exist.a[0][0]; sm.res[32 + 7] = sm.exist.a[1][0]; sm.res[32 + 8] = sm.exist.a[2][0]; }
-        if(F.ms2 > 1) finish_segment(P, F, &sm, 5, true, no2, 0.0, 0.0, sm.E + 6 * (g2 + 1), sm.Fl + g2 + 1, 3, sm.res[32 + 14]);
+        if(F.ms2 > 1) finish_segment_d<SRV>(P, F, &sm, 5, true, no2, 0.0, 0.0, sm.E + 6 * (g2 + 1), sm.Fl + g2 + 1, 3, sm.res[32 + 14]);
       }
-      if(F.do_ewald) ewald_total_slot(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
-      export_molecule(F, sm.mN, GBK_BUF_TEMP);            // tempMolStorage: what gb_accept_identity_swap commits
+      if(F.do_ewald) ewald_total_slot_d<SRV>(F, &sm, reinterpret_cast<double*>(dyn), ew, alive);
+      export_molecule_d<SRV>(F, sm.mN, GBK_BUF_TEMP);            // tempMolStorage: what gb_accept_identity_swap commits
     }
   }
   else
   {
     // ---- translation / rotation: every CTA builds the proposal; items = (new | old) x atom slices; Ewald CTAs at the grid's end
     const int ne = F.do_ewald ? ewald_ctas(F) : 0;
-    const int npair = max(1, (int) gridDim.x - ne);          // CTAs that share the pair items
+    const int npair = max(1, F.ngrid - ne);          // CTAs that share the pair items
     const int nslice = max(1, min((F.natoms + 255) / 256, GBF_MAX_ITEMS / 2));
     const unsigned int tag0 = stage_tag(F.seq, 0);
     double* part = part_half(F, 0);
@@ -706,11 +765,11 @@ k_move(DevParams P, SysView S, FusedArgs F)
           sm.T.q[a] = M.a[6][a] * M.a[8][a]; sm.T.scale[a] = M.a[7][a]; sm.T.type[a] = M.type[a]; sm.T.slot[a] = 0;
         }
         __syncthreads();
-        group_energy<0>(P, W, S, F, &sm, (int) F.molecule, ms, slice, nslice, part + (size_t) w * 16, tag0);
+        group_energy0_d<SRV>(P, W, S, F, &sm, (int) F.molecule, ms, slice, nslice, part + (size_t) w * 16, tag0);
       }
     }
     double* ew = part + GBF_PART_EWALD;
-    if(F.do_ewald) ewald_slice(P, F, dyn, sm.red, &sm.mO, ms, &sm.mN, ms, ew);
+    if(F.do_ewald) ewald_slice_d<SRV>(P, F, dyn, sm.red, &sm.mO, ms, &sm.mN, ms, ew);
     if(blockIdx.x == 0)
     {
       // delta = sum(new) - sum(old) over the slices in fixed order (mc_single_particle.h:183-200); overlap of NEW only (:768-769)
@@ -736,8 +795,8 @@ k_move(DevParams P, SysView S, FusedArgs F)
         sm.res[16 * 5] = sS; sm.res[16 * 5 + 1] = 2.0 * cS;
       }
       __syncthreads();
-      export_molecule(F, sm.mN, GBK_BUF_NEW);
-      export_molecule(F, sm.mO, GBK_BUF_OLD);
+      export_molecule_d<SRV>(F, sm.mN, GBK_BUF_NEW);
+      export_molecule_d<SRV>(F, sm.mO, GBK_BUF_OLD);
     }
   }
   // publish: CTA 0 holds every result slot; it stores them to the host and then raises the sequence flag, so the host
@@ -758,10 +817,20 @@ k_move(DevParams P, SysView S, FusedArgs F)
   GBK_MARK();
   if(blockIdx.x == 0 && threadIdx.x == 0 && F.seq >= 20000 && F.seq < 20040)
   {
-    printf("kind %d grid %d:", F.kind, gridDim.x);
+    printf("kind %d grid %d:", F.kind, F.ngrid);
     for(int i = 1; i < g_nmarks; i++) printf(" %lld", g_marks[i] - g_marks[i - 1]);
     printf("\n");
   }
 #endif
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_move(DevParams P, SysView S, FusedArgs F)
+{
+  // dynamic shared memory: [FusedSmem | scratch: eik tables of the Ewald stage / stash of the collect steps (>= 12 KB)]
+  extern __shared__ __align__(128) unsigned char dyn_all[];
+  FusedSmem& sm = *reinterpret_cast<FusedSmem*>(dyn_all);
+  unsigned char* dyn = dyn_all + ((sizeof(FusedSmem) + 127) / 128) * 128;
+  move_body<false>(P, S, F, sm, dyn);
 }
 

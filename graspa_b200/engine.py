@@ -35,7 +35,7 @@ DECLARED_SYMBOLS = [
     "gb_accept_translation", "gb_accept_insertion", "gb_accept_deletion", "gb_accept_reinsertion", "gb_accept_identity_swap", "gb_append_molecule",
     "gb_number_of_molecules", "gb_total_vdw_real", "gb_total_ewald", "gb_volume_move_trial", "gb_volume_move_finish",
     "gb_widom_batch", "gb_widom_first_bead_success",
-    "gb_launch_count", "gb_timing_enable", "gb_timing_read", "gb_measure_fp64_peak",
+    "gb_launch_count", "gb_timing_enable", "gb_timing_read", "gb_move_server", "gb_measure_fp64_peak",
 ]
 
 
@@ -452,6 +452,12 @@ class Engine:
         ms = C.c_double(); n = C.c_int64()
         self._chk(self.lib.gb_timing_read(self.h, C.c_int32(family), C.byref(ms), C.byref(n), C.c_int32(int(reset))))
         return ms.value, n.value
+
+    def move_server(self, on=None):
+        """enable / disable the resident move server (None: leave as is); returns (server launches, moves it executed)"""
+        a = C.c_int64(); b = C.c_int64()
+        self._chk(self.lib.gb_move_server(self.h, C.c_int32(-1 if on is None else int(bool(on))), C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def measure_fp64_peak(self):
         t = C.c_double(); self._chk(self.lib.gb_measure_fp64_peak(self.h, C.byref(t))); return t.value

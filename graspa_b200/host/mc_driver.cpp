@@ -1362,15 +1362,16 @@ int main(int argc, char** argv)
     catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
     return 0;
   }
-  if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--timing] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
+  if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--no-server] [--timing] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
   const std::string dir = argv[1];
-  bool sequential_widom = false, staged = false, timing = false; const char* trace_path = nullptr; const char* restart_out = nullptr;
+  bool sequential_widom = false, staged = false, timing = false, no_server = false; const char* trace_path = nullptr; const char* restart_out = nullptr;
   long o_init = -1, o_equil = -1, o_prod = -1; double o_pressure = -1.0, o_temperature = -1.0; int o_device = -1; long o_seed = -1;
   for(int i = 2; i < argc; i++)
   {
     const std::string a = argv[i];
     if(a == "--sequential-widom") sequential_widom = true;
     else if(a == "--staged") staged = true;
+    else if(a == "--no-server") no_server = true;            // one k_move launch per move instead of the resident move server
     else if(a == "--timing") timing = true;
     else if(a == "--trace" && i + 1 < argc) trace_path = argv[++i];
     else if(a == "--init" && i + 1 < argc) o_init = std::atol(argv[++i]);
@@ -1424,6 +1425,7 @@ int main(int argc, char** argv)
   if(S2) { std::printf("--- box 1\n"); E0b = initial_state(*S2); SH.gibbs_total_volume = S.d.volume + S2->d.volume; }
 
   if(timing) GB(gb_timing_enable(S.e, 1));
+  if(no_server) { GB(gb_move_server(S.e, 0, nullptr, nullptr)); if(S2) GB(gb_move_server(S2->e, 0, nullptr, nullptr)); }
   const auto t0 = std::chrono::steady_clock::now();
   int wcomp = -1;
   const bool batched = !sequential_widom && widom_only(S, wcomp) && S.d.init_cycles == 0 && S.d.equil_cycles == 0;
@@ -1510,9 +1512,10 @@ int main(int argc, char** argv)
     std::printf("%s{\"component\": \"%s\", \"molecules\": %ld, \"production_average\": %.6f}", c > S.nhost ? ", " : "", comp_name(S, c), S.C[c].nmol,
                 S.C[c].load_n ? S.C[c].load_sum / (double) S.C[c].load_n : (double) S.C[c].nmol);
   std::printf("]}\n");
-  std::printf("{\"moves\": %ld, \"cycles\": %ld, \"seconds\": %.6f, \"moves_per_s\": %.3f, \"cycles_per_s\": %.3f, \"widom_path\": \"%s\", \"move_calls\": \"%s\", \"rng_draws\": %llu, \"pool_refills\": %ld, \"kernel_launches\": %lld}\n",
+  int64_t srv_starts = 0, srv_moves = 0; gb_move_server(S.e, -1, &srv_starts, &srv_moves);
+  std::printf("{\"moves\": %ld, \"cycles\": %ld, \"seconds\": %.6f, \"moves_per_s\": %.3f, \"cycles_per_s\": %.3f, \"widom_path\": \"%s\", \"move_calls\": \"%s\", \"rng_draws\": %llu, \"pool_refills\": %ld, \"kernel_launches\": %lld, \"server_starts\": %lld, \"server_moves\": %lld}\n",
               S.moves_done, cycles, secs, S.moves_done / secs, cycles / secs, batched ? "batched-exact" : "sequential", S.fused ? "fused" : "staged",
-              (unsigned long long) S.rng.consumed(), S.pool_rounds, (long long) launches);
+              (unsigned long long) S.rng.consumed(), S.pool_rounds, (long long) launches, (long long) srv_starts, (long long) srv_moves);
   if(S.fused)
   {
     const char* nm[5] = {"insertion", "deletion", "reinsertion", "translation/rotation", "identity swap"};

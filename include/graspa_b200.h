@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GB_ABI_VERSION 6
+#define GB_ABI_VERSION 7
 
 enum {
   GB_OK = 0,
@@ -372,6 +372,17 @@ int  gb_launch_count(gb_engine* e, int64_t* n, int32_t reset);
  * enabled first; a timed call synchronises the host after every timed group. */
 int  gb_timing_enable(gb_engine* e, int32_t on);
 int  gb_timing_read(gb_engine* e, int32_t family, double* ms, int64_t* launches, int32_t reset);
+/* The resident move server.  The gb_move_* calls do not launch a kernel per move: the first one starts ONE cooperative kernel (one
+ * CTA per SM) that stays resident and executes move after move from a mailbox in pinned host memory; the gb_accept_* calls queue
+ * their state change for the next move's command; gb_tail_*, gb_ewald_commit and gb_upload_random_pool run beside it; every other
+ * call stops it first (and it leaves by itself after GB_MOVE_SERVER_IDLE_MS, default 200, without a command), so the calling
+ * sequence of a driver does not change.  It replaces the per-move launches of the reference's move drivers (mc_swap_utilities.h:3-225,
+ * move_struct.h:186-406, mc_single_particle.h:123-241, mc_swap_moves.h:199-431: 3-6 launches + synchronisations per move).  Used only
+ * while one engine lives in the process (one engine per GPU) and the device supports cooperative launches; otherwise, with on = 0,
+ * or with GB_MOVE_SERVER=0 in the environment, every move is one k_move launch.  Results are bitwise identical either way.
+ * on: 1 / 0 = enable / disable (disabling stops a resident server), -1 = leave unchanged.  starts / commands (may be NULL):
+ * server launches and moves executed by it since the engine was created. */
+int  gb_move_server(gb_engine* e, int32_t on, int64_t* starts, int64_t* commands);
 /* FP64 FMA peak microbenchmark on this device: returns TFLOP/s (2 flop per DFMA) */
 int  gb_measure_fp64_peak(gb_engine* e, double* tflops);
 
