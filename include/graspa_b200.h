@@ -379,7 +379,9 @@ int  gb_timing_read(gb_engine* e, int32_t family, double* ms, int64_t* launches,
  * sequence of a driver does not change.  It replaces the per-move launches of the reference's move drivers (mc_swap_utilities.h:3-225,
  * move_struct.h:186-406, mc_single_particle.h:123-241, mc_swap_moves.h:199-431: 3-6 launches + synchronisations per move).  Used only
  * while one engine lives in the process (one engine per GPU) and the device supports cooperative launches; otherwise, with on = 0,
- * or with GB_MOVE_SERVER=0 in the environment, every move is one k_move launch.  Results are bitwise identical either way.
+ * or with GB_MOVE_SERVER=0 in the environment, every move is one k_move launch.  Decisions, selections and committed positions are the
+ * same either way; energies agree to rounding (<= 1e-12 relative: the server runs out-of-line copies of the stage routines, in which
+ * the compiler contracts a few multiply-adds differently).
  * on: 1 / 0 = enable / disable (disabling stops a resident server), -1 = leave unchanged.  starts / commands (may be NULL):
  * server launches and moves executed by it since the engine was created. */
 int  gb_move_server(gb_engine* e, int32_t on, int64_t* starts, int64_t* commands);
