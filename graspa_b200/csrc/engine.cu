@@ -109,6 +109,9 @@ struct gb_engine
   // cell-sorted Widom pair stage (widom_cells.cuh)
   DevBuf<double> wc_udelta, wc_e4, wc_fbres, wc_afx, wc_afy, wc_afz, wc_aq; DevBuf<double4> wc_srec;
   DevBuf<int> wc_ucell, wc_flag, wc_count, wc_off, wc_cursor, wc_items, wc_ctl, wc_atk;
+  // first-bead trial energies kept by gb_widom_first_bead_success for gb_widom_batch(resume_first_bead): indexed by pool row
+  DevBuf<double> fbk_e4; DevBuf<int> fbk_flag; bool fbk_valid = false; long long fbk_row0 = 0, fbk_rows = 0, fbk_serial = -1, pool_gen = 0, fbk_pool_gen = -1; int fbk_comp = -1;
+  long long call_serial = 0;             // entry points that went through ready() (Widom calls take themselves out again)
   bool wc_overflowed = false;            // a candidate list did not fit even with one CTA per SM: this engine keeps to k_widom_pair
   int wc_ctas_cap = 8, wc_last_ctas = 1; // CTAs per SM of the energy kernel: lowered (larger lists per CTA) when a list overflowed
   // CBMC
@@ -236,6 +239,7 @@ int ready(gb_engine* e)
   if(e->ncomp == 0) return fail(GB_ERR_STATE, "gb_set_components has not been called");
   for(int c = 0; c < e->ncomp; c++) if(!e->comps[c].uploaded) return fail(GB_ERR_STATE, "component " + std::to_string(c) + " has not been uploaded");
   CUDA_TRY(cudaSetDevice(e->device));
+  e->call_serial++;
   if((e->srv_running || !e->pending_commits.empty()) && e->srv_compat == 0) { int rc = server_stop(e); if(rc) return rc; }
   e->P.erfc_table_ok = (e->P.alpha * std::sqrt(e->P.cut_coul2) < GBK_ERFC_XMAX) ? 1 : 0;
   {
@@ -602,6 +606,7 @@ int gb_engine_destroy(gb_engine* e)
   e->d_ktab.release(); e->d_pool.release(); e->d_rec.release(); e->d_out8.release(); e->d_partial.release(); e->d_sums.release();
   e->d_uni.release(); e->d_scratch.release(); e->d_result.release(); e->d_stage.release(); e->d_iscratch.release();
   e->d_idx0.release(); e->d_idx1.release(); e->d_ticket.release(); e->d_mv.release(); e->d_mvi.release(); e->d_ewpos.release();
+  e->fbk_e4.release(); e->fbk_flag.release();
   e->wc_udelta.release(); e->wc_e4.release(); e->wc_fbres.release(); e->wc_afx.release(); e->wc_afy.release(); e->wc_afz.release(); e->wc_aq.release(); e->wc_srec.release();
   e->wc_ucell.release(); e->wc_flag.release(); e->wc_count.release(); e->wc_off.release(); e->wc_cursor.release(); e->wc_items.release(); e->wc_ctl.release(); e->wc_atk.release();
   e->d_vol_xyz.release(); e->d_vol_sf.release(); e->d_rowidx.release(); e->d_rowmeta.release(); e->d_round.release(); e->d_rtab.release();
@@ -967,7 +972,7 @@ int gb_upload_random_pool(gb_engine* e, const double* r3, int64_t n)
   CUDA_TRY(e->d_pool.reserve((size_t) n * 3));
   CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, r3, (size_t) n * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
-  e->n_pool = n;
+  e->n_pool = n; e->pool_gen++;
   return GB_OK;
 }
 
@@ -1343,7 +1348,7 @@ int gb_volume_move_finish(gb_engine* e, int32_t accept)
 // ins0 / n_total: this launch covers insertions [ins0, ins0 + n) of a batch of n_total (its inputs already point at ins0)
 static bool widom_cells_wanted(gb_engine* e, int comp, long long n_total);
 static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double* d_pool, const long long* d_fb, const long long* d_or, const double* d_uni,
-                               int first_bead_only, long long ins0, long long n_total);
+                               int first_bead_only, long long ins0, long long n_total, bool resume = false, bool keep = false);
 
 static int widom_stage_a(gb_engine* e, int comp, long long n, const double* d_pool, const long long* d_fb, const long long* d_or, const double* d_uni,
                          int first_bead_only, long long ins0 = 0, long long n_total = 0)
@@ -1392,7 +1397,7 @@ static int widom_stage_a(gb_engine* e, int comp, long long n, const double* d_po
 }
 
 // ---- cell-sorted pair stage (widom_cells.cuh): same inputs and the same rec / stage outputs as widom_stage_a
-static int widom_cells_grid(gb_engine* e, WcGrid& G);
+static int widom_cells_grid(gb_engine* e, WcGrid& G, long long n_trials = 0);
 static bool widom_cells_wanted(gb_engine* e, int comp, long long n_total)
 {
   const Comp& C = e->comps[comp];
@@ -1406,7 +1411,10 @@ static bool widom_cells_wanted(gb_engine* e, int comp, long long n_total)
   return n_total * (long long) e->ntrials >= 64LL * G.ncells;
 }
 
-static int widom_cells_grid(gb_engine* e, WcGrid& G)
+// Cells are 2 A wide (the measured optimum for large batches; fixed, so that an insertion's result does not depend on the size of the
+// batch it is in).  n_trials > 0 (the RNG-exact replay: the rows of the pool it walks through): a pool with fewer than 64 rows per
+// such cell gets wider cells, up to 4 A, so that a candidate list is still built for ~64 trial atoms
+static int widom_cells_grid(gb_engine* e, WcGrid& G, long long n_trials)
 {
   const double* H = e->P.cell;
   double h = 2.0;
@@ -1420,7 +1428,8 @@ static int widom_cells_grid(gb_engine* e, WcGrid& G)
       G.n[k] = std::max(1, (int) std::lround(len / h));
       nc *= G.n[k];
     }
-    if(nc <= 131072) { G.ncells = (int) nc; break; }
+    const bool sparse = n_trials > 0 && n_trials < 64 * nc && h < 4.0 && !std::getenv("GB_WC_H");
+    if(nc <= 131072 && !sparse) { G.ncells = (int) nc; break; }
     h *= 1.1;
   }
   G.rcell = 0.0;
@@ -1438,7 +1447,7 @@ static int widom_cells_grid(gb_engine* e, WcGrid& G)
 }
 
 static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double* d_pool, const long long* d_fb, const long long* d_or, const double* d_uni,
-                               int first_bead_only, long long ins0, long long n_total)
+                               int first_bead_only, long long ins0, long long n_total, bool resume, bool keep)
 {
   NvtxRange nvtx_stage("widom pair stage (cell-sorted)");
   const Comp& C = e->comps[comp];
@@ -1446,7 +1455,10 @@ static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double
   const int rec_stride = 5 + 3 * ms;
   if(n_total < ins0 + n) n_total = ins0 + n;
   if(ins0 == 0) { CUDA_TRY(e->d_rec.reserve((size_t) n_total * rec_stride)); CUDA_TRY(e->d_stage.reserve((size_t) n_total)); }
-  WcGrid G; int rc = widom_cells_grid(e, G); if(rc) return rc;
+  if(n_total < ins0 + n) n_total = ins0 + n;
+  // RNG-exact replay (kept / resumed first-bead energies): every row of the engine's pool is a trial position of the replay, whatever
+  // share of it this call or this GPU evaluates -- the grid follows the pool, so results do not depend on how the pool was cut
+  WcGrid G; int rc = widom_cells_grid(e, G, (resume || keep) ? e->n_pool : 0); if(rc) return rc;
   // ---- live atoms of every component, contiguous
   SegList L = seg_list(e, 0);
   int ntot = 0, nads = 0;
@@ -1510,21 +1522,30 @@ static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double
     return GB_OK;
   };
   Timer tm(e, 0);
-  // ---- first beads
-  CUDA_TRY(cudaMemsetAsync(e->wc_count.p, 0, ((size_t) G.ncells + 1) * sizeof(int), e->stream));
+  // ---- first beads (resume: their trial energies were kept, by pool row, by gb_widom_first_bead_success)
   if(ins0 == 0) CUDA_TRY(cudaMemsetAsync(e->wc_ctl.p + 2, 0, sizeof(int), e->stream));
-  WcGen Gn; Gn.pool3 = d_pool; Gn.fb_index = d_fb; Gn.n = n; Gn.ntrials = e->ntrials; Gn.norient = e->norient;
-  Gn.ucell = e->wc_ucell.p; Gn.udelta = e->wc_udelta.p; Gn.count = e->wc_count.p;
-  k_wc_gen_fb<<<(unsigned) ((nfb + 255) / 256), 256, 0, e->stream>>>(e->P, G, Gn);
-  e->launches++;
-  CUDA_TRY(cudaGetLastError());
-  rc = sort_and_energy(nfb, 1, 0); if(rc) return rc;
+  if(!resume)
+  {
+    CUDA_TRY(cudaMemsetAsync(e->wc_count.p, 0, ((size_t) G.ncells + 1) * sizeof(int), e->stream));
+    WcGen Gn; Gn.pool3 = d_pool; Gn.fb_index = d_fb; Gn.n = n; Gn.ntrials = e->ntrials; Gn.norient = e->norient;
+    Gn.ucell = e->wc_ucell.p; Gn.udelta = e->wc_udelta.p; Gn.count = e->wc_count.p;
+    k_wc_gen_fb<<<(unsigned) ((nfb + 255) / 256), 256, 0, e->stream>>>(e->P, G, Gn);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    rc = sort_and_energy(nfb, 1, 0); if(rc) return rc;
+    if(keep)
+    {
+      CUDA_TRY(e->fbk_e4.reserve((size_t) nfb * 4)); CUDA_TRY(e->fbk_flag.reserve((size_t) nfb));
+      CUDA_TRY(cudaMemcpyAsync(e->fbk_e4.p, e->wc_e4.p, (size_t) nfb * 4 * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(e->fbk_flag.p, e->wc_flag.p, (size_t) nfb * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
+    }
+  }
   // ---- first-bead selection + chain trial atoms
   WcSel S;
   S.pool3 = d_pool; S.fb_index = d_fb; S.or_index = d_or; S.uni = d_uni; S.n = n; S.ntrials = e->ntrials; S.norient = e->norient; S.ms = ms;
   S.tx = e->dx.p + C.offset; S.ty = e->dy.p + C.offset; S.tz = e->dz.p + C.offset;
   memset(&S.C, 0, sizeof(S.C)); S.C.pocket = C.d_pocket; S.C.npocket = C.npocket; S.C.pocket_invert = C.pocket_invert;
-  S.e4 = e->wc_e4.p; S.flag = e->wc_flag.p; S.fbres = e->wc_fbres.p;
+  S.e4 = resume ? e->fbk_e4.p - 4 * e->fbk_row0 : e->wc_e4.p; S.flag = resume ? e->fbk_flag.p - e->fbk_row0 : e->wc_flag.p; S.e4_by_row = resume ? 1 : 0; S.fbres = e->wc_fbres.p;
   S.rec = e->d_rec.p + (size_t) ins0 * rec_stride; S.stage = e->d_stage.p + ins0; S.first_bead_only = first_bead_only;
   S.ucell = e->wc_ucell.p; S.udelta = e->wc_udelta.p; S.count = e->wc_count.p;
   if(cs > 0 && !first_bead_only)
@@ -1538,29 +1559,55 @@ static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double
   if(cs > 0 && !first_bead_only)
   {
     rc = sort_and_energy(nch, cs, 1); if(rc) return rc;
+    S.e4 = e->wc_e4.p; S.flag = e->wc_flag.p; S.e4_by_row = 0;
     k_wc_select_chain<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, e->stream>>>(e->P, S);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
   }
-  tm.stop(first_bead_only || cs == 0 ? 6 : 10);
+  tm.stop(resume ? 5 : (first_bead_only || cs == 0 ? 6 : 10));
   return GB_OK;
 }
 
 int gb_widom_first_bead_success(gb_engine* e, int32_t comp, int64_t n, const double* pool3, int64_t n_pool, const int64_t* fb_index, int32_t* code)
 {
   int rc = ready(e); if(rc) return rc;
-  if(n <= 0 || !pool3 || !fb_index || !code) return fail(GB_ERR_ARG, "bad arguments");
+  e->call_serial--;                                            // a Widom call changes nothing of the system
+  if(n <= 0 || !fb_index || !code) return fail(GB_ERR_ARG, "bad arguments");
   if(comp < e->nhost || comp >= e->ncomp) return fail(GB_ERR_ARG, "Widom component must be an adsorbate component");
   if(!e->have_cbmc) return fail(GB_ERR_STATE, "gb_set_cbmc has not been called");
-  if(e->comps[comp].npocket > 0 && !widom_cells_wanted(e, comp, n)) return fail(GB_ERR_UNIMPLEMENTED, "block pockets need the cell-sorted Widom stage (unit scaling factors, molecules of <= 33 atoms)");
-  CUDA_TRY(e->d_pool.reserve((size_t) n_pool * 3));
-  CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, pool3, (size_t) n_pool * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  e->n_pool = n_pool;
+  if(!pool3 && e->n_pool <= 0) return fail(GB_ERR_STATE, "pool3 is NULL and gb_upload_random_pool has not been called");
+  // consecutive blocks in pool order (fb_index[k] = fb_index[0] + k * ntrials; a shard of the pool in a multi-GPU replay) on the engine's own pool: the per-trial energies can be kept by pool
+  // row for gb_widom_batch(resume_first_bead); that needs the cell-sorted stage, which is taken from 16 pool rows per 2 A cell on here
+  bool in_order = !pool3 && fb_index[0] % e->ntrials == 0;
+  for(int64_t k = 0; k < n && in_order; k++) in_order = fb_index[k] == fb_index[0] + k * (int64_t) e->ntrials;
+  WcGrid G; widom_cells_grid(e, G);
+  const Comp& C = e->comps[comp];
+  const bool keep = in_order && e->P.all_unit_scale && C.molsize <= 33 && !e->wc_overflowed && !std::getenv("GB_WIDOM_NO_RESUME") && e->n_pool >= 16LL * G.ncells;
+  const bool cells = keep || widom_cells_wanted(e, comp, n);
+  if(C.npocket > 0 && !cells) return fail(GB_ERR_UNIMPLEMENTED, "block pockets need the cell-sorted Widom stage (unit scaling factors, molecules of <= 33 atoms)");
+  e->fbk_valid = false;
+  if(pool3)
+  {
+    CUDA_TRY(e->d_pool.reserve((size_t) n_pool * 3));
+    CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, pool3, (size_t) n_pool * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    e->n_pool = n_pool; e->pool_gen++;
+  }
+  for(int64_t k = 0; k < n; k++) if(fb_index[k] < 0 || fb_index[k] + e->ntrials > e->n_pool) return fail(GB_ERR_ARG, "first-bead block outside the pool");
   CUDA_TRY(e->d_idx0.reserve((size_t) n));
   CUDA_TRY(cudaMemcpyAsync(e->d_idx0.p, fb_index, (size_t) n * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
-  rc = widom_stage_a(e, comp, n, e->d_pool.p, e->d_idx0.p, e->d_idx0.p, nullptr, 1); if(rc) return rc;
+  if(cells) rc = widom_stage_a_cells(e, comp, n, e->d_pool.p, e->d_idx0.p, e->d_idx0.p, nullptr, 1, 0, n, false, keep);
+  else      rc = widom_stage_a(e, comp, n, e->d_pool.p, e->d_idx0.p, e->d_idx0.p, nullptr, 1);
+  if(rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(code, e->d_stage.p, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  if(cells) CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<int*>(e->h_pinned + 12), e->wc_ctl.p + 2, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if(cells && *reinterpret_cast<int*>(e->h_pinned + 12) != 0)
+  {
+    // a candidate list overflowed its shared-memory capacity: again with larger lists (fewer CTAs per SM), in the end with the warp kernel
+    if(e->wc_last_ctas > 1) e->wc_ctas_cap = e->wc_last_ctas - 1; else e->wc_overflowed = true;
+    return gb_widom_first_bead_success(e, comp, n, pool3, n_pool, fb_index, code);
+  }
+  if(keep) { e->fbk_valid = true; e->fbk_row0 = fb_index[0]; e->fbk_rows = n * (long long) e->ntrials; e->fbk_comp = comp; e->fbk_pool_gen = e->pool_gen; e->fbk_serial = e->call_serial; }
   return GB_OK;
 }
 
@@ -1569,11 +1616,24 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
 {
   NvtxRange nvtx_call("gb_widom_batch");
   int rc = ready(e); if(rc) return rc;
-  if(!in || n <= 0 || !in->pool3 || !in->uniforms) return fail(GB_ERR_ARG, "bad Widom inputs");
+  e->call_serial--;                                            // a Widom call changes nothing of the system
+  if(!in || n <= 0 || !in->uniforms) return fail(GB_ERR_ARG, "bad Widom inputs");
+  const bool engine_pool = !in->pool3;
+  if(engine_pool && (in->inputs_on_device || e->n_pool <= 0)) return fail(GB_ERR_STATE, "pool3 is NULL: needs host inputs and a pool left by gb_upload_random_pool");
+  const bool resume = in->resume_first_bead != 0;
+  if(resume)
+  {
+    if(!engine_pool || !in->fb_index || !in->or_index) return fail(GB_ERR_ARG, "resume_first_bead needs pool3 == NULL and fb_index / or_index");
+    if(e->wc_overflowed) return fail(GB_ERR_STATE, "resume_first_bead: the cell-sorted stage is not available for this system (candidate lists overflow)");
+    if(!e->fbk_valid || e->fbk_comp != comp || e->fbk_pool_gen != e->pool_gen || e->fbk_serial != e->call_serial)
+      return fail(GB_ERR_STATE, "resume_first_bead: no valid first-bead energies (gb_widom_first_bead_success on this pool, nothing but Widom calls since)");
+    for(int64_t i = 0; i < n; i++)
+      if(in->fb_index[i] < e->fbk_row0 || in->fb_index[i] % e->ntrials != 0 || in->fb_index[i] + e->ntrials > e->fbk_row0 + e->fbk_rows) return fail(GB_ERR_ARG, "resume_first_bead: fb_index is not the start of an evaluated block");
+  }
   if(comp < e->nhost || comp >= e->ncomp) return fail(GB_ERR_ARG, "Widom component must be an adsorbate component");
   if(!e->have_cbmc) return fail(GB_ERR_STATE, "gb_set_cbmc has not been called");
   const Comp& C = e->comps[comp];
-  const bool cells = widom_cells_wanted(e, comp, n);
+  const bool cells = resume || widom_cells_wanted(e, comp, n);
   if(C.npocket > 0 && !cells) return fail(GB_ERR_UNIMPLEMENTED, "block pockets need the cell-sorted Widom stage (unit scaling factors, molecules of <= 33 atoms)");
   const int ms = C.molsize, cs = ms - 1;
   if(cs > GBK_MAX_CS) return fail(GB_ERR_ARG, "molecule too large for the CBMC chain stage");
@@ -1593,7 +1653,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   // host inputs in the packed layout and a batch worth pipelining: the randoms go up in chunks on a second stream while the pair
   // kernel already works on the chunks that have arrived (measured: 2-4 chunks are equivalent, 8 lose more in kernel tails than
   // they hide; default = a first chunk of n/8 and the rest, so that 7/8 of the 0.48 KB per insertion travel under compute)
-  const int nchunk = (!in->inputs_on_device && !in->fb_index && n >= 65536 && in->n_pool >= n * per && !std::getenv("GB_WIDOM_NO_OVERLAP")) ? (std::getenv("GB_WIDOM_CHUNKS") ? std::max(2, std::min(8, std::atoi(std::getenv("GB_WIDOM_CHUNKS")))) : 2) : 1;
+  const int nchunk = (!in->inputs_on_device && !engine_pool && !in->fb_index && n >= 65536 && in->n_pool >= n * per && !std::getenv("GB_WIDOM_NO_OVERLAP")) ? (std::getenv("GB_WIDOM_CHUNKS") ? std::max(2, std::min(8, std::atoi(std::getenv("GB_WIDOM_CHUNKS")))) : 2) : 1;
   if(nchunk > 1)
   {
     if(!e->copy_stream)
@@ -1602,7 +1662,7 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
       for(int c = 0; c < 8; c++) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_chunk[c], cudaEventDisableTiming));
     }
     CUDA_TRY(e->d_pool.reserve((size_t) in->n_pool * 3)); CUDA_TRY(e->d_uni.reserve((size_t) n * 2));
-    d_pool = e->d_pool.p; d_uni = e->d_uni.p;
+    d_pool = e->d_pool.p; d_uni = e->d_uni.p; e->n_pool = in->n_pool; e->pool_gen++;
     CUDA_TRY(cudaStreamSynchronize(e->stream));                      // nothing of an earlier call may still read the buffers
     long long c0[9];
     for(int c = 0; c <= nchunk; c++) c0[c] = (n * c / nchunk) / 32 * 32;
@@ -1625,8 +1685,12 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
   }
   else if(!in->inputs_on_device)
   {
-    CUDA_TRY(e->d_pool.reserve((size_t) in->n_pool * 3));
-    CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, in->pool3, (size_t) in->n_pool * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if(!engine_pool)
+    {
+      CUDA_TRY(e->d_pool.reserve((size_t) in->n_pool * 3));
+      CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, in->pool3, (size_t) in->n_pool * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+      e->n_pool = in->n_pool; e->pool_gen++;
+    }
     d_pool = e->d_pool.p;
     CUDA_TRY(e->d_uni.reserve((size_t) n * 2));
     CUDA_TRY(cudaMemcpyAsync(e->d_uni.p, in->uniforms, (size_t) n * 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
@@ -1639,10 +1703,11 @@ int gb_widom_batch(gb_engine* e, int32_t comp, int64_t n, const gb_widom_inputs*
       d_fb = e->d_idx0.p; d_or = e->d_idx1.p;
     }
   }
-  if(!in->fb_index && in->n_pool < n * per) return fail(GB_ERR_ARG, "random pool smaller than n*(trial positions+orientations)");
+  if(!in->fb_index && (engine_pool ? e->n_pool : in->n_pool) < n * per) return fail(GB_ERR_ARG, "random pool smaller than n*(trial positions+orientations)");
 
   // ---- stage A
-  if(nchunk == 1) { rc = widom_stage_a(e, comp, n, d_pool, d_fb, d_or, d_uni, 0); if(rc) return rc; }
+  if(resume) { rc = widom_stage_a_cells(e, comp, n, d_pool, d_fb, d_or, d_uni, 0, 0, n, true, false); if(rc) return rc; }
+  else if(nchunk == 1) { rc = widom_stage_a(e, comp, n, d_pool, d_fb, d_or, d_uni, 0); if(rc) return rc; }
   // ---- stage B
   rc = ensure_ktab(e); if(rc) return rc;
   const int warpsB = GBK_EWALD_THREADS / 32;

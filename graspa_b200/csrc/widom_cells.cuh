@@ -410,6 +410,7 @@ struct WcSel
   const double* __restrict__ tx; const double* __restrict__ ty; const double* __restrict__ tz;       // template molecule (Cartesian)
   CompView C;                                   // only the block-pocket fields are used
   const double* __restrict__ e4; const int* __restrict__ flag;
+  int e4_by_row;                                // 1: e4 / flag are indexed by pool row (kept by gb_widom_first_bead_success), 0: by insertion * ntrials
   double* fbres;                                // per insertion {W, HGv, HGr, GGv, GGr, x, y, z} of the selected first bead
   double* rec; int* stage;                      // as k_widom_pair leaves them for k_widom_ewald
   int first_bead_only;
@@ -432,8 +433,9 @@ k_wc_select_fb(DevParams P, WcGrid G, WcSel A)
   {
     const double* r = A.pool3 + 3 * (fb_off + lane);
     px = P.cell[0] * r[0]; py = P.cell[4] * r[1]; pz = P.cell[8] * r[2];
-    const double4 v = *reinterpret_cast<const double4*>(A.e4 + 4 * (ins * A.ntrials + lane));
-    e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w; fl = A.flag[ins * A.ntrials + lane];
+    const long long g = (A.e4_by_row ? fb_off : ins * A.ntrials) + lane;
+    const double4 v = *reinterpret_cast<const double4*>(A.e4 + 4 * g);
+    e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w; fl = A.flag[g];
   }
   if(A.C.npocket > 0)
   {

@@ -88,7 +88,8 @@ class GbMoveResult(C.Structure):
 class GbWidomInputs(C.Structure):
     _fields_ = [("pool3", C.c_void_p), ("n_pool", C.c_int64), ("fb_index", C.c_void_p), ("or_index", C.c_void_p),
                 ("uniforms", C.c_void_p), ("inputs_on_device", C.c_int32), ("n_blocks", C.c_int32),
-                ("global_first", C.c_int64), ("global_n", C.c_int64), ("sums_device", C.c_void_p)]
+                ("global_first", C.c_int64), ("global_n", C.c_int64), ("sums_device", C.c_void_p),
+                ("resume_first_bead", C.c_int32), ("reserved", C.c_int32)]
 
 
 class EngineError(RuntimeError):
@@ -387,11 +388,24 @@ class Engine:
         n = C.c_int64(); self._chk(self.lib.gb_number_of_molecules(self.h, C.c_int32(comp), C.byref(n))); return n.value
 
     # ------------------------------------------------------------ batched Widom
-    def widom_batch(self, comp, rnd, uni, fb_index=None, or_index=None, n_blocks=5, want_outputs=True, shard=(0, 0), d_sums=None):
-        """rnd: (n_pool, 3) double3 pool (host); uni: (n, 2).  Packed layout unless indices are given.
+    def widom_batch(self, comp, rnd, uni, fb_index=None, or_index=None, n_blocks=5, want_outputs=True, shard=(0, 0), d_sums=None, resume=False):
+        """rnd: (n_pool, 3) double3 pool (host), or None = the pool upload_random_pool left on the device; uni: (n, 2).  Packed layout
+        unless indices are given.  resume: start from the first-bead energies widom_first_bead_success(None, ...) kept.
         Returns (out8 (n,8) or None, stage (n,) or None, sums (n_blocks, 12))."""
-        rnd = np.ascontiguousarray(rnd, dtype=np.float64).reshape(-1, 3)
         uni = np.ascontiguousarray(uni, dtype=np.float64).reshape(-1, 2)
+        if rnd is None:
+            n = uni.shape[0]
+            fb = np.ascontiguousarray(fb_index, dtype=np.int64) if fb_index is not None else None
+            orr = np.ascontiguousarray(or_index, dtype=np.int64) if or_index is not None else None
+            inp = GbWidomInputs(None, 0, fb.ctypes.data if fb is not None else None, orr.ctypes.data if orr is not None else None,
+                                uni.ctypes.data, 0, n_blocks, int(shard[0]), int(shard[1]), d_sums, int(bool(resume)), 0)
+            out8 = np.zeros((n, 8)) if want_outputs else None
+            stage = np.zeros(n, dtype=np.int32) if want_outputs else None
+            sums = np.zeros((n_blocks, 12))
+            self._chk(self.lib.gb_widom_batch(self.h, C.c_int32(comp), C.c_int64(n), C.byref(inp), _p(out8, f64p), _p(stage, i32p),
+                                              C.c_int32(0), _p(sums, f64p)))
+            return out8, stage, sums
+        rnd = np.ascontiguousarray(rnd, dtype=np.float64).reshape(-1, 3)
         n = uni.shape[0]
         fb = np.ascontiguousarray(fb_index, dtype=np.int64) if fb_index is not None else None
         orr = np.ascontiguousarray(or_index, dtype=np.int64) if or_index is not None else None
@@ -403,6 +417,16 @@ class Engine:
         self._chk(self.lib.gb_widom_batch(self.h, C.c_int32(comp), C.c_int64(n), C.byref(inp), _p(out8, f64p), _p(stage, i32p),
                                           C.c_int32(0), _p(sums, f64p)))
         return out8, stage, sums
+
+    def widom_first_bead_success(self, comp, rnd, fb_index):
+        """first-bead classification of the pool blocks starting at fb_index (1 success, 0 failed with a survivor, 2 no survivor);
+        rnd None = the pool upload_random_pool left on the device"""
+        fb = np.ascontiguousarray(fb_index, dtype=np.int64); code = np.zeros(fb.shape[0], dtype=np.int32)
+        if rnd is not None:
+            rnd = np.ascontiguousarray(rnd, dtype=np.float64).reshape(-1, 3)
+        self._chk(self.lib.gb_widom_first_bead_success(self.h, C.c_int32(comp), C.c_int64(fb.shape[0]), _p(rnd, f64p) if rnd is not None else None,
+                                                       C.c_int64(rnd.shape[0] if rnd is not None else 0), _p(fb, i64p), _p(code, i32p)))
+        return code
 
     def widom_batch_device(self, comp, n, d_pool, n_pool, d_uni, n_blocks=5, d_out8=None, shard=(0, 0), d_sums=None, want_host_sums=True):
         """device-resident inputs (raw device pointers as ints, e.g. torch tensor.data_ptr()); d_sums: device pointer of n_blocks*12

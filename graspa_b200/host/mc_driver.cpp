@@ -30,6 +30,7 @@
 #include <string>
 #include <vector>
 #include <memory>
+#include <thread>
 
 namespace {
 
@@ -81,6 +82,9 @@ struct Shared
   std::FILE* trace = nullptr; long trace_lines = 0;   // one trace line per RunMoves call (moves that do nothing included)
   long moves_done = 0;
   std::vector<Sim*> boxes;
+  // --gpus N: replicas of box 0 on the other GPUs; the batched Widom replay cuts every pool into one share per engine (axpy.cu:163-186
+  // issues the insertions one by one; they are independent)
+  std::vector<gb_engine*> replicas;
   // Gibbs, data_struct.h:66-79
   MoveCount gibbs_vol_window, gibbs_vol_total, gibbs_xfer; double gibbs_max_change = 0.1, gibbs_total_volume = 0.0;
 };
@@ -107,6 +111,7 @@ struct Sim                                        // one simulation box
   int nblock = 5; long block_size = 1; bool production = false;
   int device = -1;                                // CUDA device of the engine (-1: the current one)
   bool fused = true;                              // one host round trip per move (gb_move_*); false: the stage calls
+  double widom_s[5] = {0, 0, 0, 0, 0};            // batched Widom replay: host seconds in {pool refill (rand + upload), classification, batch calls, averages, walk}
   double call_s[5] = {0, 0, 0, 0, 0}; long call_n[5] = {0, 0, 0, 0, 0};   // host time inside gb_move_{insertion,deletion,reinsertion,single_body,identity_swap}
 };
 
@@ -118,7 +123,12 @@ void pool_reset(Sim& S)                           // RandomNumber::ResetRandom
   S.pool_off = 0;
   for(size_t i = 0; i < S.pool_size; i++) { S.pool[3 * i] = S.rng.uniform(); S.pool[3 * i + 1] = S.rng.uniform(); S.pool[3 * i + 2] = S.rng.uniform(); }
   for(size_t i = S.pool_size * 3; i < 1000000; i++) S.rng.uniform();
-  for(Sim* b : S.sh.boxes) if(b->e) GB(gb_upload_random_pool(b->e, S.pool.data(), (int64_t) S.pool_size));     // every box reads the same pool
+  {
+    std::vector<std::thread> up;                           // the replicas' copies travel next to box 0's
+    for(gb_engine* r : S.sh.replicas) up.emplace_back([&S, r] { GB(gb_upload_random_pool(r, S.pool.data(), (int64_t) S.pool_size)); });
+    for(Sim* b : S.sh.boxes) if(b->e) GB(gb_upload_random_pool(b->e, S.pool.data(), (int64_t) S.pool_size));     // every box reads the same pool
+    for(auto& t : up) t.join();
+  }
   S.pool_rounds++;
 }
 inline void pool_check(Sim& S, size_t change) { if(S.pool_off + change >= S.pool_size) pool_reset(S); }
@@ -1002,15 +1012,46 @@ namespace {
 
 struct Queue { std::vector<int64_t> fb, orr; std::vector<double> uni; std::vector<long> cyc; };
 
-void flush_queue(Sim& S, int comp, const std::vector<double>& pool, Queue& Q)
+// the pool of the walk is the one pool_reset left on the device (gb_upload_random_pool): the Widom calls are told to use it
+// (pool3 = NULL) instead of receiving it again, and the batch resumes from the first-bead energies the classification pass kept
+// (resume_first_bead), so every first bead is evaluated once
+// shares of the pool blocks [0, ndec): engine g classifies -- and later resumes from -- blocks [ndec g / G, ndec (g + 1) / G)
+inline size_t share_begin(size_t ndec, size_t g, size_t G) { return ndec * g / G; }
+
+void flush_queue(Sim& S, int comp, Queue& Q, bool resume)
 {
   const size_t n = Q.fb.size();
   if(n == 0) return;
-  std::vector<double> out8(n * 8); std::vector<int32_t> stage(n); std::vector<double> sums(12);
-  gb_widom_inputs in; std::memset(&in, 0, sizeof(in));
-  in.pool3 = pool.data(); in.n_pool = (int64_t) (pool.size() / 3); in.fb_index = Q.fb.data(); in.or_index = Q.orr.data(); in.uniforms = Q.uni.data();
-  in.inputs_on_device = 0; in.n_blocks = 1;
-  GB(gb_widom_batch(S.e, comp, (int64_t) n, &in, out8.data(), stage.data(), 0, sums.data()));
+  static std::vector<double> out8; static std::vector<int32_t> stage;
+  out8.resize(n * 8); stage.resize(n);
+  std::vector<gb_engine*> eng{S.e}; eng.insert(eng.end(), S.sh.replicas.begin(), S.sh.replicas.end());
+  const size_t G = eng.size(), ntp = (size_t) S.d.n_trial_positions, ndec = S.pool_size / ntp;
+  // the queue is in pool order: the insertions whose first-bead block lies in engine g's share are one contiguous piece of it
+  std::vector<size_t> cut(G + 1, n);
+  cut[0] = 0;
+  for(size_t g = 1; g < G; g++)
+    cut[g] = (size_t) (std::lower_bound(Q.fb.begin(), Q.fb.end(), (int64_t) (share_begin(ndec, g, G) * ntp)) - Q.fb.begin());
+  auto piece = [&](size_t g)
+  {
+    const size_t a = cut[g], m = cut[g + 1] - cut[g];
+    if(m == 0) return;
+    double sums[12];
+    gb_widom_inputs in; std::memset(&in, 0, sizeof(in));
+    in.pool3 = nullptr; in.n_pool = 0; in.fb_index = Q.fb.data() + a; in.or_index = Q.orr.data() + a; in.uniforms = Q.uni.data() + 2 * a;
+    in.inputs_on_device = 0; in.n_blocks = 1; in.resume_first_bead = resume ? 1 : 0;
+    int rc = gb_widom_batch(eng[g], comp, (int64_t) m, &in, out8.data() + 8 * a, stage.data() + a, 0, sums);
+    if(rc == GB_ERR_STATE && resume) { in.resume_first_bead = 0; rc = gb_widom_batch(eng[g], comp, (int64_t) m, &in, out8.data() + 8 * a, stage.data() + a, 0, sums); }
+    GB(rc);
+  };
+  {
+    long dummy = 0; CallClock cc(S.widom_s[2], dummy);
+    std::vector<std::thread> th;
+    for(size_t g = 1; g < G; g++) th.emplace_back(piece, g);
+    piece(0);
+    for(auto& t : th) t.join();
+  }
+  long dummy2 = 0; CallClock cavg(S.widom_s[3], dummy2);
+  // the averages are taken on the host in cycle order, whatever the number of engines: the same sums to the last bit
   for(size_t i = 0; i < n; i++)
   {
     Energy E; const double* o = &out8[8 * i];
@@ -1032,12 +1073,24 @@ void run_widom_batched_v2(Sim& S, int comp, long cycles)
   S.block_size = std::max<long>(1, cycles / S.nblock);
   S.production = true;
   std::vector<int32_t> ok;
+  std::vector<int64_t> idx;
   auto classify = [&](const std::vector<double>& pool) {
+    (void) pool;                                                // already on every engine (pool_reset)
+    long dummy = 0; CallClock cc(S.widom_s[1], dummy);
     const size_t ndec = S.pool_size / ntp;
-    ok.assign(ndec, 0);
-    std::vector<int64_t> idx(ndec);
+    ok.assign(ndec, 0); idx.resize(ndec);
     for(size_t k = 0; k < ndec; k++) idx[k] = (int64_t) (k * ntp);
-    GB(gb_widom_first_bead_success(S.e, comp, (int64_t) ndec, pool.data(), (int64_t) S.pool_size, idx.data(), ok.data()));
+    std::vector<gb_engine*> eng{S.e}; eng.insert(eng.end(), S.sh.replicas.begin(), S.sh.replicas.end());
+    const size_t G = eng.size();
+    auto share = [&](size_t g)
+    {
+      const size_t a = share_begin(ndec, g, G), b = share_begin(ndec, g + 1, G);
+      if(b > a) GB(gb_widom_first_bead_success(eng[g], comp, (int64_t) (b - a), nullptr, 0, idx.data() + a, ok.data() + a));
+    };
+    std::vector<std::thread> th;
+    for(size_t g = 1; g < G; g++) th.emplace_back(share, g);
+    share(0);
+    for(auto& t : th) t.join();
   };
   classify(S.pool);
   Queue Q;
@@ -1049,7 +1102,7 @@ void run_widom_batched_v2(Sim& S, int comp, long cycles)
     S.rng.uniform(); S.rng.uniform();
     S.moves_done++;
     // first bead: Random.Check(ntp)
-    if(S.pool_off + ntp >= S.pool_size) { flush_queue(S, comp, S.pool, Q); pool_reset(S); classify(S.pool); }
+    if(S.pool_off + ntp >= S.pool_size) { flush_queue(S, comp, Q, true); { long dummy = 0; CallClock cc(S.widom_s[0], dummy); pool_reset(S); } classify(S.pool); }
     const size_t dfb = S.pool_off / ntp;
     S.pool_off += ntp;
     const double u1 = (ok[dfb] != 2) ? S.rng.uniform() : 0.5;   // SelectTrialPosition draws only when a trial survived (mc_widom.h:334-335)
@@ -1058,7 +1111,7 @@ void run_widom_batched_v2(Sim& S, int comp, long cycles)
     if(S.pool_off + ntp >= S.pool_size)
     {
       // the orientation block lies in the NEXT pool: finish this insertion with the stage calls (once per pool)
-      flush_queue(S, comp, S.pool, Q);
+      flush_queue(S, comp, Q, true);
       gb_cbmc_result r; int32_t used = 0; const double scale[2] = {1.0, 1.0};
       GB(gb_cbmc_first_bead(S.e, GB_CBMC_INSERTION, comp, 0, (int64_t) (dfb * ntp), u1, scale, 0.0, -1, -1, nullptr, &r, &used));
       double W = r.rosenbluth; Energy E; E.HGVDW = r.energy[0]; E.HGReal = r.energy[1]; E.GGVDW = r.energy[2]; E.GGReal = r.energy[3];
@@ -1084,7 +1137,7 @@ void run_widom_batched_v2(Sim& S, int comp, long cycles)
     const double u2 = S.rng.uniform();
     Q.fb.push_back((int64_t) (dfb * ntp)); Q.orr.push_back((int64_t) (dor * ntp)); Q.uni.push_back(u1); Q.uni.push_back(u2); Q.cyc.push_back(cycle);
   }
-  flush_queue(S, comp, S.pool, Q);
+  flush_queue(S, comp, Q, true);
 }
 
 void print_widom(Sim& S, int comp)
@@ -1362,10 +1415,10 @@ int main(int argc, char** argv)
     catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
     return 0;
   }
-  if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--no-server] [--timing] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
+  if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--no-server] [--gpus N] [--timing] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
   const std::string dir = argv[1];
   bool sequential_widom = false, staged = false, timing = false, no_server = false; const char* trace_path = nullptr; const char* restart_out = nullptr;
-  long o_init = -1, o_equil = -1, o_prod = -1; double o_pressure = -1.0, o_temperature = -1.0; int o_device = -1; long o_seed = -1;
+  long o_init = -1, o_equil = -1, o_prod = -1; double o_pressure = -1.0, o_temperature = -1.0; int o_device = -1, o_gpus = 1; long o_seed = -1;
   for(int i = 2; i < argc; i++)
   {
     const std::string a = argv[i];
@@ -1380,6 +1433,7 @@ int main(int argc, char** argv)
     else if(a == "--pressure" && i + 1 < argc) o_pressure = std::atof(argv[++i]);        // Pa: one isotherm point per process / GPU
     else if(a == "--temperature" && i + 1 < argc) o_temperature = std::atof(argv[++i]);
     else if(a == "--device" && i + 1 < argc) o_device = std::atoi(argv[++i]);
+    else if(a == "--gpus" && i + 1 < argc) o_gpus = std::atoi(argv[++i]);       // batched Widom replay: one share of every pool per GPU
     else if(a == "--seed" && i + 1 < argc) o_seed = std::atol(argv[++i]);
     else if(a == "--write-restart" && i + 1 < argc) restart_out = argv[++i];
   }
@@ -1395,6 +1449,17 @@ int main(int argc, char** argv)
   S.fused = !staged;
   setup_engine(S);
   setup_probabilities(S);
+  // --gpus N: replicas of the system on the next N - 1 devices (same deck, same uploads); only the batched Widom replay uses them
+  std::vector<std::unique_ptr<Shared>> replica_shared;
+  for(int g = 1; g < o_gpus; g++)
+  {
+    replica_shared.emplace_back(new Shared());
+    Sim R(*replica_shared.back());
+    R.d = S.d; R.device = std::max(o_device, 0) + g; R.fused = S.fused;
+    R.C.assign(1 + R.d.fw.size() + R.d.comps.size(), CompState());
+    setup_engine(R);
+    SH.replicas.push_back(R.e);
+  }
   // two boxes run together (NumberOfSimulations 2, SingleSimulation no): the Gibbs ensemble of the reference's examples
   std::unique_ptr<Sim> S2;
   if(S.d.n_simulations == 2 && !S.d.single_simulation)
@@ -1420,7 +1485,9 @@ int main(int argc, char** argv)
   // the very first trial position of a run comes from those three numbers.
   S.pool[0] = 2.3; S.pool[1] = 4.5; S.pool[2] = 6.7;
   for(Sim* b : SH.boxes) GB(gb_upload_random_pool(b->e, S.pool.data(), (int64_t) S.pool_size));
+  for(gb_engine* r : SH.replicas) GB(gb_upload_random_pool(r, S.pool.data(), (int64_t) S.pool_size));
   Energy E0 = initial_state(S);
+  for(gb_engine* r : SH.replicas) { gb_move_energy w; GB(gb_total_ewald(r, 1, &w)); }          // the stored structure factors of the Fourier stage
   Energy E0b;
   if(S2) { std::printf("--- box 1\n"); E0b = initial_state(*S2); SH.gibbs_total_volume = S.d.volume + S2->d.volume; }
 
@@ -1513,9 +1580,12 @@ int main(int argc, char** argv)
                 S.C[c].load_n ? S.C[c].load_sum / (double) S.C[c].load_n : (double) S.C[c].nmol);
   std::printf("]}\n");
   int64_t srv_starts = 0, srv_moves = 0; gb_move_server(S.e, -1, &srv_starts, &srv_moves);
-  std::printf("{\"moves\": %ld, \"cycles\": %ld, \"seconds\": %.6f, \"moves_per_s\": %.3f, \"cycles_per_s\": %.3f, \"widom_path\": \"%s\", \"move_calls\": \"%s\", \"rng_draws\": %llu, \"pool_refills\": %ld, \"kernel_launches\": %lld, \"server_starts\": %lld, \"server_moves\": %lld}\n",
+  std::printf("{\"moves\": %ld, \"cycles\": %ld, \"seconds\": %.6f, \"moves_per_s\": %.3f, \"cycles_per_s\": %.3f, \"widom_path\": \"%s\", \"move_calls\": \"%s\", \"rng_draws\": %llu, \"pool_refills\": %ld, \"kernel_launches\": %lld, \"server_starts\": %lld, \"server_moves\": %lld, \"gpus\": %d}\n",
               S.moves_done, cycles, secs, S.moves_done / secs, cycles / secs, batched ? "batched-exact" : "sequential", S.fused ? "fused" : "staged",
-              (unsigned long long) S.rng.consumed(), S.pool_rounds, (long long) launches, (long long) srv_starts, (long long) srv_moves);
+              (unsigned long long) S.rng.consumed(), S.pool_rounds, (long long) launches, (long long) srv_starts, (long long) srv_moves, 1 + (int) SH.replicas.size());
+  if(batched)
+    std::printf("batched Widom replay, host seconds: pool refills %.3f, first-bead classification %.3f, batch calls %.3f, averages %.3f, walk and the rest %.3f\n",
+                S.widom_s[0], S.widom_s[1], S.widom_s[2], S.widom_s[3], secs - S.widom_s[0] - S.widom_s[1] - S.widom_s[2] - S.widom_s[3]);
   if(S.fused)
   {
     const char* nm[5] = {"insertion", "deletion", "reinsertion", "translation/rotation", "identity swap"};
@@ -1532,6 +1602,7 @@ int main(int argc, char** argv)
   }
   if(S.trace) std::fclose(S.trace);
   if(S2) gb_engine_destroy(S2->e);
+  for(gb_engine* r : SH.replicas) gb_engine_destroy(r);
   gb_engine_destroy(S.e);
   return 0;
 }

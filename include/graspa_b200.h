@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GB_ABI_VERSION 7
+#define GB_ABI_VERSION 8
 
 enum {
   GB_OK = 0,
@@ -341,6 +341,13 @@ typedef struct {
    * evaluated in several calls accumulates there, and a multi-GPU run all-reduces from there (NCCL on the same stream, SURVEY
    * section 5) without staging through the host.  NULL: not used.  (ABI 6) */
   double* sums_device;
+  /* RNG-exact replay (ABI 8).  pool3 == NULL (inputs_on_device 0): the pool is the one gb_upload_random_pool left on the device -- no
+   * second upload.  resume_first_bead != 0: the first-bead trials of this batch were already evaluated by
+   * gb_widom_first_bead_success on that same pool (called with pool3 == NULL and consecutive blocks, fb_index[k] = fb_index[0] +
+   * k * n_trial_positions -- the whole pool, or this GPU's share of it; nothing but
+   * Widom calls since); their energies are still on the device, so the batch starts at the first-bead SELECTION: every first bead is
+   * evaluated once.  Every fb_index[i] must be the start of one of those blocks.  GB_ERR_STATE when the kept energies are not valid. */
+  int32_t resume_first_bead; int32_t reserved;
 } gb_widom_inputs;
 
 /* per insertion outputs (any may be NULL): out8[i*8 + {W, HGVDW, HGReal, GGVDW, GGReal, GGEwaldE, HGEwaldE, TailE}],
@@ -357,7 +364,9 @@ int  gb_widom_batch(gb_engine* e, int32_t component, int64_t n, const gb_widom_i
  * (>= 1 trial without overlap, Rosenbluth >= 1e-150), 0 it fails although a trial survived, 2 no trial survived.
  * This is what a host needs to replay the reference's random-number stream exactly for batched Widom insertions:
  * whether an insertion consumes its orientation block and its second uniform depends only on these codes
- * (mc_widom.h:332-341, mc_swap_utilities.h:19-27).  Host buffers. */
+ * (mc_widom.h:332-341, mc_swap_utilities.h:19-27).  Host buffers.  pool3 == NULL: the pool gb_upload_random_pool left on the device
+ * (n_pool ignored); with consecutive blocks (fb_index[k] = fb_index[0] + k * n_trial_positions) the per-trial energies stay on the device for a following
+ * gb_widom_batch(resume_first_bead). */
 int  gb_widom_first_bead_success(gb_engine* e, int32_t component, int64_t n, const double* pool3, int64_t n_pool,
                                  const int64_t* fb_index, int32_t* code);
 

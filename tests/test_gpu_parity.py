@@ -451,3 +451,60 @@ def test_widom_batch_honours_block_pockets(gpu_engine_factory):
         assert stage[i] == 0 and abs(out[i, 0] - W) <= 1e-9 * W, (i, out[i, 0], W)
     assert nfail > 10 and nfail < n
     eng.close()
+
+
+def test_widom_replay_resumes_from_the_kept_first_bead_energies(gpu_engine_factory):
+    """the RNG-exact replay of the host driver (mc_driver.cpp run_widom_batched_v2): every pool block is classified once
+    (gb_widom_first_bead_success on the pool gb_upload_random_pool left on the device), the walk pairs first-bead and orientation
+    blocks, and gb_widom_batch(resume_first_bead) starts from the kept first-bead energies.  Same insertions, to the bit, as a batch
+    that is handed the pool and evaluates its first beads itself; a call that may change the system in between invalidates the kept
+    energies (GB_ERR_STATE)."""
+    from graspa_b200.engine import EngineError
+    box, ff, s, z = load_config("A")
+    comp = int(z["comp"])
+    eng = gpu_engine_factory(box, ff, s, float(z["beta"]), 10, 10)
+    eng.upload_structure_factors(z["sf_ads"], z["sf_fw"]); eng.set_exclusion_constants(comp, float(z["excl"][0]), float(z["excl"][1]))
+    rng = np.random.default_rng(404)
+    nblk = 16000                                                       # 160 000 first-bead trials: >= 16 per cell of config A, the kept-energies path
+    pool = rng.random((nblk * 10, 3)); eng.upload_random_pool(pool)
+    blocks = np.arange(nblk, dtype=np.int64) * 10
+    code = eng.widom_first_bead_success(comp, None, blocks)
+    ref_code = eng.widom_first_bead_success(comp, pool, blocks)          # handed the pool: nothing is kept
+    assert np.array_equal(code, ref_code) and (code == 1).sum() > nblk // 4
+    with pytest.raises(EngineError):
+        eng.widom_batch(comp, None, np.full((1, 2), 0.5), fb_index=[0], or_index=[10], resume=True)
+    eng.upload_random_pool(pool)
+    code = eng.widom_first_bead_success(comp, None, blocks)
+    # the driver's walk: a successful first bead consumes the next block as its orientation block
+    fb, orr, k = [], [], 0
+    while k + 1 < nblk:
+        if code[k] == 1:
+            fb.append(k * 10); orr.append((k + 1) * 10); k += 2
+        else:
+            fb.append(k * 10); orr.append(k * 10); k += 1
+    uni = rng.random((len(fb), 2))
+    o1, s1, m1 = eng.widom_batch(comp, None, uni, fb_index=fb, or_index=orr, n_blocks=1, resume=True)
+    o2, s2, m2 = eng.widom_batch(comp, None, uni, fb_index=fb, or_index=orr, n_blocks=1, resume=True)       # nothing but Widom calls since: still valid
+    o0, s0, m0 = eng.widom_batch(comp, pool, uni, fb_index=fb, or_index=orr, n_blocks=1)
+    assert np.array_equal(s1, s0) and np.array_equal(s2, s0)
+    assert (s0 == 0).sum() > len(fb) // 8
+    # the unresumed batch of this size takes the warp-per-insertion kernel (another summation order; the replay's cells also follow
+    # the pool: wider than 2 A for this small one): same selections, energies to rounding; the replay itself is bitwise repeatable
+    esc = np.abs(o0[:, 1:]).sum(axis=1, keepdims=True) + 1e-3
+    assert np.max(np.abs(o1[:, 1:] - o0[:, 1:]) / esc) < 1e-11 and rel_err(o1[s0 == 0][:, 0], o0[s0 == 0][:, 0], floor=1e-290) < 1e-10
+    assert np.array_equal(o1, o2) and np.array_equal(m1, m2)
+    # a GPU that holds only a share of the pool's blocks (the multi-GPU replay): the same bits for the insertions of that share
+    half = nblk // 2
+    eng.upload_random_pool(pool)
+    code_h = eng.widom_first_bead_success(comp, None, blocks[half:])
+    assert np.array_equal(code_h, code[half:])
+    first = int(np.searchsorted(np.asarray(fb), half * 10))
+    oh, sh, mh = eng.widom_batch(comp, None, uni[first:], fb_index=fb[first:], or_index=orr[first:], n_blocks=1, resume=True)
+    assert np.array_equal(oh, o1[first:]) and np.array_equal(sh, s1[first:])
+    with pytest.raises(EngineError):                                   # a first bead outside the share this engine classified
+        eng.widom_batch(comp, None, uni[:4], fb_index=fb[:4], or_index=orr[:4], n_blocks=1, resume=True)
+    o0, s0, m0 = eng.widom_batch(comp, pool, uni, fb_index=fb, or_index=orr, n_blocks=1)
+    # the explicit pool replaced the engine's: the kept energies belong to another pool generation
+    with pytest.raises(EngineError):
+        eng.widom_batch(comp, None, uni, fb_index=fb, or_index=orr, n_blocks=1, resume=True)
+    eng.close()
