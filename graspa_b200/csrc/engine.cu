@@ -999,6 +999,9 @@ int gb_number_of_molecules(gb_engine* e, int32_t c, int64_t* n)
 }
 
 // ---------------------------------------------------------------------------------------------- trial energies
+static int widom_cells_grid(gb_engine* e, WcGrid& G, long long n_trials);
+static int trial_energies_cells(gb_engine* e, long long ntr, int cs, const TrialBuf& B, const double* d_tq, const int* d_ttype, double* d_out6, int* d_flag, bool* done);
+
 int gb_trial_energies(gb_engine* e, int32_t ntr, int32_t cs, const double* pos, const double* scale, const double* charge,
                       const double* scale_coul, const uint64_t* type, int32_t new_comp, int64_t new_molid,
                       int32_t excl_comp, int64_t excl_mol, double* out_energy, int32_t* out_flag)
@@ -1025,11 +1028,30 @@ int gb_trial_energies(gb_engine* e, int32_t ntr, int32_t cs, const double* pos, 
   TrialBuf B; B.fx = e->d_scratch.p; B.fy = B.fx + n; B.fz = B.fy + n; B.q = B.fz + n; B.scale = B.q + n; B.type = e->d_iscratch.p;
   double* d_out = e->d_scratch.p + n * 5; int* d_flag = e->d_iscratch.p + n;
   SegList L = seg_list(e, 0);
-  Timer tm(e, 0);
-  k_trial_energies<<<ntr, 256, 0, e->stream>>>(e->P, sys_view(e), L, B, cs, new_comp, (int) new_molid, excl_comp, (int) excl_mol, d_out, d_flag);
-  e->launches++;
-  CUDA_TRY(cudaGetLastError());
-  tm.stop(1);
+  // a large batch of equal groups of an adsorbate molecule that excludes nothing of the system (trial insertions): the cell-sorted
+  // energy kernel of the Widom stage (from 64 trial atoms per 2 A cell on, like gb_widom_batch); otherwise one CTA per group
+  bool cells = false;
+  {
+    bool eligible = e->P.all_unit_scale && !e->wc_overflowed && cs <= 33 && excl_comp < 0 && (new_comp < 0 || new_comp >= e->nhost) && !std::getenv("GB_TRIAL_NO_CELLS");
+    if(eligible && new_comp >= 0 && new_comp < e->ncomp) eligible = new_molid < 0 || new_molid >= e->comps[new_comp].natoms / std::max(1, e->comps[new_comp].molsize);
+    if(eligible) { WcGrid G; widom_cells_grid(e, G, 0); eligible = (long long) n >= 64LL * G.ncells; }
+    for(size_t i = 0; i < n && eligible; i++) eligible = h[4 * n + i] == 1.0 && h[3 * n + i] == h[3 * n + i % cs] && ht[i] == ht[i % cs];
+    // a candidate list that overflows its shared-memory capacity: again with fewer CTAs per SM (larger lists), like gb_widom_batch
+    while(eligible && !cells && !e->wc_overflowed)
+    {
+      Timer tm(e, 0);
+      rc = trial_energies_cells(e, ntr, cs, B, B.q, B.type, d_out, d_flag, &cells); if(rc) return rc;
+      if(cells) tm.stop(6);
+    }
+  }
+  if(!cells)
+  {
+    Timer tm(e, 0);
+    k_trial_energies<<<ntr, 256, 0, e->stream>>>(e->P, sys_view(e), L, B, cs, new_comp, (int) new_molid, excl_comp, (int) excl_mol, d_out, d_flag);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    tm.stop(1);
+  }
   std::vector<double> o((size_t) ntr * 6);
   CUDA_TRY(cudaMemcpyAsync(o.data(), d_out, o.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaMemcpyAsync(out_flag, d_flag, ntr * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
@@ -1446,6 +1468,118 @@ static int widom_cells_grid(gb_engine* e, WcGrid& G, long long n_trials)
   return GB_OK;
 }
 
+// what one pass of the cell-sorted energy kernel needs: the grid, the live atoms gathered contiguously, the launch shape with the
+// capacities of the candidate lists, and buffers for nmax trial atoms.  The caller fills in the trial atoms' template (E.tq, E.tscoul,
+// E.ttype, E.ms), bins its trial atoms (wc_ucell / wc_udelta / wc_count) and calls wc_sort_and_energy.
+struct WcPlan { WcGrid G; WcEnergy E; int mode = 1, ctas = 4, thrE = 192, gridE = 0, nads = 0; size_t smemE = 0; };
+
+static int wc_plan(gb_engine* e, long long grid_basis, long long nmax, WcPlan& W)
+{
+  WcGrid& G = W.G;
+  int rc = widom_cells_grid(e, G, grid_basis); if(rc) return rc;
+  // ---- live atoms of every component, contiguous
+  SegList L = seg_list(e, 0);
+  int ntot = 0, nads = 0;
+  for(int s = 0; s < L.nseg; s++) { ntot += L.count[s]; if(L.kind[s] == 2) nads += L.count[s]; }
+  W.nads = nads;
+  const size_t na = (size_t) std::max(ntot, 1);
+  CUDA_TRY(e->wc_afx.reserve(na)); CUDA_TRY(e->wc_afy.reserve(na)); CUDA_TRY(e->wc_afz.reserve(na)); CUDA_TRY(e->wc_aq.reserve(na)); CUDA_TRY(e->wc_atk.reserve(na));
+  if(ntot > 0)
+  {
+    k_wc_pack<<<(ntot + 255) / 256, 256, 0, e->stream>>>(sys_view(e), L, ntot, e->wc_afx.p, e->wc_afy.p, e->wc_afz.p, e->wc_aq.p, e->wc_atk.p);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  // ---- launch shape, capacities and shared memory of the energy kernel
+  // mode 1 (default): a lane per trial atom, several small CTAs per SM, each with the lists of its own cell;
+  // mode 0: a warp per trial atom, one large CTA per SM
+  int& mode = W.mode; int& ctas = W.ctas; int& thrE = W.thrE;
+  mode = 1; ctas = 4; thrE = 192;
+  if(const char* env = std::getenv("GB_WC_MODE")) mode = std::atoi(env) ? 1 : 0;
+  if(mode == 0) { ctas = 1; thrE = 768; }
+  if(mode == 1 && e->wc_ctas_cap < 4) thrE = 256;
+  if(const char* env = std::getenv("GB_WC_CTAS")) ctas = std::max(1, std::min(mode ? 6 : 1, std::atoi(env)));
+  ctas = std::max(1, std::min(ctas, e->wc_ctas_cap));
+  e->wc_last_ctas = ctas;
+  if(const char* env = std::getenv("GB_WC_THREADS")) thrE = std::min(mode ? 256 : 768, std::max(64, std::atoi(env) / 32 * 32));
+  const bool stage_ff = e->ntypes <= 24;
+  const size_t budget = std::min(e->smem_optin, (size_t) (e->prop.sharedMemPerMultiprocessor / ctas) - 1024 - 128);
+  G.cap_fast = std::min((std::max(ntot, 32) + 1) & ~1, 2304); G.cap_slow = std::min((std::max(ntot, 32) + 1) & ~1, 768);
+  while(wc_energy_smem(e->ntypes, stage_ff, G.cap_fast, G.cap_slow) > budget && G.cap_fast > 256) { G.cap_fast -= 64; G.cap_slow = std::max(128, G.cap_slow - 16); }
+  W.smemE = wc_energy_smem(e->ntypes, stage_ff, G.cap_fast, G.cap_slow);
+  if(W.smemE > e->smem_optin) return fail(GB_ERR_ARG, "cell-sorted Widom stage: shared memory exceeds the device limit");
+  if(mode == 1 && !std::getenv("GB_WC_CHUNK")) G.chunk = 32 * (thrE / 32) * 4;
+  // ---- buffers
+  CUDA_TRY(e->wc_ucell.reserve((size_t) nmax)); CUDA_TRY(e->wc_udelta.reserve((size_t) nmax * 3)); CUDA_TRY(e->wc_srec.reserve((size_t) nmax));
+  CUDA_TRY(e->wc_e4.reserve((size_t) nmax * 4)); CUDA_TRY(e->wc_flag.reserve((size_t) nmax));
+  CUDA_TRY(e->wc_count.reserve((size_t) G.ncells + 1)); CUDA_TRY(e->wc_off.reserve((size_t) G.ncells + 1)); CUDA_TRY(e->wc_cursor.reserve((size_t) G.ncells + 1));
+  CUDA_TRY(e->wc_items.reserve(3 * ((size_t) G.ncells + (size_t) (nmax / G.chunk) + 2))); CUDA_TRY(e->wc_ctl.reserve(8));
+  WcEnergy& E = W.E;
+  memset(&E, 0, sizeof(E));
+  E.atoms.fx = e->wc_afx.p; E.atoms.fy = e->wc_afy.p; E.atoms.fz = e->wc_afz.p; E.atoms.q = e->wc_aq.p; E.atoms.tk = e->wc_atk.p; E.atoms.n = ntot;
+  E.srec = e->wc_srec.p; E.items = e->wc_items.p; E.ctl = e->wc_ctl.p;
+  E.stage_ff = stage_ff ? 1 : 0; E.e4 = e->wc_e4.p; E.flag = e->wc_flag.p; E.overflow = e->wc_ctl.p + 2;
+  W.gridE = e->prop.multiProcessorCount * ctas;
+  return GB_OK;
+}
+
+// counting sort of the binned trial atoms (wc_ucell / wc_udelta / wc_count) and the energy kernel over the cells
+static int wc_sort_and_energy(gb_engine* e, WcPlan& W, long long nitems_src, int amod, int abase)
+{
+  WcGrid& G = W.G; WcEnergy& E = W.E;
+  const int gridE = W.gridE, thrE = W.thrE; const size_t smemE = W.smemE;
+  k_wc_scan<<<1, 1024, 0, e->stream>>>(e->wc_count.p, G.ncells, G.chunk, e->wc_off.p, e->wc_cursor.p, e->wc_items.p, e->wc_ctl.p);
+  k_wc_scatter<<<(unsigned) ((nitems_src + 255) / 256), 256, 0, e->stream>>>(e->wc_ucell.p, e->wc_udelta.p, nitems_src, e->wc_off.p, e->wc_cursor.p, e->wc_srec.p);
+  E.amod = amod; E.abase = abase;
+  const bool gg = W.nads > 0;
+#define GBK_WC_LAUNCH(K) do { \
+    if(e->P.cell_mode == 2)      { if(gg) K<2, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<2, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } \
+    else if(e->P.cell_mode == 1) { if(gg) K<1, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<1, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } \
+    else                         { if(gg) K<0, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<0, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } } while(0)
+  {
+    Timer te(e, 3);
+    if(W.mode == 1) GBK_WC_LAUNCH(k_wc_energy_lt); else GBK_WC_LAUNCH(k_wc_energy);
+    te.stop(1);
+  }
+#undef GBK_WC_LAUNCH
+  e->launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  return GB_OK;
+}
+
+// gb_trial_energies for a large batch of equal trial groups with nothing of the system excluded: the trial atoms (fractional coordinates
+// in B) are binned into the cells and evaluated by the energy kernel of the Widom stage; d_out6 / d_flag as k_trial_energies leaves them.
+// *done = false (nothing launched) when the route does not apply or a candidate list overflowed.
+static int trial_energies_cells(gb_engine* e, long long ntr, int cs, const TrialBuf& B, const double* d_tq, const int* d_ttype, double* d_out6, int* d_flag, bool* done)
+{
+  *done = false;
+  const long long n = ntr * cs;
+  WcPlan W; int rc = wc_plan(e, 0, n, W); if(rc) return rc;
+  CUDA_TRY(e->d_uni.reserve(64));                                   // 64 ones: the scaleCoul column of the trial template
+  {
+    std::vector<double> ones(64, 1.0);
+    CUDA_TRY(cudaMemcpyAsync(e->d_uni.p, ones.data(), 64 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  }
+  W.E.tq = d_tq; W.E.tscoul = e->d_uni.p; W.E.ttype = d_ttype; W.E.ms = cs;
+  CUDA_TRY(cudaMemsetAsync(e->wc_count.p, 0, ((size_t) W.G.ncells + 1) * sizeof(int), e->stream));
+  CUDA_TRY(cudaMemsetAsync(e->wc_ctl.p + 2, 0, sizeof(int), e->stream));
+  k_wc_gen_explicit<<<(unsigned) ((n + 255) / 256), 256, 0, e->stream>>>(e->P, W.G, B.fx, B.fy, B.fz, n, e->wc_ucell.p, e->wc_udelta.p, e->wc_count.p);
+  e->launches++;
+  rc = wc_sort_and_energy(e, W, n, cs, 0); if(rc) return rc;
+  k_wc_sum_groups<<<(unsigned) ((ntr + 255) / 256), 256, 0, e->stream>>>(e->wc_e4.p, e->wc_flag.p, ntr, cs, d_out6, d_flag);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<int*>(e->h_pinned + 12), e->wc_ctl.p + 2, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if(*reinterpret_cast<int*>(e->h_pinned + 12) != 0)
+  {
+    if(e->wc_last_ctas > 1) e->wc_ctas_cap = e->wc_last_ctas - 1; else e->wc_overflowed = true;
+    return GB_OK;                                                   // the caller runs k_trial_energies instead
+  }
+  *done = true;
+  return GB_OK;
+}
+
 static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double* d_pool, const long long* d_fb, const long long* d_or, const double* d_uni,
                                int first_bead_only, long long ins0, long long n_total, bool resume, bool keep)
 {
@@ -1458,69 +1592,12 @@ static int widom_stage_a_cells(gb_engine* e, int comp, long long n, const double
   if(n_total < ins0 + n) n_total = ins0 + n;
   // RNG-exact replay (kept / resumed first-bead energies): every row of the engine's pool is a trial position of the replay, whatever
   // share of it this call or this GPU evaluates -- the grid follows the pool, so results do not depend on how the pool was cut
-  WcGrid G; int rc = widom_cells_grid(e, G, (resume || keep) ? e->n_pool : 0); if(rc) return rc;
-  // ---- live atoms of every component, contiguous
-  SegList L = seg_list(e, 0);
-  int ntot = 0, nads = 0;
-  for(int s = 0; s < L.nseg; s++) { ntot += L.count[s]; if(L.kind[s] == 2) nads += L.count[s]; }
-  const size_t na = (size_t) std::max(ntot, 1);
-  CUDA_TRY(e->wc_afx.reserve(na)); CUDA_TRY(e->wc_afy.reserve(na)); CUDA_TRY(e->wc_afz.reserve(na)); CUDA_TRY(e->wc_aq.reserve(na)); CUDA_TRY(e->wc_atk.reserve(na));
-  if(ntot > 0)
-  {
-    k_wc_pack<<<(ntot + 255) / 256, 256, 0, e->stream>>>(sys_view(e), L, ntot, e->wc_afx.p, e->wc_afy.p, e->wc_afz.p, e->wc_aq.p, e->wc_atk.p);
-    e->launches++;
-    CUDA_TRY(cudaGetLastError());
-  }
-  // ---- launch shape, capacities and shared memory of the energy kernel
-  // mode 1 (default): a lane per trial atom, several small CTAs per SM, each with the lists of its own cell;
-  // mode 0: a warp per trial atom, one large CTA per SM
-  int mode = 1, ctas = 4, thrE = 192;
-  if(const char* env = std::getenv("GB_WC_MODE")) mode = std::atoi(env) ? 1 : 0;
-  if(mode == 0) { ctas = 1; thrE = 768; }
-  if(mode == 1 && e->wc_ctas_cap < 4) thrE = 256;
-  if(const char* env = std::getenv("GB_WC_CTAS")) ctas = std::max(1, std::min(mode ? 6 : 1, std::atoi(env)));
-  ctas = std::max(1, std::min(ctas, e->wc_ctas_cap));
-  e->wc_last_ctas = ctas;
-  if(const char* env = std::getenv("GB_WC_THREADS")) thrE = std::min(mode ? 256 : 768, std::max(64, std::atoi(env) / 32 * 32));
-  const bool stage_ff = e->ntypes <= 24;
-  const size_t budget = std::min(e->smem_optin, (size_t) (e->prop.sharedMemPerMultiprocessor / ctas) - 1024 - 128);
-  G.cap_fast = std::min((std::max(ntot, 32) + 1) & ~1, 2304); G.cap_slow = std::min((std::max(ntot, 32) + 1) & ~1, 768);
-  while(wc_energy_smem(e->ntypes, stage_ff, G.cap_fast, G.cap_slow) > budget && G.cap_fast > 256) { G.cap_fast -= 64; G.cap_slow = std::max(128, G.cap_slow - 16); }
-  const size_t smemE = wc_energy_smem(e->ntypes, stage_ff, G.cap_fast, G.cap_slow);
-  if(smemE > e->smem_optin) return fail(GB_ERR_ARG, "cell-sorted Widom stage: shared memory exceeds the device limit");
-  if(mode == 1 && !std::getenv("GB_WC_CHUNK")) G.chunk = 32 * (thrE / 32) * 4;
-  // ---- buffers
   const long long nfb = n * e->ntrials, nch = n * (long long) e->norient * cs, nmax = std::max(nfb, nch);
-  CUDA_TRY(e->wc_ucell.reserve((size_t) nmax)); CUDA_TRY(e->wc_udelta.reserve((size_t) nmax * 3)); CUDA_TRY(e->wc_srec.reserve((size_t) nmax));
-  CUDA_TRY(e->wc_e4.reserve((size_t) nmax * 4)); CUDA_TRY(e->wc_flag.reserve((size_t) nmax)); CUDA_TRY(e->wc_fbres.reserve((size_t) n * 8));
-  CUDA_TRY(e->wc_count.reserve((size_t) G.ncells + 1)); CUDA_TRY(e->wc_off.reserve((size_t) G.ncells + 1)); CUDA_TRY(e->wc_cursor.reserve((size_t) G.ncells + 1));
-  CUDA_TRY(e->wc_items.reserve(3 * ((size_t) G.ncells + (size_t) (nmax / G.chunk) + 2))); CUDA_TRY(e->wc_ctl.reserve(8));
-  WcEnergy E;
-  E.atoms.fx = e->wc_afx.p; E.atoms.fy = e->wc_afy.p; E.atoms.fz = e->wc_afz.p; E.atoms.q = e->wc_aq.p; E.atoms.tk = e->wc_atk.p; E.atoms.n = ntot;
-  E.srec = e->wc_srec.p; E.items = e->wc_items.p; E.ctl = e->wc_ctl.p;
-  E.tq = e->dq.p + C.offset; E.tscoul = e->dscoul.p + C.offset; E.ttype = e->dtype.p + C.offset; E.ms = ms;
-  E.stage_ff = stage_ff ? 1 : 0; E.e4 = e->wc_e4.p; E.flag = e->wc_flag.p; E.overflow = e->wc_ctl.p + 2;
-  const int gridE = e->prop.multiProcessorCount * ctas;
-  auto sort_and_energy = [&](long long nitems_src, int amod, int abase) -> int
-  {
-    k_wc_scan<<<1, 1024, 0, e->stream>>>(e->wc_count.p, G.ncells, G.chunk, e->wc_off.p, e->wc_cursor.p, e->wc_items.p, e->wc_ctl.p);
-    k_wc_scatter<<<(unsigned) ((nitems_src + 255) / 256), 256, 0, e->stream>>>(e->wc_ucell.p, e->wc_udelta.p, nitems_src, e->wc_off.p, e->wc_cursor.p, e->wc_srec.p);
-    E.amod = amod; E.abase = abase;
-    const bool gg = nads > 0;
-#define GBK_WC_LAUNCH(K) do { \
-      if(e->P.cell_mode == 2)      { if(gg) K<2, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<2, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } \
-      else if(e->P.cell_mode == 1) { if(gg) K<1, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<1, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } \
-      else                         { if(gg) K<0, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<0, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } } while(0)
-    {
-      Timer te(e, 3);
-      if(mode == 1) GBK_WC_LAUNCH(k_wc_energy_lt); else GBK_WC_LAUNCH(k_wc_energy);
-      te.stop(1);
-    }
-#undef GBK_WC_LAUNCH
-    e->launches += 3;
-    CUDA_TRY(cudaGetLastError());
-    return GB_OK;
-  };
+  WcPlan W; int rc = wc_plan(e, (resume || keep) ? e->n_pool : 0, nmax, W); if(rc) return rc;
+  CUDA_TRY(e->wc_fbres.reserve((size_t) n * 8));
+  WcGrid& G = W.G;
+  W.E.tq = e->dq.p + C.offset; W.E.tscoul = e->dscoul.p + C.offset; W.E.ttype = e->dtype.p + C.offset; W.E.ms = ms;
+  auto sort_and_energy = [&](long long nitems_src, int amod, int abase) -> int { return wc_sort_and_energy(e, W, nitems_src, amod, abase); };
   Timer tm(e, 0);
   // ---- first beads (resume: their trial energies were kept, by pool row, by gb_widom_first_bead_success)
   if(ins0 == 0) CUDA_TRY(cudaMemsetAsync(e->wc_ctl.p + 2, 0, sizeof(int), e->stream));

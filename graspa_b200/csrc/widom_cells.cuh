@@ -401,6 +401,44 @@ template <int CELL, bool HAS_GG>
 __global__ void __launch_bounds__(256, 3)
 k_wc_energy_lt(DevParams P, WcGrid G, WcEnergy A) { wc_energy_body<CELL, HAS_GG, 1>(P, G, A); }
 
+// ---------------------------------------------------------------------------------------------- caller-supplied trial atoms
+// gb_trial_energies with a large batch of trial groups (every group the same molecule, unit scaling factors, nothing of the system
+// excluded): the trial atoms are binned like the Widom ones (fractional coordinates in, one thread per atom) and evaluated by the same
+// energy kernel; k_wc_sum_groups then adds the atoms of a group in atom order.
+__global__ void k_wc_gen_explicit(DevParams P, WcGrid G, const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz, long long n,
+                                  int* ucell, double* udelta, int* count)
+{
+  const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if(g >= n) return;
+  double a = fx[g], b = fy[g], c = fz[g];
+  a -= floor(a); b -= floor(b); c -= floor(c);
+  int ix = (int) (a * G.n[0]), iy = (int) (b * G.n[1]), iz = (int) (c * G.n[2]);
+  ix = min(max(ix, 0), G.n[0] - 1); iy = min(max(iy, 0), G.n[1] - 1); iz = min(max(iz, 0), G.n[2] - 1);
+  const double ex = a - ((double) ix + 0.5) * G.inv_n[0], ey = b - ((double) iy + 0.5) * G.inv_n[1], ez = c - ((double) iz + 0.5) * G.inv_n[2];
+  const int cell = (ix * G.n[1] + iy) * G.n[2] + iz;
+  ucell[g] = cell;
+  udelta[3 * g] = P.cell[0] * ex + P.cell[3] * ey + P.cell[6] * ez;
+  udelta[3 * g + 1] = P.cell[1] * ex + P.cell[4] * ey + P.cell[7] * ez;
+  udelta[3 * g + 2] = P.cell[2] * ex + P.cell[5] * ey + P.cell[8] * ez;
+  atomicAdd(&count[cell], 1);
+}
+
+// out6[t] = {0, 0, HGVDW, HGReal, GGVDW, GGReal} (the layout of k_trial_energies; host-host terms do not occur on this route), flag[t]
+__global__ void k_wc_sum_groups(const double* __restrict__ e4, const int* __restrict__ flag, long long ngroups, int cs, double* out6, int* out_flag)
+{
+  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if(t >= ngroups) return;
+  double s[4] = {0, 0, 0, 0}; int fl = 0;
+  for(int a = 0; a < cs; a++)
+  {
+    const double4 v = *reinterpret_cast<const double4*>(e4 + 4 * (t * cs + a));
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w; fl |= flag[t * cs + a];
+  }
+  double* o = out6 + 6 * t;
+  o[0] = 0.0; o[1] = 0.0; o[2] = s[0]; o[3] = s[1]; o[4] = s[2]; o[5] = s[3];
+  out_flag[t] = fl ? 1 : 0;
+}
+
 // ---------------------------------------------------------------------------------------------- selection stages
 struct WcSel
 {

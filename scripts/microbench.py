@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel microbenchmarks of SURVEY.md section 8(d), items 1 and 4, on one B200 through the C ABI:
 
-  1. pair kernel: framework of config A (2430 atoms), B (2304 + CO2), D (1216, no charges), E (3456); trial batches of
+  1. pair kernel: framework of config A (2430 atoms), B (2304 + CO2), C (NaX + movable Na+), D (1216, no charges), E (3456); trial batches of
      T in {10, 10^3, 10^5, 10^6} groups of 1 atom or of a 3-atom CO2; first-bead positions uniform in the cell, orientations from
      uniform randoms; seed 1234.  Device time by CUDA events on the engine's stream (gb_timing_read), algorithmic flops by
      SURVEY's count F = N_pairs (44 | 20) + 17 N_vdw + 9 N_coul + 2 N_in with the in-cutoff fractions the CPU oracle counts
@@ -9,7 +9,7 @@
   4. Fourier kernels: the Widom Fourier kernel per insertion and the single-move delta per call at the nvec of each charged
      config, 3 moved atoms (insertion) and 6 (translation: 3 old + 3 new).
 
-    python scripts/microbench.py > profiles/r1_microbench.json        (oracle/ is used as the counter of in-cutoff pairs only)
+    python scripts/microbench.py > profiles/r2_microbench.json        (oracle/ is used as the counter of in-cutoff pairs only)
 """
 import json
 import os
@@ -39,7 +39,7 @@ def main():
     rng = np.random.default_rng(1234)
     out = {"what": "SURVEY section 8(d) microbenchmarks", "pair": [], "fourier": []}
     peak = None
-    for name in ("A", "B", "D", "E"):
+    for name in ("A", "B", "C", "D", "E"):
         box, ff, s, z = load_config(name)
         comp = int(z["comp"]); ms = int(s.molsize[comp]); o = int(s.offsets[comp])
         eng = engine.Engine(0).setup(box, ff, s, float(z["beta"]), 10, 10)
@@ -71,6 +71,9 @@ def main():
                 npairs_s = float(cnt[0]); f_vdw = cnt[1] / npairs_s; f_coul = cnt[2] / npairs_s; f_in = cnt[3] / npairs_s
                 reps = 5 if T <= 100000 else 2
                 eng.trial_energies(T, cs, tr, comp, 10 ** 9)
+                l0 = eng.launch_count()
+                eng.trial_energies(T, cs, tr, comp, 10 ** 9)
+                route = "cell-sorted (k_wc_energy_lt)" if eng.launch_count() - l0 > 1 else "k_trial_energies"
                 eng.timing_read(0, reset=True)
                 t0 = time.perf_counter()
                 for _ in range(reps):
@@ -81,7 +84,7 @@ def main():
                 npairs = float(T) * cs * nsys
                 flops = npairs * (per_pair + 17.0 * f_vdw + 9.0 * f_coul + 2.0 * f_in)
                 out["pair"].append({"config": name, "system_atoms": nsys, "cell": "orthorhombic" if box.cubic else "triclinic", "charged": charged,
-                                    "kernel": "k_trial_energies (gb_trial_energies)", "trial_groups": T, "atoms_per_group": cs,
+                                    "kernel": "gb_trial_energies: " + route, "trial_groups": T, "atoms_per_group": cs,
                                     "device_ms": ms_dev, "call_ms_with_copies": wall * 1e3, "pairs_per_s": npairs / (ms_dev * 1e-3),
                                     "in_cutoff_fraction": {"vdw": f_vdw, "coulomb": f_coul}, "algorithmic_tflops": flops / (ms_dev * 1e-3) / 1e12,
                                     "frac_of_fp64_peak": flops / (ms_dev * 1e-3) / 1e12 / peak})

@@ -508,3 +508,33 @@ def test_widom_replay_resumes_from_the_kept_first_bead_energies(gpu_engine_facto
     with pytest.raises(EngineError):
         eng.widom_batch(comp, None, uni, fb_index=fb, or_index=orr, n_blocks=1, resume=True)
     eng.close()
+
+
+@pytest.mark.parametrize("name,ngroups", [("E", 280000), ("B", 120000), ("C", 150000)])
+def test_large_trial_batches_take_the_cell_sorted_kernel(gpu_engine_factory, monkeypatch, name, ngroups):
+    """gb_trial_energies with a batch of >= 64 trial atoms per 2 A cell (equal groups, nothing excluded) is evaluated by the cell-sorted
+    energy kernel of the Widom stage; same energies (to summation order) and the same overlap flags as one CTA per group"""
+    from graspa_b200.types import TrialAtoms
+    box, ff, s, z = load_config(name)
+    comp = int(z["comp"]); ms = int(s.molsize[comp]); o = int(s.offsets[comp])
+    eng = gpu_engine_factory(box, ff, s)
+    rng = np.random.default_rng(12)
+    cell = box.cell.reshape(3, 3)
+    tmpl = s.pos[o:o + ms] - s.pos[o]
+    first = rng.random((ngroups, 3)) @ cell
+    ang = rng.random(ngroups) * 2 * np.pi
+    R = np.zeros((ngroups, 3, 3)); R[:, 0, 0] = np.cos(ang); R[:, 0, 1] = -np.sin(ang); R[:, 1, 0] = np.sin(ang); R[:, 1, 1] = np.cos(ang); R[:, 2, 2] = 1.0
+    pos = (first[:, None, :] + np.einsum("nij,aj->nai", R, tmpl)).reshape(-1, 3)
+    tr = TrialAtoms(pos, np.tile(s.charge[o:o + ms], ngroups), np.tile(s.type[o:o + ms], ngroups))
+    n0 = eng.launch_count()
+    e1, f1 = eng.trial_energies(ngroups, ms, tr, comp, 10 ** 9)
+    assert eng.launch_count() - n0 >= 6                                  # pack, bin, scan, scatter, energy, group sums
+    monkeypatch.setenv("GB_TRIAL_NO_CELLS", "1")
+    n0 = eng.launch_count()
+    e0, f0 = eng.trial_energies(ngroups, ms, tr, comp, 10 ** 9)
+    assert eng.launch_count() - n0 == 1
+    assert np.array_equal(f0, f1) and (f0 == 0).sum() > ngroups // 20
+    ok = f0 == 0
+    assert np.max(np.abs(e1[ok] - e0[ok]) / _scale(e0[ok])) < 1e-11
+    assert not np.array_equal(e1[ok], e0[ok])
+    eng.close()
