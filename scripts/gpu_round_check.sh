@@ -14,6 +14,7 @@ for deck in "XeKr-Mixture 20000" "CO2-MFI 3000"; do
   set -- $deck
   D=$(mktemp -d /tmp/rc.XXXX); cp -r oracle/_ref/examples/$1/* $D/; chmod -R u+w $D
   ./graspa_b200/host/graspa_b200_mc $D --init $2 --equil 0 --prod 0 2>&1 | grep -E "cycles_per_s|host time" | tee -a gpurun_out/${R}_moves.log
+  ./graspa_b200/host/graspa_b200_mc $D --init $2 --equil 0 --prod 0 --no-server 2>&1 | grep -E "cycles_per_s|host time" | sed 's/^/[--no-server] /' | tee -a gpurun_out/${R}_moves.log
   ./graspa_b200/host/graspa_b200_mc $D --init $2 --equil 0 --prod 0 --timing 2>&1 | grep -E "device time" | tee -a gpurun_out/${R}_moves.log
   rm -rf $D
 done
@@ -28,5 +29,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_wi
   $NCUB --steps 1 --warmup 3 > gpurun_out/${R}_ncu_ewald.log 2>&1
 D=$(mktemp -d /tmp/rc.XXXX); cp -r oracle/_ref/examples/XeKr-Mixture/* $D/; chmod -R u+w $D
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_move -s 4000 -c 3 -o gpurun_out/prof_move_${R} -f \
-  graspa_b200/host/graspa_b200_mc $D --init 6000 --equil 0 --prod 0 > gpurun_out/${R}_ncu_move.log 2>&1
+  graspa_b200/host/graspa_b200_mc $D --init 6000 --equil 0 --prod 0 --no-server > gpurun_out/${R}_ncu_move.log 2>&1   # per-launch k_move: a resident kernel that waits for host commands cannot be replayed by ncu
 ls -la gpurun_out | tail -12
