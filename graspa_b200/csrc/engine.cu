@@ -79,7 +79,7 @@ struct gb_engine
   std::vector<Comp> comps;
   // tail-correction deltas already evaluated on the device, keyed by (count delta per type, N_pseudo per type): the delta is a
   // function of integer occupation numbers only, and a GCMC run revisits the same few hundred states over and over
-  std::map<std::vector<long long>, double> tail_memo;
+  std::map<std::vector<long long>, double> tail_memo; std::vector<long long> tail_key;
   int nslots = 0;
   // host staging of the slot arrays (authoritative until the first device-side commit)
   std::vector<double> hx, hy, hz, hq, hscale, hscoul; std::vector<int> htype, hmolid;
@@ -234,6 +234,9 @@ std::atomic<int> g_engines_alive{0};
 int ready(gb_engine* e)
 {
   if(!e) return fail(GB_ERR_ARG, "null engine");
+  // a server-compatible call while the move server is resident: everything below was checked when the server was started, and the call
+  // touches the device through the mailbox only (the few that launch something set the device themselves)
+  if(e->srv_running && e->srv_compat > 0) { e->call_serial++; return GB_OK; }
   if(!e->have_ff) return fail(GB_ERR_STATE, "gb_upload_forcefield has not been called");
   if(!e->have_box) return fail(GB_ERR_STATE, "gb_upload_box has not been called");
   if(e->ncomp == 0) return fail(GB_ERR_STATE, "gb_set_components has not been called");
@@ -445,6 +448,7 @@ __global__ void k_tail(int n, const long long* __restrict__ np, const int* __res
 int tail_device(gb_engine* e, const std::vector<int>* dcount, double* d_out)
 {
   const int n = e->ntypes;
+  CUDA_TRY(cudaSetDevice(e->device));
   if(!e->has_tail) { CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(double), e->stream)); return GB_OK; }
   CUDA_TRY(e->d_iscratch.reserve((size_t) n + 16));
   CUDA_TRY(e->d_idx0.reserve((size_t) n + 16));
@@ -459,9 +463,10 @@ int tail_device(gb_engine* e, const std::vector<int>* dcount, double* d_out)
 // tail delta for a change of `d` pseudo-atoms per type at the current occupation, evaluated by k_tail once per distinct state
 int tail_delta_memo(gb_engine* e, const std::vector<int>& d, double* out)
 {
-  std::vector<long long> key; key.reserve(2 * (size_t) e->ntypes);
-  for(int i = 0; i < e->ntypes; i++) key.push_back(d[i]);
-  for(int i = 0; i < e->ntypes; i++) key.push_back(e->npseudo[i]);
+  // the key is built in a buffer the engine keeps (a hit allocates nothing): moves of a GCMC run ask for the same few hundred states
+  std::vector<long long>& key = e->tail_key;
+  key.resize(2 * (size_t) e->ntypes);
+  for(int i = 0; i < e->ntypes; i++) { key[i] = d[i]; key[e->ntypes + i] = e->npseudo[i]; }
   auto it = e->tail_memo.find(key);
   if(it != e->tail_memo.end()) { *out = it->second; return GB_OK; }
   int rc = tail_device(e, &d, e->d_result.p + 8); if(rc) return rc;
@@ -469,7 +474,7 @@ int tail_delta_memo(gb_engine* e, const std::vector<int>& d, double* out)
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   *out = e->h_pinned[8];
   if(e->tail_memo.size() > 200000) e->tail_memo.clear();
-  e->tail_memo.emplace(std::move(key), *out);
+  e->tail_memo.emplace(key, *out);
   return GB_OK;
 }
 

@@ -26,6 +26,7 @@
 #include "move_kernels.cuh"
 
 enum { GBF_INSERTION = 0, GBF_DELETION = 1, GBF_REINSERTION = 2, GBF_SINGLE = 3, GBF_IDSWAP = 4, GBF_EXIT = 5 };
+#define GBF_TAIL_TYPES 16           // pseudo-atom types the in-kernel tail difference handles (more: the host asks the engine separately)
 #define GBF_MAX_GROUPS 96           // trial groups of one stage: ntrials + 1 + norient <= 65
 #define GBF_PART_HALF 4096          // doubles per parity half of MoveBufs::partial()
 #define GBF_MAX_DYN_SMEM (160 * 1024)
@@ -42,6 +43,11 @@ struct FusedArgs
   int kind, comp, ms, move_type;          // move_type: GB_TRANSLATION / GB_ROTATION / GB_SPECIAL_ROTATION for GBF_SINGLE
   int ngrid;                              // CTAs that take part in this move (= gridDim.x of a k_move launch; <= grid of the resident server)
   int ncommit; CommitOp commit[2];        // resident server only: commits of the previous accepted move, applied first
+  // tail-correction difference of the move (TailCorrectionDifference / TailCorrectionIdentitySwap, TailCorrection_Energy_Functions.h:36-113),
+  // evaluated by a warp of CTA 0 beside the first stage: tail_n pseudo-atom types (0: not asked for), their occupation numbers and
+  // the change the move would make; result in result slot 5, entry 2
+  int tail_n; int tail_np[GBF_TAIL_TYPES]; short tail_d[GBF_TAIL_TYPES];
+  const int* tail_use; const double* tail_e;
   long long molecule, pool_off;
   double u0, u1, scale0, scale1, maxc[3];
   int ntrials, norient, nmol;             // nmol = NumberOfMolecule_for_Component (MolID of an inserted molecule)
@@ -102,6 +108,7 @@ struct FusedSmem
   SmemMol tmpl2;                                            // identity swap: template of the OLD species (geometry of its retrace orientations)
   double pool[3 * (2 * 32 + 2 * 32 + 1)];                   // the random-pool entries this move consumes
   int blocked;                                              // block-pocket flag of the trial group being evaluated
+  double tailv[GBF_TAIL_TYPES * (GBF_TAIL_TYPES + 1) / 2];  // terms of the tail-correction difference, in (i, j >= i) order
 };
 
 // one segment of a stage: n trial groups of one CBMC type
@@ -493,6 +500,35 @@ template <bool SRV> __device__ __forceinline__ void export_molecule_d(const Fuse
 template <bool SRV> __device__ __forceinline__ void group_energy0_d(const DevParams& P, const PairTables& W, const SysView& S, const FusedArgs& F, FusedSmem* sm, int new_molid, int cs, int split, int nsplit, double* rec, unsigned int tag)
 { if(SRV) group_energy0_out(P, W, S, F, sm, new_molid, cs, split, nsplit, rec, tag); else group_energy<0>(P, W, S, F, sm, new_molid, cs, split, nsplit, rec, tag); }
 
+// Tail-correction difference by the last warp of CTA 0: the lanes evaluate the (i, j >= i) terms, lane 0 adds them in the reference's
+// loop order (a term that is not used adds an exact zero) and divides by the volume -- the arithmetic of k_tail, engine.cu.
+__device__ __forceinline__ void tail_delta_warp(const DevParams& P, const FusedArgs& F, FusedSmem& sm)
+{
+  const int lane = (int) lane_id(), n = F.tail_n, npair = n * (n + 1) / 2;
+  for(int k = lane; k < npair; k += 32)
+  {
+    int i = 0, rem = k;
+    while(rem >= n - i) { rem -= n - i; i++; }
+    const int j = i + rem;
+    double v = 0.0;
+    if(F.tail_use[i * n + j])
+    {
+      const int Ni = F.tail_np[i], Nj = F.tail_np[j], di = F.tail_d[i], dj = F.tail_d[j];
+      const int dN = Ni * dj + Nj * di + di * dj;
+      v = F.tail_e[i * n + j] * (double) dN;
+      if(i != j) v *= 2.0;
+    }
+    sm.tailv[k] = v;
+  }
+  __syncwarp();
+  if(lane == 0)
+  {
+    double T = 0.0;
+    for(int k = 0; k < npair; k++) T += sm.tailv[k];
+    sm.res[16 * 5 + 2] = T / P.volume;
+  }
+}
+
 // The whole move, run by every CTA with blockIdx.x < F.ngrid.  SRV = false: the body of one k_move launch (P, S, F are kernel
 // parameters).  SRV = true: one command of the resident server (k_move_server): F and S are shared-memory copies -- the compiler then
 // cannot route the loads of the (mutable) slot arrays through the non-coherent path -- and the erfc table is already staged.
@@ -581,6 +617,7 @@ __device__ __forceinline__ void move_body(const DevParams& P, const SysView& S, 
     sm.blocked = blk;
   }
   __syncthreads();
+  if(F.tail_n > 0 && blockIdx.x == 0 && threadIdx.x >= blockDim.x - 32) tail_delta_warp(P, F, sm);
   GBK_MARK();
   PairTables W; W.etab = sm.etab; W.ffp = P.ffA; W.unit = false;
 
