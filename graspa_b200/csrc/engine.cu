@@ -974,6 +974,9 @@ int gb_upload_random_pool(gb_engine* e, const double* r3, int64_t n)
 {
   if(!e || !r3 || n <= 0) return fail(GB_ERR_ARG, "bad pool");
   CUDA_TRY(cudaSetDevice(e->device));
+  // a refill of the same size runs beside the resident move server (a copy on the engine's stream); a LARGER pool frees the old
+  // buffer, and cudaFree waits for every kernel on the device: stop the server first
+  if(e->srv_running && (size_t) n * 3 > e->d_pool.cap) { int rc = server_stop(e); if(rc) return rc; }
   CUDA_TRY(e->d_pool.reserve((size_t) n * 3));
   CUDA_TRY(cudaMemcpyAsync(e->d_pool.p, r3, (size_t) n * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
