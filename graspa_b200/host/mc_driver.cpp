@@ -118,11 +118,17 @@ struct Sim                                        // one simulation box
 inline int comp_ms(const Sim& S, int c) { return c == 0 ? 0 : (c < S.nhost ? S.d.fw[c - 1].molsize : S.d.comps[c - S.nhost].ms()); }
 inline const char* comp_name(const Sim& S, int c) { return c == 0 ? S.d.framework_name.c_str() : (c < S.nhost ? S.d.fw[c - 1].name.c_str() : S.d.comps[c - S.nhost].name.c_str()); }
 
-void pool_reset(Sim& S)                           // RandomNumber::ResetRandom
+void pool_reset_host(Sim& S)                      // RandomNumber::ResetRandom, the host side: the next pool from the random stream
 {
   S.pool_off = 0;
   for(size_t i = 0; i < S.pool_size; i++) { S.pool[3 * i] = S.rng.uniform(); S.pool[3 * i + 1] = S.rng.uniform(); S.pool[3 * i + 2] = S.rng.uniform(); }
   for(size_t i = S.pool_size * 3; i < 1000000; i++) S.rng.uniform();
+  S.pool_rounds++;
+}
+
+void pool_reset(Sim& S)                           // ... and its copy to every engine
+{
+  pool_reset_host(S); S.pool_rounds--;
   {
     std::vector<std::thread> up;                           // the replicas' copies travel next to box 0's
     for(gb_engine* r : S.sh.replicas) up.emplace_back([&S, r] { GB(gb_upload_random_pool(r, S.pool.data(), (int64_t) S.pool_size)); });
@@ -1018,82 +1024,118 @@ struct Queue { std::vector<int64_t> fb, orr; std::vector<double> uni; std::vecto
 // shares of the pool blocks [0, ndec): engine g classifies -- and later resumes from -- blocks [ndec g / G, ndec (g + 1) / G)
 inline size_t share_begin(size_t ndec, size_t g, size_t G) { return ndec * g / G; }
 
-void flush_queue(Sim& S, int comp, Queue& Q, bool resume)
+// One lane of the replay: a set of engines (one per GPU) that holds ONE pool at a time -- upload, classify, (walk on the host), evaluate.
+// Two lanes alternate pools, so that the evaluation of pool k (a background thread) runs beside the generation, upload and
+// classification of pool k + 1 and the host's walk through it.
+struct WidomLane
 {
-  const size_t n = Q.fb.size();
+  std::vector<gb_engine*> eng;
+  Queue Q; std::vector<int32_t> ok; std::vector<int64_t> idx;
+  std::vector<double> out8; std::vector<int32_t> stage;
+  std::thread th; bool pending = false;
+};
+
+void lane_upload_pool(Sim& S, WidomLane& L)
+{
+  std::vector<std::thread> up;
+  for(size_t g = 1; g < L.eng.size(); g++) up.emplace_back([&S, &L, g] { GB(gb_upload_random_pool(L.eng[g], S.pool.data(), (int64_t) S.pool_size)); });
+  GB(gb_upload_random_pool(L.eng[0], S.pool.data(), (int64_t) S.pool_size));
+  for(auto& t : up) t.join();
+}
+
+// first-bead classification of every block of the pool the lane holds, one share per engine
+void lane_classify(Sim& S, int comp, WidomLane& L)
+{
+  long dummy = 0; CallClock cc(S.widom_s[1], dummy);
+  const size_t ntp = (size_t) S.d.n_trial_positions, ndec = S.pool_size / ntp, G = L.eng.size();
+  L.ok.assign(ndec, 0); L.idx.resize(ndec);
+  for(size_t k = 0; k < ndec; k++) L.idx[k] = (int64_t) (k * ntp);
+  auto share = [&](size_t g)
+  {
+    const size_t a = share_begin(ndec, g, G), b = share_begin(ndec, g + 1, G);
+    if(b > a) GB(gb_widom_first_bead_success(L.eng[g], comp, (int64_t) (b - a), nullptr, 0, L.idx.data() + a, L.ok.data() + a));
+  };
+  std::vector<std::thread> th;
+  for(size_t g = 1; g < G; g++) th.emplace_back(share, g);
+  share(0);
+  for(auto& t : th) t.join();
+}
+
+// the queued insertions of the lane's pool: the Widom calls use the pool the lane's engines hold (pool3 = NULL) and resume from the
+// first-bead energies the classification kept, so every first bead is evaluated once.  Touches nothing but the lane: may run in a thread.
+void lane_evaluate(Sim& S, int comp, WidomLane& L)
+{
+  const size_t n = L.Q.fb.size();
   if(n == 0) return;
-  static std::vector<double> out8; static std::vector<int32_t> stage;
-  out8.resize(n * 8); stage.resize(n);
-  std::vector<gb_engine*> eng{S.e}; eng.insert(eng.end(), S.sh.replicas.begin(), S.sh.replicas.end());
-  const size_t G = eng.size(), ntp = (size_t) S.d.n_trial_positions, ndec = S.pool_size / ntp;
+  L.out8.resize(n * 8); L.stage.resize(n);
+  const size_t G = L.eng.size(), ntp = (size_t) S.d.n_trial_positions, ndec = S.pool_size / ntp;
   // the queue is in pool order: the insertions whose first-bead block lies in engine g's share are one contiguous piece of it
   std::vector<size_t> cut(G + 1, n);
   cut[0] = 0;
   for(size_t g = 1; g < G; g++)
-    cut[g] = (size_t) (std::lower_bound(Q.fb.begin(), Q.fb.end(), (int64_t) (share_begin(ndec, g, G) * ntp)) - Q.fb.begin());
+    cut[g] = (size_t) (std::lower_bound(L.Q.fb.begin(), L.Q.fb.end(), (int64_t) (share_begin(ndec, g, G) * ntp)) - L.Q.fb.begin());
   auto piece = [&](size_t g)
   {
     const size_t a = cut[g], m = cut[g + 1] - cut[g];
     if(m == 0) return;
     double sums[12];
     gb_widom_inputs in; std::memset(&in, 0, sizeof(in));
-    in.pool3 = nullptr; in.n_pool = 0; in.fb_index = Q.fb.data() + a; in.or_index = Q.orr.data() + a; in.uniforms = Q.uni.data() + 2 * a;
-    in.inputs_on_device = 0; in.n_blocks = 1; in.resume_first_bead = resume ? 1 : 0;
-    int rc = gb_widom_batch(eng[g], comp, (int64_t) m, &in, out8.data() + 8 * a, stage.data() + a, 0, sums);
-    if(rc == GB_ERR_STATE && resume) { in.resume_first_bead = 0; rc = gb_widom_batch(eng[g], comp, (int64_t) m, &in, out8.data() + 8 * a, stage.data() + a, 0, sums); }
+    in.pool3 = nullptr; in.n_pool = 0; in.fb_index = L.Q.fb.data() + a; in.or_index = L.Q.orr.data() + a; in.uniforms = L.Q.uni.data() + 2 * a;
+    in.inputs_on_device = 0; in.n_blocks = 1; in.resume_first_bead = 1;
+    int rc = gb_widom_batch(L.eng[g], comp, (int64_t) m, &in, L.out8.data() + 8 * a, L.stage.data() + a, 0, sums);
+    if(rc == GB_ERR_STATE) { in.resume_first_bead = 0; rc = gb_widom_batch(L.eng[g], comp, (int64_t) m, &in, L.out8.data() + 8 * a, L.stage.data() + a, 0, sums); }
     GB(rc);
   };
-  {
-    long dummy = 0; CallClock cc(S.widom_s[2], dummy);
-    std::vector<std::thread> th;
-    for(size_t g = 1; g < G; g++) th.emplace_back(piece, g);
-    piece(0);
-    for(auto& t : th) t.join();
-  }
-  long dummy2 = 0; CallClock cavg(S.widom_s[3], dummy2);
-  // the averages are taken on the host in cycle order, whatever the number of engines: the same sums to the last bit
+  std::vector<std::thread> th;
+  for(size_t g = 1; g < G; g++) th.emplace_back(piece, g);
+  piece(0);
+  for(auto& t : th) t.join();
+}
+
+// the averages are taken on the host in cycle order, whatever the number of engines and lanes: the same sums to the last bit
+void lane_record(Sim& S, int comp, WidomLane& L)
+{
+  long dummy = 0; CallClock cc(S.widom_s[3], dummy);
+  const size_t n = L.Q.fb.size();
   for(size_t i = 0; i < n; i++)
   {
-    Energy E; const double* o = &out8[8 * i];
+    Energy E; const double* o = &L.out8[8 * i];
     E.HGVDW = o[1]; E.HGReal = o[2]; E.GGVDW = o[3]; E.GGReal = o[4]; E.GGEwald = o[5]; E.HGEwald = o[6]; E.Tail = o[7];
     S.C[comp].widom.total++;
-    if(stage[i] == 3)
+    if(L.stage[i] == 3)
     {
       std::fprintf(stderr, "graspa_b200_mc: a chain stage lost every orientation to the overlap criterion; the batched replay cannot know that in advance. Re-run with --sequential-widom.\n");
       std::exit(3);
     }
-    record_rosen(S, comp, stage[i] == 0 ? o[0] : 0.0, stage[i] == 0 ? E : Energy(), Q.cyc[i]);
+    record_rosen(S, comp, L.stage[i] == 0 ? o[0] : 0.0, L.stage[i] == 0 ? E : Energy(), L.Q.cyc[i]);
   }
-  Q.fb.clear(); Q.orr.clear(); Q.uni.clear(); Q.cyc.clear();
+  L.Q.fb.clear(); L.Q.orr.clear(); L.Q.uni.clear(); L.Q.cyc.clear();
 }
 
-void run_widom_batched_v2(Sim& S, int comp, long cycles)
+void lane_finish(Sim& S, int comp, WidomLane& L)               // wait for a background evaluation and book its results
+{
+  if(!L.pending) return;
+  { long dummy = 0; CallClock cc(S.widom_s[2], dummy); L.th.join(); }
+  L.pending = false;
+  lane_record(S, comp, L);
+}
+
+void run_widom_batched_v2(Sim& S, int comp, long cycles, std::vector<gb_engine*> second_lane)
 {
   const size_t ntp = (size_t) S.d.n_trial_positions;
   S.block_size = std::max<long>(1, cycles / S.nblock);
   S.production = true;
-  std::vector<int32_t> ok;
-  std::vector<int64_t> idx;
-  auto classify = [&](const std::vector<double>& pool) {
-    (void) pool;                                                // already on every engine (pool_reset)
-    long dummy = 0; CallClock cc(S.widom_s[1], dummy);
-    const size_t ndec = S.pool_size / ntp;
-    ok.assign(ndec, 0); idx.resize(ndec);
-    for(size_t k = 0; k < ndec; k++) idx[k] = (int64_t) (k * ntp);
-    std::vector<gb_engine*> eng{S.e}; eng.insert(eng.end(), S.sh.replicas.begin(), S.sh.replicas.end());
-    const size_t G = eng.size();
-    auto share = [&](size_t g)
-    {
-      const size_t a = share_begin(ndec, g, G), b = share_begin(ndec, g + 1, G);
-      if(b > a) GB(gb_widom_first_bead_success(eng[g], comp, (int64_t) (b - a), nullptr, 0, idx.data() + a, ok.data() + a));
-    };
-    std::vector<std::thread> th;
-    for(size_t g = 1; g < G; g++) th.emplace_back(share, g);
-    share(0);
-    for(auto& t : th) t.join();
+  WidomLane lanes[2];
+  lanes[0].eng.push_back(S.e); lanes[0].eng.insert(lanes[0].eng.end(), S.sh.replicas.begin(), S.sh.replicas.end());
+  lanes[1].eng = second_lane;
+  const bool two = !lanes[1].eng.empty();
+  int cur = 0;
+  lane_classify(S, comp, lanes[cur]);                           // the first pool is on every engine already
+  auto next_pool = [&](int lane)
+  {
+    { long dummy = 0; CallClock cc(S.widom_s[0], dummy); pool_reset_host(S); lane_upload_pool(S, lanes[lane]); }
+    lane_classify(S, comp, lanes[lane]);
   };
-  classify(S.pool);
-  Queue Q;
   for(long cycle = 0; cycle < cycles; cycle++)
   {
     // Select_Box_Component_Molecule
@@ -1102,42 +1144,62 @@ void run_widom_batched_v2(Sim& S, int comp, long cycles)
     S.rng.uniform(); S.rng.uniform();
     S.moves_done++;
     // first bead: Random.Check(ntp)
-    if(S.pool_off + ntp >= S.pool_size) { flush_queue(S, comp, Q, true); { long dummy = 0; CallClock cc(S.widom_s[0], dummy); pool_reset(S); } classify(S.pool); }
+    if(S.pool_off + ntp >= S.pool_size)
+    {
+      WidomLane& L = lanes[cur];
+      if(two)
+      {
+        // pool k is evaluated in the background by this lane while the other lane takes pool k + 1; the results of pool k - 1 are booked first
+        L.pending = true; L.th = std::thread([&S, comp, &L] { lane_evaluate(S, comp, L); });
+        cur = 1 - cur;
+        lane_finish(S, comp, lanes[cur]);
+      }
+      else { { long dummy = 0; CallClock cc(S.widom_s[2], dummy); lane_evaluate(S, comp, L); } lane_record(S, comp, L); }
+      next_pool(cur);
+    }
+    WidomLane& L = lanes[cur];
     const size_t dfb = S.pool_off / ntp;
     S.pool_off += ntp;
-    const double u1 = (ok[dfb] != 2) ? S.rng.uniform() : 0.5;   // SelectTrialPosition draws only when a trial survived (mc_widom.h:334-335)
-    if(ok[dfb] != 1) { Q.fb.push_back((int64_t) (dfb * ntp)); Q.orr.push_back((int64_t) (dfb * ntp)); Q.uni.push_back(u1); Q.uni.push_back(0.5); Q.cyc.push_back(cycle); continue; }
+    const double u1 = (L.ok[dfb] != 2) ? S.rng.uniform() : 0.5;   // SelectTrialPosition draws only when a trial survived (mc_widom.h:334-335)
+    if(L.ok[dfb] != 1) { L.Q.fb.push_back((int64_t) (dfb * ntp)); L.Q.orr.push_back((int64_t) (dfb * ntp)); L.Q.uni.push_back(u1); L.Q.uni.push_back(0.5); L.Q.cyc.push_back(cycle); continue; }
     // chain: Random.Check(nto)
     if(S.pool_off + ntp >= S.pool_size)
     {
-      // the orientation block lies in the NEXT pool: finish this insertion with the stage calls (once per pool)
-      flush_queue(S, comp, Q, true);
+      // the orientation block lies in the NEXT pool: finish this insertion with the stage calls (once per pool), on this lane's first
+      // engine, which then takes the next pool as well; everything queued so far is evaluated and booked first
+      lane_finish(S, comp, lanes[1 - cur]);
+      { long dummy = 0; CallClock cc(S.widom_s[2], dummy); lane_evaluate(S, comp, L); }
+      lane_record(S, comp, L);
+      gb_engine* e0 = L.eng[0];
       gb_cbmc_result r; int32_t used = 0; const double scale[2] = {1.0, 1.0};
-      GB(gb_cbmc_first_bead(S.e, GB_CBMC_INSERTION, comp, 0, (int64_t) (dfb * ntp), u1, scale, 0.0, -1, -1, nullptr, &r, &used));
+      GB(gb_cbmc_first_bead(e0, GB_CBMC_INSERTION, comp, 0, (int64_t) (dfb * ntp), u1, scale, 0.0, -1, -1, nullptr, &r, &used));
       double W = r.rosenbluth; Energy E; E.HGVDW = r.energy[0]; E.HGReal = r.energy[1]; E.GGVDW = r.energy[2]; E.GGReal = r.energy[3];
-      pool_reset(S); classify(S.pool);
-      GB(gb_cbmc_chain(S.e, GB_CBMC_INSERTION, comp, 0, 0, S.rng.peek(0), -1, -1, &r, &used));
+      { long dummy = 0; CallClock cc(S.widom_s[0], dummy); pool_reset_host(S); lane_upload_pool(S, L); }
+      GB(gb_cbmc_chain(e0, GB_CBMC_INSERTION, comp, 0, 0, S.rng.peek(0), -1, -1, &r, &used));
       S.pool_off += ntp; S.rng.advance(used);
       bool good = r.success != 0; W *= r.rosenbluth; if(W <= 1e-150) good = false;
       E.HGVDW += r.energy[0]; E.HGReal += r.energy[1]; E.GGVDW += r.energy[2]; E.GGReal += r.energy[3];
       if(good)
       {
         double ew[2] = {0, 0}, tail = 0.0;
-        if(!S.d.no_charges && S.C[comp].has_charge) GB(gb_ewald_delta(S.e, comp, GB_INSERTION, r.selected, scale, ew));
-        GB(gb_tail_difference(S.e, comp, GB_INSERTION, &tail));
+        if(!S.d.no_charges && S.C[comp].has_charge) GB(gb_ewald_delta(e0, comp, GB_INSERTION, r.selected, scale, ew));
+        GB(gb_tail_difference(e0, comp, GB_INSERTION, &tail));
         E.GGEwald = ew[0]; E.HGEwald = ew[1]; E.Tail = tail;
         W *= std::exp(-S.d.beta * (ew[0] + ew[1])); W *= std::exp(-S.d.beta * tail);
       }
       S.C[comp].widom.total++;
       record_rosen(S, comp, good ? W : 0.0, good ? E : Energy(), cycle);
+      lane_classify(S, comp, L);                                  // after the stage calls: what it keeps stays valid for the batch of this pool
       continue;
     }
     const size_t dor = S.pool_off / ntp;
     S.pool_off += ntp;
     const double u2 = S.rng.uniform();
-    Q.fb.push_back((int64_t) (dfb * ntp)); Q.orr.push_back((int64_t) (dor * ntp)); Q.uni.push_back(u1); Q.uni.push_back(u2); Q.cyc.push_back(cycle);
+    L.Q.fb.push_back((int64_t) (dfb * ntp)); L.Q.orr.push_back((int64_t) (dor * ntp)); L.Q.uni.push_back(u1); L.Q.uni.push_back(u2); L.Q.cyc.push_back(cycle);
   }
-  flush_queue(S, comp, Q, true);
+  lane_finish(S, comp, lanes[1 - cur]);
+  { long dummy = 0; CallClock cc(S.widom_s[2], dummy); lane_evaluate(S, comp, lanes[cur]); }
+  lane_record(S, comp, lanes[cur]);
 }
 
 void print_widom(Sim& S, int comp)
@@ -1415,15 +1477,16 @@ int main(int argc, char** argv)
     catch(const std::exception& ex) { std::fprintf(stderr, "graspa_b200_mc: %s\n", ex.what()); return 1; }
     return 0;
   }
-  if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--no-server] [--gpus N] [--timing] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
+  if(argc < 2) { std::fprintf(stderr, "usage: graspa_b200_mc <deck directory> [--sequential-widom] [--staged] [--no-server] [--gpus N] [--no-pipeline] [--timing] [--trace file] [--init N] [--equil N] [--prod N]\n"); return 2; }
   const std::string dir = argv[1];
-  bool sequential_widom = false, staged = false, timing = false, no_server = false; const char* trace_path = nullptr; const char* restart_out = nullptr;
+  bool sequential_widom = false, staged = false, timing = false, no_server = false, no_pipeline = false; const char* trace_path = nullptr; const char* restart_out = nullptr;
   long o_init = -1, o_equil = -1, o_prod = -1; double o_pressure = -1.0, o_temperature = -1.0; int o_device = -1, o_gpus = 1; long o_seed = -1;
   for(int i = 2; i < argc; i++)
   {
     const std::string a = argv[i];
     if(a == "--sequential-widom") sequential_widom = true;
     else if(a == "--staged") staged = true;
+    else if(a == "--no-pipeline") no_pipeline = true;        // batched Widom replay: one lane (no overlap of a pool's evaluation with the next pool)
     else if(a == "--no-server") no_server = true;            // one k_move launch per move instead of the resident move server
     else if(a == "--timing") timing = true;
     else if(a == "--trace" && i + 1 < argc) trace_path = argv[++i];
@@ -1449,16 +1512,26 @@ int main(int argc, char** argv)
   S.fused = !staged;
   setup_engine(S);
   setup_probabilities(S);
-  // --gpus N: replicas of the system on the next N - 1 devices (same deck, same uploads); only the batched Widom replay uses them
+  // --gpus N: replicas of the system on the next N - 1 devices (same deck, same uploads); only the batched Widom replay uses them.
+  // A long replay (more than a few pools) gets a second engine per GPU as well: two lanes that alternate pools, so that the
+  // evaluation of one pool overlaps the generation, upload, classification and walk of the next (--no-pipeline: one lane)
   std::vector<std::unique_ptr<Shared>> replica_shared;
-  for(int g = 1; g < o_gpus; g++)
+  std::vector<gb_engine*> second_lane;
   {
-    replica_shared.emplace_back(new Shared());
-    Sim R(*replica_shared.back());
-    R.d = S.d; R.device = std::max(o_device, 0) + g; R.fused = S.fused;
-    R.C.assign(1 + R.d.fw.size() + R.d.comps.size(), CompState());
-    setup_engine(R);
-    SH.replicas.push_back(R.e);
+    int wc = -1;
+    const bool replay = !sequential_widom && widom_only(S, wc) && S.d.init_cycles == 0 && S.d.equil_cycles == 0;
+    const bool pipeline = replay && !no_pipeline && S.d.prod_cycles >= 100000;
+    auto replica = [&](int device) -> gb_engine*
+    {
+      replica_shared.emplace_back(new Shared());
+      Sim R(*replica_shared.back());
+      R.d = S.d; R.device = device; R.fused = S.fused;
+      R.C.assign(1 + R.d.fw.size() + R.d.comps.size(), CompState());
+      setup_engine(R);
+      return R.e;
+    };
+    for(int g = 1; g < o_gpus; g++) SH.replicas.push_back(replica(std::max(o_device, 0) + g));
+    if(pipeline) for(int g = 0; g < o_gpus; g++) second_lane.push_back(replica(std::max(o_device, 0) + g));
   }
   // two boxes run together (NumberOfSimulations 2, SingleSimulation no): the Gibbs ensemble of the reference's examples
   std::unique_ptr<Sim> S2;
@@ -1486,8 +1559,10 @@ int main(int argc, char** argv)
   S.pool[0] = 2.3; S.pool[1] = 4.5; S.pool[2] = 6.7;
   for(Sim* b : SH.boxes) GB(gb_upload_random_pool(b->e, S.pool.data(), (int64_t) S.pool_size));
   for(gb_engine* r : SH.replicas) GB(gb_upload_random_pool(r, S.pool.data(), (int64_t) S.pool_size));
+  for(gb_engine* r : second_lane) GB(gb_upload_random_pool(r, S.pool.data(), (int64_t) S.pool_size));
   Energy E0 = initial_state(S);
   for(gb_engine* r : SH.replicas) { gb_move_energy w; GB(gb_total_ewald(r, 1, &w)); }          // the stored structure factors of the Fourier stage
+  for(gb_engine* r : second_lane) { gb_move_energy w; GB(gb_total_ewald(r, 1, &w)); }
   Energy E0b;
   if(S2) { std::printf("--- box 1\n"); E0b = initial_state(*S2); SH.gibbs_total_volume = S.d.volume + S2->d.volume; }
 
@@ -1503,7 +1578,7 @@ int main(int argc, char** argv)
     run_phase_boxes(SH, S.d.prod_cycles, true);
     GB(gb_synchronize(S2->e));
   }
-  else if(batched) run_widom_batched_v2(S, wcomp, S.d.prod_cycles);
+  else if(batched) run_widom_batched_v2(S, wcomp, S.d.prod_cycles, second_lane);
   else
   {
     run_phase(S, S.d.init_cycles, false);
@@ -1603,6 +1678,7 @@ int main(int argc, char** argv)
   if(S.trace) std::fclose(S.trace);
   if(S2) gb_engine_destroy(S2->e);
   for(gb_engine* r : SH.replicas) gb_engine_destroy(r);
+  for(gb_engine* r : second_lane) gb_engine_destroy(r);
   gb_engine_destroy(S.e);
   return 0;
 }
