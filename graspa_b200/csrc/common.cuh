@@ -176,7 +176,8 @@ __device__ __forceinline__ void pair_energy(const DevParams& P, const double* __
                                             double r2, int row, double scaling, double qq_scaled,
                                             double& e_vdw, double& e_real, int& flag)
 {
-  const double rinv = rsqrt(r2);
+  double rinv = rsqrt(r2);
+  asm volatile("" : "+d"(rinv));                       // ONE reciprocal square root for both terms (the compiler otherwise sinks a copy into each branch)
   const double rinv2 = rinv * rinv;
   e_vdw = 0.0; e_real = 0.0; flag = 0;
   if(r2 < P.cut_vdw2)

@@ -560,12 +560,15 @@ static int engine_init(gb_engine* e, int device)
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+#define GBK_WC_ATTR(F) \
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<0, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024)); \
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<1, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024)); \
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<2, false, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024)); \
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<0, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024)); \
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<1, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024)); \
+    CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<2, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+    GBK_WC_ATTR(0) GBK_WC_ATTR(1) GBK_WC_ATTR(2)
+#undef GBK_WC_ATTR
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_move));
     CUDA_TRY(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, GBF_MAX_DYN_SMEM));
     {
@@ -1479,7 +1482,7 @@ static int widom_cells_grid(gb_engine* e, WcGrid& G, long long n_trials)
 // what one pass of the cell-sorted energy kernel needs: the grid, the live atoms gathered contiguously, the launch shape with the
 // capacities of the candidate lists, and buffers for nmax trial atoms.  The caller fills in the trial atoms' template (E.tq, E.tscoul,
 // E.ttype, E.ms), bins its trial atoms (wc_ucell / wc_udelta / wc_count) and calls wc_sort_and_energy.
-struct WcPlan { WcGrid G; WcEnergy E; int mode = 1, ctas = 4, thrE = 192, gridE = 0, nads = 0; size_t smemE = 0; };
+struct WcPlan { WcGrid G; WcEnergy E; int mode = 1, ctas = 4, thrE = 192, gridE = 0, nads = 0, fast = 0; size_t smemE = 0; };
 
 static int wc_plan(gb_engine* e, long long grid_basis, long long nmax, WcPlan& W)
 {
@@ -1505,12 +1508,15 @@ static int wc_plan(gb_engine* e, long long grid_basis, long long nmax, WcPlan& W
   mode = 1; ctas = 4; thrE = 192;
   if(const char* env = std::getenv("GB_WC_MODE")) mode = std::atoi(env) ? 1 : 0;
   if(mode == 0) { ctas = 1; thrE = 768; }
-  if(mode == 1 && e->wc_ctas_cap < 4) thrE = 256;
+  // the pair body without run-time switches (wc_sort_and_energy) needs 59 registers: four CTAs of 256 threads fit an SM (32 warps);
+  // the general body (66 registers) four of 192
+  const bool stage_ff = e->ntypes <= 24;
+  W.fast = (stage_ff && !e->P.use1264 && !std::getenv("GB_WC_GENERAL")) ? (e->P.no_charges ? 2 : (e->P.erfc_table_ok ? 1 : 0)) : 0;
+  if(mode == 1 && (e->wc_ctas_cap < 4 || W.fast == 1)) thrE = 256;
   if(const char* env = std::getenv("GB_WC_CTAS")) ctas = std::max(1, std::min(mode ? 6 : 1, std::atoi(env)));
   ctas = std::max(1, std::min(ctas, e->wc_ctas_cap));
   e->wc_last_ctas = ctas;
   if(const char* env = std::getenv("GB_WC_THREADS")) thrE = std::min(mode ? 256 : 768, std::max(64, std::atoi(env) / 32 * 32));
-  const bool stage_ff = e->ntypes <= 24;
   const size_t budget = std::min(e->smem_optin, (size_t) (e->prop.sharedMemPerMultiprocessor / ctas) - 1024 - 128);
   G.cap_fast = std::min((std::max(ntot, 32) + 1) & ~1, 2304); G.cap_slow = std::min((std::max(ntot, 32) + 1) & ~1, 768);
   while(wc_energy_smem(e->ntypes, stage_ff, G.cap_fast, G.cap_slow) > budget && G.cap_fast > 256) { G.cap_fast -= 64; G.cap_slow = std::max(128, G.cap_slow - 16); }
@@ -1540,13 +1546,19 @@ static int wc_sort_and_energy(gb_engine* e, WcPlan& W, long long nitems_src, int
   k_wc_scatter<<<(unsigned) ((nitems_src + 255) / 256), 256, 0, e->stream>>>(e->wc_ucell.p, e->wc_udelta.p, nitems_src, e->wc_off.p, e->wc_cursor.p, e->wc_srec.p);
   E.amod = amod; E.abase = abase;
   const bool gg = W.nads > 0;
-#define GBK_WC_LAUNCH(K) do { \
-    if(e->P.cell_mode == 2)      { if(gg) K<2, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<2, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } \
-    else if(e->P.cell_mode == 1) { if(gg) K<1, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<1, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } \
-    else                         { if(gg) K<0, true><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<0, false><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } } while(0)
+#define GBK_WC_LAUNCH(K, ...) do { \
+    if(e->P.cell_mode == 2)      { if(gg) K<2, true __VA_ARGS__><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<2, false __VA_ARGS__><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } \
+    else if(e->P.cell_mode == 1) { if(gg) K<1, true __VA_ARGS__><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<1, false __VA_ARGS__><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } \
+    else                         { if(gg) K<0, true __VA_ARGS__><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); else K<0, false __VA_ARGS__><<<gridE, thrE, smemE, e->stream>>>(e->P, G, E); } } while(0)
   {
     Timer te(e, 3);
-    if(W.mode == 1) GBK_WC_LAUNCH(k_wc_energy_lt); else GBK_WC_LAUNCH(k_wc_energy);
+    // the common case -- plain 12-6 LJ, LJ table staged in shared memory, every in-cutoff erfc argument inside the table -- runs a pair body
+    // without run-time switches (1: with real-space Coulomb, 2: no charges); everything else the general one
+    const int fast = W.fast;
+    if(W.mode != 1) GBK_WC_LAUNCH(k_wc_energy);
+    else if(fast == 1) GBK_WC_LAUNCH(k_wc_energy_lt, , 1);
+    else if(fast == 2) GBK_WC_LAUNCH(k_wc_energy_lt, , 2);
+    else GBK_WC_LAUNCH(k_wc_energy_lt, , 0);
     te.stop(1);
   }
 #undef GBK_WC_LAUNCH

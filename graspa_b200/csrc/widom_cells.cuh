@@ -167,10 +167,74 @@ __host__ __device__ inline size_t wc_energy_smem(int ntypes, bool stage_ff, int 
   return (b + 15) / 16 * 16;
 }
 
+// The pair body of the common case, without the run-time switches of pair_energy (common.cuh): plain 12-6 LJ with unit scaling factors,
+// the LJ table and the erfc table in shared memory (LDS, not generic loads), every in-cutoff argument inside the erfc table.
+// FAST 1: with real-space Coulomb, FAST 2: a system without charges.  Same expressions as pair_energy's unit path.
+__device__ __forceinline__ double lds_f64(uint32_t addr, int byte_off)
+{
+  double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr + (uint32_t) byte_off)); return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
+{
+  double2 v; asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr)); return v;
+}
+
+// erfc_table_eval (common.cuh) with the table given by its 32-bit shared-memory address: plain LDS with immediate offsets, no
+// generic-to-shared address arithmetic per pair.  Same polynomial, same order.
+__device__ __forceinline__ double erfc_table_eval_s(uint32_t tab, double x)
+{
+  const double M = 6755399441055744.0;
+  const double y = x * GBK_ERFC_SCALE;
+  double kd = __dadd_rn(y, M);
+  const int k = __double2loint(kd);
+  kd = __dsub_rn(kd, M);
+  const double t = y - kd;
+  const uint32_t a = tab + 8u * (uint32_t) k;
+  double acc = lds_f64(a, 8 * GBK_ERFC_NINT * GBK_ERFC_DEG);
+#pragma unroll
+  for(int j = GBK_ERFC_DEG - 1; j >= 0; j--) acc = fma(acc, t, lds_f64(a, 8 * GBK_ERFC_NINT * j));
+  return acc;
+}
+
+template <int FAST>
+__device__ __forceinline__ void pair_energy_fast(const DevParams& P, uint32_t etab_s, uint32_t ff_s,
+                                                 double r2, int row, double qq, double& e_vdw, double& e_real, int& flag)
+{
+  double rinv = rsqrt(r2);
+  asm volatile("" : "+d"(rinv));                       // ONE reciprocal square root for both terms (the compiler otherwise sinks a copy into each branch)
+  const double rinv2 = rinv * rinv;
+  e_vdw = 0.0; e_real = 0.0; flag = 0;
+  if(r2 < P.cut_vdw2)
+  {
+    const double2 f01 = lds_f64x2(ff_s + 32u * (uint32_t) row);            // {4 eps, sigma^2}
+    const double fz = lds_f64(ff_s + 32u * (uint32_t) row, 16);            // shift
+    const double x = f01.y * rinv2; const double rri3 = x * x * x;
+    const double e = f01.x * (rri3 * (rri3 - 1.0)) - fz;
+    if(e > P.overlap) flag = 1;
+    if(r2 < 0.01) flag = 1;
+    e_vdw = e;
+  }
+  if(FAST == 1 && r2 < P.cut_coul2)
+  {
+    const double r = r2 * rinv;
+    const double ec = erfc_table_eval_s(etab_s, P.alpha * r);
+    e_real = P.prefactor * qq * ec * rinv;
+  }
+}
+
+// FAST 0: pair_energy with all its switches (12-6-4 potential, LJ table in global memory, arguments beyond the erfc table)
+template <int FAST>
+__device__ __forceinline__ void wc_pair(const DevParams& P, const double* __restrict__ etab, const double4* __restrict__ ffp, uint32_t etab_s, uint32_t ff_s,
+                                        double r2, int row, double qq, double& ev, double& er, int& f)
+{
+  if(FAST == 0) pair_energy(P, etab, ffp, true, r2, row, 1.0, qq, ev, er, f);
+  else          pair_energy_fast<FAST>(P, etab_s, ff_s, r2, row, qq, ev, er, f);
+}
+
 // MODE 0: a warp per trial atom, lanes over the candidates (warp reduction at the end).
 // MODE 1: a lane per trial atom, the warp walks the candidates in lockstep: every candidate load is a shared-memory BROADCAST
 //         (one wavefront for 32 pairs, two candidates per 16-byte load) and nothing is reduced across lanes.
-template <int CELL, bool HAS_GG, int MODE>
+template <int CELL, bool HAS_GG, int MODE, int FAST>
 __device__ __forceinline__ void wc_energy_body(const DevParams& P, const WcGrid& G, const WcEnergy& A)
 {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -192,7 +256,9 @@ __device__ __forceinline__ void wc_energy_body(const DevParams& P, const WcGrid&
   stage_erfc_table(P, etab);
   if(A.stage_ff) for(int i = threadIdx.x; i < P.ntypes * P.ntypes; i += blockDim.x) fftab[i] = P.ffA[i];
   for(int a = threadIdx.x; a < A.ms && a < 64; a += blockDim.x) { Tq[a] = A.tq[a] * A.tscoul[a]; Ttype[a] = A.ttype[a]; }
-  const double4* ffp = A.stage_ff ? fftab : P.ffA;
+  const double4* ffp = (FAST > 0 || A.stage_ff) ? fftab : P.ffA;      // FAST kernels are launched only with the staged table
+  uint32_t etab_s = smem_u32(etab), ff_s = smem_u32(fftab);
+  asm volatile("" : "+r"(etab_s), "+r"(ff_s));       // kept in registers: the compiler otherwise re-derives the shared window base at every use
   GBK_ASSUME_SHARED(Fx); GBK_ASSUME_SHARED(Fy); GBK_ASSUME_SHARED(Fz); GBK_ASSUME_SHARED(Fq); GBK_ASSUME_SHARED(Ftk);
   GBK_ASSUME_SHARED(Sx); GBK_ASSUME_SHARED(Sy); GBK_ASSUME_SHARED(Sz); GBK_ASSUME_SHARED(Sq); GBK_ASSUME_SHARED(Stk);
   CellRegs<CELL> C; C.load(P);
@@ -295,7 +361,7 @@ __device__ __forceinline__ void wc_energy_body(const DevParams& P, const WcGrid&
           {
             const int tk = Ftk[j];
             double ev, er; int f;
-            pair_energy(P, etab, ffp, true, ra, (tk & 0xffff) * P.ntypes + ttype, 1.0, Fq[j] * tq, ev, er, f);
+            wc_pair<FAST>(P, etab, ffp, etab_s, ff_s, ra, (tk & 0xffff) * P.ntypes + ttype, Fq[j] * tq, ev, er, f);
             if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
             else { ev0 += ev; er0 += er; }
             fl |= f;
@@ -304,7 +370,7 @@ __device__ __forceinline__ void wc_energy_body(const DevParams& P, const WcGrid&
           {
             const int tk = Ftk[j + 1];
             double ev, er; int f;
-            pair_energy(P, etab, ffp, true, rb, (tk & 0xffff) * P.ntypes + ttype, 1.0, Fq[j + 1] * tq, ev, er, f);
+            wc_pair<FAST>(P, etab, ffp, etab_s, ff_s, rb, (tk & 0xffff) * P.ntypes + ttype, Fq[j + 1] * tq, ev, er, f);
             if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
             else { ev0 += ev; er0 += er; }
             fl |= f;
@@ -320,7 +386,7 @@ __device__ __forceinline__ void wc_energy_body(const DevParams& P, const WcGrid&
             {
               const int tk = Stk[j];
               double ev, er; int f;
-              pair_energy(P, etab, ffp, true, r2, (tk & 0xffff) * P.ntypes + ttype, 1.0, Sq[j] * tq, ev, er, f);
+              wc_pair<FAST>(P, etab, ffp, etab_s, ff_s, r2, (tk & 0xffff) * P.ntypes + ttype, Sq[j] * tq, ev, er, f);
               if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
               else { ev0 += ev; er0 += er; }
               fl |= f;
@@ -395,11 +461,11 @@ __device__ __forceinline__ void wc_energy_body(const DevParams& P, const WcGrid&
 
 template <int CELL, bool HAS_GG>
 __global__ void __launch_bounds__(768, 1)
-k_wc_energy(DevParams P, WcGrid G, WcEnergy A) { wc_energy_body<CELL, HAS_GG, 0>(P, G, A); }
+k_wc_energy(DevParams P, WcGrid G, WcEnergy A) { wc_energy_body<CELL, HAS_GG, 0, 0>(P, G, A); }
 
-template <int CELL, bool HAS_GG>
+template <int CELL, bool HAS_GG, int FAST>
 __global__ void __launch_bounds__(256, 3)
-k_wc_energy_lt(DevParams P, WcGrid G, WcEnergy A) { wc_energy_body<CELL, HAS_GG, 1>(P, G, A); }
+k_wc_energy_lt(DevParams P, WcGrid G, WcEnergy A) { wc_energy_body<CELL, HAS_GG, 1, FAST>(P, G, A); }
 
 // ---------------------------------------------------------------------------------------------- caller-supplied trial atoms
 // gb_trial_energies with a large batch of trial groups (every group the same molecule, unit scaling factors, nothing of the system
