@@ -567,7 +567,7 @@ static int engine_init(gb_engine* e, int device)
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<0, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024)); \
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<1, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024)); \
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<2, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
-    GBK_WC_ATTR(0) GBK_WC_ATTR(1) GBK_WC_ATTR(2)
+    GBK_WC_ATTR(0) GBK_WC_ATTR(1) GBK_WC_ATTR(2) GBK_WC_ATTR(3)
 #undef GBK_WC_ATTR
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_move));
     CUDA_TRY(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, GBF_MAX_DYN_SMEM));
@@ -1512,7 +1512,8 @@ static int wc_plan(gb_engine* e, long long grid_basis, long long nmax, WcPlan& W
   // the general body (66 registers) four of 192
   const bool stage_ff = e->ntypes <= 24;
   W.fast = (stage_ff && !e->P.use1264 && !std::getenv("GB_WC_GENERAL")) ? (e->P.no_charges ? 2 : (e->P.erfc_table_ok ? 1 : 0)) : 0;
-  if(mode == 1 && (e->wc_ctas_cap < 4 || W.fast == 1)) thrE = 256;
+  if(W.fast == 1 && e->P.cut_vdw2 == e->P.cut_coul2 && !std::getenv("GB_WC_NO_SAMECUT")) W.fast = 3;
+  if(mode == 1 && (e->wc_ctas_cap < 4 || W.fast == 1 || W.fast == 3)) thrE = 256;
   if(const char* env = std::getenv("GB_WC_CTAS")) ctas = std::max(1, std::min(mode ? 6 : 1, std::atoi(env)));
   ctas = std::max(1, std::min(ctas, e->wc_ctas_cap));
   e->wc_last_ctas = ctas;
@@ -1558,6 +1559,7 @@ static int wc_sort_and_energy(gb_engine* e, WcPlan& W, long long nitems_src, int
     if(W.mode != 1) GBK_WC_LAUNCH(k_wc_energy);
     else if(fast == 1) GBK_WC_LAUNCH(k_wc_energy_lt, , 1);
     else if(fast == 2) GBK_WC_LAUNCH(k_wc_energy_lt, , 2);
+    else if(fast == 3) GBK_WC_LAUNCH(k_wc_energy_lt, , 3);
     else GBK_WC_LAUNCH(k_wc_energy_lt, , 0);
     te.stop(1);
   }

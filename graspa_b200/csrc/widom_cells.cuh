@@ -169,7 +169,8 @@ __host__ __device__ inline size_t wc_energy_smem(int ntypes, bool stage_ff, int 
 
 // The pair body of the common case, without the run-time switches of pair_energy (common.cuh): plain 12-6 LJ with unit scaling factors,
 // the LJ table and the erfc table in shared memory (LDS, not generic loads), every in-cutoff argument inside the erfc table.
-// FAST 1: with real-space Coulomb, FAST 2: a system without charges.  Same expressions as pair_energy's unit path.
+// FAST 1: with real-space Coulomb, FAST 2: a system without charges, FAST 3: as 1 with CutOffVDW == CutOffCoul (every pair the caller
+// found inside the cutoff gets both terms: no range tests).  Same expressions as pair_energy's unit path.
 __device__ __forceinline__ double lds_f64(uint32_t addr, int byte_off)
 {
   double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr + (uint32_t) byte_off)); return v;
@@ -204,7 +205,7 @@ __device__ __forceinline__ void pair_energy_fast(const DevParams& P, uint32_t et
   asm volatile("" : "+d"(rinv));                       // ONE reciprocal square root for both terms (the compiler otherwise sinks a copy into each branch)
   const double rinv2 = rinv * rinv;
   e_vdw = 0.0; e_real = 0.0; flag = 0;
-  if(r2 < P.cut_vdw2)
+  if(FAST == 3 || r2 < P.cut_vdw2)
   {
     const double2 f01 = lds_f64x2(ff_s + 32u * (uint32_t) row);            // {4 eps, sigma^2}
     const double fz = lds_f64(ff_s + 32u * (uint32_t) row, 16);            // shift
@@ -214,7 +215,7 @@ __device__ __forceinline__ void pair_energy_fast(const DevParams& P, uint32_t et
     if(r2 < 0.01) flag = 1;
     e_vdw = e;
   }
-  if(FAST == 1 && r2 < P.cut_coul2)
+  if(FAST == 3 || (FAST == 1 && r2 < P.cut_coul2))
   {
     const double r = r2 * rinv;
     const double ec = erfc_table_eval_s(etab_s, P.alpha * r);
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(768, 1)
 k_wc_energy(DevParams P, WcGrid G, WcEnergy A) { wc_energy_body<CELL, HAS_GG, 0, 0>(P, G, A); }
 
 template <int CELL, bool HAS_GG, int FAST>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, (FAST == 1 || FAST == 3) ? 4 : 3)      // the bodies without switches fit 64 registers: 32 warps per SM
 k_wc_energy_lt(DevParams P, WcGrid G, WcEnergy A) { wc_energy_body<CELL, HAS_GG, 1, FAST>(P, G, A); }
 
 // ---------------------------------------------------------------------------------------------- caller-supplied trial atoms
