@@ -9,6 +9,8 @@ mkdir -p gpurun_out
 if [ "$WHAT" != prof ]; then
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 | tee gpurun_out/${R}_gputest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+# the committed N = 1 sums of the 10^7 job are rewritten with the kernels of this build (one pass), then the bench checks itself against them
+timeout 600 python bench.py --write-job-sums --no-secondary --no-cpu-baseline --steps 1 --warmup 1 > /dev/null 2>&1; cp tests/golden/job_sums_E.json gpurun_out/job_sums_E.json
 timeout 900 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err; tail -c 1500 gpurun_out/${R}_bench.json; tail -3 gpurun_out/${R}_bench.err
 for deck in "XeKr-Mixture 20000" "CO2-MFI 3000"; do
   set -- $deck
