@@ -361,7 +361,12 @@ def main():
     h_uni = torch.empty((count, 2), dtype=torch.float64).pin_memory(); h_uni.copy_(d_uni)
     torch.cuda.synchronize()
     t_sums = torch.zeros((5, 12), dtype=torch.float64, device=dev)
-    subs = [(off, min(args.sub_batch, count - off)) for off in range(0, count, args.sub_batch)]
+    # this rank's range in equal sub-batches of at most --sub-batch insertions (equal: a short last call would pay the fixed costs of
+    # the cell-sorted stage -- sort, one list build per cell -- for fewer insertions)
+    nsub_ = max(1, -(-count // args.sub_batch)); q_, r_ = divmod(count, nsub_)
+    subs = []; off_ = 0
+    for i_ in range(nsub_):
+        subs.append((off_, q_ + (1 if i_ < r_ else 0))); off_ += subs[-1][1]
     hp, hu = h_pool.numpy(), h_uni.numpy()
 
     def finish():
