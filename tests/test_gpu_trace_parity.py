@@ -117,6 +117,20 @@ def test_henry_coefficient_deck_equals_the_reference_program(tmp_path):
         assert abs(kh - ref_kh) <= 1e-9 * abs(ref_kh) + 1e-14
 
 
+def test_pipelined_widom_replay_gives_the_single_lane_averages(tmp_path):
+    """a long RNG-exact replay alternates pools between two lanes of engines (evaluation of pool k in a background thread beside the
+    upload, classification and walk of pool k + 1) and books the averages in cycle order: every printed digit of the per-block <W>,
+    of the average and of the Henry coefficient equals the single-lane run's (300 000 insertions = 18 pools)"""
+    d = _deck_copy("Henrys_coefficient", tmp_path, 0, 300000)
+    runs = []
+    for flags in ((), ("--no-pipeline",)):
+        o = subprocess.run([DRIVER, d, "--init", "0", "--equil", "0", "--prod", "300000", *flags], capture_output=True, text=True, timeout=1200)
+        assert o.returncode == 0, o.stderr[-2000:]
+        assert '"widom_path": "batched-exact"' in o.stdout
+        runs.append([ln for ln in o.stdout.splitlines() if "Averaged" in ln or ln.startswith("AVG WIDOM")])
+    assert len(runs[0]) >= 12 and runs[0] == runs[1]
+
+
 REF_OVERLAY = os.path.join(ROOT, "oracle", "_ref", "graspa_ref_overlay.x")
 
 
