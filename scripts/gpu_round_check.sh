@@ -22,12 +22,14 @@ for deck in "XeKr-Mixture 20000" "CO2-MFI 3000"; do
 done
 fi
 [ "$WHAT" = check ] && exit 0
-NCUB="python bench.py --scaling weak --batch 200000 --no-cpu-baseline --no-secondary"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${R}_launches.csv \
-  $NCUB --steps 2 --warmup 3 > gpurun_out/${R}_bench_under_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_wc_energy_lt -s 8 -c 2 -o gpurun_out/prof_wc_energy_${R} -f \
+# the bench's own command (the 10^7-insertion job in sub-batches of 10^6), without the CPU legs and the GCMC section
+NCUB="python bench.py --no-cpu-baseline --no-secondary"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${R}_launches.csv \
+  $NCUB --steps 1 --warmup 3 > gpurun_out/${R}_bench_under_ncu.log 2>&1
+# the two energy launches of one 10^6-insertion sub-batch of the timed step (20 launches per pass over the job: skip the 3 warm-up passes)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_wc_energy_lt -s 60 -c 2 -o gpurun_out/prof_wc_energy_${R} -f \
   $NCUB --steps 1 --warmup 3 > gpurun_out/${R}_ncu_wc.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_widom_ewald -s 3 -c 1 -o gpurun_out/prof_ewald_${R} -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_widom_ewald -s 30 -c 1 -o gpurun_out/prof_ewald_${R} -f \
   $NCUB --steps 1 --warmup 3 > gpurun_out/${R}_ncu_ewald.log 2>&1
 D=$(mktemp -d /tmp/rc.XXXX); cp -r oracle/_ref/examples/XeKr-Mixture/* $D/; chmod -R u+w $D
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_move -s 4000 -c 3 -o gpurun_out/prof_move_${R} -f \
