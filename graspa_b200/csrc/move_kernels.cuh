@@ -534,6 +534,20 @@ __global__ void k_commit_delete(SlotArrays S, int dst, int src, int n)
   S.q[dst + i] = S.q[src + i]; S.scale[dst + i] = S.scale[src + i]; S.scoul[dst + i] = S.scoul[src + i]; S.type[dst + i] = S.type[src + i];
 }
 
+// exchange two molecules' slots (Update_deletion_data_fractional / Revert_CBCF_Deletion, mc_cbcfc.h:133-214: the fractional molecule
+// that is provisionally deleted is parked in the last slot so that a rejection can put it back); MolIDs stay where they are
+__global__ void k_commit_swap(SlotArrays S, int a, int b, int n)
+{
+  const int i = threadIdx.x;
+  if(i >= n || a == b) return;
+  double t;
+  t = S.x[a + i]; S.x[a + i] = S.x[b + i]; S.x[b + i] = t;  t = S.y[a + i]; S.y[a + i] = S.y[b + i]; S.y[b + i] = t;  t = S.z[a + i]; S.z[a + i] = S.z[b + i]; S.z[b + i] = t;
+  t = S.fx[a + i]; S.fx[a + i] = S.fx[b + i]; S.fx[b + i] = t;  t = S.fy[a + i]; S.fy[a + i] = S.fy[b + i]; S.fy[b + i] = t;  t = S.fz[a + i]; S.fz[a + i] = S.fz[b + i]; S.fz[b + i] = t;
+  t = S.q[a + i]; S.q[a + i] = S.q[b + i]; S.q[b + i] = t;  t = S.scale[a + i]; S.scale[a + i] = S.scale[b + i]; S.scale[b + i] = t;
+  t = S.scoul[a + i]; S.scoul[a + i] = S.scoul[b + i]; S.scoul[b + i] = t;
+  const int ty = S.type[a + i]; S.type[a + i] = S.type[b + i]; S.type[b + i] = ty;
+}
+
 // buffer <- buffer / buffer <- slots copies (StoreNewLocation_Reinsertion mc_swap_moves.h:27-41 and Ewald gathers)
 __global__ void k_copy_buffer(MoveBufs B, int dst_buf, int src_buf, int n)
 {

@@ -30,7 +30,7 @@ DECLARED_SYMBOLS = [
     "gb_set_cbmc", "gb_get_pseudo_atom_counts", "gb_cbmc_first_bead", "gb_cbmc_chain", "gb_cbmc_grown_positions", "gb_reinsertion_store", "gb_move_insertion", "gb_move_deletion", "gb_move_reinsertion", "gb_move_single_body", "gb_move_identity_swap",
     "gb_trial_energies", "gb_single_body_propose", "gb_single_body_delta", "gb_single_body_delta_explicit",
     "gb_ewald_delta", "gb_ewald_delta_identity_swap", "gb_ewald_delta_explicit", "gb_ewald_commit",
-    "gb_lambda_change_delta", "gb_ewald_delta_lambda_change", "gb_accept_lambda_change",
+    "gb_lambda_change_delta", "gb_ewald_delta_lambda_change", "gb_accept_lambda_change", "gb_cbcf_set_scale", "gb_cbcf_deletion_stage",
     "gb_tail_total", "gb_tail_difference", "gb_tail_identity_swap",
     "gb_accept_translation", "gb_accept_insertion", "gb_accept_deletion", "gb_accept_reinsertion", "gb_accept_identity_swap", "gb_append_molecule",
     "gb_number_of_molecules", "gb_total_vdw_real", "gb_total_ewald", "gb_volume_move_trial", "gb_volume_move_finish",
@@ -376,6 +376,13 @@ class Engine:
     def accept_lambda_change(self, comp, molecule, new_scale):
         sc = (C.c_double * 2)(*new_scale)
         self._chk(self.lib.gb_accept_lambda_change(self.h, C.c_int32(comp), C.c_int64(molecule), sc))
+
+    def cbcf_set_scale(self, comp, molecule, scale):
+        sc = (C.c_double * 2)(*scale)
+        self._chk(self.lib.gb_cbcf_set_scale(self.h, C.c_int32(comp), C.c_int64(molecule), sc))
+
+    def cbcf_deletion_stage(self, comp, molecule, revert=False):
+        self._chk(self.lib.gb_cbcf_deletion_stage(self.h, C.c_int32(comp), C.c_int64(molecule), C.c_int32(int(revert))))
 
     def accept_identity_swap(self, old_comp, old_molecule, new_comp):
         self._chk(self.lib.gb_accept_identity_swap(self.h, C.c_int32(old_comp), C.c_int64(old_molecule), C.c_int32(new_comp)))

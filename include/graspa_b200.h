@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GB_ABI_VERSION 8
+#define GB_ABI_VERSION 9
 
 enum {
   GB_OK = 0,
@@ -272,6 +272,18 @@ int  gb_lambda_change_delta(gb_engine* e, int32_t component, int64_t molecule, c
 int  gb_ewald_delta_lambda_change(gb_engine* e, int32_t component, const double old_scale[2], const double new_scale[2],
                                   int32_t use_temp_vector, double out[2]);
 int  gb_accept_lambda_change(gb_engine* e, int32_t component, int64_t molecule, const double new_scale[2]);
+/* CBCF insertion and deletion (CBCFMove, mc_cbcfc.h:296-447) are two-step moves that put the system into the intermediate state
+ * BEFORE the acceptance test and take it back on rejection; the Fourier state of the first step stays in tempEik (UseTempVector).
+ *   insertion: gb_lambda_change_delta(fractional molecule -> 1) + gb_ewald_delta_lambda_change(use_temp_vector 0);
+ *              gb_cbcf_set_scale(molecule, {1,1})                      -- update_CBCF_scale<<<>>> :312
+ *              gb_cbmc_first_bead / gb_cbmc_chain(scale = new lambda); gb_ewald_delta(GB_CBCF_INSERTION) continues from tempEik
+ *              accepted: gb_accept_insertion;  rejected: gb_cbcf_set_scale(molecule, old scale)   -- Revert_CBCF_Insertion<<<>>> :359
+ *   deletion:  gb_cbmc_first_bead / gb_cbmc_chain(GB_CBMC_DELETION, scale = old lambda); gb_ewald_delta(GB_CBCF_DELETION);
+ *              gb_cbcf_deletion_stage(molecule, 0)                     -- Update_deletion_data_fractional<<<>>> + Update_NumberOfMolecules :382-386
+ *              gb_lambda_change_delta(new fractional molecule, new lambda) + gb_ewald_delta_lambda_change(use_temp_vector 1)
+ *              accepted: gb_accept_lambda_change;  rejected: gb_cbcf_deletion_stage(molecule, 1)  -- Revert_CBCF_Deletion<<<>>> :441-446 */
+int  gb_cbcf_set_scale(gb_engine* e, int32_t component, int64_t molecule, const double scale[2]);
+int  gb_cbcf_deletion_stage(gb_engine* e, int32_t component, int64_t molecule, int32_t revert);
 
 /* ------------------------------------------------------------------------------------------------
  * tail corrections  (replaces TailCorrection_Energy_Functions.h:3-113)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(engine.DECLARED_SYMBOLS) == syms
     import re
     want = int(re.search(r"#define GB_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "graspa_b200.h")).read()).group(1))
-    assert lib.gb_abi_version() == want == 8      # 3: block pockets, identity-swap commit; 4: CB/CFC lambda change; 5: NPT volume move; 6: gb_widom_inputs.sums_device; 7: gb_move_server; 8: gb_widom_inputs.resume_first_bead, engine pool for the Widom calls
+    assert lib.gb_abi_version() == want == 9      # 3: block pockets, identity-swap commit; 4: CB/CFC lambda change; 5: NPT volume move; 6: gb_widom_inputs.sums_device; 7: gb_move_server; 8: gb_widom_inputs.resume_first_bead, engine pool for the Widom calls; 9: CBCF insertion / deletion stages (gb_cbcf_set_scale, gb_cbcf_deletion_stage, gb_ewald_delta(GB_CBCF_INSERTION))
 
 
 def test_engine_creation_fails_loudly_without_gpu():

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from graspa_b200.types import (TrialAtoms, CBMC_INSERTION, CBMC_DELETION, REINSERTION_INSERTION, REINSERTION_RETRACE,
-                               TRANSLATION, ROTATION, INSERTION, DELETION, REINSERTION)
+                               TRANSLATION, ROTATION, INSERTION, DELETION, REINSERTION, CBCF_INSERTION, CBCF_DELETION)
 from graspa_b200.types import pseudo_atom_counts
 from tests.conftest import load_config
 
@@ -570,6 +570,126 @@ def test_cbcfc_lambda_change_vs_oracle(gpu_engine_factory, oracle):
         cur = System(cur.nhost, cur.natoms, cur.molsize, cur.pos, cur.charge, cur.type, cur.molid, sc, scc, alloc=cur.alloc)
         old_scale = new_scale
     assert abs(running) <= 1e-7 * max(1.0, abs(E0))          # back at lambda = 1: the three deltas cancel
+    eng.close()
+
+
+def _totals_no_tail(eng):
+    v = eng.total_vdw_real(); w = eng.total_ewald(store=False)
+    return (v["HHVDW"] + v["HGVDW"] + v["GGVDW"] + v["HHReal"] + v["HGReal"] + v["GGReal"] + w["HHEwaldE"] + w["HGEwaldE"] + w["GGEwaldE"])
+
+
+def _sb_sum(d):
+    return sum(d[k] for k in ("HHVDW", "HHReal", "HGVDW", "HGReal", "GGVDW", "GGReal"))
+
+
+def test_cbcf_insertion_and_deletion_compositions(gpu_engine_factory, oracle):
+    """The two-step CB/CFC moves of CBCFMove (mc_cbcfc.h:296-447) composed from the stage calls, with the intermediate Fourier state
+    in tempEik (UseTempVector, Ewald_Energy_Functions.h:362-377, :510-517, :713-716).
+    Insertion: the fractional molecule goes to lambda = 1 (update_CBCF_scale before the acceptance test), a new fractional molecule is
+    grown at the new lambda and its Fourier delta continues from tempEik; accepted -> the from-scratch total energy moves by the sum of
+    the two steps and the stored structure factors are those of the new state; rejected -> Revert_CBCF_Insertion leaves every slot and
+    structure factor bit for bit as it was.
+    Deletion: the fractional molecule is retraced and its Fourier delta written to tempEik, Update_deletion_data_fractional parks it
+    behind the live range, another molecule goes from 1 to the new lambda on top of tempEik; accepted / rejected (Revert_CBCF_Deletion)
+    as above.  The reference's own CBCFMove tests a local SuccessConstruction that nothing sets (mc_cbcfc.h:307-318, :372-393), so its
+    program never accepts these branches: the energies are pinned here by the oracle and by the recomputed totals instead of a run."""
+    box, ff, s, z, eng = _setup(gpu_engine_factory, "B", grow=600)
+    comp = 1; ms = 3; o = int(s.offsets[comp])
+    excl = float(z["excl"][0]) + float(z["excl"][1])
+    rng = np.random.default_rng(77)
+    pool = rng.random((4096, 3)); eng.upload_random_pool(pool)
+    eng.total_ewald(store=True)
+    lam = lambda x: (x, x ** 5)
+    nmol0 = eng.number_of_molecules(comp)
+    frac = 2; s_old = lam(0.4)
+    eng.lambda_change_delta(comp, frac, s_old); eng.ewald_delta_lambda_change(comp, (1.0, 1.0), s_old); eng.accept_lambda_change(comp, frac, s_old)
+
+    def insertion(accept, frac, s_old, s_new, off):
+        E0 = _totals_no_tail(eng); a0 = eng.download_atoms(comp); sf0 = eng.download_structure_factors()[0].copy()
+        d1, ov = eng.lambda_change_delta(comp, frac, (1.0, 1.0)); assert not ov
+        ew1 = eng.ewald_delta_lambda_change(comp, s_old, (1.0, 1.0))
+        eng.cbcf_set_scale(comp, frac, (1.0, 1.0))
+        while True:
+            fb = eng.cbmc_first_bead(CBMC_INSERTION, comp, 0, off, rng.random(), scale=s_new); off += 10
+            if not fb["success"]:
+                continue
+            ch = eng.cbmc_chain(CBMC_INSERTION, comp, 0, off, rng.random()); off += 10
+            if ch["success"]:
+                break
+        _, sfw, stmp = eng.download_structure_factors()
+        ew2 = eng.ewald_delta(comp, CBCF_INSERTION, location=ch["selected"], scale=s_new)
+        grown = eng.cbmc_grown_positions(comp)
+        ref, _, _ = oracle.ewald_delta(box, grown, s.charge[o:o + ms], np.full(ms, s_new[1]), 0, ms, stmp, sfw)
+        ref[0] -= excl * s_new[1] ** 2
+        assert _close(ew2, ref, scale=max(1.0, float(np.abs(ref).max())))
+        dE = _sb_sum(d1) + ew1.sum() + fb["energy"].sum() + ch["energy"].sum() + ew2.sum()
+        if accept:
+            eng.accept_insertion(comp)
+            E1 = _totals_no_tail(eng)
+            assert abs((E1 - E0) - dE) <= 1e-9 * max(1.0, abs(E1)), (E1 - E0, dE)
+            n = eng.number_of_molecules(comp); a1 = eng.download_atoms(comp)
+            assert n == a0["n_live"] // ms + 1
+            assert np.all(a1["scale"][(n - 1) * ms:n * ms] == s_new[0]) and np.all(a1["scale_coul"][(n - 1) * ms:n * ms] == s_new[1])
+            assert np.all(a1["scale"][frac * ms:(frac + 1) * ms] == 1.0) and np.all(a1["scale_coul"][frac * ms:(frac + 1) * ms] == 1.0)
+            assert np.allclose(a1["pos"][(n - 1) * ms:n * ms], grown, rtol=0, atol=1e-12)
+            sa = eng.download_structure_factors()[0].copy(); eng.total_ewald(store=True); sb = eng.download_structure_factors()[0]
+            assert np.max(np.abs(sa - sb)) < 1e-8
+        else:
+            eng.cbcf_set_scale(comp, frac, s_old)
+            a1 = eng.download_atoms(comp)
+            for k in ("pos", "scale", "charge", "scale_coul", "type"):
+                assert np.array_equal(a0[k][:a0["n_live"]], a1[k][:a1["n_live"]]), k
+            assert a1["n_live"] == a0["n_live"] and np.array_equal(sf0, eng.download_structure_factors()[0])
+            assert abs(_totals_no_tail(eng) - E0) <= 1e-12 * max(1.0, abs(E0))
+        return off
+
+    off = insertion(False, frac, s_old, lam(0.7), 0)
+    off = insertion(True, frac, s_old, lam(0.7), off)
+    assert eng.number_of_molecules(comp) == nmol0 + 1
+
+    def deletion(accept, mdel, s_del, knew, s_new, off):
+        E0 = _totals_no_tail(eng); a0 = eng.download_atoms(comp); sf0 = eng.download_structure_factors()[0].copy()
+        n0 = eng.number_of_molecules(comp)
+        fb = eng.cbmc_first_bead(CBMC_DELETION, comp, mdel, off, 0.5, scale=s_del); off += 10
+        ch = eng.cbmc_chain(CBMC_DELETION, comp, mdel, off, 0.5); off += 10
+        ewd = eng.ewald_delta(comp, CBCF_DELETION, location=mdel * ms, scale=s_del)
+        eng.cbcf_deletion_stage(comp, mdel)
+        assert eng.number_of_molecules(comp) == n0 - 1
+        a_mid = eng.download_atoms(comp)
+        if mdel != n0 - 1:        # the last molecule took the slot, the deleted one is parked behind the live range
+            assert np.array_equal(a_mid["pos"][mdel * ms:(mdel + 1) * ms], a0["pos"][(n0 - 1) * ms:n0 * ms])
+        d2, ov = eng.lambda_change_delta(comp, knew, s_new); assert not ov
+        _, sfw, stmp = eng.download_structure_factors()
+        ew2 = eng.ewald_delta_lambda_change(comp, (1.0, 1.0), s_new, use_temp_vector=True)
+        pk = a_mid["pos"][knew * ms:(knew + 1) * ms]; q = s.charge[o:o + ms]
+        ref, _, _ = oracle.ewald_delta(box, np.concatenate([pk, pk]), np.concatenate([q, q]),
+                                       np.concatenate([np.ones(ms), np.full(ms, s_new[1])]), ms, ms, stmp, sfw)
+        ref[0] -= excl * (s_new[1] ** 2 - 1.0)
+        assert _close(ew2, ref, scale=max(1.0, float(np.abs(ref).max())))
+        dE = -(fb["energy"].sum() + ch["energy"].sum()) + ewd.sum() + _sb_sum(d2) + ew2.sum()
+        if accept:
+            eng.accept_lambda_change(comp, knew, s_new)
+            E1 = _totals_no_tail(eng)
+            assert abs((E1 - E0) - dE) <= 1e-9 * max(1.0, abs(E1)), (E1 - E0, dE)
+            sa = eng.download_structure_factors()[0].copy(); eng.total_ewald(store=True); sb = eng.download_structure_factors()[0]
+            assert np.max(np.abs(sa - sb)) < 1e-8
+        else:
+            eng.cbcf_deletion_stage(comp, mdel, revert=True)
+            a1 = eng.download_atoms(comp)
+            for k in ("pos", "scale", "charge", "scale_coul", "type"):
+                assert np.array_equal(a0[k][:a0["n_live"]], a1[k][:a1["n_live"]]), k
+            assert a1["n_live"] == a0["n_live"] and np.array_equal(sf0, eng.download_structure_factors()[0])
+            assert abs(_totals_no_tail(eng) - E0) <= 1e-12 * max(1.0, abs(E0))
+        return off
+
+    nfrac = eng.number_of_molecules(comp) - 1             # the molecule grown above is the fractional one now (lambda 0.7)
+    off = deletion(False, nfrac, lam(0.7), 4, lam(0.3), off)
+    # make a molecule in the middle the fractional one, so that the exchange with the last slot is exercised
+    eng.lambda_change_delta(comp, nfrac, (1.0, 1.0)); eng.ewald_delta_lambda_change(comp, lam(0.7), (1.0, 1.0)); eng.accept_lambda_change(comp, nfrac, (1.0, 1.0))
+    eng.lambda_change_delta(comp, 3, lam(0.6)); eng.ewald_delta_lambda_change(comp, (1.0, 1.0), lam(0.6)); eng.accept_lambda_change(comp, 3, lam(0.6))
+    off = deletion(False, 3, lam(0.6), 5, lam(0.2), off)
+    off = deletion(True, 3, lam(0.6), 5, lam(0.2), off)
+    assert eng.number_of_molecules(comp) == nmol0
     eng.close()
 
 
