@@ -130,6 +130,7 @@ struct gb_engine
   // resident move server (move_server.cuh): one cooperative launch that executes move after move; the fused move calls post
   // commands to it, the accept calls queue their commits for the next command, every other call stops it first (ready())
   bool counted = false;
+  double growth_scale[2] = {1.0, 1.0};   // scaling factors of the molecule the last CBMC insertion grew (a fractional molecule clears P.all_unit_scale when it is committed)
   bool srv_enabled = true, srv_running = false; int srv_compat = 0, srv_grid = 0; size_t srv_smem = 0;
   cudaStream_t srv_stream = nullptr;
   unsigned long long* srv_hcmd = nullptr;        // 4 KB pinned: [0, 2 KB) command records, [2 KB] status word

@@ -151,6 +151,31 @@ inline void b200_take_single_body(MoveEnergy& tot)
   tot.HHVDW = d.HHVDW; tot.HHReal = d.HHReal; tot.HGVDW = d.HGVDW; tot.HGReal = d.HGReal; tot.GGVDW = d.GGVDW; tot.GGReal = d.GGReal;
 }
 
+// CB/CFC (mc_cbcfc.h): replaces Prepare_LambdaChange<<<>>> + Calculate_Single_Body_Energy_VDWReal_LambdaChange<<<>>> + the copy of the
+// overlap flag (:39-69); the host sum of Blocksum that follows is overwritten by b200_take_single_body
+inline void b200_lambda_change_delta(Components& SC, size_t comp, size_t molecule, double2 newScale)
+{
+  B200Binding& G = b200(); int32_t ov = 0; const double sc[2] = {newScale.x, newScale.y};
+  GB_CHECK(gb_lambda_change_delta(G.e, (int32_t) comp, (int64_t) molecule, sc, &G.sb, &ov));
+  G.flag[0] = ov != 0;
+  SC.flag = G.flag;
+}
+// replaces GPU_EwaldDifference_LambdaChange (Ewald_Energy_Functions.h:637-788): a CBCF deletion's lambda change continues from tempEik (:761-764)
+inline double2 b200_ewald_delta_lambda_change(size_t comp, double2 oldScale, double2 newScale, int MoveType)
+{
+  const double so[2] = {oldScale.x, oldScale.y}, sn[2] = {newScale.x, newScale.y}; double out[2] = {0.0, 0.0};
+  GB_CHECK(gb_ewald_delta_lambda_change(b200().e, (int32_t) comp, so, sn, MoveType == CBCF_DELETION ? 1 : 0, out));
+  return {out[0], out[1]};
+}
+// update_CBCF_scale<<<>>> before the acceptance test / Revert_CBCF_Insertion<<<>>> (mc_cbcfc.h:312, :359); accepted: :427, :487
+inline void b200_cbcf_set_scale(size_t comp, size_t molecule, double2 scale)
+{ const double sc[2] = {scale.x, scale.y}; GB_CHECK(gb_cbcf_set_scale(b200().e, (int32_t) comp, (int64_t) molecule, sc)); }
+inline void b200_accept_lambda_change(size_t comp, size_t molecule, double2 scale)
+{ const double sc[2] = {scale.x, scale.y}; GB_CHECK(gb_accept_lambda_change(b200().e, (int32_t) comp, (int64_t) molecule, sc)); }
+// Update_deletion_data_fractional<<<>>> / Revert_CBCF_Deletion<<<>>> (mc_cbcfc.h:382, :441)
+inline void b200_cbcf_deletion_stage(size_t comp, size_t molecule, bool revert)
+{ GB_CHECK(gb_cbcf_deletion_stage(b200().e, (int32_t) comp, (int64_t) molecule, revert ? 1 : 0)); }
+
 // state commits (mc_utilities.h:294-417, move_struct.h:271,371): each includes the swap of the structure-factor vectors
 inline void b200_accept_translation(size_t comp) { GB_CHECK(gb_accept_translation(b200().e, (int32_t) comp)); }
 inline void b200_accept_insertion(size_t comp) { GB_CHECK(gb_accept_insertion(b200().e, (int32_t) comp)); }
@@ -160,7 +185,7 @@ inline void b200_accept_reinsertion(size_t comp, size_t molecule) { GB_CHECK(gb_
 
 // before the reference's own FINAL energy check (fxn_main.h:282-404, which reads Sims.d_a): the engine's state goes back into the
 // reference's device arrays, so that the reference's CPU and GPU total-energy routines judge the run (ENERGY DRIFT, fxn_main.h:467-468)
-inline void b200_sync_back(Variables& Vars, size_t sim)
+inline void b200_sync_back(Variables& Vars, size_t sim, bool report = true)
 {
   B200Binding& G = b200();
   if(!G.e) return;
@@ -189,5 +214,5 @@ inline void b200_sync_back(Variables& Vars, size_t sim)
   cudaMemcpy(Sims.Box.FrameworkEik, fw.data(), 2 * nvec * sizeof(double), cudaMemcpyHostToDevice);
   cudaDeviceSynchronize();
   int64_t launches = 0; gb_launch_count(G.e, &launches, 0);
-  fprintf(stderr, "graspa_b200 overlay: %lld engine kernel launches served the reference's drivers\n", (long long) launches);
+  if(report) fprintf(stderr, "graspa_b200 overlay: %lld engine kernel launches served the reference's drivers\n", (long long) launches);
 }

@@ -15,17 +15,26 @@ What is redirected (file:line of the reference):
   move_struct.h:271,371         StoreNewLocation_Reinsertion / Update_Reinsertion_data<<<>>> -> gb_reinsertion_store / gb_accept_reinsertion
   data_struct.h:1300-1320       RandomNumber::ResetRandom     -> + gb_upload_random_pool
   data_struct.cpp:6-11          Get_Uniform_Random            -> + Peek_Uniform_Random (one value of look-ahead)
-  main.cpp:427                  before the FINAL energy check -> engine state copied back into Sims.d_a (the reference's own CPU + GPU
+  main.cpp:340, :427            before the CREATE_MOLECULE and FINAL energy checks -> engine state copied back into Sims.d_a (the reference's own CPU + GPU
                                                                  total-energy routines then judge the run: ENERGY DRIFT)
   axpy.cu:297                   the one-line move trace of `build_ref.sh trace`
-Scope: the moves of the CO2-MFI deck (translation, rotation, CBMC insertion / deletion, reinsertion)."""
+  mc_cbcfc.h:39-104             Prepare_LambdaChange / Calculate_Single_Body_Energy_VDWReal_LambdaChange<<<>>> + host sum -> gb_lambda_change_delta;
+                                GPU_EwaldDifference_LambdaChange -> gb_ewald_delta_lambda_change
+  mc_cbcfc.h:312,359,427,487    update_CBCF_scale / Revert_CBCF_Insertion<<<>>> -> gb_cbcf_set_scale (provisional) / gb_accept_lambda_change (accepted)
+  mc_cbcfc.h:382,441            Update_deletion_data_fractional / Revert_CBCF_Deletion<<<>>> -> gb_cbcf_deletion_stage
+  mc_cbcfc.h:343                Update_insertion_data_Parallel<<<>>> of an accepted CBCF insertion -> gb_accept_insertion
+Scope: the moves of the CO2-MFI deck (translation, rotation, CBMC insertion / deletion, reinsertion) and, with CBCFProbability added to
+that deck, the CB/CFC move (lambda change; the first steps and the reversal of a fractional insertion / deletion -- the reference's
+CBCFMove never accepts those two: it tests a local SuccessConstruction that nothing sets, mc_cbcfc.h:307-318, :372-393)."""
 import sys
 
 
 def patch(path, edits):
     s = open(path).read()
-    for old, new in edits:
-        assert s.count(old) == 1, (path, s.count(old), old[:80])
+    for ed in edits:
+        old, new = ed[0], ed[1]
+        want = ed[2] if len(ed) > 2 else 1
+        assert s.count(old) == want, (path, s.count(old), old[:80])
         s = s.replace(old, new)
     open(path, "w").write(s)
 
@@ -74,7 +83,35 @@ def main(scr):
          "      b200_reinsertion_store(SelectedComponent);"),
         ("    Update_Reinsertion_data<<<1,SystemComponents.Moleculesize[SelectedComponent]>>>(Sims.d_a, SystemComponents.tempMolStorage, SelectedComponent, UpdateLocation); checkCUDAError(\"error Updating Reinsertion data\");",
          "    b200_accept_reinsertion(SelectedComponent, SystemComponents.TempVal.molecule);")])
-    patch(f"{scr}/main.cpp", [("    check_energy_wrapper(Vars, i);\n    //Report Random Number Summary", "    b200_sync_back(Vars, i);\n    check_energy_wrapper(Vars, i);\n    //Report Random Number Summary")])
+    MS = "SystemComponents.Moleculesize[SelectedComponent]"
+    patch(f"{scr}/mc_cbcfc.h", [
+        ("  Prepare_LambdaChange<<<1, Molsize>>>(Sims.d_a, Sims.Old, Sims, FF, start_position, SelectedComponent, Sims.device_flag);",
+         "  b200_engine(Vars, systemId);"),
+        ("  Calculate_Single_Body_Energy_VDWReal_LambdaChange<<<Total_Nblock, Nthread, Nthread * 2 * sizeof(double)>>>(Sims.Box, Sims.d_a, Sims.Old, Sims.New, FF, Sims.Blocksum, SelectedComponent, Atomsize, Molsize, Sims.device_flag, NBlocks, Do_New, Do_Old, SystemComponents.NComponents, newScale);\n\n"
+         "  cudaMemcpy(SystemComponents.flag, Sims.device_flag, sizeof(bool), cudaMemcpyDeviceToHost);",
+         "  b200_lambda_change_delta(SystemComponents, SelectedComponent, SelectedMolInComponent, newScale);"),
+        ("    if(!FF.noCharges && SystemComponents.hasPartialCharge[SelectedComponent])\n    {\n"
+         "      //Zhao's note: since we changed it from using translation/rotation functions to its own, this needs to be changed as well//\n"
+         "      double2 EwaldE = GPU_EwaldDifference_LambdaChange(Sims.Box, Sims.d_a, Sims.Old, FF, Sims.Blocksum, SystemComponents, SelectedComponent, oldScale, newScale, MoveType);",
+         "    b200_take_single_body(tot);\n    if(!FF.noCharges && SystemComponents.hasPartialCharge[SelectedComponent])\n    {\n"
+         "      double2 EwaldE = b200_ewald_delta_lambda_change(SelectedComponent, oldScale, newScale, MoveType);"),
+        (f"    update_CBCF_scale<<<1,{MS}>>>(Sims.d_a, start_position, SelectedComponent, InterScale);",
+         f"    b200_cbcf_set_scale(SelectedComponent, start_position / {MS}, InterScale);"),
+        (f"    if(!Accepted) Revert_CBCF_Insertion<<<1, {MS}>>>(Sims.d_a, SelectedComponent, start_position, oldScale);",
+         f"    if(!Accepted) b200_cbcf_set_scale(SelectedComponent, start_position / {MS}, oldScale);"),
+        (f"        Update_insertion_data_Parallel<<<1,{MS}>>>(Sims.d_a, Sims.Old, Sims.New, SelectedTrial, SelectedComponent, UpdateLocation, (int) {MS});",
+         "        b200_accept_insertion(SelectedComponent);"),
+        (f"    Update_deletion_data_fractional<<<1,1>>>(Sims.d_a, SelectedComponent, UpdateLocation, (int) {MS}, LastLocation);",
+         f"    b200_cbcf_deletion_stage(SelectedComponent, UpdateLocation / {MS}, false);"),
+        (f"      Revert_CBCF_Deletion<<<1,1>>>(Sims.d_a, Sims.New, SelectedComponent, UpdateLocation, (int) {MS}, LastLocation);",
+         f"      b200_cbcf_deletion_stage(SelectedComponent, UpdateLocation / {MS}, true);"),
+        # accepted lambda change (:487) and accepted CBCF deletion (:427): scaling factors + swap of the structure-factor vectors
+        (f"update_CBCF_scale<<<1,{MS}>>>(Sims.d_a, start_position, SelectedComponent, newScale);",
+         f"b200_accept_lambda_change(SelectedComponent, start_position / {MS}, newScale);", 2)])
+    patch(f"{scr}/main.cpp", [("    check_energy_wrapper(Vars, i);\n    //Report Random Number Summary", "    b200_sync_back(Vars, i);\n    check_energy_wrapper(Vars, i);\n    //Report Random Number Summary"),
+                              # the CREATE_MOLECULE stage check reads Sims.d_a as well (molecules created through the engine)
+                              ("    Check_Simulation_Energy(Vars.Box[a], Vars.SystemComponents[a].HostSystem, Vars.FF, Vars.device_FF, Vars.SystemComponents[a], CREATEMOL, a, Vars.Sims[a], true);",
+                               "    b200_sync_back(Vars, a, false);\n    Check_Simulation_Energy(Vars.Box[a], Vars.SystemComponents[a].HostSystem, Vars.FF, Vars.device_FF, Vars.SystemComponents[a], CREATEMOL, a, Vars.Sims[a], true);")])
 
 
 if __name__ == "__main__":

@@ -693,6 +693,62 @@ def test_cbcf_insertion_and_deletion_compositions(gpu_engine_factory, oracle):
     eng.close()
 
 
+def test_fractional_molecule_created_by_an_insertion_is_seen_by_later_moves(gpu_engine_factory):
+    """CreateMolecule_InOneBox (axpy.cu:322-349) creates the fractional molecule of a CB/CFC component by an ordinary CBMC insertion
+    with TempVal.Scale = SET_SCALE(lambda).  From then on every pair loop has to honour the scaling factors of system atoms (the engine
+    skips them while every atom has scale 1): translations and reinsertions of the OTHER molecules against the recomputed totals.
+    Found by the CB/CFC run of the bound reference program: one reinsertion next to the fresh fractional molecule was off by 0.049 in
+    guest-guest VDW."""
+    box, ff, s, z, eng = _setup(gpu_engine_factory, "B", grow=600)
+    comp = 1; ms = 3
+    rng = np.random.default_rng(5)
+    pool = rng.random((8192, 3)); eng.upload_random_pool(pool)
+    eng.total_ewald(store=True)
+    E0 = _totals_no_tail(eng); run = 0.0; off = 0
+    sc = (0.5, 0.5 ** 5)
+    # grow the fractional molecule next to an existing one, so that guest-guest pairs with it matter
+    target = s.pos[int(s.offsets[comp]) + 3 * 4]
+    while True:
+        fb = eng.cbmc_first_bead(CBMC_INSERTION, comp, 0, off, rng.random(), scale=sc); off += 10
+        if not fb["success"]:
+            continue
+        ch = eng.cbmc_chain(CBMC_INSERTION, comp, 0, off, rng.random()); off += 10
+        if ch["success"]:
+            break
+    ew = eng.ewald_delta(comp, INSERTION, location=ch["selected"], scale=sc)
+    eng.accept_insertion(comp); run += fb["energy"].sum() + ch["energy"].sum() + ew.sum()
+    nmol = eng.number_of_molecules(comp); frac = nmol - 1
+    a = eng.download_atoms(comp)
+    assert np.all(a["scale"][frac * ms:(frac + 1) * ms] == sc[0]) and np.all(a["scale_coul"][frac * ms:(frac + 1) * ms] == sc[1])
+    assert abs((_totals_no_tail(eng) - E0) - run) <= 1e-9 * max(1.0, abs(E0))
+    # bring molecules close to the fractional one and move them around it
+    done = 0
+    for mol in range(nmol - 1):
+        for kind in (TRANSLATION, ROTATION):
+            eng.single_body_propose(kind, comp, mol, (1.0, 1.0, 1.0), off, want_pos=False); off += 3
+            d, ov = eng.single_body_delta(comp)
+            if ov:
+                continue
+            ew = eng.ewald_delta(comp, kind)
+            eng.accept_translation(comp); run += _sb_sum(d) + ew.sum(); done += 1
+        fb = eng.cbmc_first_bead(REINSERTION_INSERTION, comp, mol, off, rng.random()); off += 10
+        if not fb["success"]:
+            continue
+        ch = eng.cbmc_chain(REINSERTION_INSERTION, comp, mol, off, rng.random()); off += 10
+        if not ch["success"]:
+            continue
+        eng.reinsertion_store(comp)
+        rb = eng.cbmc_first_bead(REINSERTION_RETRACE, comp, mol, off, 0.5, stored_r=fb["stored_r"]); off += 1
+        rc = eng.cbmc_chain(REINSERTION_RETRACE, comp, mol, off, 0.5); off += 10
+        ew = eng.ewald_delta(comp, REINSERTION, location=mol * ms)
+        eng.accept_reinsertion(comp, mol); done += 1
+        run += (fb["energy"].sum() + ch["energy"].sum()) - (rb["energy"].sum() + rc["energy"].sum()) + ew.sum()
+    E1 = _totals_no_tail(eng)
+    assert done >= nmol
+    assert abs((E1 - E0) - run) <= 1e-9 * max(1.0, abs(E0), abs(E1)), (E1 - E0, run)
+    eng.close()
+
+
 @pytest.mark.parametrize("b", [1, 4])
 def test_host_driver_reads_and_writes_raspa2_restarts(b, tmp_path):
     """The NIST SPC/E decks end to end through the C++ host driver: `RestartFile yes` (RestartFileParser,

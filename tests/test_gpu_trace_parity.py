@@ -134,6 +134,30 @@ def test_pipelined_widom_replay_gives_the_single_lane_averages(tmp_path):
 REF_OVERLAY = os.path.join(ROOT, "oracle", "_ref", "graspa_ref_overlay.x")
 
 
+def _stock_and_overlay(d, tmp_path):
+    """runs the stock reference (trace build) and the reference bound to libgraspa_b200.so on deck d; -> their outputs, both traces,
+    the number of moves whose component / move type / accepted-or-not differ, accepted moves, worst relative energy difference"""
+    traces = {}
+    outs = {}
+    for tag, exe in (("stock", REF_TRACE), ("overlay", REF_OVERLAY)):
+        tr = str(tmp_path / f"{tag}_trace.txt")
+        r = subprocess.run([exe], cwd=d, env=dict(os.environ, GRASPA_TRACE=tr), capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0, (tag, (r.stdout + r.stderr)[-3000:])
+        traces[tag] = [l.split() for l in open(tr)]
+        outs[tag] = r
+    a, b = traces["stock"], traces["overlay"]
+    differ = 0; worst = 0.0; accepted = 0
+    for x, y in zip(a, b):
+        dx, dy = float(x[2]), float(y[2])
+        if x[0] != y[0] or x[1] != y[1] or (dx != 0.0) != (dy != 0.0):
+            differ += 1
+        elif dx != 0.0:
+            accepted += 1
+            worst = max(worst, abs(dx - dy) / max(abs(dx), 1e-4))     # floor: a move of a molecule at lambda = 0 changes the energy by rounding noise only
+    print("overlay vs stock:", len(a), "moves,", accepted, "accepted,", differ, "differ, worst relative energy difference", worst)
+    return outs, a, b, differ, accepted, worst
+
+
 def test_reference_drivers_bound_to_the_c_abi_reproduce_the_stock_reference(tmp_path):
     """The drop-in, demonstrated: the reference's OWN program with its hot-path call sites bound to libgraspa_b200.so
     (oracle/overlay/: the adapter header a maintainer would add + the call-site patch, applied to a scratch copy by
@@ -145,25 +169,8 @@ def test_reference_drivers_bound_to_the_c_abi_reproduce_the_stock_reference(tmp_
         if not os.path.exists(need):
             pytest.skip(f"{need} not built (oracle/build_ref.sh trace / overlay)")
     d = _deck_copy("CO2-MFI", tmp_path, 10000, 0)
-    traces = {}
-    outs = {}
-    for tag, exe in (("stock", REF_TRACE), ("overlay", REF_OVERLAY)):
-        tr = str(tmp_path / f"{tag}_trace.txt")
-        r = subprocess.run([exe], cwd=d, env=dict(os.environ, GRASPA_TRACE=tr), capture_output=True, text=True, timeout=1500)
-        assert r.returncode == 0, (tag, (r.stdout + r.stderr)[-3000:])
-        traces[tag] = [l.split() for l in open(tr)]
-        outs[tag] = r
-    a, b = traces["stock"], traces["overlay"]
+    outs, a, b, differ, accepted, worst = _stock_and_overlay(d, tmp_path)
     assert len(a) == len(b) and len(a) > 200000, (len(a), len(b))
-    differ = 0; worst = 0.0; accepted = 0
-    for x, y in zip(a, b):
-        dx, dy = float(x[2]), float(y[2])
-        if x[0] != y[0] or x[1] != y[1] or (dx != 0.0) != (dy != 0.0):
-            differ += 1
-        elif dx != 0.0:
-            accepted += 1
-            worst = max(worst, abs(dx - dy) / abs(dx))
-    print("overlay vs stock:", len(a), "moves,", accepted, "accepted,", differ, "differ, worst relative energy difference", worst)
     assert differ == 0 and accepted > 50000 and worst < 1e-8
     # the engine really served the run, and the reference's own end-of-run check is content with the state it left
     assert "engine kernel launches served the reference's drivers" in outs["overlay"].stderr
@@ -179,3 +186,44 @@ def test_reference_drivers_bound_to_the_c_abi_reproduce_the_stock_reference(tmp_
         k = max(i for i, ln in enumerate(lines) if header in ln)
         return float([ln for ln in lines[k:k + 25] if ln.startswith("Total Energy:")][0].split(":")[1].split("(")[0])
     assert abs(block_total(outs["overlay"].stdout, "ENERGY DRIFT (CPU FINAL - RUNNING FINAL)")) < 1e-3      # the reference's own criterion (test_examples.py:59-61)
+
+
+def test_cbcf_moves_through_the_bound_reference_reproduce_the_stock_reference(tmp_path):
+    """CB/CFC through the drop-in: the CO2-MFI deck with `CBCFProbability` added (no example deck of the reference uses CB/CFC), 8
+    molecules created, 3000 cycles, stock reference against the reference bound to libgraspa_b200.so.  CBCFMove, its lambda bins and
+    its Wang-Landau bookkeeping stay the reference's code (mc_cbcfc.h:224-495); the kernels under it go through gb_lambda_change_delta,
+    gb_ewald_delta_lambda_change, gb_cbcf_set_scale, gb_cbcf_deletion_stage and gb_accept_lambda_change.  Same decisions move by move,
+    the same CBCF statistics, no drift in the reference's own final energy check.  (The stock program accepts lambda changes only: its
+    fractional insertion / deletion branches test a local SuccessConstruction that nothing sets, mc_cbcfc.h:307-318, :372-393 -- their
+    first steps and reversals still run and are compared; the accepted compositions are pinned in
+    tests/test_gpu_moves.py::test_cbcf_insertion_and_deletion_compositions.)"""
+    for need in (REF_TRACE, REF_OVERLAY):
+        if not os.path.exists(need):
+            pytest.skip(f"{need} not built (oracle/build_ref.sh trace / overlay)")
+    d = _deck_copy("CO2-MFI", tmp_path, 3000, 0)
+    p = os.path.join(d, "simulation.input")
+    out = []
+    for ln in open(p).read().splitlines():
+        if "CreateNumberOfMolecules" in ln:
+            ln = ln.replace(" 0", " 8")
+        out.append(ln)
+        if "SwapProbability" in ln:
+            pad = ln[:len(ln) - len(ln.lstrip())]
+            out += [pad + "CBCFProbability          1.0", pad + "LambdaType               ShiMaginn"]
+    open(p, "w").write("\n".join(out) + "\n")
+    outs, a, b, differ, accepted, worst = _stock_and_overlay(d, tmp_path)
+    assert len(a) == len(b) and len(a) > 50000, (len(a), len(b))
+    assert differ == 0 and accepted > 5000 and worst < 1e-8, (differ, accepted, worst)
+    def stats(text):
+        return [ln for ln in text.splitlines() if ln.startswith("CBCF ")]
+    st = stats(outs["stock"].stdout)
+    assert len(st) >= 8 and st == stats(outs["overlay"].stdout), (st, stats(outs["overlay"].stdout))
+    val = lambda key: int([ln for ln in st if ln.startswith(key)][0].split(":")[1])
+    assert val("CBCF Lambda Accepted") > 1000 and val("CBCF Insertion Performed") > 1000 and val("CBCF Deletion Performed") > 10
+    assert val("CBCF Insertion Accepted") == 0 and val("CBCF Deletion Accepted") == 0          # the reference's dead branches, see above
+    def block_total(text, header):
+        lines = text.splitlines()
+        k = max(i for i, ln in enumerate(lines) if header in ln)
+        return float([ln for ln in lines[k:k + 25] if ln.startswith("Total Energy:")][0].split(":")[1].split("(")[0])
+    assert abs(block_total(outs["overlay"].stdout, "*** FINAL STAGE ***") - block_total(outs["stock"].stdout, "*** FINAL STAGE ***")) < 2e-5
+    assert abs(block_total(outs["overlay"].stdout, "ENERGY DRIFT (CPU FINAL - RUNNING FINAL)")) < 1e-3
