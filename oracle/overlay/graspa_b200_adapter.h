@@ -66,7 +66,9 @@ inline gb_engine* b200_engine(Variables& Vars, size_t sim)
     a.pos = reinterpret_cast<const double*>(A.pos); a.scale = A.scale; a.charge = A.charge; a.scale_coul = A.scaleCoul;
     a.type = reinterpret_cast<const uint64_t*>(A.Type); a.molid = reinterpret_cast<const uint64_t*>(A.MolID);
     GB_CHECK(gb_upload_atoms(G.e, (int32_t) c, &a));
-    GB_CHECK(gb_set_exclusion_constants(G.e, (int32_t) c, SC.ExclusionIntra[c], SC.ExclusionAtom[c], SC.rigid[c], SC.hasPartialCharge[c]));
+    // the exclusion constants exist only when the deck has charges (ewald_preparation.h:261-366 fills them)
+    const double xi = c < SC.ExclusionIntra.size() ? SC.ExclusionIntra[c] : 0.0, xa = c < SC.ExclusionAtom.size() ? SC.ExclusionAtom[c] : 0.0;
+    GB_CHECK(gb_set_exclusion_constants(G.e, (int32_t) c, xi, xa, SC.rigid[c], SC.hasPartialCharge[c]));
   }
   GB_CHECK(gb_set_cbmc(G.e, (int32_t) Vars.Widom[sim].NumberWidomTrials, (int32_t) Vars.Widom[sim].NumberWidomTrialsOrientations, SC.Beta));
   // the CPU Ewald_Total of the reference (ewald_preparation.h:5-259) is replaced by a build of the structure factors on the GPU
@@ -89,8 +91,11 @@ inline void b200_first_bead(Variables& Vars, size_t systemId, CBMC_Variables& CB
   Random.Check(ntr);
   const double scale[2] = {SC.TempVal.Scale.x, SC.TempVal.Scale.y};
   gb_cbmc_result r; int32_t used = 0;
+  // Sims.ExcludeList[0] (managed memory, written by IdentitySwapMove mc_swap_moves.h:268): the molecule left out of the pair sums; for
+  // IDENTITY_SWAP_NEW the engine also takes the single trial position from its first atom (copy_firstbead_to_new, :178-181)
+  const int2 ex = Vars.Sims[systemId].ExcludeList[0];
   GB_CHECK(gb_cbmc_first_bead(e, type, (int32_t) comp, (int64_t) SC.TempVal.molecule, (int64_t) Random.offset, Peek_Uniform_Random(), scale, CBMC.StoredR,
-                              -1, -1, nullptr, &r, &used));
+                              ex.x, ex.y, nullptr, &r, &used));
   Random.Update(ntr);
   if(used) Get_Uniform_Random();                        // the draw SelectTrialPosition would have made (mc_widom.h:14-39)
   SC.Rosen.clear(); SC.TrialEnergies.clear(); SC.Trialindex.clear();
@@ -110,7 +115,8 @@ inline void b200_chain(Variables& Vars, size_t systemId, CBMC_Variables& CBMC)
   const size_t comp = SC.TempVal.component; const int type = CBMC.MoveType;
   Random.Check(Widom.NumberWidomTrialsOrientations);
   gb_cbmc_result r; int32_t used = 0;
-  GB_CHECK(gb_cbmc_chain(e, type, (int32_t) comp, (int64_t) SC.TempVal.molecule, (int64_t) Random.offset, Peek_Uniform_Random(), -1, -1, &r, &used));
+  const int2 ex = Vars.Sims[systemId].ExcludeList[0];
+  GB_CHECK(gb_cbmc_chain(e, type, (int32_t) comp, (int64_t) SC.TempVal.molecule, (int64_t) Random.offset, Peek_Uniform_Random(), ex.x, ex.y, &r, &used));
   Random.Update(Widom.NumberWidomTrialsOrientations);
   if(used) Get_Uniform_Random();
   SC.Rosen.clear(); SC.TrialEnergies.clear(); SC.Trialindex.clear();
@@ -176,6 +182,16 @@ inline void b200_accept_lambda_change(size_t comp, size_t molecule, double2 scal
 inline void b200_cbcf_deletion_stage(size_t comp, size_t molecule, bool revert)
 { GB_CHECK(gb_cbcf_deletion_stage(b200().e, (int32_t) comp, (int64_t) molecule, revert ? 1 : 0)); }
 
+// IdentitySwapMove (mc_swap_moves.h:355, :393-412)
+inline double2 b200_ewald_delta_identity_swap(size_t oldc, size_t newc, size_t update_location)
+{
+  double out[2] = {0.0, 0.0};
+  GB_CHECK(gb_ewald_delta_identity_swap(b200().e, (int32_t) oldc, (int32_t) newc, (int64_t) update_location, out));
+  return {out[0], out[1]};
+}
+inline void b200_accept_identity_swap(size_t oldc, size_t oldmol, size_t newc)
+{ GB_CHECK(gb_accept_identity_swap(b200().e, (int32_t) oldc, (int64_t) oldmol, (int32_t) newc)); }
+
 // state commits (mc_utilities.h:294-417, move_struct.h:271,371): each includes the swap of the structure-factor vectors
 inline void b200_accept_translation(size_t comp) { GB_CHECK(gb_accept_translation(b200().e, (int32_t) comp)); }
 inline void b200_accept_insertion(size_t comp) { GB_CHECK(gb_accept_insertion(b200().e, (int32_t) comp)); }
@@ -207,11 +223,14 @@ inline void b200_sync_back(Variables& Vars, size_t sim, bool report = true)
     dev[c].size = (size_t) live;
   }
   cudaMemcpy(Sims.d_a, dev.data(), nc * sizeof(Atoms), cudaMemcpyHostToDevice);
-  const size_t nvec = (size_t) (Sims.Box.kmax.x + 1) * (2 * Sims.Box.kmax.y + 1) * (2 * Sims.Box.kmax.z + 1);
-  std::vector<double> ads(2 * nvec), fw(2 * nvec);
-  GB_CHECK(gb_download_structure_factors(G.e, ads.data(), fw.data(), nullptr));
-  cudaMemcpy(Sims.Box.AdsorbateEik, ads.data(), 2 * nvec * sizeof(double), cudaMemcpyHostToDevice);
-  cudaMemcpy(Sims.Box.FrameworkEik, fw.data(), 2 * nvec * sizeof(double), cudaMemcpyHostToDevice);
+  if(!Vars.FF.noCharges)       // a deck without charges has no structure-factor arrays (Allocate_Copy_Ewald_Vector is not reached)
+  {
+    const size_t nvec = (size_t) (Sims.Box.kmax.x + 1) * (2 * Sims.Box.kmax.y + 1) * (2 * Sims.Box.kmax.z + 1);
+    std::vector<double> ads(2 * nvec), fw(2 * nvec);
+    GB_CHECK(gb_download_structure_factors(G.e, ads.data(), fw.data(), nullptr));
+    cudaMemcpy(Sims.Box.AdsorbateEik, ads.data(), 2 * nvec * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(Sims.Box.FrameworkEik, fw.data(), 2 * nvec * sizeof(double), cudaMemcpyHostToDevice);
+  }
   cudaDeviceSynchronize();
   int64_t launches = 0; gb_launch_count(G.e, &launches, 0);
   if(report) fprintf(stderr, "graspa_b200 overlay: %lld engine kernel launches served the reference's drivers\n", (long long) launches);

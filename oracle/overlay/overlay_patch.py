@@ -18,12 +18,16 @@ What is redirected (file:line of the reference):
   main.cpp:340, :427            before the CREATE_MOLECULE and FINAL energy checks -> engine state copied back into Sims.d_a (the reference's own CPU + GPU
                                                                  total-energy routines then judge the run: ENERGY DRIFT)
   axpy.cu:297                   the one-line move trace of `build_ref.sh trace`
+  mc_swap_moves.h:266,298,355,393-412  IdentitySwapMove: copy_firstbead_to_new / StoreNewLocation_Reinsertion<<<>>> -> (engine) / gb_reinsertion_store;
+                                GPU_EwaldDifference_IdentitySwap -> gb_ewald_delta_identity_swap; Update_deletion_data + Update_IdentitySwap_Insertion_data /
+                                Update_Reinsertion_data<<<>>> -> gb_accept_identity_swap
   mc_cbcfc.h:39-104             Prepare_LambdaChange / Calculate_Single_Body_Energy_VDWReal_LambdaChange<<<>>> + host sum -> gb_lambda_change_delta;
                                 GPU_EwaldDifference_LambdaChange -> gb_ewald_delta_lambda_change
   mc_cbcfc.h:312,359,427,487    update_CBCF_scale / Revert_CBCF_Insertion<<<>>> -> gb_cbcf_set_scale (provisional) / gb_accept_lambda_change (accepted)
   mc_cbcfc.h:382,441            Update_deletion_data_fractional / Revert_CBCF_Deletion<<<>>> -> gb_cbcf_deletion_stage
   mc_cbcfc.h:343                Update_insertion_data_Parallel<<<>>> of an accepted CBCF insertion -> gb_accept_insertion
-Scope: the moves of the CO2-MFI deck (translation, rotation, CBMC insertion / deletion, reinsertion) and, with CBCFProbability added to
+Scope: the moves of the CO2-MFI deck (translation, rotation, CBMC insertion / deletion, reinsertion), the identity swap of the
+XeKr-Mixture deck, the Widom move of the Henrys_coefficient deck (it is Insertion_Body) and, with CBCFProbability added to
 that deck, the CB/CFC move (lambda change; the first steps and the reversal of a fractional insertion / deletion -- the reference's
 CBCFMove never accepts those two: it tests a local SuccessConstruction that nothing sets, mc_cbcfc.h:307-318, :372-393)."""
 import sys
@@ -83,6 +87,21 @@ def main(scr):
          "      b200_reinsertion_store(SelectedComponent);"),
         ("    Update_Reinsertion_data<<<1,SystemComponents.Moleculesize[SelectedComponent]>>>(Sims.d_a, SystemComponents.tempMolStorage, SelectedComponent, UpdateLocation); checkCUDAError(\"error Updating Reinsertion data\");",
          "    b200_accept_reinsertion(SelectedComponent, SystemComponents.TempVal.molecule);")])
+    # IdentitySwapMove (mc_swap_moves.h:199-431): the first bead of the new species is read by the engine from the molecule named in
+    # Sims.ExcludeList[0] (b200_first_bead passes the list entry on), the grown molecule is kept aside, both commits are one call
+    patch(f"{scr}/mc_swap_moves.h", [
+        ("  copy_firstbead_to_new<<<1,1>>>(Sims.New, Sims.d_a, OLDComponent, OLDMolInComponent * SystemComponents.Moleculesize[OLDComponent]);",
+         "  b200_engine(Vars, systemId);"),
+        ("  StoreNewLocation_Reinsertion<<<1,SystemComponents.Moleculesize[NEWComponent]>>>(Sims.Old, Sims.New, SystemComponents.tempMolStorage, SelectedTrial, SystemComponents.Moleculesize[NEWComponent]);",
+         "  b200_reinsertion_store(NEWComponent);"),
+        ("    double2 EwaldE = GPU_EwaldDifference_IdentitySwap(Sims.Box, Sims.d_a, Sims.Old, SystemComponents.tempMolStorage, FF, Sims.Blocksum, SystemComponents, OLDComponent, NEWComponent, UpdateLocation);",
+         "    double2 EwaldE = b200_ewald_delta_identity_swap(OLDComponent, NEWComponent, UpdateLocation);"),
+        ("      Update_deletion_data<<<1,1>>>(Sims.d_a, OLDComponent, UpdateLocation, (int) SystemComponents.Moleculesize[OLDComponent], LastLocation);",
+         "      b200_accept_identity_swap(OLDComponent, OLDMolInComponent, NEWComponent);"),
+        ("      Update_IdentitySwap_Insertion_data<<<1,1>>>(Sims.d_a, SystemComponents.tempMolStorage, NEWComponent, UpdateLocation, NEWMolInComponent, SystemComponents.Moleculesize[NEWComponent]); checkCUDAError(\"error Updating Identity Swap Insertion data\");",
+         "      // (the engine appended the new molecule in b200_accept_identity_swap)"),
+        ("      Update_Reinsertion_data<<<1,SystemComponents.Moleculesize[OLDComponent]>>>(Sims.d_a, SystemComponents.tempMolStorage, OLDComponent, UpdateLocation);",
+         "      b200_accept_identity_swap(OLDComponent, OLDMolInComponent, NEWComponent);")])
     MS = "SystemComponents.Moleculesize[SelectedComponent]"
     patch(f"{scr}/mc_cbcfc.h", [
         ("  Prepare_LambdaChange<<<1, Molsize>>>(Sims.d_a, Sims.Old, Sims, FF, start_position, SelectedComponent, Sims.device_flag);",

@@ -158,7 +158,11 @@ def _stock_and_overlay(d, tmp_path):
     return outs, a, b, differ, accepted, worst
 
 
-def test_reference_drivers_bound_to_the_c_abi_reproduce_the_stock_reference(tmp_path):
+@pytest.mark.parametrize("deck,min_moves,min_accepted,min_launches", [
+    ("CO2-MFI", 200000, 50000, 400000),          # translation / rotation / CBMC insertion / deletion / reinsertion, Ewald
+    ("XeKr-Mixture", 10000, 2000, 20000),        # + IdentitySwapMove (mc_swap_moves.h:199-431), two species, tail corrections
+])
+def test_reference_drivers_bound_to_the_c_abi_reproduce_the_stock_reference(deck, min_moves, min_accepted, min_launches, tmp_path):
     """The drop-in, demonstrated: the reference's OWN program with its hot-path call sites bound to libgraspa_b200.so
     (oracle/overlay/: the adapter header a maintainer would add + the call-site patch, applied to a scratch copy by
     oracle/build_ref.sh overlay; RunMoves, Insertion_Body, Deletion_Body, ReinsertionMove, SingleBodyMove, the acceptance tests and
@@ -168,14 +172,14 @@ def test_reference_drivers_bound_to_the_c_abi_reproduce_the_stock_reference(tmp_
     for need in (REF_TRACE, REF_OVERLAY):
         if not os.path.exists(need):
             pytest.skip(f"{need} not built (oracle/build_ref.sh trace / overlay)")
-    d = _deck_copy("CO2-MFI", tmp_path, 10000, 0)
+    d = _deck_copy(deck, tmp_path, 10000, 0)
     outs, a, b, differ, accepted, worst = _stock_and_overlay(d, tmp_path)
-    assert len(a) == len(b) and len(a) > 200000, (len(a), len(b))
-    assert differ == 0 and accepted > 50000 and worst < 1e-8
+    assert len(a) == len(b) and len(a) > min_moves, (len(a), len(b))
+    assert differ == 0 and accepted > min_accepted and worst < 1e-8, (differ, accepted, worst)
     # the engine really served the run, and the reference's own end-of-run check is content with the state it left
     assert "engine kernel launches served the reference's drivers" in outs["overlay"].stderr
     launches = int(outs["overlay"].stderr.split("graspa_b200 overlay:")[1].split()[0])
-    assert launches > 400000
+    assert launches > min_launches
     def final_total(text):
         lines = text.splitlines()
         k = max(i for i, ln in enumerate(lines) if "*** FINAL STAGE ***" in ln)
@@ -186,6 +190,27 @@ def test_reference_drivers_bound_to_the_c_abi_reproduce_the_stock_reference(tmp_
         k = max(i for i, ln in enumerate(lines) if header in ln)
         return float([ln for ln in lines[k:k + 25] if ln.startswith("Total Energy:")][0].split(":")[1].split("(")[0])
     assert abs(block_total(outs["overlay"].stdout, "ENERGY DRIFT (CPU FINAL - RUNNING FINAL)")) < 1e-3      # the reference's own criterion (test_examples.py:59-61)
+
+
+def test_widom_deck_through_the_bound_reference_prints_the_stock_averages(tmp_path):
+    """Examples/Henrys_coefficient through the drop-in: the reference's Widom move (axpy.cu:163-186) is Insertion_Body, whose stages the
+    overlay binds; per-block <W>, the average and the Henry coefficient of the bound program against the UNMODIFIED reference program."""
+    for need in (REF_PLAIN, REF_OVERLAY):
+        if not os.path.exists(need):
+            pytest.skip(f"{need} not built (oracle/build_ref.sh cuda / overlay)")
+    d = _deck_copy("Henrys_coefficient", tmp_path, 0, 20000)
+    res = {}
+    for tag, exe in (("stock", REF_PLAIN), ("overlay", REF_OVERLAY)):
+        r = subprocess.run([exe], cwd=d, capture_output=True, text=True, timeout=1200)
+        assert r.returncode == 0, (tag, (r.stdout + r.stderr)[-2000:])
+        res[tag] = _widom_lines(r.stdout)
+        if tag == "overlay":
+            assert "engine kernel launches served the reference's drivers" in r.stderr
+    (w0, a0, k0), (w1, a1, k1) = res["stock"], res["overlay"]
+    assert len(w0) == 5 and len(w1) == 5 and a0 is not None and k0 is not None
+    for x, y in zip(w1, w0):
+        assert abs(x - y) <= 1e-9 * abs(y) + 2e-10, (w1, w0)
+    assert abs(a1 - a0) <= 1e-9 * abs(a0) + 2e-10 and abs(k1 - k0) <= 1e-9 * abs(k0) + 1e-14
 
 
 def test_cbcf_moves_through_the_bound_reference_reproduce_the_stock_reference(tmp_path):
