@@ -18,6 +18,8 @@ value : inputs (random pool, uniforms) already resident in HBM; sums read back.
 e2e   : the same step through the C ABI with HOST (pinned) buffers: H2D of the randoms and D2H of the sums inside
         the timed region (e2e_pageable: the same from pageable host memory).
 Timing: CUDA events recorded on the engine's own stream (made torch's current stream), max over ranks.
+Extra key at every N (skipped with --no-secondary): "multibox_xekr" -- BASELINE.json configs[3], one Xe/Kr isotherm point per GPU through the
+host driver, each rank on its own GPU, no exchange: aggregate cycles/s = all boxes' cycles / the slowest box's Monte Carlo loop time.
 Extra keys (N=1 only, skipped with --no-secondary): "gcmc" -- cycles/s of the sequential Markov chain on the reference's
 CO2-MFI example through the host driver (one kernel per move), with the reference's own CUDA build (oracle/_ref) timed
 beside it on the same GPU when the binary is present.
@@ -245,6 +247,40 @@ def more_secondaries():
             "gibbs_co2": _deck_pair("NVT-Gibbs", 20, 0, "cycles/s")}
 
 
+MULTIBOX_PRESSURES = [1e4, 3e4, 1e5, 3e5, 1e6, 3e6, 1e7, 3e7]
+
+
+def multibox_point(rank, local, cycles=100000):
+    """BASELINE.json configs[3]: one Xe/Kr isotherm point per GPU (the reference works through its boxes one after the other on one
+    GPU, Run_Simulation_MultipleBoxes axpy.cu:593-625).  Every rank runs the point of its own pressure through the host driver on its
+    own GPU (graspa_b200/boxes.py); nothing is exchanged.  -> this rank's record."""
+    from graspa_b200.boxes import run_boxes
+    deck = os.path.join(ROOT, "oracle", "_ref", "examples", "XeKr-Mixture")
+    if not os.path.isdir(deck):
+        return {"error": "example deck not built (oracle/build_ref.sh examples)"}
+    try:
+        t0 = time.perf_counter()
+        res, wall = run_boxes(deck, [{"pressure": MULTIBOX_PRESSURES[rank % len(MULTIBOX_PRESSURES)]}], gpus=1, init=cycles, prod=0, devices=[local], timeout=600)
+        r = res[0]; run = r.get("run") or {}
+        return {"rank": rank, "pressure_pa": r["point"]["pressure"], "returncode": r["returncode"], "cycles": run.get("cycles"), "mc_seconds": run.get("seconds"),
+                "cycles_per_s": run.get("cycles_per_s"), "process_seconds": time.perf_counter() - t0, "loading": r.get("loading"),
+                "energy_drift": r.get("energy_drift"), "stderr": r.get("stderr")}
+    except Exception as ex:  # noqa: BLE001
+        return {"rank": rank, "error": str(ex)}
+
+
+def multibox_summary(recs):
+    ok = [r for r in recs if r.get("cycles") and r.get("mc_seconds")]
+    out = {"workload": "XeKr-Mixture example deck, one isotherm point (pressure) per GPU, %d cycles each, no exchange between boxes" % (ok[0]["cycles"] if ok else 0),
+           "unit": "cycles/s", "boxes": len(recs), "per_box": recs}
+    if len(ok) == len(recs) and ok:
+        cyc = sum(r["cycles"] for r in ok)
+        out["value"] = cyc / max(r["mc_seconds"] for r in ok)              # Monte Carlo work: all boxes' cycles / the slowest box's loop time
+        out["value_incl_process_start"] = cyc / max(r["process_seconds"] for r in ok)
+        out["max_abs_energy_drift"] = max(abs(r["energy_drift"]) for r in ok if r.get("energy_drift") is not None) if any(r.get("energy_drift") is not None for r in ok) else None
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -431,6 +467,18 @@ def main():
     dt_pin1, _ = timed(lambda: step_host(hp, hu), min(args.steps, 3))
     subs = subs_saved
 
+    # independent boxes, one per GPU (configs[3]): every rank runs its own isotherm point, the records are gathered on rank 0
+    mb = None
+    if not args.no_secondary:
+        if world > 1:
+            dist.barrier()
+        mine = multibox_point(rank, local)
+        if world > 1:
+            allrec = [None] * world
+            dist.all_gather_object(allrec, mine)
+        else:
+            allrec = [mine]
+        mb = multibox_summary(allrec)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -457,6 +505,8 @@ def main():
             "kernels": {"pair_stage_ms": ms_pair / nsub, "k_wc_energy_ms": ms_en / max(n_en, 1), "k_wc_energy_launches_per_sub_batch": n_en / nsub,
                         "k_widom_ewald_ms": ms_ew / nsub, "insertions_per_sub_batch": subs[0][1],
                         "how": "CUDA events around the launches on the engine's stream, one extra step after the timed ones"}}
+    if mb is not None:
+        line["multibox_xekr"] = mb
     if args.write_job_sums and world == 1 and args.scaling == "strong":
         json.dump({"total": total, "seed": JOB_SEED, "workload": WORKLOAD, "sums": sums.tolist(),
                    "columns": "per block: sumW, sumW2, count, sum(W*E) x 7, n_failed, reserved"}, open(JOB_SUMS, "w"), indent=1)

@@ -41,10 +41,11 @@ def _json_lines(text):
     return out
 
 
-def run_boxes(deck, points, gpus=1, init=None, prod=None, equil=0, driver=DRIVER, extra=(), timeout=3600):
+def run_boxes(deck, points, gpus=1, init=None, prod=None, equil=0, driver=DRIVER, extra=(), timeout=3600, devices=None):
     """points: list of dicts with optional keys pressure (Pa), temperature (K), seed.  -> list of per-box results in the
     order of `points`: {"box", "gpu", "point", "seconds", "returncode", "loading": [...], "run": {...}, "final_total_energy"}.
-    One worker thread per GPU feeds that GPU's queue; the driver processes do the work."""
+    One worker thread per GPU feeds that GPU's queue; the driver processes do the work.  devices: the device of worker g
+    (default: entry g of CUDA_VISIBLE_DEVICES, else g) -- a rank of a multi-process launch passes its own device."""
     if not os.path.exists(driver):
         raise FileNotFoundError(f"{driver} is missing: make -C graspa_b200/csrc && make -C graspa_b200/host (there is no CPU path)")
     queues = assign_boxes(len(points), gpus)
@@ -56,7 +57,8 @@ def run_boxes(deck, points, gpus=1, init=None, prod=None, equil=0, driver=DRIVER
 
     def worker(g):
         env = dict(os.environ)
-        env["CUDA_VISIBLE_DEVICES"] = visible[g] if g < len(visible) else str(g)
+        dev = devices[g] if devices is not None else g
+        env["CUDA_VISIBLE_DEVICES"] = visible[dev] if dev < len(visible) else str(dev)
         for b in queues[g]:
             pt = points[b]
             cmd = [driver, deck, "--device", "0"]
