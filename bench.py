@@ -277,6 +277,8 @@ def multibox_summary(recs):
         cyc = sum(r["cycles"] for r in ok)
         out["value"] = cyc / max(r["mc_seconds"] for r in ok)              # Monte Carlo work: all boxes' cycles / the slowest box's loop time
         out["value_incl_process_start"] = cyc / max(r["process_seconds"] for r in ok)
+        # the same boxes one after the other on one GPU (what Run_Simulation_MultipleBoxes does) would take the SUM of the loop times
+        out["speedup_vs_one_after_the_other"] = sum(r["mc_seconds"] for r in ok) / max(r["mc_seconds"] for r in ok)
         out["max_abs_energy_drift"] = max(abs(r["energy_drift"]) for r in ok if r.get("energy_drift") is not None) if any(r.get("energy_drift") is not None for r in ok) else None
     return out
 
