@@ -70,6 +70,16 @@ inline gb_engine* b200_engine(Variables& Vars, size_t sim)
     const double xi = c < SC.ExclusionIntra.size() ? SC.ExclusionIntra[c] : 0.0, xa = c < SC.ExclusionAtom.size() ? SC.ExclusionAtom[c] : 0.0;
     GB_CHECK(gb_set_exclusion_constants(G.e, (int32_t) c, xi, xa, SC.rigid[c], SC.hasPartialCharge[c]));
   }
+  // block pockets as ReplicateBlockPockets left them (main.cpp:286-292, read_data.cpp:3290-3454): Cartesian centres and radii per component
+  for(size_t c = 0; c < (size_t) SC.NComponents.x; c++)
+    if(c < SC.UseBlockPockets.size() && SC.UseBlockPockets[c] && c < SC.BlockPocketCenters.size() && !SC.BlockPocketCenters[c].empty())
+    {
+      const std::vector<double3>& ctr = SC.BlockPocketCenters[c];
+      std::vector<double> xyz(3 * ctr.size());
+      for(size_t i = 0; i < ctr.size(); i++) { xyz[3 * i] = ctr[i].x; xyz[3 * i + 1] = ctr[i].y; xyz[3 * i + 2] = ctr[i].z; }
+      const bool invert = c < SC.InvertBlockPockets.size() && SC.InvertBlockPockets[c];
+      GB_CHECK(gb_set_block_pockets(G.e, (int32_t) c, (int32_t) ctr.size(), xyz.data(), SC.BlockPocketRadii[c].data(), invert ? 1 : 0));
+    }
   GB_CHECK(gb_set_cbmc(G.e, (int32_t) Vars.Widom[sim].NumberWidomTrials, (int32_t) Vars.Widom[sim].NumberWidomTrialsOrientations, SC.Beta));
   // the CPU Ewald_Total of the reference (ewald_preparation.h:5-259) is replaced by a build of the structure factors on the GPU
   gb_move_energy E; GB_CHECK(gb_total_ewald(G.e, 1, &E));

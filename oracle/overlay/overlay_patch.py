@@ -18,6 +18,8 @@ What is redirected (file:line of the reference):
   main.cpp:340, :427            before the CREATE_MOLECULE and FINAL energy checks -> engine state copied back into Sims.d_a (the reference's own CPU + GPU
                                                                  total-energy routines then judge the run: ENERGY DRIFT)
   axpy.cu:297                   the one-line move trace of `build_ref.sh trace`
+  mc_single_particle.h:83-119, mc_swap_utilities.h:46-80, move_struct.h:219-262, mc_swap_moves.h:302-330   host-side BlockedPocket tests of
+                                proposed / grown molecules -> skipped; the engine's kernels run the test (gb_set_block_pockets at set-up)
   mc_swap_moves.h:266,298,355,393-412  IdentitySwapMove: copy_firstbead_to_new / StoreNewLocation_Reinsertion<<<>>> -> (engine) / gb_reinsertion_store;
                                 GPU_EwaldDifference_IdentitySwap -> gb_ewald_delta_identity_swap; Update_deletion_data + Update_IdentitySwap_Insertion_data /
                                 Update_Reinsertion_data<<<>>> -> gb_accept_identity_swap
@@ -27,7 +29,8 @@ What is redirected (file:line of the reference):
   mc_cbcfc.h:382,441            Update_deletion_data_fractional / Revert_CBCF_Deletion<<<>>> -> gb_cbcf_deletion_stage
   mc_cbcfc.h:343                Update_insertion_data_Parallel<<<>>> of an accepted CBCF insertion -> gb_accept_insertion
 Scope: the moves of the CO2-MFI deck (translation, rotation, CBMC insertion / deletion, reinsertion), the identity swap of the
-XeKr-Mixture deck, the Widom move of the Henrys_coefficient deck (it is Insertion_Body) and, with CBCFProbability added to
+XeKr-Mixture deck, the Widom move of the Henrys_coefficient deck (it is Insertion_Body), the CO2_NaX_Zeolite deck (moves of a separated
+framework component, block pockets) and, with CBCFProbability added to
 that deck, the CB/CFC move (lambda change; the first steps and the reversal of a fractional insertion / deletion -- the reference's
 CBCFMove never accepts those two: it tests a local SuccessConstruction that nothing sets, mc_cbcfc.h:307-318, :372-393)."""
 import sys
@@ -87,6 +90,14 @@ def main(scr):
          "      b200_reinsertion_store(SelectedComponent);"),
         ("    Update_Reinsertion_data<<<1,SystemComponents.Moleculesize[SelectedComponent]>>>(Sims.d_a, SystemComponents.tempMolStorage, SelectedComponent, UpdateLocation); checkCUDAError(\"error Updating Reinsertion data\");",
          "    b200_accept_reinsertion(SelectedComponent, SystemComponents.TempVal.molecule);")])
+    # block pockets: gb_set_block_pockets hands the replicated list to the engine, whose stage kernels run BlockedPocket themselves (first-bead
+    # trials, grown molecules, proposed positions); the drivers' host-side copies of those tests read Sims.Old / Sims.New, which the bound
+    # program no longer fills, and are skipped while the engine is bound (their statistics counters stay at zero)
+    POCK = "SystemComponents.UseBlockPockets[SelectedComponent]"
+    patch(f"{scr}/mc_single_particle.h", [(f"     {POCK})\n  {{", f"     {POCK} && !b200().e)\n  {{")])
+    patch(f"{scr}/mc_swap_utilities.h", [(f"       {POCK} &&\n", f"       {POCK} && !b200().e &&\n")])
+    patch(f"{scr}/move_struct.h", [(f"       {POCK} &&\n", f"       {POCK} && !b200().e &&\n")])
+    patch(f"{scr}/mc_swap_moves.h", [("     SystemComponents.UseBlockPockets[NEWComponent])\n  {", "     SystemComponents.UseBlockPockets[NEWComponent] && !b200().e)\n  {")])
     # IdentitySwapMove (mc_swap_moves.h:199-431): the first bead of the new species is read by the engine from the molecule named in
     # Sims.ExcludeList[0] (b200_first_bead passes the list entry on), the grown molecule is kept aside, both commits are one call
     patch(f"{scr}/mc_swap_moves.h", [
