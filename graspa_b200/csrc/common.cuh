@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <math.h>
 #include "erfc_table.inc"
+#include "erfc_table10.inc"
 
 #define GBK_PI 3.14159265358979323846
 #ifdef GBK_PHASE_TIMING
@@ -41,6 +42,8 @@ struct DevParams
   const double4* __restrict__ ffA;    // LJ: {4*eps, sigma^2, shift, 1/sigma^2}; 12-6-4: {C12, C6, C4, shift}
   const double*  __restrict__ ffB;    // 12-6-4: C10
   const double*  __restrict__ erfc_tab;   // device copy of h_erfc_table
+  const double*  __restrict__ erfc_tab10; // device copy of h_erfc_table10 (degree 10 on [0, GBK_ERFC10_XMAX): the short table of k_wc_energy_lt)
+  int erfc10_ok;                      // alpha*sqrt(cut_coul2) < GBK_ERFC10_XMAX (RASPA's default Ewald precision 1e-6 gives alpha * r_cut = 3.42)
 };
 
 // system atoms, SoA over slots (fractional coordinates are derived from the Cartesian ones)

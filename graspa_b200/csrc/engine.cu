@@ -71,7 +71,7 @@ struct gb_engine
   DevParams P{};
   bool have_ff = false, have_box = false;
   int ntypes = 0;
-  DevBuf<double4> d_ffA; DevBuf<double> d_ffB; DevBuf<double> d_erfc;
+  DevBuf<double4> d_ffA; DevBuf<double> d_ffB; DevBuf<double> d_erfc, d_erfc10;
   std::vector<int> tail_use; std::vector<double> tail_e; bool has_tail = false;
   DevBuf<int> d_tail_use; DevBuf<double> d_tail_e;
 
@@ -246,6 +246,7 @@ int ready(gb_engine* e)
   e->call_serial++;
   if((e->srv_running || !e->pending_commits.empty()) && e->srv_compat == 0) { int rc = server_stop(e); if(rc) return rc; }
   e->P.erfc_table_ok = (e->P.alpha * std::sqrt(e->P.cut_coul2) < GBK_ERFC_XMAX) ? 1 : 0;
+  e->P.erfc10_ok = (e->P.alpha * std::sqrt(e->P.cut_coul2) < GBK_ERFC10_XMAX) ? 1 : 0;
   {
     // reach of the cutoff sphere along each fractional axis: |s_i| = |r . inv[:,i]| <= |r| |inv[:,i]|  (tile culling)
     const double rc = std::sqrt(e->P.no_charges ? e->P.cut_vdw2 : std::max(e->P.cut_vdw2, e->P.cut_coul2));
@@ -568,7 +569,7 @@ static int engine_init(gb_engine* e, int device)
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<0, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024)); \
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<1, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024)); \
     CUDA_TRY(cudaFuncSetAttribute(k_wc_energy_lt<2, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
-    GBK_WC_ATTR(0) GBK_WC_ATTR(1) GBK_WC_ATTR(2) GBK_WC_ATTR(3)
+    GBK_WC_ATTR(0) GBK_WC_ATTR(1) GBK_WC_ATTR(2) GBK_WC_ATTR(3) GBK_WC_ATTR(4) GBK_WC_ATTR(5)
 #undef GBK_WC_ATTR
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_move));
     CUDA_TRY(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, GBF_MAX_DYN_SMEM));
@@ -593,6 +594,9 @@ static int engine_init(gb_engine* e, int device)
   CUDA_TRY(e->d_erfc.reserve((GBK_ERFC_DEG + 1) * GBK_ERFC_NINT));
   CUDA_TRY(copy_on_stream(e, e->d_erfc.p, h_erfc_table, sizeof(h_erfc_table), cudaMemcpyHostToDevice));
   e->P.erfc_tab = e->d_erfc.p;
+  CUDA_TRY(e->d_erfc10.reserve((GBK_ERFC10_DEG + 1) * GBK_ERFC10_NINT));
+  CUDA_TRY(copy_on_stream(e, e->d_erfc10.p, h_erfc_table10, sizeof(h_erfc_table10), cudaMemcpyHostToDevice));
+  e->P.erfc_tab10 = e->d_erfc10.p;
   return GB_OK;
 }
 
@@ -606,7 +610,7 @@ int gb_engine_destroy(gb_engine* e)
   if(e->srv_hcmd) cudaFreeHost(e->srv_hcmd);
   e->srv_dcmd.release(); e->srv_done.release();
   if(e->stream) cudaStreamSynchronize(e->stream);
-  e->d_ffA.release(); e->d_ffB.release(); e->d_erfc.release(); e->d_tail_use.release(); e->d_tail_e.release();
+  e->d_ffA.release(); e->d_ffB.release(); e->d_erfc.release(); e->d_erfc10.release(); e->d_tail_use.release(); e->d_tail_e.release();
   e->dx.release(); e->dy.release(); e->dz.release(); e->dfx.release(); e->dfy.release(); e->dfz.release();
   e->dq.release(); e->dscale.release(); e->dscoul.release(); e->dtype.release(); e->dmolid.release();
   e->d_pack.release(); e->d_kpack.release(); e->d_kslot.release(); e->d_ktemp.release();
@@ -1514,7 +1518,8 @@ static int wc_plan(gb_engine* e, long long grid_basis, long long nmax, WcPlan& W
   const bool stage_ff = e->ntypes <= 24;
   W.fast = (stage_ff && !e->P.use1264 && !std::getenv("GB_WC_GENERAL")) ? (e->P.no_charges ? 2 : (e->P.erfc_table_ok ? 1 : 0)) : 0;
   if(W.fast == 1 && e->P.cut_vdw2 == e->P.cut_coul2 && !std::getenv("GB_WC_NO_SAMECUT")) W.fast = 3;
-  if(mode == 1 && (e->wc_ctas_cap < 4 || W.fast == 1 || W.fast == 3)) thrE = 256;
+  if((W.fast == 1 || W.fast == 3) && e->P.erfc10_ok && !std::getenv("GB_WC_NO_SHORT_ERFC")) W.fast = (W.fast == 1) ? 4 : 5;      // 4 / 5: the short erfc table
+  if(mode == 1 && (e->wc_ctas_cap < 4 || W.fast == 1 || W.fast >= 3)) thrE = 256;
   if(const char* env = std::getenv("GB_WC_CTAS")) ctas = std::max(1, std::min(mode ? 6 : 1, std::atoi(env)));
   ctas = std::max(1, std::min(ctas, e->wc_ctas_cap));
   e->wc_last_ctas = ctas;
@@ -1561,6 +1566,8 @@ static int wc_sort_and_energy(gb_engine* e, WcPlan& W, long long nitems_src, int
     else if(fast == 1) GBK_WC_LAUNCH(k_wc_energy_lt, , 1);
     else if(fast == 2) GBK_WC_LAUNCH(k_wc_energy_lt, , 2);
     else if(fast == 3) GBK_WC_LAUNCH(k_wc_energy_lt, , 3);
+    else if(fast == 4) GBK_WC_LAUNCH(k_wc_energy_lt, , 4);
+    else if(fast == 5) GBK_WC_LAUNCH(k_wc_energy_lt, , 5);
     else GBK_WC_LAUNCH(k_wc_energy_lt, , 0);
     te.stop(1);
   }

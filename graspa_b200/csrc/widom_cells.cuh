@@ -170,7 +170,8 @@ __host__ __device__ inline size_t wc_energy_smem(int ntypes, bool stage_ff, int 
 // The pair body of the common case, without the run-time switches of pair_energy (common.cuh): plain 12-6 LJ with unit scaling factors,
 // the LJ table and the erfc table in shared memory (LDS, not generic loads), every in-cutoff argument inside the erfc table.
 // FAST 1: with real-space Coulomb, FAST 2: a system without charges, FAST 3: as 1 with CutOffVDW == CutOffCoul (every pair the caller
-// found inside the cutoff gets both terms: no range tests).  Same expressions as pair_energy's unit path.
+// found inside the cutoff gets both terms: no range tests); FAST 4 / 5: as 1 / 3 with the short erfc table (P.erfc10_ok).
+// Same expressions as pair_energy's unit path.
 __device__ __forceinline__ double lds_f64(uint32_t addr, int byte_off)
 {
   double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr + (uint32_t) byte_off)); return v;
@@ -182,6 +183,9 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
 
 // erfc_table_eval (common.cuh) with the table given by its 32-bit shared-memory address: plain LDS with immediate offsets, no
 // generic-to-shared address arithmetic per pair.  Same polynomial, same order.
+// DEG / NINT: the table of common.cuh (12 / 49, arguments up to 6.06) or the short one (10 / 28, arguments up to 3.4375: as accurate
+// there -- 2.3e-16 relative -- with two coefficient gathers and two multiply-adds fewer per pair; the gathers are what binds the kernel).
+template <int DEG, int NINT>
 __device__ __forceinline__ double erfc_table_eval_s(uint32_t tab, double x)
 {
   const double M = 6755399441055744.0;
@@ -191,9 +195,9 @@ __device__ __forceinline__ double erfc_table_eval_s(uint32_t tab, double x)
   kd = __dsub_rn(kd, M);
   const double t = y - kd;
   const uint32_t a = tab + 8u * (uint32_t) k;
-  double acc = lds_f64(a, 8 * GBK_ERFC_NINT * GBK_ERFC_DEG);
+  double acc = lds_f64(a, 8 * NINT * DEG);
 #pragma unroll
-  for(int j = GBK_ERFC_DEG - 1; j >= 0; j--) acc = fma(acc, t, lds_f64(a, 8 * GBK_ERFC_NINT * j));
+  for(int j = DEG - 1; j >= 0; j--) acc = fma(acc, t, lds_f64(a, 8 * NINT * j));
   return acc;
 }
 
@@ -205,7 +209,8 @@ __device__ __forceinline__ void pair_energy_fast(const DevParams& P, uint32_t et
   asm volatile("" : "+d"(rinv));                       // ONE reciprocal square root for both terms (the compiler otherwise sinks a copy into each branch)
   const double rinv2 = rinv * rinv;
   e_vdw = 0.0; e_real = 0.0; flag = 0;
-  if(FAST == 3 || r2 < P.cut_vdw2)
+  constexpr bool SAMECUT = (FAST == 3 || FAST == 5), SHORT_TABLE = (FAST == 4 || FAST == 5);
+  if(SAMECUT || r2 < P.cut_vdw2)
   {
     const double2 f01 = lds_f64x2(ff_s + 32u * (uint32_t) row);            // {4 eps, sigma^2}
     const double fz = lds_f64(ff_s + 32u * (uint32_t) row, 16);            // shift
@@ -215,10 +220,11 @@ __device__ __forceinline__ void pair_energy_fast(const DevParams& P, uint32_t et
     if(r2 < 0.01) flag = 1;
     e_vdw = e;
   }
-  if(FAST == 3 || (FAST == 1 && r2 < P.cut_coul2))
+  if(SAMECUT || ((FAST == 1 || FAST == 4) && r2 < P.cut_coul2))
   {
     const double r = r2 * rinv;
-    const double ec = erfc_table_eval_s(etab_s, P.alpha * r);
+    const double ec = SHORT_TABLE ? erfc_table_eval_s<GBK_ERFC10_DEG, GBK_ERFC10_NINT>(etab_s, P.alpha * r)
+                                  : erfc_table_eval_s<GBK_ERFC_DEG, GBK_ERFC_NINT>(etab_s, P.alpha * r);
     e_real = P.prefactor * qq * ec * rinv;
   }
 }
@@ -254,7 +260,8 @@ __device__ __forceinline__ void wc_energy_body(const DevParams& P, const WcGrid&
 
   const int lane = (int) lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  stage_erfc_table(P, etab);
+  if(FAST == 4 || FAST == 5) { for(int i = threadIdx.x; i < (GBK_ERFC10_DEG + 1) * GBK_ERFC10_NINT; i += blockDim.x) etab[i] = __ldg(&P.erfc_tab10[i]); }
+  else stage_erfc_table(P, etab);
   if(A.stage_ff) for(int i = threadIdx.x; i < P.ntypes * P.ntypes; i += blockDim.x) fftab[i] = P.ffA[i];
   for(int a = threadIdx.x; a < A.ms && a < 64; a += blockDim.x) { Tq[a] = A.tq[a] * A.tscoul[a]; Ttype[a] = A.ttype[a]; }
   const double4* ffp = (FAST > 0 || A.stage_ff) ? fftab : P.ffA;      // FAST kernels are launched only with the staged table
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(768, 1)
 k_wc_energy(DevParams P, WcGrid G, WcEnergy A) { wc_energy_body<CELL, HAS_GG, 0, 0>(P, G, A); }
 
 template <int CELL, bool HAS_GG, int FAST>
-__global__ void __launch_bounds__(256, (FAST == 1 || FAST == 3) ? 4 : 3)      // the bodies without switches fit 64 registers: 32 warps per SM
+__global__ void __launch_bounds__(256, (FAST == 1 || FAST >= 3) ? 4 : 3)      // the bodies without switches fit 64 registers: 32 warps per SM
 k_wc_energy_lt(DevParams P, WcGrid G, WcEnergy A) { wc_energy_body<CELL, HAS_GG, 1, FAST>(P, G, A); }
 
 // ---------------------------------------------------------------------------------------------- caller-supplied trial atoms
