@@ -43,7 +43,7 @@ struct DevParams
   const double*  __restrict__ ffB;    // 12-6-4: C10
   const double*  __restrict__ erfc_tab;   // device copy of h_erfc_table
   const double*  __restrict__ erfc_tab10; // device copy of h_erfc_table10 (degree 10 on [0, GBK_ERFC10_XMAX): the short table of k_wc_energy_lt)
-  int erfc10_ok;                      // alpha*sqrt(cut_coul2) < GBK_ERFC10_XMAX (RASPA's default Ewald precision 1e-6 gives alpha * r_cut = 3.42)
+  int erfc10_ok;                      // alpha*sqrt(cut_coul2) < GBK_ERFC10_XMAX (EwaldPrecision 1e-6 gives alpha * r_cut = 3.1-3.2, read_data.cpp:693-697)
 };
 
 // system atoms, SoA over slots (fractional coordinates are derived from the Cartesian ones)
