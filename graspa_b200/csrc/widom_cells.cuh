@@ -365,20 +365,22 @@ __device__ __forceinline__ void wc_energy_body(const DevParams& P, const WcGrid&
           const double ax = X.x - rec.x, ay = Y.x - rec.y, az = Z.x - rec.z;
           const double bx = X.y - rec.x, by = Y.y - rec.y, bz = Z.y - rec.z;
           const double ra = ax * ax + ay * ay + az * az, rb = bx * bx + by * by + bz * bz;
+          // charge and type of both candidates in one broadcast load each (the loop takes two candidates per step): 1 % on the kernel
+          const double2 Qp = *reinterpret_cast<const double2*>(Fq + j); const int2 Tp = *reinterpret_cast<const int2*>(Ftk + j);
           if(ra < cut_max)
           {
-            const int tk = Ftk[j];
+            const int tk = Tp.x; const double qa = Qp.x;
             double ev, er; int f;
-            wc_pair<FAST>(P, etab, ffp, etab_s, ff_s, ra, (tk & 0xffff) * P.ntypes + ttype, Fq[j] * tq, ev, er, f);
+            wc_pair<FAST>(P, etab, ffp, etab_s, ff_s, ra, (tk & 0xffff) * P.ntypes + ttype, qa * tq, ev, er, f);
             if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
             else { ev0 += ev; er0 += er; }
             fl |= f;
           }
           if(rb < cut_max)
           {
-            const int tk = Ftk[j + 1];
+            const int tk = Tp.y; const double qb = Qp.y;
             double ev, er; int f;
-            wc_pair<FAST>(P, etab, ffp, etab_s, ff_s, rb, (tk & 0xffff) * P.ntypes + ttype, Fq[j + 1] * tq, ev, er, f);
+            wc_pair<FAST>(P, etab, ffp, etab_s, ff_s, rb, (tk & 0xffff) * P.ntypes + ttype, qb * tq, ev, er, f);
             if(HAS_GG) { const bool gg = (tk >> 16) != 0; ev0 += gg ? 0.0 : ev; er0 += gg ? 0.0 : er; ev1 += gg ? ev : 0.0; er1 += gg ? er : 0.0; }
             else { ev0 += ev; er0 += er; }
             fl |= f;
