@@ -202,6 +202,29 @@ inline double2 b200_ewald_delta_identity_swap(size_t oldc, size_t newc, size_t u
 inline void b200_accept_identity_swap(size_t oldc, size_t oldmol, size_t newc)
 { GB_CHECK(gb_accept_identity_swap(b200().e, (int32_t) oldc, (int64_t) oldmol, (int32_t) newc)); }
 
+// VolumeMove (mc_box.h:196-320).  ScalePositions<<<>>> has just scaled the reference's Sim.Box (cell, inverse cell, volume, kmax and reciprocal
+// cutoff, :66-94); that box goes to the engine, which moves every adsorbate molecule with its first atom, rebuilds its wave-vector table and
+// evaluates Total_VDW_Coulomb_Energy + Ewald_TotalEnergy of the scaled system in one call (:236-252).  The old state stays on the device
+// until b200_volume_finish tells the decision (CopyScaledPositions + the swap of the structure factors / Revert_Boxsize, :292-306).
+inline MoveEnergy b200_volume_trial(Simulations& Sim, double Scale, bool& overlap)
+{
+  cudaDeviceSynchronize();
+  gb_box b{};
+  cudaMemcpy(b.cell, Sim.Box.Cell, 9 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaMemcpy(b.inverse_cell, Sim.Box.InverseCell, 9 * sizeof(double), cudaMemcpyDeviceToHost);
+  b.cubic = Sim.Box.Cubic; b.volume = Sim.Box.Volume; b.alpha = Sim.Box.Alpha; b.prefactor = Sim.Box.Prefactor;
+  b.kmax[0] = Sim.Box.kmax.x; b.kmax[1] = Sim.Box.kmax.y; b.kmax[2] = Sim.Box.kmax.z; b.reciprocal_cutoff = Sim.Box.ReciprocalCutOff;
+  b.use_lammps_ewald = Sim.Box.UseLAMMPSEwald;
+  gb_move_energy m; int32_t ov = 0;
+  GB_CHECK(gb_volume_move_trial(b200().e, &b, Scale, &m, &ov));
+  overlap = ov != 0;
+  MoveEnergy E;
+  E.HHVDW = m.HHVDW; E.HGVDW = m.HGVDW; E.GGVDW = m.GGVDW; E.HHReal = m.HHReal; E.HGReal = m.HGReal; E.GGReal = m.GGReal;
+  E.HHEwaldE = m.HHEwaldE; E.HGEwaldE = m.HGEwaldE; E.GGEwaldE = m.GGEwaldE;
+  return E;
+}
+inline void b200_volume_finish(bool accept) { if(b200().e) GB_CHECK(gb_volume_move_finish(b200().e, accept ? 1 : 0)); }
+
 // state commits (mc_utilities.h:294-417, move_struct.h:271,371): each includes the swap of the structure-factor vectors
 inline void b200_accept_translation(size_t comp) { GB_CHECK(gb_accept_translation(b200().e, (int32_t) comp)); }
 inline void b200_accept_insertion(size_t comp) { GB_CHECK(gb_accept_insertion(b200().e, (int32_t) comp)); }

@@ -23,6 +23,8 @@ What is redirected (file:line of the reference):
   mc_swap_moves.h:266,298,355,393-412  IdentitySwapMove: copy_firstbead_to_new / StoreNewLocation_Reinsertion<<<>>> -> (engine) / gb_reinsertion_store;
                                 GPU_EwaldDifference_IdentitySwap -> gb_ewald_delta_identity_swap; Update_deletion_data + Update_IdentitySwap_Insertion_data /
                                 Update_Reinsertion_data<<<>>> -> gb_accept_identity_swap
+  mc_box.h:236-252, 292, 306    VolumeMove: Total_VDW_Coulomb_Energy + overlap flag + Ewald_TotalEnergy of the scaled system -> gb_volume_move_trial;
+                                CopyScaledPositions / Revert_Boxsize<<<>>> -> + gb_volume_move_finish(1 / 0)
   mc_cbcfc.h:39-104             Prepare_LambdaChange / Calculate_Single_Body_Energy_VDWReal_LambdaChange<<<>>> + host sum -> gb_lambda_change_delta;
                                 GPU_EwaldDifference_LambdaChange -> gb_ewald_delta_lambda_change
   mc_cbcfc.h:312,359,427,487    update_CBCF_scale / Revert_CBCF_Insertion<<<>>> -> gb_cbcf_set_scale (provisional) / gb_accept_lambda_change (accepted)
@@ -30,7 +32,7 @@ What is redirected (file:line of the reference):
   mc_cbcfc.h:343                Update_insertion_data_Parallel<<<>>> of an accepted CBCF insertion -> gb_accept_insertion
 Scope: the moves of the CO2-MFI deck (translation, rotation, CBMC insertion / deletion, reinsertion), the identity swap of the
 XeKr-Mixture deck, the Widom move of the Henrys_coefficient deck (it is Insertion_Body), the CO2_NaX_Zeolite deck (moves of a separated
-framework component, block pockets) and, with CBCFProbability added to
+framework component, block pockets), the NPT volume move of the NPTMC deck and, with CBCFProbability added to
 that deck, the CB/CFC move (lambda change; the first steps and the reversal of a fractional insertion / deletion -- the reference's
 CBCFMove never accepts those two: it tests a local SuccessConstruction that nothing sets, mc_cbcfc.h:307-318, :372-393)."""
 import sys
@@ -138,6 +140,19 @@ def main(scr):
         # accepted lambda change (:487) and accepted CBCF deletion (:427): scaling factors + swap of the structure-factor vectors
         (f"update_CBCF_scale<<<1,{MS}>>>(Sims.d_a, start_position, SelectedComponent, newScale);",
          f"b200_accept_lambda_change(SelectedComponent, start_position / {MS}, newScale);", 2)])
+    # VolumeMove (mc_box.h:196-320): ScalePositions<<<>>> still scales the reference's own Sim.Box (cell, inverse cell, kmax, reciprocal cutoff);
+    # the engine takes that box, scales its molecules and evaluates both totals in one call; acceptance / rejection are passed on
+    patch(f"{scr}/mc_box.h", [
+        ("  NewE = Total_VDW_Coulomb_Energy(Sim, SystemComponents, FF, UseOffset);",
+         "  bool b200_overlap = false;\n  if(b200().e) NewE = b200_volume_trial(Sim, Scale, b200_overlap); else NewE = Total_VDW_Coulomb_Energy(Sim, SystemComponents, FF, UseOffset);"),
+        ("  cudaMemcpy(SystemComponents.flag, Sim.device_flag, sizeof(bool), cudaMemcpyDeviceToHost);",
+         "  cudaMemcpy(SystemComponents.flag, Sim.device_flag, sizeof(bool), cudaMemcpyDeviceToHost);\n  if(b200().e) SystemComponents.flag[0] = b200_overlap;"),
+        ("    NewE += Ewald_TotalEnergy(Sim, SystemComponents, UseOffSet);",
+         "    if(!b200().e) NewE += Ewald_TotalEnergy(Sim, SystemComponents, UseOffSet);     // the engine's call returned the Fourier totals as well"),
+        ("    CopyScaledPositions<<<Nblock, Nthread>>>(Sim.d_a, SystemComponents.NComponents.x, ScaleFirstComponentFramework, totMol);",
+         "    CopyScaledPositions<<<Nblock, Nthread>>>(Sim.d_a, SystemComponents.NComponents.x, ScaleFirstComponentFramework, totMol);\n    b200_volume_finish(true);"),
+        ("    Revert_Boxsize<<<1,1>>>(Sim.Box, Scale, FF.noCharges, OldV);",
+         "    Revert_Boxsize<<<1,1>>>(Sim.Box, Scale, FF.noCharges, OldV);\n    b200_volume_finish(false);")])
     patch(f"{scr}/main.cpp", [("    check_energy_wrapper(Vars, i);\n    //Report Random Number Summary", "    b200_sync_back(Vars, i);\n    check_energy_wrapper(Vars, i);\n    //Report Random Number Summary"),
                               # the CREATE_MOLECULE stage check reads Sims.d_a as well (molecules created through the engine)
                               ("    Check_Simulation_Energy(Vars.Box[a], Vars.SystemComponents[a].HostSystem, Vars.FF, Vars.device_FF, Vars.SystemComponents[a], CREATEMOL, a, Vars.Sims[a], true);",

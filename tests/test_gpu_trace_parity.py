@@ -158,12 +158,13 @@ def _stock_and_overlay(d, tmp_path):
     return outs, a, b, differ, accepted, worst
 
 
-@pytest.mark.parametrize("deck,min_moves,min_accepted,min_launches", [
-    ("CO2-MFI", 200000, 50000, 400000),          # translation / rotation / CBMC insertion / deletion / reinsertion, Ewald
-    ("XeKr-Mixture", 9999, 2000, 20000),         # + IdentitySwapMove (mc_swap_moves.h:199-431), two species, tail corrections
-    ("CO2_NaX_Zeolite", 9999, 500, 30000),       # + moves of a separated framework component (Na+), block pockets, cubic cell
+@pytest.mark.parametrize("deck,n_init,n_prod,min_moves,min_accepted,min_launches", [
+    ("CO2-MFI", 10000, 0, 200000, 50000, 400000),          # translation / rotation / CBMC insertion / deletion / reinsertion, Ewald
+    ("XeKr-Mixture", 10000, 0, 9999, 2000, 20000),         # + IdentitySwapMove (mc_swap_moves.h:199-431), two species, tail corrections
+    ("CO2_NaX_Zeolite", 5000, 5000, 9999, 500, 30000),     # + moves of a separated framework component (Na+), block pockets, cubic cell
+    ("NPTMC", 300, 0, 30000, 10000, 100000),               # + VolumeMove (mc_box.h:196-320): 100 CO2 created in an empty box, ~900 volume moves
 ])
-def test_reference_drivers_bound_to_the_c_abi_reproduce_the_stock_reference(deck, min_moves, min_accepted, min_launches, tmp_path):
+def test_reference_drivers_bound_to_the_c_abi_reproduce_the_stock_reference(deck, n_init, n_prod, min_moves, min_accepted, min_launches, tmp_path):
     """The drop-in, demonstrated: the reference's OWN program with its hot-path call sites bound to libgraspa_b200.so
     (oracle/overlay/: the adapter header a maintainer would add + the call-site patch, applied to a scratch copy by
     oracle/build_ref.sh overlay; RunMoves, Insertion_Body, Deletion_Body, ReinsertionMove, SingleBodyMove, the acceptance tests and
@@ -173,10 +174,14 @@ def test_reference_drivers_bound_to_the_c_abi_reproduce_the_stock_reference(deck
     for need in (REF_TRACE, REF_OVERLAY):
         if not os.path.exists(need):
             pytest.skip(f"{need} not built (oracle/build_ref.sh trace / overlay)")
-    d = _deck_copy(deck, tmp_path, 10000, 0) if deck != "CO2_NaX_Zeolite" else _deck_copy(deck, tmp_path, 5000, 5000)
+    d = _deck_copy(deck, tmp_path, n_init, n_prod)
     outs, a, b, differ, accepted, worst = _stock_and_overlay(d, tmp_path)
     assert len(a) == len(b) and len(a) > min_moves, (len(a), len(b))
     assert differ == 0 and accepted > min_accepted and worst < 1e-8, (differ, accepted, worst)
+    if deck == "NPTMC":
+        vol = lambda text: [ln for ln in text.splitlines() if ln.startswith("VOLUME MOVE A") or ln.startswith("CYCLE:")]
+        assert len(vol(outs["stock"].stdout)) >= 2 and vol(outs["stock"].stdout) == vol(outs["overlay"].stdout)
+        assert int(vol(outs["stock"].stdout)[-1].split(":")[1]) > 100       # accepted volume moves
     # the engine really served the run, and the reference's own end-of-run check is content with the state it left
     assert "engine kernel launches served the reference's drivers" in outs["overlay"].stderr
     launches = int(outs["overlay"].stderr.split("graspa_b200 overlay:")[1].split()[0])
