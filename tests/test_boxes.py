@@ -45,3 +45,38 @@ echo "{\\"moves\\": 10, \\"cycles\\": 10, \\"seconds\\": 0.1, \\"moves_per_s\\":
 def test_missing_driver_fails_loudly(tmp_path):
     with pytest.raises(FileNotFoundError):
         run_boxes("deck", [{}], driver=str(tmp_path / "nope"))
+
+
+def test_a_rank_runs_its_box_on_its_own_device(tmp_path):
+    """bench.py's multibox_xekr: every rank of a torchrun launch calls run_boxes with ONE point and devices=[LOCAL_RANK]"""
+    fake = tmp_path / "fake_driver.sh"
+    fake.write_text("""#!/bin/bash
+echo "{\\"loading\\": [{\\"component\\": \\"X\\", \\"molecules\\": $CUDA_VISIBLE_DEVICES, \\"production_average\\": 0}]}"
+echo "{\\"moves\\": 10, \\"cycles\\": 10, \\"seconds\\": 0.1, \\"moves_per_s\\": 100, \\"cycles_per_s\\": 100}"
+""")
+    os.chmod(fake, os.stat(fake).st_mode | stat.S_IEXEC)
+    env_before = os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+    try:
+        for local in (0, 3, 7):
+            res, _ = run_boxes("deck", [{"pressure": 1e5}], gpus=1, init=1, prod=0, driver=str(fake), devices=[local])
+            assert res[0]["loading"][0]["molecules"] == local
+        os.environ["CUDA_VISIBLE_DEVICES"] = "4,5,6"          # a restricted launch: local rank 1 owns physical device 5
+        res, _ = run_boxes("deck", [{"pressure": 1e5}], gpus=1, init=1, prod=0, driver=str(fake), devices=[1])
+        assert res[0]["loading"][0]["molecules"] == 5
+    finally:
+        os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+        if env_before is not None:
+            os.environ["CUDA_VISIBLE_DEVICES"] = env_before
+
+
+def test_multibox_summary_of_the_bench_line():
+    """aggregate = all boxes' cycles / the slowest box's Monte Carlo loop time; a failed box withholds the aggregate instead of flattering it"""
+    import bench
+    recs = [{"rank": r, "pressure_pa": p, "returncode": 0, "cycles": 1000, "mc_seconds": t, "cycles_per_s": 1000 / t, "process_seconds": t + 2.0, "energy_drift": d}
+            for r, (p, t, d) in enumerate([(1e4, 0.010, 1e-11), (3e4, 0.012, -3e-10), (1e5, 0.008, None)])]
+    s = bench.multibox_summary(recs)
+    assert s["boxes"] == 3 and abs(s["value"] - 3000 / 0.012) < 1e-6
+    assert abs(s["value_incl_process_start"] - 3000 / 2.012) < 1e-6
+    assert abs(s["speedup_vs_one_after_the_other"] - 0.030 / 0.012) < 1e-9 and s["max_abs_energy_drift"] == 3e-10
+    bad = bench.multibox_summary(recs[:2] + [{"rank": 2, "error": "driver missing"}])
+    assert "value" not in bad and bad["boxes"] == 3
