@@ -193,3 +193,77 @@ def test_scale_positions_properties(oracle):
     assert np.max(np.abs(new[:, 0] - 1.05 * old[:, 0])) < 1e-12
     d_old = np.linalg.norm(old[:, 1:] - old[:, :1], axis=2); d_new = np.linalg.norm(new[:, 1:] - new[:, :1], axis=2)
     assert np.max(np.abs(d_old - d_new)) < 1e-12 and d_old.max() < 3.0
+
+
+def _with(s, comp, scale_coul=None, extra_pos=None, extra_scoul=1.0):
+    """copy of System s: new scale_coul per atom and / or one more molecule of `comp` (positions extra_pos, the template's charges and types)"""
+    from graspa_b200.types import System
+    ms = int(s.molsize[comp]); o = int(s.offsets[comp]); nl = int(s.natoms[comp])
+    scc = (s.scale_coul if scale_coul is None else scale_coul).copy()
+    if extra_pos is None:
+        return System(s.nhost, s.natoms.copy(), s.molsize.copy(), s.pos.copy(), s.charge.copy(), s.type.copy(), s.molid.copy(), s.scale.copy(), scc, alloc=s.alloc.copy())
+    natoms = s.natoms.copy(); natoms[comp] += ms
+    alloc = np.maximum(s.alloc, natoms)
+    chunks = {k: [] for k in ("pos", "charge", "type", "molid", "scale", "scoul")}
+    for c in range(s.ncomp):
+        a = int(s.offsets[c]); n = int(s.alloc[c])
+        cols = dict(pos=s.pos[a:a + n], charge=s.charge[a:a + n], type=s.type[a:a + n], molid=s.molid[a:a + n], scale=s.scale[a:a + n], scoul=scc[a:a + n])
+        if c == comp:
+            live = {k: v[:nl] for k, v in cols.items()}
+            add = dict(pos=np.asarray(extra_pos).reshape(ms, 3), charge=s.charge[o:o + ms], type=s.type[o:o + ms], molid=np.full(ms, nl // ms),
+                       scale=np.ones(ms), scoul=np.full(ms, extra_scoul))
+            pad = int(alloc[c]) - nl - ms
+            cols = {k: np.concatenate([live[k], add[k], np.zeros((pad,) + live[k].shape[1:], dtype=live[k].dtype)]) for k in cols}
+        for k in chunks:
+            chunks[k].append(cols[k])
+    cat = {k: np.concatenate(v) for k, v in chunks.items()}
+    return System(s.nhost, natoms, s.molsize.copy(), cat["pos"], cat["charge"], cat["type"], cat["molid"], cat["scale"], cat["scoul"], alloc=alloc)
+
+
+def test_cbcf_two_step_fourier_deltas_on_the_temp_vector_match_reference_totals(oracle):
+    """The two-step CB/CFC moves keep their intermediate Fourier state in tempEik (UseTempVector, Ewald_Energy_Functions.h:362-377, :510-517,
+    :713-716): the second step's delta is taken against the FIRST step's new structure factors, not against the stored ones.  Restated with
+    orc_ewald_delta and pinned to the REFERENCE's Ewald_Total of the three states (config B, CO2 in MFI):
+      insertion: molecule m at lambda_c = 0.4^5 -> 1, then a new molecule at lambda_c = 0.7^5;
+      deletion : that new molecule removed, then molecule k from 1 -> 0.3^5 on top of it."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    box, ff, s, z = load_config("B")
+    comp = int(z["comp"]); ms = int(s.molsize[comp]); o = int(s.offsets[comp]); q = s.charge[o:o + ms]
+    excl = float(z["excl"][0]) + float(z["excl"][1])
+    m, k = 2, 4
+    pm = s.pos[o + m * ms:o + (m + 1) * ms]; pk = s.pos[o + k * ms:o + (k + 1) * ms]
+    sc0, sc2, sc3 = 0.4 ** 5, 0.7 ** 5, 0.3 ** 5
+    scc = s.scale_coul.copy(); scc[o + m * ms:o + (m + 1) * ms] = sc0
+    s1 = _with(s, comp, scale_coul=scc)                                    # before: molecule m is the fractional one
+    E1, sa1, sf1 = oracle.ref_ewald_total(box, s1)
+    # the reference side is a difference of totals of magnitude 1.5e7 (GG includes HH, ewald_preparation.h:174): 1e-12 of that is a few times
+    # its double-precision resolution and 200 times smaller than what using the wrong vector would change (checked below)
+    tol = 1e-12 * max(1.0, float(np.abs(E1).max()))
+    same = lambda E: E[0]                                                  # guest-guest Fourier total incl. exclusions (ewald_E[0])
+    cross = lambda E: E[2] if len(E) > 2 else 0.0
+    # ---- insertion, step 1 (lambda change from the stored vectors) and step 2 (growth, continuing from the temp vector of step 1)
+    d1, t1, _ = oracle.ewald_delta(box, np.concatenate([pm, pm]), np.concatenate([q, q]), np.concatenate([np.full(ms, sc0), np.ones(ms)]), ms, ms, sa1, sf1)
+    d2, t2, _ = oracle.ewald_delta(box, z["ins_pos"], q, np.full(ms, sc2), 0, ms, t1, sf1)
+    s2 = _with(_with(s, comp), comp, extra_pos=z["ins_pos"], extra_scoul=sc2)       # after: m whole again, the new molecule fractional
+    E2, sa2, sf2 = oracle.ref_ewald_total(box, s2)
+    got_same = (d1[0] - excl * (1.0 - sc0 ** 2)) + (d2[0] - excl * sc2 ** 2)
+    assert abs(got_same - (same(E2) - same(E1))) <= tol, (got_same, same(E2) - same(E1))
+    assert abs((d1[1] + d2[1]) - (cross(E2) - cross(E1))) <= tol
+    act = np.abs(t2.reshape(-1, 2)).sum(axis=1) > 0
+    assert np.max(np.abs(t2.reshape(-1, 2)[act] - sa2.reshape(-1, 2)[act])) < 1e-9          # what the acceptance swaps in
+    # the second step taken against the STORED vectors instead (what Insertion_Body's INSERTION call does in the reference snapshot) differs
+    d2_wrong, _, _ = oracle.ewald_delta(box, z["ins_pos"], q, np.full(ms, sc2), 0, ms, sa1, sf1)
+    print("second step against the stored vectors instead of the temp vector: off by", d2_wrong[0] - d2[0])
+    assert abs(d2_wrong[0] - d2[0]) > 100 * tol
+    # ---- deletion of the fractional molecule (step 1 into temp), then molecule k from 1 to sc3 on top of it (UseTempVector)
+    d3, t3, _ = oracle.ewald_delta(box, z["ins_pos"], q, np.full(ms, sc2), ms, 0, sa2, sf2)
+    d4, t4, _ = oracle.ewald_delta(box, np.concatenate([pk, pk]), np.concatenate([q, q]), np.concatenate([np.ones(ms), np.full(ms, sc3)]), ms, ms, t3, sf2)
+    scc3 = s.scale_coul.copy(); scc3[o + k * ms:o + (k + 1) * ms] = sc3
+    s3 = _with(s, comp, scale_coul=scc3)
+    E3, sa3, _ = oracle.ref_ewald_total(box, s3)
+    got_same = (d3[0] - excl * (0.0 - sc2 ** 2)) + (d4[0] - excl * (sc3 ** 2 - 1.0))
+    assert abs(got_same - (same(E3) - same(E2))) <= tol, (got_same, same(E3) - same(E2))
+    assert abs((d3[1] + d4[1]) - (cross(E3) - cross(E2))) <= tol
+    act = np.abs(t4.reshape(-1, 2)).sum(axis=1) > 0
+    assert np.max(np.abs(t4.reshape(-1, 2)[act] - sa3.reshape(-1, 2)[act])) < 1e-9
