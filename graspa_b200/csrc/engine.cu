@@ -93,6 +93,9 @@ struct gb_engine
   // Ewald
   long long nvec = 0;
   std::vector<int> h_kpack, h_kslot; std::vector<double> h_ktemp;
+  // what the INDEX part of the k table (active list, slots, row-ordered walk) was built for: without the LAMMPS-style set-up the active set is
+  // decided by integer kx^2 + ky^2 + kz^2 against the reciprocal cutoff, i.e. by kmax alone -- a volume move that keeps kmax reuses it
+  bool kindex_valid = false; int kindex_kmax[3] = {-1, -1, -1}; double kindex_rcut = 0.0;
   DevBuf<int> d_kpack, d_kslot; DevBuf<double> d_ktemp;
   int nact = 0, nact_pad = 0;
   DevBuf<double> d_sf[3];                 // ads, fw, temp (full arrays)
@@ -700,12 +703,15 @@ int apply_box(gb_engine* e, const gb_box* box)
   // active k table: Ewald_Energy_Functions.h:299-334, 358-360
   const int kxm = box->kmax[0], kym = box->kmax[1], kzm = box->kmax[2];
   e->nvec = (long long)(kxm + 1) * (2 * kym + 1) * (2 * kzm + 1);
-  e->h_kpack.clear(); e->h_kslot.clear(); e->h_ktemp.clear();
+  const bool reuse_index = e->kindex_valid && !box->use_lammps_ewald && box->alpha > 0.0 && e->kindex_kmax[0] == kxm && e->kindex_kmax[1] == kym &&
+                           e->kindex_kmax[2] == kzm && e->kindex_rcut == box->reciprocal_cutoff && !std::getenv("GB_NO_KINDEX_CACHE");
+  e->h_ktemp.clear();
+  if(!reuse_index) { e->h_kpack.clear(); e->h_kslot.clear(); e->kindex_valid = false; }      // valid again only once every table of the new index is queued
   const double* I = box->inverse_cell;
   const double ax[3] = {I[0], I[3], I[6]}, ay[3] = {I[1], I[4], I[7]}, az[3] = {I[2], I[5], I[8]};
   const double alpha_sq = box->alpha * box->alpha;
   const double prefactor = box->prefactor * (2.0 * GBK_PI / box->volume);
-  if(box->alpha > 0.0)
+  if(box->alpha > 0.0 && !reuse_index)
     for(long long kxyz = 0; kxyz < e->nvec; kxyz++)
     {
       const int kz = (int)(kxyz % (2 * kzm + 1)) - kzm;
@@ -722,15 +728,23 @@ int apply_box(gb_engine* e, const gb_box* box)
         ksqr = kvx * kvx + kvy * kvy + kvz * kvz;
       }
       if(!((ksqr > 1e-10) && (ksqr < box->reciprocal_cutoff))) continue;
-      double kv[3];
-      for(int d = 0; d < 3; d++) kv[d] = ax[d] * 2.0 * GBK_PI * (double) kx + ay[d] * 2.0 * GBK_PI * (double) ky + az[d] * 2.0 * GBK_PI * (double) kz;
-      const double rksq = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2];
-      const double factor = (kx == 0) ? (1.0 * prefactor) : (2.0 * prefactor);
-      e->h_ktemp.push_back(factor * std::exp((-0.25 / alpha_sq) * rksq) / rksq);
       e->h_kpack.push_back((kx << 16) | ((ky + 128) << 8) | (kz + 128));
       e->h_kslot.push_back((int) kxyz);
     }
+  if(box->alpha <= 0.0) { e->h_kpack.clear(); e->h_kslot.clear(); }
   e->nact = (int) e->h_kpack.size(); e->nact_pad = (e->nact + 31) / 32 * 32;
+  // the weights of the active wave vectors: the only part of the table that follows the cell (one code path, rebuilt and reused index alike)
+  e->h_ktemp.reserve((size_t) e->nact);
+  for(int k = 0; k < e->nact; k++)
+  {
+    const int kx = e->h_kpack[k] >> 16, ky = ((e->h_kpack[k] >> 8) & 255) - 128, kz = (e->h_kpack[k] & 255) - 128;
+    double kv[3];
+    for(int d = 0; d < 3; d++) kv[d] = ax[d] * 2.0 * GBK_PI * (double) kx + ay[d] * 2.0 * GBK_PI * (double) ky + az[d] * 2.0 * GBK_PI * (double) kz;
+    const double rksq = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2];
+    const double factor = (kx == 0) ? (1.0 * prefactor) : (2.0 * prefactor);
+    e->h_ktemp.push_back(factor * std::exp((-0.25 / alpha_sq) * rksq) / rksq);
+  }
+  if(!reuse_index)
   {
     // rows (kx, ky) of the active list, longest kz reach first; 32 rows per round, positions [round][j = |kz|][sign][lane]
     std::map<int, std::vector<int>> rows;                  // key = kpack >> 8 (kx, ky), values = active indices
@@ -770,10 +784,15 @@ int apply_box(gb_engine* e, const gb_box* box)
   if(e->nact > 0)
   {
     CUDA_TRY(e->d_kpack.reserve(e->nact)); CUDA_TRY(e->d_kslot.reserve(e->nact)); CUDA_TRY(e->d_ktemp.reserve(e->nact));
-    CUDA_TRY(cudaMemcpyAsync(e->d_kpack.p, e->h_kpack.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(cudaMemcpyAsync(e->d_kslot.p, e->h_kslot.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    if(!reuse_index)
+    {
+      CUDA_TRY(cudaMemcpyAsync(e->d_kpack.p, e->h_kpack.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(e->d_kslot.p, e->h_kslot.data(), e->nact * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    }
     CUDA_TRY(cudaMemcpyAsync(e->d_ktemp.p, e->h_ktemp.data(), e->nact * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   }
+  e->kindex_valid = !box->use_lammps_ewald && box->alpha > 0.0;
+  e->kindex_kmax[0] = kxm; e->kindex_kmax[1] = kym; e->kindex_kmax[2] = kzm; e->kindex_rcut = box->reciprocal_cutoff;
   for(int i = 0; i < 3; i++)
   {
     CUDA_TRY(e->d_sf[i].reserve((size_t) std::max<long long>(2 * e->nvec, 2)));
