@@ -248,7 +248,10 @@ int  gb_single_body_delta_explicit(gb_engine* e, int32_t component, int64_t moli
  *   GPU_EwaldDifference_IdentitySwap :582-632; Update_Vector_Ewald :423-433)
  * ------------------------------------------------------------------------------------------------ */
 /* returns {same-type, 2*cross-type} exactly like the reference's double2, exclusion constants applied.
- * location = the reference's Location argument (selected trial for INSERTION, UpdateLocation for DELETION/REINSERTION). */
+ * location = the reference's Location argument (selected trial for INSERTION, UpdateLocation for DELETION/REINSERTION).
+ * GB_CBCF_INSERTION (the second step of a fractional insertion) reads the same-type structure factors from tempEik, where the lambda
+ * change of the first step left them, and leaves the sum of both steps there (UseTempVector, :362-377, :510-517);
+ * GB_CBCF_DELETION is a DELETION whose exclusion term carries scale[1]^2 (:570-575). */
 int  gb_ewald_delta(gb_engine* e, int32_t component, int32_t move_type, int64_t location, const double scale[2], double out[2]);
 /* old molecule = slots [update_location, +molsize) of old_component; new molecule = tempMolStorage, i.e. the molecule kept by
  * gb_reinsertion_store(new_component) after its IDENTITY_SWAP_NEW growth (mc_swap_moves.h:355) */
