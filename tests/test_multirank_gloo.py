@@ -89,3 +89,48 @@ def test_reference_arm_runs_on_rank_zero_only():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def _box_worker(rank, world, port, outdir, fake_driver):
+    """what bench.py does for its multibox_xekr key: every rank runs ITS isotherm point on ITS device, the records are gathered with
+    all_gather_object and rank 0 summarises them"""
+    import json
+    import torch.distributed as dist
+    import bench
+    from graspa_b200.boxes import run_boxes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res, _ = run_boxes("deck", [{"pressure": bench.MULTIBOX_PRESSURES[rank]}], gpus=1, init=100, prod=0, driver=fake_driver, devices=[rank])
+    r = res[0]; run = r["run"]
+    mine = {"rank": rank, "pressure_pa": r["point"]["pressure"], "returncode": r["returncode"], "cycles": run["cycles"], "mc_seconds": run["seconds"],
+            "cycles_per_s": run["cycles_per_s"], "process_seconds": r["seconds"], "device_seen": r["loading"][0]["molecules"], "energy_drift": r.get("energy_drift")}
+    allrec = [None] * world
+    dist.all_gather_object(allrec, mine)
+    if rank == 0:
+        json.dump(bench.multibox_summary(allrec), open(os.path.join(outdir, "multibox.json"), "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_run_one_box_each_and_rank_zero_gathers_them(tmp_path):
+    import json
+    import stat
+    import torch.multiprocessing as mp
+    fake = tmp_path / "fake_driver.sh"
+    fake.write_text("""#!/bin/bash
+# stand-in for graspa_b200_mc: a box at higher pressure takes longer; reports the ONE device it can see
+p=0; while [ $# -gt 0 ]; do case "$1" in --pressure) p=$2; shift;; esac; shift; done
+secs=$(python3 -c "print(0.001 * (1 + ($p > 20000)))")
+echo "ENERGY DRIFT (FINAL - INITIAL - RUNNING) Total Energy: 2.0e-11"
+echo "{\\"pressure_pa\\": $p, \\"loading\\": [{\\"component\\": \\"Xe\\", \\"molecules\\": $CUDA_VISIBLE_DEVICES, \\"production_average\\": 0}]}"
+echo "{\\"moves\\": 100, \\"cycles\\": 100, \\"seconds\\": $secs, \\"moves_per_s\\": 1, \\"cycles_per_s\\": 1}"
+""")
+    os.chmod(fake, os.stat(fake).st_mode | stat.S_IEXEC)
+    mp.spawn(_box_worker, args=(2, _free_port(), str(tmp_path), str(fake)), nprocs=2, join=True)
+    s = json.load(open(tmp_path / "multibox.json"))
+    assert s["boxes"] == 2 and [r["rank"] for r in s["per_box"]] == [0, 1]
+    assert [r["device_seen"] for r in s["per_box"]] == [0, 1]                      # every rank's box ran on its own device
+    assert [r["pressure_pa"] for r in s["per_box"]] == [1e4, 3e4]
+    assert abs(s["value"] - 200 / 0.002) < 1e-6                                    # all cycles / the slowest box's loop time
+    assert abs(s["speedup_vs_one_after_the_other"] - 1.5) < 1e-9 and s["max_abs_energy_drift"] == 2.0e-11
